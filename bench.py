@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py — LM iterations/s of the B200-native Levenberg-Marquardt inner loop on a synthetic BAL problem.
+
+A "step" is one LM iteration (damping, matrix-free Schur PCG solve, back-substitution, update, cost, accept or
+reject + re-linearisation) of the optimisation trajectory under the reference's BAL protocol
+(examples/bal.cu:284-309: lambda0 1e-4, PCG 10 iterations / tolerance 1.0 / rejection ratio 5.0).
+W warm-up iterations start from the initial state, then exactly K iterations are timed.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                     (CPU arm: the oracle port on the host cores)
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definition of every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from graphite_b200 import synthetic  # noqa: E402
+
+METRIC = "LM iterations/s (synthetic BAL, Schur PCG)"
+UNIT = "LM it/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.rows = []
+        self.device = device
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def partition_points(prob, nranks: int, rank: int):
+    """Contiguous point ranges balanced by observation count."""
+    from graphite_b200.distributed import partition_by_point
+    return partition_by_point(prob, nranks, rank)
+
+
+def algorithmic_bytes(nc, npts, m, nseg, sT, sS):
+    """Bytes one launch of each tile kernel has to move in this layout (DESIGN.md "Kernels")."""
+    V = 9 * nc * sT
+    product = m * (24 * sS + 9) + npts * 6 * sT + V + nseg * 9 * sT
+    # SURVEY section 8(d) K4 implicit, whole PCG iteration, for reference next to it
+    survey_k4 = 27 * m * sS + 4 * m + 9 * npts * sS + 81 * nc * sS + 10 * V
+    return product, survey_k4
+
+
+def run_reference(args):
+    """CPU arm: the oracle port (the reference's Eigen CPU path cannot be built here: Eigen is absent)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.binding import Oracle, default_options
+    prob = synthetic.make_named(args.workload)
+    cores = os.cpu_count() or 1
+    O = Oracle(prob, "f64")
+    opts = default_options(iterations=args.warmup + args.steps, threads=cores)
+    O.lm_begin(opts)
+    ks = []
+    for _ in range(args.warmup):
+        out, go = O.lm_step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out, go = O.lm_step()
+        ks.append(int(out[3]))
+    dt = time.perf_counter() - t0
+    value = args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(prob, "f64-f64", 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} LM iterations after {args.warmup} warm-up iterations of the same workload "
+                                   f"(explicit Schur + PCG, OpenMP); pcg iterations per step {ks}"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "final_chi2": float(out[1]),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(prob, precision, n_gpus):
+    nc, npts, m = prob.shape()
+    return {"workload": f"{prob.name}: {nc} cams / {npts} pts / {m} obs, seed 0, {precision.upper()}, points eliminated, "
+                        f"lambda0 1e-4, PCG 10 it / tol 1.0 / rejection 5.0, diagonal damping, Jacobi scaling",
+            "cams": nc, "points": npts, "observations": m, "precision": precision,
+            "schur": "implicit (matrix-free)", "parallelism": f"points partitioned over {n_gpus} GPU(s), cameras replicated",
+            "l2": "no flush needed: each pass streams the 0.96 GB Jacobian store (FP64) which is larger than the 126 MB L2"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="venice-1778")
+    ap.add_argument("--precision", default="f64-f64")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline-steps", type=int, default=4)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    from graphite_b200 import binding
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    prob = synthetic.make_named(args.workload)
+    nc, npts, m = prob.shape()
+    local = partition_points(prob, world, rank) if world > 1 else prob
+    ctx = binding.Context(local_rank)
+    if world > 1:
+        uid = [binding.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(world, rank, uid[0])
+    tname, sname = args.precision.split("-")
+    T = np.float64 if tname == "f64" else np.float32
+    sT, sS = (8 if tname == "f64" else 4), (8 if sname == "f64" else 4)
+    P = binding.Problem(ctx, local.cam_idx, local.pt_idx, local.n_cams, local.n_pts, args.precision)
+    info = P.info()
+
+    # pinned host copies of the inputs (the e2e arm copies from these every step)
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=T)).pin_memory()
+        return t
+    h_obs, h_cams, h_pts = pinned(local.obs), pinned(local.cams), pinned(local.pts)
+    out_cams, out_pts = torch.empty_like(h_cams).pin_memory(), torch.empty_like(h_pts).pin_memory()
+    P.set_observations_raw(h_obs.data_ptr())
+    P.set_vertices_raw(h_cams.data_ptr(), h_pts.data_ptr())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident arm: W warm-up LM iterations, then K timed --------------------------------------
+    traj_w, res_w = P.lm(iterations=args.warmup)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.kernel_launches()
+    t0 = time.perf_counter()
+    traj, res = P.lm(iterations=args.steps, initial_damping=res_w["final_damping"], initial_nu=res_w["final_nu"],
+                     resume=True, profile_product=True)
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = ctx.kernel_launches() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    seconds = max_over_ranks(res["seconds_total"])  # CUDA events on the context stream, max over ranks
+    steps_done = int(res["iterations"])
+    value = steps_done / seconds
+
+    # ---- roofline of the dominant kernel (matrix-free Schur product), timed live in the run above ----------
+    peak, peak_kind = load_peaks()
+    prod_bytes, survey_k4 = algorithmic_bytes(nc, local.n_pts, info["n_obs"], info["n_camera_segments"], sT, sS)
+    n_prod = max(int(res["product_launches"]), 1)
+    prod_ms = 1e3 * res["product_seconds"] / n_prod
+    achieved = prod_bytes / (prod_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_schur_tiles<MODE 0> (matrix-free Schur product, one launch per PCG iteration)",
+                "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "bytes_per_launch": prod_bytes, "launches_timed": int(res["product_launches"]), "ms_per_launch": prod_ms,
+                "share_of_step": res["product_seconds"] / max(res["seconds_total"], 1e-12),
+                "survey_k4_bytes_per_pcg_iteration": survey_k4}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            with open(prof) as fh:
+                tr = json.load(fh)
+            key = f"{args.workload}:{args.precision}:{world}"
+            if key in tr:
+                roofline["traffic"] = tr[key]
+        except Exception:
+            pass
+
+    # ---- e2e arm: every step copies its inputs from pinned host memory and reads the result back ----------
+    P.set_vertices_raw(h_cams.data_ptr(), h_pts.data_ptr())
+    tw, rw = P.lm(iterations=args.warmup)
+    # state after warm-up becomes the host-side state the steps start from
+    P.get_vertices_raw(out_cams.data_ptr(), out_pts.data_ptr())
+    mu, nu = rw["final_damping"], rw["final_nu"]
+    h2d = h_obs.numel() * h_obs.element_size() + out_cams.numel() * out_cams.element_size() + out_pts.numel() * out_pts.element_size()
+    d2h = out_cams.numel() * out_cams.element_size() + out_pts.numel() * out_pts.element_size() + 8
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = 0
+    for _ in range(args.steps):
+        P.set_observations_raw(h_obs.data_ptr())                       # H2D
+        P.set_vertices_raw(out_cams.data_ptr(), out_pts.data_ptr())    # H2D
+        tj, rj = P.lm(iterations=1, initial_damping=mu, initial_nu=nu)  # linearize + one LM iteration
+        P.get_vertices_raw(out_cams.data_ptr(), out_pts.data_ptr())    # D2H (+ chi2 in rj)
+        mu, nu = rj["final_damping"], rj["final_nu"]
+        e2e_steps += 1
+    barrier()
+    e2e_seconds = max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": e2e_steps / e2e_seconds, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "ms_per_step": 1e3 * e2e_seconds / max(e2e_steps, 1),
+           "note": "per step: pinned-host -> device copy of observations + vertices, gb_lm(1 iteration) through the C ABI, "
+                   "device -> host copy of the vertices and the cost"}
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle port on the host cores, bounded sample -----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.binding import Oracle, default_options
+        cores = os.cpu_count() or 1
+        O = Oracle(prob, "f64" if tname == "f64" else "f32")
+        O.lm_begin(default_options(iterations=args.cpu_baseline_steps + 1, threads=cores))
+        O.lm_step()
+        t0 = time.perf_counter()
+        for _ in range(args.cpu_baseline_steps):
+            O.lm_step()
+        dtc = time.perf_counter() - t0
+        cpu = {"value": args.cpu_baseline_steps / dtc, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"LM iterations 2..{args.cpu_baseline_steps + 1} of the same workload from the same initial state "
+                         f"(oracle/oracle_bal.cpp, explicit Schur + PCG, OpenMP, {dtc:.1f} s)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps_done, "warmup": args.warmup,
+            "ms_per_step": 1e3 * seconds / max(steps_done, 1), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64" if tname == "f64" else "f32", "data": "synthetic",
+            "config": workload_config(prob, args.precision, world),
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "pcg": {"iterations_per_step": [int(v) for v in traj[:, 3]], "total": int(res["pcg_iterations_total"]),
+                    "ms_per_product_launch": prod_ms, "product_gbps": achieved},
+            "stages_ms_per_step": {k[8:]: 1e3 * v / max(steps_done, 1) for k, v in res.items()
+                                   if k.startswith("seconds_") and k != "seconds_total"},
+            "accepted": int(res["accepted"]), "rejected": int(res["rejected"]),
+            "chi2": {"start": float(traj[0, 0]) if len(traj) else None, "end": float(res["final_chi2"])},
+            "wall_seconds_timed_region": wall, "structure": info,
+        }
+        print(json.dumps(line), flush=True)
+    P.close()
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,911 @@
+// api.cu — context, problem state, host-side LM driver and the C ABI (include/graphite_b200.h).
+//
+// Host control flow mirrors optimizer::levenberg_marquardt (include/graphite/optimizer/levenberg_marquardt.hpp:109-242)
+// and PCGSchurSolver (include/graphite/solver/pcg_schur.hpp:49-168); all arithmetic runs in the kernels of
+// kernels.cuh.  There is no CPU fallback: every entry point needs a live CUDA context.
+#include "../../include/graphite_b200.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "structure.hpp"
+
+// ---- NCCL, bound at run time (the library must load on boxes where only torch's bundled NCCL exists) ----
+extern "C" {
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId_gb;
+}
+namespace {
+struct NcclApi {
+  void *handle = nullptr;
+  int (*GetUniqueId)(ncclUniqueId_gb *) = nullptr;
+  int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId_gb, int) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  bool load() {
+    if (handle) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+      handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (handle) break;
+    }
+    if (!handle) return false;
+    GetUniqueId = (int (*)(ncclUniqueId_gb *))dlsym(handle, "ncclGetUniqueId");
+    CommInitRank = (int (*)(ncclComm_t *, int, ncclUniqueId_gb, int))dlsym(handle, "ncclCommInitRank");
+    AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(handle, "ncclAllReduce");
+    CommDestroy = (int (*)(ncclComm_t))dlsym(handle, "ncclCommDestroy");
+    GetErrorString = (const char *(*)(int))dlsym(handle, "ncclGetErrorString");
+    return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
+  }
+};
+NcclApi g_nccl;
+constexpr int NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8, NCCL_SUM = 0;
+} // namespace
+
+struct gb_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  ncclComm_t comm = nullptr;
+  int nranks = 1, rank = 0;
+  int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+  }
+};
+
+#define GB_CUDA(ctx, call)                                                                          \
+  do {                                                                                              \
+    cudaError_t e__ = (call);                                                                       \
+    if (e__ != cudaSuccess)                                                                         \
+      return (ctx)->fail(GB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+#define GB_TRY(expr)            \
+  do {                          \
+    int rc__ = (expr);          \
+    if (rc__ != GB_OK) return rc__; \
+  } while (0)
+#define GB_LAUNCH(ctx) ((ctx)->launches++)
+
+namespace gb {
+
+struct ProblemBase {
+  gb_context *ctx = nullptr;
+  HostStructure hs;
+  virtual ~ProblemBase() {}
+  virtual int init() = 0;
+  virtual int set_observations(const void *) = 0;
+  virtual int set_vertices(const void *, const void *) = 0;
+  virtual int get_vertices(void *, void *) = 0;
+  virtual int linearize(double *) = 0;
+  virtual int compute_cost(double *) = 0;
+  virtual int get_gradient(void *) = 0;
+  virtual int get_scales(void *) = 0;
+  virtual int get_residuals(void *) = 0;
+  virtual int get_jacobians(double *, double *) = 0;
+  virtual int hessian_values(void *) = 0;
+  virtual int set_damping(double, int) = 0;
+  virtual int solve(const gb_pcg_options *, void *, gb_solve_info *) = 0;
+  virtual int get_schur_rhs(void *) = 0;
+  virtual int get_schur_diagonal(void *) = 0;
+  virtual int schur_multiply(const void *, void *) = 0;
+  virtual int try_step(double *, double *) = 0;
+  virtual int revert_step() = 0;
+  virtual int lm(const gb_lm_options *, gb_lm_result *, double *) = 0;
+  virtual int time_stage(int, int, double *) = 0;
+  virtual int64_t device_bytes() const = 0;
+};
+
+template <typename T, typename S> struct Problem : ProblemBase {
+  using T2 = typename V2<T>::type;
+  using S2 = typename V2<S>::type;
+  TileStruct ts{};
+  std::vector<void *> allocs;
+  int64_t bytes = 0;
+  // state
+  T *cams = nullptr, *pts = nullptr, *cams_bak = nullptr, *pts_bak = nullptr;
+  T2 *obs = nullptr, *res = nullptr;
+  S2 *Jc = nullptr, *Jp = nullptr;
+  T *Cg = nullptr, *part18 = nullptr, *part54 = nullptr, *part9 = nullptr, *sums54 = nullptr;
+  T *diagB = nullptr, *gc = nullptr, *scale = nullptr /*[9Nc+3Np]*/, *b = nullptr /*[9Nc+3Np]*/;
+  T *W = nullptr, *h = nullptr;
+  T *Sdiag = nullptr, *Minv = nullptr, *bS = nullptr, *dterm = nullptr;
+  T *x = nullptr, *r = nullptr, *z = nullptr, *pv = nullptr, *Ap = nullptr, *Ap_raw = nullptr, *xbak = nullptr, *xs = nullptr;
+  T *delta = nullptr; // [9Nc+3Np] scaled-space step
+  double *cost_part = nullptr, *rho_part = nullptr, *scalars = nullptr; // scalars: [0]=cost [1]=rho points [2]=rho cams
+  PcgState<T> *pcg_state = nullptr;
+  int *done_flag = nullptr;
+  int pcg_state_cap = 0;
+  // host mirrors
+  double *h_scalars = nullptr;
+  PcgState<T> *h_state = nullptr;
+  // flags
+  bool have_obs = false, have_vertices = false, linearized = false, prepared = false, solved = false, stepped = false;
+  bool scale_on = true;
+  T mu = T(1e-4);
+  int use_identity = 0;
+  int ncamblocks = 0;
+  gb_pcg_options last_pcg{10, 1.0, 5.0};
+  int64_t dimc = 0, dimH = 0;
+  cudaEvent_t ev[8];
+  double last_chi2 = 0.0;
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_ev; // pairs around k_schur_tiles<MODE 0>, one pair per PCG iteration
+
+  ~Problem() override {
+    if (ctx) cudaSetDevice(ctx->device);
+    for (void *p : allocs) cudaFree(p);
+    if (h_scalars) cudaFreeHost(h_scalars);
+    if (h_state) cudaFreeHost(h_state);
+    for (auto &e : ev) if (e) cudaEventDestroy(e);
+    for (auto &e : prof_ev) cudaEventDestroy(e);
+  }
+  int64_t device_bytes() const override { return bytes; }
+
+  template <typename X> int dalloc(X *&p, size_t n) {
+    void *q = nullptr;
+    const size_t sz = std::max<size_t>(n, 1) * sizeof(X);
+    GB_CUDA(ctx, cudaMalloc(&q, sz));
+    GB_CUDA(ctx, cudaMemsetAsync(q, 0, sz, ctx->stream));
+    allocs.push_back(q);
+    bytes += (int64_t)sz;
+    p = (X *)q;
+    return GB_OK;
+  }
+  template <typename X> int upload(const X *&dst, const std::vector<X> &v) {
+    X *p = nullptr;
+    GB_TRY(dalloc(p, v.size()));
+    GB_CUDA(ctx, cudaMemcpyAsync(p, v.data(), v.size() * sizeof(X), cudaMemcpyHostToDevice, ctx->stream));
+    dst = p;
+    return GB_OK;
+  }
+
+  int init() override {
+    GB_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (auto &e : ev) e = nullptr;
+    for (auto &e : ev) GB_CUDA(ctx, cudaEventCreate(&e));
+    const int64_t M = hs.M, Nc = hs.Nc, Np = hs.Np;
+    dimc = 9 * Nc;
+    dimH = 9 * Nc + 3 * Np;
+    ts.M = M;
+    ts.Mpad = (M + 31) / 32 * 32;
+    ts.Nc = hs.Nc; ts.Np = hs.Np; ts.ntiles = hs.ntiles(); ts.nseg = hs.nseg();
+    GB_TRY(upload(ts.cam_idx, hs.cam_idx));
+    GB_TRY(upload(ts.pt_idx, hs.pt_idx));
+    GB_TRY(upload(ts.rank, hs.rank));
+    GB_TRY(upload(ts.pptr, hs.pptr));
+    GB_TRY(upload(ts.tile_obs, hs.tile_obs));
+    GB_TRY(upload(ts.tile_pt, hs.tile_pt));
+    GB_TRY(upload(ts.tile_seg, hs.tile_seg));
+    GB_TRY(upload(ts.seg_cam, hs.seg_cam));
+    GB_TRY(upload(ts.seg_begin, hs.seg_begin));
+    GB_TRY(upload(ts.cam_seg_ptr, hs.cam_seg_ptr));
+    GB_TRY(upload(ts.cam_seg_list, hs.cam_seg_list));
+    GB_TRY(dalloc(cams, Nc * CAM_STRIDE)); GB_TRY(dalloc(cams_bak, Nc * CAM_STRIDE));
+    GB_TRY(dalloc(pts, 3 * Np)); GB_TRY(dalloc(pts_bak, 3 * Np));
+    GB_TRY(dalloc(obs, M)); GB_TRY(dalloc(res, M));
+    GB_TRY(dalloc(Jc, 9 * ts.Mpad)); GB_TRY(dalloc(Jp, 3 * ts.Mpad));
+    GB_TRY(dalloc(Cg, 9 * Np));
+    GB_TRY(dalloc(part18, (size_t)ts.nseg * 18)); GB_TRY(dalloc(part54, (size_t)ts.nseg * 54));
+    GB_TRY(dalloc(part9, (size_t)ts.nseg * 9)); GB_TRY(dalloc(sums54, Nc * 54));
+    GB_TRY(dalloc(diagB, dimc)); GB_TRY(dalloc(gc, dimc));
+    GB_TRY(dalloc(scale, dimH)); GB_TRY(dalloc(b, dimH)); GB_TRY(dalloc(delta, dimH));
+    GB_TRY(dalloc(W, 6 * Np)); GB_TRY(dalloc(h, 3 * Np));
+    GB_TRY(dalloc(Sdiag, Nc * 81)); GB_TRY(dalloc(Minv, Nc * 81));
+    GB_TRY(dalloc(bS, dimc)); GB_TRY(dalloc(dterm, dimc));
+    GB_TRY(dalloc(x, dimc)); GB_TRY(dalloc(r, dimc)); GB_TRY(dalloc(z, dimc)); GB_TRY(dalloc(pv, dimc));
+    GB_TRY(dalloc(Ap, dimc)); GB_TRY(dalloc(Ap_raw, dimc)); GB_TRY(dalloc(xbak, dimc));
+    GB_TRY(dalloc(xs, Nc * CAM_STRIDE));
+    ncamblocks = (int)((dimc + 255) / 256);
+    GB_TRY(dalloc(cost_part, ts.ntiles)); GB_TRY(dalloc(rho_part, ts.ntiles + ncamblocks));
+    GB_TRY(dalloc(scalars, 8));
+    GB_TRY(dalloc(done_flag, 1));
+    pcg_state_cap = 2 * 64 + 3;
+    GB_TRY(dalloc(pcg_state, pcg_state_cap));
+    GB_CUDA(ctx, cudaMallocHost((void **)&h_scalars, 8 * sizeof(double)));
+    GB_CUDA(ctx, cudaMallocHost((void **)&h_state, sizeof(PcgState<T>)));
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GB_OK;
+  }
+
+  int ensure_state_cap(int64_t max_iter) {
+    const int need = (int)(2 * max_iter + 3);
+    if (need > pcg_state_cap) {
+      GB_TRY(dalloc(pcg_state, need));
+      pcg_state_cap = need;
+    }
+    return GB_OK;
+  }
+
+  // ---- collectives -----------------------------------------------------------------------------------
+  int allreduce(void *buf, size_t count, bool is_double) {
+    if (ctx->nranks <= 1) return GB_OK;
+    const int rc = g_nccl.AllReduce(buf, buf, count, is_double ? NCCL_FLOAT64 : NCCL_FLOAT32, NCCL_SUM, ctx->comm, ctx->stream);
+    if (rc != 0) return ctx->fail(GB_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    return GB_OK;
+  }
+  int allreduce_T(T *buf, size_t count) { return allreduce(buf, count, sizeof(T) == 8); }
+
+  // ---- IO ----------------------------------------------------------------------------------------------
+  int set_observations(const void *o) override {
+    const T *src = (const T *)o;
+    std::vector<T> tmp;
+    if (!hs.identity_perm) {
+      tmp.resize(2 * hs.M);
+      for (int64_t i = 0; i < hs.M; i++) { tmp[2 * i] = src[2 * hs.perm[i]]; tmp[2 * i + 1] = src[2 * hs.perm[i] + 1]; }
+      src = tmp.data();
+    }
+    GB_CUDA(ctx, cudaMemcpyAsync(obs, src, 2 * hs.M * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    have_obs = true;
+    linearized = prepared = solved = stepped = false;
+    return GB_OK;
+  }
+  int set_vertices(const void *c, const void *p) override {
+    // 9 -> 10 padded rows: a strided 2-D copy, no host staging
+    GB_CUDA(ctx, cudaMemcpy2DAsync(cams, CAM_STRIDE * sizeof(T), c, 9 * sizeof(T), 9 * sizeof(T), hs.Nc,
+                                   cudaMemcpyHostToDevice, ctx->stream));
+    GB_CUDA(ctx, cudaMemcpyAsync(pts, p, 3 * (size_t)hs.Np * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    have_vertices = true;
+    linearized = prepared = solved = stepped = false;
+    return GB_OK;
+  }
+  int get_vertices(void *c, void *p) override {
+    if (!have_vertices) return ctx->fail(GB_ERR_INVALID, "gb_get_vertices before gb_set_vertices");
+    if (c)
+      GB_CUDA(ctx, cudaMemcpy2DAsync(c, 9 * sizeof(T), cams, CAM_STRIDE * sizeof(T), 9 * sizeof(T), hs.Nc,
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+    if (p) GB_CUDA(ctx, cudaMemcpyAsync(p, pts, 3 * (size_t)hs.Np * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GB_OK;
+  }
+
+  // ---- stages (asynchronous on the context stream) -----------------------------------------------------
+  int launch_check() {
+    GB_CUDA(ctx, cudaGetLastError());
+    return GB_OK;
+  }
+
+  int enqueue_linearize() {
+    cudaStream_t st = ctx->stream;
+    k_linearize<T, S><<<ts.ntiles, TILE, 0, st>>>(ts, cams, pts, obs, Jc, Jp, res, Cg, part18, cost_part);
+    GB_LAUNCH(ctx);
+    const bool multi = ctx->nranks > 1;
+    k_cam_reduce_lin<T><<<ts.Nc, 288, 0, st>>>(ts, part18, diagB, gc, multi ? 0 : 1, scale_on ? 1 : 0, scale, b);
+    GB_LAUNCH(ctx);
+    k_sum_partials<<<1, 1024, 0, st>>>(cost_part, ts.ntiles, scalars, 0);
+    GB_LAUNCH(ctx);
+    if (multi) {
+      GB_TRY(allreduce_T(diagB, dimc));
+      GB_TRY(allreduce_T(gc, dimc));
+      GB_TRY(allreduce(scalars, 1, true));
+      k_cam_finish_lin<T><<<(int)((dimc + 255) / 256), 256, 0, st>>>((int)dimc, scale_on ? 1 : 0, diagB, gc, scale, b);
+      GB_LAUNCH(ctx);
+    }
+    // point scales and b_p (mu-independent part of k_point_prepare); W/h are refreshed by prepare
+    k_point_prepare<T><<<(ts.Np + 255) / 256, 256, 0, st>>>(ts.Np, scale_on ? 1 : 0, mu, use_identity, Cg, scale + dimc,
+                                                           b + dimc, W, h, 1);
+    GB_LAUNCH(ctx);
+    GB_TRY(launch_check());
+    linearized = true;
+    prepared = solved = stepped = false;
+    return GB_OK;
+  }
+
+  int enqueue_prepare() {
+    cudaStream_t st = ctx->stream;
+    k_point_prepare<T><<<(ts.Np + 255) / 256, 256, 0, st>>>(ts.Np, scale_on ? 1 : 0, mu, use_identity, Cg, scale + dimc,
+                                                           b + dimc, W, h, 0);
+    GB_LAUNCH(ctx);
+    k_prepare_tiles<T, S><<<ts.ntiles, TILE, 0, st>>>(ts, Jc, Jp, W, h, part54);
+    GB_LAUNCH(ctx);
+    const bool multi = ctx->nranks > 1;
+    k_cam_reduce_prepare<T><<<ts.Nc, 288, 0, st>>>(ts, part54, 0, sums54, multi ? 0 : 1, mu, use_identity, diagB, gc,
+                                                   scale, Sdiag, Minv, bS, dterm);
+    GB_LAUNCH(ctx);
+    if (multi) {
+      GB_TRY(allreduce_T(sums54, (size_t)ts.Nc * 54));
+      k_cam_reduce_prepare<T><<<ts.Nc, 288, 0, st>>>(ts, part54, 1, sums54, 1, mu, use_identity, diagB, gc, scale, Sdiag,
+                                                     Minv, bS, dterm);
+      GB_LAUNCH(ctx);
+    }
+    GB_TRY(launch_check());
+    prepared = true;
+    return GB_OK;
+  }
+
+  // y_raw = D (B - E W E^T) D applied to the vector whose scaled copy is in xs
+  int enqueue_schur_product(T *out_raw, const int *flag, int prof_slot = -1) {
+    cudaStream_t st = ctx->stream;
+    const bool prof = profiling && prof_slot >= 0;
+    if (prof) {
+      while ((int)prof_ev.size() < 2 * prof_slot + 2) {
+        cudaEvent_t e;
+        GB_CUDA(ctx, cudaEventCreate(&e));
+        prof_ev.push_back(e);
+      }
+      GB_CUDA(ctx, cudaEventRecord(prof_ev[2 * prof_slot], st));
+    }
+    k_schur_tiles<T, S, 0><<<ts.ntiles, TILE, 0, st>>>(ts, Jc, Jp, W, xs, part9, nullptr, nullptr, nullptr, T(0), nullptr,
+                                                       nullptr, nullptr, nullptr, 0, flag);
+    GB_LAUNCH(ctx);
+    if (prof) GB_CUDA(ctx, cudaEventRecord(prof_ev[2 * prof_slot + 1], st));
+    k_cam_reduce_spmv<T><<<ts.Nc, 288, 0, st>>>(ts, part9, scale, out_raw, flag);
+    GB_LAUNCH(ctx);
+    GB_TRY(allreduce_T(out_raw, dimc));
+    return GB_OK;
+  }
+
+  int enqueue_pcg(const gb_pcg_options *o) {
+    cudaStream_t st = ctx->stream;
+    GB_TRY(ensure_state_cap(o->max_iterations));
+    const int gridc = (ts.Nc + PCG_CAMS - 1) / PCG_CAMS;
+    GB_CUDA(ctx, cudaMemsetAsync(done_flag, 0, sizeof(int), st));
+    k_pcg_init<T><<<gridc, 288, 0, st>>>(ts.Nc, bS, Minv, scale, x, r, z, pv, xs);
+    GB_LAUNCH(ctx);
+    k_pcg_init_state<T><<<1, 1024, 0, st>>>((int)dimc, r, z, pcg_state);
+    GB_LAUNCH(ctx);
+    for (int64_t k = 0; k < o->max_iterations; k++) {
+      GB_TRY(enqueue_schur_product(Ap_raw, done_flag, (int)k));
+      k_pcg_update1<T><<<gridc, 288, 0, st>>>(ts.Nc, pcg_state + 2 * k, pcg_state + 2 * k + 1, Ap_raw, dterm, Minv, Ap, x,
+                                              xbak, r, z, pv, done_flag);
+      GB_LAUNCH(ctx);
+      k_pcg_update2<T><<<gridc, 288, 0, st>>>(ts.Nc, pcg_state + 2 * k + 1, pcg_state + 2 * k + 2, (T)o->tolerance,
+                                              (T)o->rejection_ratio, (int)o->max_iterations, scale, x, xbak, r, z, pv, xs,
+                                              done_flag);
+      GB_LAUNCH(ctx);
+    }
+    GB_CUDA(ctx, cudaMemcpyAsync(h_state, pcg_state + 2 * o->max_iterations, sizeof(PcgState<T>), cudaMemcpyDeviceToHost, st));
+    GB_TRY(launch_check());
+    last_pcg = *o;
+    solved = true;
+    stepped = false;
+    return GB_OK;
+  }
+
+  // back-substitution (+ optional application of the step) ; fills delta and the rho partials
+  int enqueue_step(bool apply) {
+    cudaStream_t st = ctx->stream;
+    // camera part: delta_c = x, xs = D x, rho, (apply) cams += D x
+    k_cam_step<T><<<ncamblocks, 256, 0, st>>>((int)dimc, x, scale, b, mu, xs, cams, cams_bak, delta, rho_part + ts.ntiles,
+                                              apply ? 1 : 0);
+    GB_LAUNCH(ctx);
+    k_schur_tiles<T, S, 1><<<ts.ntiles, TILE, 0, st>>>(ts, Jc, Jp, W, xs, nullptr, h, scale + dimc, b + dimc, mu, pts, pts_bak,
+                                                       delta + dimc, rho_part, apply ? 1 : 0, nullptr);
+    GB_LAUNCH(ctx);
+    k_sum_partials<<<1, 1024, 0, st>>>(rho_part, ts.ntiles, scalars, 1);
+    GB_LAUNCH(ctx);
+    k_sum_partials<<<1, 1024, 0, st>>>(rho_part + ts.ntiles, ncamblocks, scalars, 2);
+    GB_LAUNCH(ctx);
+    GB_TRY(launch_check());
+    return GB_OK;
+  }
+
+  int enqueue_cost() {
+    cudaStream_t st = ctx->stream;
+    k_cost_tiles<T><<<ts.ntiles, TILE, 0, st>>>(ts, cams, pts, obs, cost_part);
+    GB_LAUNCH(ctx);
+    k_sum_partials<<<1, 1024, 0, st>>>(cost_part, ts.ntiles, scalars, 0);
+    GB_LAUNCH(ctx);
+    GB_TRY(launch_check());
+    return GB_OK;
+  }
+
+  int fetch_scalars() {
+    if (ctx->nranks > 1) GB_TRY(allreduce(scalars, 2, true)); // cost and the point part of rho; the camera part is replicated
+    GB_CUDA(ctx, cudaMemcpyAsync(h_scalars, scalars, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GB_OK;
+  }
+
+  int require(bool cond, const char *what) {
+    if (!cond) return ctx->fail(GB_ERR_INVALID, "%s", what);
+    return GB_OK;
+  }
+
+  // ---- public operations ---------------------------------------------------------------------------------
+  int linearize(double *chi2) override {
+    GB_TRY(require(have_obs && have_vertices, "gb_linearize needs observations and vertices"));
+    GB_TRY(enqueue_linearize());
+    GB_CUDA(ctx, cudaMemcpyAsync(h_scalars, scalars, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    last_chi2 = (double)(T)h_scalars[0];
+    if (chi2) *chi2 = last_chi2;
+    return GB_OK;
+  }
+  int compute_cost(double *chi2) override {
+    GB_TRY(require(have_obs && have_vertices, "gb_compute_cost needs observations and vertices"));
+    GB_TRY(enqueue_cost());
+    if (ctx->nranks > 1) GB_TRY(allreduce(scalars, 1, true));
+    GB_CUDA(ctx, cudaMemcpyAsync(h_scalars, scalars, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (chi2) *chi2 = (double)(T)h_scalars[0];
+    return GB_OK;
+  }
+  int d2h(void *dst, const void *src, size_t n) {
+    GB_CUDA(ctx, cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, ctx->stream));
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GB_OK;
+  }
+  int get_gradient(void *out) override {
+    GB_TRY(require(linearized, "gb_get_gradient before gb_linearize"));
+    return d2h(out, b, dimH * sizeof(T));
+  }
+  int get_scales(void *out) override {
+    GB_TRY(require(linearized, "gb_get_scales before gb_linearize"));
+    return d2h(out, scale, dimH * sizeof(T));
+  }
+  int get_residuals(void *out) override {
+    GB_TRY(require(linearized, "gb_get_residuals before gb_linearize"));
+    if (hs.identity_perm) return d2h(out, res, 2 * hs.M * sizeof(T));
+    std::vector<T> tmp(2 * hs.M);
+    GB_TRY(d2h(tmp.data(), res, 2 * hs.M * sizeof(T)));
+    T *o = (T *)out;
+    for (int64_t i = 0; i < hs.M; i++) { o[2 * hs.perm[i]] = tmp[2 * i]; o[2 * hs.perm[i] + 1] = tmp[2 * i + 1]; }
+    return GB_OK;
+  }
+  int get_jacobians(double *oc, double *op) override {
+    GB_TRY(require(linearized, "gb_get_jacobians before gb_linearize"));
+    std::vector<S> hc(18 * ts.Mpad), hp(6 * ts.Mpad);
+    GB_TRY(d2h(hc.data(), Jc, hc.size() * sizeof(S)));
+    GB_TRY(d2h(hp.data(), Jp, hp.size() * sizeof(S)));
+    for (int64_t i = 0; i < hs.M; i++) {
+      const int64_t u = hs.identity_perm ? i : hs.perm[i];
+      for (int j = 0; j < 9; j++) {
+        oc[18 * u + 2 * j] = (double)hc[2 * (j * ts.Mpad + i)];
+        oc[18 * u + 2 * j + 1] = (double)hc[2 * (j * ts.Mpad + i) + 1];
+      }
+      for (int j = 0; j < 3; j++) {
+        op[6 * u + 2 * j] = (double)hp[2 * (j * ts.Mpad + i)];
+        op[6 * u + 2 * j + 1] = (double)hp[2 * (j * ts.Mpad + i) + 1];
+      }
+    }
+    return GB_OK;
+  }
+  int hessian_values(void *out) override {
+    GB_TRY(require(linearized, "gb_hessian_values before gb_linearize"));
+    GB_TRY(require(ctx->nranks == 1, "gb_hessian_values is single-rank only"));
+    const int64_t nv = 81 * (int64_t)hs.Nc + 27 * hs.M + 9 * (int64_t)hs.Np;
+    S *vals = nullptr;
+    GB_CUDA(ctx, cudaMalloc((void **)&vals, nv * sizeof(S)));
+    const int64_t n = std::max<int64_t>(hs.M, hs.Np);
+    k_hessian_EC<T, S><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ts, Jc, Jp, Cg, scale, scale + dimc, vals);
+    GB_LAUNCH(ctx);
+    k_hessian_B<T, S><<<ts.Nc, 96, 0, ctx->stream>>>(ts, Jc, scale, vals);
+    GB_LAUNCH(ctx);
+    int rc = d2h(out, vals, nv * sizeof(S));
+    cudaFree(vals);
+    return rc;
+  }
+  int set_damping(double m, int ident) override {
+    mu = (T)m;
+    use_identity = ident;
+    prepared = solved = false;
+    return GB_OK;
+  }
+  int solve(const gb_pcg_options *o, void *delta_host, gb_solve_info *info) override {
+    GB_TRY(require(linearized, "gb_solve before gb_linearize"));
+    GB_TRY(require(o && o->max_iterations >= 0 && o->max_iterations < (1 << 20), "bad PCG options"));
+    GB_TRY(enqueue_prepare());
+    GB_TRY(enqueue_pcg(o));
+    if (delta_host) {
+      GB_TRY(enqueue_step(false));
+      GB_TRY(d2h(delta_host, delta, dimH * sizeof(T)));
+    }
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (info) {
+      info->pcg_iterations = h_state->iter;
+      info->rz_final = (double)h_state->rz;
+      info->stop_reason = h_state->reason;
+      info->reserved = 0;
+    }
+    return GB_OK;
+  }
+  int get_schur_rhs(void *out) override {
+    GB_TRY(require(linearized, "gb_get_schur_rhs before gb_linearize"));
+    if (!prepared) GB_TRY(enqueue_prepare());
+    return d2h(out, bS, dimc * sizeof(T));
+  }
+  int get_schur_diagonal(void *out) override {
+    GB_TRY(require(linearized, "gb_get_schur_diagonal before gb_linearize"));
+    if (!prepared) GB_TRY(enqueue_prepare());
+    return d2h(out, Sdiag, (size_t)hs.Nc * 81 * sizeof(T));
+  }
+  int schur_multiply(const void *xin, void *yout) override {
+    GB_TRY(require(linearized, "gb_schur_multiply before gb_linearize"));
+    if (!prepared) GB_TRY(enqueue_prepare());
+    // xs = D x (host side scaling keeps this export path free of extra kernels)
+    std::vector<T> hscale(dimc), hx(hs.Nc * CAM_STRIDE, T(0)), hd(dimc), hy(dimc);
+    GB_TRY(d2h(hscale.data(), scale, dimc * sizeof(T)));
+    GB_TRY(d2h(hd.data(), dterm, dimc * sizeof(T)));
+    const T *xi = (const T *)xin;
+    for (int64_t c = 0; c < hs.Nc; c++)
+      for (int k = 0; k < 9; k++) hx[c * CAM_STRIDE + k] = hscale[c * 9 + k] * xi[c * 9 + k];
+    GB_CUDA(ctx, cudaMemcpyAsync(xs, hx.data(), hx.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    GB_TRY(enqueue_schur_product(Ap_raw, nullptr));
+    GB_TRY(d2h(hy.data(), Ap_raw, dimc * sizeof(T)));
+    T *yo = (T *)yout;
+    for (int64_t i = 0; i < dimc; i++) yo[i] = hy[i] + hd[i] * xi[i];
+    solved = false; // xs was overwritten
+    return GB_OK;
+  }
+  int try_step(double *new_chi2, double *rho_den) override {
+    GB_TRY(require(solved, "gb_try_step before gb_solve"));
+    GB_TRY(enqueue_step(true));
+    GB_TRY(enqueue_cost());
+    GB_TRY(fetch_scalars());
+    stepped = true;
+    if (new_chi2) *new_chi2 = (double)(T)h_scalars[0];
+    if (rho_den) *rho_den = (double)((T)(h_scalars[1] + h_scalars[2]) + (T)1.0e-3);
+    return GB_OK;
+  }
+  int enqueue_revert() {
+    cudaStream_t st = ctx->stream;
+    GB_CUDA(ctx, cudaMemcpyAsync(cams, cams_bak, (size_t)ts.Nc * CAM_STRIDE * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    GB_CUDA(ctx, cudaMemcpyAsync(pts, pts_bak, 3 * (size_t)ts.Np * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    return GB_OK;
+  }
+  int revert_step() override {
+    GB_TRY(require(stepped, "gb_revert_step without a step"));
+    GB_TRY(enqueue_revert());
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    stepped = false;
+    return GB_OK;
+  }
+
+  // optimizer::levenberg_marquardt (levenberg_marquardt.hpp:109-242)
+  int lm(const gb_lm_options *o, gb_lm_result *res_out, double *traj) override {
+    GB_TRY(require(have_obs && have_vertices, "gb_lm needs observations and vertices"));
+    GB_TRY(require(o && o->iterations >= 0, "bad LM options"));
+    cudaStream_t st = ctx->stream;
+    gb_lm_result R{};
+    const bool resume = o->resume != 0 && linearized;
+    T mu_l = (T)o->initial_damping, nu = o->initial_nu > 0 ? (T)o->initial_nu : T(2);
+    use_identity = o->use_identity;
+    profiling = o->profile_product != 0;
+    double acc[5] = {0, 0, 0, 0, 0};
+    float ms = 0.f;
+    GB_CUDA(ctx, cudaEventRecord(ev[6], st));
+    mu = mu_l;
+    T chi2;
+    if (!resume) {
+      GB_CUDA(ctx, cudaEventRecord(ev[0], st));
+      GB_TRY(enqueue_linearize());
+      GB_CUDA(ctx, cudaEventRecord(ev[1], st));
+      GB_CUDA(ctx, cudaMemcpyAsync(h_scalars, scalars, sizeof(double), cudaMemcpyDeviceToHost, st));
+      GB_CUDA(ctx, cudaStreamSynchronize(st));
+      cudaEventElapsedTime(&ms, ev[0], ev[1]);
+      acc[0] += ms;
+      chi2 = (T)h_scalars[0];
+    } else {
+      chi2 = (T)last_chi2;
+    }
+    R.initial_chi2 = (double)chi2;
+    bool run = true;
+    int64_t it = 0;
+    for (; it < o->iterations && run; it++) {
+      mu = mu_l;
+      GB_CUDA(ctx, cudaEventRecord(ev[0], st));
+      GB_TRY(enqueue_prepare());
+      GB_CUDA(ctx, cudaEventRecord(ev[1], st));
+      GB_TRY(enqueue_pcg(&o->pcg));
+      GB_CUDA(ctx, cudaEventRecord(ev[2], st));
+      GB_TRY(enqueue_step(true));
+      GB_CUDA(ctx, cudaEventRecord(ev[3], st));
+      GB_TRY(enqueue_cost());
+      GB_CUDA(ctx, cudaEventRecord(ev[4], st));
+      GB_TRY(fetch_scalars());
+      cudaEventElapsedTime(&ms, ev[0], ev[1]); acc[1] += ms;
+      cudaEventElapsedTime(&ms, ev[1], ev[2]); acc[2] += ms;
+      cudaEventElapsedTime(&ms, ev[2], ev[3]); acc[3] += ms;
+      cudaEventElapsedTime(&ms, ev[3], ev[4]); acc[4] += ms;
+      T new_chi2 = (T)h_scalars[0];
+      const bool solve_ok = true; // PCGSchurSolver::solve always returns true (pcg_schur.hpp:167)
+      const T denom = (T)(h_scalars[1] + h_scalars[2]) + (T)1.0e-3;
+      const T rho = (chi2 - new_chi2) / denom;
+      R.pcg_iterations_total += h_state->iter;
+      const int64_t k_exec = h_state->iter;
+      if (profiling) {
+        // launches 0 .. k_exec-1 did the work (a launch after the stop flag returns at once), except that an
+        // iteration stopped by rz == 0 or a bad denominator never used its product
+        for (int64_t k = 0; k < k_exec && 2 * k + 1 < (int64_t)prof_ev.size(); k++) {
+          cudaEventElapsedTime(&ms, prof_ev[2 * k], prof_ev[2 * k + 1]);
+          R.product_seconds += ms * 1e-3;
+          R.product_launches++;
+        }
+      }
+      if (solve_ok && std::isfinite((double)new_chi2) && rho > T(0)) {
+        double alpha = 1.0 - std::pow(2.0 * (double)rho - 1.0, 3);
+        alpha = std::max(std::min(alpha, 2.0 / 3.0), 1.0 / 3.0);
+        mu_l *= (T)alpha;
+        nu = T(2);
+        mu = mu_l;
+        GB_CUDA(ctx, cudaEventRecord(ev[0], st));
+        GB_TRY(enqueue_linearize());
+        GB_CUDA(ctx, cudaEventRecord(ev[1], st));
+        GB_CUDA(ctx, cudaStreamSynchronize(st));
+        cudaEventElapsedTime(&ms, ev[0], ev[1]);
+        acc[0] += ms;
+        R.accepted++;
+      } else {
+        GB_TRY(enqueue_revert());
+        mu_l *= nu;
+        nu *= T(2);
+        new_chi2 = chi2;
+        R.rejected++;
+        solved = false;
+      }
+      if (traj) {
+        traj[4 * it + 0] = (double)chi2; traj[4 * it + 1] = (double)new_chi2;
+        traj[4 * it + 2] = (double)mu_l; traj[4 * it + 3] = (double)k_exec;
+      }
+      if (o->verbose)
+        printf("%6ld %22.12g %22.12g %16.8g  pcg %ld\n", (long)it, (double)chi2, (double)new_chi2, (double)mu_l, (long)k_exec);
+      chi2 = new_chi2;
+      if (!std::isfinite((double)mu_l)) run = false;
+      if (rho == T(0)) { it++; break; }
+      if (o->stop_flag && *o->stop_flag) { it++; break; }
+    }
+    GB_CUDA(ctx, cudaEventRecord(ev[7], st));
+    GB_CUDA(ctx, cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&ms, ev[6], ev[7]);
+    stepped = false;
+    profiling = false;
+    last_chi2 = (double)chi2;
+    R.iterations = it;
+    R.final_chi2 = (double)chi2;
+    R.final_damping = (double)mu_l;
+    R.final_nu = (double)nu;
+    R.seconds_total = ms * 1e-3;
+    R.seconds_linearize = acc[0] * 1e-3; R.seconds_prepare = acc[1] * 1e-3; R.seconds_pcg = acc[2] * 1e-3;
+    R.seconds_backsubst = acc[3] * 1e-3; R.seconds_cost = acc[4] * 1e-3;
+    if (res_out) *res_out = R;
+    return GB_OK;
+  }
+
+  int time_stage(int stage, int reps, double *ms_avg) override {
+    GB_TRY(require(have_obs && have_vertices, "gb_time_stage needs observations and vertices"));
+    GB_TRY(require(reps > 0, "repetitions must be positive"));
+    cudaStream_t st = ctx->stream;
+    if (!linearized) GB_TRY(enqueue_linearize());
+    if (stage >= 2 && !prepared) GB_TRY(enqueue_prepare());
+    if (stage == 2 || stage == 3) {
+      // a defined vector in xs / x: one PCG initialisation
+      const int gridc = (ts.Nc + PCG_CAMS - 1) / PCG_CAMS;
+      k_pcg_init<T><<<gridc, 288, 0, st>>>(ts.Nc, bS, Minv, scale, x, r, z, pv, xs);
+      GB_LAUNCH(ctx);
+    }
+    GB_CUDA(ctx, cudaStreamSynchronize(st));
+    GB_CUDA(ctx, cudaEventRecord(ev[0], st));
+    for (int i = 0; i < reps; i++) {
+      switch (stage) {
+      case 0: GB_TRY(enqueue_linearize()); break;
+      case 1: GB_TRY(enqueue_prepare()); break;
+      case 2: GB_TRY(enqueue_schur_product(Ap_raw, nullptr)); break;
+      case 3: GB_TRY(enqueue_step(false)); break;
+      case 4: GB_TRY(enqueue_cost()); break;
+      default: return ctx->fail(GB_ERR_INVALID, "unknown stage %d", stage);
+      }
+    }
+    GB_CUDA(ctx, cudaEventRecord(ev[1], st));
+    GB_CUDA(ctx, cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev[0], ev[1]);
+    *ms_avg = (double)ms / reps;
+    if (stage == 0) { prepared = solved = false; }
+    solved = false;
+    return GB_OK;
+  }
+};
+
+} // namespace gb
+
+struct gb_problem {
+  gb::ProblemBase *impl;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+int gb_version(void) { return GB_VERSION; }
+
+int gb_context_create(int device, gb_context **out) {
+  if (!out) return GB_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return GB_ERR_NO_DEVICE;
+  if (device < 0 || device >= n) return GB_ERR_INVALID;
+  if (cudaSetDevice(device) != cudaSuccess) return GB_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return GB_ERR_CUDA;
+  if (prop.major != 10) return GB_ERR_UNSUPPORTED; // kernels are built for sm_100a only
+  gb_context *c = new gb_context();
+  c->device = device;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return GB_ERR_CUDA;
+  }
+  *out = c;
+  return GB_OK;
+}
+
+int gb_context_destroy(gb_context *ctx) {
+  if (!ctx) return GB_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return GB_OK;
+}
+
+const char *gb_last_error(const gb_context *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int gb_comm_unique_id(void *id128) {
+  if (!id128) return GB_ERR_INVALID;
+  if (!g_nccl.load()) return GB_ERR_NCCL;
+  ncclUniqueId_gb id;
+  if (g_nccl.GetUniqueId(&id) != 0) return GB_ERR_NCCL;
+  memcpy(id128, &id, 128);
+  return GB_OK;
+}
+
+int gb_comm_init(gb_context *ctx, int nranks, int rank, const void *id128) {
+  if (!ctx || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return GB_ERR_INVALID;
+  if (!g_nccl.load()) return ctx->fail(GB_ERR_NCCL, "libnccl.so.2 not found");
+  GB_CUDA(ctx, cudaSetDevice(ctx->device));
+  ncclUniqueId_gb id;
+  memcpy(&id, id128, 128);
+  const int rc = g_nccl.CommInitRank(&ctx->comm, nranks, id, rank);
+  if (rc != 0) return ctx->fail(GB_ERR_NCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  ctx->nranks = nranks;
+  ctx->rank = rank;
+  return GB_OK;
+}
+
+int gb_problem_create(gb_context *ctx, const gb_problem_desc *d, gb_problem **out) {
+  if (!ctx) return GB_ERR_INVALID;
+  if (!d || !out || !d->camera_index || !d->point_index) return ctx->fail(GB_ERR_INVALID, "null argument");
+  *out = nullptr;
+  gb::ProblemBase *impl = nullptr;
+  if (d->precision_T == GB_F64 && d->precision_S == GB_F64) impl = new gb::Problem<double, double>();
+  else if (d->precision_T == GB_F32 && d->precision_S == GB_F32) impl = new gb::Problem<float, float>();
+  else if (d->precision_T == GB_F64 && d->precision_S == GB_F32) impl = new gb::Problem<double, float>();
+  else return ctx->fail(GB_ERR_UNSUPPORTED, "precision (T=%d,S=%d) not supported", d->precision_T, d->precision_S);
+  impl->ctx = ctx;
+  const std::string why = impl->hs.build(d->num_cameras, d->num_points, d->num_observations, d->camera_index,
+                                         d->point_index, d->tile_size);
+  if (!why.empty()) {
+    delete impl;
+    return ctx->fail(GB_ERR_UNSUPPORTED, "structure: %s", why.c_str());
+  }
+  const int rc = impl->init();
+  if (rc != GB_OK) {
+    delete impl;
+    return rc;
+  }
+  *out = new gb_problem{impl};
+  return GB_OK;
+}
+
+int gb_problem_destroy(gb_problem *p) {
+  if (p) {
+    delete p->impl;
+    delete p;
+  }
+  return GB_OK;
+}
+
+struct gb_structure {
+  gb::HostStructure hs;
+};
+
+static void fill_info(const gb::HostStructure &h, int64_t info[8], int64_t bytes) {
+  info[0] = h.ntiles();
+  info[1] = h.nseg();
+  info[2] = h.max_track;
+  info[3] = 9 * (int64_t)h.Nc + 3 * (int64_t)h.Np;
+  info[4] = (int64_t)h.Nc + h.M + h.Np;
+  info[5] = 81 * (int64_t)h.Nc + 27 * h.M + 9 * (int64_t)h.Np;
+  info[6] = bytes;
+  info[7] = h.M;
+}
+
+int gb_structure_create(const gb_problem_desc *d, gb_structure **out, char *errbuf, int errlen) {
+  if (!d || !out || !d->camera_index || !d->point_index) return GB_ERR_INVALID;
+  *out = nullptr;
+  gb_structure *s = new gb_structure();
+  const std::string why = s->hs.build(d->num_cameras, d->num_points, d->num_observations, d->camera_index,
+                                      d->point_index, d->tile_size);
+  if (!why.empty()) {
+    if (errbuf && errlen > 0) snprintf(errbuf, errlen, "%s", why.c_str());
+    delete s;
+    return GB_ERR_UNSUPPORTED;
+  }
+  *out = s;
+  return GB_OK;
+}
+int gb_structure_destroy(gb_structure *s) { delete s; return GB_OK; }
+int gb_structure_info(const gb_structure *s, int64_t info[8]) {
+  if (!s || !info) return GB_ERR_INVALID;
+  fill_info(s->hs, info, 0);
+  return GB_OK;
+}
+int gb_structure_array(const gb_structure *s, int which, void *out, int64_t *count) {
+  if (!s || !count) return GB_ERR_INVALID;
+  const gb::HostStructure &h = s->hs;
+  const std::vector<int32_t> *v32[] = {&h.cam_idx, &h.pt_idx, &h.pptr, &h.tile_obs, &h.tile_pt, &h.tile_seg,
+                                       &h.seg_cam, &h.seg_begin, &h.cam_seg_ptr, &h.cam_seg_list};
+  if (which >= 0 && which < 10) {
+    *count = (int64_t)v32[which]->size();
+    if (out) memcpy(out, v32[which]->data(), v32[which]->size() * sizeof(int32_t));
+  } else if (which == 10) {
+    *count = (int64_t)h.rank.size();
+    if (out) memcpy(out, h.rank.data(), h.rank.size());
+  } else if (which == 11) {
+    *count = (int64_t)h.perm.size();
+    if (out) memcpy(out, h.perm.data(), h.perm.size() * sizeof(int64_t));
+  } else {
+    return GB_ERR_INVALID;
+  }
+  return GB_OK;
+}
+int gb_structure_hessian(const gb_structure *s, int64_t *cp, int64_t *ri, int64_t *off) {
+  if (!s || !cp || !ri || !off) return GB_ERR_INVALID;
+  s->hs.hessian_structure(cp, ri, off);
+  return GB_OK;
+}
+
+int gb_problem_info(const gb_problem *p, int64_t info[8]) {
+  if (!p || !info) return GB_ERR_INVALID;
+  fill_info(p->impl->hs, info, p->impl->device_bytes());
+  return GB_OK;
+}
+
+#define GB_P(p) \
+  if (!(p) || !(p)->impl) return GB_ERR_INVALID; \
+  cudaSetDevice((p)->impl->ctx->device)
+
+int gb_set_observations(gb_problem *p, const void *o) { GB_P(p); if (!o) return GB_ERR_INVALID; return p->impl->set_observations(o); }
+int gb_set_vertices(gb_problem *p, const void *c, const void *q) { GB_P(p); if (!c || !q) return GB_ERR_INVALID; return p->impl->set_vertices(c, q); }
+int gb_get_vertices(gb_problem *p, void *c, void *q) { GB_P(p); return p->impl->get_vertices(c, q); }
+int gb_hessian_structure(const gb_problem *p, int64_t *cp, int64_t *ri, int64_t *off) {
+  if (!p || !cp || !ri || !off) return GB_ERR_INVALID;
+  p->impl->hs.hessian_structure(cp, ri, off);
+  return GB_OK;
+}
+int gb_linearize(gb_problem *p, double *chi2) { GB_P(p); return p->impl->linearize(chi2); }
+int gb_compute_cost(gb_problem *p, double *chi2) { GB_P(p); return p->impl->compute_cost(chi2); }
+int gb_get_gradient(gb_problem *p, void *b) { GB_P(p); return p->impl->get_gradient(b); }
+int gb_get_scales(gb_problem *p, void *s) { GB_P(p); return p->impl->get_scales(s); }
+int gb_get_residuals(gb_problem *p, void *r) { GB_P(p); return p->impl->get_residuals(r); }
+int gb_get_jacobians(gb_problem *p, double *a, double *b) { GB_P(p); return p->impl->get_jacobians(a, b); }
+int gb_hessian_values(gb_problem *p, void *v) { GB_P(p); return p->impl->hessian_values(v); }
+int gb_set_damping(gb_problem *p, double mu, int id) { GB_P(p); return p->impl->set_damping(mu, id); }
+int gb_solve(gb_problem *p, const gb_pcg_options *o, void *d, gb_solve_info *i) { GB_P(p); return p->impl->solve(o, d, i); }
+int gb_get_schur_rhs(gb_problem *p, void *b) { GB_P(p); return p->impl->get_schur_rhs(b); }
+int gb_get_schur_diagonal(gb_problem *p, void *b) { GB_P(p); return p->impl->get_schur_diagonal(b); }
+int gb_schur_multiply(gb_problem *p, const void *x, void *y) { GB_P(p); return p->impl->schur_multiply(x, y); }
+int gb_try_step(gb_problem *p, double *c, double *r) { GB_P(p); return p->impl->try_step(c, r); }
+int gb_revert_step(gb_problem *p) { GB_P(p); return p->impl->revert_step(); }
+int gb_lm(gb_problem *p, const gb_lm_options *o, gb_lm_result *r, double *t) { GB_P(p); return p->impl->lm(o, r, t); }
+int64_t gb_kernel_launches(const gb_context *ctx) { return ctx ? ctx->launches : 0; }
+int gb_time_stage(gb_problem *p, int stage, int reps, double *ms) { GB_P(p); if (!ms) return GB_ERR_INVALID; return p->impl->time_stage(stage, reps, ms); }
+
+} // extern "C"

@@ -91,7 +91,8 @@ def make_bal(n_cams: int, n_pts: int, n_obs: int, seed: int = 0, name: str = "cu
     spacing = 0.25
     length = spacing * n_cams
     # --- ground-truth cameras ---------------------------------------------------------
-    centre = np.stack([spacing * (np.arange(n_cams) + 0.5), rng.normal(0, 0.3, n_cams), rng.normal(0, 0.3, n_cams)], 1)
+    x0 = -0.5 * length  # scene centred on the origin
+    centre = np.stack([x0 + spacing * (np.arange(n_cams) + 0.5), rng.normal(0, 0.3, n_cams), rng.normal(0, 0.3, n_cams)], 1)
     w = rng.normal(0, 0.08, (n_cams, 3))
     w[np.linalg.norm(w, axis=1) < 1e-3] = [0.01, -0.02, 0.015]  # keep theta > 0 (reprojection_error.cuh:72)
     R = _rodrigues(w)
@@ -101,14 +102,14 @@ def make_bal(n_cams: int, n_pts: int, n_obs: int, seed: int = 0, name: str = "cu
     k2 = rng.normal(0, 0.005, n_cams)
     cams_gt = np.concatenate([w, t, f[:, None], k1[:, None], k2[:, None]], 1)
     # --- ground-truth points (index grows with x: incremental-SfM-like locality) ---------
-    x = np.sort(rng.uniform(0.0, length, n_pts))
+    x = np.sort(rng.uniform(x0, x0 + length, n_pts))
     depth = rng.uniform(5.0, 50.0, n_pts)
     y = rng.uniform(-0.25, 0.25, n_pts) * depth
     pts_gt = np.stack([x, y, -depth], 1)
     # --- visibility -------------------------------------------------------------------------
     half = 0.5 * depth
-    lo = np.clip(np.ceil((x - half) / spacing - 0.5).astype(np.int64), 0, n_cams - 1)
-    hi = np.clip(np.floor((x + half) / spacing - 0.5).astype(np.int64), 0, n_cams - 1)
+    lo = np.clip(np.ceil((x - x0 - half) / spacing - 0.5).astype(np.int64), 0, n_cams - 1)
+    hi = np.clip(np.floor((x - x0 + half) / spacing - 0.5).astype(np.int64), 0, n_cams - 1)
     ncand = np.maximum(hi - lo + 1, 1)
     if (ncand < 2).any():
         raise ValueError("scene too small: a point has fewer than two candidate cameras")
@@ -160,9 +161,12 @@ def make_bal(n_cams: int, n_pts: int, n_obs: int, seed: int = 0, name: str = "cu
     # rejects steps and PCG runs several iterations instead of converging in two steps
     bad = rng.random(n_obs) < outlier_frac
     obs[bad] += rng.normal(0, outlier_px, (int(bad.sum()), 2))
-    cams = cams_gt.copy()
-    cams[:, :6] += rng.normal(0, cam_sigma, (n_cams, 6))
-    cams[:, 6] *= 1.0 + rng.normal(0, 1e-3, n_cams)
+    # perturb rotation and camera CENTRE (not t = -R c: with the origin hundreds of units away a 1e-2 rad
+    # change of R at fixed t would move the camera by several units)
+    w0 = w + rng.normal(0, cam_sigma, (n_cams, 3))
+    c0 = centre + rng.normal(0, cam_sigma, (n_cams, 3))
+    t0 = -np.einsum("nij,nj->ni", _rodrigues(w0), c0)
+    cams = np.concatenate([w0, t0, (f * (1.0 + rng.normal(0, 1e-3, n_cams)))[:, None], k1[:, None], k2[:, None]], 1)
     pts = pts_gt + rng.normal(0, 1.0, (n_pts, 3)) * (pt_sigma * depth)[:, None]
     return BALProblem(cam_idx, pt_idx, np.ascontiguousarray(obs), cams, pts, name)
 
@@ -184,7 +188,7 @@ def schur_fixture() -> BALProblem:
 
 
 def write_gbal(prob: BALProblem, path: str) -> None:
-    """Binary container read by oracle/ref_driver.cu (int64 header, int32 ids, f64 payload)."""
+    """Binary container read by the reference driver (int64 header, int32 ids, f64 payload)."""
     with open(path, "wb") as fh:
         fh.write(struct.pack("<qqq", prob.n_cams, prob.n_pts, prob.n_obs))
         fh.write(np.ascontiguousarray(prob.cam_idx, dtype="<i4").tobytes())

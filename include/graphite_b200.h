@@ -1,0 +1,191 @@
+/* graphite_b200.h — C ABI of the B200-native Levenberg-Marquardt inner loop for bundle adjustment.
+ *
+ * This is the drop-in boundary for ONE hot path of sfu-rsl/graphite: the LM loop with the
+ * Schur-complement PCG solver on BAL-type problems (camera 9-dof / point 3-dof / 2-d reprojection
+ * factors).  Every entry point names the reference interface it replaces (paths relative to the
+ * reference tree).  Signatures carry plain pointers and sizes only; there are no C++ or torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative gb_status; the message for the last failure
+ *     on a context is gb_last_error(ctx).  Nothing throws.  There is NO CPU fallback: without a
+ *     CUDA device (or when built without a matching kernel image) gb_context_create fails.
+ *   - "host" pointers are caller-owned host memory (pinned or pageable); copies are issued on the
+ *     context stream and completed before the call returns unless the name ends in _async.
+ *   - T = graph precision (vertices, residuals, gradient, step, PCG vectors); S = linear-system
+ *     precision (stored Jacobians).  (include/graphite/graph.hpp:25-29)
+ *   - block order: cameras (vertex id = camera index) then points (vertex id = n_cams + point index),
+ *     i.e. non-eliminated vertices by ascending id, then eliminated ones (graph.hpp:112-147).
+ *   - the step delta_x is in the Jacobi-scaled space, length 9*n_cams + 3*n_points, cameras first
+ *     (Solver::solve contract, solver/solver.hpp:24; pcg_schur.hpp:79-168).
+ */
+#ifndef GRAPHITE_B200_H
+#define GRAPHITE_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GB_VERSION 100
+
+typedef enum {
+  GB_OK = 0,
+  GB_ERR_INVALID = -1,     /* bad argument / call order */
+  GB_ERR_CUDA = -2,        /* CUDA runtime failure (message has the CUDA error string) */
+  GB_ERR_UNSUPPORTED = -3, /* precision combination or problem shape not supported */
+  GB_ERR_NCCL = -4,
+  GB_ERR_NO_DEVICE = -5
+} gb_status;
+
+typedef enum { GB_F32 = 0, GB_F64 = 1 } gb_dtype;
+
+typedef struct gb_context gb_context;
+typedef struct gb_problem gb_problem;
+
+/* Replaces: cudaSetDevice + StreamPool (examples/bal.cu:53,251; include/graphite/stream.hpp). */
+int gb_context_create(int device, gb_context **out);
+int gb_context_destroy(gb_context *ctx);
+const char *gb_last_error(const gb_context *ctx);
+int gb_version(void);
+
+/* Multi-GPU (new; the reference is single-GPU).  One process per GPU.  Rank 0 calls gb_comm_unique_id,
+ * the 128 bytes are broadcast by the host program (torch.distributed / MPI), then every rank calls
+ * gb_comm_init.  Points are partitioned across ranks by the caller; cameras are replicated. */
+int gb_comm_unique_id(void *id128);
+int gb_comm_init(gb_context *ctx, int nranks, int rank, const void *id128);
+
+typedef struct {
+  int32_t precision_T;       /* gb_dtype */
+  int32_t precision_S;       /* gb_dtype; (F64,F64), (F32,F32), (F64,F32) */
+  int64_t num_cameras;       /* all cameras (replicated on every rank) */
+  int64_t num_points;        /* points owned by this rank */
+  int64_t num_observations;  /* observations of those points */
+  const int32_t *camera_index; /* host [num_observations] */
+  const int32_t *point_index;  /* host [num_observations], local point index */
+  int32_t tile_size;         /* 0 = default (256) */
+  int32_t reserved;
+} gb_problem_desc;
+
+/* Replaces: Graph::initialize_optimization + build_structure (graph.hpp:92-219),
+ * FactorDescriptor::initialize_device_ids (factor.hpp:455-467), Hessian::build_structure
+ * (hessian.hpp:257-288), SchurComplement::build_structure (schur.hpp:194-225) and
+ * PCGSchurSolver::update_structure (solver/pcg_schur.hpp:49-65): sorts the factors by (point, camera),
+ * builds the point CSR, the observation tiles and the per-tile camera segments used by the
+ * atomic-free reductions. */
+int gb_problem_create(gb_context *ctx, const gb_problem_desc *desc, gb_problem **out);
+int gb_problem_destroy(gb_problem *p);
+
+/* Host-only view of the same structure build (no GPU needed): used by the CPU test-suite and by callers that
+ * want the tiling before committing device memory.  which: 0 cam_idx 1 pt_idx (sorted order) 2 pptr 3 tile_obs
+ * 4 tile_pt 5 tile_seg 6 seg_cam 7 seg_begin 8 cam_seg_ptr 9 cam_seg_list (all int32), 10 rank (uint8),
+ * 11 perm (int64; empty when the input was already sorted).  out may be NULL to query the count. */
+typedef struct gb_structure gb_structure;
+int gb_structure_create(const gb_problem_desc *desc, gb_structure **out, char *errbuf, int errlen);
+int gb_structure_destroy(gb_structure *s);
+int gb_structure_info(const gb_structure *s, int64_t info[8]);
+int gb_structure_array(const gb_structure *s, int which, void *out, int64_t *count);
+int gb_structure_hessian(const gb_structure *s, int64_t *colptr, int64_t *rowidx, int64_t *offsets);
+
+/* Sizes: [0]=n_tiles [1]=n_camera_segments [2]=max_track_length [3]=hessian_dim [4]=n_hessian_blocks
+ * [5]=n_hessian_values [6]=device bytes allocated [7]=n_obs */
+int gb_problem_info(const gb_problem *p, int64_t info[8]);
+
+/* Replaces: add_factor(..., obs) (factor.hpp:374-412) / add_vertex (vertex.hpp:240-252) + to_device.
+ * Arrays are in the caller's order; element type is T.  cams [n_cams][9] = [w(3) t(3) f k1 k2]
+ * (examples/bal.cu:118-125), pts [n_pts][3], obs [n_obs][2]. */
+int gb_set_observations(gb_problem *p, const void *obs_host);
+int gb_set_vertices(gb_problem *p, const void *cams_host, const void *pts_host);
+/* Replaces the in-place update through user pointers (docs/markdown/memory.md:4-13): writes back. */
+int gb_get_vertices(gb_problem *p, void *cams_host, void *pts_host);
+
+/* Replaces: Hessian::get_block_col_pointers / row_indices / value_offsets (hessian.hpp:238-248).
+ * colptr [n_blocks+1], rowidx/offsets [n_hessian_blocks]; upper-triangular block CSC, (col,row) sorted. */
+int gb_hessian_structure(const gb_problem *p, int64_t *colptr, int64_t *rowidx, int64_t *offsets);
+
+/* Replaces: Graph::linearize + Graph::chi2 (graph.hpp:228-290): residuals, analytic Jacobians,
+ * Jacobi scales, gradient b = -J~^T r.  chi2 (optional) receives sum r^T r (no 1/2). */
+int gb_linearize(gb_problem *p, double *chi2);
+/* Replaces: Graph::compute_error + chi2 (graph.hpp:221-234). */
+int gb_compute_cost(gb_problem *p, double *chi2);
+/* Parity exports (host, element type T): b and scales [hessian_dim] (graph.hpp:57,67); residuals [n_obs][2]
+ * in the caller's factor order; Jacobians unscaled, column-major 2x9 / 2x3 per factor (as double). */
+int gb_get_gradient(gb_problem *p, void *b_host);
+int gb_get_scales(gb_problem *p, void *scales_host);
+int gb_get_residuals(gb_problem *p, void *r_host);
+int gb_get_jacobians(gb_problem *p, double *Jc_host, double *Jp_host);
+/* Replaces: Hessian::update_values + get_values (hessian.hpp:290-307): scaled, undamped J~^T J in the
+ * reference's value layout (element type S). */
+int gb_hessian_values(gb_problem *p, void *values_host);
+
+typedef struct {
+  int64_t max_iterations;  /* PCGSchurSolver ctor (pcg_schur.hpp:42-45); bal default 10 */
+  double tolerance;        /* 1.0 */
+  double rejection_ratio;  /* 5.0 */
+} gb_pcg_options;
+
+typedef struct {
+  int64_t pcg_iterations;  /* executed */
+  double rz_final;
+  int32_t stop_reason;     /* 0 max_iter, 1 converged, 2 rejected iterate, 3 rz==0, 4 bad denominator */
+  int32_t reserved;
+} gb_solve_info;
+
+/* Replaces: Solver::set_damping_factor (Hessian::apply_damping, hessian.hpp:136-176). */
+int gb_set_damping(gb_problem *p, double mu, int use_identity);
+/* Replaces: PCGSchurSolver::solve (pcg_schur.hpp:79-168) = SchurComplement::update_values
+ * (schur.hpp:227-235, matrix-free here) + BlockJacobiSchurPreconditioner::update_values
+ * (block_jacobi_schur.hpp:114-151) + PCG + compute_landmark_update (schur.hpp:279-302).
+ * delta_host (optional) receives the scaled-space step (element type T). */
+int gb_solve(gb_problem *p, const gb_pcg_options *opt, void *delta_host, gb_solve_info *info);
+/* Parity exports of the reduced system at the current damping (element type T): b_S [9 n_cams]
+ * (schur.hpp:237), diagonal blocks of S [n_cams][81] column-major, and y = S x for a host vector. */
+int gb_get_schur_rhs(gb_problem *p, void *bS_host);
+int gb_get_schur_diagonal(gb_problem *p, void *blocks_host);
+int gb_schur_multiply(gb_problem *p, const void *x_host, void *y_host);
+
+/* Replaces: backup_parameters + apply_update + compute_error + chi2 + compute_rho
+ * (levenberg_marquardt.hpp:174-185): applies the last solve's step, returns the new chi2 and the rho
+ * denominator sum dx(mu dx + b) + 1e-3. */
+int gb_try_step(gb_problem *p, double *new_chi2, double *rho_denominator);
+/* Replaces: Graph::revert_parameters (graph.hpp:311-318). */
+int gb_revert_step(gb_problem *p);
+
+typedef struct {
+  double initial_damping;   /* LevenbergMarquardtOptions (levenberg_marquardt.hpp:52-75) */
+  int64_t iterations;
+  int32_t use_identity;
+  int32_t verbose;
+  gb_pcg_options pcg;
+  const volatile int32_t *stop_flag; /* optional (levenberg_marquardt.hpp:69-70) */
+  /* Continuation (bench warm-up / step-wise drivers): resume != 0 keeps the current linearisation instead of
+   * re-linearising first; initial_nu > 0 replaces the reference's starting nu = 2. */
+  int32_t resume;
+  int32_t profile_product;  /* != 0: CUDA-event time every launch of the matrix-free Schur product kernel */
+  double initial_nu;
+} gb_lm_options;
+
+typedef struct {
+  int64_t iterations;       /* executed */
+  double initial_chi2, final_chi2, final_damping;
+  int64_t accepted, rejected, pcg_iterations_total;
+  double seconds_total;     /* device time of the loop (CUDA events) */
+  double seconds_linearize, seconds_prepare, seconds_pcg, seconds_backsubst, seconds_cost;
+  double final_nu;
+  int64_t product_launches;  /* profile_product: executed launches of k_schur_tiles<MODE 0> and their device time */
+  double product_seconds;
+} gb_lm_result;
+
+/* Replaces: optimizer::levenberg_marquardt (levenberg_marquardt.hpp:109-242).  trajectory (optional,
+ * host, [iterations][4]) receives initial chi2, current chi2, lambda, executed PCG iterations. */
+int gb_lm(gb_problem *p, const gb_lm_options *opt, gb_lm_result *result, double *trajectory);
+
+/* Measurement hooks used by bench.py: number of kernels launched by this context since creation,
+ * and event-timed repetitions of one stage (0 linearize, 1 prepare, 2 one PCG iteration, 3 back-subst +
+ * update, 4 cost) -> average milliseconds per repetition. */
+int64_t gb_kernel_launches(const gb_context *ctx);
+int gb_time_stage(gb_problem *p, int stage, int repetitions, double *ms_avg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAPHITE_B200_H */

@@ -62,6 +62,9 @@ def lib():
         L.orc_lm.restype = C.c_int64
         L.orc_lm.argtypes = [C.c_void_p, C.POINTER(LMOptions), dp]
         L.orc_last_timings.argtypes = [C.c_void_p, dp]
+        L.orc_lm_begin.argtypes = [C.c_void_p, C.POINTER(LMOptions)]
+        L.orc_lm_step.restype = C.c_int
+        L.orc_lm_step.argtypes = [C.c_void_p, C.POINTER(LMOptions), dp]
         _LIB = L
     return _LIB
 
@@ -152,6 +155,15 @@ class Oracle:
         traj = np.zeros((opts.iterations, 4))
         n = self.L.orc_lm(self.h, C.byref(opts), _dp(traj))
         return traj[:n]
+
+    def lm_begin(self, opts=None):
+        self._opts = opts or default_options()
+        self.L.orc_lm_begin(self.h, C.byref(self._opts))
+
+    def lm_step(self):
+        out = np.zeros(4)
+        go = self.L.orc_lm_step(self.h, C.byref(self._opts), _dp(out))
+        return out, bool(go)
 
     def timings(self):
         t = np.zeros(6)

@@ -100,6 +100,13 @@ def run_case(name, prob, solver, precision, iterations, dump=False, lam=1e-4, ti
     return rec
 
 
+def second_run(name, prob):
+    """An extra FP64 run kept as *.run2.json: the reference's own run-to-run spread (float atomics)."""
+    run_case(name, prob, "pcg-schur", "FP64-FP64", 50, timeout=6000)
+    base = os.path.join(OUT, f"{name}__pcg-schur__FP64-FP64")
+    os.replace(base + ".json", base + ".run2.json")
+
+
 def main(which):
     if "fixture" in which:
         p = synthetic.schur_fixture()
@@ -115,14 +122,17 @@ def main(which):
         run_case("ladybug-49", p, "pcg", "FP64-FP64", 50)
     if "trafalgar" in which:
         p = synthetic.make_named("trafalgar-257")
+        second_run("trafalgar-257", p)
         run_case("trafalgar-257", p, "pcg-schur", "FP64-FP64", 50)
         run_case("trafalgar-257", p, "pcg-schur", "FP32-FP32", 50)
         run_case("trafalgar-257", p, "pcg", "FP64-FP32", 50)
     if "dubrovnik" in which:
         p = synthetic.make_named("dubrovnik-356")
+        second_run("dubrovnik-356", p)
         run_case("dubrovnik-356", p, "pcg-schur", "FP64-FP64", 50)
     if "venice" in which:
         p = synthetic.make_named("venice-1778")
+        second_run("venice-1778", p)
         run_case("venice-1778", p, "pcg-schur", "FP64-FP64", 50, timeout=6000)
     # .gbal inputs are regenerated from the seed; do not ship them back
     for f in os.listdir(OUT):

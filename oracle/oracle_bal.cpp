@@ -58,6 +58,8 @@ struct Base {
   virtual int64_t schur_nnz_blocks() = 0;
   virtual int64_t solve(const orc_lm_options *, double, double *) = 0;
   virtual int64_t lm(const orc_lm_options *, double *) = 0;
+  virtual void lm_begin(const orc_lm_options *) = 0;
+  virtual int lm_step(const orc_lm_options *, double *) = 0;
   double tim[6] = {0, 0, 0, 0, 0, 0};
 };
 
@@ -686,54 +688,67 @@ template <typename T> struct Impl : Base {
     return ok ? k : -1;
   }
 
-  // levenberg_marquardt.hpp:109-242
-  int64_t lm(const orc_lm_options *o, double *traj) override {
+  // levenberg_marquardt.hpp:109-242, split into "everything before the loop" and "one loop body"
+  T mu_s = 0, nu_s = 2, chi2_s = 0;
+  bool run_s = true;
+  void lm_begin(const orc_lm_options *o) override {
     set_threads(o->threads);
     for (double &t : tim) t = 0;
-    T mu = (T)o->initial_damping, nu = 2;
+    mu_s = (T)o->initial_damping;
+    nu_s = 2;
     do_linearize();
     build_hessian();
-    T chi2 = compute_error_chi2();
+    chi2_s = compute_error_chi2();
+    run_s = true;
+  }
+  // returns 1 to continue, 0 when the loop would terminate after this iteration
+  int lm_step(const orc_lm_options *o, double *out4) override {
     std::vector<T> dx(dimH);
+    bool ok;
+    const int64_t k = do_solve(o, mu_s, dx.data(), ok);
+    auto t0 = clk::now();
+    cams_bak = cams; pts_bak = pts;
+    // ops/update.hpp:23-30
+    for (int64_t i = 0; i < dimc; i++) cams[i] += dx[i] * scales[i];
+    for (int64_t i = 0; i < 3 * np; i++) pts[i] += dx[dimc + i] * scales[dimc + i];
+    T nchi2 = compute_error_chi2();
+    if (!ok) nchi2 = std::numeric_limits<T>::max();
+    // compute_rho :19-47
+    T num = chi2_s - nchi2, denom = 1.0;
+    if (ok) {
+      T sacc = 0;
+      for (int64_t i = 0; i < dimH; i++) sacc += dx[i] * (mu_s * dx[i] + b[i]);
+      denom = sacc + (T)1.0e-3;
+    }
+    const T rho = num / denom;
+    tim[5] += secs(t0);
+    if (ok && std::isfinite(nchi2) && rho > 0) {
+      double alpha = 1.0 - std::pow(2.0 * rho - 1.0, 3);
+      alpha = std::max(std::min(alpha, 2.0 / 3.0), 1.0 / 3.0);
+      mu_s *= (T)alpha;
+      nu_s = 2;
+      do_linearize();
+      build_hessian();
+    } else {
+      cams = cams_bak; pts = pts_bak;
+      compute_error_chi2();
+      mu_s *= nu_s;
+      nu_s *= 2;
+      nchi2 = chi2_s;
+    }
+    out4[0] = chi2_s; out4[1] = nchi2; out4[2] = mu_s; out4[3] = (double)k;
+    chi2_s = nchi2;
+    if (!std::isfinite(mu_s)) run_s = false;
+    if (rho == 0) return 0;
+    return run_s ? 1 : 0;
+  }
+  int64_t lm(const orc_lm_options *o, double *traj) override {
+    lm_begin(o);
     int64_t it = 0;
-    bool run = true;
-    for (; it < o->iterations && run; it++) {
-      bool ok;
-      const int64_t k = do_solve(o, mu, dx.data(), ok);
-      auto t0 = clk::now();
-      cams_bak = cams; pts_bak = pts;
-      // ops/update.hpp:23-30
-      for (int64_t i = 0; i < dimc; i++) cams[i] += dx[i] * scales[i];
-      for (int64_t i = 0; i < 3 * np; i++) pts[i] += dx[dimc + i] * scales[dimc + i];
-      T nchi2 = compute_error_chi2();
-      if (!ok) nchi2 = std::numeric_limits<T>::max();
-      // compute_rho :19-47
-      T num = chi2 - nchi2, denom = 1.0;
-      if (ok) {
-        T s = 0;
-        for (int64_t i = 0; i < dimH; i++) s += dx[i] * (mu * dx[i] + b[i]);
-        denom = s + (T)1.0e-3;
-      }
-      const T rho = num / denom;
-      tim[5] += secs(t0);
-      if (ok && std::isfinite(nchi2) && rho > 0) {
-        double alpha = 1.0 - std::pow(2.0 * rho - 1.0, 3);
-        alpha = std::max(std::min(alpha, 2.0 / 3.0), 1.0 / 3.0);
-        mu *= (T)alpha;
-        nu = 2;
-        do_linearize();
-        build_hessian();
-      } else {
-        cams = cams_bak; pts = pts_bak;
-        compute_error_chi2();
-        mu *= nu;
-        nu *= 2;
-        nchi2 = chi2;
-      }
-      traj[4 * it + 0] = chi2; traj[4 * it + 1] = nchi2; traj[4 * it + 2] = mu; traj[4 * it + 3] = (double)k;
-      chi2 = nchi2;
-      if (!std::isfinite(mu)) run = false;
-      if (rho == 0) { it++; break; }
+    while (it < o->iterations) {
+      const int go = lm_step(o, traj + 4 * it);
+      it++;
+      if (!go) break;
     }
     return it;
   }
@@ -766,5 +781,7 @@ void orc_schur(orc_problem *h, double mu, int id, double *S, double *bS) { h->im
 int64_t orc_schur_nnz_blocks(orc_problem *h) { return h->impl->schur_nnz_blocks(); }
 int64_t orc_solve(orc_problem *h, const orc_lm_options *o, double mu, double *d) { return h->impl->solve(o, mu, d); }
 int64_t orc_lm(orc_problem *h, const orc_lm_options *o, double *t) { return h->impl->lm(o, t); }
+void orc_lm_begin(orc_problem *h, const orc_lm_options *o) { h->impl->lm_begin(o); }
+int orc_lm_step(orc_problem *h, const orc_lm_options *o, double *out4) { return h->impl->lm_step(o, out4); }
 void orc_last_timings(orc_problem *h, double *t) { for (int i = 0; i < 6; i++) t[i] = h->impl->tim[i]; }
 }

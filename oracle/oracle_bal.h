@@ -62,6 +62,10 @@ int64_t orc_solve(orc_problem *, const orc_lm_options *, double mu, double *delt
 /* levenberg_marquardt.hpp:109-242.  traj: [iterations][4] = initial chi2, current chi2, lambda, pcg iters.
  * Returns the number of iterations executed. */
 int64_t orc_lm(orc_problem *, const orc_lm_options *, double *traj);
+/* The same loop one iteration at a time (bench warm-up / timed split): begin = everything before the loop,
+ * step = one loop body; out4 = initial chi2, current chi2, lambda, pcg iters; returns 0 when the loop ends. */
+void orc_lm_begin(orc_problem *, const orc_lm_options *);
+int orc_lm_step(orc_problem *, const orc_lm_options *, double *out4);
 /* Stage timings of the last orc_lm/orc_solve in seconds: linearize, hessian, schur, pcg, backsubst, update+cost */
 void orc_last_timings(orc_problem *, double *t6);
 

@@ -1,0 +1,171 @@
+"""CPU: the C-ABI library loads and exports every declared symbol; host-side structure build; sharding logic."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden_npz
+from graphite_b200 import binding, synthetic
+from graphite_b200.distributed import partition_by_point, point_ranges
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "graphite_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    L = binding.load_library()
+    names = declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(L, n), f"libgraphite_b200.so does not export {n}"
+    assert sorted(binding.SYMBOLS) == names, "binding.SYMBOLS must list exactly the header's entry points"
+    assert L.gb_version() == 100
+
+
+def test_no_gpu_means_loud_failure(built):
+    """No CPU fallback: without a device the context cannot be created."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(binding.GraphiteB200Error):
+        binding.Context(0)
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under graphite_b200/ may import, link or execute it."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "graphite_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower(), f"{f} mentions the oracle"
+    out = subprocess.run(["ldd", binding.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+
+
+def test_structure_matches_reference_golden(built):
+    prob = synthetic.make_named("ladybug-49")
+    z = golden_npz("ladybug-49__pcg-schur__FP64-FP64.npz")
+    s = binding.host_structure(prob.cam_idx, prob.pt_idx, prob.n_cams, prob.n_pts)
+    cp, ri, off = s["hessian"]
+    assert np.array_equal(cp, z["H_colptr"]) and np.array_equal(ri, z["H_rowidx"]) and np.array_equal(off, z["H_offsets"])
+
+
+@pytest.mark.parametrize("tile", [0, 64, 32])
+def test_tiles_ranks_and_segments(built, tile):
+    prob = synthetic.make_named("ladybug-49")
+    s = binding.host_structure(prob.cam_idx, prob.pt_idx, prob.n_cams, prob.n_pts, tile)
+    T = tile or 256
+    to, tp, tsg = s["tile_obs"], s["tile_pt"], s["tile_seg"]
+    m = prob.n_obs
+    assert to[0] == 0 and to[-1] == m and tp[-1] == prob.n_pts
+    sizes = np.diff(to)
+    assert sizes.min() > 0 and sizes.max() <= T
+    # tiles hold whole points
+    assert np.array_equal(s["pptr"][tp], to)
+    # ranks: a permutation of 0..n-1 inside every tile, sorted by (camera, observation)
+    for k in range(len(sizes)):
+        o0, o1 = to[k], to[k + 1]
+        r = s["rank"][o0:o1].astype(int)
+        assert sorted(r) == list(range(o1 - o0))
+        order = np.empty(o1 - o0, dtype=int); order[r] = np.arange(o1 - o0)
+        cams_sorted = prob.cam_idx[o0:o1][order]
+        assert np.all(np.diff(cams_sorted) >= 0)
+        segs = slice(tsg[k], tsg[k + 1])
+        assert np.array_equal(np.unique(cams_sorted), s["seg_cam"][segs])
+        assert s["seg_begin"][tsg[k]] == o0 and s["seg_begin"][tsg[k + 1]] == o1
+    # camera -> segment CSR lists every segment once, in ascending (tile) order per camera
+    lst, ptr = s["cam_seg_list"], s["cam_seg_ptr"]
+    assert sorted(lst) == list(range(len(s["seg_cam"])))
+    for c in range(prob.n_cams):
+        mine = lst[ptr[c]:ptr[c + 1]]
+        assert np.all(s["seg_cam"][mine] == c) and np.all(np.diff(mine) > 0)
+
+
+def test_unsorted_input_is_sorted_with_a_permutation(built):
+    prob = synthetic.make_named("ladybug-49")
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(prob.n_obs)
+    s = binding.host_structure(prob.cam_idx[perm], prob.pt_idx[perm], prob.n_cams, prob.n_pts)
+    assert np.array_equal(s["cam_idx"], prob.cam_idx) and np.array_equal(s["pt_idx"], prob.pt_idx)
+    assert np.array_equal(perm[s["perm"]], np.arange(prob.n_obs))
+
+
+def test_structure_rejects_what_it_cannot_handle(built):
+    prob = synthetic.schur_fixture()
+    with pytest.raises(binding.GraphiteB200Error, match="no observation"):
+        binding.host_structure(prob.cam_idx, prob.pt_idx, prob.n_cams, prob.n_pts + 1)
+    with pytest.raises(binding.GraphiteB200Error, match="duplicate"):
+        binding.host_structure(np.array([0, 1, 1], dtype=np.int32), np.array([0, 0, 0], dtype=np.int32), 2, 1)
+    with pytest.raises(binding.GraphiteB200Error, match="out of range"):
+        binding.host_structure(np.array([0, 5], dtype=np.int32), np.array([0, 0], dtype=np.int32), 2, 1)
+    with pytest.raises(binding.GraphiteB200Error, match="tile size"):
+        binding.host_structure(np.arange(40, dtype=np.int32), np.zeros(40, dtype=np.int32), 40, 1, 32)
+
+
+def test_point_partition_covers_everything(built):
+    prob = synthetic.make_named("trafalgar-257")
+    for n in (2, 4, 8):
+        rng_ = point_ranges(prob.pt_idx, prob.n_pts, n)
+        assert rng_[0][0] == 0 and rng_[-1][1] == prob.n_pts
+        assert all(a[1] == b[0] for a, b in zip(rng_, rng_[1:]))
+        parts = [partition_by_point(prob, n, r) for r in range(n)]
+        assert sum(p.n_obs for p in parts) == prob.n_obs and sum(p.n_pts for p in parts) == prob.n_pts
+        counts = np.array([p.n_obs for p in parts])
+        assert counts.max() / counts.mean() < 1.02  # balanced by observations
+        for p in parts:
+            assert p.n_cams == prob.n_cams and p.pt_idx.min() == 0 and p.pt_idx.max() == p.n_pts - 1
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch, torch.distributed as dist
+from graphite_b200 import synthetic
+from graphite_b200.distributed import partition_by_point
+from oracle.binding import Oracle
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+prob = synthetic.make_named("ladybug-49")
+local = partition_by_point(prob, world, rank)
+o = Oracle(local)
+chi2, sc, b = o.linearize()
+# what the C library all-reduces: cost and the camera part of the (unscaled) gradient / Hessian diagonal
+jc, jp = Oracle(local).jacobians()
+r, _ = Oracle(local).residuals()
+diag = np.zeros(9 * prob.n_cams); g = np.zeros(9 * prob.n_cams)
+J = jc.reshape(-1, 9, 2)
+np.add.at(diag.reshape(-1, 9), local.cam_idx, (J ** 2).sum(2))
+np.add.at(g.reshape(-1, 9), local.cam_idx, -(J * r[:, None, :]).sum(2))
+t = torch.from_numpy(np.concatenate([[chi2], diag, g]))
+dist.all_reduce(t)
+if rank == 0:
+    full = Oracle(prob)
+    fchi2, fsc, fb = full.linearize()
+    tot = t.numpy()
+    assert abs(tot[0] - fchi2) <= 1e-12 * fchi2
+    n = 9 * prob.n_cams
+    scale = 1.0 / (np.finfo(float).eps + np.sqrt(tot[1:1 + n]))
+    assert np.allclose(scale, fsc[:n], rtol=1e-12)
+    assert np.allclose(scale * tot[1 + n:], fb[:n], rtol=1e-9, atol=1e-9 * np.abs(fb[:n]).max())
+    print("GLOO_OK")
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_sharding_over_gloo(built, tmp_path):
+    """world_size 2 on CPU: the point partition + all-reduce of camera-sized vectors reproduces the full problem."""
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29611", str(script), ROOT]
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert "GLOO_OK" in res.stdout
