@@ -94,10 +94,12 @@ def partition_points(prob, nranks: int, rank: int):
     return partition_by_point(prob, nranks, rank)
 
 
-def algorithmic_bytes(nc, npts, m, nseg, sT, sS):
-    """Bytes one launch of each tile kernel has to move in this layout (DESIGN.md "Kernels")."""
+def algorithmic_bytes(nc, npts, m, nrows, ntiles, sT, sS):
+    """Bytes one launch of the Schur-product kernel has to move in this layout (DESIGN.md "Kernels"):
+    Jacobians 24 values + 4 B packed meta per observation, the per-tile segment/point tables, W per point,
+    camera-vector rows in and partial rows out per (super-tile, camera)."""
     V = 9 * nc * sT
-    product = m * (24 * sS + 9) + npts * 6 * sT + V + nseg * 9 * sT
+    product = m * (24 * sS + 4) + ntiles * (2368 - 1024) + npts * 6 * sT + 2 * nrows * 9 * sT
     # SURVEY section 8(d) K4 implicit, whole PCG iteration, for reference next to it
     survey_k4 = 27 * m * sS + 4 * m + 9 * npts * sS + 81 * nc * sS + 10 * V
     return product, survey_k4
@@ -231,11 +233,11 @@ def main():
 
     # ---- roofline of the dominant kernel (matrix-free Schur product), timed live in the run above ----------
     peak, peak_kind = load_peaks()
-    prod_bytes, survey_k4 = algorithmic_bytes(nc, local.n_pts, info["n_obs"], info["n_camera_segments"], sT, sS)
+    prod_bytes, survey_k4 = algorithmic_bytes(nc, local.n_pts, info["n_obs"], info["n_partial_rows"], info["n_tiles"], sT, sS)
     n_prod = max(int(res["product_launches"]), 1)
     prod_ms = 1e3 * res["product_seconds"] / n_prod
     achieved = prod_bytes / (prod_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_schur_tiles<MODE 0> (matrix-free Schur product, one launch per PCG iteration)",
+    roofline = {"bound": "hbm", "kernel": "k_schur_product (matrix-free Schur product, TMA-staged, one launch per PCG iteration)",
                 "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "bytes_per_launch": prod_bytes, "launches_timed": int(res["product_launches"]), "ms_per_launch": prod_ms,

@@ -32,7 +32,8 @@ SYMBOLS = [
 class ProblemDesc(C.Structure):
     _fields_ = [("precision_T", C.c_int32), ("precision_S", C.c_int32), ("num_cameras", C.c_int64),
                 ("num_points", C.c_int64), ("num_observations", C.c_int64), ("camera_index", C.POINTER(C.c_int32)),
-                ("point_index", C.POINTER(C.c_int32)), ("tile_size", C.c_int32), ("reserved", C.c_int32)]
+                ("point_index", C.POINTER(C.c_int32)), ("tile_size", C.c_int32), ("slot_cap", C.c_int32),
+                ("super_tile_observations", C.c_int64)]
 
 
 class PcgOptions(C.Structure):
@@ -155,7 +156,8 @@ class Context:
 class Problem:
     """One BAL problem on one GPU (one rank's point partition)."""
 
-    def __init__(self, ctx: Context, cam_idx, pt_idx, n_cams: int, n_pts: int, precision: str = "f64-f64", tile_size: int = 0):
+    def __init__(self, ctx: Context, cam_idx, pt_idx, n_cams: int, n_pts: int, precision: str = "f64-f64", tile_size: int = 0,
+                 slot_cap: int = 0, super_tile_observations: int = 0):
         self.ctx, self.L = ctx, ctx.L
         t, s = precision.split("-")
         self.T, self.S = _NP[t], _NP[s]
@@ -166,7 +168,7 @@ class Problem:
         ci = np.ascontiguousarray(cam_idx, dtype=np.int32)
         pi = np.ascontiguousarray(pt_idx, dtype=np.int32)
         d = ProblemDesc(_DT[t], _DT[s], self.n_cams, self.n_pts, self.n_obs, ci.ctypes.data_as(C.POINTER(C.c_int32)),
-                        pi.ctypes.data_as(C.POINTER(C.c_int32)), tile_size, 0)
+                        pi.ctypes.data_as(C.POINTER(C.c_int32)), tile_size, slot_cap, super_tile_observations)
         h = C.c_void_p()
         ctx.check(self.L.gb_problem_create(ctx.h, C.byref(d), C.byref(h)))
         self.h = h
@@ -183,11 +185,9 @@ class Problem:
             pass
 
     def info(self):
-        a = (C.c_int64 * 8)()
+        a = (C.c_int64 * 12)()
         self.ctx.check(self.L.gb_problem_info(self.h, a))
-        keys = ["n_tiles", "n_camera_segments", "max_track", "hessian_dim", "n_hessian_blocks", "n_hessian_values",
-                "device_bytes", "n_obs"]
-        return dict(zip(keys, [int(v) for v in a]))
+        return dict(zip(INFO_KEYS, [int(v) for v in a]))
 
     # ---- data ------------------------------------------------------------------------------------
     def set_observations(self, obs):
@@ -309,24 +309,29 @@ class Problem:
         return v.value
 
 
-def problem_from_bal(ctx: Context, prob, precision="f64-f64", tile_size=0) -> Problem:
-    p = Problem(ctx, prob.cam_idx, prob.pt_idx, prob.n_cams, prob.n_pts, precision, tile_size)
+def problem_from_bal(ctx: Context, prob, precision="f64-f64", tile_size=0, slot_cap=0, super_tile_observations=0) -> Problem:
+    p = Problem(ctx, prob.cam_idx, prob.pt_idx, prob.n_cams, prob.n_pts, precision, tile_size, slot_cap,
+                super_tile_observations)
     p.set_observations(prob.obs)
     p.set_vertices(prob.cams, prob.pts)
     return p
 
 
-STRUCT_ARRAYS = ["cam_idx", "pt_idx", "pptr", "tile_obs", "tile_pt", "tile_seg", "seg_cam", "seg_begin", "cam_seg_ptr",
-                 "cam_seg_list", "rank", "perm"]
+STRUCT_ARRAYS = ["cam_idx", "pt_idx", "pptr", "tile_obs", "tile_pt", "st_tile", "st_row", "row_cam", "cam_row_ptr",
+                 "cam_row_list", "slot_of_obs", "rank", "perm", "ometa", "seg_tab", "pt_tab", "tmeta"]
+_STRUCT_DTYPES = {"rank": np.uint8, "perm": np.int64, "ometa": np.uint32, "seg_tab": np.uint32, "pt_tab": np.uint16}
+INFO_KEYS = ["n_tiles", "n_partial_rows", "max_track", "hessian_dim", "n_hessian_blocks", "n_hessian_values",
+             "device_bytes", "n_obs", "n_super_tiles", "n_camera_segments", "storage_slots", "reserved"]
 
 
-def host_structure(cam_idx, pt_idx, n_cams: int, n_pts: int, tile_size: int = 0):
+def host_structure(cam_idx, pt_idx, n_cams: int, n_pts: int, tile_size: int = 0, slot_cap: int = 0,
+                   super_tile_observations: int = 0):
     """Structure build on the host only (no GPU): dict of arrays + info + Hessian block CSC."""
     L = load_library()
     ci = np.ascontiguousarray(cam_idx, dtype=np.int32)
     pi = np.ascontiguousarray(pt_idx, dtype=np.int32)
     d = ProblemDesc(GB_F64, GB_F64, int(n_cams), int(n_pts), int(len(ci)), ci.ctypes.data_as(C.POINTER(C.c_int32)),
-                    pi.ctypes.data_as(C.POINTER(C.c_int32)), tile_size, 0)
+                    pi.ctypes.data_as(C.POINTER(C.c_int32)), tile_size, slot_cap, super_tile_observations)
     h = C.c_void_p()
     err = C.create_string_buffer(256)
     rc = L.gb_structure_create(C.byref(d), C.byref(h), err, 256)
@@ -337,13 +342,12 @@ def host_structure(cam_idx, pt_idx, n_cams: int, n_pts: int, tile_size: int = 0)
         for i, name in enumerate(STRUCT_ARRAYS):
             n = C.c_int64()
             L.gb_structure_array(h, i, None, C.byref(n))
-            dt = np.uint8 if name == "rank" else (np.int64 if name == "perm" else np.int32)
-            a = np.empty(n.value, dtype=dt)
+            a = np.empty(n.value, dtype=_STRUCT_DTYPES.get(name, np.int32))
             L.gb_structure_array(h, i, _ptr(a), C.byref(n))
-            out[name] = a
-        info = (C.c_int64 * 8)()
+            out[name] = a.reshape(-1, 8) if name == "tmeta" else a
+        info = (C.c_int64 * 12)()
         L.gb_structure_info(h, info)
-        out["info"] = [int(v) for v in info]
+        out["info"] = dict(zip(INFO_KEYS, [int(v) for v in info]))
         nblk = int(n_cams) + int(n_pts)
         nnz = int(n_cams) + len(ci) + int(n_pts)
         cp = np.empty(nblk + 1, dtype=np.int64); ri = np.empty(nnz, dtype=np.int64); off = np.empty(nnz, dtype=np.int64)

@@ -113,14 +113,17 @@ struct ProblemBase {
 template <typename T, typename S> struct Problem : ProblemBase {
   using T2 = typename V2<T>::type;
   using S2 = typename V2<S>::type;
-  TileStruct ts{};
+  static constexpr int NSTAGE = 3; // TMA pipeline depth of the Schur product (fits 227 KB in FP64)
+  DevStruct ts{};
   std::vector<void *> allocs;
   int64_t bytes = 0;
   // state
   T *cams = nullptr, *pts = nullptr, *cams_bak = nullptr, *pts_bak = nullptr;
-  T2 *obs = nullptr, *res = nullptr;
-  S2 *Jc = nullptr, *Jp = nullptr;
+  T2 *obs = nullptr, *res = nullptr, *obs_stage = nullptr; // obs/res per storage slot; stage in caller order
+  const int64_t *d_perm = nullptr;                          // sorted position -> caller index (null = identity)
+  S2 *J = nullptr; // tile-major [ntiles][12][256]
   T *Cg = nullptr, *part18 = nullptr, *part54 = nullptr, *part9 = nullptr, *sums54 = nullptr;
+  T *dot_part = nullptr, *rz_part = nullptr;
   T *diagB = nullptr, *gc = nullptr, *scale = nullptr /*[9Nc+3Np]*/, *b = nullptr /*[9Nc+3Np]*/;
   T *W = nullptr, *h = nullptr;
   T *Sdiag = nullptr, *Minv = nullptr, *bS = nullptr, *dterm = nullptr;
@@ -182,29 +185,40 @@ template <typename T, typename S> struct Problem : ProblemBase {
     dimc = 9 * Nc;
     dimH = 9 * Nc + 3 * Np;
     ts.M = M;
-    ts.Mpad = (M + 31) / 32 * 32;
-    ts.Nc = hs.Nc; ts.Np = hs.Np; ts.ntiles = hs.ntiles(); ts.nseg = hs.nseg();
+    ts.Mstore = hs.Mstore;
+    ts.Nc = hs.Nc; ts.Np = hs.Np; ts.ntiles = hs.ntiles(); ts.nst = hs.nst(); ts.nrows = hs.nrows(); ts.pad = 0;
+    GB_TRY(upload(ts.tmeta, hs.tmeta));
+    GB_TRY(upload(ts.ometa, hs.ometa));
+    GB_TRY(upload(ts.seg_tab, hs.seg_tab));
+    GB_TRY(upload(ts.pt_tab, hs.pt_tab));
+    GB_TRY(upload(ts.trec, hs.trec));
+    GB_TRY(upload(ts.tile_cam, hs.tile_cam));
+    GB_TRY(upload(ts.st_tile, hs.st_tile));
+    GB_TRY(upload(ts.st_row, hs.st_row));
+    GB_TRY(upload(ts.row_cam, hs.row_cam));
+    GB_TRY(upload(ts.cam_row_ptr, hs.cam_row_ptr));
+    GB_TRY(upload(ts.cam_row_list, hs.cam_row_list));
+    GB_TRY(upload(ts.slot_of_obs, hs.slot_of_obs));
     GB_TRY(upload(ts.cam_idx, hs.cam_idx));
     GB_TRY(upload(ts.pt_idx, hs.pt_idx));
-    GB_TRY(upload(ts.rank, hs.rank));
     GB_TRY(upload(ts.pptr, hs.pptr));
-    GB_TRY(upload(ts.tile_obs, hs.tile_obs));
-    GB_TRY(upload(ts.tile_pt, hs.tile_pt));
-    GB_TRY(upload(ts.tile_seg, hs.tile_seg));
-    GB_TRY(upload(ts.seg_cam, hs.seg_cam));
-    GB_TRY(upload(ts.seg_begin, hs.seg_begin));
-    GB_TRY(upload(ts.cam_seg_ptr, hs.cam_seg_ptr));
-    GB_TRY(upload(ts.cam_seg_list, hs.cam_seg_list));
     GB_TRY(dalloc(cams, Nc * CAM_STRIDE)); GB_TRY(dalloc(cams_bak, Nc * CAM_STRIDE));
     GB_TRY(dalloc(pts, 3 * Np)); GB_TRY(dalloc(pts_bak, 3 * Np));
-    GB_TRY(dalloc(obs, M)); GB_TRY(dalloc(res, M));
-    GB_TRY(dalloc(Jc, 9 * ts.Mpad)); GB_TRY(dalloc(Jp, 3 * ts.Mpad));
+    GB_TRY(dalloc(obs, hs.Mstore)); GB_TRY(dalloc(res, hs.Mstore)); GB_TRY(dalloc(obs_stage, M));
+    if (!hs.identity_perm) GB_TRY(upload(d_perm, hs.perm));
+    GB_TRY(dalloc(J, (size_t)NPLANES * hs.Mstore)); // zero-filled: padding slots stay zero for ever
     GB_TRY(dalloc(Cg, 9 * Np));
-    GB_TRY(dalloc(part18, (size_t)ts.nseg * 18)); GB_TRY(dalloc(part54, (size_t)ts.nseg * 54));
-    GB_TRY(dalloc(part9, (size_t)ts.nseg * 9)); GB_TRY(dalloc(sums54, Nc * 54));
+    GB_TRY(dalloc(part18, (size_t)ts.nrows * 18)); GB_TRY(dalloc(part54, (size_t)ts.nrows * 54));
+    GB_TRY(dalloc(part9, (size_t)ts.nrows * 9)); GB_TRY(dalloc(sums54, Nc * 54));
+    GB_TRY(dalloc(dot_part, Nc)); GB_TRY(dalloc(rz_part, Nc));
+    // the super-tile kernels keep their camera accumulator rows in (opt-in sized) dynamic shared memory
+    GB_CUDA(ctx, cudaFuncSetAttribute(k_linearize<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIN * sizeof(T))));
+    GB_CUDA(ctx, cudaFuncSetAttribute(k_prepare_tiles<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_PREP * sizeof(T))));
+    GB_CUDA(ctx, cudaFuncSetAttribute(k_schur_product<T, S, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      SchurSmem<T, S>::TOTAL(NSTAGE)));
     GB_TRY(dalloc(diagB, dimc)); GB_TRY(dalloc(gc, dimc));
     GB_TRY(dalloc(scale, dimH)); GB_TRY(dalloc(b, dimH)); GB_TRY(dalloc(delta, dimH));
-    GB_TRY(dalloc(W, 6 * Np)); GB_TRY(dalloc(h, 3 * Np));
+    GB_TRY(dalloc(W, (size_t)WST<T>::value * Np + 8)); GB_TRY(dalloc(h, 3 * Np));
     GB_TRY(dalloc(Sdiag, Nc * 81)); GB_TRY(dalloc(Minv, Nc * 81));
     GB_TRY(dalloc(bS, dimc)); GB_TRY(dalloc(dterm, dimc));
     GB_TRY(dalloc(x, dimc)); GB_TRY(dalloc(r, dimc)); GB_TRY(dalloc(z, dimc)); GB_TRY(dalloc(pv, dimc));
@@ -242,14 +256,10 @@ template <typename T, typename S> struct Problem : ProblemBase {
 
   // ---- IO ----------------------------------------------------------------------------------------------
   int set_observations(const void *o) override {
-    const T *src = (const T *)o;
-    std::vector<T> tmp;
-    if (!hs.identity_perm) {
-      tmp.resize(2 * hs.M);
-      for (int64_t i = 0; i < hs.M; i++) { tmp[2 * i] = src[2 * hs.perm[i]]; tmp[2 * i + 1] = src[2 * hs.perm[i] + 1]; }
-      src = tmp.data();
-    }
-    GB_CUDA(ctx, cudaMemcpyAsync(obs, src, 2 * hs.M * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    // one H2D copy in the caller's order, then a device scatter into the tile-padded storage slots
+    GB_CUDA(ctx, cudaMemcpyAsync(obs_stage, o, 2 * hs.M * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    k_scatter_slots<T2><<<(unsigned)((hs.M + 255) / 256), 256, 0, ctx->stream>>>(hs.M, ts.slot_of_obs, d_perm, obs_stage, obs);
+    GB_LAUNCH(ctx);
     GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     have_obs = true;
     linearized = prepared = solved = stepped = false;
@@ -283,12 +293,12 @@ template <typename T, typename S> struct Problem : ProblemBase {
 
   int enqueue_linearize() {
     cudaStream_t st = ctx->stream;
-    k_linearize<T, S><<<ts.ntiles, TILE, 0, st>>>(ts, cams, pts, obs, Jc, Jp, res, Cg, part18, cost_part);
+    k_linearize<T, S><<<ts.nst, TILE, SMEM_LIN * sizeof(T), st>>>(ts, cams, pts, obs, J, res, Cg, part18, cost_part);
     GB_LAUNCH(ctx);
     const bool multi = ctx->nranks > 1;
     k_cam_reduce_lin<T><<<ts.Nc, 288, 0, st>>>(ts, part18, diagB, gc, multi ? 0 : 1, scale_on ? 1 : 0, scale, b);
     GB_LAUNCH(ctx);
-    k_sum_partials<<<1, 1024, 0, st>>>(cost_part, ts.ntiles, scalars, 0);
+    k_sum_partials<<<1, 1024, 0, st>>>(cost_part, ts.nst, scalars, 0);
     GB_LAUNCH(ctx);
     if (multi) {
       GB_TRY(allreduce_T(diagB, dimc));
@@ -312,7 +322,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     k_point_prepare<T><<<(ts.Np + 255) / 256, 256, 0, st>>>(ts.Np, scale_on ? 1 : 0, mu, use_identity, Cg, scale + dimc,
                                                            b + dimc, W, h, 0);
     GB_LAUNCH(ctx);
-    k_prepare_tiles<T, S><<<ts.ntiles, TILE, 0, st>>>(ts, Jc, Jp, W, h, part54);
+    k_prepare_tiles<T, S><<<ts.nst, TILE, SMEM_PREP * sizeof(T), st>>>(ts, J, W, h, part54);
     GB_LAUNCH(ctx);
     const bool multi = ctx->nranks > 1;
     k_cam_reduce_prepare<T><<<ts.Nc, 288, 0, st>>>(ts, part54, 0, sums54, multi ? 0 : 1, mu, use_identity, diagB, gc,
@@ -329,8 +339,9 @@ template <typename T, typename S> struct Problem : ProblemBase {
     return GB_OK;
   }
 
-  // y_raw = D (B - E W E^T) D applied to the vector whose scaled copy is in xs
-  int enqueue_schur_product(T *out_raw, const int *flag, int prof_slot = -1) {
+  // Ap_raw = D (B - E W E^T) D v for the vector v whose scaled copy D v is in xs; with `pvec` also
+  // Ap = Ap_raw + dterm pvec and the per-camera partials of pvec.Ap
+  int enqueue_schur_product(const int *flag, const T *pvec, int prof_slot = -1) {
     cudaStream_t st = ctx->stream;
     const bool prof = profiling && prof_slot >= 0;
     if (prof) {
@@ -341,13 +352,20 @@ template <typename T, typename S> struct Problem : ProblemBase {
       }
       GB_CUDA(ctx, cudaEventRecord(prof_ev[2 * prof_slot], st));
     }
-    k_schur_tiles<T, S, 0><<<ts.ntiles, TILE, 0, st>>>(ts, Jc, Jp, W, xs, part9, nullptr, nullptr, nullptr, T(0), nullptr,
-                                                       nullptr, nullptr, nullptr, 0, flag);
+    k_schur_product<T, S, NSTAGE><<<ts.nst, TILE, SchurSmem<T, S>::TOTAL(NSTAGE), st>>>(ts, J, W, xs, part9, flag);
     GB_LAUNCH(ctx);
     if (prof) GB_CUDA(ctx, cudaEventRecord(prof_ev[2 * prof_slot + 1], st));
-    k_cam_reduce_spmv<T><<<ts.Nc, 288, 0, st>>>(ts, part9, scale, out_raw, flag);
+    const bool multi = ctx->nranks > 1;
+    const int finish = (!multi && pvec) ? 1 : 0;
+    k_cam_reduce_spmv<T><<<ts.Nc, 288, 0, st>>>(ts, part9, scale, Ap_raw, finish, dterm, pvec, Ap, dot_part, flag);
     GB_LAUNCH(ctx);
-    GB_TRY(allreduce_T(out_raw, dimc));
+    if (multi) {
+      GB_TRY(allreduce_T(Ap_raw, dimc));
+      if (pvec) {
+        k_dot_partials<T><<<(ts.Nc + 127) / 128, 128, 0, st>>>(ts.Nc, Ap_raw, dterm, pvec, Ap, dot_part, flag);
+        GB_LAUNCH(ctx);
+      }
+    }
     return GB_OK;
   }
 
@@ -356,18 +374,18 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_TRY(ensure_state_cap(o->max_iterations));
     const int gridc = (ts.Nc + PCG_CAMS - 1) / PCG_CAMS;
     GB_CUDA(ctx, cudaMemsetAsync(done_flag, 0, sizeof(int), st));
-    k_pcg_init<T><<<gridc, 288, 0, st>>>(ts.Nc, bS, Minv, scale, x, r, z, pv, xs);
+    k_pcg_init<T><<<gridc, 288, 0, st>>>(ts.Nc, bS, Minv, scale, x, r, z, pv, xs, rz_part);
     GB_LAUNCH(ctx);
-    k_pcg_init_state<T><<<1, 1024, 0, st>>>((int)dimc, r, z, pcg_state);
+    k_pcg_init_state<T><<<1, 1024, 0, st>>>(ts.Nc, rz_part, pcg_state);
     GB_LAUNCH(ctx);
     for (int64_t k = 0; k < o->max_iterations; k++) {
-      GB_TRY(enqueue_schur_product(Ap_raw, done_flag, (int)k));
-      k_pcg_update1<T><<<gridc, 288, 0, st>>>(ts.Nc, pcg_state + 2 * k, pcg_state + 2 * k + 1, Ap_raw, dterm, Minv, Ap, x,
-                                              xbak, r, z, pv, done_flag);
+      GB_TRY(enqueue_schur_product(done_flag, pv, (int)k));
+      k_pcg_update1<T><<<gridc, 288, 0, st>>>(ts.Nc, pcg_state + 2 * k, pcg_state + 2 * k + 1, dot_part, Ap, Minv, x, xbak,
+                                              r, z, pv, rz_part, done_flag);
       GB_LAUNCH(ctx);
       k_pcg_update2<T><<<gridc, 288, 0, st>>>(ts.Nc, pcg_state + 2 * k + 1, pcg_state + 2 * k + 2, (T)o->tolerance,
-                                              (T)o->rejection_ratio, (int)o->max_iterations, scale, x, xbak, r, z, pv, xs,
-                                              done_flag);
+                                              (T)o->rejection_ratio, (int)o->max_iterations, scale, rz_part, x, xbak, z, pv,
+                                              xs, done_flag);
       GB_LAUNCH(ctx);
     }
     GB_CUDA(ctx, cudaMemcpyAsync(h_state, pcg_state + 2 * o->max_iterations, sizeof(PcgState<T>), cudaMemcpyDeviceToHost, st));
@@ -385,8 +403,8 @@ template <typename T, typename S> struct Problem : ProblemBase {
     k_cam_step<T><<<ncamblocks, 256, 0, st>>>((int)dimc, x, scale, b, mu, xs, cams, cams_bak, delta, rho_part + ts.ntiles,
                                               apply ? 1 : 0);
     GB_LAUNCH(ctx);
-    k_schur_tiles<T, S, 1><<<ts.ntiles, TILE, 0, st>>>(ts, Jc, Jp, W, xs, nullptr, h, scale + dimc, b + dimc, mu, pts, pts_bak,
-                                                       delta + dimc, rho_part, apply ? 1 : 0, nullptr);
+    k_backsubst_tiles<T, S><<<ts.ntiles, TILE, 0, st>>>(ts, J, W, xs, h, scale + dimc, b + dimc, mu, pts, pts_bak,
+                                                        delta + dimc, rho_part, apply ? 1 : 0);
     GB_LAUNCH(ctx);
     k_sum_partials<<<1, 1024, 0, st>>>(rho_part, ts.ntiles, scalars, 1);
     GB_LAUNCH(ctx);
@@ -452,27 +470,32 @@ template <typename T, typename S> struct Problem : ProblemBase {
   }
   int get_residuals(void *out) override {
     GB_TRY(require(linearized, "gb_get_residuals before gb_linearize"));
-    if (hs.identity_perm) return d2h(out, res, 2 * hs.M * sizeof(T));
-    std::vector<T> tmp(2 * hs.M);
-    GB_TRY(d2h(tmp.data(), res, 2 * hs.M * sizeof(T)));
+    std::vector<T> tmp(2 * (size_t)hs.Mstore);
+    GB_TRY(d2h(tmp.data(), res, tmp.size() * sizeof(T)));
     T *o = (T *)out;
-    for (int64_t i = 0; i < hs.M; i++) { o[2 * hs.perm[i]] = tmp[2 * i]; o[2 * hs.perm[i] + 1] = tmp[2 * i + 1]; }
+    for (int64_t i = 0; i < hs.M; i++) {
+      const int64_t u = hs.identity_perm ? i : hs.perm[i], sl = hs.slot_of_obs[i];
+      o[2 * u] = tmp[2 * sl];
+      o[2 * u + 1] = tmp[2 * sl + 1];
+    }
     return GB_OK;
   }
   int get_jacobians(double *oc, double *op) override {
     GB_TRY(require(linearized, "gb_get_jacobians before gb_linearize"));
-    std::vector<S> hc(18 * ts.Mpad), hp(6 * ts.Mpad);
-    GB_TRY(d2h(hc.data(), Jc, hc.size() * sizeof(S)));
-    GB_TRY(d2h(hp.data(), Jp, hp.size() * sizeof(S)));
+    std::vector<S> hj(2 * (size_t)NPLANES * hs.Mstore);
+    GB_TRY(d2h(hj.data(), J, hj.size() * sizeof(S)));
     for (int64_t i = 0; i < hs.M; i++) {
-      const int64_t u = hs.identity_perm ? i : hs.perm[i];
+      const int64_t u = hs.identity_perm ? i : hs.perm[i], sl = hs.slot_of_obs[i];
+      const int64_t tile = sl / TILE, t = sl % TILE;
       for (int j = 0; j < 9; j++) {
-        oc[18 * u + 2 * j] = (double)hc[2 * (j * ts.Mpad + i)];
-        oc[18 * u + 2 * j + 1] = (double)hc[2 * (j * ts.Mpad + i) + 1];
+        const int64_t e = ((tile * NPLANES + j) * TILE + t) * 2;
+        oc[18 * u + 2 * j] = (double)hj[e];
+        oc[18 * u + 2 * j + 1] = (double)hj[e + 1];
       }
       for (int j = 0; j < 3; j++) {
-        op[6 * u + 2 * j] = (double)hp[2 * (j * ts.Mpad + i)];
-        op[6 * u + 2 * j + 1] = (double)hp[2 * (j * ts.Mpad + i) + 1];
+        const int64_t e = ((tile * NPLANES + 9 + j) * TILE + t) * 2;
+        op[6 * u + 2 * j] = (double)hj[e];
+        op[6 * u + 2 * j + 1] = (double)hj[e + 1];
       }
     }
     return GB_OK;
@@ -482,14 +505,18 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_TRY(require(ctx->nranks == 1, "gb_hessian_values is single-rank only"));
     const int64_t nv = 81 * (int64_t)hs.Nc + 27 * hs.M + 9 * (int64_t)hs.Np;
     S *vals = nullptr;
+    double *Bacc = nullptr;
     GB_CUDA(ctx, cudaMalloc((void **)&vals, nv * sizeof(S)));
+    GB_CUDA(ctx, cudaMalloc((void **)&Bacc, 81 * (size_t)hs.Nc * sizeof(double)));
+    GB_CUDA(ctx, cudaMemsetAsync(Bacc, 0, 81 * (size_t)hs.Nc * sizeof(double), ctx->stream));
     const int64_t n = std::max<int64_t>(hs.M, hs.Np);
-    k_hessian_EC<T, S><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ts, Jc, Jp, Cg, scale, scale + dimc, vals);
+    k_hessian_export<T, S><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ts, J, Cg, scale, scale + dimc, vals, Bacc);
     GB_LAUNCH(ctx);
-    k_hessian_B<T, S><<<ts.Nc, 96, 0, ctx->stream>>>(ts, Jc, scale, vals);
+    k_copy_B<S><<<(81 * hs.Nc + 255) / 256, 256, 0, ctx->stream>>>(81 * hs.Nc, Bacc, vals);
     GB_LAUNCH(ctx);
     int rc = d2h(out, vals, nv * sizeof(S));
     cudaFree(vals);
+    cudaFree(Bacc);
     return rc;
   }
   int set_damping(double m, int ident) override {
@@ -537,7 +564,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     for (int64_t c = 0; c < hs.Nc; c++)
       for (int k = 0; k < 9; k++) hx[c * CAM_STRIDE + k] = hscale[c * 9 + k] * xi[c * 9 + k];
     GB_CUDA(ctx, cudaMemcpyAsync(xs, hx.data(), hx.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
-    GB_TRY(enqueue_schur_product(Ap_raw, nullptr));
+    GB_TRY(enqueue_schur_product(nullptr, nullptr));
     GB_TRY(d2h(hy.data(), Ap_raw, dimc * sizeof(T)));
     T *yo = (T *)yout;
     for (int64_t i = 0; i < dimc; i++) yo[i] = hy[i] + hd[i] * xi[i];
@@ -687,7 +714,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     if (stage == 2 || stage == 3) {
       // a defined vector in xs / x: one PCG initialisation
       const int gridc = (ts.Nc + PCG_CAMS - 1) / PCG_CAMS;
-      k_pcg_init<T><<<gridc, 288, 0, st>>>(ts.Nc, bS, Minv, scale, x, r, z, pv, xs);
+      k_pcg_init<T><<<gridc, 288, 0, st>>>(ts.Nc, bS, Minv, scale, x, r, z, pv, xs, rz_part);
       GB_LAUNCH(ctx);
     }
     GB_CUDA(ctx, cudaStreamSynchronize(st));
@@ -696,7 +723,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
       switch (stage) {
       case 0: GB_TRY(enqueue_linearize()); break;
       case 1: GB_TRY(enqueue_prepare()); break;
-      case 2: GB_TRY(enqueue_schur_product(Ap_raw, nullptr)); break;
+      case 2: GB_TRY(enqueue_schur_product(nullptr, pv)); break;
       case 3: GB_TRY(enqueue_step(false)); break;
       case 4: GB_TRY(enqueue_cost()); break;
       default: return ctx->fail(GB_ERR_INVALID, "unknown stage %d", stage);
@@ -790,7 +817,7 @@ int gb_problem_create(gb_context *ctx, const gb_problem_desc *d, gb_problem **ou
   else return ctx->fail(GB_ERR_UNSUPPORTED, "precision (T=%d,S=%d) not supported", d->precision_T, d->precision_S);
   impl->ctx = ctx;
   const std::string why = impl->hs.build(d->num_cameras, d->num_points, d->num_observations, d->camera_index,
-                                         d->point_index, d->tile_size);
+                                         d->point_index, d->tile_size, d->slot_cap, d->super_tile_observations);
   if (!why.empty()) {
     delete impl;
     return ctx->fail(GB_ERR_UNSUPPORTED, "structure: %s", why.c_str());
@@ -816,15 +843,19 @@ struct gb_structure {
   gb::HostStructure hs;
 };
 
-static void fill_info(const gb::HostStructure &h, int64_t info[8], int64_t bytes) {
+static void fill_info(const gb::HostStructure &h, int64_t info[12], int64_t bytes) {
   info[0] = h.ntiles();
-  info[1] = h.nseg();
+  info[1] = h.nrows();
   info[2] = h.max_track;
   info[3] = 9 * (int64_t)h.Nc + 3 * (int64_t)h.Np;
   info[4] = (int64_t)h.Nc + h.M + h.Np;
   info[5] = 81 * (int64_t)h.Nc + 27 * h.M + 9 * (int64_t)h.Np;
   info[6] = bytes;
   info[7] = h.M;
+  info[8] = h.nst();
+  info[9] = h.nseg_total;
+  info[10] = h.Mstore;
+  info[11] = 0;
 }
 
 int gb_structure_create(const gb_problem_desc *d, gb_structure **out, char *errbuf, int errlen) {
@@ -832,7 +863,7 @@ int gb_structure_create(const gb_problem_desc *d, gb_structure **out, char *errb
   *out = nullptr;
   gb_structure *s = new gb_structure();
   const std::string why = s->hs.build(d->num_cameras, d->num_points, d->num_observations, d->camera_index,
-                                      d->point_index, d->tile_size);
+                                      d->point_index, d->tile_size, d->slot_cap, d->super_tile_observations);
   if (!why.empty()) {
     if (errbuf && errlen > 0) snprintf(errbuf, errlen, "%s", why.c_str());
     delete s;
@@ -842,7 +873,7 @@ int gb_structure_create(const gb_problem_desc *d, gb_structure **out, char *errb
   return GB_OK;
 }
 int gb_structure_destroy(gb_structure *s) { delete s; return GB_OK; }
-int gb_structure_info(const gb_structure *s, int64_t info[8]) {
+int gb_structure_info(const gb_structure *s, int64_t info[12]) {
   if (!s || !info) return GB_ERR_INVALID;
   fill_info(s->hs, info, 0);
   return GB_OK;
@@ -850,17 +881,29 @@ int gb_structure_info(const gb_structure *s, int64_t info[8]) {
 int gb_structure_array(const gb_structure *s, int which, void *out, int64_t *count) {
   if (!s || !count) return GB_ERR_INVALID;
   const gb::HostStructure &h = s->hs;
-  const std::vector<int32_t> *v32[] = {&h.cam_idx, &h.pt_idx, &h.pptr, &h.tile_obs, &h.tile_pt, &h.tile_seg,
-                                       &h.seg_cam, &h.seg_begin, &h.cam_seg_ptr, &h.cam_seg_list};
-  if (which >= 0 && which < 10) {
+  const std::vector<int32_t> *v32[] = {&h.cam_idx, &h.pt_idx, &h.pptr, &h.tile_obs, &h.tile_pt, &h.st_tile,
+                                       &h.st_row, &h.row_cam, &h.cam_row_ptr, &h.cam_row_list, &h.slot_of_obs};
+  if (which >= 0 && which < 11) {
     *count = (int64_t)v32[which]->size();
     if (out) memcpy(out, v32[which]->data(), v32[which]->size() * sizeof(int32_t));
-  } else if (which == 10) {
+  } else if (which == 11) {
     *count = (int64_t)h.rank.size();
     if (out) memcpy(out, h.rank.data(), h.rank.size());
-  } else if (which == 11) {
+  } else if (which == 12) {
     *count = (int64_t)h.perm.size();
     if (out) memcpy(out, h.perm.data(), h.perm.size() * sizeof(int64_t));
+  } else if (which == 13) {
+    *count = (int64_t)h.ometa.size();
+    if (out) memcpy(out, h.ometa.data(), h.ometa.size() * sizeof(uint32_t));
+  } else if (which == 14) {
+    *count = (int64_t)h.seg_tab.size();
+    if (out) memcpy(out, h.seg_tab.data(), h.seg_tab.size() * sizeof(uint32_t));
+  } else if (which == 15) {
+    *count = (int64_t)h.pt_tab.size();
+    if (out) memcpy(out, h.pt_tab.data(), h.pt_tab.size() * sizeof(uint16_t));
+  } else if (which == 16) {
+    *count = (int64_t)h.tmeta.size() * 8;
+    if (out) memcpy(out, h.tmeta.data(), h.tmeta.size() * sizeof(gb::TileMeta));
   } else {
     return GB_ERR_INVALID;
   }
@@ -872,7 +915,7 @@ int gb_structure_hessian(const gb_structure *s, int64_t *cp, int64_t *ri, int64_
   return GB_OK;
 }
 
-int gb_problem_info(const gb_problem *p, int64_t info[8]) {
+int gb_problem_info(const gb_problem *p, int64_t info[12]) {
   if (!p || !info) return GB_ERR_INVALID;
   fill_info(p->impl->hs, info, p->impl->device_bytes());
   return GB_OK;

@@ -1,22 +1,24 @@
 // kernels.cuh — the sm_100a kernels of the LM inner loop.
 //
-// Layout (HBM).  Observations are sorted by (point, camera) and cut into TILES of whole points with at
-// most TILE (=256) observations; one CTA owns one tile, one thread one observation.  Per observation:
-//   Jc   9 planes of vec2<S>   (plane j = column j of the 2x9 camera Jacobian)   -> fully coalesced
-//   Jp   3 planes of vec2<S>
-//   r    vec2<T>
-// Per point:  Cg[9] = {C00,C01,C02,C11,C12,C22, g0,g1,g2}  (C = sum Jp^T Jp, g = -sum Jp^T r, unscaled),
-//             W[6] (= D_p (D_p C D_p + damping)^-1 D_p), h[3] = W g.
-// Per camera: 10-padded rows (80 B in FP64) so that a gather is five 16-byte loads.
+// Layout (HBM).  Observations are sorted by (point, camera) and cut into TILES of whole points; a tile owns
+// 256 storage slots (slot = tile * 256 + position, unused slots are padding with zero Jacobians), one thread
+// per slot.  Consecutive tiles form a SUPER-TILE owned by one CTA (structure.hpp).
+//   J     tile-major: J[tile][12 planes][256] of vec2<S>; planes 0-8 = columns of the 2x9 camera Jacobian,
+//         planes 9-11 = columns of the 2x3 point Jacobian.  Every plane access is a coalesced 16-byte stream.
+//   r,obs vec2<T> per slot.
+//   per point:  Cg[9] = {C00,C01,C02,C11,C12,C22, g0,g1,g2}  (C = sum Jp^T Jp, g = -sum Jp^T r, unscaled),
+//               W[6] (= D_p (D_p C D_p + damping)^-1 D_p), h[3] = W g.
+//   per camera: 10-padded rows (80 B in FP64) so that a gather is five 16-byte loads.
 //
 // Reductions are atomic-free and deterministic:
-//   by point  - a point's observations are contiguous inside one tile: staged in shared memory,
-//               summed sequentially by one thread per point;
-//   by camera - each tile knows (structure build) the rank of every observation in the tile's
-//               (camera, observation) order and the camera SEGMENTS of that order.  Threads stage their
-//               9-vectors in shared memory at their rank, one thread per (segment, component) sums the
-//               segment, the partial goes to part[segment]; a second kernel sums each camera's partials
-//               in tile order (camera -> segment CSR).
+//   by point  - a point's observations are contiguous inside one tile: staged in shared memory, summed
+//               sequentially by one thread per (point, component);
+//   by camera - the structure build gives every slot its RANK in the tile's (camera, observation) order and the
+//               tile's camera SEGMENTS.  Threads stage their 9-vectors in shared memory at their rank; one
+//               thread per (segment, component) sums the segment and adds it to the super-tile's accumulator
+//               row of that camera in shared memory (exactly one writer per row and tile, tiles in order).
+//               At the end the CTA writes its rows; a per-camera kernel sums the rows of all super-tiles in
+//               ascending order (camera -> row CSR).
 // All arithmetic on the Jacobians is done in the UNSCALED space; the Jacobi scaling of the reference
 // (graph.hpp:254-281) is applied as D_c / D_p on the camera- and point-sized quantities, which is the
 // same algebra: J~ = J D  =>  J~^T J~ = D J^T J D.
@@ -26,11 +28,17 @@
 #include <cuda_runtime.h>
 
 #include "bal_math.cuh"
+#include "structure.hpp"
 
 namespace gb {
 
-constexpr int TILE = 256;
 constexpr int CAM_STRIDE = 10; // padded camera row
+constexpr int NPLANES = 12;
+// dynamic shared memory of the super-tile kernels, in elements of T
+constexpr int SMEM_LIN = TILE * 9 + SLOT_CAP * 18;
+constexpr int SMEM_PREP = TILE * 9 + SLOT_CAP * 54;
+// per-point W row stride: 6 values, padded to 8 in FP32 so that a tile's rows start 16-byte aligned (TMA)
+template <typename T> struct WST { static constexpr int value = sizeof(T) == 4 ? 8 : 6; };
 
 template <typename T> struct V2;
 template <> struct V2<double> {
@@ -42,17 +50,21 @@ template <> struct V2<float> {
   static __device__ __forceinline__ type make(float a, float b) { return make_float2(a, b); }
 };
 
-struct TileStruct {
-  int64_t M, Mpad;
-  int32_t Nc, Np, ntiles, nseg;
-  const int32_t *cam_idx, *pt_idx; // [M]
-  const uint8_t *rank;             // [M] rank of the observation in its tile's (camera, obs) order
-  const int32_t *pptr;             // [Np+1]
-  const int32_t *tile_obs, *tile_pt, *tile_seg; // [ntiles+1]
-  const int32_t *seg_cam;          // [nseg]
-  const int32_t *seg_begin;        // [nseg+1] global sorted position where the segment starts
-  const int32_t *cam_seg_ptr;      // [Nc+1]
-  const int32_t *cam_seg_list;     // [nseg]
+struct DevStruct {
+  int64_t M, Mstore;
+  int32_t Nc, Np, ntiles, nst, nrows, pad;
+  const TileMeta *tmeta;     // [ntiles]
+  const uint32_t *ometa;     // [Mstore]  cslot:16 | rank:8 | point-in-tile:8
+  const uint32_t *seg_tab;   // per tile at seg_off: nseg + 1 entries  begin:16 | cslot:16
+  const uint16_t *pt_tab;    // per tile at pt_off: np + 1 row offsets
+  const unsigned char *trec; // [ntiles][REC_BYTES] packed per-tile record (ometa | seg_tab | pt_tab | meta)
+  const int32_t *tile_cam;   // [Mstore] camera of each storage slot (one-CTA-per-tile kernels)
+  const int32_t *st_tile;    // [nst+1]
+  const int32_t *st_row;     // [nst+1] first partial row of the super-tile
+  const int32_t *row_cam;    // [nrows] camera of each partial row
+  const int32_t *cam_row_ptr, *cam_row_list; // camera -> rows (ascending super-tile)
+  const int32_t *slot_of_obs; // [M] sorted observation -> storage slot (exports)
+  const int32_t *cam_idx, *pt_idx, *pptr;    // sorted observations (exports)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -72,37 +84,36 @@ template <typename T> __device__ __forceinline__ T block_sum(T v, T *sh /*[32]*/
   return tot;
 }
 
-// Stage v[9] at row `rank`, then sum every camera segment of this tile; part row stride = pstride.
+// Stage v[9] at row `rank`, sum every camera segment of the tile and add it to the accumulator row of the
+// segment's camera slot.  acc row stride astride, component offset aoff.
 template <typename T>
-__device__ __forceinline__ void tile_cam_reduce(const T v[9], bool active, int rank, int o0, int sg, int nsg,
-                                                const int32_t *__restrict__ seg_begin, T *sv /*[TILE*9]*/,
-                                                T *__restrict__ part, int pstride, int poff) {
-  if (active) {
+__device__ __forceinline__ void tile_cam_accumulate(const T v[9], int rank, int nseg, const uint32_t *st /*global or shared*/,
+                                                    T *sv /*[TILE*9]*/, T *acc, int astride, int aoff) {
 #pragma unroll
-    for (int k = 0; k < 9; k++) sv[rank * 9 + k] = v[k];
-  }
+  for (int k = 0; k < 9; k++) sv[rank * 9 + k] = v[k];
   __syncthreads();
-  for (int item = threadIdx.x; item < nsg * 9; item += blockDim.x) {
+  for (int item = threadIdx.x; item < nseg * 9; item += TILE) {
     const int s = item / 9, k = item - 9 * s;
-    const int b = seg_begin[sg + s] - o0, e = seg_begin[sg + s + 1] - o0;
-    T acc = T(0);
-    for (int row = b; row < e; row++) acc += sv[row * 9 + k];
-    part[(int64_t)(sg + s) * pstride + poff + k] = acc;
+    const uint32_t e0 = st[s], e1 = st[s + 1];
+    const int b = (int)(e0 >> 16), e = (int)(e1 >> 16), cslot = (int)(e0 & 0xffffu);
+    T a = T(0);
+    for (int row = b; row < e; row++) a += sv[row * 9 + k];
+    acc[cslot * astride + aoff + k] += a;
   }
   __syncthreads();
 }
 
-// Sum the partials of one camera (block per camera, 288 threads = 32 sub-lists x 9 components).
-// out[g*9+k] for g < ngroups; deterministic: sub-list i takes list entries i, i+32, ...; then 0..31 in order.
+// Sum the partial rows of one camera (block per camera, 288 threads = 32 sub-lists x 9 components).
+// out[g*9+k] for g < ngroups; deterministic: sub-list i takes rows i, i+32, ...; then 0..31 in order.
 template <typename T>
-__device__ __forceinline__ void cam_gather(const TileStruct &ts, int c, const T *__restrict__ part, int pstride,
+__device__ __forceinline__ void cam_gather(const DevStruct &ds, int c, const T *__restrict__ part, int pstride,
                                            int ngroups, T *sh /*[32*9]*/, T *out /*smem [ngroups*9]*/) {
   const int sub = threadIdx.x / 9, k = threadIdx.x - 9 * sub;
-  const int b = ts.cam_seg_ptr[c], e = ts.cam_seg_ptr[c + 1];
+  const int b = ds.cam_row_ptr[c], e = ds.cam_row_ptr[c + 1];
   for (int g = 0; g < ngroups; g++) {
     T acc = T(0);
     if (sub < 32)
-      for (int i = b + sub; i < e; i += 32) acc += part[(int64_t)ts.cam_seg_list[i] * pstride + g * 9 + k];
+      for (int i = b + sub; i < e; i += 32) acc += part[(int64_t)ds.cam_row_list[i] * pstride + g * 9 + k];
     __syncthreads();
     if (sub < 32) sh[sub * 9 + k] = acc;
     __syncthreads();
@@ -135,6 +146,23 @@ template <> __device__ __forceinline__ void load_cam<float>(const float *__restr
   }
 }
 
+template <typename T, typename S>
+__device__ __forceinline__ void load_J(const typename V2<S>::type *__restrict__ J, int tile, int t, T *jc, T *jp) {
+  const typename V2<S>::type *base = J + ((int64_t)tile * NPLANES) * TILE + t;
+#pragma unroll
+  for (int j = 0; j < 9; j++) {
+    const typename V2<S>::type v = base[j * TILE];
+    jc[2 * j] = (T)v.x;
+    jc[2 * j + 1] = (T)v.y;
+  }
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const typename V2<S>::type v = base[(9 + j) * TILE];
+    jp[2 * j] = (T)v.x;
+    jp[2 * j + 1] = (T)v.y;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1: factor evaluation + point-side assembly + camera-side partials of diag(B) and g_c
 //     replaces compute_error_kernel / compute_jacobian_kernel / compute_chi2_kernel /
@@ -143,88 +171,95 @@ template <> __device__ __forceinline__ void load_cam<float>(const float *__restr
 // ---------------------------------------------------------------------------------------------
 template <typename T, typename S>
 __global__ void __launch_bounds__(TILE)
-k_linearize(TileStruct ts, const T *__restrict__ cams, const T *__restrict__ pts,
-            const typename V2<T>::type *__restrict__ obs, typename V2<S>::type *__restrict__ Jc,
-            typename V2<S>::type *__restrict__ Jp, typename V2<T>::type *__restrict__ res, T *__restrict__ Cg,
-            T *__restrict__ part /*[nseg][18]*/, double *__restrict__ cost_part) {
-  __shared__ T sv[TILE * 9];
+k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
+            const typename V2<T>::type *__restrict__ obs, typename V2<S>::type *__restrict__ J,
+            typename V2<T>::type *__restrict__ res, T *__restrict__ Cg, T *__restrict__ part /*[nrows][18]*/,
+            double *__restrict__ cost_part /*[nst]*/) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T *sv = reinterpret_cast<T *>(smem_raw); // [TILE*9]
+  T *acc = sv + TILE * 9;                  // [SLOT_CAP*18]
   __shared__ double shd[32];
-  const int tile = blockIdx.x, t = threadIdx.x;
-  const int o0 = ts.tile_obs[tile], n = ts.tile_obs[tile + 1] - o0;
-  const int64_t o = (int64_t)o0 + t;
-  const bool active = t < n;
-  BalObs<T> B;
-  int rank = 0;
+  const int st = blockIdx.x, t = threadIdx.x;
+  const int row0 = ds.st_row[st], nslots = ds.st_row[st + 1] - row0;
+  for (int i = t; i < nslots * 18; i += TILE) acc[i] = T(0);
+  __syncthreads();
   double cost = 0.0;
-  if (active) {
-    const int c = ts.cam_idx[o], p = ts.pt_idx[o];
-    rank = ts.rank[o];
-    T cam[10], X[3], ob[2];
-    load_cam<T>(cams, c, cam);
-    X[0] = pts[3 * (int64_t)p];
-    X[1] = pts[3 * (int64_t)p + 1];
-    X[2] = pts[3 * (int64_t)p + 2];
-    const typename V2<T>::type ov = obs[o];
-    ob[0] = ov.x;
-    ob[1] = ov.y;
-    bal_residual_jacobian<T>(cam, X, ob, B);
+  for (int tile = ds.st_tile[st]; tile < ds.st_tile[st + 1]; tile++) {
+    const TileMeta tm = ds.tmeta[tile];
+    const int64_t slot = (int64_t)tile * TILE + t;
+    const uint32_t om = ds.ometa[slot];
+    const int cslot = (int)(om >> 16), rank = (int)((om >> 8) & 0xffu), ptl = (int)(om & 0xffu);
+    const bool active = t < tm.n;
+    BalObs<T> B;
+    if (active) {
+      const int c = ds.row_cam[row0 + cslot], p = tm.p0 + ptl;
+      T cam[10], X[3], ob[2];
+      load_cam<T>(cams, c, cam);
+      X[0] = pts[3 * (int64_t)p];
+      X[1] = pts[3 * (int64_t)p + 1];
+      X[2] = pts[3 * (int64_t)p + 2];
+      const typename V2<T>::type ov = obs[slot];
+      ob[0] = ov.x;
+      ob[1] = ov.y;
+      bal_residual_jacobian<T>(cam, X, ob, B);
+      typename V2<S>::type *base = J + ((int64_t)tile * NPLANES) * TILE + t;
 #pragma unroll
-    for (int j = 0; j < 9; j++) Jc[(int64_t)j * ts.Mpad + o] = V2<S>::make((S)B.Jc[2 * j], (S)B.Jc[2 * j + 1]);
+      for (int j = 0; j < 9; j++) base[j * TILE] = V2<S>::make((S)B.Jc[2 * j], (S)B.Jc[2 * j + 1]);
 #pragma unroll
-    for (int j = 0; j < 3; j++) Jp[(int64_t)j * ts.Mpad + o] = V2<S>::make((S)B.Jp[2 * j], (S)B.Jp[2 * j + 1]);
-    res[o] = V2<T>::make(B.r[0], B.r[1]);
-    cost = (double)(B.r[0] * B.r[0] + B.r[1] * B.r[1]);
-    // what is stored is what every later kernel reads: keep the assembly consistent with S
+      for (int j = 0; j < 3; j++) base[(9 + j) * TILE] = V2<S>::make((S)B.Jp[2 * j], (S)B.Jp[2 * j + 1]);
+      res[slot] = V2<T>::make(B.r[0], B.r[1]);
+      cost += (double)(B.r[0] * B.r[0] + B.r[1] * B.r[1]);
+      // what is stored is what every later kernel reads: keep the assembly consistent with S
 #pragma unroll
-    for (int j = 0; j < 18; j++) B.Jc[j] = (T)(S)B.Jc[j];
+      for (int j = 0; j < 18; j++) B.Jc[j] = (T)(S)B.Jc[j];
 #pragma unroll
-    for (int j = 0; j < 6; j++) B.Jp[j] = (T)(S)B.Jp[j];
-    // point side: C (6 unique) and g = -Jp^T r
-    T *row = sv + t * 9;
-    row[0] = B.Jp[0] * B.Jp[0] + B.Jp[1] * B.Jp[1];
-    row[1] = B.Jp[0] * B.Jp[2] + B.Jp[1] * B.Jp[3];
-    row[2] = B.Jp[0] * B.Jp[4] + B.Jp[1] * B.Jp[5];
-    row[3] = B.Jp[2] * B.Jp[2] + B.Jp[3] * B.Jp[3];
-    row[4] = B.Jp[2] * B.Jp[4] + B.Jp[3] * B.Jp[5];
-    row[5] = B.Jp[4] * B.Jp[4] + B.Jp[5] * B.Jp[5];
-    row[6] = -(B.Jp[0] * B.r[0] + B.Jp[1] * B.r[1]);
-    row[7] = -(B.Jp[2] * B.r[0] + B.Jp[3] * B.r[1]);
-    row[8] = -(B.Jp[4] * B.r[0] + B.Jp[5] * B.r[1]);
-  }
-  __syncthreads();
-  {
-    const int p0 = ts.tile_pt[tile], npt = ts.tile_pt[tile + 1] - p0;
-    // 9 threads per point: thread (q, k) sums component k of point q sequentially over its observations
-    for (int item = t; item < npt * 9; item += TILE) {
-      const int q = item / 9, k = item - 9 * q;
-      const int b = ts.pptr[p0 + q] - o0, e = ts.pptr[p0 + q + 1] - o0;
-      T acc = T(0);
-      for (int rowi = b; rowi < e; rowi++) acc += sv[rowi * 9 + k];
-      Cg[(int64_t)(p0 + q) * 9 + k] = acc;
+      for (int j = 0; j < 6; j++) B.Jp[j] = (T)(S)B.Jp[j];
+      // point side: C (6 unique) and g = -Jp^T r
+      T *row = sv + t * 9;
+      row[0] = B.Jp[0] * B.Jp[0] + B.Jp[1] * B.Jp[1];
+      row[1] = B.Jp[0] * B.Jp[2] + B.Jp[1] * B.Jp[3];
+      row[2] = B.Jp[0] * B.Jp[4] + B.Jp[1] * B.Jp[5];
+      row[3] = B.Jp[2] * B.Jp[2] + B.Jp[3] * B.Jp[3];
+      row[4] = B.Jp[2] * B.Jp[4] + B.Jp[3] * B.Jp[5];
+      row[5] = B.Jp[4] * B.Jp[4] + B.Jp[5] * B.Jp[5];
+      row[6] = -(B.Jp[0] * B.r[0] + B.Jp[1] * B.r[1]);
+      row[7] = -(B.Jp[2] * B.r[0] + B.Jp[3] * B.r[1]);
+      row[8] = -(B.Jp[4] * B.r[0] + B.Jp[5] * B.r[1]);
     }
+    __syncthreads();
+    {
+      const uint16_t *pt = ds.pt_tab + tm.pt_off;
+      for (int item = t; item < tm.np * 9; item += TILE) {
+        const int q = item / 9, k = item - 9 * q;
+        const int b = pt[q], e = pt[q + 1];
+        T a = T(0);
+        for (int rowi = b; rowi < e; rowi++) a += sv[rowi * 9 + k];
+        Cg[(int64_t)(tm.p0 + q) * 9 + k] = a;
+      }
+    }
+    __syncthreads();
+    T v[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) v[k] = active ? B.Jc[2 * k] * B.Jc[2 * k] + B.Jc[2 * k + 1] * B.Jc[2 * k + 1] : T(0);
+    tile_cam_accumulate<T>(v, rank, tm.nseg, ds.seg_tab + tm.seg_off, sv, acc, 18, 0);
+#pragma unroll
+    for (int k = 0; k < 9; k++) v[k] = active ? -(B.Jc[2 * k] * B.r[0] + B.Jc[2 * k + 1] * B.r[1]) : T(0);
+    tile_cam_accumulate<T>(v, rank, tm.nseg, ds.seg_tab + tm.seg_off, sv, acc, 18, 9);
   }
-  __syncthreads();
-  const int sg = ts.tile_seg[tile], nsg = ts.tile_seg[tile + 1] - sg;
-  T v[9];
-#pragma unroll
-  for (int k = 0; k < 9; k++) v[k] = active ? B.Jc[2 * k] * B.Jc[2 * k] + B.Jc[2 * k + 1] * B.Jc[2 * k + 1] : T(0);
-  tile_cam_reduce<T>(v, active, rank, o0, sg, nsg, ts.seg_begin, sv, part, 18, 0);
-#pragma unroll
-  for (int k = 0; k < 9; k++) v[k] = active ? -(B.Jc[2 * k] * B.r[0] + B.Jc[2 * k + 1] * B.r[1]) : T(0);
-  tile_cam_reduce<T>(v, active, rank, o0, sg, nsg, ts.seg_begin, sv, part, 18, 9);
+  for (int i = t; i < nslots * 18; i += TILE) part[(int64_t)row0 * 18 + i] = acc[i];
   const double tot = block_sum<double>(cost, shd);
-  if (t == 0) cost_part[tile] = tot;
+  if (t == 0) cost_part[st] = tot;
 }
 
 // Camera side of linearize: diag(B), g_c, Jacobi scales s = 1/(eps + sqrt(diag)) (graph.hpp:262-270), b_c = s g_c.
 template <typename T>
 __global__ void __launch_bounds__(288)
-k_cam_reduce_lin(TileStruct ts, const T *__restrict__ part, T *__restrict__ diagB, T *__restrict__ gc,
+k_cam_reduce_lin(DevStruct ds, const T *__restrict__ part, T *__restrict__ diagB, T *__restrict__ gc,
                  int do_finish, int scale_on, T *__restrict__ scale_c, T *__restrict__ b_c) {
   __shared__ T sh[32 * 9];
   __shared__ T out[18];
   const int c = blockIdx.x;
-  cam_gather<T>(ts, c, part, 18, 2, sh, out);
+  cam_gather<T>(ds, c, part, 18, 2, sh, out);
   if (threadIdx.x < 9) {
     const int k = threadIdx.x;
     diagB[c * 9 + k] = out[k];
@@ -247,7 +282,15 @@ __global__ void k_cam_finish_lin(int n, int scale_on, const T *__restrict__ diag
   b_c[i] = s * gc[i];
 }
 
-// Deterministic sum of per-tile partials (single CTA).
+// dst[slot_of[i]] = src[perm ? perm[i] : i]   (observations: caller order -> tile-padded storage slots)
+template <typename V>
+__global__ void k_scatter_slots(int64_t n, const int32_t *__restrict__ slot_of, const int64_t *__restrict__ perm,
+                                const V *__restrict__ src, V *__restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[slot_of[i]] = src[perm ? perm[i] : i];
+}
+
+// Deterministic sum of partials (single CTA).
 __global__ void k_sum_partials(const double *__restrict__ part, int n, double *__restrict__ out, int out_idx) {
   __shared__ double shd[32];
   double acc = 0.0;
@@ -298,54 +341,38 @@ __global__ void k_point_prepare(int Np, int scale_on, T mu, int use_identity, co
   const T id = T(1) / det;
   const T w00 = s0 * s0 * m00 * id, w01 = s0 * s1 * m01 * id, w02 = s0 * s2 * m02 * id;
   const T w11 = s1 * s1 * m11 * id, w12 = s1 * s2 * m12 * id, w22 = s2 * s2 * m22 * id;
-  T *w = W + (int64_t)p * 6;
+  T *w = W + (int64_t)p * WST<T>::value;
   w[0] = w00; w[1] = w01; w[2] = w02; w[3] = w11; w[4] = w12; w[5] = w22;
   h[3 * (int64_t)p] = w00 * g0 + w01 * g1 + w02 * g2;
   h[3 * (int64_t)p + 1] = w01 * g0 + w11 * g1 + w12 * g2;
   h[3 * (int64_t)p + 2] = w02 * g0 + w12 * g1 + w22 * g2;
 }
 
-template <typename T, typename S>
-__device__ __forceinline__ void load_J(const TileStruct &ts, const typename V2<S>::type *__restrict__ Jc,
-                                       const typename V2<S>::type *__restrict__ Jp, int64_t o, T *jc, T *jp) {
-#pragma unroll
-  for (int j = 0; j < 9; j++) {
-    const typename V2<S>::type v = Jc[(int64_t)j * ts.Mpad + o];
-    jc[2 * j] = (T)v.x;
-    jc[2 * j + 1] = (T)v.y;
-  }
-#pragma unroll
-  for (int j = 0; j < 3; j++) {
-    const typename V2<S>::type v = Jp[(int64_t)j * ts.Mpad + o];
-    jp[2 * j] = (T)v.x;
-    jp[2 * j + 1] = (T)v.y;
-  }
-}
-
-// K3b: per tile — camera-side partials of the Schur diagonal blocks and of the reduced right-hand side:
+// K3b: per super-tile — camera-side partials of the Schur diagonal blocks and of the reduced right-hand side:
 //   A_c = sum_o Jc^T (I - N_o) Jc   (N_o = Jp W Jp^T; equals B_c - sum E W E^T restricted to the diagonal)
 //   u_c = sum_o Jc^T Jp h_p
 // replaces execute_schur_multiplication on the diagonal pairs + execute_b_Schur_computation
 // (schur.hpp:649-734, 901-920) and the block copy of block_jacobi_schur.hpp:126-137.
+// Dynamic shared memory: sv[TILE*9] + acc[SLOT_CAP*54] of T.
 template <typename T, typename S>
 __global__ void __launch_bounds__(TILE)
-k_prepare_tiles(TileStruct ts, const typename V2<S>::type *__restrict__ Jc, const typename V2<S>::type *__restrict__ Jp,
-                const T *__restrict__ W, const T *__restrict__ h, T *__restrict__ part /*[nseg][54]*/) {
-  __shared__ T sv[TILE * 9];
-  const int tile = blockIdx.x, t = threadIdx.x;
-  const int o0 = ts.tile_obs[tile], n = ts.tile_obs[tile + 1] - o0;
-  const int64_t o = (int64_t)o0 + t;
-  const bool active = t < n;
-  T jc[18], K[18], q0 = T(0), q1 = T(0);
-  int rank = 0;
-#pragma unroll
-  for (int j = 0; j < 18; j++) { jc[j] = T(0); K[j] = T(0); }
-  if (active) {
-    T jp[6];
-    load_J<T, S>(ts, Jc, Jp, o, jc, jp);
-    rank = ts.rank[o];
-    const int p = ts.pt_idx[o];
-    const T *w = W + (int64_t)p * 6;
+k_prepare_tiles(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *__restrict__ W,
+                const T *__restrict__ h, T *__restrict__ part /*[nrows][54]*/) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T *sv = reinterpret_cast<T *>(smem_raw);
+  T *acc = sv + TILE * 9;
+  const int st = blockIdx.x, t = threadIdx.x;
+  const int row0 = ds.st_row[st], nslots = ds.st_row[st + 1] - row0;
+  for (int i = t; i < nslots * 54; i += TILE) acc[i] = T(0);
+  __syncthreads();
+  for (int tile = ds.st_tile[st]; tile < ds.st_tile[st + 1]; tile++) {
+    const TileMeta tm = ds.tmeta[tile];
+    const uint32_t om = ds.ometa[(int64_t)tile * TILE + t];
+    const int rank = (int)((om >> 8) & 0xffu), ptl = (int)(om & 0xffu);
+    T jc[18], jp[6], K[18];
+    load_J<T, S>(J, tile, t, jc, jp);   // padding slots hold zeros
+    const int p = tm.p0 + ptl;
+    const T *w = W + (int64_t)p * WST<T>::value;
     const T w00 = w[0], w01 = w[1], w02 = w[2], w11 = w[3], w12 = w[4], w22 = w[5];
     // rows of Jp: a = (jp[0], jp[2], jp[4]), b = (jp[1], jp[3], jp[5])
     const T wa0 = w00 * jp[0] + w01 * jp[2] + w02 * jp[4];
@@ -364,29 +391,29 @@ k_prepare_tiles(TileStruct ts, const typename V2<S>::type *__restrict__ Jc, cons
       K[2 * j + 1] = m01 * jc[2 * j] + m11 * jc[2 * j + 1];
     }
     const T *hp = h + (int64_t)p * 3;
-    q0 = jp[0] * hp[0] + jp[2] * hp[1] + jp[4] * hp[2];
-    q1 = jp[1] * hp[0] + jp[3] * hp[1] + jp[5] * hp[2];
-  }
-  const int sg = ts.tile_seg[tile], nsg = ts.tile_seg[tile + 1] - sg;
-  // 45 upper entries A(i,j), i <= j, row-wise: (0,0..8), (1,1..8), ... packed index idx; 5 groups of 9
-  T v[9];
-  int gi = 0, gcount = 0;
+    const T q0 = jp[0] * hp[0] + jp[2] * hp[1] + jp[4] * hp[2];
+    const T q1 = jp[1] * hp[0] + jp[3] * hp[1] + jp[5] * hp[2];
+    // 45 upper entries A(i,j), i <= j, row-wise: (0,0..8), (1,1..8), ... ; 5 groups of 9
+    T v[9];
+    int gi = 0, gcount = 0;
 #pragma unroll
-  for (int i = 0; i < 9; i++) {
+    for (int i = 0; i < 9; i++) {
 #pragma unroll
-    for (int j = i; j < 9; j++) {
-      v[gcount] = jc[2 * i] * K[2 * j] + jc[2 * i + 1] * K[2 * j + 1];
-      gcount++;
-      if (gcount == 9) {
-        tile_cam_reduce<T>(v, active, rank, o0, sg, nsg, ts.seg_begin, sv, part, 54, gi * 9);
-        gcount = 0;
-        gi++;
+      for (int j = i; j < 9; j++) {
+        v[gcount] = jc[2 * i] * K[2 * j] + jc[2 * i + 1] * K[2 * j + 1];
+        gcount++;
+        if (gcount == 9) {
+          tile_cam_accumulate<T>(v, rank, tm.nseg, ds.seg_tab + tm.seg_off, sv, acc, 54, gi * 9);
+          gcount = 0;
+          gi++;
+        }
       }
     }
-  }
 #pragma unroll
-  for (int k = 0; k < 9; k++) v[k] = jc[2 * k] * q0 + jc[2 * k + 1] * q1;
-  tile_cam_reduce<T>(v, active, rank, o0, sg, nsg, ts.seg_begin, sv, part, 54, 45);
+    for (int k = 0; k < 9; k++) v[k] = jc[2 * k] * q0 + jc[2 * k + 1] * q1;
+    tile_cam_accumulate<T>(v, rank, tm.nseg, ds.seg_tab + tm.seg_off, sv, acc, 54, 45);
+  }
+  for (int i = t; i < nslots * 54; i += TILE) part[(int64_t)row0 * 54 + i] = acc[i];
 }
 
 // In-place Gauss-Jordan inverse of a 9x9 matrix in shared memory by one thread (partial pivoting).
@@ -415,13 +442,13 @@ template <typename T> __device__ void invert9(T *A /*[81] col-major*/, T *Ai /*[
   }
 }
 
-// K3c: per camera — sum partials (or take the allreduced sums), scale, damp, invert.
+// K3c: per camera — sum partial rows (or take the allreduced sums), scale, damp, invert.
 //   S~_cc = D A D with diagonal + (damp(B~_kk) - B~_kk);  Minv = S~_cc^-1  (block_jacobi_schur.hpp:139-147)
 //   b_S   = D (g_c - u_c)                                  (schur.hpp:901-920)
 //   dterm = damp(B~_kk) - B~_kk  (added to S p on the diagonal)
 template <typename T>
 __global__ void __launch_bounds__(288)
-k_cam_reduce_prepare(TileStruct ts, const T *__restrict__ part, int from_sums, T *__restrict__ sums /*[Nc][54]*/,
+k_cam_reduce_prepare(DevStruct ds, const T *__restrict__ part, int from_sums, T *__restrict__ sums /*[Nc][54]*/,
                      int finish, T mu, int use_identity, const T *__restrict__ diagB, const T *__restrict__ gc,
                      const T *__restrict__ scale_c, T *__restrict__ Sdiag /*[Nc][81]*/, T *__restrict__ Minv,
                      T *__restrict__ bS, T *__restrict__ dterm) {
@@ -430,7 +457,7 @@ k_cam_reduce_prepare(TileStruct ts, const T *__restrict__ part, int from_sums, T
   __shared__ T A[81], Ai[81];
   const int c = blockIdx.x, t = threadIdx.x;
   if (!from_sums) {
-    cam_gather<T>(ts, c, part, 54, 6, sh, out);
+    cam_gather<T>(ds, c, part, 54, 6, sh, out);
     if (t < 54) sums[(int64_t)c * 54 + t] = out[t];
   } else {
     if (t < 54) out[t] = sums[(int64_t)c * 54 + t];
@@ -460,37 +487,189 @@ k_cam_reduce_prepare(TileStruct ts, const T *__restrict__ part, int from_sums, T
 }
 
 // ---------------------------------------------------------------------------------------------
-// K4: matrix-free Schur product, per tile.  xs = D_c x (10-padded rows).
-//   y_o = Jc x_c ; t_p = sum_o Jp^T y_o ; w_p = W_p t_p ; z_o = Jp w_p ; v_o = Jc^T (y_o - z_o)
-//   part[segment] = sum over the segment of v_o        ( = (B - E W E^T) x restricted to the tile )
-// replaces execute_schur_vector_multiply (schur.hpp:347-393) on an explicit S.
-// mode 1 (back-substitution, schur.hpp:279-302 + ops/update.hpp:9-31): instead of z/v, finish per point
-//   x~_p = (h_p - W_p t_p) / s_p ; delta_p = x~_p s_p ; backup and update the point ; rho partial.
+// TMA (bulk async copy) + mbarrier helpers — sm_90+/sm_100a.  One thread issues, all threads wait on parity.
 // ---------------------------------------------------------------------------------------------
-template <typename T, typename S, int MODE>
-__global__ void __launch_bounds__(TILE)
-k_schur_tiles(TileStruct ts, const typename V2<S>::type *__restrict__ Jc, const typename V2<S>::type *__restrict__ Jp,
-              const T *__restrict__ W, const T *__restrict__ xs, T *__restrict__ part /*[nseg][9]*/,
-              // MODE 1 only:
-              const T *__restrict__ h, const T *__restrict__ scale_p, const T *__restrict__ b_p, T mu,
-              T *__restrict__ pts, T *__restrict__ pts_bak, T *__restrict__ delta_p, double *__restrict__ rho_part,
-              int apply, const int *__restrict__ done_flag) {
-  __shared__ T sv[TILE * 9];
-  __shared__ T sw[TILE * 3];
-  __shared__ double shd[32];
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+// global -> shared bulk copy, completion counted in bytes on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// order generic-proxy accesses to shared memory before later async-proxy (TMA) writes to the same bytes
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// K4: matrix-free Schur product, one CTA per super-tile, tiles streamed through a TMA pipeline.
+//   xs = D_c x (10-padded rows).
+//   y_o = Jc x_c ; t_p = sum_o Jp^T y_o ; w_p = W_p t_p ; z_o = Jp w_p ; v_o = Jc^T (y_o - z_o)
+//   row[camera] += sum over the camera's segment of v_o      ( = (B - E W E^T) x restricted to the super-tile )
+// replaces execute_schur_vector_multiply (schur.hpp:347-393) on an explicit S.
+//
+// Shared memory: NSTAGE stages of {J tile (12 planes x 256 x vec2<S>), packed tile record, W of the tile's
+// points}, each filled by three bulk copies that complete on the stage's mbarrier; the camera vector rows and
+// the accumulator rows of the super-tile's cameras; small staging for the point sums.  The camera staging
+// (256 x 9) reuses the J region of the stage being consumed (its values are in registers by then).
+// While tile i is processed, tiles i+1 .. i+NSTAGE-1 are in flight, independent of the barriers below.
+// ---------------------------------------------------------------------------------------------
+template <typename T, typename S> struct SchurSmem {
+  static constexpr int J_BYTES = NPLANES * TILE * (int)sizeof(typename V2<S>::type);
+  static constexpr int W_BYTES = TILE_PTS * WST<T>::value * (int)sizeof(T);
+  static constexpr int STAGE_BYTES = J_BYTES + REC_BYTES + W_BYTES;
+  static constexpr int XL_OFF(int nstage) { return nstage * STAGE_BYTES; }
+  static constexpr int ACC_OFF(int nstage) { return XL_OFF(nstage) + SLOT_CAP * 9 * (int)sizeof(T); }
+  static constexpr int SV3_OFF(int nstage) { return ACC_OFF(nstage) + SLOT_CAP * 9 * (int)sizeof(T); }
+  static constexpr int SW_OFF(int nstage) { return SV3_OFF(nstage) + TILE * 3 * (int)sizeof(T); }
+  static constexpr int BAR_OFF(int nstage) { return SW_OFF(nstage) + TILE_PTS * 3 * (int)sizeof(T); }
+  static constexpr int TOTAL(int nstage) { return BAR_OFF(nstage) + 64; }
+};
+
+template <typename T, typename S, int NSTAGE>
+__global__ void __launch_bounds__(TILE, 1)
+k_schur_product(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *__restrict__ W,
+                const T *__restrict__ xs, T *__restrict__ part /*[nrows][9]*/, const int *__restrict__ done_flag) {
+  using SM = SchurSmem<T, S>;
+  using S2 = typename V2<S>::type;
+  extern __shared__ __align__(128) unsigned char smem[];
   if (done_flag && *done_flag) return; // PCG already stopped: nothing to do (uniform across the grid)
+  T *xl = reinterpret_cast<T *>(smem + SM::XL_OFF(NSTAGE));
+  T *acc = reinterpret_cast<T *>(smem + SM::ACC_OFF(NSTAGE));
+  T *sv3 = reinterpret_cast<T *>(smem + SM::SV3_OFF(NSTAGE));
+  T *sw = reinterpret_cast<T *>(smem + SM::SW_OFF(NSTAGE));
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM::BAR_OFF(NSTAGE));
+  const int st = blockIdx.x, t = threadIdx.x;
+  const int tile0 = ds.st_tile[st], ntl = ds.st_tile[st + 1] - tile0;
+  const int row0 = ds.st_row[st], nslots = ds.st_row[st + 1] - row0;
+
+  auto issue = [&](int tile, int s) {
+    const TileMeta tm = ds.tmeta[tile];
+    unsigned char *base = smem + s * SM::STAGE_BYTES;
+    const uint32_t wbytes = (uint32_t)(tm.np * WST<T>::value * (int)sizeof(T));
+    mbar_expect_tx(&bars[s], (uint32_t)(SM::J_BYTES + REC_BYTES) + wbytes);
+    bulk_g2s(base, J + (int64_t)tile * NPLANES * TILE, SM::J_BYTES, &bars[s]);
+    bulk_g2s(base + SM::J_BYTES, ds.trec + (int64_t)tile * REC_BYTES, REC_BYTES, &bars[s]);
+    bulk_g2s(base + SM::J_BYTES + REC_BYTES, W + (int64_t)tm.p0 * WST<T>::value, wbytes, &bars[s]);
+  };
+
+  if (t == 0) {
+    for (int s = 0; s < NSTAGE; s++) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+    fence_proxy_async();
+    for (int i = 0; i < NSTAGE && i < ntl; i++) issue(tile0 + i, i);
+  }
+  for (int i = t; i < nslots * 9; i += TILE) {
+    const int s = i / 9, k = i - 9 * s;
+    xl[i] = xs[(int64_t)ds.row_cam[row0 + s] * CAM_STRIDE + k];
+    acc[i] = T(0);
+  }
+  __syncthreads();
+
+  for (int i = 0; i < ntl; i++) {
+    const int s = i % NSTAGE;
+    mbar_wait(&bars[s], (uint32_t)((i / NSTAGE) & 1));
+    unsigned char *base = smem + s * SM::STAGE_BYTES;
+    const S2 *Js = reinterpret_cast<const S2 *>(base);
+    const unsigned char *rec = base + SM::J_BYTES;
+    const T *Ws = reinterpret_cast<const T *>(base + SM::J_BYTES + REC_BYTES);
+    const TileMeta tm = *reinterpret_cast<const TileMeta *>(rec + REC_META);
+    const uint32_t om = reinterpret_cast<const uint32_t *>(rec + REC_OMETA)[t];
+    const int cslot = (int)(om >> 16), rank = (int)((om >> 8) & 0xffu), ptl = (int)(om & 0xffu);
+    T jc[18], jp[6], y0 = T(0), y1 = T(0);
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+      const S2 v = Js[j * TILE + t];
+      jc[2 * j] = (T)v.x;
+      jc[2 * j + 1] = (T)v.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const S2 v = Js[(9 + j) * TILE + t];
+      jp[2 * j] = (T)v.x;
+      jp[2 * j + 1] = (T)v.y;
+    }
+    {
+      const T *x = xl + cslot * 9;
+#pragma unroll
+      for (int j = 0; j < 9; j++) {
+        const T xv = x[j];
+        y0 += jc[2 * j] * xv;
+        y1 += jc[2 * j + 1] * xv;
+      }
+    }
+    sv3[t * 3 + 0] = jp[0] * y0 + jp[1] * y1;
+    sv3[t * 3 + 1] = jp[2] * y0 + jp[3] * y1;
+    sv3[t * 3 + 2] = jp[4] * y0 + jp[5] * y1;
+    __syncthreads(); // also: every thread has its J values in registers, the stage's J region may be reused
+    {
+      const uint16_t *pt = reinterpret_cast<const uint16_t *>(rec + REC_PT);
+      for (int item = t; item < tm.np * 3; item += TILE) {
+        const int q = item / 3, k = item - 3 * q;
+        const int b = pt[q], e = pt[q + 1];
+        T a = T(0);
+        for (int row = b; row < e; row++) a += sv3[row * 3 + k];
+        sw[item] = a;
+      }
+    }
+    __syncthreads();
+    T v[9];
+    {
+      const T t0 = sw[ptl * 3], t1 = sw[ptl * 3 + 1], t2 = sw[ptl * 3 + 2];
+      const T *w = Ws + ptl * WST<T>::value;
+      const T w0 = w[0] * t0 + w[1] * t1 + w[2] * t2;
+      const T w1 = w[1] * t0 + w[3] * t1 + w[4] * t2;
+      const T w2 = w[2] * t0 + w[4] * t1 + w[5] * t2;
+      const T d0 = y0 - (jp[0] * w0 + jp[2] * w1 + jp[4] * w2);
+      const T d1 = y1 - (jp[1] * w0 + jp[3] * w1 + jp[5] * w2);
+#pragma unroll
+      for (int k = 0; k < 9; k++) v[k] = jc[2 * k] * d0 + jc[2 * k + 1] * d1;
+    }
+    T *sv = reinterpret_cast<T *>(base); // camera staging over the consumed J region
+    tile_cam_accumulate<T>(v, rank, tm.nseg, reinterpret_cast<const uint32_t *>(rec + REC_SEG), sv, acc, 9, 0);
+    // the stage is free (all threads passed the barrier at the end of tile_cam_accumulate): refill it
+    if (t == 0 && i + NSTAGE < ntl) {
+      fence_proxy_async();
+      issue(tile0 + i + NSTAGE, s);
+    }
+  }
+  for (int i = t; i < nslots * 9; i += TILE) part[(int64_t)row0 * 9 + i] = acc[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5a: back-substitution + point update, one CTA per tile (schur.hpp:279-302 + ops/update.hpp:9-31):
+//   t_p = sum_o Jp^T Jc (D_c x~_c) ; x~_p = (h_p - W_p t_p) / s_p ; delta_p = x~_p s_p ; rho partial.
+// ---------------------------------------------------------------------------------------------
+template <typename T, typename S>
+__global__ void __launch_bounds__(TILE)
+k_backsubst_tiles(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *__restrict__ W,
+                  const T *__restrict__ xs, const T *__restrict__ h, const T *__restrict__ scale_p,
+                  const T *__restrict__ b_p, T mu, T *__restrict__ pts, T *__restrict__ pts_bak,
+                  T *__restrict__ delta_p, double *__restrict__ rho_part /*[ntiles]*/, int apply) {
+  __shared__ T sv3[TILE * 3];
+  __shared__ double shd[32];
   const int tile = blockIdx.x, t = threadIdx.x;
-  const int o0 = ts.tile_obs[tile], n = ts.tile_obs[tile + 1] - o0;
-  const int64_t o = (int64_t)o0 + t;
-  const bool active = t < n;
-  const int p0 = ts.tile_pt[tile], npt = ts.tile_pt[tile + 1] - p0;
+  const unsigned char *rec = ds.trec + (int64_t)tile * REC_BYTES;
+  const TileMeta tm = *reinterpret_cast<const TileMeta *>(rec + REC_META);
+  const uint32_t om = reinterpret_cast<const uint32_t *>(rec + REC_OMETA)[t];
+  const int c = ds.tile_cam[(int64_t)tile * TILE + t];
   T jc[18], jp[6], y0 = T(0), y1 = T(0);
-  int rank = 0, plocal = 0;
-  if (active) {
-    load_J<T, S>(ts, Jc, Jp, o, jc, jp);
-    const int c = ts.cam_idx[o];
-    plocal = ts.pt_idx[o] - p0;
-    rank = ts.rank[o];
+  load_J<T, S>(J, tile, t, jc, jp);
+  {
     T x[10];
     load_cam<T>(xs, c, x);
 #pragma unroll
@@ -498,81 +677,49 @@ k_schur_tiles(TileStruct ts, const typename V2<S>::type *__restrict__ Jc, const 
       y0 += jc[2 * j] * x[j];
       y1 += jc[2 * j + 1] * x[j];
     }
-    sv[t * 3 + 0] = jp[0] * y0 + jp[1] * y1;
-    sv[t * 3 + 1] = jp[2] * y0 + jp[3] * y1;
-    sv[t * 3 + 2] = jp[4] * y0 + jp[5] * y1;
   }
+  (void)om;
+  sv3[t * 3 + 0] = jp[0] * y0 + jp[1] * y1;
+  sv3[t * 3 + 1] = jp[2] * y0 + jp[3] * y1;
+  sv3[t * 3 + 2] = jp[4] * y0 + jp[5] * y1;
   __syncthreads();
   double rho = 0.0;
-  if (t < npt) {
-    const int p = p0 + t;
-    const int b = ts.pptr[p] - o0, e = ts.pptr[p + 1] - o0;
+  if (t < tm.np) {
+    const uint16_t *pt = reinterpret_cast<const uint16_t *>(rec + REC_PT);
+    const int b = pt[t], e = pt[t + 1];
     T t0 = T(0), t1 = T(0), t2 = T(0);
     for (int row = b; row < e; row++) {
-      t0 += sv[row * 3];
-      t1 += sv[row * 3 + 1];
-      t2 += sv[row * 3 + 2];
+      t0 += sv3[row * 3];
+      t1 += sv3[row * 3 + 1];
+      t2 += sv3[row * 3 + 2];
     }
-    const T *w = W + (int64_t)p * 6;
-    const T w0 = w[0] * t0 + w[1] * t1 + w[2] * t2;
-    const T w1 = w[1] * t0 + w[3] * t1 + w[4] * t2;
-    const T w2 = w[2] * t0 + w[4] * t1 + w[5] * t2;
-    if (MODE == 0) {
-      sw[t * 3] = w0; sw[t * 3 + 1] = w1; sw[t * 3 + 2] = w2;
-    } else {
-      const T wv[3] = {w0, w1, w2};
+    const int p = tm.p0 + t;
+    const T *w = W + (int64_t)p * WST<T>::value;
+    const T wv[3] = {w[0] * t0 + w[1] * t1 + w[2] * t2, w[1] * t0 + w[3] * t1 + w[4] * t2,
+                     w[2] * t0 + w[4] * t1 + w[5] * t2};
 #pragma unroll
-      for (int k = 0; k < 3; k++) {
-        const int64_t i = 3 * (int64_t)p + k;
-        const T s = scale_p[i];
-        const T xt = (h[i] - wv[k]) / s; // scaled-space step of the point
-        delta_p[i] = xt;
-        rho += (double)(xt * (mu * xt + b_p[i]));
-        if (apply) {
-          const T old = pts[i];
-          pts_bak[i] = old;
-          pts[i] = old + xt * s;
-        }
+    for (int k = 0; k < 3; k++) {
+      const int64_t i = 3 * (int64_t)p + k;
+      const T s = scale_p[i];
+      const T xt = (h[i] - wv[k]) / s; // scaled-space step of the point
+      delta_p[i] = xt;
+      rho += (double)(xt * (mu * xt + b_p[i]));
+      if (apply) {
+        const T old = pts[i];
+        pts_bak[i] = old;
+        pts[i] = old + xt * s;
       }
     }
   }
-  if (MODE == 1) {
-    const double tot = block_sum<double>(rho, shd);
-    if (t == 0) rho_part[tile] = tot;
-    return;
-  }
-  __syncthreads();
-  T v[9];
-  if (active) {
-    const T z0 = jp[0] * sw[plocal * 3] + jp[2] * sw[plocal * 3 + 1] + jp[4] * sw[plocal * 3 + 2];
-    const T z1 = jp[1] * sw[plocal * 3] + jp[3] * sw[plocal * 3 + 1] + jp[5] * sw[plocal * 3 + 2];
-    const T d0 = y0 - z0, d1 = y1 - z1;
-#pragma unroll
-    for (int k = 0; k < 9; k++) v[k] = jc[2 * k] * d0 + jc[2 * k + 1] * d1;
-  }
-  __syncthreads(); // sv is reused by the camera reduction
-  const int sg = ts.tile_seg[tile], nsg = ts.tile_seg[tile + 1] - sg;
-  tile_cam_reduce<T>(v, active, rank, o0, sg, nsg, ts.seg_begin, sv, part, 9, 0);
-}
-
-// Camera side of the product: Ap_raw = D_c * sum(partials)   (the damping term is added by the PCG update).
-template <typename T>
-__global__ void __launch_bounds__(288)
-k_cam_reduce_spmv(TileStruct ts, const T *__restrict__ part, const T *__restrict__ scale_c, T *__restrict__ Ap,
-                  const int *__restrict__ done_flag) {
-  __shared__ T sh[32 * 9];
-  __shared__ T out[9];
-  if (done_flag && *done_flag) return;
-  const int c = blockIdx.x;
-  cam_gather<T>(ts, c, part, 9, 1, sh, out);
-  if (threadIdx.x < 9) Ap[c * 9 + threadIdx.x] = scale_c[c * 9 + threadIdx.x] * out[threadIdx.x];
+  const double tot = block_sum<double>(rho, shd);
+  if (t == 0) rho_part[tile] = tot;
 }
 
 // ---------------------------------------------------------------------------------------------
-// PCG on the reduced camera system (solver/pcg_schur.hpp:79-168).  Scalars stay on the device;
-// every CTA recomputes the two dot products in the same fixed order, so all CTAs (and all ranks)
-// take identical decisions without a broadcast.  State is ping-ponged: kernel k reads st[k], CTA 0
-// writes st[k+1].
+// PCG on the reduced camera system (solver/pcg_schur.hpp:79-168).  Scalars stay on the device; the two dot
+// products are per-camera partials summed by every CTA in the same fixed order, so all CTAs (and all ranks)
+// take identical decisions without a broadcast.  State is ping-ponged: kernel k reads st[k], CTA 0 writes
+// st[k+1].
 // ---------------------------------------------------------------------------------------------
 template <typename T> struct PcgState {
   T rz, rz0, alpha, beta, denom;
@@ -581,45 +728,98 @@ template <typename T> struct PcgState {
 
 constexpr int PCG_CAMS = 32; // cameras per CTA (288 threads)
 
-template <typename T> __device__ __forceinline__ T dot_all(const T *a, const T *b, const T *dterm, int n, T *sh) {
-  // sum_i a_i * (b_i + dterm_i a_i); dterm may be null
+template <typename T> __device__ __forceinline__ T sum_all(const T *a, int n, T *sh) {
   T acc = T(0);
-  if (dterm)
-    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += a[i] * (b[i] + dterm[i] * a[i]);
-  else
-    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += a[i] * b[i];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += a[i];
   return block_sum<T>(acc, sh);
 }
 
-// x = 0 ; r = bS ; z = Minv r ; p = z ; xs = D p.
+// Camera side of the product: Ap_raw = D_c * sum(partial rows).  With finish != 0 (single GPU) it also forms
+// Ap = Ap_raw + dterm p and the per-camera partial of p.Ap.
+template <typename T>
+__global__ void __launch_bounds__(288)
+k_cam_reduce_spmv(DevStruct ds, const T *__restrict__ part, const T *__restrict__ scale_c, T *__restrict__ Ap_raw,
+                  int finish, const T *__restrict__ dterm, const T *__restrict__ p, T *__restrict__ Ap,
+                  T *__restrict__ dot_part, const int *__restrict__ done_flag) {
+  __shared__ T sh[32 * 9];
+  __shared__ T out[9];
+  if (done_flag && *done_flag) return;
+  const int c = blockIdx.x;
+  cam_gather<T>(ds, c, part, 9, 1, sh, out);
+  if (threadIdx.x == 0) {
+    T d = T(0);
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+      const T raw = scale_c[c * 9 + k] * out[k];
+      Ap_raw[c * 9 + k] = raw;
+      if (finish) {
+        const T pk = p[c * 9 + k];
+        const T ap = raw + dterm[c * 9 + k] * pk;
+        Ap[c * 9 + k] = ap;
+        d += pk * ap;
+      }
+    }
+    if (finish) dot_part[c] = d;
+  }
+}
+// Multi-GPU: after the allreduce of Ap_raw.
+template <typename T>
+__global__ void k_dot_partials(int Nc, const T *__restrict__ Ap_raw, const T *__restrict__ dterm,
+                               const T *__restrict__ p, T *__restrict__ Ap, T *__restrict__ dot_part,
+                               const int *__restrict__ done_flag) {
+  if (done_flag && *done_flag) return;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Nc) return;
+  T d = T(0);
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    const T pk = p[c * 9 + k];
+    const T ap = Ap_raw[c * 9 + k] + dterm[c * 9 + k] * pk;
+    Ap[c * 9 + k] = ap;
+    d += pk * ap;
+  }
+  dot_part[c] = d;
+}
+
+// x = 0 ; r = bS ; z = Minv r ; p = z ; xs = D p ; rz partial per camera.
 template <typename T>
 __global__ void __launch_bounds__(288)
 k_pcg_init(int Nc, const T *__restrict__ bS, const T *__restrict__ Minv, const T *__restrict__ scale_c,
-           T *__restrict__ x, T *__restrict__ r, T *__restrict__ z, T *__restrict__ p, T *__restrict__ xs) {
-  __shared__ T sr[288];
-  const int t = threadIdx.x, c = blockIdx.x * PCG_CAMS + t / 9, k = t % 9;
+           T *__restrict__ x, T *__restrict__ r, T *__restrict__ z, T *__restrict__ p, T *__restrict__ xs,
+           T *__restrict__ rz_part) {
+  __shared__ T sr[288], sq[288];
+  const int t = threadIdx.x, g = t / 9, c = blockIdx.x * PCG_CAMS + g, k = t - 9 * g;
   const bool ok = c < Nc;
   const int i = c * 9 + k;
   sr[t] = ok ? bS[i] : T(0);
   __syncthreads();
-  if (!ok) return;
   T acc = T(0);
-  const T *m = Minv + (int64_t)c * 81;
-  const T *rc = sr + (t / 9) * 9;
+  if (ok) {
+    const T *m = Minv + (int64_t)c * 81;
+    const T *rc = sr + g * 9;
 #pragma unroll
-  for (int j = 0; j < 9; j++) acc += m[k + 9 * j] * rc[j];
-  x[i] = T(0);
-  r[i] = sr[t];
-  z[i] = acc;
-  p[i] = acc;
-  xs[c * CAM_STRIDE + k] = scale_c[i] * acc;
-  if (k == 0) xs[c * CAM_STRIDE + 9] = T(0);
+    for (int j = 0; j < 9; j++) acc += m[k + 9 * j] * rc[j];
+    x[i] = T(0);
+    r[i] = sr[t];
+    z[i] = acc;
+    p[i] = acc;
+    xs[c * CAM_STRIDE + k] = scale_c[i] * acc;
+    if (k == 0) xs[c * CAM_STRIDE + 9] = T(0);
+  }
+  sq[t] = sr[t] * acc;
+  __syncthreads();
+  if (ok && k == 0) {
+    T d = T(0);
+#pragma unroll
+    for (int j = 0; j < 9; j++) d += sq[g * 9 + j];
+    rz_part[c] = d;
+  }
 }
 template <typename T>
 __global__ void __launch_bounds__(1024)
-k_pcg_init_state(int n, const T *__restrict__ r, const T *__restrict__ z, PcgState<T> *st) {
+k_pcg_init_state(int Nc, const T *__restrict__ rz_part, PcgState<T> *st) {
   __shared__ T sh[32];
-  const T rz = dot_all<T>(r, z, nullptr, n, sh);
+  const T rz = sum_all<T>(rz_part, Nc, sh);
   if (threadIdx.x == 0) {
     PcgState<T> s;
     s.rz = rz; s.rz0 = (T)INFINITY; s.alpha = T(0); s.beta = T(0); s.denom = T(0);
@@ -628,56 +828,62 @@ k_pcg_init_state(int n, const T *__restrict__ r, const T *__restrict__ z, PcgSta
   }
 }
 
-// first half of an iteration (after Ap_raw = S_undamped p): denom, alpha, x/r update, z = Minv r
+// first half of an iteration (Ap and the p.Ap partials are ready): denom, alpha, x/r update, z = Minv r, r.z partials
 template <typename T>
 __global__ void __launch_bounds__(288)
 k_pcg_update1(int Nc, const PcgState<T> *__restrict__ sin, PcgState<T> *__restrict__ sout,
-              const T *__restrict__ Ap_raw, const T *__restrict__ dterm, const T *__restrict__ Minv,
-              T *__restrict__ Ap, T *__restrict__ x, T *__restrict__ xbak, T *__restrict__ r, T *__restrict__ z,
-              const T *__restrict__ p, int *done_flag) {
+              const T *__restrict__ dot_part, const T *__restrict__ Ap, const T *__restrict__ Minv,
+              T *__restrict__ x, T *__restrict__ xbak, T *__restrict__ r, T *__restrict__ z,
+              const T *__restrict__ p, T *__restrict__ rz_part, int *done_flag) {
   __shared__ T sh[32];
-  __shared__ T sr[288];
+  __shared__ T sr[288], sq[288];
   PcgState<T> s = *sin;
+  const bool leader = blockIdx.x == 0 && threadIdx.x == 0;
   if (s.done) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) *sout = s;
+    if (leader) *sout = s;
     return;
   }
-  const int n = Nc * 9;
   if (s.rz == T(0)) { // pcg_schur.hpp:109-111
-    if (blockIdx.x == 0 && threadIdx.x == 0) { s.done = 1; s.reason = 3; *sout = s; *done_flag = 1; }
+    if (leader) { s.done = 1; s.reason = 3; *sout = s; *done_flag = 1; }
     return;
   }
-  const T denom = dot_all<T>(p, Ap_raw, dterm, n, sh);
+  const T denom = sum_all<T>(dot_part, Nc, sh);
   if (denom == T(0) || isnan(denom)) { // :120-122
-    if (blockIdx.x == 0 && threadIdx.x == 0) { s.done = 1; s.reason = 4; s.denom = denom; *sout = s; *done_flag = 1; }
+    if (leader) { s.done = 1; s.reason = 4; s.denom = denom; *sout = s; *done_flag = 1; }
     return;
   }
   const T alpha = s.rz / denom;
-  const int t = threadIdx.x, c = blockIdx.x * PCG_CAMS + t / 9, k = t % 9;
+  const int t = threadIdx.x, g = t / 9, c = blockIdx.x * PCG_CAMS + g, k = t - 9 * g;
   const bool ok = c < Nc;
   const int i = c * 9 + k;
   T rn = T(0);
   if (ok) {
     const T pi = p[i];
-    const T ap = Ap_raw[i] + dterm[i] * pi;
-    Ap[i] = ap;
     const T xo = x[i];
     xbak[i] = xo;
-    x[i] = alpha * pi + xo;   // ops::axpy_async(x, alpha, p, x)
-    rn = -alpha * ap + r[i];  // ops::axpy_async(r, -alpha, Ap, r)
+    x[i] = alpha * pi + xo;      // ops::axpy_async(x, alpha, p, x)
+    rn = -alpha * Ap[i] + r[i];  // ops::axpy_async(r, -alpha, Ap, r)
     r[i] = rn;
   }
   sr[t] = rn;
   __syncthreads();
+  T acc = T(0);
   if (ok) {
-    T acc = T(0);
     const T *m = Minv + (int64_t)c * 81;
-    const T *rc = sr + (t / 9) * 9;
+    const T *rc = sr + g * 9;
 #pragma unroll
     for (int j = 0; j < 9; j++) acc += m[k + 9 * j] * rc[j];
     z[i] = acc;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  sq[t] = rn * acc;
+  __syncthreads();
+  if (ok && k == 0) {
+    T d = T(0);
+#pragma unroll
+    for (int j = 0; j < 9; j++) d += sq[g * 9 + j];
+    rz_part[c] = d;
+  }
+  if (leader) {
     s.alpha = alpha;
     s.denom = denom;
     *sout = s;
@@ -688,21 +894,20 @@ k_pcg_update1(int Nc, const PcgState<T> *__restrict__ sin, PcgState<T> *__restri
 template <typename T>
 __global__ void __launch_bounds__(288)
 k_pcg_update2(int Nc, const PcgState<T> *__restrict__ sin, PcgState<T> *__restrict__ sout, T tol, T ratio,
-              int max_iter, const T *__restrict__ scale_c, T *__restrict__ x, const T *__restrict__ xbak,
-              const T *__restrict__ r, const T *__restrict__ z, T *__restrict__ p, T *__restrict__ xs,
+              int max_iter, const T *__restrict__ scale_c, const T *__restrict__ rz_part, T *__restrict__ x,
+              const T *__restrict__ xbak, const T *__restrict__ z, T *__restrict__ p, T *__restrict__ xs,
               int *done_flag) {
   __shared__ T sh[32];
   PcgState<T> s = *sin;
+  const bool leader = blockIdx.x == 0 && threadIdx.x == 0;
   if (s.done) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) *sout = s;
+    if (leader) *sout = s;
     return;
   }
-  const int n = Nc * 9;
-  const T rzn = dot_all<T>(r, z, nullptr, n, sh);
-  const int t = threadIdx.x, c = blockIdx.x * PCG_CAMS + t / 9, k = t % 9;
+  const T rzn = sum_all<T>(rz_part, Nc, sh);
+  const int t = threadIdx.x, g = t / 9, c = blockIdx.x * PCG_CAMS + g, k = t - 9 * g;
   const bool ok = c < Nc;
   const int i = c * 9 + k;
-  const bool leader = blockIdx.x == 0 && threadIdx.x == 0;
   s.iter += 1;
   if (fabs(rzn) > ratio * s.rz0 || isnan(rzn)) { // :144-148
     if (ok) x[i] = xbak[i];
@@ -752,24 +957,24 @@ __global__ void k_cam_step(int n, const T *__restrict__ x, const T *__restrict__
   if (threadIdx.x == 0) rho_part[blockIdx.x] = tot;
 }
 
-// K5 cost: residual only (graph.hpp:221-234 compute_error + chi2)
+// K5 cost: residual only (graph.hpp:221-234 compute_error + chi2); one CTA per tile
 template <typename T>
 __global__ void __launch_bounds__(TILE)
-k_cost_tiles(TileStruct ts, const T *__restrict__ cams, const T *__restrict__ pts,
-             const typename V2<T>::type *__restrict__ obs, double *__restrict__ cost_part) {
+k_cost_tiles(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
+             const typename V2<T>::type *__restrict__ obs, double *__restrict__ cost_part /*[ntiles]*/) {
   __shared__ double shd[32];
   const int tile = blockIdx.x, t = threadIdx.x;
-  const int o0 = ts.tile_obs[tile], n = ts.tile_obs[tile + 1] - o0;
-  const int64_t o = (int64_t)o0 + t;
+  const TileMeta tm = ds.tmeta[tile];
   double cost = 0.0;
-  if (t < n) {
-    const int c = ts.cam_idx[o], p = ts.pt_idx[o];
+  if (t < tm.n) {
+    const int64_t slot = (int64_t)tile * TILE + t;
+    const int c = ds.tile_cam[slot], p = tm.p0 + (int)(ds.ometa[slot] & 0xffu);
     T cam[10], X[3], ob[2], r[2];
     load_cam<T>(cams, c, cam);
     X[0] = pts[3 * (int64_t)p];
     X[1] = pts[3 * (int64_t)p + 1];
     X[2] = pts[3 * (int64_t)p + 2];
-    const typename V2<T>::type ov = obs[o];
+    const typename V2<T>::type ov = obs[slot];
     ob[0] = ov.x;
     ob[1] = ov.y;
     bal_residual<T>(cam, X, ob, r);
@@ -780,68 +985,50 @@ k_cost_tiles(TileStruct ts, const T *__restrict__ cams, const T *__restrict__ pt
 }
 
 // ---------------------------------------------------------------------------------------------
-// parity exports
+// parity exports (test paths; not timed)
 // ---------------------------------------------------------------------------------------------
 // Scaled, undamped Hessian values in the reference layout (hessian.hpp:257-288):
 // [B_0 .. B_{Nc-1}] then per point [E_{c1,p} E_{c2,p} ... C_p], blocks column-major.
-// E and C per observation / point here; B via k_hessian_B.
+// J~ is rounded to S after scaling (ops/linearize.hpp:176-178) as the reference does.
 template <typename T, typename S>
-__global__ void k_hessian_EC(TileStruct ts, const typename V2<S>::type *__restrict__ Jc,
-                             const typename V2<S>::type *__restrict__ Jp, const T *__restrict__ Cg,
-                             const T *__restrict__ scale_c, const T *__restrict__ scale_p, S *__restrict__ vals) {
+__global__ void k_hessian_export(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *__restrict__ Cg,
+                                 const T *__restrict__ scale_c, const T *__restrict__ scale_p, S *__restrict__ vals,
+                                 double *__restrict__ Bacc /*[Nc][81], zeroed*/) {
   const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (o < ts.M) {
+  if (o < ds.M) {
     T jc[18], jp[6];
-    load_J<T, S>(ts, Jc, Jp, o, jc, jp);
-    const int c = ts.cam_idx[o], p = ts.pt_idx[o];
+    const int slot = ds.slot_of_obs[o];
+    load_J<T, S>(J, slot / TILE, slot % TILE, jc, jp);
+    const int c = ds.cam_idx[o], p = ds.pt_idx[o];
+    T a[18], b[6];
+    for (int i = 0; i < 9; i++) {
+      a[2 * i] = (T)(S)(jc[2 * i] * scale_c[c * 9 + i]);
+      a[2 * i + 1] = (T)(S)(jc[2 * i + 1] * scale_c[c * 9 + i]);
+    }
+    for (int j = 0; j < 3; j++) {
+      b[2 * j] = (T)(S)(jp[2 * j] * scale_p[3 * (int64_t)p + j]);
+      b[2 * j + 1] = (T)(S)(jp[2 * j + 1] * scale_p[3 * (int64_t)p + j]);
+    }
     // offset: 81 Nc + 27 o + 9 p  (every earlier point contributes its E blocks and one C block)
-    S *dst = vals + 81 * (int64_t)ts.Nc + 27 * o + 9 * (int64_t)p;
+    S *dst = vals + 81 * (int64_t)ds.Nc + 27 * o + 9 * (int64_t)p;
     for (int j = 0; j < 3; j++)
-      for (int i = 0; i < 9; i++) {
-        const T a0 = (T)(S)(jc[2 * i] * scale_c[c * 9 + i]), a1 = (T)(S)(jc[2 * i + 1] * scale_c[c * 9 + i]);
-        const T b0 = (T)(S)(jp[2 * j] * scale_p[3 * (int64_t)p + j]), b1 = (T)(S)(jp[2 * j + 1] * scale_p[3 * (int64_t)p + j]);
-        dst[i + 9 * j] = (S)(a0 * b0 + a1 * b1);
-      }
+      for (int i = 0; i < 9; i++) dst[i + 9 * j] = (S)(a[2 * i] * b[2 * j] + a[2 * i + 1] * b[2 * j + 1]);
+    for (int j = 0; j < 9; j++)
+      for (int i = 0; i < 9; i++)
+        atomicAdd(Bacc + (int64_t)c * 81 + i + 9 * j, (double)(a[2 * i] * a[2 * j] + a[2 * i + 1] * a[2 * j + 1]));
   }
-  if (o < ts.Np) {
+  if (o < ds.Np) {
     const int64_t p = o;
     const T *cg = Cg + p * 9;
     const T s[3] = {scale_p[3 * p], scale_p[3 * p + 1], scale_p[3 * p + 2]};
     const T cf[9] = {cg[0], cg[1], cg[2], cg[1], cg[3], cg[4], cg[2], cg[4], cg[5]};
-    S *dst = vals + 81 * (int64_t)ts.Nc + 27 * (int64_t)ts.pptr[p + 1] + 9 * p;
+    S *dst = vals + 81 * (int64_t)ds.Nc + 27 * (int64_t)ds.pptr[p + 1] + 9 * p;
     for (int k = 0; k < 9; k++) dst[k] = (S)(s[k % 3] * s[k / 3] * cf[k]);
   }
 }
-// B blocks: one CTA per camera, gathers through the camera -> segment lists (export only; not a hot path)
-template <typename T, typename S>
-__global__ void k_hessian_B(TileStruct ts, const typename V2<S>::type *__restrict__ Jc, const T *__restrict__ scale_c,
-                            S *__restrict__ vals) {
-  const int c = blockIdx.x, t = threadIdx.x; // 81 threads
-  if (t >= 81) return;
-  const int i = t % 9, j = t / 9;
-  T acc = T(0);
-  for (int q = ts.cam_seg_ptr[c]; q < ts.cam_seg_ptr[c + 1]; q++) {
-    const int s = ts.cam_seg_list[q];
-    // observations of the segment: those whose rank falls in [seg_begin[s], seg_begin[s+1]) — the export walks
-    // the tile to find them (slow, test-only)
-    int lo = 0, hi = ts.ntiles; // tile containing the segment: largest tile with tile_seg <= s
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (ts.tile_seg[mid] <= s) lo = mid; else hi = mid;
-    }
-    const int o0 = ts.tile_obs[lo], n = ts.tile_obs[lo + 1] - o0;
-    const int rb = ts.seg_begin[s] - o0, re = ts.seg_begin[s + 1] - o0;
-    for (int u = 0; u < n; u++) {
-      const int rk = ts.rank[o0 + u];
-      if (rk >= rb && rk < re) {
-        const int64_t o = o0 + u;
-        const typename V2<S>::type a = Jc[(int64_t)i * ts.Mpad + o], b = Jc[(int64_t)j * ts.Mpad + o];
-        const T a0 = (T)a.x, a1 = (T)a.y, b0 = (T)b.x, b1 = (T)b.y;
-        acc += a0 * b0 + a1 * b1;
-      }
-    }
-  }
-  vals[(int64_t)c * 81 + i + 9 * j] = (S)(scale_c[c * 9 + i] * scale_c[c * 9 + j] * acc);
+template <typename S> __global__ void k_copy_B(int n, const double *__restrict__ Bacc, S *__restrict__ vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) vals[i] = (S)Bacc[i];
 }
 
 } // namespace gb

@@ -8,32 +8,76 @@
 //   column c  < Nc : the single diagonal block (c, c)                           -> 81 values
 //   column Nc + p  : blocks (cam, Nc+p) for the point's cameras ascending, then (Nc+p, Nc+p)
 // so no hash maps or coordinate sorts are needed.
+//
+// Execution structure built here (see kernels.cuh):
+//   TILE        256 storage slots = one CTA iteration; a tile holds whole points (<= tile_fill observations),
+//               unused slots are padding with zero Jacobians.  Storage slot = tile * 256 + position.
+//   SUPER-TILE  consecutive tiles owned by one CTA; it keeps one shared-memory accumulator row per distinct
+//               camera it touches (<= slot_cap rows).  Rows of all super-tiles form the "partial rows" that the
+//               per-camera kernels sum in ascending super-tile order (camera -> row CSR).
+//   per slot    packed meta  cslot:16 | rank:8 | point-in-tile:8   (rank = position in the tile's
+//               (camera, observation) order, used to stage values so that camera segments are contiguous)
+//   per tile    segment table (begin:16 | cslot:16) and point offset table.
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <cstring>
 #include <numeric>
 #include <string>
 #include <vector>
 
 namespace gb {
 
+constexpr int TILE = 256;       // storage slots per tile = threads per CTA
+constexpr int SLOT_CAP = 256;   // camera accumulator rows per super-tile
+constexpr int TILE_PTS = 128;   // max points per tile (bounds the per-tile W stage)
+// Packed per-tile record (one TMA bulk copy): ometa[256] u32 | seg_tab[260] u32 | pt_tab[136] u16 | TileMeta
+constexpr int REC_OMETA = 0;
+constexpr int REC_SEG = REC_OMETA + TILE * 4;            // 1024
+constexpr int REC_PT = REC_SEG + (TILE + 4) * 4;         // 2064
+constexpr int REC_META = REC_PT + (TILE_PTS + 8) * 2;    // 2336
+constexpr int REC_BYTES = REC_META + 32;                 // 2368 = 148 * 16
+
+struct TileMeta {
+  int32_t p0;      // first point
+  int32_t n;       // observations in the tile
+  int32_t np;      // points in the tile
+  int32_t nseg;    // camera segments
+  int32_t seg_off; // offset into seg_tab (multiple of 4)
+  int32_t pt_off;  // offset into pt_tab (multiple of 8)
+  int32_t o0;      // sorted observation index of slot 0
+  int32_t pad;
+};
+
 struct HostStructure {
-  int64_t M = 0;
-  int32_t Nc = 0, Np = 0, tile = 256;
+  int64_t M = 0, Mstore = 0;
+  int32_t Nc = 0, Np = 0, tile_fill = TILE, slot_cap = SLOT_CAP;
   bool identity_perm = true;
   std::vector<int64_t> perm;  // sorted position -> caller's factor index (empty when identity)
-  std::vector<int32_t> cam_idx, pt_idx, pptr;
+  std::vector<int32_t> cam_idx, pt_idx, pptr;  // sorted by (point, camera)
+  std::vector<int32_t> tile_obs, tile_pt;      // [ntiles+1] (sorted-observation / point boundaries)
+  std::vector<TileMeta> tmeta;
+  std::vector<uint32_t> ometa;                  // [Mstore]
+  std::vector<uint32_t> seg_tab;
+  std::vector<uint16_t> pt_tab;
+  std::vector<uint8_t> trec;                    // [ntiles][REC_BYTES] packed copy of the three tables + meta
+  std::vector<int32_t> st_tile, st_row, row_cam, cam_row_ptr, cam_row_list, slot_of_obs;
+  std::vector<int32_t> tile_cam;                // [Mstore] camera per storage slot (0 in padding)
+  // per sorted observation (tests / host view): rank in tile order and camera segment count
   std::vector<uint8_t> rank;
-  std::vector<int32_t> tile_obs, tile_pt, tile_seg, seg_cam, seg_begin, cam_seg_ptr, cam_seg_list;
   int32_t max_track = 0;
+  int64_t nseg_total = 0;
 
   // returns an empty string on success, else the reason
-  std::string build(int64_t nc, int64_t np, int64_t m, const int32_t *ci, const int32_t *pi, int tile_size) {
+  std::string build(int64_t nc, int64_t np, int64_t m, const int32_t *ci, const int32_t *pi, int tile_size,
+                    int slot_cap_opt = 0, int64_t st_obs_opt = 0) {
     if (nc <= 0 || np <= 0 || m <= 0) return "empty problem";
-    if (m >= (int64_t(1) << 31) - 1024 || nc + np >= (int64_t(1) << 31)) return "problem too large for 32-bit indices";
-    if (tile_size <= 0) tile_size = 256;
-    if (tile_size > 256) return "tile_size must be <= 256";
-    M = m; Nc = (int32_t)nc; Np = (int32_t)np; tile = tile_size;
+    if (m >= (int64_t(1) << 30) || nc + np >= (int64_t(1) << 31)) return "problem too large for 32-bit indices";
+    if (tile_size <= 0) tile_size = TILE;
+    if (tile_size > TILE) return "tile_size must be <= 256";
+    if (slot_cap_opt <= 0) slot_cap_opt = SLOT_CAP;
+    if (slot_cap_opt > SLOT_CAP) return "slot cap must be <= 256";
+    M = m; Nc = (int32_t)nc; Np = (int32_t)np; tile_fill = tile_size; slot_cap = slot_cap_opt;
     for (int64_t i = 0; i < m; i++)
       if (ci[i] < 0 || ci[i] >= nc || pi[i] < 0 || pi[i] >= np) return "observation index out of range";
     bool sorted = true;
@@ -64,20 +108,21 @@ struct HostStructure {
       max_track = std::max(max_track, pptr[p + 1]);
       pptr[p + 1] += pptr[p];
     }
-    if (max_track > tile) return "a point has more observations than the tile size (" + std::to_string(max_track) + ")";
+    if (max_track > tile_fill) return "a point has more observations than the tile size (" + std::to_string(max_track) + ")";
+    if (max_track > slot_cap) return "a point has more observations than the slot cap (" + std::to_string(max_track) + ")";
     {
       std::vector<uint8_t> seen((size_t)nc, 0);
       for (int64_t i = 0; i < m; i++) seen[cam_idx[i]] = 1;
       for (int64_t c = 0; c < nc; c++)
         if (!seen[c]) return "a camera has no observation (unused vertices are not supported)";
     }
-    // tiles of whole points
+    // ---- tiles of whole points ----------------------------------------------------------------------
     tile_obs.clear(); tile_pt.clear();
     tile_obs.push_back(0); tile_pt.push_back(0);
     int32_t cur = 0;
     for (int32_t p = 0; p < Np; p++) {
       const int32_t t = pptr[p + 1] - pptr[p];
-      if (cur + t > tile) {
+      if (cur + t > tile_fill || p - tile_pt.back() >= TILE_PTS) {
         tile_obs.push_back(pptr[p]); tile_pt.push_back(p);
         cur = 0;
       }
@@ -85,39 +130,116 @@ struct HostStructure {
     }
     tile_obs.push_back((int32_t)m); tile_pt.push_back(Np);
     const int32_t nt = (int32_t)tile_obs.size() - 1;
-    // per-tile (camera, observation) order -> rank and camera segments
-    rank.resize(m);
-    tile_seg.assign((size_t)nt + 1, 0);
-    seg_cam.clear(); seg_begin.clear();
-    std::vector<std::pair<int32_t, int32_t>> loc;
-    for (int32_t k = 0; k < nt; k++) {
-      const int32_t o0 = tile_obs[k], n = tile_obs[k + 1] - o0;
-      loc.resize(n);
-      for (int32_t u = 0; u < n; u++) loc[u] = {cam_idx[o0 + u], u};
-      std::sort(loc.begin(), loc.end());
-      tile_seg[k] = (int32_t)seg_cam.size();
-      for (int32_t u = 0; u < n; u++) {
-        rank[o0 + loc[u].second] = (uint8_t)u;
-        if (u == 0 || loc[u].first != loc[u - 1].first) {
-          seg_cam.push_back(loc[u].first);
-          seg_begin.push_back(o0 + u);
+    Mstore = (int64_t)nt * TILE;
+    if (Mstore >= (int64_t(1) << 31)) return "problem too large for 32-bit slot indices";
+    // ---- super-tiles: consecutive tiles, bounded observation count and distinct cameras ----------------
+    int64_t st_obs = st_obs_opt > 0 ? st_obs_opt : std::max<int64_t>(TILE, m / (148 * 8));
+    st_tile.clear(); st_row.clear(); row_cam.clear();
+    std::vector<int32_t> stamp((size_t)nc, -1), local((size_t)nc, 0);
+    std::vector<int32_t> tile_st((size_t)nt, 0);
+    {
+      int32_t k = 0;
+      while (k < nt) {
+        const int32_t s = (int32_t)st_tile.size();
+        st_tile.push_back(k);
+        st_row.push_back((int32_t)row_cam.size());
+        std::vector<int32_t> cams_here;
+        int64_t obs_here = 0;
+        while (k < nt) {
+          // distinct cameras this tile would add
+          std::vector<int32_t> add;
+          for (int32_t o = tile_obs[k]; o < tile_obs[k + 1]; o++) {
+            const int32_t c = cam_idx[o];
+            if (stamp[c] != s) { stamp[c] = s; add.push_back(c); }
+          }
+          if (!cams_here.empty() && ((int32_t)(cams_here.size() + add.size()) > slot_cap || obs_here >= st_obs)) {
+            for (int32_t c : add) stamp[c] = -1; // undo: the tile starts the next super-tile
+            break;
+          }
+          if ((int32_t)add.size() > slot_cap) return "a tile touches more cameras than the slot cap";
+          cams_here.insert(cams_here.end(), add.begin(), add.end());
+          obs_here += tile_obs[k + 1] - tile_obs[k];
+          tile_st[k] = s;
+          k++;
         }
+        std::sort(cams_here.begin(), cams_here.end());
+        row_cam.insert(row_cam.end(), cams_here.begin(), cams_here.end());
+      }
+      st_tile.push_back(nt);
+      st_row.push_back((int32_t)row_cam.size());
+    }
+    const int32_t nst = (int32_t)st_tile.size() - 1;
+    // ---- per-tile tables ----------------------------------------------------------------------------------
+    tmeta.assign((size_t)nt, TileMeta{});
+    ometa.assign((size_t)Mstore, 0u);
+    rank.assign((size_t)m, 0);
+    slot_of_obs.resize(m);
+    tile_cam.assign((size_t)Mstore, 0);
+    seg_tab.clear(); pt_tab.clear();
+    nseg_total = 0;
+    std::vector<std::pair<int32_t, int32_t>> loc;
+    for (int32_t s = 0; s < nst; s++) {
+      for (int32_t r = st_row[s]; r < st_row[s + 1]; r++) local[row_cam[r]] = r - st_row[s];
+      for (int32_t k = st_tile[s]; k < st_tile[s + 1]; k++) {
+        const int32_t o0 = tile_obs[k], n = tile_obs[k + 1] - o0;
+        const int32_t p0 = tile_pt[k], npt = tile_pt[k + 1] - p0;
+        TileMeta &tm = tmeta[k];
+        tm.p0 = p0; tm.n = n; tm.np = npt; tm.o0 = o0; tm.pad = 0;
+        loc.resize(n);
+        for (int32_t u = 0; u < n; u++) loc[u] = {cam_idx[o0 + u], u};
+        std::sort(loc.begin(), loc.end());
+        tm.seg_off = (int32_t)seg_tab.size();
+        int32_t nseg = 0;
+        for (int32_t u = 0; u < n; u++) {
+          const int32_t pos = loc[u].second;
+          rank[o0 + pos] = (uint8_t)u;
+          const uint32_t cslot = (uint32_t)local[loc[u].first];
+          const uint32_t ptl = (uint32_t)(pt_idx[o0 + pos] - p0);
+          ometa[(size_t)k * TILE + pos] = (cslot << 16) | ((uint32_t)u << 8) | ptl;
+          slot_of_obs[o0 + pos] = k * TILE + pos;
+          tile_cam[(size_t)k * TILE + pos] = loc[u].first;
+          if (u == 0 || loc[u].first != loc[u - 1].first) {
+            seg_tab.push_back(((uint32_t)u << 16) | cslot);
+            nseg++;
+          }
+        }
+        // padding slots: unique ranks n..TILE-1 (their rows are never read), camera slot 0, point 0
+        for (int32_t u = n; u < TILE; u++) ometa[(size_t)k * TILE + u] = ((uint32_t)u << 8);
+        tm.nseg = nseg;
+        nseg_total += nseg;
+        seg_tab.push_back(((uint32_t)n << 16)); // sentinel: end of the last segment
+        while (seg_tab.size() % 4) seg_tab.push_back(((uint32_t)n << 16));
+        tm.pt_off = (int32_t)pt_tab.size();
+        for (int32_t q = 0; q <= npt; q++) pt_tab.push_back((uint16_t)(pptr[p0 + q] - o0));
+        while (pt_tab.size() % 8) pt_tab.push_back((uint16_t)n);
       }
     }
-    tile_seg[nt] = (int32_t)seg_cam.size();
-    seg_begin.push_back((int32_t)m);
-    const int32_t ns = (int32_t)seg_cam.size();
-    cam_seg_ptr.assign((size_t)nc + 1, 0);
-    for (int32_t s = 0; s < ns; s++) cam_seg_ptr[seg_cam[s] + 1]++;
-    for (int64_t c = 0; c < nc; c++) cam_seg_ptr[c + 1] += cam_seg_ptr[c];
-    cam_seg_list.resize(ns);
-    std::vector<int32_t> fill(cam_seg_ptr.begin(), cam_seg_ptr.end() - 1);
-    for (int32_t s = 0; s < ns; s++) cam_seg_list[fill[seg_cam[s]]++] = s; // ascending tile order per camera
+    // ---- packed per-tile records ----------------------------------------------------------------------------
+    trec.assign((size_t)nt * REC_BYTES, 0);
+    for (int32_t k = 0; k < nt; k++) {
+      uint8_t *rec = trec.data() + (size_t)k * REC_BYTES;
+      const TileMeta &tm = tmeta[k];
+      memcpy(rec + REC_OMETA, ometa.data() + (size_t)k * TILE, TILE * 4);
+      uint32_t *sg = reinterpret_cast<uint32_t *>(rec + REC_SEG);
+      for (int32_t i = 0; i < TILE + 4; i++) sg[i] = i <= tm.nseg ? seg_tab[tm.seg_off + i] : ((uint32_t)tm.n << 16);
+      uint16_t *pt = reinterpret_cast<uint16_t *>(rec + REC_PT);
+      for (int32_t i = 0; i < TILE_PTS + 8; i++) pt[i] = i <= tm.np ? pt_tab[tm.pt_off + i] : (uint16_t)tm.n;
+      memcpy(rec + REC_META, &tm, sizeof(TileMeta));
+    }
+    // ---- camera -> partial rows, ascending super-tile order ------------------------------------------------
+    const int32_t nrows = (int32_t)row_cam.size();
+    cam_row_ptr.assign((size_t)nc + 1, 0);
+    for (int32_t r = 0; r < nrows; r++) cam_row_ptr[row_cam[r] + 1]++;
+    for (int64_t c = 0; c < nc; c++) cam_row_ptr[c + 1] += cam_row_ptr[c];
+    cam_row_list.resize(nrows);
+    std::vector<int32_t> fill(cam_row_ptr.begin(), cam_row_ptr.end() - 1);
+    for (int32_t r = 0; r < nrows; r++) cam_row_list[fill[row_cam[r]]++] = r;
     return "";
   }
 
   int32_t ntiles() const { return (int32_t)tile_obs.size() - 1; }
-  int32_t nseg() const { return (int32_t)seg_cam.size(); }
+  int32_t nst() const { return (int32_t)st_tile.size() - 1; }
+  int32_t nrows() const { return (int32_t)row_cam.size(); }
 
   // Upper block-CSC of the Hessian in the reference's order (hessian.hpp:59-84, 270-278; csc_utils.hpp:16-50).
   void hessian_structure(int64_t *colptr, int64_t *rowidx, int64_t *offsets) const {

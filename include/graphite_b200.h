@@ -62,8 +62,9 @@ typedef struct {
   int64_t num_observations;  /* observations of those points */
   const int32_t *camera_index; /* host [num_observations] */
   const int32_t *point_index;  /* host [num_observations], local point index */
-  int32_t tile_size;         /* 0 = default (256) */
-  int32_t reserved;
+  int32_t tile_size;         /* max observations per tile, 0 = default (256, the storage tile) */
+  int32_t slot_cap;          /* max distinct cameras per super-tile, 0 = default (256) */
+  int64_t super_tile_observations; /* target observations per super-tile (one CTA), 0 = default M / (148*8) */
 } gb_problem_desc;
 
 /* Replaces: Graph::initialize_optimization + build_structure (graph.hpp:92-219),
@@ -77,18 +78,20 @@ int gb_problem_destroy(gb_problem *p);
 
 /* Host-only view of the same structure build (no GPU needed): used by the CPU test-suite and by callers that
  * want the tiling before committing device memory.  which: 0 cam_idx 1 pt_idx (sorted order) 2 pptr 3 tile_obs
- * 4 tile_pt 5 tile_seg 6 seg_cam 7 seg_begin 8 cam_seg_ptr 9 cam_seg_list (all int32), 10 rank (uint8),
- * 11 perm (int64; empty when the input was already sorted).  out may be NULL to query the count. */
+ * 4 tile_pt 5 st_tile 6 st_row 7 row_cam 8 cam_row_ptr 9 cam_row_list 10 slot_of_obs (all int32), 11 rank (uint8),
+ * 12 perm (int64; empty when the input was already sorted), 13 ometa (uint32) 14 seg_tab (uint32) 15 pt_tab (uint16)
+ * 16 tile meta (8 x int32 per tile).  out may be NULL to query the count. */
 typedef struct gb_structure gb_structure;
 int gb_structure_create(const gb_problem_desc *desc, gb_structure **out, char *errbuf, int errlen);
 int gb_structure_destroy(gb_structure *s);
-int gb_structure_info(const gb_structure *s, int64_t info[8]);
+int gb_structure_info(const gb_structure *s, int64_t info[12]);
 int gb_structure_array(const gb_structure *s, int which, void *out, int64_t *count);
 int gb_structure_hessian(const gb_structure *s, int64_t *colptr, int64_t *rowidx, int64_t *offsets);
 
-/* Sizes: [0]=n_tiles [1]=n_camera_segments [2]=max_track_length [3]=hessian_dim [4]=n_hessian_blocks
- * [5]=n_hessian_values [6]=device bytes allocated [7]=n_obs */
-int gb_problem_info(const gb_problem *p, int64_t info[8]);
+/* Sizes: [0]=n_tiles [1]=n_partial_rows (super-tile x camera) [2]=max_track_length [3]=hessian_dim
+ * [4]=n_hessian_blocks [5]=n_hessian_values [6]=device bytes allocated [7]=n_obs [8]=n_super_tiles
+ * [9]=n_camera_segments (tile x camera) [10]=storage slots [11]=0 */
+int gb_problem_info(const gb_problem *p, int64_t info[12]);
 
 /* Replaces: add_factor(..., obs) (factor.hpp:374-412) / add_vertex (vertex.hpp:240-252) + to_device.
  * Arrays are in the caller's order; element type is T.  cams [n_cams][9] = [w(3) t(3) f k1 k2]

@@ -57,35 +57,58 @@ def test_structure_matches_reference_golden(built):
     assert np.array_equal(cp, z["H_colptr"]) and np.array_equal(ri, z["H_rowidx"]) and np.array_equal(off, z["H_offsets"])
 
 
-@pytest.mark.parametrize("tile", [0, 64, 32])
-def test_tiles_ranks_and_segments(built, tile):
+@pytest.mark.parametrize("tile,cap,st_obs", [(0, 0, 0), (64, 0, 0), (32, 40, 500), (0, 64, 2000)])
+def test_tiles_ranks_segments_and_super_tiles(built, tile, cap, st_obs):
     prob = synthetic.make_named("ladybug-49")
-    s = binding.host_structure(prob.cam_idx, prob.pt_idx, prob.n_cams, prob.n_pts, tile)
-    T = tile or 256
-    to, tp, tsg = s["tile_obs"], s["tile_pt"], s["tile_seg"]
-    m = prob.n_obs
+    s = binding.host_structure(prob.cam_idx, prob.pt_idx, prob.n_cams, prob.n_pts, tile, cap, st_obs)
+    fill, capv = tile or 256, cap or 256
+    to, tp, tm = s["tile_obs"], s["tile_pt"], s["tmeta"]
+    m, nt = prob.n_obs, len(s["tile_obs"]) - 1
     assert to[0] == 0 and to[-1] == m and tp[-1] == prob.n_pts
     sizes = np.diff(to)
-    assert sizes.min() > 0 and sizes.max() <= T
-    # tiles hold whole points
-    assert np.array_equal(s["pptr"][tp], to)
-    # ranks: a permutation of 0..n-1 inside every tile, sorted by (camera, observation)
-    for k in range(len(sizes)):
-        o0, o1 = to[k], to[k + 1]
-        r = s["rank"][o0:o1].astype(int)
-        assert sorted(r) == list(range(o1 - o0))
-        order = np.empty(o1 - o0, dtype=int); order[r] = np.arange(o1 - o0)
-        cams_sorted = prob.cam_idx[o0:o1][order]
-        assert np.all(np.diff(cams_sorted) >= 0)
-        segs = slice(tsg[k], tsg[k + 1])
-        assert np.array_equal(np.unique(cams_sorted), s["seg_cam"][segs])
-        assert s["seg_begin"][tsg[k]] == o0 and s["seg_begin"][tsg[k + 1]] == o1
-    # camera -> segment CSR lists every segment once, in ascending (tile) order per camera
-    lst, ptr = s["cam_seg_list"], s["cam_seg_ptr"]
-    assert sorted(lst) == list(range(len(s["seg_cam"])))
+    assert sizes.min() > 0 and sizes.max() <= fill
+    assert np.array_equal(s["pptr"][tp], to), "tiles hold whole points"
+    assert s["info"]["storage_slots"] == nt * 256 and len(s["ometa"]) == nt * 256
+    # storage slots: tile-padded, observation i of tile k at k*256 + (i - tile start)
+    exp_slot = np.concatenate([k * 256 + np.arange(sizes[k]) for k in range(nt)])
+    assert np.array_equal(s["slot_of_obs"], exp_slot)
+    st_tile, st_row, row_cam = s["st_tile"], s["st_row"], s["row_cam"]
+    assert st_tile[0] == 0 and st_tile[-1] == nt and np.all(np.diff(st_tile) > 0)
+    assert np.diff(st_row).max() <= capv
+    nseg = 0
+    for sidx in range(len(st_tile) - 1):
+        rows = row_cam[st_row[sidx]:st_row[sidx + 1]]
+        assert np.all(np.diff(rows) > 0), "rows of a super-tile: its distinct cameras, ascending"
+        o0, o1 = to[st_tile[sidx]], to[st_tile[sidx + 1]]
+        assert np.array_equal(np.unique(prob.cam_idx[o0:o1]), rows)
+        for k in range(st_tile[sidx], st_tile[sidx + 1]):
+            p0, n, npt, ns, seg_off, pt_off, o0k, _ = tm[k]
+            assert (p0, n, npt, o0k) == (tp[k], sizes[k], tp[k + 1] - tp[k], to[k])
+            om = s["ometa"][k * 256:(k + 1) * 256]
+            cslot, rank, ptl = om >> 16, (om >> 8) & 0xff, om & 0xff
+            assert sorted(rank.tolist()) == list(range(256)), "ranks are a permutation of the 256 slots"
+            assert np.array_equal(rank[:n], s["rank"][to[k]:to[k + 1]])
+            assert np.array_equal(rows[cslot[:n]], prob.cam_idx[to[k]:to[k + 1]])
+            assert np.array_equal(ptl[:n] + p0, prob.pt_idx[to[k]:to[k + 1]])
+            order = np.empty(n, dtype=int); order[rank[:n]] = np.arange(n)
+            cams_sorted = prob.cam_idx[to[k]:to[k + 1]][order]
+            assert np.all(np.diff(cams_sorted) >= 0)
+            seg = s["seg_tab"][seg_off:seg_off + ns + 1]
+            begins, slots = seg >> 16, seg & 0xffff
+            heads = np.flatnonzero(np.diff(cams_sorted, prepend=-1) != 0)
+            assert np.array_equal(begins[:ns], heads) and begins[ns] == n
+            assert np.array_equal(rows[slots[:ns]], cams_sorted[heads])
+            assert seg_off % 4 == 0 and pt_off % 8 == 0
+            pt = s["pt_tab"][pt_off:pt_off + npt + 1]
+            assert np.array_equal(pt, s["pptr"][p0:p0 + npt + 1] - to[k])
+            nseg += ns
+    assert nseg == s["info"]["n_camera_segments"]
+    # camera -> partial rows CSR lists every row once, ascending super-tile order per camera
+    lst, ptr = s["cam_row_list"], s["cam_row_ptr"]
+    assert sorted(lst.tolist()) == list(range(len(row_cam)))
     for c in range(prob.n_cams):
         mine = lst[ptr[c]:ptr[c + 1]]
-        assert np.all(s["seg_cam"][mine] == c) and np.all(np.diff(mine) > 0)
+        assert np.all(row_cam[mine] == c) and np.all(np.diff(mine) > 0)
 
 
 def test_unsorted_input_is_sorted_with_a_permutation(built):
@@ -107,6 +130,8 @@ def test_structure_rejects_what_it_cannot_handle(built):
         binding.host_structure(np.array([0, 5], dtype=np.int32), np.array([0, 0], dtype=np.int32), 2, 1)
     with pytest.raises(binding.GraphiteB200Error, match="tile size"):
         binding.host_structure(np.arange(40, dtype=np.int32), np.zeros(40, dtype=np.int32), 40, 1, 32)
+    with pytest.raises(binding.GraphiteB200Error, match="slot cap"):
+        binding.host_structure(np.arange(40, dtype=np.int32), np.zeros(40, dtype=np.int32), 40, 1, 0, 16)
 
 
 def test_point_partition_covers_everything(built):
