@@ -298,7 +298,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     const bool multi = ctx->nranks > 1;
     k_cam_reduce_lin<T><<<ts.Nc, 288, 0, st>>>(ts, part18, diagB, gc, multi ? 0 : 1, scale_on ? 1 : 0, scale, b);
     GB_LAUNCH(ctx);
-    k_sum_partials<<<1, 1024, 0, st>>>(cost_part, ts.nst, scalars, 0);
+    k_sum_partials<<<1, 1024, 0, st>>>(cost_part, ts.ntiles, scalars, 0);
     GB_LAUNCH(ctx);
     if (multi) {
       GB_TRY(allreduce_T(diagB, dimc));
@@ -352,7 +352,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
       }
       GB_CUDA(ctx, cudaEventRecord(prof_ev[2 * prof_slot], st));
     }
-    k_schur_product<T, S, NSTAGE><<<ts.nst, TILE, SchurSmem<T, S>::TOTAL(NSTAGE), st>>>(ts, J, W, xs, part9, flag);
+    k_schur_product<T, S, NSTAGE><<<ts.nst, 2 * TILE, SchurSmem<T, S>::TOTAL(NSTAGE), st>>>(ts, J, W, xs, part9, flag);
     GB_LAUNCH(ctx);
     if (prof) GB_CUDA(ctx, cudaEventRecord(prof_ev[2 * prof_slot + 1], st));
     const bool multi = ctx->nranks > 1;

@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(TILE)
 k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
             const typename V2<T>::type *__restrict__ obs, typename V2<S>::type *__restrict__ J,
             typename V2<T>::type *__restrict__ res, T *__restrict__ Cg, T *__restrict__ part /*[nrows][18]*/,
-            double *__restrict__ cost_part /*[nst]*/) {
+            double *__restrict__ cost_part /*[ntiles]*/) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T *sv = reinterpret_cast<T *>(smem_raw); // [TILE*9]
   T *acc = sv + TILE * 9;                  // [SLOT_CAP*18]
@@ -183,7 +183,6 @@ k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
   const int row0 = ds.st_row[st], nslots = ds.st_row[st + 1] - row0;
   for (int i = t; i < nslots * 18; i += TILE) acc[i] = T(0);
   __syncthreads();
-  double cost = 0.0;
   for (int tile = ds.st_tile[st]; tile < ds.st_tile[st + 1]; tile++) {
     const TileMeta tm = ds.tmeta[tile];
     const int64_t slot = (int64_t)tile * TILE + t;
@@ -191,6 +190,7 @@ k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
     const int cslot = (int)(om >> 16), rank = (int)((om >> 8) & 0xffu), ptl = (int)(om & 0xffu);
     const bool active = t < tm.n;
     BalObs<T> B;
+    double cost = 0.0;
     if (active) {
       const int c = ds.row_cam[row0 + cslot], p = tm.p0 + ptl;
       T cam[10], X[3], ob[2];
@@ -208,7 +208,7 @@ k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
 #pragma unroll
       for (int j = 0; j < 3; j++) base[(9 + j) * TILE] = V2<S>::make((S)B.Jp[2 * j], (S)B.Jp[2 * j + 1]);
       res[slot] = V2<T>::make(B.r[0], B.r[1]);
-      cost += (double)(B.r[0] * B.r[0] + B.r[1] * B.r[1]);
+      cost = (double)(B.r[0] * B.r[0] + B.r[1] * B.r[1]);
       // what is stored is what every later kernel reads: keep the assembly consistent with S
 #pragma unroll
       for (int j = 0; j < 18; j++) B.Jc[j] = (T)(S)B.Jc[j];
@@ -245,10 +245,11 @@ k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
 #pragma unroll
     for (int k = 0; k < 9; k++) v[k] = active ? -(B.Jc[2 * k] * B.r[0] + B.Jc[2 * k + 1] * B.r[1]) : T(0);
     tile_cam_accumulate<T>(v, rank, tm.nseg, ds.seg_tab + tm.seg_off, sv, acc, 18, 9);
+    // per-tile cost partial with the same reduction tree as k_cost_tiles: chi2 of linearize == chi2 of cost, bit for bit
+    const double tot = block_sum<double>(cost, shd);
+    if (t == 0) cost_part[tile] = tot;
   }
   for (int i = t; i < nslots * 18; i += TILE) part[(int64_t)row0 * 18 + i] = acc[i];
-  const double tot = block_sum<double>(cost, shd);
-  if (t == 0) cost_part[st] = tot;
 }
 
 // Camera side of linearize: diag(B), g_c, Jacobi scales s = 1/(eps + sqrt(diag)) (graph.hpp:262-270), b_c = s g_c.
@@ -532,28 +533,37 @@ template <typename T, typename S> struct SchurSmem {
   static constexpr int J_BYTES = NPLANES * TILE * (int)sizeof(typename V2<S>::type);
   static constexpr int W_BYTES = TILE_PTS * WST<T>::value * (int)sizeof(T);
   static constexpr int STAGE_BYTES = J_BYTES + REC_BYTES + W_BYTES;
+  // inside the J region once its values are in registers: camera staging [TILE*9], then point sums [TILE_PTS*3]
+  static constexpr int SV_IN_STAGE = 0;
+  static constexpr int SW_IN_STAGE = TILE * 9 * (int)sizeof(T);
   static constexpr int XL_OFF(int nstage) { return nstage * STAGE_BYTES; }
-  static constexpr int ACC_OFF(int nstage) { return XL_OFF(nstage) + SLOT_CAP * 9 * (int)sizeof(T); }
-  static constexpr int SV3_OFF(int nstage) { return ACC_OFF(nstage) + SLOT_CAP * 9 * (int)sizeof(T); }
-  static constexpr int SW_OFF(int nstage) { return SV3_OFF(nstage) + TILE * 3 * (int)sizeof(T); }
-  static constexpr int BAR_OFF(int nstage) { return SW_OFF(nstage) + TILE_PTS * 3 * (int)sizeof(T); }
+  static constexpr int ACC_OFF(int nstage) { return XL_OFF(nstage) + SLOT_CAP * 9 * (int)sizeof(T); }      // 2 workers
+  static constexpr int SV3_OFF(int nstage) { return ACC_OFF(nstage) + 2 * SLOT_CAP * 9 * (int)sizeof(T); } // 2 workers
+  static constexpr int BAR_OFF(int nstage) { return SV3_OFF(nstage) + 2 * TILE * 3 * (int)sizeof(T); }
   static constexpr int TOTAL(int nstage) { return BAR_OFF(nstage) + 64; }
+  static_assert(SW_IN_STAGE + TILE_PTS * 3 * (int)sizeof(T) <= J_BYTES, "staging must fit in the J region");
 };
 
+// bar.sync among the 256 threads of one worker (ids 1 and 2; id 0 is __syncthreads)
+__device__ __forceinline__ void worker_sync(int worker) { asm volatile("bar.sync %0, 256;" ::"r"(worker + 1) : "memory"); }
+
+// The CTA has two WORKERS of 256 threads; worker w processes tiles w, w+2, ... of the super-tile with its own
+// accumulator rows (summed in fixed order at the end), so twice as many warps hide the shared-memory and FP64
+// latencies of the short per-tile phases while the TMA keeps the next tiles in flight.
 template <typename T, typename S, int NSTAGE>
-__global__ void __launch_bounds__(TILE, 1)
+__global__ void __launch_bounds__(2 * TILE, 1)
 k_schur_product(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *__restrict__ W,
                 const T *__restrict__ xs, T *__restrict__ part /*[nrows][9]*/, const int *__restrict__ done_flag) {
   using SM = SchurSmem<T, S>;
   using S2 = typename V2<S>::type;
   extern __shared__ __align__(128) unsigned char smem[];
   if (done_flag && *done_flag) return; // PCG already stopped: nothing to do (uniform across the grid)
+  const int worker = threadIdx.x >> 8, t = threadIdx.x & (TILE - 1);
   T *xl = reinterpret_cast<T *>(smem + SM::XL_OFF(NSTAGE));
-  T *acc = reinterpret_cast<T *>(smem + SM::ACC_OFF(NSTAGE));
-  T *sv3 = reinterpret_cast<T *>(smem + SM::SV3_OFF(NSTAGE));
-  T *sw = reinterpret_cast<T *>(smem + SM::SW_OFF(NSTAGE));
+  T *acc = reinterpret_cast<T *>(smem + SM::ACC_OFF(NSTAGE)) + worker * SLOT_CAP * 9;
+  T *sv3 = reinterpret_cast<T *>(smem + SM::SV3_OFF(NSTAGE)) + worker * TILE * 3;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM::BAR_OFF(NSTAGE));
-  const int st = blockIdx.x, t = threadIdx.x;
+  const int st = blockIdx.x;
   const int tile0 = ds.st_tile[st], ntl = ds.st_tile[st + 1] - tile0;
   const int row0 = ds.st_row[st], nslots = ds.st_row[st + 1] - row0;
 
@@ -567,20 +577,20 @@ k_schur_product(DevStruct ds, const typename V2<S>::type *__restrict__ J, const 
     bulk_g2s(base + SM::J_BYTES + REC_BYTES, W + (int64_t)tm.p0 * WST<T>::value, wbytes, &bars[s]);
   };
 
-  if (t == 0) {
+  if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; s++) mbar_init(&bars[s], 1);
     mbar_fence_init();
     fence_proxy_async();
     for (int i = 0; i < NSTAGE && i < ntl; i++) issue(tile0 + i, i);
   }
-  for (int i = t; i < nslots * 9; i += TILE) {
+  for (int i = threadIdx.x; i < nslots * 9; i += 2 * TILE) {
     const int s = i / 9, k = i - 9 * s;
     xl[i] = xs[(int64_t)ds.row_cam[row0 + s] * CAM_STRIDE + k];
-    acc[i] = T(0);
   }
+  for (int i = t; i < nslots * 9; i += TILE) acc[i] = T(0);
   __syncthreads();
 
-  for (int i = 0; i < ntl; i++) {
+  for (int i = worker; i < ntl; i += 2) {
     const int s = i % NSTAGE;
     mbar_wait(&bars[s], (uint32_t)((i / NSTAGE) & 1));
     unsigned char *base = smem + s * SM::STAGE_BYTES;
@@ -615,7 +625,9 @@ k_schur_product(DevStruct ds, const typename V2<S>::type *__restrict__ J, const 
     sv3[t * 3 + 0] = jp[0] * y0 + jp[1] * y1;
     sv3[t * 3 + 1] = jp[2] * y0 + jp[3] * y1;
     sv3[t * 3 + 2] = jp[4] * y0 + jp[5] * y1;
-    __syncthreads(); // also: every thread has its J values in registers, the stage's J region may be reused
+    worker_sync(worker); // also: every thread has its J values in registers, the stage's J region may be reused
+    T *sv = reinterpret_cast<T *>(base + SM::SV_IN_STAGE);
+    T *sw = reinterpret_cast<T *>(base + SM::SW_IN_STAGE);
     {
       const uint16_t *pt = reinterpret_cast<const uint16_t *>(rec + REC_PT);
       for (int item = t; item < tm.np * 3; item += TILE) {
@@ -626,8 +638,7 @@ k_schur_product(DevStruct ds, const typename V2<S>::type *__restrict__ J, const 
         sw[item] = a;
       }
     }
-    __syncthreads();
-    T v[9];
+    worker_sync(worker);
     {
       const T t0 = sw[ptl * 3], t1 = sw[ptl * 3 + 1], t2 = sw[ptl * 3 + 2];
       const T *w = Ws + ptl * WST<T>::value;
@@ -636,18 +647,44 @@ k_schur_product(DevStruct ds, const typename V2<S>::type *__restrict__ J, const 
       const T w2 = w[2] * t0 + w[4] * t1 + w[5] * t2;
       const T d0 = y0 - (jp[0] * w0 + jp[2] * w1 + jp[4] * w2);
       const T d1 = y1 - (jp[1] * w0 + jp[3] * w1 + jp[5] * w2);
+      // stage v = Jc^T d at the slot's rank: camera segments become contiguous rows
 #pragma unroll
-      for (int k = 0; k < 9; k++) v[k] = jc[2 * k] * d0 + jc[2 * k + 1] * d1;
+      for (int k = 0; k < 9; k++) sv[rank * 9 + k] = jc[2 * k] * d0 + jc[2 * k + 1] * d1;
     }
-    T *sv = reinterpret_cast<T *>(base); // camera staging over the consumed J region
-    tile_cam_accumulate<T>(v, rank, tm.nseg, reinterpret_cast<const uint32_t *>(rec + REC_SEG), sv, acc, 9, 0);
-    // the stage is free (all threads passed the barrier at the end of tile_cam_accumulate): refill it
+    worker_sync(worker);
+    {
+      // one thread per (segment, component triple): sum the segment's rows, add to the camera's accumulator row
+      const uint32_t *sg = reinterpret_cast<const uint32_t *>(rec + REC_SEG);
+      for (int item = t; item < tm.nseg * 3; item += TILE) {
+        const int q = item / 3, g = item - 3 * q;
+        const uint32_t e0 = sg[q], e1 = sg[q + 1];
+        const int b = (int)(e0 >> 16), e = (int)(e1 >> 16), cs = (int)(e0 & 0xffffu);
+        T a0 = T(0), a1 = T(0), a2 = T(0);
+        for (int row = b; row < e; row++) {
+          const T *r = sv + row * 9 + 3 * g;
+          a0 += r[0];
+          a1 += r[1];
+          a2 += r[2];
+        }
+        T *ar = acc + cs * 9 + 3 * g;
+        ar[0] += a0;
+        ar[1] += a1;
+        ar[2] += a2;
+      }
+    }
+    worker_sync(worker);
+    // the stage is free (all threads of the worker are past the barrier): refill it with tile i + NSTAGE
     if (t == 0 && i + NSTAGE < ntl) {
       fence_proxy_async();
       issue(tile0 + i + NSTAGE, s);
     }
   }
-  for (int i = t; i < nslots * 9; i += TILE) part[(int64_t)row0 * 9 + i] = acc[i];
+  __syncthreads();
+  {
+    const T *acc0 = reinterpret_cast<const T *>(smem + SM::ACC_OFF(NSTAGE));
+    for (int i = threadIdx.x; i < nslots * 9; i += 2 * TILE)
+      part[(int64_t)row0 * 9 + i] = acc0[i] + acc0[SLOT_CAP * 9 + i]; // worker 0 (even tiles) + worker 1 (odd tiles)
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -29,7 +29,7 @@
 namespace gb {
 
 constexpr int TILE = 256;       // storage slots per tile = threads per CTA
-constexpr int SLOT_CAP = 256;   // camera accumulator rows per super-tile
+constexpr int SLOT_CAP = 192;   // camera accumulator rows per super-tile (bounded by shared memory)
 constexpr int TILE_PTS = 128;   // max points per tile (bounds the per-tile W stage)
 // Packed per-tile record (one TMA bulk copy): ometa[256] u32 | seg_tab[260] u32 | pt_tab[136] u16 | TileMeta
 constexpr int REC_OMETA = 0;
@@ -76,7 +76,7 @@ struct HostStructure {
     if (tile_size <= 0) tile_size = TILE;
     if (tile_size > TILE) return "tile_size must be <= 256";
     if (slot_cap_opt <= 0) slot_cap_opt = SLOT_CAP;
-    if (slot_cap_opt > SLOT_CAP) return "slot cap must be <= 256";
+    if (slot_cap_opt > SLOT_CAP) return "slot cap must be <= 192";
     M = m; Nc = (int32_t)nc; Np = (int32_t)np; tile_fill = tile_size; slot_cap = slot_cap_opt;
     for (int64_t i = 0; i < m; i++)
       if (ci[i] < 0 || ci[i] >= nc || pi[i] < 0 || pi[i] >= np) return "observation index out of range";
@@ -119,13 +119,21 @@ struct HostStructure {
     // ---- tiles of whole points ----------------------------------------------------------------------
     tile_obs.clear(); tile_pt.clear();
     tile_obs.push_back(0); tile_pt.push_back(0);
-    int32_t cur = 0;
+    int32_t cur = 0, ncam_tile = 0;
+    std::vector<int32_t> tstamp((size_t)nc, -1);
     for (int32_t p = 0; p < Np; p++) {
       const int32_t t = pptr[p + 1] - pptr[p];
-      if (cur + t > tile_fill || p - tile_pt.back() >= TILE_PTS) {
+      // cameras this point would add to the tile (a tile may not touch more cameras than a super-tile has rows)
+      const int32_t tid = (int32_t)tile_pt.size() - 1;
+      int32_t add = 0;
+      for (int32_t o = pptr[p]; o < pptr[p + 1]; o++) add += tstamp[cam_idx[o]] != tid;
+      if (cur + t > tile_fill || p - tile_pt.back() >= TILE_PTS || ncam_tile + add > slot_cap) {
         tile_obs.push_back(pptr[p]); tile_pt.push_back(p);
-        cur = 0;
+        cur = 0; ncam_tile = 0;
       }
+      const int32_t tid2 = (int32_t)tile_pt.size() - 1;
+      for (int32_t o = pptr[p]; o < pptr[p + 1]; o++)
+        if (tstamp[cam_idx[o]] != tid2) { tstamp[cam_idx[o]] = tid2; ncam_tile++; }
       cur += t;
     }
     tile_obs.push_back((int32_t)m); tile_pt.push_back(Np);

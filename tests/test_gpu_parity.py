@@ -194,7 +194,7 @@ def test_unsorted_input_and_small_tiles_give_the_same_answer(ctx):
     assert np.array_equal(r1, P0.residuals()[perm]), "residuals must come back in the caller's factor order"
     t1, _ = P1.lm(iterations=8)
     assert np.array_equal(t0, t1), "same sorted problem => bit-identical trajectory"
-    for kw in (dict(tile_size=32), dict(tile_size=32, slot_cap=48, super_tile_observations=700), dict(super_tile_observations=100000)):
+    for kw in (dict(tile_size=32), dict(slot_cap=30, super_tile_observations=700), dict(super_tile_observations=100000)):
         P2 = binding.problem_from_bal(ctx, prob, "f64-f64", **kw)
         t2, _ = P2.lm(iterations=8)
         assert np.abs(t2[:, 1] - t0[:, 1]).max() <= 1e-10 * t0[0, 0], kw
@@ -304,6 +304,9 @@ def test_full_size_properties(ctx):
         col = P.schur_multiply(e)
         assert rel(col[9 * c:9 * c + 9], Sd[c][:, k]) <= 1e-10
     # a converged PCG solve satisfies S x = b_S, and back-substitution zeroes the point rows of the normal equations
+    # heavily damped so that the (nonlinear) step is inside the trust region: the reference's own run rejects the
+    # first steps of this problem until lambda has grown past 1e2
+    P.set_damping(1e3)
     d, info = P.solve(500, 1e-20, 1e30)
     # a step along the solution decreases the cost and revert is exact
     new_chi2, rho_den = P.try_step()

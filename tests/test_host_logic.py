@@ -57,11 +57,11 @@ def test_structure_matches_reference_golden(built):
     assert np.array_equal(cp, z["H_colptr"]) and np.array_equal(ri, z["H_rowidx"]) and np.array_equal(off, z["H_offsets"])
 
 
-@pytest.mark.parametrize("tile,cap,st_obs", [(0, 0, 0), (64, 0, 0), (32, 40, 500), (0, 64, 2000)])
+@pytest.mark.parametrize("tile,cap,st_obs", [(0, 0, 0), (64, 0, 0), (32, 40, 500), (0, 30, 2000)])
 def test_tiles_ranks_segments_and_super_tiles(built, tile, cap, st_obs):
     prob = synthetic.make_named("ladybug-49")
     s = binding.host_structure(prob.cam_idx, prob.pt_idx, prob.n_cams, prob.n_pts, tile, cap, st_obs)
-    fill, capv = tile or 256, cap or 256
+    fill, capv = tile or 256, cap or 192
     to, tp, tm = s["tile_obs"], s["tile_pt"], s["tmeta"]
     m, nt = prob.n_obs, len(s["tile_obs"]) - 1
     assert to[0] == 0 and to[-1] == m and tp[-1] == prob.n_pts
@@ -132,6 +132,8 @@ def test_structure_rejects_what_it_cannot_handle(built):
         binding.host_structure(np.arange(40, dtype=np.int32), np.zeros(40, dtype=np.int32), 40, 1, 32)
     with pytest.raises(binding.GraphiteB200Error, match="slot cap"):
         binding.host_structure(np.arange(40, dtype=np.int32), np.zeros(40, dtype=np.int32), 40, 1, 0, 16)
+    with pytest.raises(binding.GraphiteB200Error, match="slot cap"):
+        binding.host_structure(np.arange(40, dtype=np.int32), np.zeros(40, dtype=np.int32), 40, 1, 0, 500)
 
 
 def test_point_partition_covers_everything(built):
