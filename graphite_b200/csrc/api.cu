@@ -114,6 +114,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
   using T2 = typename V2<T>::type;
   using S2 = typename V2<S>::type;
   static constexpr int NSTAGE = 3; // TMA pipeline depth of the Schur product (fits 227 KB in FP64)
+  static constexpr int PSTAGE = 2; // ... of the prepare kernel (its 54-wide accumulator rows take 81 KB)
   DevStruct ts{};
   std::vector<void *> allocs;
   int64_t bytes = 0;
@@ -213,12 +214,13 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_TRY(dalloc(dot_part, Nc)); GB_TRY(dalloc(rz_part, Nc));
     // the super-tile kernels keep their camera accumulator rows in (opt-in sized) dynamic shared memory
     GB_CUDA(ctx, cudaFuncSetAttribute(k_linearize<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIN * sizeof(T))));
-    GB_CUDA(ctx, cudaFuncSetAttribute(k_prepare_tiles<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_PREP * sizeof(T))));
+    GB_CUDA(ctx, cudaFuncSetAttribute(k_prepare_tiles<T, S, PSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      PrepSmem<T, S>::TOTAL(PSTAGE)));
     GB_CUDA(ctx, cudaFuncSetAttribute(k_schur_product<T, S, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       SchurSmem<T, S>::TOTAL(NSTAGE)));
     GB_TRY(dalloc(diagB, dimc)); GB_TRY(dalloc(gc, dimc));
     GB_TRY(dalloc(scale, dimH)); GB_TRY(dalloc(b, dimH)); GB_TRY(dalloc(delta, dimH));
-    GB_TRY(dalloc(W, (size_t)WST<T>::value * Np + 8)); GB_TRY(dalloc(h, 3 * Np));
+    GB_TRY(dalloc(W, (size_t)WST<T>::value * Np + 8)); GB_TRY(dalloc(h, (size_t)HST * Np + 8));
     GB_TRY(dalloc(Sdiag, Nc * 81)); GB_TRY(dalloc(Minv, Nc * 81));
     GB_TRY(dalloc(bS, dimc)); GB_TRY(dalloc(dterm, dimc));
     GB_TRY(dalloc(x, dimc)); GB_TRY(dalloc(r, dimc)); GB_TRY(dalloc(z, dimc)); GB_TRY(dalloc(pv, dimc));
@@ -322,7 +324,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     k_point_prepare<T><<<(ts.Np + 255) / 256, 256, 0, st>>>(ts.Np, scale_on ? 1 : 0, mu, use_identity, Cg, scale + dimc,
                                                            b + dimc, W, h, 0);
     GB_LAUNCH(ctx);
-    k_prepare_tiles<T, S><<<ts.nst, TILE, SMEM_PREP * sizeof(T), st>>>(ts, J, W, h, part54);
+    k_prepare_tiles<T, S, PSTAGE><<<ts.nst, 2 * TILE, PrepSmem<T, S>::TOTAL(PSTAGE), st>>>(ts, J, W, h, part54);
     GB_LAUNCH(ctx);
     const bool multi = ctx->nranks > 1;
     k_cam_reduce_prepare<T><<<ts.Nc, 288, 0, st>>>(ts, part54, 0, sums54, multi ? 0 : 1, mu, use_identity, diagB, gc,

@@ -36,9 +36,9 @@ constexpr int CAM_STRIDE = 10; // padded camera row
 constexpr int NPLANES = 12;
 // dynamic shared memory of the super-tile kernels, in elements of T
 constexpr int SMEM_LIN = TILE * 9 + SLOT_CAP * 18;
-constexpr int SMEM_PREP = TILE * 9 + SLOT_CAP * 54;
 // per-point W row stride: 6 values, padded to 8 in FP32 so that a tile's rows start 16-byte aligned (TMA)
 template <typename T> struct WST { static constexpr int value = sizeof(T) == 4 ? 8 : 6; };
+constexpr int HST = 4; // per-point h row stride (3 values + pad): 16-byte aligned rows in FP32 and FP64
 
 template <typename T> struct V2;
 template <> struct V2<double> {
@@ -66,6 +66,38 @@ struct DevStruct {
   const int32_t *slot_of_obs; // [M] sorted observation -> storage slot (exports)
   const int32_t *cam_idx, *pt_idx, *pptr;    // sorted observations (exports)
 };
+
+// ---------------------------------------------------------------------------------------------
+// TMA (bulk async copy) + mbarrier helpers — sm_90+/sm_100a.  One thread issues, all threads wait on parity.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+// global -> shared bulk copy, completion counted in bytes on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// order generic-proxy accesses to shared memory before later async-proxy (TMA) writes to the same bytes
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// bar.sync among the 256 threads of one worker (ids 1 and 2; id 0 is __syncthreads)
+__device__ __forceinline__ void worker_sync(int worker) { asm volatile("bar.sync %0, 256;" ::"r"(worker + 1) : "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 // reductions
@@ -344,9 +376,9 @@ __global__ void k_point_prepare(int Np, int scale_on, T mu, int use_identity, co
   const T w11 = s1 * s1 * m11 * id, w12 = s1 * s2 * m12 * id, w22 = s2 * s2 * m22 * id;
   T *w = W + (int64_t)p * WST<T>::value;
   w[0] = w00; w[1] = w01; w[2] = w02; w[3] = w11; w[4] = w12; w[5] = w22;
-  h[3 * (int64_t)p] = w00 * g0 + w01 * g1 + w02 * g2;
-  h[3 * (int64_t)p + 1] = w01 * g0 + w11 * g1 + w12 * g2;
-  h[3 * (int64_t)p + 2] = w02 * g0 + w12 * g1 + w22 * g2;
+  h[HST * (int64_t)p] = w00 * g0 + w01 * g1 + w02 * g2;
+  h[HST * (int64_t)p + 1] = w01 * g0 + w11 * g1 + w12 * g2;
+  h[HST * (int64_t)p + 2] = w02 * g0 + w12 * g1 + w22 * g2;
 }
 
 // K3b: per super-tile — camera-side partials of the Schur diagonal blocks and of the reduced right-hand side:
@@ -354,26 +386,141 @@ __global__ void k_point_prepare(int Np, int scale_on, T mu, int use_identity, co
 //   u_c = sum_o Jc^T Jp h_p
 // replaces execute_schur_multiplication on the diagonal pairs + execute_b_Schur_computation
 // (schur.hpp:649-734, 901-920) and the block copy of block_jacobi_schur.hpp:126-137.
-// Dynamic shared memory: sv[TILE*9] + acc[SLOT_CAP*54] of T.
-template <typename T, typename S>
-__global__ void __launch_bounds__(TILE)
+// Same TMA tile pipeline as the Schur product.  The 54 values per camera (45 upper entries of A, 9 of u) are
+// split between the CTA's two workers: both read every tile from the same stage, worker 0 accumulates values
+// 0..26, worker 1 values 27..53, each into its own columns of the shared accumulator rows.
+template <typename T, typename S> struct PrepSmem {
+  static constexpr int J_BYTES = NPLANES * TILE * (int)sizeof(typename V2<S>::type);
+  static constexpr int W_BYTES = TILE_PTS * WST<T>::value * (int)sizeof(T);
+  static constexpr int H_BYTES = TILE_PTS * HST * (int)sizeof(T);
+  static constexpr int STAGE_BYTES = J_BYTES + REC_BYTES + W_BYTES + H_BYTES;
+  static constexpr int SV_BYTES = TILE * 9 * (int)sizeof(T); // staging per worker
+  // the two staging areas reuse the consumed J region when they fit (T == S); else they get their own space
+  static constexpr bool SV_ALIAS = 2 * SV_BYTES <= J_BYTES;
+  static constexpr int ACC_OFF(int nstage) { return nstage * STAGE_BYTES; }
+  static constexpr int SV_OFF(int nstage) { return ACC_OFF(nstage) + SLOT_CAP * 54 * (int)sizeof(T); }
+  static constexpr int BAR_OFF(int nstage) { return SV_OFF(nstage) + (SV_ALIAS ? 0 : 2 * SV_BYTES); }
+  static constexpr int TOTAL(int nstage) { return BAR_OFF(nstage) + 64; }
+};
+
+// packed upper-triangle index (row-wise, i <= j) -> (i, j)
+__host__ __device__ constexpr int tri_i(int idx) {
+  int i = 0, rem = idx;
+  while (rem >= 9 - i) { rem -= 9 - i; i++; }
+  return i;
+}
+__host__ __device__ constexpr int tri_j(int idx) {
+  int i = 0, rem = idx;
+  while (rem >= 9 - i) { rem -= 9 - i; i++; }
+  return i + rem;
+}
+
+// values [9 G, 9 G + 9) of the 54: G < 5 -> entries of A = Jc^T K, G == 5 -> u = Jc^T q.  All register indices are
+// compile-time constants (a run-time index would push jc / K to local memory).
+template <int IDX> struct Tri {
+  static constexpr int i = tri_i(IDX < 45 ? IDX : 0), j = tri_j(IDX < 45 ? IDX : 0);
+};
+template <typename T, int G, int K9> struct PrepOne {
+  static __device__ __forceinline__ void run(const T *jc, const T *K, T q0, T q1, T *v) {
+    if constexpr (G < 5) {
+      constexpr int i = Tri<G * 9 + K9>::i, j = Tri<G * 9 + K9>::j;
+      v[K9] = jc[2 * i] * K[2 * j] + jc[2 * i + 1] * K[2 * j + 1];
+    } else {
+      v[K9] = jc[2 * K9] * q0 + jc[2 * K9 + 1] * q1;
+    }
+    if constexpr (K9 + 1 < 9) PrepOne<T, G, K9 + 1>::run(jc, K, q0, q1, v);
+  }
+};
+template <typename T, int G> __device__ __forceinline__ void prep_group(const T *jc, const T *K, T q0, T q1, T *v) {
+  PrepOne<T, G, 0>::run(jc, K, q0, q1, v);
+}
+
+// stage v at rank, sum camera segments (one thread per segment and component triple), add into acc columns [goff, goff+9)
+template <typename T>
+__device__ __forceinline__ void worker_cam_accumulate(const T v[9], int rank, int nseg, const uint32_t *sg, T *sv, T *acc,
+                                                      int astride, int goff, int worker, int t) {
+#pragma unroll
+  for (int k = 0; k < 9; k++) sv[rank * 9 + k] = v[k];
+  worker_sync(worker);
+  for (int item = t; item < nseg * 3; item += TILE) {
+    const int q = item / 3, g = item - 3 * q;
+    const uint32_t e0 = sg[q], e1 = sg[q + 1];
+    const int b = (int)(e0 >> 16), e = (int)(e1 >> 16), cs = (int)(e0 & 0xffffu);
+    T a0 = T(0), a1 = T(0), a2 = T(0);
+    for (int row = b; row < e; row++) {
+      const T *r = sv + row * 9 + 3 * g;
+      a0 += r[0];
+      a1 += r[1];
+      a2 += r[2];
+    }
+    T *ar = acc + cs * astride + goff + 3 * g;
+    ar[0] += a0;
+    ar[1] += a1;
+    ar[2] += a2;
+  }
+  worker_sync(worker);
+}
+
+template <typename T, typename S, int NSTAGE>
+__global__ void __launch_bounds__(2 * TILE, 1)
 k_prepare_tiles(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *__restrict__ W,
                 const T *__restrict__ h, T *__restrict__ part /*[nrows][54]*/) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T *sv = reinterpret_cast<T *>(smem_raw);
-  T *acc = sv + TILE * 9;
-  const int st = blockIdx.x, t = threadIdx.x;
+  using SM = PrepSmem<T, S>;
+  using S2 = typename V2<S>::type;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int worker = threadIdx.x >> 8, t = threadIdx.x & (TILE - 1);
+  T *acc = reinterpret_cast<T *>(smem + SM::ACC_OFF(NSTAGE));
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM::BAR_OFF(NSTAGE));
+  const int st = blockIdx.x;
+  const int tile0 = ds.st_tile[st], ntl = ds.st_tile[st + 1] - tile0;
   const int row0 = ds.st_row[st], nslots = ds.st_row[st + 1] - row0;
-  for (int i = t; i < nslots * 54; i += TILE) acc[i] = T(0);
-  __syncthreads();
-  for (int tile = ds.st_tile[st]; tile < ds.st_tile[st + 1]; tile++) {
+
+  auto issue = [&](int tile, int s) {
     const TileMeta tm = ds.tmeta[tile];
-    const uint32_t om = ds.ometa[(int64_t)tile * TILE + t];
+    unsigned char *base = smem + s * SM::STAGE_BYTES;
+    const uint32_t wbytes = (uint32_t)(tm.np * WST<T>::value * (int)sizeof(T));
+    const uint32_t hbytes = (uint32_t)(tm.np * HST * (int)sizeof(T));
+    mbar_expect_tx(&bars[s], (uint32_t)(SM::J_BYTES + REC_BYTES) + wbytes + hbytes);
+    bulk_g2s(base, J + (int64_t)tile * NPLANES * TILE, SM::J_BYTES, &bars[s]);
+    bulk_g2s(base + SM::J_BYTES, ds.trec + (int64_t)tile * REC_BYTES, REC_BYTES, &bars[s]);
+    bulk_g2s(base + SM::J_BYTES + REC_BYTES, W + (int64_t)tm.p0 * WST<T>::value, wbytes, &bars[s]);
+    bulk_g2s(base + SM::J_BYTES + REC_BYTES + SM::W_BYTES, h + (int64_t)tm.p0 * HST, hbytes, &bars[s]);
+  };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; s++) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+    fence_proxy_async();
+    for (int i = 0; i < NSTAGE && i < ntl; i++) issue(tile0 + i, i);
+  }
+  for (int i = threadIdx.x; i < nslots * 54; i += 2 * TILE) acc[i] = T(0);
+  __syncthreads();
+
+  for (int i = 0; i < ntl; i++) {
+    const int s = i % NSTAGE;
+    mbar_wait(&bars[s], (uint32_t)((i / NSTAGE) & 1));
+    unsigned char *base = smem + s * SM::STAGE_BYTES;
+    const S2 *Js = reinterpret_cast<const S2 *>(base);
+    const unsigned char *rec = base + SM::J_BYTES;
+    const T *Ws = reinterpret_cast<const T *>(base + SM::J_BYTES + REC_BYTES);
+    const T *Hs = reinterpret_cast<const T *>(base + SM::J_BYTES + REC_BYTES + SM::W_BYTES);
+    const TileMeta tm = *reinterpret_cast<const TileMeta *>(rec + REC_META);
+    const uint32_t om = reinterpret_cast<const uint32_t *>(rec + REC_OMETA)[t];
     const int rank = (int)((om >> 8) & 0xffu), ptl = (int)(om & 0xffu);
     T jc[18], jp[6], K[18];
-    load_J<T, S>(J, tile, t, jc, jp);   // padding slots hold zeros
-    const int p = tm.p0 + ptl;
-    const T *w = W + (int64_t)p * WST<T>::value;
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+      const S2 v = Js[j * TILE + t];
+      jc[2 * j] = (T)v.x;
+      jc[2 * j + 1] = (T)v.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const S2 v = Js[(9 + j) * TILE + t];
+      jp[2 * j] = (T)v.x;
+      jp[2 * j + 1] = (T)v.y;
+    }
+    const T *w = Ws + ptl * WST<T>::value;
     const T w00 = w[0], w01 = w[1], w02 = w[2], w11 = w[3], w12 = w[4], w22 = w[5];
     // rows of Jp: a = (jp[0], jp[2], jp[4]), b = (jp[1], jp[3], jp[5])
     const T wa0 = w00 * jp[0] + w01 * jp[2] + w02 * jp[4];
@@ -391,30 +538,35 @@ k_prepare_tiles(DevStruct ds, const typename V2<S>::type *__restrict__ J, const 
       K[2 * j] = m00 * jc[2 * j] + m01 * jc[2 * j + 1];
       K[2 * j + 1] = m01 * jc[2 * j] + m11 * jc[2 * j + 1];
     }
-    const T *hp = h + (int64_t)p * 3;
+    const T *hp = Hs + ptl * HST;
     const T q0 = jp[0] * hp[0] + jp[2] * hp[1] + jp[4] * hp[2];
     const T q1 = jp[1] * hp[0] + jp[3] * hp[1] + jp[5] * hp[2];
-    // 45 upper entries A(i,j), i <= j, row-wise: (0,0..8), (1,1..8), ... ; 5 groups of 9
+    __syncthreads(); // both workers hold the tile in registers: the J region becomes the two staging areas
+    T *sv = reinterpret_cast<T *>((SM::SV_ALIAS ? base : smem + SM::SV_OFF(NSTAGE)) + worker * SM::SV_BYTES);
+    const uint32_t *sg = reinterpret_cast<const uint32_t *>(rec + REC_SEG);
     T v[9];
-    int gi = 0, gcount = 0;
-#pragma unroll
-    for (int i = 0; i < 9; i++) {
-#pragma unroll
-      for (int j = i; j < 9; j++) {
-        v[gcount] = jc[2 * i] * K[2 * j] + jc[2 * i + 1] * K[2 * j + 1];
-        gcount++;
-        if (gcount == 9) {
-          tile_cam_accumulate<T>(v, rank, tm.nseg, ds.seg_tab + tm.seg_off, sv, acc, 54, gi * 9);
-          gcount = 0;
-          gi++;
-        }
-      }
+    if (worker == 0) {
+      prep_group<T, 0>(jc, K, q0, q1, v);
+      worker_cam_accumulate<T>(v, rank, tm.nseg, sg, sv, acc, 54, 0, worker, t);
+      prep_group<T, 1>(jc, K, q0, q1, v);
+      worker_cam_accumulate<T>(v, rank, tm.nseg, sg, sv, acc, 54, 9, worker, t);
+      prep_group<T, 2>(jc, K, q0, q1, v);
+      worker_cam_accumulate<T>(v, rank, tm.nseg, sg, sv, acc, 54, 18, worker, t);
+    } else {
+      prep_group<T, 3>(jc, K, q0, q1, v);
+      worker_cam_accumulate<T>(v, rank, tm.nseg, sg, sv, acc, 54, 27, worker, t);
+      prep_group<T, 4>(jc, K, q0, q1, v);
+      worker_cam_accumulate<T>(v, rank, tm.nseg, sg, sv, acc, 54, 36, worker, t);
+      prep_group<T, 5>(jc, K, q0, q1, v);
+      worker_cam_accumulate<T>(v, rank, tm.nseg, sg, sv, acc, 54, 45, worker, t);
     }
-#pragma unroll
-    for (int k = 0; k < 9; k++) v[k] = jc[2 * k] * q0 + jc[2 * k + 1] * q1;
-    tile_cam_accumulate<T>(v, rank, tm.nseg, ds.seg_tab + tm.seg_off, sv, acc, 54, 45);
+    __syncthreads(); // both workers are done with the stage
+    if (threadIdx.x == 0 && i + NSTAGE < ntl) {
+      fence_proxy_async();
+      issue(tile0 + i + NSTAGE, s);
+    }
   }
-  for (int i = t; i < nslots * 54; i += TILE) part[(int64_t)row0 * 54 + i] = acc[i];
+  for (int i = threadIdx.x; i < nslots * 54; i += 2 * TILE) part[(int64_t)row0 * 54 + i] = acc[i];
 }
 
 // In-place Gauss-Jordan inverse of a 9x9 matrix in shared memory by one thread (partial pivoting).
@@ -488,35 +640,6 @@ k_cam_reduce_prepare(DevStruct ds, const T *__restrict__ part, int from_sums, T 
 }
 
 // ---------------------------------------------------------------------------------------------
-// TMA (bulk async copy) + mbarrier helpers — sm_90+/sm_100a.  One thread issues, all threads wait on parity.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok)
-                 : "r"(smem_u32(bar)), "r"(parity)
-                 : "memory");
-  } while (!ok);
-}
-// global -> shared bulk copy, completion counted in bytes on the mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-// order generic-proxy accesses to shared memory before later async-proxy (TMA) writes to the same bytes
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// ---------------------------------------------------------------------------------------------
 // K4: matrix-free Schur product, one CTA per super-tile, tiles streamed through a TMA pipeline.
 //   xs = D_c x (10-padded rows).
 //   y_o = Jc x_c ; t_p = sum_o Jp^T y_o ; w_p = W_p t_p ; z_o = Jp w_p ; v_o = Jc^T (y_o - z_o)
@@ -543,9 +666,6 @@ template <typename T, typename S> struct SchurSmem {
   static constexpr int TOTAL(int nstage) { return BAR_OFF(nstage) + 64; }
   static_assert(SW_IN_STAGE + TILE_PTS * 3 * (int)sizeof(T) <= J_BYTES, "staging must fit in the J region");
 };
-
-// bar.sync among the 256 threads of one worker (ids 1 and 2; id 0 is __syncthreads)
-__device__ __forceinline__ void worker_sync(int worker) { asm volatile("bar.sync %0, 256;" ::"r"(worker + 1) : "memory"); }
 
 // The CTA has two WORKERS of 256 threads; worker w processes tiles w, w+2, ... of the super-tile with its own
 // accumulator rows (summed in fixed order at the end), so twice as many warps hide the shared-memory and FP64
@@ -738,7 +858,7 @@ k_backsubst_tiles(DevStruct ds, const typename V2<S>::type *__restrict__ J, cons
     for (int k = 0; k < 3; k++) {
       const int64_t i = 3 * (int64_t)p + k;
       const T s = scale_p[i];
-      const T xt = (h[i] - wv[k]) / s; // scaled-space step of the point
+      const T xt = (h[HST * (int64_t)p + k] - wv[k]) / s; // scaled-space step of the point
       delta_p[i] = xt;
       rho += (double)(xt * (mu * xt + b_p[i]));
       if (apply) {
