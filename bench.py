@@ -188,7 +188,7 @@ def main():
     tname, sname = args.precision.split("-")
     T = np.float64 if tname == "f64" else np.float32
     sT, sS = (8 if tname == "f64" else 4), (8 if sname == "f64" else 4)
-    P = binding.Problem(ctx, local.cam_idx, local.pt_idx, local.n_cams, local.n_pts, args.precision)
+    P = binding.Problem(ctx, local.cam_idx, local.pt_idx, local.n_cams, local.n_pts, args.precision, partition=world > 1)
     info = P.info()
 
     # pinned host copies of the inputs (the e2e arm copies from these every step)

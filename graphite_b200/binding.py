@@ -33,7 +33,7 @@ class ProblemDesc(C.Structure):
     _fields_ = [("precision_T", C.c_int32), ("precision_S", C.c_int32), ("num_cameras", C.c_int64),
                 ("num_points", C.c_int64), ("num_observations", C.c_int64), ("camera_index", C.POINTER(C.c_int32)),
                 ("point_index", C.POINTER(C.c_int32)), ("tile_size", C.c_int32), ("slot_cap", C.c_int32),
-                ("super_tile_observations", C.c_int64)]
+                ("super_tile_observations", C.c_int64), ("flags", C.c_int64)]
 
 
 class PcgOptions(C.Structure):
@@ -157,7 +157,7 @@ class Problem:
     """One BAL problem on one GPU (one rank's point partition)."""
 
     def __init__(self, ctx: Context, cam_idx, pt_idx, n_cams: int, n_pts: int, precision: str = "f64-f64", tile_size: int = 0,
-                 slot_cap: int = 0, super_tile_observations: int = 0):
+                 slot_cap: int = 0, super_tile_observations: int = 0, partition: bool = False):
         self.ctx, self.L = ctx, ctx.L
         t, s = precision.split("-")
         self.T, self.S = _NP[t], _NP[s]
@@ -168,7 +168,8 @@ class Problem:
         ci = np.ascontiguousarray(cam_idx, dtype=np.int32)
         pi = np.ascontiguousarray(pt_idx, dtype=np.int32)
         d = ProblemDesc(_DT[t], _DT[s], self.n_cams, self.n_pts, self.n_obs, ci.ctypes.data_as(C.POINTER(C.c_int32)),
-                        pi.ctypes.data_as(C.POINTER(C.c_int32)), tile_size, slot_cap, super_tile_observations)
+                        pi.ctypes.data_as(C.POINTER(C.c_int32)), tile_size, slot_cap, super_tile_observations,
+                        1 if partition else 0)
         h = C.c_void_p()
         ctx.check(self.L.gb_problem_create(ctx.h, C.byref(d), C.byref(h)))
         self.h = h
@@ -309,9 +310,10 @@ class Problem:
         return v.value
 
 
-def problem_from_bal(ctx: Context, prob, precision="f64-f64", tile_size=0, slot_cap=0, super_tile_observations=0) -> Problem:
+def problem_from_bal(ctx: Context, prob, precision="f64-f64", tile_size=0, slot_cap=0, super_tile_observations=0,
+                     partition=False) -> Problem:
     p = Problem(ctx, prob.cam_idx, prob.pt_idx, prob.n_cams, prob.n_pts, precision, tile_size, slot_cap,
-                super_tile_observations)
+                super_tile_observations, partition)
     p.set_observations(prob.obs)
     p.set_vertices(prob.cams, prob.pts)
     return p
@@ -331,7 +333,7 @@ def host_structure(cam_idx, pt_idx, n_cams: int, n_pts: int, tile_size: int = 0,
     ci = np.ascontiguousarray(cam_idx, dtype=np.int32)
     pi = np.ascontiguousarray(pt_idx, dtype=np.int32)
     d = ProblemDesc(GB_F64, GB_F64, int(n_cams), int(n_pts), int(len(ci)), ci.ctypes.data_as(C.POINTER(C.c_int32)),
-                    pi.ctypes.data_as(C.POINTER(C.c_int32)), tile_size, slot_cap, super_tile_observations)
+                    pi.ctypes.data_as(C.POINTER(C.c_int32)), tile_size, slot_cap, super_tile_observations, 0)
     h = C.c_void_p()
     err = C.create_string_buffer(256)
     rc = L.gb_structure_create(C.byref(d), C.byref(h), err, 256)

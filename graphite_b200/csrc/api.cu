@@ -819,7 +819,8 @@ int gb_problem_create(gb_context *ctx, const gb_problem_desc *d, gb_problem **ou
   else return ctx->fail(GB_ERR_UNSUPPORTED, "precision (T=%d,S=%d) not supported", d->precision_T, d->precision_S);
   impl->ctx = ctx;
   const std::string why = impl->hs.build(d->num_cameras, d->num_points, d->num_observations, d->camera_index,
-                                         d->point_index, d->tile_size, d->slot_cap, d->super_tile_observations);
+                                         d->point_index, d->tile_size, d->slot_cap, d->super_tile_observations,
+                                      (d->flags & GB_FLAG_PARTITION) != 0);
   if (!why.empty()) {
     delete impl;
     return ctx->fail(GB_ERR_UNSUPPORTED, "structure: %s", why.c_str());
@@ -865,7 +866,8 @@ int gb_structure_create(const gb_problem_desc *d, gb_structure **out, char *errb
   *out = nullptr;
   gb_structure *s = new gb_structure();
   const std::string why = s->hs.build(d->num_cameras, d->num_points, d->num_observations, d->camera_index,
-                                      d->point_index, d->tile_size, d->slot_cap, d->super_tile_observations);
+                                      d->point_index, d->tile_size, d->slot_cap, d->super_tile_observations,
+                                      (d->flags & GB_FLAG_PARTITION) != 0);
   if (!why.empty()) {
     if (errbuf && errlen > 0) snprintf(errbuf, errlen, "%s", why.c_str());
     delete s;

@@ -70,7 +70,7 @@ struct HostStructure {
 
   // returns an empty string on success, else the reason
   std::string build(int64_t nc, int64_t np, int64_t m, const int32_t *ci, const int32_t *pi, int tile_size,
-                    int slot_cap_opt = 0, int64_t st_obs_opt = 0) {
+                    int slot_cap_opt = 0, int64_t st_obs_opt = 0, bool partition = false) {
     if (nc <= 0 || np <= 0 || m <= 0) return "empty problem";
     if (m >= (int64_t(1) << 30) || nc + np >= (int64_t(1) << 31)) return "problem too large for 32-bit indices";
     if (tile_size <= 0) tile_size = TILE;
@@ -110,7 +110,7 @@ struct HostStructure {
     }
     if (max_track > tile_fill) return "a point has more observations than the tile size (" + std::to_string(max_track) + ")";
     if (max_track > slot_cap) return "a point has more observations than the slot cap (" + std::to_string(max_track) + ")";
-    {
+    if (!partition) {
       std::vector<uint8_t> seen((size_t)nc, 0);
       for (int64_t i = 0; i < m; i++) seen[cam_idx[i]] = 1;
       for (int64_t c = 0; c < nc; c++)

@@ -65,7 +65,11 @@ typedef struct {
   int32_t tile_size;         /* max observations per tile, 0 = default (256, the storage tile) */
   int32_t slot_cap;          /* max distinct cameras per super-tile, 0 = default (256) */
   int64_t super_tile_observations; /* target observations per super-tile (one CTA), 0 = default M / (148*8) */
+  int64_t flags;             /* GB_FLAG_* */
 } gb_problem_desc;
+/* This rank holds a point partition: cameras without a local observation are legal (their sums come from the
+ * other ranks through the all-reduce).  Without the flag such a camera is an unused vertex and is rejected. */
+#define GB_FLAG_PARTITION 1
 
 /* Replaces: Graph::initialize_optimization + build_structure (graph.hpp:92-219),
  * FactorDescriptor::initialize_device_ids (factor.hpp:455-467), Hessian::build_structure

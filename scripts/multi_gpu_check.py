@@ -21,7 +21,7 @@ uid = [binding.Context.comm_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(uid, src=0)
 ctx.comm_init(world, rank, uid[0])
 part = partition_by_point(prob, world, rank)
-P = binding.problem_from_bal(ctx, part, "f64-f64")
+P = binding.problem_from_bal(ctx, part, "f64-f64", partition=True)
 traj, res = P.lm(iterations=iters)
 cams, pts = P.get_vertices()
 ok = True
