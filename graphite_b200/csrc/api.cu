@@ -198,7 +198,9 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_TRY(upload(ts.st_row, hs.st_row));
     GB_TRY(upload(ts.row_cam, hs.row_cam));
     GB_TRY(upload(ts.cam_row_ptr, hs.cam_row_ptr));
-    GB_TRY(upload(ts.cam_row_list, hs.cam_row_list));
+    GB_TRY(upload(ts.row_out, hs.row_out));
+    GB_TRY(upload(ts.cta_st, hs.cta_st));
+    ts.ncta = hs.ncta(); ts.pad2 = 0;
     GB_TRY(upload(ts.slot_of_obs, hs.slot_of_obs));
     GB_TRY(upload(ts.cam_idx, hs.cam_idx));
     GB_TRY(upload(ts.pt_idx, hs.pt_idx));
@@ -324,7 +326,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     k_point_prepare<T><<<(ts.Np + 255) / 256, 256, 0, st>>>(ts.Np, scale_on ? 1 : 0, mu, use_identity, Cg, scale + dimc,
                                                            b + dimc, W, h, 0);
     GB_LAUNCH(ctx);
-    k_prepare_tiles<T, S, PSTAGE><<<ts.nst, 2 * TILE, PrepSmem<T, S>::TOTAL(PSTAGE), st>>>(ts, J, W, h, part54);
+    k_prepare_tiles<T, S, PSTAGE><<<ts.ncta, 2 * TILE, PrepSmem<T, S>::TOTAL(PSTAGE), st>>>(ts, J, W, h, part54);
     GB_LAUNCH(ctx);
     const bool multi = ctx->nranks > 1;
     k_cam_reduce_prepare<T><<<ts.Nc, 288, 0, st>>>(ts, part54, 0, sums54, multi ? 0 : 1, mu, use_identity, diagB, gc,
@@ -354,7 +356,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
       }
       GB_CUDA(ctx, cudaEventRecord(prof_ev[2 * prof_slot], st));
     }
-    k_schur_product<T, S, NSTAGE><<<ts.nst, 2 * TILE, SchurSmem<T, S>::TOTAL(NSTAGE), st>>>(ts, J, W, xs, part9, flag);
+    k_schur_product<T, S, NSTAGE><<<ts.ncta, 2 * TILE, SchurSmem<T, S>::TOTAL(NSTAGE), st>>>(ts, J, W, xs, part9, flag);
     GB_LAUNCH(ctx);
     if (prof) GB_CUDA(ctx, cudaEventRecord(prof_ev[2 * prof_slot + 1], st));
     const bool multi = ctx->nranks > 1;

@@ -62,7 +62,10 @@ struct DevStruct {
   const int32_t *st_tile;    // [nst+1]
   const int32_t *st_row;     // [nst+1] first partial row of the super-tile
   const int32_t *row_cam;    // [nrows] camera of each partial row
-  const int32_t *cam_row_ptr, *cam_row_list; // camera -> rows (ascending super-tile)
+  const int32_t *cam_row_ptr;  // [Nc+1] camera -> its contiguous rows in the partial buffers (ascending super-tile)
+  const int32_t *row_out;      // [nrows] super-tile row (st_row + slot) -> position in the partial buffers
+  const int32_t *cta_st;       // [ncta+1] super-tile ranges of the persistent CTAs
+  int32_t ncta, pad2;
   const int32_t *slot_of_obs; // [M] sorted observation -> storage slot (exports)
   const int32_t *cam_idx, *pt_idx, *pptr;    // sorted observations (exports)
 };
@@ -145,7 +148,7 @@ __device__ __forceinline__ void cam_gather(const DevStruct &ds, int c, const T *
   for (int g = 0; g < ngroups; g++) {
     T acc = T(0);
     if (sub < 32)
-      for (int i = b + sub; i < e; i += 32) acc += part[(int64_t)ds.cam_row_list[i] * pstride + g * 9 + k];
+      for (int i = b + sub; i < e; i += 32) acc += part[(int64_t)i * pstride + g * 9 + k];
     __syncthreads();
     if (sub < 32) sh[sub * 9 + k] = acc;
     __syncthreads();
@@ -281,7 +284,7 @@ k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
     const double tot = block_sum<double>(cost, shd);
     if (t == 0) cost_part[tile] = tot;
   }
-  for (int i = t; i < nslots * 18; i += TILE) part[(int64_t)row0 * 18 + i] = acc[i];
+  for (int i = t; i < nslots * 18; i += TILE) part[(int64_t)ds.row_out[row0 + i / 18] * 18 + i % 18] = acc[i];
 }
 
 // Camera side of linearize: diag(B), g_c, Jacobi scales s = 1/(eps + sqrt(diag)) (graph.hpp:262-270), b_c = s g_c.
@@ -471,9 +474,8 @@ k_prepare_tiles(DevStruct ds, const typename V2<S>::type *__restrict__ J, const 
   const int worker = threadIdx.x >> 8, t = threadIdx.x & (TILE - 1);
   T *acc = reinterpret_cast<T *>(smem + SM::ACC_OFF(NSTAGE));
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM::BAR_OFF(NSTAGE));
-  const int st = blockIdx.x;
-  const int tile0 = ds.st_tile[st], ntl = ds.st_tile[st + 1] - tile0;
-  const int row0 = ds.st_row[st], nslots = ds.st_row[st + 1] - row0;
+  const int st_begin = ds.cta_st[blockIdx.x], st_end = ds.cta_st[blockIdx.x + 1]; // persistent CTA, see k_schur_product
+  const int tile0 = ds.st_tile[st_begin], ntl = ds.st_tile[st_end] - tile0;
 
   auto issue = [&](int tile, int s) {
     const TileMeta tm = ds.tmeta[tile];
@@ -493,10 +495,12 @@ k_prepare_tiles(DevStruct ds, const typename V2<S>::type *__restrict__ J, const 
     fence_proxy_async();
     for (int i = 0; i < NSTAGE && i < ntl; i++) issue(tile0 + i, i);
   }
+  for (int st = st_begin; st < st_end; st++) {
+  const int row0 = ds.st_row[st], nslots = ds.st_row[st + 1] - row0;
   for (int i = threadIdx.x; i < nslots * 54; i += 2 * TILE) acc[i] = T(0);
   __syncthreads();
 
-  for (int i = 0; i < ntl; i++) {
+  for (int i = ds.st_tile[st] - tile0; i < ds.st_tile[st + 1] - tile0; i++) {
     const int s = i % NSTAGE;
     mbar_wait(&bars[s], (uint32_t)((i / NSTAGE) & 1));
     unsigned char *base = smem + s * SM::STAGE_BYTES;
@@ -566,32 +570,26 @@ k_prepare_tiles(DevStruct ds, const typename V2<S>::type *__restrict__ J, const 
       issue(tile0 + i + NSTAGE, s);
     }
   }
-  for (int i = threadIdx.x; i < nslots * 54; i += 2 * TILE) part[(int64_t)row0 * 54 + i] = acc[i];
+  for (int i = threadIdx.x; i < nslots * 54; i += 2 * TILE) part[(int64_t)ds.row_out[row0 + i / 54] * 54 + i % 54] = acc[i];
+  __syncthreads(); // acc is zeroed again for the next super-tile
+  }
 }
 
-// In-place Gauss-Jordan inverse of a 9x9 matrix in shared memory by one thread (partial pivoting).
-template <typename T> __device__ void invert9(T *A /*[81] col-major*/, T *Ai /*[81]*/) {
-  for (int i = 0; i < 81; i++) Ai[i] = T(0);
-  for (int i = 0; i < 9; i++) Ai[10 * i] = T(1);
+// Gauss-Jordan inverse of a symmetric positive definite 9x9 matrix by 162 threads on the augmented matrix
+// M = [A | I] (9 x 18, row-major in shared memory).  S_cc is SPD with a unit-scale diagonal (Jacobi scaling plus
+// damping), so no pivoting is needed.  Every thread of the block must call it (barriers inside).
+template <typename T> __device__ __forceinline__ void invert9_block(T *M /*[9*18]*/, T *f /*[9]*/, int t) {
+  const int i = t / 18, j = t - 18 * i; // element (i, j) for t < 162
   for (int c = 0; c < 9; c++) {
-    int piv = c;
-    T best = fabs(A[c + 9 * c]);
-    for (int i = c + 1; i < 9; i++) {
-      const T v = fabs(A[i + 9 * c]);
-      if (v > best) { best = v; piv = i; }
+    const T piv = M[c * 18 + c];
+    __syncthreads();
+    if (t < 162) {
+      if (i == c) M[t] = M[t] / piv;   // scale the pivot row
+      if (j == c) f[i] = M[t];         // column c before elimination (f[c] is unused)
     }
-    if (piv != c)
-      for (int j = 0; j < 9; j++) {
-        T tmp = A[c + 9 * j]; A[c + 9 * j] = A[piv + 9 * j]; A[piv + 9 * j] = tmp;
-        tmp = Ai[c + 9 * j]; Ai[c + 9 * j] = Ai[piv + 9 * j]; Ai[piv + 9 * j] = tmp;
-      }
-    const T ip = T(1) / A[c + 9 * c];
-    for (int j = 0; j < 9; j++) { A[c + 9 * j] *= ip; Ai[c + 9 * j] *= ip; }
-    for (int i = 0; i < 9; i++) {
-      if (i == c) continue;
-      const T f = A[i + 9 * c];
-      for (int j = 0; j < 9; j++) { A[i + 9 * j] -= f * A[c + 9 * j]; Ai[i + 9 * j] -= f * Ai[c + 9 * j]; }
-    }
+    __syncthreads();
+    if (t < 162 && i != c) M[t] -= f[i] * M[c * 18 + j];
+    __syncthreads();
   }
 }
 
@@ -607,7 +605,7 @@ k_cam_reduce_prepare(DevStruct ds, const T *__restrict__ part, int from_sums, T 
                      T *__restrict__ bS, T *__restrict__ dterm) {
   __shared__ T sh[32 * 9];
   __shared__ T out[54];
-  __shared__ T A[81], Ai[81];
+  __shared__ T Maug[9 * 18], fcol[9];
   const int c = blockIdx.x, t = threadIdx.x;
   if (!from_sums) {
     cam_gather<T>(ds, c, part, 54, 6, sh, out);
@@ -630,13 +628,15 @@ k_cam_reduce_prepare(DevStruct ds, const T *__restrict__ part, int from_sums, T 
       dterm[c * 9 + i] = dt;
       bS[c * 9 + i] = si * (gc[c * 9 + i] - out[45 + i]);
     }
-    A[i + 9 * j] = val;
+    Maug[i * 18 + j] = val;
+    Maug[i * 18 + 9 + j] = (i == j) ? T(1) : T(0);
     Sdiag[(int64_t)c * 81 + i + 9 * j] = val;
   }
-  __syncthreads();
-  if (t == 0) invert9<T>(A, Ai);
-  __syncthreads();
-  if (t < 81) Minv[(int64_t)c * 81 + t] = Ai[t];
+  invert9_block<T>(Maug, fcol, t);
+  if (t < 81) {
+    const int i = t % 9, j = t / 9;
+    Minv[(int64_t)c * 81 + i + 9 * j] = Maug[i * 18 + 9 + j];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -680,12 +680,14 @@ k_schur_product(DevStruct ds, const typename V2<S>::type *__restrict__ J, const 
   if (done_flag && *done_flag) return; // PCG already stopped: nothing to do (uniform across the grid)
   const int worker = threadIdx.x >> 8, t = threadIdx.x & (TILE - 1);
   T *xl = reinterpret_cast<T *>(smem + SM::XL_OFF(NSTAGE));
-  T *acc = reinterpret_cast<T *>(smem + SM::ACC_OFF(NSTAGE)) + worker * SLOT_CAP * 9;
+  T *acc_all = reinterpret_cast<T *>(smem + SM::ACC_OFF(NSTAGE));
+  T *acc = acc_all + worker * SLOT_CAP * 9;
   T *sv3 = reinterpret_cast<T *>(smem + SM::SV3_OFF(NSTAGE)) + worker * TILE * 3;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM::BAR_OFF(NSTAGE));
-  const int st = blockIdx.x;
-  const int tile0 = ds.st_tile[st], ntl = ds.st_tile[st + 1] - tile0;
-  const int row0 = ds.st_row[st], nslots = ds.st_row[st + 1] - row0;
+  // persistent CTA: a contiguous range of super-tiles = a contiguous range of tiles; the TMA ring runs across
+  // super-tile boundaries, only the camera rows (xl) and the accumulators are switched there
+  const int st_begin = ds.cta_st[blockIdx.x], st_end = ds.cta_st[blockIdx.x + 1];
+  const int tile0 = ds.st_tile[st_begin], ntl = ds.st_tile[st_end] - tile0;
 
   auto issue = [&](int tile, int s) {
     const TileMeta tm = ds.tmeta[tile];
@@ -703,107 +705,112 @@ k_schur_product(DevStruct ds, const typename V2<S>::type *__restrict__ J, const 
     fence_proxy_async();
     for (int i = 0; i < NSTAGE && i < ntl; i++) issue(tile0 + i, i);
   }
-  for (int i = threadIdx.x; i < nslots * 9; i += 2 * TILE) {
-    const int s = i / 9, k = i - 9 * s;
-    xl[i] = xs[(int64_t)ds.row_cam[row0 + s] * CAM_STRIDE + k];
-  }
-  for (int i = t; i < nslots * 9; i += TILE) acc[i] = T(0);
-  __syncthreads();
 
-  for (int i = worker; i < ntl; i += 2) {
-    const int s = i % NSTAGE;
-    mbar_wait(&bars[s], (uint32_t)((i / NSTAGE) & 1));
-    unsigned char *base = smem + s * SM::STAGE_BYTES;
-    const S2 *Js = reinterpret_cast<const S2 *>(base);
-    const unsigned char *rec = base + SM::J_BYTES;
-    const T *Ws = reinterpret_cast<const T *>(base + SM::J_BYTES + REC_BYTES);
-    const TileMeta tm = *reinterpret_cast<const TileMeta *>(rec + REC_META);
-    const uint32_t om = reinterpret_cast<const uint32_t *>(rec + REC_OMETA)[t];
-    const int cslot = (int)(om >> 16), rank = (int)((om >> 8) & 0xffu), ptl = (int)(om & 0xffu);
-    T jc[18], jp[6], y0 = T(0), y1 = T(0);
-#pragma unroll
-    for (int j = 0; j < 9; j++) {
-      const S2 v = Js[j * TILE + t];
-      jc[2 * j] = (T)v.x;
-      jc[2 * j + 1] = (T)v.y;
+  for (int st = st_begin; st < st_end; st++) {
+    const int row0 = ds.st_row[st], nslots = ds.st_row[st + 1] - row0;
+    for (int i = threadIdx.x; i < nslots * 9; i += 2 * TILE) {
+      const int s = i / 9, k = i - 9 * s;
+      xl[i] = xs[(int64_t)ds.row_cam[row0 + s] * CAM_STRIDE + k];
     }
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-      const S2 v = Js[(9 + j) * TILE + t];
-      jp[2 * j] = (T)v.x;
-      jp[2 * j + 1] = (T)v.y;
-    }
-    {
-      const T *x = xl + cslot * 9;
+    for (int i = t; i < nslots * 9; i += TILE) acc[i] = T(0);
+    __syncthreads();
+    const int ib = ds.st_tile[st] - tile0, ie = ds.st_tile[st + 1] - tile0; // ring indices of this super-tile
+    for (int i = ib + ((ib ^ worker) & 1); i < ie; i += 2) {                 // worker w takes ring indices of parity w
+      const int s = i % NSTAGE;
+      mbar_wait(&bars[s], (uint32_t)((i / NSTAGE) & 1));
+      unsigned char *base = smem + s * SM::STAGE_BYTES;
+      const S2 *Js = reinterpret_cast<const S2 *>(base);
+      const unsigned char *rec = base + SM::J_BYTES;
+      const T *Ws = reinterpret_cast<const T *>(base + SM::J_BYTES + REC_BYTES);
+      const TileMeta tm = *reinterpret_cast<const TileMeta *>(rec + REC_META);
+      const uint32_t om = reinterpret_cast<const uint32_t *>(rec + REC_OMETA)[t];
+      const int cslot = (int)(om >> 16), rank = (int)((om >> 8) & 0xffu), ptl = (int)(om & 0xffu);
+      T jc[18], jp[6], y0 = T(0), y1 = T(0);
 #pragma unroll
       for (int j = 0; j < 9; j++) {
-        const T xv = x[j];
-        y0 += jc[2 * j] * xv;
-        y1 += jc[2 * j + 1] * xv;
+        const S2 v = Js[j * TILE + t];
+        jc[2 * j] = (T)v.x;
+        jc[2 * j + 1] = (T)v.y;
       }
-    }
-    sv3[t * 3 + 0] = jp[0] * y0 + jp[1] * y1;
-    sv3[t * 3 + 1] = jp[2] * y0 + jp[3] * y1;
-    sv3[t * 3 + 2] = jp[4] * y0 + jp[5] * y1;
-    worker_sync(worker); // also: every thread has its J values in registers, the stage's J region may be reused
-    T *sv = reinterpret_cast<T *>(base + SM::SV_IN_STAGE);
-    T *sw = reinterpret_cast<T *>(base + SM::SW_IN_STAGE);
-    {
-      const uint16_t *pt = reinterpret_cast<const uint16_t *>(rec + REC_PT);
-      for (int item = t; item < tm.np * 3; item += TILE) {
-        const int q = item / 3, k = item - 3 * q;
-        const int b = pt[q], e = pt[q + 1];
-        T a = T(0);
-        for (int row = b; row < e; row++) a += sv3[row * 3 + k];
-        sw[item] = a;
-      }
-    }
-    worker_sync(worker);
-    {
-      const T t0 = sw[ptl * 3], t1 = sw[ptl * 3 + 1], t2 = sw[ptl * 3 + 2];
-      const T *w = Ws + ptl * WST<T>::value;
-      const T w0 = w[0] * t0 + w[1] * t1 + w[2] * t2;
-      const T w1 = w[1] * t0 + w[3] * t1 + w[4] * t2;
-      const T w2 = w[2] * t0 + w[4] * t1 + w[5] * t2;
-      const T d0 = y0 - (jp[0] * w0 + jp[2] * w1 + jp[4] * w2);
-      const T d1 = y1 - (jp[1] * w0 + jp[3] * w1 + jp[5] * w2);
-      // stage v = Jc^T d at the slot's rank: camera segments become contiguous rows
 #pragma unroll
-      for (int k = 0; k < 9; k++) sv[rank * 9 + k] = jc[2 * k] * d0 + jc[2 * k + 1] * d1;
-    }
-    worker_sync(worker);
-    {
-      // one thread per (segment, component triple): sum the segment's rows, add to the camera's accumulator row
-      const uint32_t *sg = reinterpret_cast<const uint32_t *>(rec + REC_SEG);
-      for (int item = t; item < tm.nseg * 3; item += TILE) {
-        const int q = item / 3, g = item - 3 * q;
-        const uint32_t e0 = sg[q], e1 = sg[q + 1];
-        const int b = (int)(e0 >> 16), e = (int)(e1 >> 16), cs = (int)(e0 & 0xffffu);
-        T a0 = T(0), a1 = T(0), a2 = T(0);
-        for (int row = b; row < e; row++) {
-          const T *r = sv + row * 9 + 3 * g;
-          a0 += r[0];
-          a1 += r[1];
-          a2 += r[2];
+      for (int j = 0; j < 3; j++) {
+        const S2 v = Js[(9 + j) * TILE + t];
+        jp[2 * j] = (T)v.x;
+        jp[2 * j + 1] = (T)v.y;
+      }
+      {
+        const T *x = xl + cslot * 9;
+#pragma unroll
+        for (int j = 0; j < 9; j++) {
+          const T xv = x[j];
+          y0 += jc[2 * j] * xv;
+          y1 += jc[2 * j + 1] * xv;
         }
-        T *ar = acc + cs * 9 + 3 * g;
-        ar[0] += a0;
-        ar[1] += a1;
-        ar[2] += a2;
+      }
+      sv3[t * 3 + 0] = jp[0] * y0 + jp[1] * y1;
+      sv3[t * 3 + 1] = jp[2] * y0 + jp[3] * y1;
+      sv3[t * 3 + 2] = jp[4] * y0 + jp[5] * y1;
+      worker_sync(worker); // also: every thread has its J values in registers, the stage's J region may be reused
+      T *sv = reinterpret_cast<T *>(base + SM::SV_IN_STAGE);
+      T *sw = reinterpret_cast<T *>(base + SM::SW_IN_STAGE);
+      {
+        const uint16_t *pt = reinterpret_cast<const uint16_t *>(rec + REC_PT);
+        for (int item = t; item < tm.np * 3; item += TILE) {
+          const int q = item / 3, k = item - 3 * q;
+          const int b = pt[q], e = pt[q + 1];
+          T a = T(0);
+          for (int row = b; row < e; row++) a += sv3[row * 3 + k];
+          sw[item] = a;
+        }
+      }
+      worker_sync(worker);
+      {
+        const T t0 = sw[ptl * 3], t1 = sw[ptl * 3 + 1], t2 = sw[ptl * 3 + 2];
+        const T *w = Ws + ptl * WST<T>::value;
+        const T w0 = w[0] * t0 + w[1] * t1 + w[2] * t2;
+        const T w1 = w[1] * t0 + w[3] * t1 + w[4] * t2;
+        const T w2 = w[2] * t0 + w[4] * t1 + w[5] * t2;
+        const T d0 = y0 - (jp[0] * w0 + jp[2] * w1 + jp[4] * w2);
+        const T d1 = y1 - (jp[1] * w0 + jp[3] * w1 + jp[5] * w2);
+        // stage v = Jc^T d at the slot's rank: camera segments become contiguous rows
+#pragma unroll
+        for (int k = 0; k < 9; k++) sv[rank * 9 + k] = jc[2 * k] * d0 + jc[2 * k + 1] * d1;
+      }
+      worker_sync(worker);
+      {
+        // one thread per (segment, component triple): sum the segment's rows, add to the camera's accumulator row
+        const uint32_t *sg = reinterpret_cast<const uint32_t *>(rec + REC_SEG);
+        for (int item = t; item < tm.nseg * 3; item += TILE) {
+          const int q = item / 3, g = item - 3 * q;
+          const uint32_t e0 = sg[q], e1 = sg[q + 1];
+          const int b = (int)(e0 >> 16), e = (int)(e1 >> 16), cs = (int)(e0 & 0xffffu);
+          T a0 = T(0), a1 = T(0), a2 = T(0);
+          for (int row = b; row < e; row++) {
+            const T *r = sv + row * 9 + 3 * g;
+            a0 += r[0];
+            a1 += r[1];
+            a2 += r[2];
+          }
+          T *ar = acc + cs * 9 + 3 * g;
+          ar[0] += a0;
+          ar[1] += a1;
+          ar[2] += a2;
+        }
+      }
+      worker_sync(worker);
+      // the stage is free (all threads of the worker are past the barrier): refill it with tile i + NSTAGE
+      if (t == 0 && i + NSTAGE < ntl) {
+        fence_proxy_async();
+        issue(tile0 + i + NSTAGE, s);
       }
     }
-    worker_sync(worker);
-    // the stage is free (all threads of the worker are past the barrier): refill it with tile i + NSTAGE
-    if (t == 0 && i + NSTAGE < ntl) {
-      fence_proxy_async();
-      issue(tile0 + i + NSTAGE, s);
+    __syncthreads();
+    // rows of this super-tile: worker 0 (even ring indices) + worker 1 (odd), fixed order
+    for (int i = threadIdx.x; i < nslots * 9; i += 2 * TILE) {
+      const int s = i / 9, k = i - 9 * s;
+      part[(int64_t)ds.row_out[row0 + s] * 9 + k] = acc_all[i] + acc_all[SLOT_CAP * 9 + i];
     }
-  }
-  __syncthreads();
-  {
-    const T *acc0 = reinterpret_cast<const T *>(smem + SM::ACC_OFF(NSTAGE));
-    for (int i = threadIdx.x; i < nslots * 9; i += 2 * TILE)
-      part[(int64_t)row0 * 9 + i] = acc0[i] + acc0[SLOT_CAP * 9 + i]; // worker 0 (even tiles) + worker 1 (odd tiles)
+    __syncthreads(); // xl / acc are rewritten by the next super-tile
   }
 }
 

@@ -52,6 +52,10 @@ struct TileMeta {
 struct HostStructure {
   int64_t M = 0, Mstore = 0;
   int32_t Nc = 0, Np = 0, tile_fill = TILE, slot_cap = SLOT_CAP;
+  // CTAs of the TMA kernels.  Measured on Venice: 148 persistent CTAs (static ranges, ring running across
+  // super-tile boundaries) were 12 % slower than one CTA per super-tile scheduled by the hardware (SM-to-SM
+  // spread of identical work is >= 10 %), so the default is one super-tile per CTA.
+  int32_t persistent_ctas = 1 << 30;
   bool identity_perm = true;
   std::vector<int64_t> perm;  // sorted position -> caller's factor index (empty when identity)
   std::vector<int32_t> cam_idx, pt_idx, pptr;  // sorted by (point, camera)
@@ -62,6 +66,8 @@ struct HostStructure {
   std::vector<uint16_t> pt_tab;
   std::vector<uint8_t> trec;                    // [ntiles][REC_BYTES] packed copy of the three tables + meta
   std::vector<int32_t> st_tile, st_row, row_cam, cam_row_ptr, cam_row_list, slot_of_obs;
+  std::vector<int32_t> row_out;                 // [nrows] super-tile row -> camera-major position in the partial buffers
+  std::vector<int32_t> cta_st;                  // [ncta+1] super-tile ranges of the persistent CTAs (balanced by tiles)
   std::vector<int32_t> tile_cam;                // [Mstore] camera per storage slot (0 in padding)
   // per sorted observation (tests / host view): rank in tile order and camera segment count
   std::vector<uint8_t> rank;
@@ -242,12 +248,29 @@ struct HostStructure {
     cam_row_list.resize(nrows);
     std::vector<int32_t> fill(cam_row_ptr.begin(), cam_row_ptr.end() - 1);
     for (int32_t r = 0; r < nrows; r++) cam_row_list[fill[row_cam[r]]++] = r;
+    // partial buffers are camera-major: the rows of one camera are contiguous, in ascending super-tile order
+    row_out.resize(nrows);
+    for (int32_t i = 0; i < nrows; i++) row_out[cam_row_list[i]] = i;
+    // persistent CTAs: contiguous super-tile ranges with near-equal tile counts
+    {
+      const int32_t ncta = std::min<int32_t>(nst, persistent_ctas);
+      cta_st.assign(1, 0);
+      for (int32_t b = 1; b < ncta; b++) {
+        const int64_t target = (int64_t)nt * b / ncta; // first tile of CTA b
+        int32_t sidx = (int32_t)(std::lower_bound(st_tile.begin(), st_tile.end() - 1, (int32_t)target) - st_tile.begin());
+        sidx = std::max(sidx, cta_st.back() + 1);
+        sidx = std::min(sidx, nst - (ncta - b));
+        cta_st.push_back(sidx);
+      }
+      cta_st.push_back(nst);
+    }
     return "";
   }
 
   int32_t ntiles() const { return (int32_t)tile_obs.size() - 1; }
   int32_t nst() const { return (int32_t)st_tile.size() - 1; }
   int32_t nrows() const { return (int32_t)row_cam.size(); }
+  int32_t ncta() const { return (int32_t)cta_st.size() - 1; }
 
   // Upper block-CSC of the Hessian in the reference's order (hessian.hpp:59-84, 270-278; csc_utils.hpp:16-50).
   void hessian_structure(int64_t *colptr, int64_t *rowidx, int64_t *offsets) const {
