@@ -13,8 +13,8 @@
 // Reductions are atomic-free and deterministic:
 //   by point  - a point's observations are contiguous inside one tile: staged in shared memory, summed
 //               sequentially by one thread per (point, component);
-//   by camera - the structure build gives every slot its RANK in the tile's (camera, observation) order and the
-//               tile's camera SEGMENTS.  Threads stage their 9-vectors in shared memory at their rank; one
+//   by camera - the slots of a tile are in (camera, observation) order, so a camera SEGMENT is a run of adjacent
+//               threads.  Threads stage their 9-vectors in shared memory at their own row; one
 //               thread per (segment, component) sums the segment and adds it to the super-tile's accumulator
 //               row of that camera in shared memory (exactly one writer per row and tile, tiles in order).
 //               At the end the CTA writes its rows; a per-camera kernel sums the rows of all super-tiles in
@@ -38,6 +38,7 @@ constexpr int NPLANES = 12;
 constexpr int SMEM_LIN = TILE * 9 + SLOT_CAP * 18;
 // per-point W row stride: 6 values, padded to 8 in FP32 so that a tile's rows start 16-byte aligned (TMA)
 template <typename T> struct WST { static constexpr int value = sizeof(T) == 4 ? 8 : 6; };
+constexpr int ACC54 = 55; // shared-memory stride of the 54-wide accumulator rows (odd: rows start in different banks)
 constexpr int HST = 4; // per-point h row stride (3 values + pad): 16-byte aligned rows in FP32 and FP64
 
 template <typename T> struct V2;
@@ -54,7 +55,7 @@ struct DevStruct {
   int64_t M, Mstore;
   int32_t Nc, Np, ntiles, nst, nrows, pad;
   const TileMeta *tmeta;     // [ntiles]
-  const uint32_t *ometa;     // [Mstore]  cslot:16 | rank:8 | point-in-tile:8
+  const uint32_t *ometa;     // [Mstore]  cslot:16 | position in point order:8 | point-in-tile:8
   const uint32_t *seg_tab;   // per tile at seg_off: nseg + 1 entries  begin:16 | cslot:16
   const uint16_t *pt_tab;    // per tile at pt_off: np + 1 row offsets
   const unsigned char *trec; // [ntiles][REC_BYTES] packed per-tile record (ometa | seg_tab | pt_tab | meta)
@@ -249,8 +250,8 @@ k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
       for (int j = 0; j < 18; j++) B.Jc[j] = (T)(S)B.Jc[j];
 #pragma unroll
       for (int j = 0; j < 6; j++) B.Jp[j] = (T)(S)B.Jp[j];
-      // point side: C (6 unique) and g = -Jp^T r
-      T *row = sv + t * 9;
+      // point side: C (6 unique) and g = -Jp^T r, staged at the observation's position in point order
+      T *row = sv + rank * 9;
       row[0] = B.Jp[0] * B.Jp[0] + B.Jp[1] * B.Jp[1];
       row[1] = B.Jp[0] * B.Jp[2] + B.Jp[1] * B.Jp[3];
       row[2] = B.Jp[0] * B.Jp[4] + B.Jp[1] * B.Jp[5];
@@ -276,10 +277,10 @@ k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
     T v[9];
 #pragma unroll
     for (int k = 0; k < 9; k++) v[k] = active ? B.Jc[2 * k] * B.Jc[2 * k] + B.Jc[2 * k + 1] * B.Jc[2 * k + 1] : T(0);
-    tile_cam_accumulate<T>(v, rank, tm.nseg, ds.seg_tab + tm.seg_off, sv, acc, 18, 0);
+    tile_cam_accumulate<T>(v, t, tm.nseg, ds.seg_tab + tm.seg_off, sv, acc, 18, 0);
 #pragma unroll
     for (int k = 0; k < 9; k++) v[k] = active ? -(B.Jc[2 * k] * B.r[0] + B.Jc[2 * k + 1] * B.r[1]) : T(0);
-    tile_cam_accumulate<T>(v, rank, tm.nseg, ds.seg_tab + tm.seg_off, sv, acc, 18, 9);
+    tile_cam_accumulate<T>(v, t, tm.nseg, ds.seg_tab + tm.seg_off, sv, acc, 18, 9);
     // per-tile cost partial with the same reduction tree as k_cost_tiles: chi2 of linearize == chi2 of cost, bit for bit
     const double tot = block_sum<double>(cost, shd);
     if (t == 0) cost_part[tile] = tot;
@@ -401,7 +402,7 @@ template <typename T, typename S> struct PrepSmem {
   // the two staging areas reuse the consumed J region when they fit (T == S); else they get their own space
   static constexpr bool SV_ALIAS = 2 * SV_BYTES <= J_BYTES;
   static constexpr int ACC_OFF(int nstage) { return nstage * STAGE_BYTES; }
-  static constexpr int SV_OFF(int nstage) { return ACC_OFF(nstage) + SLOT_CAP * 54 * (int)sizeof(T); }
+  static constexpr int SV_OFF(int nstage) { return ACC_OFF(nstage) + SLOT_CAP * ACC54 * (int)sizeof(T); }
   static constexpr int BAR_OFF(int nstage) { return SV_OFF(nstage) + (SV_ALIAS ? 0 : 2 * SV_BYTES); }
   static constexpr int TOTAL(int nstage) { return BAR_OFF(nstage) + 64; }
 };
@@ -497,7 +498,7 @@ k_prepare_tiles(DevStruct ds, const typename V2<S>::type *__restrict__ J, const 
   }
   for (int st = st_begin; st < st_end; st++) {
   const int row0 = ds.st_row[st], nslots = ds.st_row[st + 1] - row0;
-  for (int i = threadIdx.x; i < nslots * 54; i += 2 * TILE) acc[i] = T(0);
+  for (int i = threadIdx.x; i < nslots * ACC54; i += 2 * TILE) acc[i] = T(0);
   __syncthreads();
 
   for (int i = ds.st_tile[st] - tile0; i < ds.st_tile[st + 1] - tile0; i++) {
@@ -510,7 +511,7 @@ k_prepare_tiles(DevStruct ds, const typename V2<S>::type *__restrict__ J, const 
     const T *Hs = reinterpret_cast<const T *>(base + SM::J_BYTES + REC_BYTES + SM::W_BYTES);
     const TileMeta tm = *reinterpret_cast<const TileMeta *>(rec + REC_META);
     const uint32_t om = reinterpret_cast<const uint32_t *>(rec + REC_OMETA)[t];
-    const int rank = (int)((om >> 8) & 0xffu), ptl = (int)(om & 0xffu);
+    const int ptl = (int)(om & 0xffu);
     T jc[18], jp[6], K[18];
 #pragma unroll
     for (int j = 0; j < 9; j++) {
@@ -551,18 +552,18 @@ k_prepare_tiles(DevStruct ds, const typename V2<S>::type *__restrict__ J, const 
     T v[9];
     if (worker == 0) {
       prep_group<T, 0>(jc, K, q0, q1, v);
-      worker_cam_accumulate<T>(v, rank, tm.nseg, sg, sv, acc, 54, 0, worker, t);
+      worker_cam_accumulate<T>(v, t, tm.nseg, sg, sv, acc, ACC54, 0, worker, t);
       prep_group<T, 1>(jc, K, q0, q1, v);
-      worker_cam_accumulate<T>(v, rank, tm.nseg, sg, sv, acc, 54, 9, worker, t);
+      worker_cam_accumulate<T>(v, t, tm.nseg, sg, sv, acc, ACC54, 9, worker, t);
       prep_group<T, 2>(jc, K, q0, q1, v);
-      worker_cam_accumulate<T>(v, rank, tm.nseg, sg, sv, acc, 54, 18, worker, t);
+      worker_cam_accumulate<T>(v, t, tm.nseg, sg, sv, acc, ACC54, 18, worker, t);
     } else {
       prep_group<T, 3>(jc, K, q0, q1, v);
-      worker_cam_accumulate<T>(v, rank, tm.nseg, sg, sv, acc, 54, 27, worker, t);
+      worker_cam_accumulate<T>(v, t, tm.nseg, sg, sv, acc, ACC54, 27, worker, t);
       prep_group<T, 4>(jc, K, q0, q1, v);
-      worker_cam_accumulate<T>(v, rank, tm.nseg, sg, sv, acc, 54, 36, worker, t);
+      worker_cam_accumulate<T>(v, t, tm.nseg, sg, sv, acc, ACC54, 36, worker, t);
       prep_group<T, 5>(jc, K, q0, q1, v);
-      worker_cam_accumulate<T>(v, rank, tm.nseg, sg, sv, acc, 54, 45, worker, t);
+      worker_cam_accumulate<T>(v, t, tm.nseg, sg, sv, acc, ACC54, 45, worker, t);
     }
     __syncthreads(); // both workers are done with the stage
     if (threadIdx.x == 0 && i + NSTAGE < ntl) {
@@ -570,7 +571,8 @@ k_prepare_tiles(DevStruct ds, const typename V2<S>::type *__restrict__ J, const 
       issue(tile0 + i + NSTAGE, s);
     }
   }
-  for (int i = threadIdx.x; i < nslots * 54; i += 2 * TILE) part[(int64_t)ds.row_out[row0 + i / 54] * 54 + i % 54] = acc[i];
+  for (int i = threadIdx.x; i < nslots * 54; i += 2 * TILE)
+    part[(int64_t)ds.row_out[row0 + i / 54] * 54 + i % 54] = acc[(i / 54) * ACC54 + i % 54];
   __syncthreads(); // acc is zeroed again for the next super-tile
   }
 }
@@ -747,9 +749,9 @@ k_schur_product(DevStruct ds, const typename V2<S>::type *__restrict__ J, const 
           y1 += jc[2 * j + 1] * xv;
         }
       }
-      sv3[t * 3 + 0] = jp[0] * y0 + jp[1] * y1;
-      sv3[t * 3 + 1] = jp[2] * y0 + jp[3] * y1;
-      sv3[t * 3 + 2] = jp[4] * y0 + jp[5] * y1;
+      sv3[rank * 3 + 0] = jp[0] * y0 + jp[1] * y1; // staged at the position in point order
+      sv3[rank * 3 + 1] = jp[2] * y0 + jp[3] * y1;
+      sv3[rank * 3 + 2] = jp[4] * y0 + jp[5] * y1;
       worker_sync(worker); // also: every thread has its J values in registers, the stage's J region may be reused
       T *sv = reinterpret_cast<T *>(base + SM::SV_IN_STAGE);
       T *sw = reinterpret_cast<T *>(base + SM::SW_IN_STAGE);
@@ -772,9 +774,9 @@ k_schur_product(DevStruct ds, const typename V2<S>::type *__restrict__ J, const 
         const T w2 = w[2] * t0 + w[4] * t1 + w[5] * t2;
         const T d0 = y0 - (jp[0] * w0 + jp[2] * w1 + jp[4] * w2);
         const T d1 = y1 - (jp[1] * w0 + jp[3] * w1 + jp[5] * w2);
-        // stage v = Jc^T d at the slot's rank: camera segments become contiguous rows
+        // stage v = Jc^T d at the slot's own row: slots are in camera order, so camera segments are contiguous rows
 #pragma unroll
-        for (int k = 0; k < 9; k++) sv[rank * 9 + k] = jc[2 * k] * d0 + jc[2 * k + 1] * d1;
+        for (int k = 0; k < 9; k++) sv[t * 9 + k] = jc[2 * k] * d0 + jc[2 * k + 1] * d1;
       }
       worker_sync(worker);
       {
@@ -842,10 +844,10 @@ k_backsubst_tiles(DevStruct ds, const typename V2<S>::type *__restrict__ J, cons
       y1 += jc[2 * j + 1] * x[j];
     }
   }
-  (void)om;
-  sv3[t * 3 + 0] = jp[0] * y0 + jp[1] * y1;
-  sv3[t * 3 + 1] = jp[2] * y0 + jp[3] * y1;
-  sv3[t * 3 + 2] = jp[4] * y0 + jp[5] * y1;
+  const int prank = (int)((om >> 8) & 0xffu);
+  sv3[prank * 3 + 0] = jp[0] * y0 + jp[1] * y1; // staged at the position in point order
+  sv3[prank * 3 + 1] = jp[2] * y0 + jp[3] * y1;
+  sv3[prank * 3 + 2] = jp[4] * y0 + jp[5] * y1;
   __syncthreads();
   double rho = 0.0;
   if (t < tm.np) {

@@ -15,8 +15,9 @@
 //   SUPER-TILE  consecutive tiles owned by one CTA; it keeps one shared-memory accumulator row per distinct
 //               camera it touches (<= slot_cap rows).  Rows of all super-tiles form the "partial rows" that the
 //               per-camera kernels sum in ascending super-tile order (camera -> row CSR).
-//   per slot    packed meta  cslot:16 | rank:8 | point-in-tile:8   (rank = position in the tile's
-//               (camera, observation) order, used to stage values so that camera segments are contiguous)
+//   per slot    slots of a tile are in (camera, observation) order, so the threads of one camera segment are
+//               adjacent; packed meta  cslot:16 | prank:8 | point-in-tile:8  (prank = position of the observation in
+//               the tile's (point, camera) order, where the point-side sums are staged)
 //   per tile    segment table (begin:16 | cslot:16) and point offset table.
 #pragma once
 #include <algorithm>
@@ -209,15 +210,18 @@ struct HostStructure {
           rank[o0 + pos] = (uint8_t)u;
           const uint32_t cslot = (uint32_t)local[loc[u].first];
           const uint32_t ptl = (uint32_t)(pt_idx[o0 + pos] - p0);
-          ometa[(size_t)k * TILE + pos] = (cslot << 16) | ((uint32_t)u << 8) | ptl;
-          slot_of_obs[o0 + pos] = k * TILE + pos;
-          tile_cam[(size_t)k * TILE + pos] = loc[u].first;
+          // the slot of an observation is its position u in the tile's (camera, observation) order: threads of one
+          // camera segment are adjacent (broadcast reads of the camera row, conflict-free staging); the meta keeps
+          // the position `pos` in (point, camera) order, where the point-side sums are staged
+          ometa[(size_t)k * TILE + u] = (cslot << 16) | ((uint32_t)pos << 8) | ptl;
+          slot_of_obs[o0 + pos] = k * TILE + u;
+          tile_cam[(size_t)k * TILE + u] = loc[u].first;
           if (u == 0 || loc[u].first != loc[u - 1].first) {
             seg_tab.push_back(((uint32_t)u << 16) | cslot);
             nseg++;
           }
         }
-        // padding slots: unique ranks n..TILE-1 (their rows are never read), camera slot 0, point 0
+        // padding slots: unique point-order positions n..TILE-1 (their rows are never read), camera slot 0, point 0
         for (int32_t u = n; u < TILE; u++) ometa[(size_t)k * TILE + u] = ((uint32_t)u << 8);
         tm.nseg = nseg;
         nseg_total += nseg;

@@ -69,9 +69,9 @@ def test_tiles_ranks_segments_and_super_tiles(built, tile, cap, st_obs):
     assert sizes.min() > 0 and sizes.max() <= fill
     assert np.array_equal(s["pptr"][tp], to), "tiles hold whole points"
     assert s["info"]["storage_slots"] == nt * 256 and len(s["ometa"]) == nt * 256
-    # storage slots: tile-padded, observation i of tile k at k*256 + (i - tile start)
-    exp_slot = np.concatenate([k * 256 + np.arange(sizes[k]) for k in range(nt)])
-    assert np.array_equal(s["slot_of_obs"], exp_slot)
+    # storage slots: tile-padded; inside a tile the slots are in (camera, observation) order
+    slot = s["slot_of_obs"]
+    assert sorted(slot.tolist()) == sorted(np.concatenate([k * 256 + np.arange(sizes[k]) for k in range(nt)]).tolist())
     st_tile, st_row, row_cam = s["st_tile"], s["st_row"], s["row_cam"]
     assert st_tile[0] == 0 and st_tile[-1] == nt and np.all(np.diff(st_tile) > 0)
     assert np.diff(st_row).max() <= capv
@@ -85,14 +85,18 @@ def test_tiles_ranks_segments_and_super_tiles(built, tile, cap, st_obs):
             p0, n, npt, ns, seg_off, pt_off, o0k, _ = tm[k]
             assert (p0, n, npt, o0k) == (tp[k], sizes[k], tp[k + 1] - tp[k], to[k])
             om = s["ometa"][k * 256:(k + 1) * 256]
-            cslot, rank, ptl = om >> 16, (om >> 8) & 0xff, om & 0xff
-            assert sorted(rank.tolist()) == list(range(256)), "ranks are a permutation of the 256 slots"
-            assert np.array_equal(rank[:n], s["rank"][to[k]:to[k + 1]])
-            assert np.array_equal(rows[cslot[:n]], prob.cam_idx[to[k]:to[k + 1]])
-            assert np.array_equal(ptl[:n] + p0, prob.pt_idx[to[k]:to[k + 1]])
-            order = np.empty(n, dtype=int); order[rank[:n]] = np.arange(n)
-            cams_sorted = prob.cam_idx[to[k]:to[k + 1]][order]
-            assert np.all(np.diff(cams_sorted) >= 0)
+            cslot, prank, ptl = om >> 16, (om >> 8) & 0xff, om & 0xff
+            assert sorted(prank.tolist()) == list(range(256)), "point-order positions are a permutation of the 256 slots"
+            # slot u of the tile holds the observation at point-order position prank[u]
+            obs_of_slot = to[k] + prank[:n].astype(int)
+            assert np.array_equal(slot[obs_of_slot], k * 256 + np.arange(n))
+            assert np.array_equal(s["rank"][obs_of_slot], np.arange(n))
+            cams_sorted = prob.cam_idx[obs_of_slot]
+            assert np.all(np.diff(cams_sorted) >= 0), "slots are sorted by camera"
+            same = np.diff(cams_sorted) == 0
+            assert np.all(np.diff(prank[:n].astype(int))[same] > 0), "and by observation inside a camera"
+            assert np.array_equal(rows[cslot[:n]], cams_sorted)
+            assert np.array_equal(ptl[:n] + p0, prob.pt_idx[obs_of_slot])
             seg = s["seg_tab"][seg_off:seg_off + ns + 1]
             begins, slots = seg >> 16, seg & 0xffff
             heads = np.flatnonzero(np.diff(cams_sorted, prepend=-1) != 0)
