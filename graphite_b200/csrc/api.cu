@@ -125,6 +125,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
   S2 *J = nullptr; // tile-major [ntiles][12][256]
   T *Cg = nullptr, *part18 = nullptr, *part54 = nullptr, *part9 = nullptr, *sums54 = nullptr;
   T *dot_part = nullptr, *rz_part = nullptr;
+  bool coop_update = false; // the fused PCG update needs all its CTAs co-resident
   T *diagB = nullptr, *gc = nullptr, *scale = nullptr /*[9Nc+3Np]*/, *b = nullptr /*[9Nc+3Np]*/;
   T *W = nullptr, *h = nullptr;
   T *Sdiag = nullptr, *Minv = nullptr, *bS = nullptr, *dterm = nullptr;
@@ -214,6 +215,13 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_TRY(dalloc(part18, (size_t)ts.nrows * 18)); GB_TRY(dalloc(part54, (size_t)ts.nrows * 54));
     GB_TRY(dalloc(part9, (size_t)ts.nrows * 9)); GB_TRY(dalloc(sums54, Nc * 54));
     GB_TRY(dalloc(dot_part, Nc)); GB_TRY(dalloc(rz_part, Nc));
+    {
+      int per_sm = 0, sms = 0, coop = 0;
+      GB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_update<T>, 288, 0));
+      GB_CUDA(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+      GB_CUDA(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
+      coop_update = coop && (int64_t)per_sm * sms >= (Nc + PCG_CAMS - 1) / PCG_CAMS;
+    }
     // the super-tile kernels keep their camera accumulator rows in (opt-in sized) dynamic shared memory
     GB_CUDA(ctx, cudaFuncSetAttribute(k_linearize<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIN * sizeof(T))));
     GB_CUDA(ctx, cudaFuncSetAttribute(k_prepare_tiles<T, S, PSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -356,11 +364,14 @@ template <typename T, typename S> struct Problem : ProblemBase {
       }
       GB_CUDA(ctx, cudaEventRecord(prof_ev[2 * prof_slot], st));
     }
+    const bool multi = ctx->nranks > 1;
+    const int finish = (!multi && pvec) ? 1 : 0;
     k_schur_product<T, S, NSTAGE><<<ts.ncta, 2 * TILE, SchurSmem<T, S>::TOTAL(NSTAGE), st>>>(ts, J, W, xs, part9, flag);
     GB_LAUNCH(ctx);
     if (prof) GB_CUDA(ctx, cudaEventRecord(prof_ev[2 * prof_slot + 1], st));
-    const bool multi = ctx->nranks > 1;
-    const int finish = (!multi && pvec) ? 1 : 0;
+    // The per-camera sum of the partial rows stays a separate, massively parallel kernel: fused into the tail of
+    // the product kernel (last-arriver-reduces with per-camera counters) it cost 25 us per CTA of exposed latency,
+    // because that kernel runs one CTA per SM (measured 463 us vs 249 + 11 us).
     k_cam_reduce_spmv<T><<<ts.Nc, 288, 0, st>>>(ts, part9, scale, Ap_raw, finish, dterm, pvec, Ap, dot_part, flag);
     GB_LAUNCH(ctx);
     if (multi) {
@@ -382,15 +393,27 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_LAUNCH(ctx);
     k_pcg_init_state<T><<<1, 1024, 0, st>>>(ts.Nc, rz_part, pcg_state);
     GB_LAUNCH(ctx);
+    const T tol = (T)o->tolerance, ratio = (T)o->rejection_ratio;
+    const int max_iter = (int)o->max_iterations, nc = ts.Nc;
     for (int64_t k = 0; k < o->max_iterations; k++) {
       GB_TRY(enqueue_schur_product(done_flag, pv, (int)k));
-      k_pcg_update1<T><<<gridc, 288, 0, st>>>(ts.Nc, pcg_state + 2 * k, pcg_state + 2 * k + 1, dot_part, Ap, Minv, x, xbak,
-                                              r, z, pv, rz_part, done_flag);
-      GB_LAUNCH(ctx);
-      k_pcg_update2<T><<<gridc, 288, 0, st>>>(ts.Nc, pcg_state + 2 * k + 1, pcg_state + 2 * k + 2, (T)o->tolerance,
-                                              (T)o->rejection_ratio, (int)o->max_iterations, scale, rz_part, x, xbak, z, pv,
-                                              xs, done_flag);
-      GB_LAUNCH(ctx);
+      if (coop_update) {
+        // both halves of the vector update in one cooperative launch (grid-wide sync instead of a kernel boundary)
+        PcgState<T> *stp = pcg_state + 2 * k;
+        const T *c_dot = dot_part, *c_Ap = Ap, *c_Minv = Minv, *c_scale = scale;
+        void *args[] = {(void *)&nc, (void *)&stp, (void *)&tol, (void *)&ratio, (void *)&max_iter, (void *)&c_dot,
+                        (void *)&c_Ap, (void *)&c_Minv, (void *)&c_scale, (void *)&x, (void *)&xbak, (void *)&r,
+                        (void *)&z, (void *)&pv, (void *)&xs, (void *)&rz_part, (void *)&done_flag};
+        GB_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)k_pcg_update<T>, dim3(gridc), dim3(288), args, 0, st));
+        GB_LAUNCH(ctx);
+      } else {
+        k_pcg_update1<T><<<gridc, 288, 0, st>>>(ts.Nc, pcg_state + 2 * k, pcg_state + 2 * k + 1, dot_part, Ap, Minv, x, xbak,
+                                                r, z, pv, rz_part, done_flag);
+        GB_LAUNCH(ctx);
+        k_pcg_update2<T><<<gridc, 288, 0, st>>>(ts.Nc, pcg_state + 2 * k + 1, pcg_state + 2 * k + 2, tol, ratio, max_iter,
+                                                scale, rz_part, x, xbak, z, pv, xs, done_flag);
+        GB_LAUNCH(ctx);
+      }
     }
     GB_CUDA(ctx, cudaMemcpyAsync(h_state, pcg_state + 2 * o->max_iterations, sizeof(PcgState<T>), cudaMemcpyDeviceToHost, st));
     GB_TRY(launch_check());

@@ -25,6 +25,7 @@
 #pragma once
 #include <cfloat>
 #include <cstdint>
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include "bal_math.cuh"
@@ -994,29 +995,27 @@ k_pcg_init_state(int Nc, const T *__restrict__ rz_part, PcgState<T> *st) {
   }
 }
 
-// first half of an iteration (Ap and the p.Ap partials are ready): denom, alpha, x/r update, z = Minv r, r.z partials
+// first half of an iteration (Ap and the p.Ap partials are ready): denom, alpha, x/r update, z = Minv r, r.z partials.
+// Returns false when the iteration stops here (uniform across the grid: every CTA sees the same state and sums).
 template <typename T>
-__global__ void __launch_bounds__(288)
-k_pcg_update1(int Nc, const PcgState<T> *__restrict__ sin, PcgState<T> *__restrict__ sout,
-              const T *__restrict__ dot_part, const T *__restrict__ Ap, const T *__restrict__ Minv,
-              T *__restrict__ x, T *__restrict__ xbak, T *__restrict__ r, T *__restrict__ z,
-              const T *__restrict__ p, T *__restrict__ rz_part, int *done_flag) {
+__device__ __forceinline__ bool pcg_half1(int Nc, const PcgState<T> *sin, PcgState<T> *sout, const T *dot_part, const T *Ap,
+                                          const T *Minv, T *x, T *xbak, T *r, T *z, const T *p, T *rz_part, int *done_flag) {
   __shared__ T sh[32];
   __shared__ T sr[288], sq[288];
   PcgState<T> s = *sin;
   const bool leader = blockIdx.x == 0 && threadIdx.x == 0;
   if (s.done) {
     if (leader) *sout = s;
-    return;
+    return false;
   }
   if (s.rz == T(0)) { // pcg_schur.hpp:109-111
     if (leader) { s.done = 1; s.reason = 3; *sout = s; *done_flag = 1; }
-    return;
+    return false;
   }
   const T denom = sum_all<T>(dot_part, Nc, sh);
   if (denom == T(0) || isnan(denom)) { // :120-122
     if (leader) { s.done = 1; s.reason = 4; s.denom = denom; *sout = s; *done_flag = 1; }
-    return;
+    return false;
   }
   const T alpha = s.rz / denom;
   const int t = threadIdx.x, g = t / 9, c = blockIdx.x * PCG_CAMS + g, k = t - 9 * g;
@@ -1054,15 +1053,14 @@ k_pcg_update1(int Nc, const PcgState<T> *__restrict__ sin, PcgState<T> *__restri
     s.denom = denom;
     *sout = s;
   }
+  return true;
 }
 
 // second half: rz_new, rejection / convergence tests, beta, p update, xs = D p
 template <typename T>
-__global__ void __launch_bounds__(288)
-k_pcg_update2(int Nc, const PcgState<T> *__restrict__ sin, PcgState<T> *__restrict__ sout, T tol, T ratio,
-              int max_iter, const T *__restrict__ scale_c, const T *__restrict__ rz_part, T *__restrict__ x,
-              const T *__restrict__ xbak, const T *__restrict__ z, T *__restrict__ p, T *__restrict__ xs,
-              int *done_flag) {
+__device__ __forceinline__ void pcg_half2(int Nc, const PcgState<T> *sin, PcgState<T> *sout, T tol, T ratio, int max_iter,
+                                          const T *scale_c, const T *rz_part, T *x, const T *xbak, const T *z, T *p, T *xs,
+                                          int *done_flag) {
   __shared__ T sh[32];
   PcgState<T> s = *sin;
   const bool leader = blockIdx.x == 0 && threadIdx.x == 0;
@@ -1095,6 +1093,33 @@ k_pcg_update2(int Nc, const PcgState<T> *__restrict__ sin, PcgState<T> *__restri
     *sout = s;
     if (s.done) *done_flag = 1;
   }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(288)
+k_pcg_update1(int Nc, const PcgState<T> *sin, PcgState<T> *sout, const T *dot_part, const T *Ap, const T *Minv, T *x,
+              T *xbak, T *r, T *z, const T *p, T *rz_part, int *done_flag) {
+  pcg_half1<T>(Nc, sin, sout, dot_part, Ap, Minv, x, xbak, r, z, p, rz_part, done_flag);
+}
+template <typename T>
+__global__ void __launch_bounds__(288)
+k_pcg_update2(int Nc, const PcgState<T> *sin, PcgState<T> *sout, T tol, T ratio, int max_iter, const T *scale_c,
+              const T *rz_part, T *x, const T *xbak, const T *z, T *p, T *xs, int *done_flag) {
+  pcg_half2<T>(Nc, sin, sout, tol, ratio, max_iter, scale_c, rz_part, x, xbak, z, p, xs, done_flag);
+}
+// Both halves in one cooperative launch (all CTAs co-resident): the grid-wide sync replaces a kernel boundary.
+// st[0] -> st[1] -> st[2] are consecutive entries of the ping-pong state array.
+template <typename T>
+__global__ void __launch_bounds__(288)
+k_pcg_update(int Nc, PcgState<T> *st, T tol, T ratio, int max_iter, const T *dot_part, const T *Ap, const T *Minv,
+             const T *scale_c, T *x, T *xbak, T *r, T *z, T *p, T *xs, T *rz_part, int *done_flag) {
+  const bool go = pcg_half1<T>(Nc, st, st + 1, dot_part, Ap, Minv, x, xbak, r, z, p, rz_part, done_flag);
+  if (!go) { // uniform: no CTA reaches the grid sync; carry the stopped state forward
+    if (blockIdx.x == 0 && threadIdx.x == 0) st[2] = st[1];
+    return;
+  }
+  cooperative_groups::this_grid().sync();
+  pcg_half2<T>(Nc, st + 1, st + 2, tol, ratio, max_iter, scale_c, rz_part, x, xbak, z, p, xs, done_flag);
 }
 
 // xs = D_c x (for the back-substitution) ; also camera update + rho partial (ops/update.hpp:9-31,
