@@ -99,7 +99,7 @@ def algorithmic_bytes(nc, npts, m, nrows, ntiles, sT, sS):
     Jacobians 24 values + 4 B packed meta per observation, the per-tile segment/point tables, W per point,
     camera-vector rows in and partial rows out per (super-tile, camera)."""
     V = 9 * nc * sT
-    product = m * (24 * sS + 4) + ntiles * (2368 - 1024) + npts * 6 * sT + 2 * nrows * 9 * sT
+    product = m * (24 * sS + 4) + ntiles * (2400 - 1024) + npts * 6 * sT + 2 * nrows * 9 * sT
     # SURVEY section 8(d) K4 implicit, whole PCG iteration, for reference next to it
     survey_k4 = 27 * m * sS + 4 * m + 9 * npts * sS + 81 * nc * sS + 10 * V
     return product, survey_k4

@@ -479,23 +479,25 @@ k_prepare_tiles(DevStruct ds, const typename V2<S>::type *__restrict__ J, const 
   const int st_begin = ds.cta_st[blockIdx.x], st_end = ds.cta_st[blockIdx.x + 1]; // persistent CTA, see k_schur_product
   const int tile0 = ds.st_tile[st_begin], ntl = ds.st_tile[st_end] - tile0;
 
-  auto issue = [&](int tile, int s) {
-    const TileMeta tm = ds.tmeta[tile];
+  auto issue = [&](int tile, int s, int p0, int np) {
     unsigned char *base = smem + s * SM::STAGE_BYTES;
-    const uint32_t wbytes = (uint32_t)(tm.np * WST<T>::value * (int)sizeof(T));
-    const uint32_t hbytes = (uint32_t)(tm.np * HST * (int)sizeof(T));
+    const uint32_t wbytes = (uint32_t)(np * WST<T>::value * (int)sizeof(T));
+    const uint32_t hbytes = (uint32_t)(np * HST * (int)sizeof(T));
     mbar_expect_tx(&bars[s], (uint32_t)(SM::J_BYTES + REC_BYTES) + wbytes + hbytes);
     bulk_g2s(base, J + (int64_t)tile * NPLANES * TILE, SM::J_BYTES, &bars[s]);
     bulk_g2s(base + SM::J_BYTES, ds.trec + (int64_t)tile * REC_BYTES, REC_BYTES, &bars[s]);
-    bulk_g2s(base + SM::J_BYTES + REC_BYTES, W + (int64_t)tm.p0 * WST<T>::value, wbytes, &bars[s]);
-    bulk_g2s(base + SM::J_BYTES + REC_BYTES + SM::W_BYTES, h + (int64_t)tm.p0 * HST, hbytes, &bars[s]);
+    bulk_g2s(base + SM::J_BYTES + REC_BYTES, W + (int64_t)p0 * WST<T>::value, wbytes, &bars[s]);
+    bulk_g2s(base + SM::J_BYTES + REC_BYTES + SM::W_BYTES, h + (int64_t)p0 * HST, hbytes, &bars[s]);
   };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; s++) mbar_init(&bars[s], 1);
     mbar_fence_init();
     fence_proxy_async();
-    for (int i = 0; i < NSTAGE && i < ntl; i++) issue(tile0 + i, i);
+    for (int i = 0; i < NSTAGE && i < ntl; i++) {
+      const TileMeta tm0 = ds.tmeta[tile0 + i];
+      issue(tile0 + i, i, tm0.p0, tm0.np);
+    }
   }
   for (int st = st_begin; st < st_end; st++) {
   const int row0 = ds.st_row[st], nslots = ds.st_row[st + 1] - row0;
@@ -511,6 +513,8 @@ k_prepare_tiles(DevStruct ds, const typename V2<S>::type *__restrict__ J, const 
     const T *Ws = reinterpret_cast<const T *>(base + SM::J_BYTES + REC_BYTES);
     const T *Hs = reinterpret_cast<const T *>(base + SM::J_BYTES + REC_BYTES + SM::W_BYTES);
     const TileMeta tm = *reinterpret_cast<const TileMeta *>(rec + REC_META);
+    const int next_p0 = reinterpret_cast<const int32_t *>(rec + REC_NEXT)[2 * (NSTAGE - 1)];
+    const int next_np = reinterpret_cast<const int32_t *>(rec + REC_NEXT)[2 * (NSTAGE - 1) + 1];
     const uint32_t om = reinterpret_cast<const uint32_t *>(rec + REC_OMETA)[t];
     const int ptl = (int)(om & 0xffu);
     T jc[18], jp[6], K[18];
@@ -569,7 +573,7 @@ k_prepare_tiles(DevStruct ds, const typename V2<S>::type *__restrict__ J, const 
     __syncthreads(); // both workers are done with the stage
     if (threadIdx.x == 0 && i + NSTAGE < ntl) {
       fence_proxy_async();
-      issue(tile0 + i + NSTAGE, s);
+      issue(tile0 + i + NSTAGE, s, next_p0, next_np);
     }
   }
   for (int i = threadIdx.x; i < nslots * 54; i += 2 * TILE)
@@ -692,21 +696,29 @@ k_schur_product(DevStruct ds, const typename V2<S>::type *__restrict__ J, const 
   const int st_begin = ds.cta_st[blockIdx.x], st_end = ds.cta_st[blockIdx.x + 1];
   const int tile0 = ds.st_tile[st_begin], ntl = ds.st_tile[st_end] - tile0;
 
-  auto issue = [&](int tile, int s) {
-    const TileMeta tm = ds.tmeta[tile];
+  auto issue = [&](int tile, int s, int p0, int np) {
     unsigned char *base = smem + s * SM::STAGE_BYTES;
-    const uint32_t wbytes = (uint32_t)(tm.np * WST<T>::value * (int)sizeof(T));
+    const uint32_t wbytes = (uint32_t)(np * WST<T>::value * (int)sizeof(T));
     mbar_expect_tx(&bars[s], (uint32_t)(SM::J_BYTES + REC_BYTES) + wbytes);
     bulk_g2s(base, J + (int64_t)tile * NPLANES * TILE, SM::J_BYTES, &bars[s]);
     bulk_g2s(base + SM::J_BYTES, ds.trec + (int64_t)tile * REC_BYTES, REC_BYTES, &bars[s]);
-    bulk_g2s(base + SM::J_BYTES + REC_BYTES, W + (int64_t)tm.p0 * WST<T>::value, wbytes, &bars[s]);
+    bulk_g2s(base + SM::J_BYTES + REC_BYTES, W + (int64_t)p0 * WST<T>::value, wbytes, &bars[s]);
   };
 
+  // issued[s] = number of tiles issued into stage s so far.  Consecutive tiles of one stage are consumed by
+  // alternating workers, so a worker could reach its wait for tile i + NSTAGE before the other worker's tile i has
+  // even landed; a parity wait one phase ahead would then succeed spuriously.  Waiting first until the tile has been
+  // issued (which happens only after tile i was consumed) closes that window.
+  volatile int *issued = reinterpret_cast<volatile int *>(bars + NSTAGE);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; s++) mbar_init(&bars[s], 1);
+    for (int s = 0; s < NSTAGE; s++) { mbar_init(&bars[s], 1); issued[s] = 0; }
     mbar_fence_init();
     fence_proxy_async();
-    for (int i = 0; i < NSTAGE && i < ntl; i++) issue(tile0 + i, i);
+    for (int i = 0; i < NSTAGE && i < ntl; i++) {
+      const TileMeta tm = ds.tmeta[tile0 + i];
+      issue(tile0 + i, i, tm.p0, tm.np);
+      issued[i] = 1;
+    }
   }
 
   for (int st = st_begin; st < st_end; st++) {
@@ -720,12 +732,15 @@ k_schur_product(DevStruct ds, const typename V2<S>::type *__restrict__ J, const 
     const int ib = ds.st_tile[st] - tile0, ie = ds.st_tile[st + 1] - tile0; // ring indices of this super-tile
     for (int i = ib + ((ib ^ worker) & 1); i < ie; i += 2) {                 // worker w takes ring indices of parity w
       const int s = i % NSTAGE;
+      while (issued[s] < i / NSTAGE + 1) { } // see above; almost never spins
       mbar_wait(&bars[s], (uint32_t)((i / NSTAGE) & 1));
       unsigned char *base = smem + s * SM::STAGE_BYTES;
       const S2 *Js = reinterpret_cast<const S2 *>(base);
       const unsigned char *rec = base + SM::J_BYTES;
       const T *Ws = reinterpret_cast<const T *>(base + SM::J_BYTES + REC_BYTES);
       const TileMeta tm = *reinterpret_cast<const TileMeta *>(rec + REC_META);
+      const int next_p0 = reinterpret_cast<const int32_t *>(rec + REC_NEXT)[2 * (NSTAGE - 1)];
+      const int next_np = reinterpret_cast<const int32_t *>(rec + REC_NEXT)[2 * (NSTAGE - 1) + 1];
       const uint32_t om = reinterpret_cast<const uint32_t *>(rec + REC_OMETA)[t];
       const int cslot = (int)(om >> 16), rank = (int)((om >> 8) & 0xffu), ptl = (int)(om & 0xffu);
       T jc[18], jp[6], y0 = T(0), y1 = T(0);
@@ -801,10 +816,14 @@ k_schur_product(DevStruct ds, const typename V2<S>::type *__restrict__ J, const 
         }
       }
       worker_sync(worker);
-      // the stage is free (all threads of the worker are past the barrier): refill it with tile i + NSTAGE
+      // the stage is free (all threads of the worker are past the barrier): refill it with tile i + NSTAGE, whose
+      // point range comes with the record just consumed (no dependent global load on the issue path)
       if (t == 0 && i + NSTAGE < ntl) {
+        const int nxp0 = next_p0, nxnp = next_np;
         fence_proxy_async();
-        issue(tile0 + i + NSTAGE, s);
+        issue(tile0 + i + NSTAGE, s, nxp0, nxnp);
+        __threadfence_block();
+        issued[s] = i / NSTAGE + 2;
       }
     }
     __syncthreads();

@@ -32,12 +32,14 @@ namespace gb {
 constexpr int TILE = 256;       // storage slots per tile = threads per CTA
 constexpr int SLOT_CAP = 192;   // camera accumulator rows per super-tile (bounded by shared memory)
 constexpr int TILE_PTS = 128;   // max points per tile (bounds the per-tile W stage)
-// Packed per-tile record (one TMA bulk copy): ometa[256] u32 | seg_tab[260] u32 | pt_tab[136] u16 | TileMeta
+// Packed per-tile record (one TMA bulk copy): ometa[256] u32 | seg_tab[260] u32 | pt_tab[136] u16 | TileMeta |
+// (p0, np) of the next four tiles
 constexpr int REC_OMETA = 0;
 constexpr int REC_SEG = REC_OMETA + TILE * 4;            // 1024
 constexpr int REC_PT = REC_SEG + (TILE + 4) * 4;         // 2064
 constexpr int REC_META = REC_PT + (TILE_PTS + 8) * 2;    // 2336
-constexpr int REC_BYTES = REC_META + 32;                 // 2368 = 148 * 16
+constexpr int REC_NEXT = REC_META + 32;                  // 2368: (p0, np) of tiles k+1 .. k+4 (TMA issue needs them)
+constexpr int REC_BYTES = REC_NEXT + 32;                 // 2400 = 150 * 16
 
 struct TileMeta {
   int32_t p0;      // first point
@@ -57,6 +59,7 @@ struct HostStructure {
   // super-tile boundaries) were 12 % slower than one CTA per super-tile scheduled by the hardware (SM-to-SM
   // spread of identical work is >= 10 %), so the default is one super-tile per CTA.
   int32_t persistent_ctas = 1 << 30;
+  int32_t sm_count = 148;
   bool identity_perm = true;
   std::vector<int64_t> perm;  // sorted position -> caller's factor index (empty when identity)
   std::vector<int32_t> cam_idx, pt_idx, pptr;  // sorted by (point, camera)
@@ -148,21 +151,20 @@ struct HostStructure {
     Mstore = (int64_t)nt * TILE;
     if (Mstore >= (int64_t(1) << 31)) return "problem too large for 32-bit slot indices";
     // ---- super-tiles: consecutive tiles, bounded observation count and distinct cameras ----------------
-    int64_t st_obs = st_obs_opt > 0 ? st_obs_opt : std::max<int64_t>(TILE, m / (148 * 8));
-    st_tile.clear(); st_row.clear(); row_cam.clear();
     std::vector<int32_t> stamp((size_t)nc, -1), local((size_t)nc, 0);
-    std::vector<int32_t> tile_st((size_t)nt, 0);
-    {
+    int32_t stamp_base = 0;
+    auto partition_tiles = [&](int64_t st_obs, std::vector<int32_t> &o_tile, std::vector<int32_t> &o_row,
+                               std::vector<int32_t> &o_cam) -> bool {
+      o_tile.clear(); o_row.clear(); o_cam.clear();
       int32_t k = 0;
       while (k < nt) {
-        const int32_t s = (int32_t)st_tile.size();
-        st_tile.push_back(k);
-        st_row.push_back((int32_t)row_cam.size());
+        const int32_t s = stamp_base + (int32_t)o_tile.size();
+        o_tile.push_back(k);
+        o_row.push_back((int32_t)o_cam.size());
         std::vector<int32_t> cams_here;
         int64_t obs_here = 0;
         while (k < nt) {
-          // distinct cameras this tile would add
-          std::vector<int32_t> add;
+          std::vector<int32_t> add; // distinct cameras this tile would add
           for (int32_t o = tile_obs[k]; o < tile_obs[k + 1]; o++) {
             const int32_t c = cam_idx[o];
             if (stamp[c] != s) { stamp[c] = s; add.push_back(c); }
@@ -171,17 +173,38 @@ struct HostStructure {
             for (int32_t c : add) stamp[c] = -1; // undo: the tile starts the next super-tile
             break;
           }
-          if ((int32_t)add.size() > slot_cap) return "a tile touches more cameras than the slot cap";
+          if ((int32_t)add.size() > slot_cap) return false;
           cams_here.insert(cams_here.end(), add.begin(), add.end());
           obs_here += tile_obs[k + 1] - tile_obs[k];
-          tile_st[k] = s;
           k++;
         }
         std::sort(cams_here.begin(), cams_here.end());
-        row_cam.insert(row_cam.end(), cams_here.begin(), cams_here.end());
+        o_cam.insert(o_cam.end(), cams_here.begin(), cams_here.end());
       }
-      st_tile.push_back(nt);
-      st_row.push_back((int32_t)row_cam.size());
+      stamp_base += (int32_t)o_tile.size() + 1;
+      o_tile.push_back(nt);
+      o_row.push_back((int32_t)o_cam.size());
+      return true;
+    };
+    if (st_obs_opt > 0) {
+      if (!partition_tiles(st_obs_opt, st_tile, st_row, row_cam)) return "a tile touches more cameras than the slot cap";
+    } else {
+      // The TMA kernels run one CTA per SM, so the number of super-tiles should fill whole waves of `sm_count`
+      // CTAs.  Try 6..12 waves and keep the fullest last wave (ties: fewer, longer super-tiles).  Small problems:
+      // one tile per super-tile.
+      double best = -1.0;
+      std::vector<int32_t> t_tile, t_row, t_cam;
+      if (nt <= 4 * sm_count) { // small problem: as many CTAs as tiles
+        if (!partition_tiles(1, st_tile, st_row, row_cam)) return "a tile touches more cameras than the slot cap";
+      } else
+      for (int w = 6; w <= 12; w++) {
+        const int64_t target = std::max<int64_t>(TILE, (m + (int64_t)sm_count * w - 1) / ((int64_t)sm_count * w));
+        if (!partition_tiles(target, t_tile, t_row, t_cam)) return "a tile touches more cameras than the slot cap";
+        const int64_t n = (int64_t)t_tile.size() - 1;
+        const double eff = (double)n / (double)(((n + sm_count - 1) / sm_count) * sm_count);
+        if (eff > best + 1e-9) { best = eff; st_tile = t_tile; st_row = t_row; row_cam = t_cam; }
+        if (target == TILE) break;
+      }
     }
     const int32_t nst = (int32_t)st_tile.size() - 1;
     // ---- per-tile tables ----------------------------------------------------------------------------------
@@ -243,6 +266,11 @@ struct HostStructure {
       uint16_t *pt = reinterpret_cast<uint16_t *>(rec + REC_PT);
       for (int32_t i = 0; i < TILE_PTS + 8; i++) pt[i] = i <= tm.np ? pt_tab[tm.pt_off + i] : (uint16_t)tm.n;
       memcpy(rec + REC_META, &tm, sizeof(TileMeta));
+      int32_t *nx = reinterpret_cast<int32_t *>(rec + REC_NEXT);
+      for (int32_t d = 1; d <= 4; d++) {
+        nx[2 * (d - 1)] = k + d < nt ? tmeta[k + d].p0 : 0;
+        nx[2 * (d - 1) + 1] = k + d < nt ? tmeta[k + d].np : 0;
+      }
     }
     // ---- camera -> partial rows, ascending super-tile order ------------------------------------------------
     const int32_t nrows = (int32_t)row_cam.size();
