@@ -120,6 +120,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
   int64_t bytes = 0;
   // state
   T *cams = nullptr, *pts = nullptr, *cams_bak = nullptr, *pts_bak = nullptr;
+  T *camx = nullptr; // [Nc][CAMX] per-camera precomputed model terms (k_cam_precompute)
   T2 *obs = nullptr, *res = nullptr, *obs_stage = nullptr; // obs/res per storage slot; stage in caller order
   const int64_t *d_perm = nullptr;                          // sorted position -> caller index (null = identity)
   S2 *J = nullptr; // tile-major [ntiles][12][256]
@@ -206,7 +207,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_TRY(upload(ts.cam_idx, hs.cam_idx));
     GB_TRY(upload(ts.pt_idx, hs.pt_idx));
     GB_TRY(upload(ts.pptr, hs.pptr));
-    GB_TRY(dalloc(cams, Nc * CAM_STRIDE)); GB_TRY(dalloc(cams_bak, Nc * CAM_STRIDE));
+    GB_TRY(dalloc(cams, Nc * CAM_STRIDE)); GB_TRY(dalloc(cams_bak, Nc * CAM_STRIDE)); GB_TRY(dalloc(camx, Nc * CAMX));
     GB_TRY(dalloc(pts, 3 * Np)); GB_TRY(dalloc(pts_bak, 3 * Np));
     GB_TRY(dalloc(obs, hs.Mstore)); GB_TRY(dalloc(res, hs.Mstore)); GB_TRY(dalloc(obs_stage, M));
     if (!hs.identity_perm) GB_TRY(upload(d_perm, hs.perm));
@@ -305,7 +306,9 @@ template <typename T, typename S> struct Problem : ProblemBase {
 
   int enqueue_linearize() {
     cudaStream_t st = ctx->stream;
-    k_linearize<T, S><<<ts.nst, TILE, SMEM_LIN * sizeof(T), st>>>(ts, cams, pts, obs, J, res, Cg, part18, cost_part);
+    k_cam_precompute<T><<<(ts.Nc + 127) / 128, 128, 0, st>>>(ts.Nc, cams, camx);
+    GB_LAUNCH(ctx);
+    k_linearize<T, S><<<ts.nst, TILE, SMEM_LIN * sizeof(T), st>>>(ts, camx, pts, obs, J, res, Cg, part18, cost_part);
     GB_LAUNCH(ctx);
     const bool multi = ctx->nranks > 1;
     k_cam_reduce_lin<T><<<ts.Nc, 288, 0, st>>>(ts, part18, diagB, gc, multi ? 0 : 1, scale_on ? 1 : 0, scale, b);
@@ -443,7 +446,9 @@ template <typename T, typename S> struct Problem : ProblemBase {
 
   int enqueue_cost() {
     cudaStream_t st = ctx->stream;
-    k_cost_tiles<T><<<ts.ntiles, TILE, 0, st>>>(ts, cams, pts, obs, cost_part);
+    k_cam_precompute<T><<<(ts.Nc + 127) / 128, 128, 0, st>>>(ts.Nc, cams, camx);
+    GB_LAUNCH(ctx);
+    k_cost_tiles<T><<<ts.ntiles, TILE, 0, st>>>(ts, camx, pts, obs, cost_part);
     GB_LAUNCH(ctx);
     k_sum_partials<<<1, 1024, 0, st>>>(cost_part, ts.ntiles, scalars, 0);
     GB_LAUNCH(ctx);

@@ -49,34 +49,65 @@ template <typename T> __device__ __forceinline__ T bal_rotation(const T *w, T *R
   return theta;
 }
 
-template <typename T> __device__ __forceinline__ void bal_residual(const T *cam, const T *X, const T *obs, T *r) {
+// ---------------------------------------------------------------------------------------------
+// Per-camera precomputation.  Everything in the camera model that does not depend on the point is evaluated
+// once per camera and parameter change (one thread per camera) instead of once per observation:
+//   cx[0..8] R (row-major), cx[9..11] t, cx[12] f, cx[13] k1, cx[14] k2, cx[15..17] w,
+//   cx[18] A = sin(th)/th, cx[19] B = (1-cos th)/th^2, cx[20] A' , cx[21] B', cx[22] theta > 0 ? 1 : 0
+// The per-observation functions below then need no sin/cos, square root or division by theta.
+// ---------------------------------------------------------------------------------------------
+constexpr int CAMX = 24;
+
+template <typename T> __device__ __forceinline__ void bal_cam_precompute(const T *cam, T *cx) {
   T R[9], s, c;
-  bal_rotation(cam, R, &s, &c);
-  const T Px = R[0] * X[0] + R[1] * X[1] + R[2] * X[2] + cam[3];
-  const T Py = R[3] * X[0] + R[4] * X[1] + R[5] * X[2] + cam[4];
-  const T Pz = R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + cam[5];
+  const T theta = bal_rotation(cam, R, &s, &c);
+#pragma unroll
+  for (int i = 0; i < 9; i++) cx[i] = R[i];
+  cx[9] = cam[3]; cx[10] = cam[4]; cx[11] = cam[5];
+  cx[12] = cam[6]; cx[13] = cam[7]; cx[14] = cam[8];
+  cx[15] = cam[0]; cx[16] = cam[1]; cx[17] = cam[2];
+  T A = T(0), B = T(0), Ap = T(0), Bp = T(0);
+  if (theta > T(0)) {
+    const T t2 = theta * theta;
+    A = s / theta;
+    B = (T(1) - c) / t2;
+    if (t2 < T(1e-4)) {
+      Ap = T(-1.0 / 3.0) + t2 * (T(1.0 / 30.0) - t2 * T(1.0 / 840.0));
+      Bp = T(-1.0 / 12.0) + t2 * (T(1.0 / 180.0) - t2 * T(1.0 / 6720.0));
+    } else {
+      Ap = (c - A) / t2;
+      Bp = (A - T(2) * B) / t2;
+    }
+  }
+  cx[18] = A; cx[19] = B; cx[20] = Ap; cx[21] = Bp;
+  cx[22] = theta > T(0) ? T(1) : T(0);
+  cx[23] = T(0);
+}
+
+template <typename T> __device__ __forceinline__ void bal_residual_pre(const T *cx, const T *X, const T *obs, T *r) {
+  const T Px = cx[0] * X[0] + cx[1] * X[1] + cx[2] * X[2] + cx[9];
+  const T Py = cx[3] * X[0] + cx[4] * X[1] + cx[5] * X[2] + cx[10];
+  const T Pz = cx[6] * X[0] + cx[7] * X[1] + cx[8] * X[2] + cx[11];
   const T px = -Px / Pz, py = -Py / Pz;
   const T r2 = px * px + py * py;
-  const T rd = T(1) + cam[7] * r2 + cam[8] * r2 * r2;
-  r[0] = cam[6] * rd * px - obs[0];
-  r[1] = cam[6] * rd * py - obs[1];
+  const T rd = T(1) + cx[13] * r2 + cx[14] * r2 * r2;
+  r[0] = cx[12] * rd * px - obs[0];
+  r[1] = cx[12] * rd * py - obs[1];
 }
 
 template <typename T>
-__device__ __forceinline__ void bal_residual_jacobian(const T *cam, const T *X, const T *obs, BalObs<T> &out) {
-  T R[9], s, c;
-  const T theta = bal_rotation(cam, R, &s, &c);
-  const T Px = R[0] * X[0] + R[1] * X[1] + R[2] * X[2] + cam[3];
-  const T Py = R[3] * X[0] + R[4] * X[1] + R[5] * X[2] + cam[4];
-  const T Pz = R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + cam[5];
+__device__ __forceinline__ void bal_residual_jacobian_pre(const T *cx, const T *X, const T *obs, BalObs<T> &out) {
+  const T *R = cx;
+  const T Px = R[0] * X[0] + R[1] * X[1] + R[2] * X[2] + cx[9];
+  const T Py = R[3] * X[0] + R[4] * X[1] + R[5] * X[2] + cx[10];
+  const T Pz = R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + cx[11];
   const T iz = T(1) / Pz;
   const T px = -Px * iz, py = -Py * iz;
   const T r2 = px * px + py * py;
-  const T f = cam[6], k1 = cam[7], k2 = cam[8];
+  const T f = cx[12], k1 = cx[13], k2 = cx[14];
   const T d = T(1) + k1 * r2 + k2 * r2 * r2;
-  // the residual uses the reference's division form so that cost values agree to the last bits
   {
-    const T qx = -Px / Pz, qy = -Py / Pz;
+    const T qx = -Px / Pz, qy = -Py / Pz; // the residual uses the reference's division form
     const T q2 = qx * qx + qy * qy;
     const T rd = T(1) + k1 * q2 + k2 * q2 * q2;
     out.r[0] = f * rd * qx - obs[0];
@@ -84,29 +115,19 @@ __device__ __forceinline__ void bal_residual_jacobian(const T *cam, const T *X, 
   }
   const T e = T(2) * k1 + T(4) * k2 * r2;
   const T mfz = -f * iz;
-  T G[6]; // row-major 2x3 = dr/dP
+  T G[6];
   G[0] = mfz * (d + e * px * px);
   G[1] = mfz * (e * px * py);
   G[2] = mfz * px * (d + e * r2);
   G[3] = G[1];
   G[4] = mfz * (d + e * py * py);
   G[5] = mfz * py * (d + e * r2);
-
-  T D[9]; // d(R X)/dw, row-major
+  T D[9];
 #pragma unroll
   for (int i = 0; i < 9; i++) D[i] = T(0);
-  if (theta > T(0)) {
-    const T *w = cam;
-    const T t2 = theta * theta;
-    const T A = s / theta, B = (T(1) - c) / t2;
-    T Ap, Bp;
-    if (t2 < T(1e-4)) { // series: (c - A)/t2 and (A - 2B)/t2 cancel badly for small angles
-      Ap = T(-1.0 / 3.0) + t2 * (T(1.0 / 30.0) - t2 * T(1.0 / 840.0));
-      Bp = T(-1.0 / 12.0) + t2 * (T(1.0 / 180.0) - t2 * T(1.0 / 6720.0));
-    } else {
-      Ap = (c - A) / t2;
-      Bp = (A - T(2) * B) / t2;
-    }
+  if (cx[22] != T(0)) {
+    const T *w = cx + 15;
+    const T A = cx[18], B = cx[19], Ap = cx[20], Bp = cx[21];
     const T wx0 = w[1] * X[2] - w[2] * X[1];
     const T wx1 = w[2] * X[0] - w[0] * X[2];
     const T wx2 = w[0] * X[1] - w[1] * X[0];
@@ -114,7 +135,6 @@ __device__ __forceinline__ void bal_residual_jacobian(const T *cam, const T *X, 
     const T u0 = -A * X[0] + Ap * wx0 + Bp * wX * w[0];
     const T u1 = -A * X[1] + Ap * wx1 + Bp * wX * w[1];
     const T u2 = -A * X[2] + Ap * wx2 + Bp * wX * w[2];
-    // D = u w^T - A [X]x + B (wX I + w X^T)
     D[0] = u0 * w[0] + B * (wX + w[0] * X[0]);
     D[1] = u0 * w[1] + A * X[2] + B * (w[0] * X[1]);
     D[2] = u0 * w[2] - A * X[1] + B * (w[0] * X[2]);

@@ -200,6 +200,36 @@ __device__ __forceinline__ void load_J(const typename V2<S>::type *__restrict__ 
   }
 }
 
+// per-camera part of the camera model (rotation matrix, sin/cos terms): one thread per camera, run whenever the
+// camera parameters change
+template <typename T> __global__ void k_cam_precompute(int Nc, const T *__restrict__ cams, T *__restrict__ camx) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Nc) return;
+  T cam[10], cx[CAMX];
+  load_cam<T>(cams, c, cam);
+  bal_cam_precompute<T>(cam, cx);
+#pragma unroll
+  for (int i = 0; i < CAMX; i++) camx[(int64_t)c * CAMX + i] = cx[i];
+}
+template <typename T> __device__ __forceinline__ void load_camx(const T *__restrict__ camx, int c, T *cx);
+template <> __device__ __forceinline__ void load_camx<double>(const double *__restrict__ camx, int c, double *cx) {
+  const double2 *p = reinterpret_cast<const double2 *>(camx + (int64_t)c * CAMX);
+#pragma unroll
+  for (int i = 0; i < CAMX / 2; i++) {
+    const double2 v = __ldg(p + i);
+    cx[2 * i] = v.x;
+    cx[2 * i + 1] = v.y;
+  }
+}
+template <> __device__ __forceinline__ void load_camx<float>(const float *__restrict__ camx, int c, float *cx) {
+  const float4 *p = reinterpret_cast<const float4 *>(camx + (int64_t)c * CAMX);
+#pragma unroll
+  for (int i = 0; i < CAMX / 4; i++) {
+    const float4 v = __ldg(p + i);
+    cx[4 * i] = v.x; cx[4 * i + 1] = v.y; cx[4 * i + 2] = v.z; cx[4 * i + 3] = v.w;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1: factor evaluation + point-side assembly + camera-side partials of diag(B) and g_c
 //     replaces compute_error_kernel / compute_jacobian_kernel / compute_chi2_kernel /
@@ -230,15 +260,15 @@ k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
     double cost = 0.0;
     if (active) {
       const int c = ds.row_cam[row0 + cslot], p = tm.p0 + ptl;
-      T cam[10], X[3], ob[2];
-      load_cam<T>(cams, c, cam);
+      T cx[CAMX], X[3], ob[2];
+      load_camx<T>(cams, c, cx); // `cams` is the per-camera precomputed table (k_cam_precompute)
       X[0] = pts[3 * (int64_t)p];
       X[1] = pts[3 * (int64_t)p + 1];
       X[2] = pts[3 * (int64_t)p + 2];
       const typename V2<T>::type ov = obs[slot];
       ob[0] = ov.x;
       ob[1] = ov.y;
-      bal_residual_jacobian<T>(cam, X, ob, B);
+      bal_residual_jacobian_pre<T>(cx, X, ob, B);
       typename V2<S>::type *base = J + ((int64_t)tile * NPLANES) * TILE + t;
 #pragma unroll
       for (int j = 0; j < 9; j++) base[j * TILE] = V2<S>::make((S)B.Jc[2 * j], (S)B.Jc[2 * j + 1]);
@@ -1179,15 +1209,15 @@ k_cost_tiles(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts
   if (t < tm.n) {
     const int64_t slot = (int64_t)tile * TILE + t;
     const int c = ds.tile_cam[slot], p = tm.p0 + (int)(ds.ometa[slot] & 0xffu);
-    T cam[10], X[3], ob[2], r[2];
-    load_cam<T>(cams, c, cam);
+    T cx[CAMX], X[3], ob[2], r[2];
+    load_camx<T>(cams, c, cx); // `cams` is the per-camera precomputed table (k_cam_precompute)
     X[0] = pts[3 * (int64_t)p];
     X[1] = pts[3 * (int64_t)p + 1];
     X[2] = pts[3 * (int64_t)p + 2];
     const typename V2<T>::type ov = obs[slot];
     ob[0] = ov.x;
     ob[1] = ov.y;
-    bal_residual<T>(cam, X, ob, r);
+    bal_residual_pre<T>(cx, X, ob, r);
     cost = (double)(r[0] * r[0] + r[1] * r[1]);
   }
   const double tot = block_sum<double>(cost, shd);
