@@ -26,6 +26,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION in this image) off it
+os.environ["NCCL_DEBUG"] = os.environ.get("GB_NCCL_DEBUG", "WARN")
 
 from graphite_b200 import synthetic  # noqa: E402
 

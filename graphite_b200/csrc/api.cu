@@ -379,7 +379,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_LAUNCH(ctx);
     if (multi) {
       GB_TRY(allreduce_T(Ap_raw, dimc));
-      if (pvec) {
+      if (pvec && !coop_update) { // with the cooperative update, Ap and the dot partials are formed inside it
         k_dot_partials<T><<<(ts.Nc + 127) / 128, 128, 0, st>>>(ts.Nc, Ap_raw, dterm, pvec, Ap, dot_part, flag);
         GB_LAUNCH(ctx);
       }
@@ -403,10 +403,12 @@ template <typename T, typename S> struct Problem : ProblemBase {
       if (coop_update) {
         // both halves of the vector update in one cooperative launch (grid-wide sync instead of a kernel boundary)
         PcgState<T> *stp = pcg_state + 2 * k;
-        const T *c_dot = dot_part, *c_Ap = Ap, *c_Minv = Minv, *c_scale = scale;
-        void *args[] = {(void *)&nc, (void *)&stp, (void *)&tol, (void *)&ratio, (void *)&max_iter, (void *)&c_dot,
-                        (void *)&c_Ap, (void *)&c_Minv, (void *)&c_scale, (void *)&x, (void *)&xbak, (void *)&r,
-                        (void *)&z, (void *)&pv, (void *)&xs, (void *)&rz_part, (void *)&done_flag};
+        const T *c_Minv = Minv, *c_scale = scale, *c_dterm = dterm;
+        const T *c_raw = ctx->nranks > 1 ? Ap_raw : nullptr;
+        void *args[] = {(void *)&nc, (void *)&stp, (void *)&tol, (void *)&ratio, (void *)&max_iter, (void *)&dot_part,
+                        (void *)&Ap, (void *)&c_Minv, (void *)&c_scale, (void *)&x, (void *)&xbak, (void *)&r,
+                        (void *)&z, (void *)&pv, (void *)&xs, (void *)&rz_part, (void *)&done_flag, (void *)&c_raw,
+                        (void *)&c_dterm};
         GB_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)k_pcg_update<T>, dim3(gridc), dim3(288), args, 0, st));
         GB_LAUNCH(ctx);
       } else {

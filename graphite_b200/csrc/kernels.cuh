@@ -1160,8 +1160,34 @@ k_pcg_update2(int Nc, const PcgState<T> *sin, PcgState<T> *sout, T tol, T ratio,
 // st[0] -> st[1] -> st[2] are consecutive entries of the ping-pong state array.
 template <typename T>
 __global__ void __launch_bounds__(288)
-k_pcg_update(int Nc, PcgState<T> *st, T tol, T ratio, int max_iter, const T *dot_part, const T *Ap, const T *Minv,
-             const T *scale_c, T *x, T *xbak, T *r, T *z, T *p, T *xs, T *rz_part, int *done_flag) {
+k_pcg_update(int Nc, PcgState<T> *st, T tol, T ratio, int max_iter, T *dot_part, T *Ap, const T *Minv, const T *scale_c,
+             T *x, T *xbak, T *r, T *z, T *p, T *xs, T *rz_part, int *done_flag,
+             const T *Ap_raw /*multi-GPU: all-reduced raw product, else null*/, const T *dterm) {
+  if (Ap_raw != nullptr) {
+    // multi-GPU: Ap = Ap_raw + dterm p and the per-camera p.Ap partials are formed here, after the all-reduce
+    if (!st->done) {
+      __shared__ T sq0[288];
+      const int t = threadIdx.x, g = t / 9, c = blockIdx.x * PCG_CAMS + g, k = t - 9 * g;
+      const bool ok = c < Nc;
+      T prod = T(0);
+      if (ok) {
+        const int i = c * 9 + k;
+        const T pk = p[i];
+        const T ap = Ap_raw[i] + dterm[i] * pk;
+        Ap[i] = ap;
+        prod = pk * ap;
+      }
+      sq0[t] = prod;
+      __syncthreads();
+      if (ok && k == 0) {
+        T d = T(0);
+#pragma unroll
+        for (int j = 0; j < 9; j++) d += sq0[g * 9 + j];
+        dot_part[c] = d;
+      }
+    }
+    cooperative_groups::this_grid().sync();
+  }
   const bool go = pcg_half1<T>(Nc, st, st + 1, dot_part, Ap, Minv, x, xbak, r, z, p, rz_part, done_flag);
   if (!go) { // uniform: no CTA reaches the grid sync; carry the stopped state forward
     if (blockIdx.x == 0 && threadIdx.x == 0) st[2] = st[1];
