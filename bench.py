@@ -44,50 +44,88 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed regions (B200_PROFILING.md clocks line).
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    The device-resident timed region lasts tens of milliseconds, far below nvidia-smi's polling period, so the
+    samples are taken in-process through NVML (pynvml) every ~2 ms by a thread; `mark(True/False)` brackets the timed
+    regions and only samples inside them count.  nvidia-smi is the fallback when NVML cannot be loaded."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, device: int):
-        self.rows = []
         self.device = device
-        self.proc = None
+        self.samples = []  # (in_region, sm_mhz, reasons bitmask)
+        self.in_region = False
+        self.stop_flag = False
+        self.thread = None
+        self.max_mhz = None
+        self.mode = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.device
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.device])
+                except (ValueError, IndexError):
+                    idx = self.device
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.mode = "nvml"
+        except Exception:
+            self.mode = "smi"
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([t.strip() for t in line.split(",")])
+    def _loop(self):
+        if self.mode == "nvml":
+            nv = self.nv
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            while not self.stop_flag:
+                try:
+                    mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    rs = int(get_reasons(self.h))
+                    self.samples.append((self.in_region, mhz, rs))
+                except Exception:
+                    pass
+                time.sleep(0.002)
+        else:
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            bits = [0x8, 0x40, 0x20, 0x4]
+            while not self.stop_flag:
+                try:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                          str(self.device)], capture_output=True, text=True, timeout=5).stdout
+                    r = [t.strip() for t in out.strip().split(",")]
+                    rs = sum(b for b, v in zip(bits, r[2:6]) if v.lower().startswith("active"))
+                    self.max_mhz = float(r[1])
+                    self.samples.append((self.in_region, float(r[0]), rs))
+                except Exception:
+                    time.sleep(0.05)
+
+    def mark(self, inside: bool):
+        self.in_region = inside
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except (ValueError, IndexError):
-                continue
-            for n, v in zip(names, r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=10)
+        rows = [s for s in self.samples if s[0]] or self.samples
+        where = "timed regions" if any(s[0] for s in self.samples) else "whole run (no sample fell inside a timed region)"
+        sm = [s[1] for s in rows]
+        mask = 0
+        for s in rows:
+            mask |= s[2]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(n for b, n in self.REASONS.items() if mask & b), "samples": len(sm),
+                "source": self.mode, "sampled": where}
 
 
 def partition_points(prob, nranks: int, rank: int):
@@ -153,7 +191,7 @@ def workload_config(prob, precision, n_gpus):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="venice-1778")
@@ -216,19 +254,20 @@ def main():
         return float(t.item())
 
     # ---- device-resident arm: W warm-up LM iterations, then K timed --------------------------------------
-    traj_w, res_w = P.lm(iterations=args.warmup)
     sampler = ClockSampler(local_rank)
-    barrier()
     if rank == 0:
         sampler.start()
+    traj_w, res_w = P.lm(iterations=args.warmup)
+    barrier()
+    sampler.mark(True)
     l0 = ctx.kernel_launches()
     t0 = time.perf_counter()
     traj, res = P.lm(iterations=args.steps, initial_damping=res_w["final_damping"], initial_nu=res_w["final_nu"],
                      resume=True, profile_product=True)
     barrier()
+    sampler.mark(False)
     wall = time.perf_counter() - t0
     launches = ctx.kernel_launches() - l0
-    clocks = sampler.stop() if rank == 0 else None
     seconds = max_over_ranks(res["seconds_total"])  # CUDA events on the context stream, max over ranks
     steps_done = int(res["iterations"])
     value = steps_done / seconds
@@ -265,6 +304,7 @@ def main():
     h2d = h_obs.numel() * h_obs.element_size() + out_cams.numel() * out_cams.element_size() + out_pts.numel() * out_pts.element_size()
     d2h = out_cams.numel() * out_cams.element_size() + out_pts.numel() * out_pts.element_size() + 8
     barrier()
+    sampler.mark(True)
     t0 = time.perf_counter()
     e2e_steps = 0
     for _ in range(args.steps):
@@ -275,7 +315,9 @@ def main():
         mu, nu = rj["final_damping"], rj["final_nu"]
         e2e_steps += 1
     barrier()
+    sampler.mark(False)
     e2e_seconds = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else None
     e2e = {"value": e2e_steps / e2e_seconds, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "ms_per_step": 1e3 * e2e_seconds / max(e2e_steps, 1),
            "note": "per step: pinned-host -> device copy of observations + vertices, gb_lm(1 iteration) through the C ABI, "

@@ -37,7 +37,8 @@ class ProblemDesc(C.Structure):
 
 
 class PcgOptions(C.Structure):
-    _fields_ = [("max_iterations", C.c_int64), ("tolerance", C.c_double), ("rejection_ratio", C.c_double)]
+    _fields_ = [("max_iterations", C.c_int64), ("tolerance", C.c_double), ("rejection_ratio", C.c_double),
+                ("solver", C.c_int32), ("reserved", C.c_int32)]
 
 
 class SolveInfo(C.Structure):
@@ -58,6 +59,8 @@ class LMResult(C.Structure):
                 ("seconds_cost", C.c_double), ("final_nu", C.c_double), ("product_launches", C.c_int64),
                 ("product_seconds", C.c_double)]
 
+
+SOLVERS = {"pcg-schur": 0, "pcg": 1}  # names of examples/bal.cu --solver
 
 _lib = None
 
@@ -266,8 +269,8 @@ class Problem:
     def set_damping(self, mu: float, use_identity: bool = False):
         self.ctx.check(self.L.gb_set_damping(self.h, float(mu), int(use_identity)))
 
-    def solve(self, max_iterations=10, tolerance=1.0, rejection_ratio=5.0, want_delta=True):
-        o = PcgOptions(max_iterations, tolerance, rejection_ratio)
+    def solve(self, max_iterations=10, tolerance=1.0, rejection_ratio=5.0, want_delta=True, solver="pcg-schur"):
+        o = PcgOptions(max_iterations, tolerance, rejection_ratio, SOLVERS[solver], 0)
         info = SolveInfo()
         d = np.empty(self.dimH, dtype=self.T) if want_delta else None
         self.ctx.check(self.L.gb_solve(self.h, C.byref(o), _ptr(d) if want_delta else None, C.byref(info)))
@@ -294,9 +297,9 @@ class Problem:
         self.ctx.check(self.L.gb_revert_step(self.h))
 
     def lm(self, iterations=50, initial_damping=1e-4, pcg_iterations=10, pcg_tolerance=1.0, rejection_ratio=5.0,
-           use_identity=False, verbose=False, resume=False, initial_nu=2.0, profile_product=False):
+           use_identity=False, verbose=False, resume=False, initial_nu=2.0, profile_product=False, solver="pcg-schur"):
         o = LMOptions(initial_damping, iterations, int(use_identity), int(verbose),
-                      PcgOptions(pcg_iterations, pcg_tolerance, rejection_ratio), None, int(resume),
+                      PcgOptions(pcg_iterations, pcg_tolerance, rejection_ratio, SOLVERS[solver], 0), None, int(resume),
                       int(profile_product), float(initial_nu))
         res = LMResult()
         traj = np.zeros((max(iterations, 1), 4))

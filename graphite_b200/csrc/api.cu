@@ -145,12 +145,20 @@ template <typename T, typename S> struct Problem : ProblemBase {
   T mu = T(1e-4);
   int use_identity = 0;
   int ncamblocks = 0;
-  gb_pcg_options last_pcg{10, 1.0, 5.0};
+  gb_pcg_options last_pcg{10, 1.0, 5.0, 0, 0};
   int64_t dimc = 0, dimH = 0;
   cudaEvent_t ev[8];
   double last_chi2 = 0.0;
   bool profiling = false;
   std::vector<cudaEvent_t> prof_ev; // pairs around k_schur_tiles<MODE 0>, one pair per PCG iteration
+  // full-system PCG (solver/pcg.hpp): work vectors of the whole Hessian dimension, allocated on first use
+  T *f_x = nullptr, *f_r = nullptr, *f_y = nullptr, *f_z = nullptr, *f_p = nullptr, *f_v2 = nullptr, *f_xbak = nullptr;
+  T *f_upw = nullptr, *f_outp = nullptr, *f_zero = nullptr, *f_Bfull = nullptr, *f_MinvF = nullptr, *f_part = nullptr;
+  T *f_scal = nullptr;
+  double *f_rho = nullptr;
+  bool full_alloc = false, full_lin_valid = false, solved_full = false;
+  int full_blocks = 0;
+  gb_solve_info full_info{};
 
   ~Problem() override {
     if (ctx) cudaSetDevice(ctx->device);
@@ -227,7 +235,9 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_CUDA(ctx, cudaFuncSetAttribute(k_linearize<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIN * sizeof(T))));
     GB_CUDA(ctx, cudaFuncSetAttribute(k_prepare_tiles<T, S, PSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       PrepSmem<T, S>::TOTAL(PSTAGE)));
-    GB_CUDA(ctx, cudaFuncSetAttribute(k_schur_product<T, S, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    GB_CUDA(ctx, cudaFuncSetAttribute(k_schur_product<T, S, NSTAGE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      SchurSmem<T, S>::TOTAL(NSTAGE)));
+    GB_CUDA(ctx, cudaFuncSetAttribute(k_schur_product<T, S, NSTAGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       SchurSmem<T, S>::TOTAL(NSTAGE)));
     GB_TRY(dalloc(diagB, dimc)); GB_TRY(dalloc(gc, dimc));
     GB_TRY(dalloc(scale, dimH)); GB_TRY(dalloc(b, dimH)); GB_TRY(dalloc(delta, dimH));
@@ -329,6 +339,144 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_TRY(launch_check());
     linearized = true;
     prepared = solved = stepped = false;
+    full_lin_valid = solved_full = false;
+    return GB_OK;
+  }
+
+  // ---- full-system matrix-free PCG: PCGSolver + BlockJacobiPreconditioner (solver/pcg.hpp:61-232,
+  //      preconditioner/block_jacobi.hpp:79-186).  The loop is driven from the host with blocking scalar reads,
+  //      like the reference's; products and preconditioner run in the kernels of kernels.cuh. ----------------------
+  int full_buffers() {
+    if (full_alloc) return GB_OK;
+    GB_TRY(require(ctx->nranks == 1, "the full-system PCG solver is single-rank"));
+    const size_t n = (size_t)dimH;
+    GB_TRY(dalloc(f_x, n)); GB_TRY(dalloc(f_r, n)); GB_TRY(dalloc(f_y, n)); GB_TRY(dalloc(f_z, n));
+    GB_TRY(dalloc(f_p, n)); GB_TRY(dalloc(f_v2, n)); GB_TRY(dalloc(f_xbak, n));
+    GB_TRY(dalloc(f_upw, (size_t)WST<T>::value * ts.Np + 8));
+    GB_TRY(dalloc(f_outp, 3 * (size_t)ts.Np));
+    GB_TRY(dalloc(f_zero, (size_t)WST<T>::value * ts.Np + 8)); // W = 0, h = 0: k_prepare_tiles then sums Jc^T Jc
+    GB_TRY(dalloc(f_Bfull, (size_t)ts.Nc * 81)); GB_TRY(dalloc(f_MinvF, (size_t)ts.Nc * 81));
+    full_blocks = (int)((dimH + 255) / 256);
+    GB_TRY(dalloc(f_part, full_blocks)); GB_TRY(dalloc(f_rho, full_blocks));
+    GB_TRY(dalloc(f_scal, 4));
+    full_alloc = true;
+    return GB_OK;
+  }
+  // host value of sum_i a_i b_i (two-stage, fixed order)
+  int full_dot(const T *a, const T *bb, T *out) {
+    cudaStream_t st = ctx->stream;
+    k_vec_dot<T><<<full_blocks, 256, 0, st>>>(dimH, a, bb, f_part);
+    GB_LAUNCH(ctx);
+    return full_read_sum(out);
+  }
+  int full_read_sum(T *out) {
+    cudaStream_t st = ctx->stream;
+    k_vec_sum<T><<<1, 1024, 0, st>>>(f_part, full_blocks, f_scal);
+    GB_LAUNCH(ctx);
+    GB_CUDA(ctx, cudaMemcpyAsync(h_scalars + 4, f_scal, sizeof(T), cudaMemcpyDeviceToHost, st));
+    GB_CUDA(ctx, cudaStreamSynchronize(st));
+    *out = *reinterpret_cast<const T *>(h_scalars + 4);
+    return GB_OK;
+  }
+  // y = r / |r| ; z = M^-1 y   (pcg.hpp:108-121, 184-192)
+  int full_precondition() {
+    cudaStream_t st = ctx->stream;
+    T rr;
+    GB_TRY(full_dot(f_r, f_r, &rr));
+    const T rnorm = std::sqrt(rr);
+    const T sc = (T)(1.0 / rnorm);
+    k_vec_scale<T><<<full_blocks, 256, 0, st>>>(dimH, f_y, sc, f_r);
+    GB_LAUNCH(ctx);
+    k_full_precond<T><<<full_blocks, 256, 0, st>>>(ts.Nc, ts.Np, f_MinvF, W, scale, f_y, f_z);
+    GB_LAUNCH(ctx);
+    return GB_OK;
+  }
+  int solve_full(const gb_pcg_options *o) {
+    cudaStream_t st = ctx->stream;
+    GB_TRY(full_buffers());
+    const size_t nbytes = (size_t)dimH * sizeof(T);
+    if (!full_lin_valid) {
+      // the 45 sums of Jc^T Jc per camera (mu-independent): the prepare pipeline with W = 0, h = 0
+      k_prepare_tiles<T, S, PSTAGE><<<ts.ncta, 2 * TILE, PrepSmem<T, S>::TOTAL(PSTAGE), st>>>(ts, J, f_zero, f_zero, part54);
+      GB_LAUNCH(ctx);
+      full_lin_valid = true;
+      prepared = false; // part54 no longer holds the Schur sums
+    }
+    k_point_prepare<T><<<(ts.Np + 255) / 256, 256, 0, st>>>(ts.Np, scale_on ? 1 : 0, mu, use_identity, Cg, scale + dimc,
+                                                           b + dimc, W, h, 0);
+    GB_LAUNCH(ctx);
+    k_full_cam_blocks<T><<<ts.Nc, 288, 0, st>>>(ts, part54, mu, use_identity, scale, f_Bfull, f_MinvF);
+    GB_LAUNCH(ctx);
+    GB_CUDA(ctx, cudaMemsetAsync(f_x, 0, nbytes, st));
+    GB_CUDA(ctx, cudaMemcpyAsync(f_r, b, nbytes, cudaMemcpyDeviceToDevice, st));
+    GB_TRY(full_precondition());
+    GB_CUDA(ctx, cudaMemcpyAsync(f_p, f_z, nbytes, cudaMemcpyDeviceToDevice, st));
+    T rz;
+    GB_TRY(full_dot(f_r, f_z, &rz));
+    T rz0 = std::numeric_limits<T>::infinity();
+    const T tol = (T)o->tolerance, ratio = (T)o->rejection_ratio;
+    full_info = gb_solve_info{};
+    for (int64_t k = 0; k < o->max_iterations; k++) {
+      if (rz == T(0)) { full_info.stop_reason = 3; break; }
+      // v2 = J~^T J~ p + mu clamp(diag) p   (pcg.hpp:141-168)
+      k_full_build_u<T><<<full_blocks, 256, 0, st>>>(ts.Nc, ts.Np, f_p, scale, xs, f_upw);
+      GB_LAUNCH(ctx);
+      k_schur_product<T, S, NSTAGE, true><<<ts.ncta, 2 * TILE, SchurSmem<T, S>::TOTAL(NSTAGE), st>>>(ts, J, f_upw, xs, part9,
+                                                                                                     nullptr, f_outp);
+      GB_LAUNCH(ctx);
+      k_cam_reduce_spmv<T><<<ts.Nc, 288, 0, st>>>(ts, part9, scale, Ap_raw, 0, dterm, nullptr, Ap, dot_part, nullptr);
+      GB_LAUNCH(ctx);
+      k_full_finish_v2<T><<<full_blocks, 256, 0, st>>>(ts.Nc, ts.Np, mu, use_identity, Ap_raw, f_outp, f_p, scale, diagB, Cg,
+                                                       f_v2, f_part);
+      GB_LAUNCH(ctx);
+      T pv2;
+      GB_TRY(full_read_sum(&pv2));
+      const T alpha = rz / pv2;
+      GB_CUDA(ctx, cudaMemcpyAsync(f_xbak, f_x, nbytes, cudaMemcpyDeviceToDevice, st));
+      k_vec_axpy<T><<<full_blocks, 256, 0, st>>>(dimH, f_x, alpha, f_p, f_x);
+      GB_LAUNCH(ctx);
+      k_vec_axpy<T><<<full_blocks, 256, 0, st>>>(dimH, f_r, -alpha, f_v2, f_r);
+      GB_LAUNCH(ctx);
+      GB_TRY(full_precondition());
+      T rzn;
+      GB_TRY(full_dot(f_r, f_z, &rzn));
+      full_info.pcg_iterations = k + 1;
+      full_info.rz_final = (double)rzn;
+      if (std::abs(rzn) > ratio * rz0 || std::isnan(rzn)) {
+        GB_CUDA(ctx, cudaMemcpyAsync(f_x, f_xbak, nbytes, cudaMemcpyDeviceToDevice, st));
+        full_info.stop_reason = 2;
+        break;
+      }
+      rz0 = std::min(rz0, std::abs(rzn));
+      const T beta = rzn / rz;
+      rz = rzn;
+      k_vec_axpy<T><<<full_blocks, 256, 0, st>>>(dimH, f_p, beta, f_p, f_z);
+      GB_LAUNCH(ctx);
+      if (std::abs(rzn) < tol) { full_info.stop_reason = 1; break; }
+    }
+    GB_TRY(launch_check());
+    last_pcg = *o;
+    solved_full = true;
+    solved = false;
+    stepped = false;
+    return GB_OK;
+  }
+  // delta = x, rho partials, (apply) vertices += D x   (ops/update.hpp:9-31, levenberg_marquardt.hpp:34-41)
+  int enqueue_step_full(bool apply) {
+    cudaStream_t st = ctx->stream;
+    k_cam_step<T><<<ncamblocks, 256, 0, st>>>((int)dimc, f_x, scale, b, mu, xs, cams, cams_bak, delta, rho_part + ts.ntiles,
+                                              apply ? 1 : 0);
+    GB_LAUNCH(ctx);
+    const int64_t n3 = 3 * (int64_t)ts.Np;
+    const int nb = (int)((n3 + 255) / 256);
+    k_full_point_step<T><<<nb, 256, 0, st>>>(n3, f_x + dimc, scale + dimc, b + dimc, mu, pts, pts_bak, delta + dimc, f_rho,
+                                             apply ? 1 : 0);
+    GB_LAUNCH(ctx);
+    k_sum_partials<<<1, 1024, 0, st>>>(f_rho, nb, scalars, 1);
+    GB_LAUNCH(ctx);
+    k_sum_partials<<<1, 1024, 0, st>>>(rho_part + ts.ntiles, ncamblocks, scalars, 2);
+    GB_LAUNCH(ctx);
+    GB_TRY(launch_check());
     return GB_OK;
   }
 
@@ -369,7 +517,8 @@ template <typename T, typename S> struct Problem : ProblemBase {
     }
     const bool multi = ctx->nranks > 1;
     const int finish = (!multi && pvec) ? 1 : 0;
-    k_schur_product<T, S, NSTAGE><<<ts.ncta, 2 * TILE, SchurSmem<T, S>::TOTAL(NSTAGE), st>>>(ts, J, W, xs, part9, flag);
+    k_schur_product<T, S, NSTAGE, false><<<ts.ncta, 2 * TILE, SchurSmem<T, S>::TOTAL(NSTAGE), st>>>(ts, J, W, xs, part9, flag,
+                                                                                                    nullptr);
     GB_LAUNCH(ctx);
     if (prof) GB_CUDA(ctx, cudaEventRecord(prof_ev[2 * prof_slot + 1], st));
     // The per-camera sum of the partial rows stays a separate, massively parallel kernel: fused into the tail of
@@ -424,6 +573,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_TRY(launch_check());
     last_pcg = *o;
     solved = true;
+    solved_full = false;
     stepped = false;
     return GB_OK;
   }
@@ -562,6 +712,17 @@ template <typename T, typename S> struct Problem : ProblemBase {
   int solve(const gb_pcg_options *o, void *delta_host, gb_solve_info *info) override {
     GB_TRY(require(linearized, "gb_solve before gb_linearize"));
     GB_TRY(require(o && o->max_iterations >= 0 && o->max_iterations < (1 << 20), "bad PCG options"));
+    GB_TRY(require(o->solver == GB_SOLVER_PCG_SCHUR || o->solver == GB_SOLVER_PCG_FULL, "unknown solver"));
+    if (o->solver == GB_SOLVER_PCG_FULL) {
+      GB_TRY(solve_full(o));
+      if (delta_host) {
+        GB_TRY(enqueue_step_full(false));
+        GB_TRY(d2h(delta_host, delta, dimH * sizeof(T)));
+      }
+      GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      if (info) *info = full_info;
+      return GB_OK;
+    }
     GB_TRY(enqueue_prepare());
     GB_TRY(enqueue_pcg(o));
     if (delta_host) {
@@ -606,8 +767,9 @@ template <typename T, typename S> struct Problem : ProblemBase {
     return GB_OK;
   }
   int try_step(double *new_chi2, double *rho_den) override {
-    GB_TRY(require(solved, "gb_try_step before gb_solve"));
-    GB_TRY(enqueue_step(true));
+    GB_TRY(require(solved || solved_full, "gb_try_step before gb_solve"));
+    if (solved_full) GB_TRY(enqueue_step_full(true));
+    else GB_TRY(enqueue_step(true));
     GB_TRY(enqueue_cost());
     GB_TRY(fetch_scalars());
     stepped = true;
@@ -633,6 +795,9 @@ template <typename T, typename S> struct Problem : ProblemBase {
   int lm(const gb_lm_options *o, gb_lm_result *res_out, double *traj) override {
     GB_TRY(require(have_obs && have_vertices, "gb_lm needs observations and vertices"));
     GB_TRY(require(o && o->iterations >= 0, "bad LM options"));
+    GB_TRY(require(o->pcg.solver == GB_SOLVER_PCG_SCHUR || o->pcg.solver == GB_SOLVER_PCG_FULL, "unknown solver"));
+    const bool full = o->pcg.solver == GB_SOLVER_PCG_FULL;
+    if (full) GB_TRY(full_buffers());
     cudaStream_t st = ctx->stream;
     gb_lm_result R{};
     const bool resume = o->resume != 0 && linearized;
@@ -662,11 +827,13 @@ template <typename T, typename S> struct Problem : ProblemBase {
     for (; it < o->iterations && run; it++) {
       mu = mu_l;
       GB_CUDA(ctx, cudaEventRecord(ev[0], st));
-      GB_TRY(enqueue_prepare());
+      if (!full) GB_TRY(enqueue_prepare());
       GB_CUDA(ctx, cudaEventRecord(ev[1], st));
-      GB_TRY(enqueue_pcg(&o->pcg));
+      if (full) GB_TRY(solve_full(&o->pcg));
+      else GB_TRY(enqueue_pcg(&o->pcg));
       GB_CUDA(ctx, cudaEventRecord(ev[2], st));
-      GB_TRY(enqueue_step(true));
+      if (full) GB_TRY(enqueue_step_full(true));
+      else GB_TRY(enqueue_step(true));
       GB_CUDA(ctx, cudaEventRecord(ev[3], st));
       GB_TRY(enqueue_cost());
       GB_CUDA(ctx, cudaEventRecord(ev[4], st));
@@ -679,9 +846,9 @@ template <typename T, typename S> struct Problem : ProblemBase {
       const bool solve_ok = true; // PCGSchurSolver::solve always returns true (pcg_schur.hpp:167)
       const T denom = (T)(h_scalars[1] + h_scalars[2]) + (T)1.0e-3;
       const T rho = (chi2 - new_chi2) / denom;
-      R.pcg_iterations_total += h_state->iter;
-      const int64_t k_exec = h_state->iter;
-      if (profiling) {
+      const int64_t k_exec = full ? full_info.pcg_iterations : h_state->iter;
+      R.pcg_iterations_total += k_exec;
+      if (profiling && !full) {
         // launches 0 .. k_exec-1 did the work (a launch after the stop flag returns at once), except that an
         // iteration stopped by rz == 0 or a bad denominator never used its product
         for (int64_t k = 0; k < k_exec && 2 * k + 1 < (int64_t)prof_ev.size(); k++) {
@@ -709,7 +876,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
         nu *= T(2);
         new_chi2 = chi2;
         R.rejected++;
-        solved = false;
+        solved = solved_full = false;
       }
       if (traj) {
         traj[4 * it + 0] = (double)chi2; traj[4 * it + 1] = (double)new_chi2;

@@ -707,10 +707,15 @@ template <typename T, typename S> struct SchurSmem {
 // The CTA has two WORKERS of 256 threads; worker w processes tiles w, w+2, ... of the super-tile with its own
 // accumulator rows (summed in fixed order at the end), so twice as many warps hide the shared-memory and FP64
 // latencies of the short per-tile phases while the TMA keeps the next tiles in flight.
-template <typename T, typename S, int NSTAGE>
+// FULL = true turns the same pipeline into the full-system product J^T J u of the matrix-free PCGSolver
+// (solver/pcg.hpp:141-163, kernels compute_Jv / compute_JtPv in ops/product.hpp): the W stage then carries the point part
+// of the direction (u_p, stride WST), y = Jc u_c + Jp u_p, the point sums sum_o Jp^T y go straight to out_p, and the
+// camera rows accumulate Jc^T y.
+template <typename T, typename S, int NSTAGE, bool FULL>
 __global__ void __launch_bounds__(2 * TILE, 1)
 k_schur_product(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *__restrict__ W,
-                const T *__restrict__ xs, T *__restrict__ part /*[nrows][9]*/, const int *__restrict__ done_flag) {
+                const T *__restrict__ xs, T *__restrict__ part /*[nrows][9]*/, const int *__restrict__ done_flag,
+                T *__restrict__ out_p /*FULL: [Np][3]*/) {
   using SM = SchurSmem<T, S>;
   using S2 = typename V2<S>::type;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -795,6 +800,11 @@ k_schur_product(DevStruct ds, const typename V2<S>::type *__restrict__ J, const 
           y1 += jc[2 * j + 1] * xv;
         }
       }
+      if (FULL) {
+        const T *u = Ws + ptl * WST<T>::value;
+        y0 += jp[0] * u[0] + jp[2] * u[1] + jp[4] * u[2];
+        y1 += jp[1] * u[0] + jp[3] * u[1] + jp[5] * u[2];
+      }
       sv3[rank * 3 + 0] = jp[0] * y0 + jp[1] * y1; // staged at the position in point order
       sv3[rank * 3 + 1] = jp[2] * y0 + jp[3] * y1;
       sv3[rank * 3 + 2] = jp[4] * y0 + jp[5] * y1;
@@ -808,18 +818,22 @@ k_schur_product(DevStruct ds, const typename V2<S>::type *__restrict__ J, const 
           const int b = pt[q], e = pt[q + 1];
           T a = T(0);
           for (int row = b; row < e; row++) a += sv3[row * 3 + k];
-          sw[item] = a;
+          if (FULL) out_p[(int64_t)(tm.p0 + q) * 3 + k] = a;
+          else sw[item] = a;
         }
       }
       worker_sync(worker);
       {
-        const T t0 = sw[ptl * 3], t1 = sw[ptl * 3 + 1], t2 = sw[ptl * 3 + 2];
-        const T *w = Ws + ptl * WST<T>::value;
-        const T w0 = w[0] * t0 + w[1] * t1 + w[2] * t2;
-        const T w1 = w[1] * t0 + w[3] * t1 + w[4] * t2;
-        const T w2 = w[2] * t0 + w[4] * t1 + w[5] * t2;
-        const T d0 = y0 - (jp[0] * w0 + jp[2] * w1 + jp[4] * w2);
-        const T d1 = y1 - (jp[1] * w0 + jp[3] * w1 + jp[5] * w2);
+        T d0 = y0, d1 = y1;
+        if (!FULL) {
+          const T t0 = sw[ptl * 3], t1 = sw[ptl * 3 + 1], t2 = sw[ptl * 3 + 2];
+          const T *w = Ws + ptl * WST<T>::value;
+          const T w0 = w[0] * t0 + w[1] * t1 + w[2] * t2;
+          const T w1 = w[1] * t0 + w[3] * t1 + w[4] * t2;
+          const T w2 = w[2] * t0 + w[4] * t1 + w[5] * t2;
+          d0 = y0 - (jp[0] * w0 + jp[2] * w1 + jp[4] * w2);
+          d1 = y1 - (jp[1] * w0 + jp[3] * w1 + jp[5] * w2);
+        }
         // stage v = Jc^T d at the slot's own row: slots are in camera order, so camera segments are contiguous rows
 #pragma unroll
         for (int k = 0; k < 9; k++) sv[t * 9 + k] = jc[2 * k] * d0 + jc[2 * k + 1] * d1;
@@ -1248,6 +1262,153 @@ k_cost_tiles(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts
   }
   const double tot = block_sum<double>(cost, shd);
   if (t == 0) cost_part[tile] = tot;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Full-system matrix-free PCG (solver/pcg.hpp:61-232 + preconditioner/block_jacobi.hpp): small vector kernels.
+// The loop is driven from the host like the reference's (blocking scalar reads); the reductions are two-stage with
+// a fixed order.  Vector layout: [9 Nc camera scalars | 3 Np point scalars], scaled space.
+// ---------------------------------------------------------------------------------------------
+// per-camera: full scaled block B~ (from the 45 packed sums), damped diagonal, inverse (block-parallel Gauss-Jordan)
+template <typename T>
+__global__ void __launch_bounds__(288)
+k_full_cam_blocks(DevStruct ds, const T *__restrict__ part /*[nrows][54]*/, T mu, int use_identity,
+                  const T *__restrict__ scale_c, T *__restrict__ Bfull /*[Nc][81] scaled, undamped*/, T *__restrict__ MinvF) {
+  __shared__ T sh[32 * 9];
+  __shared__ T out[54];
+  __shared__ T Maug[9 * 18], fcol[9];
+  const int c = blockIdx.x, t = threadIdx.x;
+  cam_gather<T>(ds, c, part, 54, 5, sh, out);
+  if (t < 81) {
+    const int i = t % 9, j = t / 9;
+    const int a = i < j ? i : j, b = i < j ? j : i;
+    const int idx = a * 9 - (a * (a - 1)) / 2 + (b - a);
+    T val = scale_c[c * 9 + i] * scale_c[c * 9 + j] * out[idx];
+    Bfull[(int64_t)c * 81 + i + 9 * j] = val;
+    if (i == j) val = damp_value<T>(val, mu, use_identity);
+    Maug[i * 18 + j] = val;
+    Maug[i * 18 + 9 + j] = (i == j) ? T(1) : T(0);
+  }
+  invert9_block<T>(Maug, fcol, t);
+  if (t < 81) {
+    const int i = t % 9, j = t / 9;
+    MinvF[(int64_t)c * 81 + i + 9 * j] = Maug[i * 18 + 9 + j];
+  }
+}
+// u = D p: cameras into the 10-padded rows read by the product kernel, points into the W-strided stage buffer
+template <typename T>
+__global__ void k_full_build_u(int Nc, int Np, const T *__restrict__ p, const T *__restrict__ scale, T *__restrict__ xs,
+                               T *__restrict__ upw) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t dimc = 9 * (int64_t)Nc, n = dimc + 3 * (int64_t)Np;
+  if (i >= n) return;
+  const T v = scale[i] * p[i];
+  if (i < dimc) xs[(i / 9) * CAM_STRIDE + i % 9] = v;
+  else upw[((i - dimc) / 3) * WST<T>::value + (i - dimc) % 3] = v;
+}
+// clamped scalar diagonal of J~^T J~ (pcg.hpp:93-104): cameras from diag(B), points from diag(C)
+template <typename T>
+__device__ __forceinline__ T full_diag(int64_t i, int64_t dimc, const T *diagB, const T *Cg, const T *scale) {
+  T d;
+  if (i < dimc) d = diagB[i];
+  else {
+    const int64_t q = (i - dimc) / 3;
+    const int k = (int)((i - dimc) % 3);
+    d = Cg[q * 9 + (k == 0 ? 0 : (k == 1 ? 3 : 5))];
+  }
+  d = scale[i] * scale[i] * d;
+  return fmin(fmax(d, (T)1.0e-6), (T)1.0e32);
+}
+// v2 = [Ap_raw_c | D_p out_p] + mu (diag or 1) p ; per-block partial of p . v2
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_full_finish_v2(int Nc, int Np, T mu, int use_identity, const T *__restrict__ Ap_raw, const T *__restrict__ out_p,
+                 const T *__restrict__ p, const T *__restrict__ scale, const T *__restrict__ diagB, const T *__restrict__ Cg,
+                 T *__restrict__ v2, T *__restrict__ partial) {
+  __shared__ T sh[32];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t dimc = 9 * (int64_t)Nc, n = dimc + 3 * (int64_t)Np;
+  T prod = T(0);
+  if (i < n) {
+    const T pv = p[i];
+    T v = i < dimc ? Ap_raw[i] : scale[i] * out_p[i - dimc];
+    v += use_identity ? mu * pv : mu * full_diag<T>(i, dimc, diagB, Cg, scale) * pv;
+    v2[i] = v;
+    prod = pv * v;
+  }
+  const T tot = block_sum<T>(prod, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_vec_dot(int64_t n, const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ partial) {
+  __shared__ T sh[32];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const T tot = block_sum<T>(i < n ? a[i] * b[i] : T(0), sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+template <typename T>
+__global__ void __launch_bounds__(1024) k_vec_sum(const T *__restrict__ partial, int n, T *__restrict__ out) {
+  __shared__ T sh[32];
+  const T tot = sum_all<T>(partial, n, sh);
+  if (threadIdx.x == 0) *out = tot;
+}
+// z = a x + y (ops/vector.hpp:6-14) ; out = s x (:69-78)
+template <typename T> __global__ void k_vec_axpy(int64_t n, T *z, T a, const T *x, const T *y) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) z[i] = a * x[i] + y[i];
+}
+template <typename T> __global__ void k_vec_scale(int64_t n, T *out, T s, const T *x) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = s * x[i];
+}
+// z = M^-1 y: 9x9 blocks for the cameras (MinvF), 3x3 for the points (D^-1 W D^-1, W from k_point_prepare)
+template <typename T>
+__global__ void k_full_precond(int Nc, int Np, const T *__restrict__ MinvF, const T *__restrict__ W,
+                               const T *__restrict__ scale, const T *__restrict__ y, T *__restrict__ z) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t dimc = 9 * (int64_t)Nc, n = dimc + 3 * (int64_t)Np;
+  if (i >= n) return;
+  if (i < dimc) {
+    const int64_t c = i / 9;
+    const int k = (int)(i % 9);
+    const T *m = MinvF + c * 81;
+    T acc = T(0);
+#pragma unroll
+    for (int j = 0; j < 9; j++) acc += m[k + 9 * j] * y[c * 9 + j];
+    z[i] = acc;
+  } else {
+    const int64_t q = (i - dimc) / 3;
+    const int k = (int)((i - dimc) % 3);
+    const T *w = W + q * WST<T>::value;
+    const T *sc = scale + dimc + 3 * q, *yy = y + dimc + 3 * q;
+    const T a0 = yy[0] / sc[0], a1 = yy[1] / sc[1], a2 = yy[2] / sc[2];
+    const T r = k == 0 ? w[0] * a0 + w[1] * a1 + w[2] * a2
+              : (k == 1 ? w[1] * a0 + w[3] * a1 + w[4] * a2 : w[2] * a0 + w[4] * a1 + w[5] * a2);
+    z[i] = r / sc[k];
+  }
+}
+// point part of the step for the full-system solver: delta_p = x_p, rho partial, backup + update (ops/update.hpp:9-31)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_full_point_step(int64_t n3, const T *__restrict__ xp, const T *__restrict__ scale_p, const T *__restrict__ b_p, T mu,
+                  T *__restrict__ pts, T *__restrict__ pts_bak, T *__restrict__ delta_p, double *__restrict__ rho_part,
+                  int apply) {
+  __shared__ double shd[32];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double rho = 0.0;
+  if (i < n3) {
+    const T xt = xp[i];
+    delta_p[i] = xt;
+    rho = (double)(xt * (mu * xt + b_p[i]));
+    if (apply) {
+      const T old = pts[i];
+      pts_bak[i] = old;
+      pts[i] = old + xt * scale_p[i];
+    }
+  }
+  const double tot = block_sum<double>(rho, shd);
+  if (threadIdx.x == 0) rho_part[blockIdx.x] = tot;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -124,10 +124,18 @@ int gb_get_jacobians(gb_problem *p, double *Jc_host, double *Jp_host);
  * reference's value layout (element type S). */
 int gb_hessian_values(gb_problem *p, void *values_host);
 
+/* Linear solver behind Solver<T,S> (solver/solver.hpp:16-24):
+ *   GB_SOLVER_PCG_SCHUR  PCGSchurSolver + BlockJacobiSchurPreconditioner (solver/pcg_schur.hpp) — points eliminated
+ *   GB_SOLVER_PCG_FULL   PCGSolver + BlockJacobiPreconditioner (solver/pcg.hpp:61-232, preconditioner/block_jacobi.hpp):
+ *                        matrix-free PCG on the full camera + point system, the reference's mixed-precision path */
+typedef enum { GB_SOLVER_PCG_SCHUR = 0, GB_SOLVER_PCG_FULL = 1 } gb_solver;
+
 typedef struct {
-  int64_t max_iterations;  /* PCGSchurSolver ctor (pcg_schur.hpp:42-45); bal default 10 */
+  int64_t max_iterations;  /* PCGSchurSolver / PCGSolver ctor (pcg_schur.hpp:42-45, pcg.hpp:40-45); bal default 10 */
   double tolerance;        /* 1.0 */
   double rejection_ratio;  /* 5.0 */
+  int32_t solver;          /* gb_solver */
+  int32_t reserved;
 } gb_pcg_options;
 
 typedef struct {

@@ -23,6 +23,7 @@
 //   Schur, b_S, back-subst include/graphite/schur.hpp:227-302, ops/schur.hpp:154-188, tests/schur_cpu_ref.cpp:8-51
 //   block-Jacobi           include/graphite/preconditioner/block_jacobi_schur.hpp:114-178
 //   PCG                    include/graphite/solver/pcg_schur.hpp:79-168
+//   full-system PCG        include/graphite/solver/pcg.hpp:61-232, preconditioner/block_jacobi.hpp:79-186
 //   direct solve           include/graphite/solver/eigen_schur.hpp:52-108, src/eigen_solver.cpp:10-29 (as dense LDL^T)
 //   update/backup/revert   include/graphite/ops/update.hpp:9-31, graph.hpp:292-318
 //   rho and LM control     include/graphite/optimizer/levenberg_marquardt.hpp:19-47,109-242
@@ -670,7 +671,128 @@ template <typename T> struct Impl : Base {
     tim[4] += secs(t0);
   }
 
+  // solver/pcg.hpp:61-232 with BlockJacobiPreconditioner (preconditioner/block_jacobi.hpp:79-186): matrix-free PCG on
+  // the FULL system (cameras and points), operator J~^T J~ + mu clamp(diag), preconditioner = inverse of the damped
+  // per-vertex diagonal blocks, applied to the NORMALISED residual y = r / |r|.
+  int64_t pcg_full(const orc_lm_options *o, T mu, T *x) {
+    auto t0 = clk::now();
+    const bool ident = o->use_identity != 0;
+    // diag of J~^T J~ (scaled Jacobians), clamped (pcg.hpp:93-104)
+    std::vector<T> diag(dimH);
+    for (int64_t i = 0; i < dimc; i++) diag[i] = Bd[i];
+    for (int64_t i = 0; i < 3 * np; i++) diag[dimc + i] = Cd[i];
+    for (auto &d : diag) d = std::min(std::max(d, (T)1.0e-6), (T)1.0e32);
+    // preconditioner blocks: diag_i + mu clamp(diag_i) on the diagonal, computed in double (ops/hessian.hpp:80-110)
+    std::vector<T> Mc(81 * nc), Mp(9 * np);
+#pragma omp parallel for num_threads(threads) schedule(static)
+    for (int64_t c = 0; c < nc; c++) {
+      T blk[81];
+      for (int i = 0; i < 81; i++) blk[i] = Bk[81 * c + i];
+      for (int k = 0; k < 9; k++) blk[10 * k] = damp(Bd[9 * c + k], mu, ident);
+      invert<T, 9>(blk, &Mc[81 * c]);
+    }
+#pragma omp parallel for num_threads(threads) schedule(static)
+    for (int64_t p = 0; p < np; p++) {
+      T blk[9];
+      for (int i = 0; i < 9; i++) blk[i] = Ck[9 * p + i];
+      for (int k = 0; k < 3; k++) blk[4 * k] = damp(Cd[3 * p + k], mu, ident);
+      invert<T, 3>(blk, &Mp[9 * p]);
+    }
+    auto apply = [&](const T *in, T *out) {
+#pragma omp parallel for num_threads(threads) schedule(static)
+      for (int64_t c = 0; c < nc; c++)
+        for (int row = 0; row < 9; row++) {
+          T acc = 0;
+          for (int k = 0; k < 9; k++) acc += Mc[81 * c + row + 9 * k] * in[9 * c + k];
+          out[9 * c + row] = acc;
+        }
+#pragma omp parallel for num_threads(threads) schedule(static)
+      for (int64_t p = 0; p < np; p++)
+        for (int row = 0; row < 3; row++) {
+          T acc = 0;
+          for (int k = 0; k < 3; k++) acc += Mp[9 * p + row + 3 * k] * in[dimc + 3 * p + k];
+          out[dimc + 3 * p + row] = acc;
+        }
+    };
+    // v2 = J~^T (J~ p) (ops/product.hpp:49-99, 226-288), then += mu diag p (ops/vector.hpp:24-39)
+    std::vector<T> v1(2 * m), v2(dimH);
+    std::vector<std::vector<T>> tl(threads, std::vector<T>(dimc));
+    auto op = [&](const T *pv) {
+#pragma omp parallel for num_threads(threads) schedule(static)
+      for (int64_t f = 0; f < m; f++) {
+        const T *J = &Jc[18 * f], *Q = &Jp[6 * f];
+        const T *pc = pv + 9 * ci[f], *pp = pv + dimc + 3 * pi[f];
+        T a0 = 0, a1 = 0;
+        for (int k = 0; k < 9; k++) { a0 += J[2 * k] * pc[k]; a1 += J[2 * k + 1] * pc[k]; }
+        for (int k = 0; k < 3; k++) { a0 += Q[2 * k] * pp[k]; a1 += Q[2 * k + 1] * pp[k]; }
+        v1[2 * f] = a0; v1[2 * f + 1] = a1;
+      }
+#pragma omp parallel num_threads(threads)
+      {
+#ifdef _OPENMP
+        const int tid = omp_get_thread_num();
+#else
+        const int tid = 0;
+#endif
+        T *d = tl[tid].data();
+        std::fill(d, d + dimc, T(0));
+#pragma omp for schedule(static)
+        for (int64_t f = 0; f < m; f++) {
+          const T *J = &Jc[18 * f];
+          T *dd = d + 9 * ci[f];
+          for (int k = 0; k < 9; k++) dd[k] += J[2 * k] * v1[2 * f] + J[2 * k + 1] * v1[2 * f + 1];
+        }
+      }
+      for (int64_t i = 0; i < dimc; i++) { T a = 0; for (int t = 0; t < threads; t++) a += tl[t][i]; v2[i] = a; }
+#pragma omp parallel for num_threads(threads) schedule(static)
+      for (int64_t p = 0; p < np; p++) {
+        T acc[3] = {0, 0, 0};
+        for (int64_t f = pptr[p]; f < pptr[p + 1]; f++) {
+          const T *Q = &Jp[6 * f];
+          for (int k = 0; k < 3; k++) acc[k] += Q[2 * k] * v1[2 * f] + Q[2 * k + 1] * v1[2 * f + 1];
+        }
+        for (int k = 0; k < 3; k++) v2[dimc + 3 * p + k] = acc[k];
+      }
+      for (int64_t i = 0; i < dimH; i++) v2[i] += ident ? mu * pv[i] : mu * diag[i] * pv[i];
+    };
+    std::vector<T> rv(b), y(dimH), z(dimH), p(dimH), xb(dimH);
+    std::fill(x, x + dimH, T(0));
+    T rnorm = std::sqrt(dot(rv.data(), rv.data(), dimH));
+    for (int64_t i = 0; i < dimH; i++) y[i] = (T)(1.0 / rnorm) * rv[i];
+    apply(y.data(), z.data());
+    p = z;
+    T rz = dot(rv.data(), z.data(), dimH);
+    T rz0 = std::numeric_limits<T>::infinity();
+    const T tol = (T)o->pcg_tolerance, ratio = (T)o->rejection_ratio;
+    int64_t done = 0;
+    for (int64_t k = 0; k < o->pcg_iterations; ++k) {
+      if (rz == 0) break;
+      op(p.data());
+      const T alpha = rz / dot(p.data(), v2.data(), dimH);
+      for (int64_t i = 0; i < dimH; i++) xb[i] = x[i];
+      for (int64_t i = 0; i < dimH; i++) x[i] = alpha * p[i] + x[i];
+      for (int64_t i = 0; i < dimH; i++) rv[i] = -alpha * v2[i] + rv[i];
+      rnorm = std::sqrt(dot(rv.data(), rv.data(), dimH));
+      for (int64_t i = 0; i < dimH; i++) y[i] = (T)(1.0 / rnorm) * rv[i];
+      apply(y.data(), z.data());
+      const T rzn = dot(rv.data(), z.data(), dimH);
+      done = k + 1;
+      if (std::abs(rzn) > ratio * rz0 || std::isnan(rzn)) {
+        for (int64_t i = 0; i < dimH; i++) x[i] = xb[i];
+        break;
+      }
+      rz0 = std::min(rz0, std::abs(rzn));
+      const T beta = rzn / rz;
+      rz = rzn;
+      for (int64_t i = 0; i < dimH; i++) p[i] = beta * p[i] + z[i];
+      if (std::abs(rzn) < tol) break;
+    }
+    tim[3] += secs(t0);
+    return done;
+  }
+
   int64_t do_solve(const orc_lm_options *o, T mu, T *x, bool &ok) {
+    if (o->solver == 2) { ok = true; return pcg_full(o, mu, x); }
     build_schur(mu, o->use_identity != 0);
     int64_t k = 0;
     ok = true;

@@ -24,7 +24,8 @@ typedef struct {
   double pcg_tolerance;    /* 1.0 */
   double rejection_ratio;  /* 5.0 */
   int use_identity;        /* 0 */
-  int solver;              /* 0 = PCG on explicit Schur (pcg_schur.hpp), 1 = dense LDL^T on Schur (eigen_schur.hpp) */
+  int solver;              /* 0 = PCG on explicit Schur (pcg_schur.hpp), 1 = dense LDL^T on Schur (eigen_schur.hpp),
+                              2 = matrix-free PCG on the full system (pcg.hpp) */
   int threads;             /* OpenMP threads; <=0 = all */
 } orc_lm_options;
 

@@ -133,6 +133,21 @@ def test_fp32_trajectory_matches_reference(built):
     assert rel.max() <= 1e-4
 
 
+def test_full_system_pcg_trajectory_matches_reference(built):
+    """solver/pcg.hpp restated (oracle solver 2) vs the reference's `--solver pcg` FP64-FP64 run."""
+    g = golden_json("ladybug-49__pcg__FP64-FP64.json")
+    init, cur, lam = table(g)
+    traj = Oracle(synthetic.make_named("ladybug-49")).lm(default_options(iterations=len(cur), solver=2))
+    rel = np.abs(traj[:, 1] - cur) / cur
+    assert rel.max() <= 1e-9, rel
+    assert np.array_equal(traj[:, 0] == traj[:, 1], init == cur)
+    np.testing.assert_allclose(traj[:, 2], lam, rtol=1e-6)
+    assert abs(traj[-1, 1] - g["final_chi2"]) <= 1e-6 * g["final_chi2"]
+    # the reference's mixed-precision run of the same solver stays within 1e-4 of the FP64 trajectory
+    g32 = golden_json("ladybug-49__pcg__FP64-FP32.json")
+    assert abs(traj[-1, 1] - g32["final_chi2"]) <= 1e-4 * g32["final_chi2"]
+
+
 def test_jacobian_against_finite_differences(built):
     prob = synthetic.schur_fixture()
     o = Oracle(prob)
