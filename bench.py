@@ -26,8 +26,17 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION in this image) off it
+# stdout carries exactly one JSON line: native libraries (NCCL prints its "NCCL version ..." banner on fd 1) are sent to
+# stderr for the whole run, and the line is written to the saved descriptor at the end
 os.environ["NCCL_DEBUG"] = os.environ.get("GB_NCCL_DEBUG", "WARN")
+sys.stdout.flush()
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 from graphite_b200 import synthetic  # noqa: E402
 
@@ -176,7 +185,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "final_chi2": float(out[1]),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(prob, precision, n_gpus):
@@ -347,14 +356,15 @@ def main():
             "config": workload_config(prob, args.precision, world),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "pcg": {"iterations_per_step": [int(v) for v in traj[:, 3]], "total": int(res["pcg_iterations_total"]),
-                    "ms_per_product_launch": prod_ms, "product_gbps": achieved},
+                    "ms_per_product_launch": prod_ms, "product_gbps": achieved,
+                    "ms_per_iteration_rest": 1e3 * res["update_seconds"] / n_prod},
             "stages_ms_per_step": {k[8:]: 1e3 * v / max(steps_done, 1) for k, v in res.items()
                                    if k.startswith("seconds_") and k != "seconds_total"},
             "accepted": int(res["accepted"]), "rejected": int(res["rejected"]),
             "chi2": {"start": float(traj[0, 0]) if len(traj) else None, "end": float(res["final_chi2"])},
             "wall_seconds_timed_region": wall, "structure": info,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     P.close()
     ctx.close()
     if dist is not None:

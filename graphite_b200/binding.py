@@ -57,7 +57,7 @@ class LMResult(C.Structure):
                 ("pcg_iterations_total", C.c_int64), ("seconds_total", C.c_double), ("seconds_linearize", C.c_double),
                 ("seconds_prepare", C.c_double), ("seconds_pcg", C.c_double), ("seconds_backsubst", C.c_double),
                 ("seconds_cost", C.c_double), ("final_nu", C.c_double), ("product_launches", C.c_int64),
-                ("product_seconds", C.c_double)]
+                ("product_seconds", C.c_double), ("update_seconds", C.c_double)]
 
 
 SOLVERS = {"pcg-schur": 0, "pcg": 1}  # names of examples/bal.cu --solver
@@ -326,7 +326,7 @@ STRUCT_ARRAYS = ["cam_idx", "pt_idx", "pptr", "tile_obs", "tile_pt", "st_tile", 
                  "cam_row_list", "slot_of_obs", "rank", "perm", "ometa", "seg_tab", "pt_tab", "tmeta"]
 _STRUCT_DTYPES = {"rank": np.uint8, "perm": np.int64, "ometa": np.uint32, "seg_tab": np.uint32, "pt_tab": np.uint16}
 INFO_KEYS = ["n_tiles", "n_partial_rows", "max_track", "hessian_dim", "n_hessian_blocks", "n_hessian_values",
-             "device_bytes", "n_obs", "n_super_tiles", "n_camera_segments", "storage_slots", "reserved"]
+             "device_bytes", "n_obs", "n_super_tiles", "n_camera_segments", "storage_slots", "exchange_mode"]
 
 
 def host_structure(cam_idx, pt_idx, n_cams: int, n_pts: int, tile_size: int = 0, slot_cap: int = 0,

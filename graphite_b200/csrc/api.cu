@@ -28,6 +28,7 @@ struct NcclApi {
   int (*GetUniqueId)(ncclUniqueId_gb *) = nullptr;
   int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId_gb, int) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
   bool load() {
@@ -41,13 +42,14 @@ struct NcclApi {
     GetUniqueId = (int (*)(ncclUniqueId_gb *))dlsym(handle, "ncclGetUniqueId");
     CommInitRank = (int (*)(ncclComm_t *, int, ncclUniqueId_gb, int))dlsym(handle, "ncclCommInitRank");
     AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(handle, "ncclAllReduce");
+    AllGather = (int (*)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t))dlsym(handle, "ncclAllGather");
     CommDestroy = (int (*)(ncclComm_t))dlsym(handle, "ncclCommDestroy");
     GetErrorString = (const char *(*)(int))dlsym(handle, "ncclGetErrorString");
     return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
   }
 };
 NcclApi g_nccl;
-constexpr int NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8, NCCL_SUM = 0;
+constexpr int NCCL_INT8 = 0, NCCL_INT32 = 2, NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8, NCCL_SUM = 0;
 } // namespace
 
 struct gb_context {
@@ -108,6 +110,7 @@ struct ProblemBase {
   virtual int lm(const gb_lm_options *, gb_lm_result *, double *) = 0;
   virtual int time_stage(int, int, double *) = 0;
   virtual int64_t device_bytes() const = 0;
+  virtual int exchange_mode() const = 0; // 0 single rank, 1 NCCL all-reduce, 2 peer-memory exchange (p2p.cuh)
 };
 
 template <typename T, typename S> struct Problem : ProblemBase {
@@ -127,6 +130,9 @@ template <typename T, typename S> struct Problem : ProblemBase {
   T *Cg = nullptr, *part18 = nullptr, *part54 = nullptr, *part9 = nullptr, *sums54 = nullptr;
   T *dot_part = nullptr, *rz_part = nullptr;
   bool coop_update = false; // the fused PCG update needs all its CTAs co-resident
+  bool fused_iter = false;  // reduction + exchange + update of one PCG iteration in one cooperative launch (k_pcg_iterate)
+  int iter_grid = 0;
+  T *cta_part = nullptr;
   T *diagB = nullptr, *gc = nullptr, *scale = nullptr /*[9Nc+3Np]*/, *b = nullptr /*[9Nc+3Np]*/;
   T *W = nullptr, *h = nullptr;
   T *Sdiag = nullptr, *Minv = nullptr, *bS = nullptr, *dterm = nullptr;
@@ -151,6 +157,12 @@ template <typename T, typename S> struct Problem : ProblemBase {
   double last_chi2 = 0.0;
   bool profiling = false;
   std::vector<cudaEvent_t> prof_ev; // pairs around k_schur_tiles<MODE 0>, one pair per PCG iteration
+  // multi-GPU exchange over peer memory (p2p.cuh); NCCL is the bootstrap and the fallback
+  P2P pp{};
+  bool p2p_on = false;
+  int *h_p2p_err = nullptr;
+  void *p2p_area = nullptr;                  // own receive area + flag words (one cudaMalloc, exported by cudaIpc)
+  void *p2p_peer[P2P_MAX_RANKS] = {nullptr}; // peers' areas as mapped here
   // full-system PCG (solver/pcg.hpp): work vectors of the whole Hessian dimension, allocated on first use
   T *f_x = nullptr, *f_r = nullptr, *f_y = nullptr, *f_z = nullptr, *f_p = nullptr, *f_v2 = nullptr, *f_xbak = nullptr;
   T *f_upw = nullptr, *f_outp = nullptr, *f_zero = nullptr, *f_Bfull = nullptr, *f_MinvF = nullptr, *f_part = nullptr;
@@ -162,13 +174,25 @@ template <typename T, typename S> struct Problem : ProblemBase {
 
   ~Problem() override {
     if (ctx) cudaSetDevice(ctx->device);
+    if (p2p_on) {
+      // nobody may unmap or free while a peer can still be pushing: rendezvous first
+      allreduce(scalars, 1, true);
+      cudaStreamSynchronize(ctx->stream);
+      for (int r = 0; r < ctx->nranks; r++)
+        if (r != ctx->rank && p2p_peer[r]) cudaIpcCloseMemHandle(p2p_peer[r]);
+      allreduce(scalars, 1, true);
+      cudaStreamSynchronize(ctx->stream);
+    }
+    if (p2p_area) cudaFree(p2p_area);
     for (void *p : allocs) cudaFree(p);
     if (h_scalars) cudaFreeHost(h_scalars);
     if (h_state) cudaFreeHost(h_state);
+    if (h_p2p_err) cudaFreeHost(h_p2p_err);
     for (auto &e : ev) if (e) cudaEventDestroy(e);
     for (auto &e : prof_ev) cudaEventDestroy(e);
   }
   int64_t device_bytes() const override { return bytes; }
+  int exchange_mode() const override { return ctx->nranks <= 1 ? 0 : (p2p_on ? 2 : 1); }
 
   template <typename X> int dalloc(X *&p, size_t n) {
     void *q = nullptr;
@@ -230,9 +254,15 @@ template <typename T, typename S> struct Problem : ProblemBase {
       GB_CUDA(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
       GB_CUDA(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
       coop_update = coop && (int64_t)per_sm * sms >= (Nc + PCG_CAMS - 1) / PCG_CAMS;
+      int per_sm2 = 0;
+      GB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_pcg_iterate<T>, PIT_THREADS, 0));
+      iter_grid = (int)std::min<int64_t>(std::min<int64_t>(2 * sms, (int64_t)per_sm2 * sms), (Nc + PIT_WARPS - 1) / PIT_WARPS);
+      const char *env = getenv("GB_FUSED_ITER");
+      fused_iter = coop && iter_grid >= 1 && !(env && env[0] == '0');
+      GB_TRY(dalloc(cta_part, 2 * (size_t)std::max(iter_grid, 1)));
     }
     // the super-tile kernels keep their camera accumulator rows in (opt-in sized) dynamic shared memory
-    GB_CUDA(ctx, cudaFuncSetAttribute(k_linearize<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIN * sizeof(T))));
+    GB_CUDA(ctx, cudaFuncSetAttribute(k_linearize<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_lin_bytes<T>()));
     GB_CUDA(ctx, cudaFuncSetAttribute(k_prepare_tiles<T, S, PSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       PrepSmem<T, S>::TOTAL(PSTAGE)));
     GB_CUDA(ctx, cudaFuncSetAttribute(k_schur_product<T, S, NSTAGE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -256,6 +286,87 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_CUDA(ctx, cudaMallocHost((void **)&h_scalars, 8 * sizeof(double)));
     GB_CUDA(ctx, cudaMallocHost((void **)&h_state, sizeof(PcgState<T>)));
     GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->nranks > 1) GB_TRY(p2p_setup());
+    return GB_OK;
+  }
+
+  // Peer-memory exchange: one receive area per rank ([2 halves][nranks][slot] + flag words), exported with cudaIpc;
+  // the handles travel through an NCCL all-gather.  Any failure (no peer access, IPC unavailable) leaves p2p_on false
+  // on ALL ranks (agreed through an all-reduce) and the collectives stay on NCCL.  GB_P2P=0 disables it.
+  int p2p_setup() {
+    const int n = ctx->nranks, me = ctx->rank;
+    const char *env = getenv("GB_P2P");
+    int fail = (env && env[0] == '0') || n > P2P_MAX_RANKS || !g_nccl.AllGather ? 1 : 0;
+    const size_t slot = (((size_t)54 * ts.Nc * sizeof(T) + 1024) + 255) / 256 * 256;
+    const size_t half = slot * n, flag_off = 2 * half, magic_off = flag_off + 256;
+    const size_t total = std::max<size_t>((magic_off + 256 + (1 << 21) - 1) >> 21 << 21, (size_t)4 << 20); // own VA range
+    struct Pack { cudaIpcMemHandle_t h; unsigned long long magic; };
+    std::vector<Pack> packs(n);
+    unsigned char *hbuf = nullptr;
+    unsigned int *d_counter = nullptr;
+    unsigned long long *d_seq = nullptr;
+    GB_TRY(dalloc(hbuf, sizeof(Pack) * n));
+    GB_TRY(dalloc(d_counter, 1)); GB_TRY(dalloc(d_seq, 1));
+    // the time-out flag lives in pinned host memory (device-visible through UVA): the host reads it without a copy
+    GB_CUDA(ctx, cudaMallocHost((void **)&h_p2p_err, sizeof(int)));
+    *h_p2p_err = 0;
+    const unsigned long long magic = 0x67623230ull * 1000003ull + (unsigned long long)me * 7919ull + (unsigned long long)(uintptr_t)this;
+    if (!fail) {
+      if (cudaMalloc(&p2p_area, total) != cudaSuccess) { cudaGetLastError(); p2p_area = nullptr; fail = 1; }
+    }
+    if (!fail) {
+      GB_CUDA(ctx, cudaMemsetAsync(p2p_area, 0, total, ctx->stream));
+      GB_CUDA(ctx, cudaMemcpyAsync((unsigned char *)p2p_area + magic_off, &magic, 8, cudaMemcpyHostToDevice, ctx->stream));
+      GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      Pack mine{};
+      if (cudaIpcGetMemHandle(&mine.h, p2p_area) != cudaSuccess) { cudaGetLastError(); fail = 1; }
+      mine.magic = magic;
+      GB_CUDA(ctx, cudaMemcpyAsync(hbuf + sizeof(Pack) * me, &mine, sizeof(Pack), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (g_nccl.AllGather) {
+      const int rc = g_nccl.AllGather(hbuf + sizeof(Pack) * me, hbuf, sizeof(Pack), NCCL_INT8, ctx->comm, ctx->stream);
+      if (rc != 0) return ctx->fail(GB_ERR_NCCL, "ncclAllGather failed");
+      GB_CUDA(ctx, cudaMemcpyAsync(packs.data(), hbuf, sizeof(Pack) * n, cudaMemcpyDeviceToHost, ctx->stream));
+      GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (!fail) {
+      for (int r = 0; r < n && !fail; r++) {
+        if (r == me) { p2p_peer[r] = p2p_area; continue; }
+        void *q = nullptr;
+        if (cudaIpcOpenMemHandle(&q, packs[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); fail = 1; break; }
+        p2p_peer[r] = q;
+        unsigned long long seen = 0; // the mapping must start at the peer's allocation base
+        if (cudaMemcpy(&seen, (unsigned char *)q + magic_off, 8, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); fail = 1; }
+        else if (seen != packs[r].magic) fail = 1;
+      }
+    }
+    // agree: everybody or nobody
+    int *d_fail = nullptr;
+    GB_TRY(dalloc(d_fail, 1));
+    GB_CUDA(ctx, cudaMemcpyAsync(d_fail, &fail, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    const int rc = g_nccl.AllReduce(d_fail, d_fail, 1, NCCL_INT32, NCCL_SUM, ctx->comm, ctx->stream);
+    if (rc != 0) return ctx->fail(GB_ERR_NCCL, "ncclAllReduce failed");
+    int total_fail = 0;
+    GB_CUDA(ctx, cudaMemcpyAsync(&total_fail, d_fail, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (total_fail != 0) {
+      for (int r = 0; r < n; r++)
+        if (r != me && p2p_peer[r]) { cudaIpcCloseMemHandle(p2p_peer[r]); p2p_peer[r] = nullptr; }
+      return GB_OK; // NCCL path
+    }
+    pp.nranks = n; pp.rank = me;
+    for (int r = 0; r < n; r++) {
+      pp.recv[r] = (unsigned char *)p2p_peer[r];
+      pp.flags[r] = (unsigned long long *)((unsigned char *)p2p_peer[r] + flag_off);
+    }
+    pp.half_bytes = half; pp.slot_bytes = slot;
+    pp.counter = d_counter; pp.seq = d_seq; pp.error = h_p2p_err;
+    p2p_on = true;
+    return GB_OK;
+  }
+  int p2p_check() { // after a synchronise: did any wait time out?
+    if (!p2p_on) return GB_OK;
+    if (*(volatile int *)h_p2p_err) return ctx->fail(GB_ERR_NCCL, "peer-memory exchange timed out: a rank did not arrive");
     return GB_OK;
   }
 
@@ -275,7 +386,17 @@ template <typename T, typename S> struct Problem : ProblemBase {
     if (rc != 0) return ctx->fail(GB_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
     return GB_OK;
   }
-  int allreduce_T(T *buf, size_t count) { return allreduce(buf, count, sizeof(T) == 8); }
+  template <typename X> int exchange(X *buf, size_t count) {
+    if (ctx->nranks <= 1) return GB_OK;
+    if (!p2p_on || count * sizeof(X) > pp.slot_bytes) return allreduce(buf, count, sizeof(X) == 8);
+    const int grid = (int)std::min<size_t>((count + 255) / 256, 4 * 148);
+    k_p2p_push<X><<<grid, 256, 0, ctx->stream>>>(pp, buf, (long long)count);
+    GB_LAUNCH(ctx);
+    k_p2p_sum<X><<<grid, 256, 0, ctx->stream>>>(pp, buf, (long long)count);
+    GB_LAUNCH(ctx);
+    return GB_OK;
+  }
+  int allreduce_T(T *buf, size_t count) { return exchange<T>(buf, count); }
 
   // ---- IO ----------------------------------------------------------------------------------------------
   int set_observations(const void *o) override {
@@ -318,7 +439,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     cudaStream_t st = ctx->stream;
     k_cam_precompute<T><<<(ts.Nc + 127) / 128, 128, 0, st>>>(ts.Nc, cams, camx);
     GB_LAUNCH(ctx);
-    k_linearize<T, S><<<ts.nst, TILE, SMEM_LIN * sizeof(T), st>>>(ts, camx, pts, obs, J, res, Cg, part18, cost_part);
+    k_linearize<T, S><<<ts.nst, TILE, smem_lin_bytes<T>(), st>>>(ts, camx, pts, obs, J, res, Cg, part18, cost_part);
     GB_LAUNCH(ctx);
     const bool multi = ctx->nranks > 1;
     k_cam_reduce_lin<T><<<ts.Nc, 288, 0, st>>>(ts, part18, diagB, gc, multi ? 0 : 1, scale_on ? 1 : 0, scale, b);
@@ -328,7 +449,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     if (multi) {
       GB_TRY(allreduce_T(diagB, dimc));
       GB_TRY(allreduce_T(gc, dimc));
-      GB_TRY(allreduce(scalars, 1, true));
+      GB_TRY(exchange<double>(scalars, 1));
       k_cam_finish_lin<T><<<(int)((dimc + 255) / 256), 256, 0, st>>>((int)dimc, scale_on ? 1 : 0, diagB, gc, scale, b);
       GB_LAUNCH(ctx);
     }
@@ -424,7 +545,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
       k_schur_product<T, S, NSTAGE, true><<<ts.ncta, 2 * TILE, SchurSmem<T, S>::TOTAL(NSTAGE), st>>>(ts, J, f_upw, xs, part9,
                                                                                                      nullptr, f_outp);
       GB_LAUNCH(ctx);
-      k_cam_reduce_spmv<T><<<ts.Nc, 288, 0, st>>>(ts, part9, scale, Ap_raw, 0, dterm, nullptr, Ap, dot_part, nullptr);
+      k_cam_reduce_spmv<T><<<ts.Nc, 288, 0, st>>>(ts, part9, scale, Ap_raw, 0, dterm, nullptr, Ap, dot_part, nullptr, pp, 0);
       GB_LAUNCH(ctx);
       k_full_finish_v2<T><<<full_blocks, 256, 0, st>>>(ts.Nc, ts.Np, mu, use_identity, Ap_raw, f_outp, f_p, scale, diagB, Cg,
                                                        f_v2, f_part);
@@ -480,6 +601,11 @@ template <typename T, typename S> struct Problem : ProblemBase {
     return GB_OK;
   }
 
+  int enqueue_prepare_tiles_only() {
+    k_prepare_tiles<T, S, PSTAGE><<<ts.ncta, 2 * TILE, PrepSmem<T, S>::TOTAL(PSTAGE), ctx->stream>>>(ts, J, W, h, part54);
+    GB_LAUNCH(ctx);
+    return GB_OK;
+  }
   int enqueue_prepare() {
     cudaStream_t st = ctx->stream;
     k_point_prepare<T><<<(ts.Np + 255) / 256, 256, 0, st>>>(ts.Np, scale_on ? 1 : 0, mu, use_identity, Cg, scale + dimc,
@@ -504,29 +630,34 @@ template <typename T, typename S> struct Problem : ProblemBase {
 
   // Ap_raw = D (B - E W E^T) D v for the vector v whose scaled copy D v is in xs; with `pvec` also
   // Ap = Ap_raw + dterm pvec and the per-camera partials of pvec.Ap
-  int enqueue_schur_product(const int *flag, const T *pvec, int prof_slot = -1) {
+  int enqueue_schur_product(const int *flag, const T *pvec, int prof_slot = -1, bool product_only = false) {
     cudaStream_t st = ctx->stream;
     const bool prof = profiling && prof_slot >= 0;
     if (prof) {
-      while ((int)prof_ev.size() < 2 * prof_slot + 2) {
+      while ((int)prof_ev.size() < 3 * prof_slot + 3) {
         cudaEvent_t e;
         GB_CUDA(ctx, cudaEventCreate(&e));
         prof_ev.push_back(e);
       }
-      GB_CUDA(ctx, cudaEventRecord(prof_ev[2 * prof_slot], st));
+      GB_CUDA(ctx, cudaEventRecord(prof_ev[3 * prof_slot], st));
     }
     const bool multi = ctx->nranks > 1;
     const int finish = (!multi && pvec) ? 1 : 0;
     k_schur_product<T, S, NSTAGE, false><<<ts.ncta, 2 * TILE, SchurSmem<T, S>::TOTAL(NSTAGE), st>>>(ts, J, W, xs, part9, flag,
                                                                                                     nullptr);
     GB_LAUNCH(ctx);
-    if (prof) GB_CUDA(ctx, cudaEventRecord(prof_ev[2 * prof_slot + 1], st));
+    if (prof) GB_CUDA(ctx, cudaEventRecord(prof_ev[3 * prof_slot + 1], st));
+    if (product_only) return GB_OK; // the fused iteration kernel sums the partial rows itself
     // The per-camera sum of the partial rows stays a separate, massively parallel kernel: fused into the tail of
     // the product kernel (last-arriver-reduces with per-camera counters) it cost 25 us per CTA of exposed latency,
     // because that kernel runs one CTA per SM (measured 463 us vs 249 + 11 us).
-    k_cam_reduce_spmv<T><<<ts.Nc, 288, 0, st>>>(ts, part9, scale, Ap_raw, finish, dterm, pvec, Ap, dot_part, flag);
+    // multi-GPU with the cooperative update: the reduction pushes its nine values per camera into every rank's receive
+    // slot and k_pcg_update pulls + sums them (one-shot all-gather over peer memory, p2p.cuh); otherwise NCCL / the
+    // generic exchange kernels all-reduce Ap_raw
+    const int push = (multi && p2p_on && pvec && coop_update) ? 1 : 0;
+    k_cam_reduce_spmv<T><<<ts.Nc, 288, 0, st>>>(ts, part9, scale, Ap_raw, finish, dterm, pvec, Ap, dot_part, flag, pp, push);
     GB_LAUNCH(ctx);
-    if (multi) {
+    if (multi && !push) {
       GB_TRY(allreduce_T(Ap_raw, dimc));
       if (pvec && !coop_update) { // with the cooperative update, Ap and the dot partials are formed inside it
         k_dot_partials<T><<<(ts.Nc + 127) / 128, 128, 0, st>>>(ts.Nc, Ap_raw, dterm, pvec, Ap, dot_part, flag);
@@ -548,16 +679,28 @@ template <typename T, typename S> struct Problem : ProblemBase {
     const T tol = (T)o->tolerance, ratio = (T)o->rejection_ratio;
     const int max_iter = (int)o->max_iterations, nc = ts.Nc;
     for (int64_t k = 0; k < o->max_iterations; k++) {
-      GB_TRY(enqueue_schur_product(done_flag, pv, (int)k));
-      if (coop_update) {
+      const bool fused = fused_iter && (ctx->nranks == 1 || p2p_on); // without peer memory: separate kernels + NCCL
+      GB_TRY(enqueue_schur_product(done_flag, pv, (int)k, fused));
+      if (fused) {
+        PcgState<T> *stp = pcg_state + 2 * k;
+        const T *c_part = part9, *c_scale = scale, *c_dterm = dterm, *c_Minv = Minv;
+        int multi = ctx->nranks > 1 ? 1 : 0;
+        void *args[] = {(void *)&ts, (void *)&stp, (void *)&tol, (void *)&ratio, (void *)&max_iter, (void *)&c_part,
+                        (void *)&c_scale, (void *)&c_dterm, (void *)&c_Minv, (void *)&x, (void *)&xbak, (void *)&r,
+                        (void *)&z, (void *)&pv, (void *)&xs, (void *)&Ap, (void *)&cta_part, (void *)&done_flag,
+                        (void *)&pp, (void *)&multi};
+        GB_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)k_pcg_iterate<T>, dim3(iter_grid), dim3(PIT_THREADS), args, 0, st));
+        GB_LAUNCH(ctx);
+      } else if (coop_update) {
         // both halves of the vector update in one cooperative launch (grid-wide sync instead of a kernel boundary)
         PcgState<T> *stp = pcg_state + 2 * k;
         const T *c_Minv = Minv, *c_scale = scale, *c_dterm = dterm;
         const T *c_raw = ctx->nranks > 1 ? Ap_raw : nullptr;
+        int pull = (ctx->nranks > 1 && p2p_on) ? 1 : 0;
         void *args[] = {(void *)&nc, (void *)&stp, (void *)&tol, (void *)&ratio, (void *)&max_iter, (void *)&dot_part,
                         (void *)&Ap, (void *)&c_Minv, (void *)&c_scale, (void *)&x, (void *)&xbak, (void *)&r,
                         (void *)&z, (void *)&pv, (void *)&xs, (void *)&rz_part, (void *)&done_flag, (void *)&c_raw,
-                        (void *)&c_dterm};
+                        (void *)&c_dterm, (void *)&pp, (void *)&pull};
         GB_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)k_pcg_update<T>, dim3(gridc), dim3(288), args, 0, st));
         GB_LAUNCH(ctx);
       } else {
@@ -568,6 +711,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
                                                 scale, rz_part, x, xbak, z, pv, xs, done_flag);
         GB_LAUNCH(ctx);
       }
+      if (profiling && 3 * k + 2 < (int64_t)prof_ev.size()) GB_CUDA(ctx, cudaEventRecord(prof_ev[3 * k + 2], st));
     }
     GB_CUDA(ctx, cudaMemcpyAsync(h_state, pcg_state + 2 * o->max_iterations, sizeof(PcgState<T>), cudaMemcpyDeviceToHost, st));
     GB_TRY(launch_check());
@@ -609,10 +753,10 @@ template <typename T, typename S> struct Problem : ProblemBase {
   }
 
   int fetch_scalars() {
-    if (ctx->nranks > 1) GB_TRY(allreduce(scalars, 2, true)); // cost and the point part of rho; the camera part is replicated
+    if (ctx->nranks > 1) GB_TRY(exchange<double>(scalars, 2)); // cost and the point part of rho; the camera part is replicated
     GB_CUDA(ctx, cudaMemcpyAsync(h_scalars, scalars, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return GB_OK;
+    return p2p_check();
   }
 
   int require(bool cond, const char *what) {
@@ -633,9 +777,10 @@ template <typename T, typename S> struct Problem : ProblemBase {
   int compute_cost(double *chi2) override {
     GB_TRY(require(have_obs && have_vertices, "gb_compute_cost needs observations and vertices"));
     GB_TRY(enqueue_cost());
-    if (ctx->nranks > 1) GB_TRY(allreduce(scalars, 1, true));
+    if (ctx->nranks > 1) GB_TRY(exchange<double>(scalars, 1));
     GB_CUDA(ctx, cudaMemcpyAsync(h_scalars, scalars, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    GB_TRY(p2p_check());
     if (chi2) *chi2 = (double)(T)h_scalars[0];
     return GB_OK;
   }
@@ -851,10 +996,12 @@ template <typename T, typename S> struct Problem : ProblemBase {
       if (profiling && !full) {
         // launches 0 .. k_exec-1 did the work (a launch after the stop flag returns at once), except that an
         // iteration stopped by rz == 0 or a bad denominator never used its product
-        for (int64_t k = 0; k < k_exec && 2 * k + 1 < (int64_t)prof_ev.size(); k++) {
-          cudaEventElapsedTime(&ms, prof_ev[2 * k], prof_ev[2 * k + 1]);
+        for (int64_t k = 0; k < k_exec && 3 * k + 2 < (int64_t)prof_ev.size(); k++) {
+          cudaEventElapsedTime(&ms, prof_ev[3 * k], prof_ev[3 * k + 1]);
           R.product_seconds += ms * 1e-3;
           R.product_launches++;
+          cudaEventElapsedTime(&ms, prof_ev[3 * k + 1], prof_ev[3 * k + 2]);
+          R.update_seconds += ms * 1e-3;
         }
       }
       if (solve_ok && std::isfinite((double)new_chi2) && rho > T(0)) {
@@ -912,7 +1059,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     cudaStream_t st = ctx->stream;
     if (!linearized) GB_TRY(enqueue_linearize());
     if (stage >= 2 && !prepared) GB_TRY(enqueue_prepare());
-    if (stage == 2 || stage == 3) {
+    if (stage == 2 || stage == 3 || stage == 5 || stage == 6) {
       // a defined vector in xs / x: one PCG initialisation
       const int gridc = (ts.Nc + PCG_CAMS - 1) / PCG_CAMS;
       k_pcg_init<T><<<gridc, 288, 0, st>>>(ts.Nc, bS, Minv, scale, x, r, z, pv, xs, rz_part);
@@ -927,6 +1074,16 @@ template <typename T, typename S> struct Problem : ProblemBase {
       case 2: GB_TRY(enqueue_schur_product(nullptr, pv)); break;
       case 3: GB_TRY(enqueue_step(false)); break;
       case 4: GB_TRY(enqueue_cost()); break;
+      case 5: // the product kernel alone
+        k_schur_product<T, S, NSTAGE, false><<<ts.ncta, 2 * TILE, SchurSmem<T, S>::TOTAL(NSTAGE), st>>>(ts, J, W, xs, part9,
+                                                                                                        nullptr, nullptr);
+        GB_LAUNCH(ctx);
+        break;
+      case 6: // the per-camera reduction of its partial rows alone (single-GPU form)
+        k_cam_reduce_spmv<T><<<ts.Nc, 288, 0, st>>>(ts, part9, scale, Ap_raw, 1, dterm, pv, Ap, dot_part, nullptr, pp, 0);
+        GB_LAUNCH(ctx);
+        break;
+      case 7: GB_TRY(enqueue_prepare_tiles_only()); break;
       default: return ctx->fail(GB_ERR_INVALID, "unknown stage %d", stage);
       }
     }
@@ -1121,6 +1278,7 @@ int gb_structure_hessian(const gb_structure *s, int64_t *cp, int64_t *ri, int64_
 int gb_problem_info(const gb_problem *p, int64_t info[12]) {
   if (!p || !info) return GB_ERR_INVALID;
   fill_info(p->impl->hs, info, p->impl->device_bytes());
+  info[11] = p->impl->exchange_mode();
   return GB_OK;
 }
 

@@ -29,6 +29,7 @@
 #include <cuda_runtime.h>
 
 #include "bal_math.cuh"
+#include "p2p.cuh"
 #include "structure.hpp"
 
 namespace gb {
@@ -36,7 +37,10 @@ namespace gb {
 constexpr int CAM_STRIDE = 10; // padded camera row
 constexpr int NPLANES = 12;
 // dynamic shared memory of the super-tile kernels, in elements of T
-constexpr int SMEM_LIN = TILE * 9 + SLOT_CAP * 18;
+constexpr int LIN_STR = 19; // staging row stride of k_linearize (18 values; odd stride: conflict-free 64-bit rows)
+template <typename T> constexpr int smem_lin_bytes() { // staging, accumulator rows, tile record
+  return (TILE * LIN_STR + SLOT_CAP * 18) * (int)sizeof(T) + 16 + REC_BYTES;
+}
 // per-point W row stride: 6 values, padded to 8 in FP32 so that a tile's rows start 16-byte aligned (TMA)
 template <typename T> struct WST { static constexpr int value = sizeof(T) == 4 ? 8 : 6; };
 constexpr int ACC54 = 55; // shared-memory stride of the 54-wide accumulator rows (odd: rows start in different banks)
@@ -242,24 +246,32 @@ k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
             const typename V2<T>::type *__restrict__ obs, typename V2<S>::type *__restrict__ J,
             typename V2<T>::type *__restrict__ res, T *__restrict__ Cg, T *__restrict__ part /*[nrows][18]*/,
             double *__restrict__ cost_part /*[ntiles]*/) {
+  // ncu of the first version (tables read from global memory inside the reduction loops, two 9-wide camera passes):
+  // 41 % of the stall samples were long-scoreboard waits in those loops, 61 % of all samples sat in the loops.
+  // Here the tile's packed record (segment and point tables) is copied to shared memory while the camera model is
+  // evaluated, and diag(B) and g_c go through ONE 18-wide staged pass with one thread per (segment, component triple).
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T *sv = reinterpret_cast<T *>(smem_raw); // [TILE*9]
-  T *acc = sv + TILE * 9;                  // [SLOT_CAP*18]
+  T *sv = reinterpret_cast<T *>(smem_raw);            // [TILE*LIN_STR] staging (point side uses the first TILE*9)
+  T *acc = sv + TILE * LIN_STR;                       // [SLOT_CAP*18]
+  unsigned char *rec = smem_raw + (((TILE * LIN_STR + SLOT_CAP * 18) * (int)sizeof(T) + 15) & ~15); // [REC_BYTES]
   __shared__ double shd[32];
   const int st = blockIdx.x, t = threadIdx.x;
   const int row0 = ds.st_row[st], nslots = ds.st_row[st + 1] - row0;
   for (int i = t; i < nslots * 18; i += TILE) acc[i] = T(0);
   __syncthreads();
   for (int tile = ds.st_tile[st]; tile < ds.st_tile[st + 1]; tile++) {
+    // the record is consumed after the first barrier below; its load overlaps the arithmetic
+    if (t < REC_BYTES / 16)
+      reinterpret_cast<uint4 *>(rec)[t] = __ldg(reinterpret_cast<const uint4 *>(ds.trec + (int64_t)tile * REC_BYTES) + t);
     const TileMeta tm = ds.tmeta[tile];
     const int64_t slot = (int64_t)tile * TILE + t;
     const uint32_t om = ds.ometa[slot];
-    const int cslot = (int)(om >> 16), rank = (int)((om >> 8) & 0xffu), ptl = (int)(om & 0xffu);
+    const int rank = (int)((om >> 8) & 0xffu), ptl = (int)(om & 0xffu);
     const bool active = t < tm.n;
     BalObs<T> B;
     double cost = 0.0;
     if (active) {
-      const int c = ds.row_cam[row0 + cslot], p = tm.p0 + ptl;
+      const int c = ds.tile_cam[slot], p = tm.p0 + ptl;
       T cx[CAMX], X[3], ob[2];
       load_camx<T>(cams, c, cx); // `cams` is the per-camera precomputed table (k_cam_precompute)
       X[0] = pts[3 * (int64_t)p];
@@ -295,27 +307,60 @@ k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
     }
     __syncthreads();
     {
-      const uint16_t *pt = ds.pt_tab + tm.pt_off;
-      for (int item = t; item < tm.np * 9; item += TILE) {
-        const int q = item / 9, k = item - 9 * q;
+      // one thread per (point, component triple)
+      const uint16_t *pt = reinterpret_cast<const uint16_t *>(rec + REC_PT);
+      for (int item = t; item < tm.np * 3; item += TILE) {
+        const int q = item / 3, g = item - 3 * q;
         const int b = pt[q], e = pt[q + 1];
-        T a = T(0);
-        for (int rowi = b; rowi < e; rowi++) a += sv[rowi * 9 + k];
-        Cg[(int64_t)(tm.p0 + q) * 9 + k] = a;
+        T a0 = T(0), a1 = T(0), a2 = T(0);
+        for (int rowi = b; rowi < e; rowi++) {
+          const T *r = sv + rowi * 9 + 3 * g;
+          a0 += r[0];
+          a1 += r[1];
+          a2 += r[2];
+        }
+        T *out = Cg + (int64_t)(tm.p0 + q) * 9 + 3 * g;
+        out[0] = a0;
+        out[1] = a1;
+        out[2] = a2;
       }
     }
     __syncthreads();
-    T v[9];
+    // camera side: diag(B) (9) and g_c (9) of this observation at the slot's own row (slots are in camera order)
+    {
+      T *row = sv + t * LIN_STR;
 #pragma unroll
-    for (int k = 0; k < 9; k++) v[k] = active ? B.Jc[2 * k] * B.Jc[2 * k] + B.Jc[2 * k + 1] * B.Jc[2 * k + 1] : T(0);
-    tile_cam_accumulate<T>(v, t, tm.nseg, ds.seg_tab + tm.seg_off, sv, acc, 18, 0);
-#pragma unroll
-    for (int k = 0; k < 9; k++) v[k] = active ? -(B.Jc[2 * k] * B.r[0] + B.Jc[2 * k + 1] * B.r[1]) : T(0);
-    tile_cam_accumulate<T>(v, t, tm.nseg, ds.seg_tab + tm.seg_off, sv, acc, 18, 9);
+      for (int k = 0; k < 9; k++) {
+        row[k] = active ? B.Jc[2 * k] * B.Jc[2 * k] + B.Jc[2 * k + 1] * B.Jc[2 * k + 1] : T(0);
+        row[9 + k] = active ? -(B.Jc[2 * k] * B.r[0] + B.Jc[2 * k + 1] * B.r[1]) : T(0);
+      }
+    }
+    __syncthreads();
+    {
+      const uint32_t *sg = reinterpret_cast<const uint32_t *>(rec + REC_SEG);
+      for (int item = t; item < tm.nseg * 6; item += TILE) {
+        const int q = item / 6, g = item - 6 * q;
+        const uint32_t e0 = sg[q], e1 = sg[q + 1];
+        const int b = (int)(e0 >> 16), e = (int)(e1 >> 16), cs = (int)(e0 & 0xffffu);
+        T a0 = T(0), a1 = T(0), a2 = T(0);
+        for (int rowi = b; rowi < e; rowi++) {
+          const T *r = sv + rowi * LIN_STR + 3 * g;
+          a0 += r[0];
+          a1 += r[1];
+          a2 += r[2];
+        }
+        T *ar = acc + cs * 18 + 3 * g;
+        ar[0] += a0;
+        ar[1] += a1;
+        ar[2] += a2;
+      }
+    }
     // per-tile cost partial with the same reduction tree as k_cost_tiles: chi2 of linearize == chi2 of cost, bit for bit
+    // (its two barriers also separate this tile's staging reads from the next tile's record and staging writes)
     const double tot = block_sum<double>(cost, shd);
     if (t == 0) cost_part[tile] = tot;
   }
+  __syncthreads();
   for (int i = t; i < nslots * 18; i += TILE) part[(int64_t)ds.row_out[row0 + i / 18] * 18 + i % 18] = acc[i];
 }
 
@@ -966,16 +1011,27 @@ template <typename T> __device__ __forceinline__ T sum_all(const T *a, int n, T 
 
 // Camera side of the product: Ap_raw = D_c * sum(partial rows).  With finish != 0 (single GPU) it also forms
 // Ap = Ap_raw + dterm p and the per-camera partial of p.Ap.
+// With push != 0 (multi-GPU over peer memory) the nine values go straight into every rank's receive slot of this rank
+// instead of Ap_raw, and the last CTA publishes the exchange (p2p.cuh); the consumer is k_pcg_update / k_p2p_sum.
 template <typename T>
 __global__ void __launch_bounds__(288)
 k_cam_reduce_spmv(DevStruct ds, const T *__restrict__ part, const T *__restrict__ scale_c, T *__restrict__ Ap_raw,
                   int finish, const T *__restrict__ dterm, const T *__restrict__ p, T *__restrict__ Ap,
-                  T *__restrict__ dot_part, const int *__restrict__ done_flag) {
+                  T *__restrict__ dot_part, const int *__restrict__ done_flag, P2P pp, int push) {
   __shared__ T sh[32 * 9];
   __shared__ T out[9];
   if (done_flag && *done_flag) return;
   const int c = blockIdx.x;
   cam_gather<T>(ds, c, part, 9, 1, sh, out);
+  if (push) {
+    const unsigned long long epoch = p2p_next_epoch(pp);
+    if (threadIdx.x < 9) {
+      const T raw = scale_c[c * 9 + threadIdx.x] * out[threadIdx.x];
+      for (int r = 0; r < pp.nranks; r++) p2p_slot<T>(pp, r, pp.rank, epoch)[c * 9 + threadIdx.x] = raw;
+    }
+    p2p_signal(pp, epoch, gridDim.x);
+    return;
+  }
   if (threadIdx.x == 0) {
     T d = T(0);
 #pragma unroll
@@ -1176,18 +1232,25 @@ template <typename T>
 __global__ void __launch_bounds__(288)
 k_pcg_update(int Nc, PcgState<T> *st, T tol, T ratio, int max_iter, T *dot_part, T *Ap, const T *Minv, const T *scale_c,
              T *x, T *xbak, T *r, T *z, T *p, T *xs, T *rz_part, int *done_flag,
-             const T *Ap_raw /*multi-GPU: all-reduced raw product, else null*/, const T *dterm) {
+             const T *Ap_raw /*multi-GPU: all-reduced raw product, else null*/, const T *dterm, P2P pp, int pull) {
   if (Ap_raw != nullptr) {
-    // multi-GPU: Ap = Ap_raw + dterm p and the per-camera p.Ap partials are formed here, after the all-reduce
+    // multi-GPU: Ap = Ap_raw + dterm p and the per-camera p.Ap partials are formed here, after the all-reduce.
+    // With pull != 0 the all-reduce itself happens here: wait for the peers' pushes of this iteration's exchange
+    // and add the nranks slots in rank order (p2p.cuh).
     if (!st->done) {
       __shared__ T sq0[288];
       const int t = threadIdx.x, g = t / 9, c = blockIdx.x * PCG_CAMS + g, k = t - 9 * g;
       const bool ok = c < Nc;
       T prod = T(0);
+      unsigned long long epoch = 0;
+      if (pull) {
+        epoch = p2p_current_epoch(pp);
+        p2p_wait(pp, epoch);
+      }
       if (ok) {
         const int i = c * 9 + k;
         const T pk = p[i];
-        const T ap = Ap_raw[i] + dterm[i] * pk;
+        const T ap = (pull ? p2p_sum<T>(pp, epoch, i) : Ap_raw[i]) + dterm[i] * pk;
         Ap[i] = ap;
         prod = pk * ap;
       }
@@ -1209,6 +1272,215 @@ k_pcg_update(int Nc, PcgState<T> *st, T tol, T ratio, int max_iter, T *dot_part,
   }
   cooperative_groups::this_grid().sync();
   pcg_half2<T>(Nc, st + 1, st + 2, tol, ratio, max_iter, scale_c, rz_part, x, xbak, z, p, xs, done_flag);
+}
+
+// ---------------------------------------------------------------------------------------------
+// One PCG iteration after the product kernel, in ONE cooperative launch: per-camera sum of the partial rows
+// (k_cam_reduce_spmv), the multi-GPU exchange of S p (p2p.cuh), both dot products and all vector updates
+// (pcg_half1 / pcg_half2), separated by grid-wide barriers instead of kernel boundaries.  ncu on Venice: the three
+// separate kernels took 12 + 17 us per iteration plus launch gaps next to a 250 us product.
+// A CTA owns a contiguous block of cameras, a warp works on one camera at a time: lanes (sub, k) = (lane / 9, lane % 9)
+// for lane < 27 sum rows sub, sub+3, ... of component k; lanes 0..8 then own the camera's nine vector entries.
+// Every sum has a fixed order: bit-reproducible, and identical on all ranks (the exchange adds the ranks in rank order).
+// ---------------------------------------------------------------------------------------------
+constexpr int PIT_THREADS = 256, PIT_WARPS = PIT_THREADS / 32;
+
+// lanes 0..8 hold v (others 0): fixed-tree sum, valid in lane 0
+template <typename T> __device__ __forceinline__ T sum9(T v) {
+  v += __shfl_down_sync(0xffffffffu, v, 8);
+  v += __shfl_down_sync(0xffffffffu, v, 4);
+  v += __shfl_down_sync(0xffffffffu, v, 2);
+  v += __shfl_down_sync(0xffffffffu, v, 1);
+  return v;
+}
+// per-warp values (lane 0) -> CTA total -> cta_part[blockIdx.x]; then, after the grid barrier, the grid total
+template <typename T> __device__ __forceinline__ void cta_publish(T wv, T *wpart, T *cta_part) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) wpart[warp] = wv;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    T tot = T(0);
+#pragma unroll
+    for (int w = 0; w < PIT_WARPS; w++) tot += wpart[w];
+    *(volatile T *)(cta_part + blockIdx.x) = tot;
+  }
+}
+template <typename T> __device__ __forceinline__ T grid_total(const T *cta_part, int n, T *sh) {
+  T acc = T(0);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += __ldcg(cta_part + i);
+  return block_sum<T>(acc, sh);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(PIT_THREADS)
+k_pcg_iterate(DevStruct ds, PcgState<T> *st /*in: st[0], out: st[2]*/, T tol, T ratio, int max_iter,
+              const T *__restrict__ part /*[nrows][9]*/, const T *__restrict__ scale_c, const T *__restrict__ dterm,
+              const T *__restrict__ Minv, T *x, T *xbak, T *r, T *z, T *p, T *xs, T *Ap, T *cta_part /*[2][grid]*/,
+              int *done_flag, P2P pp, int multi) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  __shared__ T sh[32];
+  __shared__ T wpart[PIT_WARPS];
+  PcgState<T> s = *st;
+  const bool leader = blockIdx.x == 0 && threadIdx.x == 0;
+  // stopped earlier, or rz == 0 (pcg_schur.hpp:109-111): uniform across the grid and across ranks
+  if (s.done) {
+    if (leader) st[2] = s;
+    return;
+  }
+  if (s.rz == T(0)) {
+    if (leader) { s.done = 1; s.reason = 3; st[2] = s; *done_flag = 1; }
+    return;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x, Nc = ds.Nc;
+  const int cpc = (Nc + G - 1) / G;
+  const int c_begin = blockIdx.x * cpc, c_end = min(Nc, c_begin + cpc);
+  const int k = lane % 9, sub = lane / 9;
+  const bool own = lane < 9;
+  const unsigned long long epoch = multi ? p2p_next_epoch(pp) : 0ull;
+  // the warp's first camera (its only one when Nc <= grid * warps): everything phase 2 needs is fetched now, so that the
+  // loads overlap the row gather instead of following the grid barrier
+  const int c_first = c_begin + warp;
+  T m_pre[9], x_pre = T(0), r_pre = T(0), p_pre = T(0), sc_pre = T(0), dt_pre = T(0);
+  if (own && c_first < c_end) {
+    const T *m = Minv + (int64_t)c_first * 81;
+#pragma unroll
+    for (int j = 0; j < 9; j++) m_pre[j] = m[k + 9 * j];
+    const int i = c_first * 9 + k;
+    x_pre = x[i]; r_pre = r[i]; p_pre = p[i]; sc_pre = scale_c[i]; dt_pre = dterm[i];
+  }
+
+  // Ap = raw + dterm p and the p.Ap contribution of one camera (lanes 0..8)
+  auto finish = [&](int c, T raw) -> T {
+    T prod = T(0);
+    if (own) {
+      const int i = c * 9 + k;
+      const T pk = c == c_first ? p_pre : p[i];
+      const T ap = raw + (c == c_first ? dt_pre : dterm[i]) * pk;
+      Ap[i] = ap;
+      prod = pk * ap;
+    }
+    return sum9<T>(prod);
+  };
+
+  // ---- phase 1: raw = D_c * (sum of the camera's partial rows) ----
+  T dot_w = T(0);
+  for (int c = c_begin + warp; c < c_end; c += PIT_WARPS) {
+    const int b = ds.cam_row_ptr[c], n = ds.cam_row_ptr[c + 1] - b;
+    T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0), a4 = T(0), a5 = T(0), a6 = T(0), a7 = T(0);
+    if (sub < 3) {
+      const T *base = part + (int64_t)b * 9 + k;
+      int row = sub;
+      for (; row + 21 < n; row += 24) { // eight independent loads in flight per lane
+        a0 += base[row * 9];
+        a1 += base[(row + 3) * 9];
+        a2 += base[(row + 6) * 9];
+        a3 += base[(row + 9) * 9];
+        a4 += base[(row + 12) * 9];
+        a5 += base[(row + 15) * 9];
+        a6 += base[(row + 18) * 9];
+        a7 += base[(row + 21) * 9];
+      }
+      for (; row + 3 < n; row += 6) {
+        a0 += base[row * 9];
+        a1 += base[(row + 3) * 9];
+      }
+      for (; row < n; row += 3) a0 += base[row * 9];
+    }
+    const T v = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    const T v1 = __shfl_sync(0xffffffffu, v, k + 9), v2 = __shfl_sync(0xffffffffu, v, k + 18);
+    T raw = T(0);
+    if (own) raw = (c == c_first ? sc_pre : scale_c[c * 9 + k]) * ((v + v1) + v2);
+    if (multi) {
+      if (own)
+        for (int q = 0; q < pp.nranks; q++) p2p_slot<T>(pp, q, pp.rank, epoch)[c * 9 + k] = raw;
+    } else {
+      dot_w += finish(c, raw);
+    }
+  }
+  if (multi) {
+    // every CTA has pushed -> publish the epoch to the peers -> wait for theirs -> sum the slots in rank order
+    __threadfence_system();
+    grid.sync();
+    if (leader) {
+      *pp.seq = epoch;
+      __threadfence_system();
+      for (int q = 0; q < pp.nranks; q++)
+        if (q != pp.rank) st_release_sys(pp.flags[q] + pp.rank, epoch);
+    }
+    p2p_wait(pp, epoch);
+    for (int c = c_begin + warp; c < c_end; c += PIT_WARPS) {
+      T raw = T(0);
+      if (own) raw = p2p_sum<T>(pp, epoch, c * 9 + k);
+      dot_w += finish(c, raw);
+    }
+  }
+  cta_publish<T>(dot_w, wpart, cta_part);
+  __threadfence();
+  grid.sync();
+  const T denom = grid_total<T>(cta_part, G, sh);
+  if (denom == T(0) || isnan(denom)) { // pcg_schur.hpp:120-122
+    if (leader) { s.done = 1; s.reason = 4; s.denom = denom; st[2] = s; *done_flag = 1; }
+    return;
+  }
+  const T alpha = s.rz / denom;
+
+  // ---- phase 2: x += alpha p ; r -= alpha Ap ; z = Minv r ; r.z ----
+  T rz_w = T(0);
+  for (int c = c_begin + warp; c < c_end; c += PIT_WARPS) {
+    T rn = T(0);
+    const int i = c * 9 + k;
+    const bool first = c == c_first;
+    if (own) {
+      const T pi = first ? p_pre : p[i], xo = first ? x_pre : x[i];
+      xbak[i] = xo;
+      x[i] = alpha * pi + xo;                         // ops::axpy_async(x, alpha, p, x)
+      rn = -alpha * Ap[i] + (first ? r_pre : r[i]);   // ops::axpy_async(r, -alpha, Ap, r)
+      r[i] = rn;
+    }
+    const T *m = Minv + (int64_t)c * 81;
+    T acc = T(0);
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+      const T rj = __shfl_sync(0xffffffffu, rn, j);
+      if (own) acc += (first ? m_pre[j] : m[k + 9 * j]) * rj;
+    }
+    if (own) z[i] = acc;
+    rz_w += sum9<T>(own ? rn * acc : T(0));
+  }
+  __syncthreads(); // wpart is reused
+  cta_publish<T>(rz_w, wpart, cta_part + G);
+  __threadfence();
+  grid.sync();
+  const T rzn = grid_total<T>(cta_part + G, G, sh);
+
+  // ---- phase 3: rejection / convergence tests, beta, p, xs = D p (pcg_schur.hpp:144-163) ----
+  s.iter += 1;
+  s.alpha = alpha;
+  s.denom = denom;
+  if (fabs(rzn) > ratio * s.rz0 || isnan(rzn)) {
+    for (int c = c_begin + warp; c < c_end; c += PIT_WARPS)
+      if (own) x[c * 9 + k] = xbak[c * 9 + k];
+    if (leader) { s.done = 1; s.reason = 2; s.rz = rzn; st[2] = s; *done_flag = 1; }
+    return;
+  }
+  s.rz0 = fmin(s.rz0, fabs(rzn));
+  const T beta = rzn / s.rz;
+  s.beta = beta;
+  s.rz = rzn;
+  for (int c = c_begin + warp; c < c_end; c += PIT_WARPS)
+    if (own) {
+      const int i = c * 9 + k;
+      const T pn = beta * p[i] + z[i]; // ops::axpy_async(p, beta, p, z)
+      p[i] = pn;
+      xs[c * CAM_STRIDE + k] = scale_c[i] * pn;
+    }
+  if (fabs(rzn) < tol) { s.done = 1; s.reason = 1; }
+  else if (s.iter >= max_iter) { s.done = 1; s.reason = 0; }
+  if (leader) {
+    st[2] = s;
+    if (s.done) *done_flag = 1;
+  }
 }
 
 // xs = D_c x (for the back-substitution) ; also camera update + rho partial (ops/update.hpp:9-31,

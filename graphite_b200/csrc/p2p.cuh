@@ -1,0 +1,122 @@
+// p2p.cuh — the multi-GPU exchange step of the point-partitioned path, written over NVLink peer memory.
+//
+// Every camera-sized reduction of the path (diag(B) and g_c after linearize, the 54 Schur-diagonal sums, S p once per
+// PCG iteration, cost and rho scalars) is a sum over ranks of a small vector (128 KB - 6 MB).  At that size an
+// all-reduce is pure latency, so it is done as a ONE-SHOT ALL-GATHER + LOCAL SUM fused into the kernels either side:
+//   - the PRODUCER (e.g. the per-camera reduction of the partial rows) stores its values straight into every rank's
+//     receive area through peer-mapped pointers (cudaIpc), rank r's slot;
+//   - the last CTA of the producer publishes the exchange's epoch number to every peer's flag word (release, system scope);
+//   - the CONSUMER (e.g. the PCG vector update) waits for the epoch on its own flag words (acquire, system scope) and adds
+//     the nranks slots in RANK ORDER, so every rank computes bit-identical sums -> identical PCG scalars and LM
+//     decisions on all ranks with no broadcast, and run-to-run reproducible results (NCCL's ring order is not used).
+// The receive area has two halves indexed by epoch parity: rank A can push epoch e+1 while B still reads e, and A cannot
+// reach e+2 before B has pushed e+1, which B does only after consuming e (same stream).  The epoch is a DEVICE-side
+// sequence number advanced by every exchange that actually runs: producers that return early (PCG already stopped -
+// uniformly on all ranks, since all ranks hold identical scalars) do not consume one, which keeps the parity argument
+// valid whatever the host enqueued.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace gb {
+
+constexpr int P2P_MAX_RANKS = 8; // one NVSwitch box
+
+struct P2P {
+  int nranks, rank;
+  unsigned char *recv[P2P_MAX_RANKS];        // receive area of every rank (peer-mapped; [rank] is local)
+  unsigned long long *flags[P2P_MAX_RANKS];  // flag words of every rank: flags[dst][src] = last epoch src pushed to dst
+  unsigned long long half_bytes, slot_bytes; // receive area = [2 halves][nranks slots][slot_bytes]
+  unsigned int *counter;                     // local: CTAs of the running producer that have finished pushing
+  unsigned long long *seq;                   // local: epoch of the last exchange this rank has pushed
+  int *error;                                // local: set when a wait timed out (a peer died)
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// slot of rank `src` inside rank `dst`'s receive area for this epoch
+template <typename T> __device__ __forceinline__ T *p2p_slot(const P2P &pp, int dst, int src, unsigned long long epoch) {
+  return reinterpret_cast<T *>(pp.recv[dst] + (epoch & 1ull) * pp.half_bytes + (unsigned long long)src * pp.slot_bytes);
+}
+
+// epoch of the exchange a producer is about to push (read by every thread BEFORE its CTA signals) / of the exchange a
+// consumer has to wait for (the producer before it in the stream has advanced seq)
+__device__ __forceinline__ unsigned long long p2p_next_epoch(const P2P &pp) {
+  return *reinterpret_cast<volatile unsigned long long *>(pp.seq) + 1ull;
+}
+__device__ __forceinline__ unsigned long long p2p_current_epoch(const P2P &pp) {
+  return *reinterpret_cast<volatile unsigned long long *>(pp.seq);
+}
+
+// Producer side, called by EVERY thread of EVERY CTA of the grid after its peer stores: the last CTA to arrive publishes
+// the epoch to all peers.  (Pattern of the CUDA threadFenceReduction sample, with system-scope fences.)
+__device__ __forceinline__ void p2p_signal(const P2P &pp, unsigned long long epoch, unsigned int nblocks) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(pp.counter, 1u);
+    if (prev == nblocks - 1) {
+      *pp.counter = 0u; // the next producer starts after this grid has ended (stream order)
+      *pp.seq = epoch;  // every CTA has read seq before arriving
+      __threadfence_system();
+      for (int r = 0; r < pp.nranks; r++)
+        if (r != pp.rank) st_release_sys(pp.flags[r] + pp.rank, epoch);
+    }
+  }
+}
+
+// Consumer side, called by every thread of a CTA: returns when all peers have published `epoch`.
+__device__ __forceinline__ void p2p_wait(const P2P &pp, unsigned long long epoch) {
+  if (threadIdx.x < pp.nranks && (int)threadIdx.x != pp.rank) {
+    const unsigned long long *f = pp.flags[pp.rank] + threadIdx.x;
+    if (ld_acquire_sys(f) < epoch) {
+      const unsigned long long t0 = global_timer_ns();
+      while (ld_acquire_sys(f) < epoch) {
+        if (global_timer_ns() - t0 > 20000000000ull) { // 20 s: a peer is gone; fail loudly on the host instead of hanging
+          *pp.error = 1;
+          break;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// sum of the nranks slots in rank order (L2 loads: the slots are written by peers over NVLink)
+template <typename T> __device__ __forceinline__ T p2p_sum(const P2P &pp, unsigned long long epoch, long long i) {
+  T acc = __ldcg(p2p_slot<T>(pp, pp.rank, 0, epoch) + i);
+  for (int r = 1; r < pp.nranks; r++) acc += __ldcg(p2p_slot<T>(pp, pp.rank, r, epoch) + i);
+  return acc;
+}
+
+// Generic pair for buffers that have no fused producer / consumer: push src to every rank, then sum in place.
+template <typename T>
+__global__ void __launch_bounds__(256) k_p2p_push(P2P pp, const T *__restrict__ src, long long n) {
+  const unsigned long long epoch = p2p_next_epoch(pp);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const T v = src[i];
+    for (int r = 0; r < pp.nranks; r++) p2p_slot<T>(pp, r, pp.rank, epoch)[i] = v;
+  }
+  p2p_signal(pp, epoch, gridDim.x);
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_p2p_sum(P2P pp, T *__restrict__ dst, long long n) {
+  const unsigned long long epoch = p2p_current_epoch(pp);
+  p2p_wait(pp, epoch);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = p2p_sum<T>(pp, epoch, i);
+}
+
+} // namespace gb

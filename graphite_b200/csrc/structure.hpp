@@ -190,20 +190,26 @@ struct HostStructure {
       if (!partition_tiles(st_obs_opt, st_tile, st_row, row_cam)) return "a tile touches more cameras than the slot cap";
     } else {
       // The TMA kernels run one CTA per SM, so the number of super-tiles should fill whole waves of `sm_count`
-      // CTAs.  Try 6..12 waves and keep the fullest last wave (ties: fewer, longer super-tiles).  Small problems:
-      // one tile per super-tile.
+      // CTAs, and a super-tile should be long enough (~12 tiles) to amortise the CTA's prologue and its row traffic:
+      // measured on rank shares of Venice (scripts/partition_probe.py, product + reduction per launch) 2 waves beat
+      // 6 by 30 % at 2.5 k tiles, 3 waves beat 8 by 20 % at 5 k tiles, 6-8 waves are level at 20 k tiles.
+      // Around w0 = tiles / (12 sm_count), clamped to 2..8 waves, keep the fullest last wave.  Small problems
+      // (under two waves of two tiles): one tile per super-tile.
       double best = -1.0;
       std::vector<int32_t> t_tile, t_row, t_cam;
-      if (nt <= 4 * sm_count) { // small problem: as many CTAs as tiles
+      if (nt < 4 * sm_count) { // small problem: as many CTAs as tiles
         if (!partition_tiles(1, st_tile, st_row, row_cam)) return "a tile touches more cameras than the slot cap";
-      } else
-      for (int w = 6; w <= 12; w++) {
-        const int64_t target = std::max<int64_t>(TILE, (m + (int64_t)sm_count * w - 1) / ((int64_t)sm_count * w));
-        if (!partition_tiles(target, t_tile, t_row, t_cam)) return "a tile touches more cameras than the slot cap";
-        const int64_t n = (int64_t)t_tile.size() - 1;
-        const double eff = (double)n / (double)(((n + sm_count - 1) / sm_count) * sm_count);
-        if (eff > best + 1e-9) { best = eff; st_tile = t_tile; st_row = t_row; row_cam = t_cam; }
-        if (target == TILE) break;
+      } else {
+        const int w0 = std::min(8, std::max(2, (int)((nt + 6 * sm_count) / (12 * sm_count))));
+        for (int w = std::max(2, w0 - 1); w <= w0 + 1; w++) {
+          const int64_t target = std::max<int64_t>(TILE, (m + (int64_t)sm_count * w - 1) / ((int64_t)sm_count * w));
+          if (!partition_tiles(target, t_tile, t_row, t_cam)) return "a tile touches more cameras than the slot cap";
+          const int64_t n = (int64_t)t_tile.size() - 1;
+          double eff = (double)n / (double)(((n + sm_count - 1) / sm_count) * sm_count);
+          if (w == w0) eff += 0.02; // prefer the target length unless a neighbour fills its last wave clearly better
+          if (eff > best + 1e-9) { best = eff; st_tile = t_tile; st_row = t_row; row_cam = t_cam; }
+          if (target == TILE) break;
+        }
       }
     }
     const int32_t nst = (int32_t)st_tile.size() - 1;

@@ -94,7 +94,8 @@ int gb_structure_hessian(const gb_structure *s, int64_t *colptr, int64_t *rowidx
 
 /* Sizes: [0]=n_tiles [1]=n_partial_rows (super-tile x camera) [2]=max_track_length [3]=hessian_dim
  * [4]=n_hessian_blocks [5]=n_hessian_values [6]=device bytes allocated [7]=n_obs [8]=n_super_tiles
- * [9]=n_camera_segments (tile x camera) [10]=storage slots [11]=0 */
+ * [9]=n_camera_segments (tile x camera) [10]=storage slots
+ * [11]=multi-GPU exchange: 0 single rank, 1 NCCL all-reduce, 2 one-shot all-gather over NVLink peer memory */
 int gb_problem_info(const gb_problem *p, int64_t info[12]);
 
 /* Replaces: add_factor(..., obs) (factor.hpp:374-412) / add_vertex (vertex.hpp:240-252) + to_device.
@@ -186,8 +187,9 @@ typedef struct {
   double seconds_total;     /* device time of the loop (CUDA events) */
   double seconds_linearize, seconds_prepare, seconds_pcg, seconds_backsubst, seconds_cost;
   double final_nu;
-  int64_t product_launches;  /* profile_product: executed launches of k_schur_tiles<MODE 0> and their device time */
+  int64_t product_launches;  /* profile_product: executed launches of the Schur product kernel and their device time */
   double product_seconds;
+  double update_seconds;     /* profile_product: device time of the rest of those PCG iterations (reduction, exchange, update) */
 } gb_lm_result;
 
 /* Replaces: optimizer::levenberg_marquardt (levenberg_marquardt.hpp:109-242).  trajectory (optional,
@@ -196,7 +198,8 @@ int gb_lm(gb_problem *p, const gb_lm_options *opt, gb_lm_result *result, double 
 
 /* Measurement hooks used by bench.py: number of kernels launched by this context since creation,
  * and event-timed repetitions of one stage (0 linearize, 1 prepare, 2 one PCG iteration, 3 back-subst +
- * update, 4 cost) -> average milliseconds per repetition. */
+ * update, 4 cost, 5 the Schur product kernel alone, 6 its per-camera reduction alone, 7 the prepare tile kernel alone)
+ * -> average milliseconds per repetition. */
 int64_t gb_kernel_launches(const gb_context *ctx);
 int gb_time_stage(gb_problem *p, int stage, int repetitions, double *ms_avg);
 

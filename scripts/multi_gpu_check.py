@@ -33,6 +33,7 @@ if rank == 0:
     rel = np.abs(traj[:, 1] - t1[:, 1]) / t1[:, 1]
     same_decisions = np.array_equal(traj[:, 0] == traj[:, 1], t1[:, 0] == t1[:, 1]) and np.array_equal(traj[:, 3], t1[:, 3])
     cam_rel = np.abs(cams - c1).max() / np.abs(c1).max()
+    print(f"exchange mode {P.info()['exchange_mode']} (2 = peer memory, 1 = NCCL)")
     print(f"world {world}: max rel cost diff {rel.max():.2e}, cameras rel {cam_rel:.2e}, same decisions {same_decisions}, "
           f"seconds {res['seconds_total']:.4f} vs single {r1['seconds_total']:.4f}")
     ok = rel.max() <= 1e-9 and same_decisions and cam_rel <= 1e-7

@@ -165,6 +165,9 @@ def test_fp32_matches_reference(ctx, gold):
     traj, res = P.lm(iterations=len(t))
     ok = t[:, 3] >= 1.2e-7
     n = int(np.argmin(ok)) if not ok.all() else len(t)
+    # a run may also end early by the reference's own rule `rho == 0 -> break` (levenberg_marquardt.hpp:228-231), which
+    # in FP32 fires as soon as a step leaves the cost bit-identical
+    n = min(n, len(traj))
     assert n >= 20
     r = np.abs(traj[:n, 1] - t[:n, 2]) / t[:n, 2]
     assert r.max() <= 1e-4, r
