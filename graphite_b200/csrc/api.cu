@@ -235,6 +235,11 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_TRY(upload(ts.row_out, hs.row_out));
     GB_TRY(upload(ts.cta_st, hs.cta_st));
     ts.ncta = hs.ncta(); ts.pad2 = 0;
+    GB_TRY(upload(ts.cm_slot, hs.cm_slot));
+    GB_TRY(upload(ts.cm_pt, hs.cm_pt));
+    GB_TRY(upload(ts.ch_ptr, hs.ch_ptr));
+    GB_TRY(upload(ts.cam_ch_ptr, hs.cam_ch_ptr));
+    ts.nchunks = hs.nchunks(); ts.pad3 = 0;
     GB_TRY(upload(ts.slot_of_obs, hs.slot_of_obs));
     GB_TRY(upload(ts.cam_idx, hs.cam_idx));
     GB_TRY(upload(ts.pt_idx, hs.pt_idx));
@@ -245,7 +250,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     if (!hs.identity_perm) GB_TRY(upload(d_perm, hs.perm));
     GB_TRY(dalloc(J, (size_t)NPLANES * hs.Mstore)); // zero-filled: padding slots stay zero for ever
     GB_TRY(dalloc(Cg, 9 * Np));
-    GB_TRY(dalloc(part18, (size_t)ts.nrows * 18)); GB_TRY(dalloc(part54, (size_t)ts.nrows * 54));
+    GB_TRY(dalloc(part18, (size_t)ts.nrows * 18)); GB_TRY(dalloc(part54, (size_t)std::max(ts.nchunks, 1) * 54));
     GB_TRY(dalloc(part9, (size_t)ts.nrows * 9)); GB_TRY(dalloc(sums54, Nc * 54));
     GB_TRY(dalloc(dot_part, Nc)); GB_TRY(dalloc(rz_part, Nc));
     {
@@ -518,7 +523,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     const size_t nbytes = (size_t)dimH * sizeof(T);
     if (!full_lin_valid) {
       // the 45 sums of Jc^T Jc per camera (mu-independent): the prepare pipeline with W = 0, h = 0
-      k_prepare_tiles<T, S, PSTAGE><<<ts.ncta, 2 * TILE, PrepSmem<T, S>::TOTAL(PSTAGE), st>>>(ts, J, f_zero, f_zero, part54);
+      k_prepare_cams<T, S><<<ts.nchunks, PC_THREADS, 0, st>>>(ts, J, f_zero, f_zero, part54);
       GB_LAUNCH(ctx);
       full_lin_valid = true;
       prepared = false; // part54 no longer holds the Schur sums
@@ -602,7 +607,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
   }
 
   int enqueue_prepare_tiles_only() {
-    k_prepare_tiles<T, S, PSTAGE><<<ts.ncta, 2 * TILE, PrepSmem<T, S>::TOTAL(PSTAGE), ctx->stream>>>(ts, J, W, h, part54);
+    k_prepare_cams<T, S><<<ts.nchunks, PC_THREADS, 0, ctx->stream>>>(ts, J, W, h, part54);
     GB_LAUNCH(ctx);
     return GB_OK;
   }
@@ -611,7 +616,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     k_point_prepare<T><<<(ts.Np + 255) / 256, 256, 0, st>>>(ts.Np, scale_on ? 1 : 0, mu, use_identity, Cg, scale + dimc,
                                                            b + dimc, W, h, 0);
     GB_LAUNCH(ctx);
-    k_prepare_tiles<T, S, PSTAGE><<<ts.ncta, 2 * TILE, PrepSmem<T, S>::TOTAL(PSTAGE), st>>>(ts, J, W, h, part54);
+    k_prepare_cams<T, S><<<ts.nchunks, PC_THREADS, 0, st>>>(ts, J, W, h, part54);
     GB_LAUNCH(ctx);
     const bool multi = ctx->nranks > 1;
     k_cam_reduce_prepare<T><<<ts.Nc, 288, 0, st>>>(ts, part54, 0, sums54, multi ? 0 : 1, mu, use_identity, diagB, gc,

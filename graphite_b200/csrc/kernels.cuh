@@ -72,6 +72,10 @@ struct DevStruct {
   const int32_t *row_out;      // [nrows] super-tile row (st_row + slot) -> position in the partial buffers
   const int32_t *cta_st;       // [ncta+1] super-tile ranges of the persistent CTAs
   int32_t ncta, pad2;
+  const int32_t *cm_slot, *cm_pt;  // [M] camera-major observation -> storage slot / point
+  const int32_t *ch_ptr;           // [nchunks+1] chunk -> camera-major observation range
+  const int32_t *cam_ch_ptr;       // [Nc+1] camera -> its chunk rows
+  int32_t nchunks, pad3;
   const int32_t *slot_of_obs; // [M] sorted observation -> storage slot (exports)
   const int32_t *cam_idx, *pt_idx, *pptr;    // sorted observations (exports)
 };
@@ -148,9 +152,11 @@ __device__ __forceinline__ void tile_cam_accumulate(const T v[9], int rank, int 
 // out[g*9+k] for g < ngroups; deterministic: sub-list i takes rows i, i+32, ...; then 0..31 in order.
 template <typename T>
 __device__ __forceinline__ void cam_gather(const DevStruct &ds, int c, const T *__restrict__ part, int pstride,
-                                           int ngroups, T *sh /*[32*9]*/, T *out /*smem [ngroups*9]*/) {
+                                           int ngroups, T *sh /*[32*9]*/, T *out /*smem [ngroups*9]*/,
+                                           const int32_t *__restrict__ row_ptr = nullptr) {
   const int sub = threadIdx.x / 9, k = threadIdx.x - 9 * sub;
-  const int b = ds.cam_row_ptr[c], e = ds.cam_row_ptr[c + 1];
+  if (!row_ptr) row_ptr = ds.cam_row_ptr;
+  const int b = row_ptr[c], e = row_ptr[c + 1];
   for (int g = 0; g < ngroups; g++) {
     T acc = T(0);
     if (sub < 32)
@@ -657,6 +663,89 @@ k_prepare_tiles(DevStruct ds, const typename V2<S>::type *__restrict__ J, const 
   }
 }
 
+// K3b, camera-major form.  The tile kernel above pushes 54 values per observation through shared-memory staging and
+// segment sums (ncu: 220 M warp instructions, 17 % FP64 pipe, 20 % DRAM - instruction-bound in the reduction loops).
+// Here one CTA owns a CHUNK of ONE camera's observations (camera-major index built on the host): every thread walks
+// its observations, gathers the 24 Jacobian values from the tile-major store by slot (adjacent slots of one camera
+// share sectors) plus W and h of the point, and keeps all 54 sums in registers - no staging, no segment tables; one
+// shuffle tree per CTA at the end.  Output: one 54-value row per chunk, rows of a camera contiguous (cam_ch_ptr).
+constexpr int PC_THREADS = 128;
+template <typename T, typename S>
+__global__ void __launch_bounds__(PC_THREADS, 2)
+k_prepare_cams(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *__restrict__ W,
+               const T *__restrict__ h, T *__restrict__ part /*[nchunks][54]*/) {
+  using S2 = typename V2<S>::type;
+  __shared__ T sm[PC_THREADS / 32][54];
+  const int ch = blockIdx.x;
+  const int b = ds.ch_ptr[ch], e = ds.ch_ptr[ch + 1];
+  T acc[54];
+#pragma unroll
+  for (int v = 0; v < 54; v++) acc[v] = T(0);
+  for (int i = b + (int)threadIdx.x; i < e; i += PC_THREADS) {
+    const int slot = ds.cm_slot[i], p = ds.cm_pt[i];
+    const S2 *base = J + ((int64_t)(slot >> 8) * NPLANES) * TILE + (slot & (TILE - 1));
+    T jc[18], jp[6];
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+      const S2 v = __ldg(base + j * TILE);
+      jc[2 * j] = (T)v.x;
+      jc[2 * j + 1] = (T)v.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const S2 v = __ldg(base + (9 + j) * TILE);
+      jp[2 * j] = (T)v.x;
+      jp[2 * j + 1] = (T)v.y;
+    }
+    const T *w = W + (int64_t)p * WST<T>::value;
+    const T w00 = w[0], w01 = w[1], w02 = w[2], w11 = w[3], w12 = w[4], w22 = w[5];
+    const T *hp = h + (int64_t)p * HST;
+    const T h0 = hp[0], h1 = hp[1], h2 = hp[2];
+    // rows of Jp: a = (jp[0], jp[2], jp[4]), b = (jp[1], jp[3], jp[5]);  N = Jp W Jp^T ; M = I - N
+    const T wa0 = w00 * jp[0] + w01 * jp[2] + w02 * jp[4];
+    const T wa1 = w01 * jp[0] + w11 * jp[2] + w12 * jp[4];
+    const T wa2 = w02 * jp[0] + w12 * jp[2] + w22 * jp[4];
+    const T wb0 = w00 * jp[1] + w01 * jp[3] + w02 * jp[5];
+    const T wb1 = w01 * jp[1] + w11 * jp[3] + w12 * jp[5];
+    const T wb2 = w02 * jp[1] + w12 * jp[3] + w22 * jp[5];
+    const T n00 = jp[0] * wa0 + jp[2] * wa1 + jp[4] * wa2;
+    const T n01 = jp[0] * wb0 + jp[2] * wb1 + jp[4] * wb2;
+    const T n11 = jp[1] * wb0 + jp[3] * wb1 + jp[5] * wb2;
+    const T m00 = T(1) - n00, m01 = -n01, m11 = T(1) - n11;
+    const T q0 = jp[0] * h0 + jp[2] * h1 + jp[4] * h2;
+    const T q1 = jp[1] * h0 + jp[3] * h1 + jp[5] * h2;
+    int idx = 0;
+#pragma unroll
+    for (int a = 0; a < 9; a++) {
+      // row a of A = Jc^T M Jc (upper part): (jc_a^T M) jc_j
+      const T k0 = m00 * jc[2 * a] + m01 * jc[2 * a + 1], k1 = m01 * jc[2 * a] + m11 * jc[2 * a + 1];
+#pragma unroll
+      for (int j = a; j < 9; j++) {
+        acc[idx] += k0 * jc[2 * j] + k1 * jc[2 * j + 1];
+        idx++;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 9; k++) acc[45 + k] += jc[2 * k] * q0 + jc[2 * k + 1] * q1;
+  }
+  // CTA total: shuffle tree inside each warp, then the warps in order
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int v = 0; v < 54; v++) {
+    T a = acc[v];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+    if (lane == 0) sm[warp][v] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x < 54) {
+    T tot = sm[0][threadIdx.x];
+#pragma unroll
+    for (int w2 = 1; w2 < PC_THREADS / 32; w2++) tot += sm[w2][threadIdx.x];
+    part[(int64_t)ch * 54 + threadIdx.x] = tot;
+  }
+}
+
 // Gauss-Jordan inverse of a symmetric positive definite 9x9 matrix by 162 threads on the augmented matrix
 // M = [A | I] (9 x 18, row-major in shared memory).  S_cc is SPD with a unit-scale diagonal (Jacobi scaling plus
 // damping), so no pivoting is needed.  Every thread of the block must call it (barriers inside).
@@ -690,7 +779,7 @@ k_cam_reduce_prepare(DevStruct ds, const T *__restrict__ part, int from_sums, T 
   __shared__ T Maug[9 * 18], fcol[9];
   const int c = blockIdx.x, t = threadIdx.x;
   if (!from_sums) {
-    cam_gather<T>(ds, c, part, 54, 6, sh, out);
+    cam_gather<T>(ds, c, part, 54, 6, sh, out, ds.cam_ch_ptr); // rows of k_prepare_cams: one per camera chunk
     if (t < 54) sums[(int64_t)c * 54 + t] = out[t];
   } else {
     if (t < 54) out[t] = sums[(int64_t)c * 54 + t];
@@ -1550,7 +1639,7 @@ k_full_cam_blocks(DevStruct ds, const T *__restrict__ part /*[nrows][54]*/, T mu
   __shared__ T out[54];
   __shared__ T Maug[9 * 18], fcol[9];
   const int c = blockIdx.x, t = threadIdx.x;
-  cam_gather<T>(ds, c, part, 54, 5, sh, out);
+  cam_gather<T>(ds, c, part, 54, 5, sh, out, ds.cam_ch_ptr);
   if (t < 81) {
     const int i = t % 9, j = t / 9;
     const int a = i < j ? i : j, b = i < j ? j : i;

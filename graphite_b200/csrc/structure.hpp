@@ -32,6 +32,7 @@ namespace gb {
 constexpr int TILE = 256;       // storage slots per tile = threads per CTA
 constexpr int SLOT_CAP = 192;   // camera accumulator rows per super-tile (bounded by shared memory)
 constexpr int TILE_PTS = 128;   // max points per tile (bounds the per-tile W stage)
+constexpr int CAM_CHUNK = 1024; // observations per CTA of the camera-major kernels (k_prepare_cams)
 // Packed per-tile record (one TMA bulk copy): ometa[256] u32 | seg_tab[260] u32 | pt_tab[136] u16 | TileMeta |
 // (p0, np) of the next four tiles
 constexpr int REC_OMETA = 0;
@@ -73,6 +74,11 @@ struct HostStructure {
   std::vector<int32_t> row_out;                 // [nrows] super-tile row -> camera-major position in the partial buffers
   std::vector<int32_t> cta_st;                  // [ncta+1] super-tile ranges of the persistent CTAs (balanced by tiles)
   std::vector<int32_t> tile_cam;                // [Mstore] camera per storage slot (0 in padding)
+  // camera-major view (k_prepare_cams): the observations of camera c in ascending (point) order are entries
+  // [cm_ptr(c), cm_ptr(c+1)); they are cut into chunks of <= CAM_CHUNK, one CTA and one partial row each
+  std::vector<int32_t> cm_slot, cm_pt;          // [M] storage slot / point of the camera-major observation
+  std::vector<int32_t> ch_ptr;                  // [nchunks+1] chunk -> range of camera-major observations
+  std::vector<int32_t> cam_ch_ptr;              // [Nc+1] camera -> its contiguous chunk rows
   // per sorted observation (tests / host view): rank in tile order and camera segment count
   std::vector<uint8_t> rank;
   int32_t max_track = 0;
@@ -289,6 +295,28 @@ struct HostStructure {
     // partial buffers are camera-major: the rows of one camera are contiguous, in ascending super-tile order
     row_out.resize(nrows);
     for (int32_t i = 0; i < nrows; i++) row_out[cam_row_list[i]] = i;
+    // ---- camera-major view: counting sort by camera (stable: ascending point order inside a camera) ---------
+    {
+      std::vector<int32_t> cptr((size_t)nc + 1, 0);
+      for (int64_t o = 0; o < m; o++) cptr[cam_idx[o] + 1]++;
+      for (int64_t c = 0; c < nc; c++) cptr[c + 1] += cptr[c];
+      cm_slot.resize(m); cm_pt.resize(m);
+      std::vector<int32_t> fillc(cptr.begin(), cptr.end() - 1);
+      for (int64_t o = 0; o < m; o++) {
+        const int32_t pos = fillc[cam_idx[o]]++;
+        cm_slot[pos] = slot_of_obs[o];
+        cm_pt[pos] = pt_idx[o];
+      }
+      ch_ptr.assign(1, 0);
+      cam_ch_ptr.assign((size_t)nc + 1, 0);
+      for (int64_t c = 0; c < nc; c++) {
+        const int32_t n = cptr[c + 1] - cptr[c];
+        const int32_t nch = (n + CAM_CHUNK - 1) / CAM_CHUNK;
+        for (int32_t k = 0; k < nch; k++) // near-equal chunks
+          ch_ptr.push_back(cptr[c] + (int32_t)(((int64_t)n * (k + 1)) / nch));
+        cam_ch_ptr[c + 1] = cam_ch_ptr[c] + nch;
+      }
+    }
     // persistent CTAs: contiguous super-tile ranges with near-equal tile counts
     {
       const int32_t ncta = std::min<int32_t>(nst, persistent_ctas);
@@ -309,6 +337,7 @@ struct HostStructure {
   int32_t nst() const { return (int32_t)st_tile.size() - 1; }
   int32_t nrows() const { return (int32_t)row_cam.size(); }
   int32_t ncta() const { return (int32_t)cta_st.size() - 1; }
+  int32_t nchunks() const { return (int32_t)ch_ptr.size() - 1; }
 
   // Upper block-CSC of the Hessian in the reference's order (hessian.hpp:59-84, 270-278; csc_utils.hpp:16-50).
   void hessian_structure(int64_t *colptr, int64_t *rowidx, int64_t *offsets) const {
