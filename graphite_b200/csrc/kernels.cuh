@@ -37,6 +37,12 @@ namespace gb {
 constexpr int CAM_STRIDE = 10; // padded camera row
 constexpr int NPLANES = 12;
 // dynamic shared memory of the super-tile kernels, in elements of T
+#ifndef J_EVICT_FIRST
+#define J_EVICT_FIRST 1
+#endif
+#ifndef LIN_MIN_BLOCKS
+#define LIN_MIN_BLOCKS 2
+#endif
 constexpr int LIN_STR = 19; // staging row stride of k_linearize (18 values; odd stride: conflict-free 64-bit rows)
 template <typename T> constexpr int smem_lin_bytes() { // staging, accumulator rows, tile record
   return (TILE * LIN_STR + SLOT_CAP * 18) * (int)sizeof(T) + 16 + REC_BYTES;
@@ -104,6 +110,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// the same with an L2 eviction-priority hint: the Jacobian stream (1 GB per pass, read once) is marked evict-first so
+// that the small vectors every pass re-reads (W, partial rows, camera vectors: ~70 MB) stay resident in the 126 MB L2
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
                : "memory");
 }
 // order generic-proxy accesses to shared memory before later async-proxy (TMA) writes to the same bytes
@@ -247,7 +266,7 @@ template <> __device__ __forceinline__ void load_camx<float>(const float *__rest
 //     ops/chi2.hpp:32, ops/hessian.hpp:418)
 // ---------------------------------------------------------------------------------------------
 template <typename T, typename S>
-__global__ void __launch_bounds__(TILE)
+__global__ void __launch_bounds__(TILE, LIN_MIN_BLOCKS)
 k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
             const typename V2<T>::type *__restrict__ obs, typename V2<S>::type *__restrict__ J,
             typename V2<T>::type *__restrict__ res, T *__restrict__ Cg, T *__restrict__ part /*[nrows][18]*/,
@@ -864,13 +883,21 @@ k_schur_product(DevStruct ds, const typename V2<S>::type *__restrict__ J, const 
   // super-tile boundaries, only the camera rows (xl) and the accumulators are switched there
   const int st_begin = ds.cta_st[blockIdx.x], st_end = ds.cta_st[blockIdx.x + 1];
   const int tile0 = ds.st_tile[st_begin], ntl = ds.st_tile[st_end] - tile0;
+#if J_EVICT_FIRST
+  const uint64_t pol = l2_policy_evict_first();
+#endif
 
   auto issue = [&](int tile, int s, int p0, int np) {
     unsigned char *base = smem + s * SM::STAGE_BYTES;
     const uint32_t wbytes = (uint32_t)(np * WST<T>::value * (int)sizeof(T));
     mbar_expect_tx(&bars[s], (uint32_t)(SM::J_BYTES + REC_BYTES) + wbytes);
+#if J_EVICT_FIRST
+    bulk_g2s_hint(base, J + (int64_t)tile * NPLANES * TILE, SM::J_BYTES, &bars[s], pol);
+    bulk_g2s_hint(base + SM::J_BYTES, ds.trec + (int64_t)tile * REC_BYTES, REC_BYTES, &bars[s], pol);
+#else
     bulk_g2s(base, J + (int64_t)tile * NPLANES * TILE, SM::J_BYTES, &bars[s]);
     bulk_g2s(base + SM::J_BYTES, ds.trec + (int64_t)tile * REC_BYTES, REC_BYTES, &bars[s]);
+#endif
     bulk_g2s(base + SM::J_BYTES + REC_BYTES, W + (int64_t)p0 * WST<T>::value, wbytes, &bars[s]);
   };
 
