@@ -21,7 +21,7 @@ _NP = {"f32": np.float32, "f64": np.float64}
 SYMBOLS = [
     "gb_version", "gb_context_create", "gb_context_destroy", "gb_last_error", "gb_comm_unique_id", "gb_comm_init",
     "gb_problem_create", "gb_problem_destroy", "gb_problem_info", "gb_set_observations", "gb_set_vertices",
-    "gb_get_vertices", "gb_hessian_structure", "gb_linearize", "gb_compute_cost", "gb_get_gradient", "gb_get_scales",
+    "gb_get_vertices", "gb_set_loss", "gb_set_precision", "gb_hessian_structure", "gb_linearize", "gb_compute_cost", "gb_get_gradient", "gb_get_scales",
     "gb_get_residuals", "gb_get_jacobians", "gb_hessian_values", "gb_set_damping", "gb_solve", "gb_get_schur_rhs",
     "gb_get_schur_diagonal", "gb_schur_multiply", "gb_try_step", "gb_revert_step", "gb_lm", "gb_kernel_launches",
     "gb_time_stage", "gb_structure_create", "gb_structure_destroy", "gb_structure_info", "gb_structure_array",
@@ -91,6 +91,8 @@ def load_library():
     L.gb_set_observations.argtypes = [vp, vp]
     L.gb_set_vertices.argtypes = [vp, vp, vp]
     L.gb_get_vertices.argtypes = [vp, vp, vp]
+    L.gb_set_loss.argtypes = [vp, C.c_int, C.c_double]
+    L.gb_set_precision.argtypes = [vp, vp]
     L.gb_hessian_structure.argtypes = [vp, vp, vp, vp]
     L.gb_linearize.argtypes = [vp, C.POINTER(C.c_double)]
     L.gb_compute_cost.argtypes = [vp, C.POINTER(C.c_double)]
@@ -204,6 +206,18 @@ class Problem:
         p = np.ascontiguousarray(pts, dtype=self.T)
         assert c.shape == (self.n_cams, 9) and p.shape == (self.n_pts, 3)
         self.ctx.check(self.L.gb_set_vertices(self.h, _ptr(c), _ptr(p)))
+
+    def set_loss(self, loss: str = "default", delta: float = 0.0):
+        self.ctx.check(self.L.gb_set_loss(self.h, {"default": 0, "huber": 1}[loss], float(delta)))
+
+    def set_precision(self, precision):
+        """[n_obs][2][2] SPD matrices in the caller's factor order, or None for the identity."""
+        if precision is None:
+            self.ctx.check(self.L.gb_set_precision(self.h, None))
+            return
+        P = np.ascontiguousarray(precision, dtype=self.T).reshape(-1)
+        assert P.size == 4 * self.n_obs
+        self.ctx.check(self.L.gb_set_precision(self.h, _ptr(P)))
 
     def set_vertices_raw(self, cams_ptr: int, pts_ptr: int):
         """Host pointers (e.g. pinned torch tensors) of dtype T, shapes [n_cams,9] / [n_pts,3]."""

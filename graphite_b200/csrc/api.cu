@@ -92,6 +92,8 @@ struct ProblemBase {
   virtual int init() = 0;
   virtual int set_observations(const void *) = 0;
   virtual int set_vertices(const void *, const void *) = 0;
+  virtual int set_loss(int, double) = 0;
+  virtual int set_precision(const void *) = 0;
   virtual int get_vertices(void *, void *) = 0;
   virtual int linearize(double *) = 0;
   virtual int compute_cost(double *) = 0;
@@ -157,6 +159,9 @@ template <typename T, typename S> struct Problem : ProblemBase {
   double last_chi2 = 0.0;
   bool profiling = false;
   std::vector<cudaEvent_t> prof_ev; // pairs around k_schur_tiles<MODE 0>, one pair per PCG iteration
+  // loss and per-factor precision matrices (whitening in k_linearize / k_cost_tiles)
+  T *Pu = nullptr;
+  Robust rb{nullptr, 0, 0.0};
   // multi-GPU exchange over peer memory (p2p.cuh); NCCL is the bootstrap and the fallback
   P2P pp{};
   bool p2p_on = false;
@@ -424,6 +429,37 @@ template <typename T, typename S> struct Problem : ProblemBase {
     linearized = prepared = solved = stepped = false;
     return GB_OK;
   }
+  // Replaces the loss argument of add_factor (factor.hpp:373-412, loss.hpp): one loss for all factors.
+  int set_loss(int kind, double delta) override {
+    if (kind != 0 && kind != 1) return ctx->fail(GB_ERR_INVALID, "unknown loss %d", kind);
+    if (kind == 1 && !(delta > 0.0)) return ctx->fail(GB_ERR_INVALID, "Huber delta must be positive");
+    rb.loss_kind = kind;
+    rb.delta = kind ? delta : 0.0;
+    linearized = prepared = solved = solved_full = stepped = false;
+    return GB_OK;
+  }
+  // Replaces the precision_matrix argument of add_factor: [n_obs][4] row-major 2x2 in the caller's factor order
+  // (element type T), symmetric positive definite; NULL restores the identity.  Factored P = U^T U here.
+  int set_precision(const void *Pin) override {
+    linearized = prepared = solved = solved_full = stepped = false;
+    if (!Pin) { rb.Pu = nullptr; return GB_OK; }
+    const T *P = (const T *)Pin;
+    std::vector<T> hu(3 * (size_t)hs.Mstore, T(0));
+    for (int64_t spos = 0; spos < hs.M; spos++) {
+      const int64_t u = hs.identity_perm ? spos : hs.perm[spos], sl = hs.slot_of_obs[spos];
+      const double p00 = (double)P[4 * u], p01 = (double)P[4 * u + 1], p10 = (double)P[4 * u + 2], p11 = (double)P[4 * u + 3];
+      const double tol = 1e-6 * std::max(std::fabs(p00), std::fabs(p11));
+      if (!(p00 > 0.0) || std::fabs(p01 - p10) > tol || !(p00 * p11 - p01 * p10 > 0.0))
+        return ctx->fail(GB_ERR_INVALID, "precision matrix of factor %ld is not symmetric positive definite", (long)u);
+      const double u00 = std::sqrt(p00), u01 = p01 / u00, u11 = std::sqrt(p11 - u01 * u01);
+      hu[3 * sl] = (T)u00; hu[3 * sl + 1] = (T)u01; hu[3 * sl + 2] = (T)u11;
+    }
+    if (!Pu) GB_TRY(dalloc(Pu, 3 * (size_t)hs.Mstore));
+    GB_CUDA(ctx, cudaMemcpyAsync(Pu, hu.data(), hu.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    rb.Pu = Pu;
+    return GB_OK;
+  }
   int get_vertices(void *c, void *p) override {
     if (!have_vertices) return ctx->fail(GB_ERR_INVALID, "gb_get_vertices before gb_set_vertices");
     if (c)
@@ -444,7 +480,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     cudaStream_t st = ctx->stream;
     k_cam_precompute<T><<<(ts.Nc + 127) / 128, 128, 0, st>>>(ts.Nc, cams, camx);
     GB_LAUNCH(ctx);
-    k_linearize<T, S><<<ts.nst, TILE, smem_lin_bytes<T>(), st>>>(ts, camx, pts, obs, J, res, Cg, part18, cost_part);
+    k_linearize<T, S><<<ts.nst, TILE, smem_lin_bytes<T>(), st>>>(ts, camx, pts, obs, J, res, Cg, part18, cost_part, rb);
     GB_LAUNCH(ctx);
     const bool multi = ctx->nranks > 1;
     k_cam_reduce_lin<T><<<ts.Nc, 288, 0, st>>>(ts, part18, diagB, gc, multi ? 0 : 1, scale_on ? 1 : 0, scale, b);
@@ -749,7 +785,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     cudaStream_t st = ctx->stream;
     k_cam_precompute<T><<<(ts.Nc + 127) / 128, 128, 0, st>>>(ts.Nc, cams, camx);
     GB_LAUNCH(ctx);
-    k_cost_tiles<T><<<ts.ntiles, TILE, 0, st>>>(ts, camx, pts, obs, cost_part);
+    k_cost_tiles<T><<<ts.ntiles, TILE, 0, st>>>(ts, camx, pts, obs, cost_part, rb);
     GB_LAUNCH(ctx);
     k_sum_partials<<<1, 1024, 0, st>>>(cost_part, ts.ntiles, scalars, 0);
     GB_LAUNCH(ctx);
@@ -1294,6 +1330,8 @@ int gb_problem_info(const gb_problem *p, int64_t info[12]) {
 int gb_set_observations(gb_problem *p, const void *o) { GB_P(p); if (!o) return GB_ERR_INVALID; return p->impl->set_observations(o); }
 int gb_set_vertices(gb_problem *p, const void *c, const void *q) { GB_P(p); if (!c || !q) return GB_ERR_INVALID; return p->impl->set_vertices(c, q); }
 int gb_get_vertices(gb_problem *p, void *c, void *q) { GB_P(p); return p->impl->get_vertices(c, q); }
+int gb_set_loss(gb_problem *p, int kind, double delta) { GB_P(p); return p->impl->set_loss(kind, delta); }
+int gb_set_precision(gb_problem *p, const void *P) { GB_P(p); return p->impl->set_precision(P); }
 int gb_hessian_structure(const gb_problem *p, int64_t *cp, int64_t *ri, int64_t *off) {
   if (!p || !cp || !ri || !off) return GB_ERR_INVALID;
   p->impl->hs.hessian_structure(cp, ri, off);

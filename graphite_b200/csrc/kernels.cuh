@@ -260,6 +260,56 @@ template <> __device__ __forceinline__ void load_camx<float>(const float *__rest
 }
 
 // ---------------------------------------------------------------------------------------------
+// Loss and precision matrix of a factor (ops/chi2.hpp:9-44, loss.hpp:15-51, factor.hpp:397-405).
+//   chi2_f = loss(r^T P r), dL = loss'(r^T P r);  H += dL J^T P J,  b -= dL J^T P r  (ops/hessian.hpp:58-76,
+//   ops/linearize.hpp:277-302).
+// With P = U^T U (U upper triangular, factored on the host when the matrices are set) and w = sqrt(dL) the factor is
+// WHITENED once, where it is evaluated:  J' = w U J,  r' = w U r,  so that J'^T J' = dL J^T P J and J'^T r' = dL J^T P r
+// and every later kernel (assembly, Schur products, back-substitution) works on J' unchanged.
+// Pu = nullptr and loss_kind = 0 (DefaultLoss, P = I) take the original code path.
+// ---------------------------------------------------------------------------------------------
+struct Robust {
+  const void *Pu;  // [Mstore][3] of T: u00, u01, u11 per storage slot, or nullptr
+  int loss_kind;   // 0 DefaultLoss, 1 HuberLoss
+  double delta;
+};
+// returns chi2_f; whitens r (2), Jc (18), Jp (6) in place
+template <typename T, typename S>
+__device__ __forceinline__ T whiten_factor(const Robust &rb, int64_t slot, T *r, T *Jc, T *Jp) {
+  T u00 = T(1), u01 = T(0), u11 = T(1);
+  if (rb.Pu) {
+    const T *u = reinterpret_cast<const T *>(rb.Pu) + 3 * slot;
+    u00 = u[0]; u01 = u[1]; u11 = u[2];
+  }
+  const T e0 = u00 * r[0] + u01 * r[1], e1 = u11 * r[1];
+  const T c = e0 * e0 + e1 * e1; // r^T P r
+  T chi = c, w = T(1);
+  const T delta = (T)rb.delta;
+  if (rb.loss_kind == 1 && c > delta * delta) {
+    const T sc = sqrt(c);
+    chi = T(2) * sc * delta - delta * delta;
+    w = sqrt((T)(S)(delta / sc)); // dL is kept in S precision by the reference (factor.hpp:166)
+  }
+  if (Jc) {
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+      const T a0 = Jc[2 * j], a1 = Jc[2 * j + 1];
+      Jc[2 * j] = w * (u00 * a0 + u01 * a1);
+      Jc[2 * j + 1] = w * (u11 * a1);
+    }
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const T a0 = Jp[2 * j], a1 = Jp[2 * j + 1];
+      Jp[2 * j] = w * (u00 * a0 + u01 * a1);
+      Jp[2 * j + 1] = w * (u11 * a1);
+    }
+    r[0] = w * e0;
+    r[1] = w * e1;
+  }
+  return chi;
+}
+
+// ---------------------------------------------------------------------------------------------
 // K1: factor evaluation + point-side assembly + camera-side partials of diag(B) and g_c
 //     replaces compute_error_kernel / compute_jacobian_kernel / compute_chi2_kernel /
 //     compute_hessian_scalar_diagonal_kernel / compute_b_kernel (ops/error.hpp:252, ops/linearize.hpp:10,238,
@@ -270,7 +320,8 @@ __global__ void __launch_bounds__(TILE, LIN_MIN_BLOCKS)
 k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
             const typename V2<T>::type *__restrict__ obs, typename V2<S>::type *__restrict__ J,
             typename V2<T>::type *__restrict__ res, T *__restrict__ Cg, T *__restrict__ part /*[nrows][18]*/,
-            double *__restrict__ cost_part /*[ntiles]*/) {
+            double *__restrict__ cost_part /*[ntiles]*/, Robust rb) {
+  const bool robust = rb.Pu != nullptr || rb.loss_kind != 0;
   // ncu of the first version (tables read from global memory inside the reduction loops, two 9-wide camera passes):
   // 41 % of the stall samples were long-scoreboard waits in those loops, 61 % of all samples sat in the loops.
   // Here the tile's packed record (segment and point tables) is copied to shared memory while the camera model is
@@ -306,13 +357,14 @@ k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
       ob[0] = ov.x;
       ob[1] = ov.y;
       bal_residual_jacobian_pre<T>(cx, X, ob, B);
+      res[slot] = V2<T>::make(B.r[0], B.r[1]); // the residual itself (export); the assembly below uses the whitened one
+      if (robust) cost = (double)whiten_factor<T, S>(rb, slot, B.r, B.Jc, B.Jp);
+      else cost = (double)(B.r[0] * B.r[0] + B.r[1] * B.r[1]);
       typename V2<S>::type *base = J + ((int64_t)tile * NPLANES) * TILE + t;
 #pragma unroll
       for (int j = 0; j < 9; j++) base[j * TILE] = V2<S>::make((S)B.Jc[2 * j], (S)B.Jc[2 * j + 1]);
 #pragma unroll
       for (int j = 0; j < 3; j++) base[(9 + j) * TILE] = V2<S>::make((S)B.Jp[2 * j], (S)B.Jp[2 * j + 1]);
-      res[slot] = V2<T>::make(B.r[0], B.r[1]);
-      cost = (double)(B.r[0] * B.r[0] + B.r[1] * B.r[1]);
       // what is stored is what every later kernel reads: keep the assembly consistent with S
 #pragma unroll
       for (int j = 0; j < 18; j++) B.Jc[j] = (T)(S)B.Jc[j];
@@ -1436,6 +1488,13 @@ k_pcg_iterate(DevStruct ds, PcgState<T> *st /*in: st[0], out: st[2]*/, T tol, T 
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
   __shared__ T sh[32];
   __shared__ T wpart[PIT_WARPS];
+#ifdef PIT_TIMING
+  unsigned long long tm_[8];
+  tm_[0] = global_timer_ns();
+#define PIT_STAMP(i) tm_[i] = global_timer_ns()
+#else
+#define PIT_STAMP(i)
+#endif
   PcgState<T> s = *st;
   const bool leader = blockIdx.x == 0 && threadIdx.x == 0;
   // stopped earlier, or rz == 0 (pcg_schur.hpp:109-111): uniform across the grid and across ranks
@@ -1531,10 +1590,13 @@ k_pcg_iterate(DevStruct ds, PcgState<T> *st /*in: st[0], out: st[2]*/, T tol, T 
       dot_w += finish(c, raw);
     }
   }
+  PIT_STAMP(1);
   cta_publish<T>(dot_w, wpart, cta_part);
   __threadfence();
   grid.sync();
+  PIT_STAMP(2);
   const T denom = grid_total<T>(cta_part, G, sh);
+  PIT_STAMP(3);
   if (denom == T(0) || isnan(denom)) { // pcg_schur.hpp:120-122
     if (leader) { s.done = 1; s.reason = 4; s.denom = denom; st[2] = s; *done_flag = 1; }
     return;
@@ -1564,11 +1626,14 @@ k_pcg_iterate(DevStruct ds, PcgState<T> *st /*in: st[0], out: st[2]*/, T tol, T 
     if (own) z[i] = acc;
     rz_w += sum9<T>(own ? rn * acc : T(0));
   }
+  PIT_STAMP(4);
   __syncthreads(); // wpart is reused
   cta_publish<T>(rz_w, wpart, cta_part + G);
   __threadfence();
   grid.sync();
+  PIT_STAMP(5);
   const T rzn = grid_total<T>(cta_part + G, G, sh);
+  PIT_STAMP(6);
 
   // ---- phase 3: rejection / convergence tests, beta, p, xs = D p (pcg_schur.hpp:144-163) ----
   s.iter += 1;
@@ -1597,6 +1662,12 @@ k_pcg_iterate(DevStruct ds, PcgState<T> *st /*in: st[0], out: st[2]*/, T tol, T 
     st[2] = s;
     if (s.done) *done_flag = 1;
   }
+#ifdef PIT_TIMING
+  PIT_STAMP(7);
+  if (leader && s.iter == 3)
+    printf("pit ns: gather %llu sync1 %llu total1 %llu phase2 %llu sync2 %llu total2 %llu phase3 %llu | whole %llu\n", tm_[1] - tm_[0],
+           tm_[2] - tm_[1], tm_[3] - tm_[2], tm_[4] - tm_[3], tm_[5] - tm_[4], tm_[6] - tm_[5], tm_[7] - tm_[6], tm_[7] - tm_[0]);
+#endif
 }
 
 // xs = D_c x (for the back-substitution) ; also camera update + rho partial (ops/update.hpp:9-31,
@@ -1629,7 +1700,7 @@ __global__ void k_cam_step(int n, const T *__restrict__ x, const T *__restrict__
 template <typename T>
 __global__ void __launch_bounds__(TILE)
 k_cost_tiles(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
-             const typename V2<T>::type *__restrict__ obs, double *__restrict__ cost_part /*[ntiles]*/) {
+             const typename V2<T>::type *__restrict__ obs, double *__restrict__ cost_part /*[ntiles]*/, Robust rb) {
   __shared__ double shd[32];
   const int tile = blockIdx.x, t = threadIdx.x;
   const TileMeta tm = ds.tmeta[tile];
@@ -1646,7 +1717,8 @@ k_cost_tiles(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts
     ob[0] = ov.x;
     ob[1] = ov.y;
     bal_residual_pre<T>(cx, X, ob, r);
-    cost = (double)(r[0] * r[0] + r[1] * r[1]);
+    if (rb.Pu != nullptr || rb.loss_kind != 0) cost = (double)whiten_factor<T, T>(rb, slot, r, (T *)nullptr, (T *)nullptr);
+    else cost = (double)(r[0] * r[0] + r[1] * r[1]);
   }
   const double tot = block_sum<double>(cost, shd);
   if (t == 0) cost_part[tile] = tot;

@@ -187,6 +187,20 @@ def schur_fixture() -> BALProblem:
     return BALProblem(cam_idx, pt_idx, np.zeros((6, 2)), cams, pts, "schur-fixture")
 
 
+def precision_matrices(n_obs: int) -> np.ndarray:
+    """Deterministic SPD 2x2 precision matrix per observation, [n_obs][2][2], for the weighted / robust test cases.
+
+    Integer arithmetic plus one correctly rounded division per entry, so a C++ restatement of the same
+    formula (the driver that generated tests/golden/*__weights.json) produces bit-identical values."""
+    i = np.arange(n_obs, dtype=np.int64)
+    a = 1.0 + ((i * 7) % 11).astype(np.float64) / 22.0
+    b = 0.8 + ((i * 5) % 13).astype(np.float64) / 26.0
+    c = (((i * 3) % 7).astype(np.float64) - 3.0) / 20.0
+    P = np.empty((n_obs, 2, 2))
+    P[:, 0, 0], P[:, 0, 1], P[:, 1, 0], P[:, 1, 1] = a, c, c, b
+    return P
+
+
 def write_gbal(prob: BALProblem, path: str) -> None:
     """Binary container read by the reference driver (int64 header, int32 ids, f64 payload)."""
     with open(path, "wb") as fh:

@@ -103,6 +103,15 @@ int gb_problem_info(const gb_problem *p, int64_t info[12]);
  * (examples/bal.cu:118-125), pts [n_pts][3], obs [n_obs][2]. */
 int gb_set_observations(gb_problem *p, const void *obs_host);
 int gb_set_vertices(gb_problem *p, const void *cams_host, const void *pts_host);
+/* Replaces the loss_func and precision_matrix arguments of add_factor (factor.hpp:373-412; loss.hpp:15-51):
+ *   chi2_f = loss(r^T P r), H += loss' J^T P J, b -= loss' J^T P r (ops/chi2.hpp:9-44, ops/hessian.hpp:58-76).
+ * One loss for all factors: GB_LOSS_DEFAULT (identity) or GB_LOSS_HUBER(delta).  precision_host: [n_obs][4] row-major
+ * 2x2 per factor in the caller's factor order (element type T), symmetric positive definite; NULL = identity
+ * (the reference default, factor.hpp:397-405).  With either set, gb_get_jacobians returns the whitened Jacobians
+ * sqrt(loss') U J (P = U^T U) that the library stores. */
+typedef enum { GB_LOSS_DEFAULT = 0, GB_LOSS_HUBER = 1 } gb_loss;
+int gb_set_loss(gb_problem *p, int loss, double delta);
+int gb_set_precision(gb_problem *p, const void *precision_host);
 /* Replaces the in-place update through user pointers (docs/markdown/memory.md:4-13): writes back. */
 int gb_get_vertices(gb_problem *p, void *cams_host, void *pts_host);
 

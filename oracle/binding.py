@@ -45,6 +45,7 @@ def lib():
         L.orc_set_threads.argtypes = [C.c_void_p, C.c_int]
         L.orc_get_params.argtypes = [C.c_void_p, dp, dp]
         L.orc_set_params.argtypes = [C.c_void_p, dp, dp]
+        L.orc_set_robust.argtypes = [C.c_void_p, C.c_int, C.c_double, dp]
         L.orc_residuals.restype = C.c_double
         L.orc_residuals.argtypes = [C.c_void_p, dp]
         L.orc_jacobians.argtypes = [C.c_void_p, dp, dp]
@@ -106,6 +107,12 @@ class Oracle:
     def set_params(self, cams, pts):
         c = np.ascontiguousarray(cams, dtype=np.float64); p = np.ascontiguousarray(pts, dtype=np.float64)
         self.L.orc_set_params(self.h, _dp(c), _dp(p))
+
+    def set_robust(self, loss="default", delta=0.0, precision=None):
+        """Loss (loss.hpp) and per-factor 2x2 precision matrices [m][2][2] (factor.hpp:373-412)."""
+        kind = {"default": 0, "huber": 1}[loss]
+        P = None if precision is None else np.ascontiguousarray(precision, dtype=np.float64).reshape(-1)
+        lib().orc_set_robust(self.h, kind, float(delta), _dp(P) if P is not None else None)
 
     def residuals(self):
         r = np.empty((self.m, 2))

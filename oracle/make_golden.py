@@ -43,13 +43,19 @@ def parse_table(text: str):
     return rows
 
 
-def run_case(name, prob, solver, precision, iterations, dump=False, lam=1e-4, timeout=3000):
+def run_case(name, prob, solver, precision, iterations, dump=False, lam=1e-4, timeout=3000, huber=0.0, weights=False):
     os.makedirs(OUT, exist_ok=True)
     gbal = os.path.join(OUT, f"{name}.gbal")
     if not os.path.exists(gbal):
         synthetic.write_gbal(prob, gbal)
     tag = f"{name}__{solver}__{precision}"
     cmd = [REF, gbal, "--solver", solver, "--precision", precision, "--iterations", str(iterations), "--lambda", repr(lam)]
+    if huber > 0:  # HuberLoss(delta) on every factor (loss.hpp:27-51)
+        tag += f"__huber{huber:g}"
+        cmd += ["--huber", repr(huber)]
+    if weights:    # per-factor precision matrices, synthetic.precision_matrices
+        tag += "__weights"
+        cmd += ["--weights"]
     prefix = os.path.join(OUT, tag)
     if dump:
         cmd += ["--dump", prefix]
@@ -62,7 +68,7 @@ def run_case(name, prob, solver, precision, iterations, dump=False, lam=1e-4, ti
     dchi = [l for l in res.stdout.splitlines() if l.startswith("DUMP chi2")]
     rec = {
         "case": name, "shape": list(prob.shape()), "seed": 0, "solver": solver, "precision": precision,
-        "lambda": lam, "pcg_iterations": 10, "pcg_tolerance": 1.0, "rejection_ratio": 5.0,
+        "lambda": lam, "huber": huber, "weights": weights, "pcg_iterations": 10, "pcg_tolerance": 1.0, "rejection_ratio": 5.0,
         "iterations": iterations, "returncode": res.returncode,
         "table_columns": ["iteration", "initial_chi2", "current_chi2", "lambda", "iter_seconds", "total_seconds"],
         "table": rows,
@@ -126,6 +132,20 @@ def main(which):
         run_case("trafalgar-257", p, "pcg-schur", "FP64-FP64", 50)
         run_case("trafalgar-257", p, "pcg-schur", "FP32-FP32", 50)
         run_case("trafalgar-257", p, "pcg", "FP64-FP32", 50)
+    if "robust" in which:
+        p = synthetic.make_named("ladybug-49")
+        run_case("ladybug-49", p, "pcg-schur", "FP64-FP64", 50, dump=True, huber=20.0, weights=True)
+        run_case("ladybug-49", p, "pcg-schur", "FP64-FP64", 50, huber=20.0)
+        run_case("ladybug-49", p, "pcg-schur", "FP64-FP64", 50, weights=True)
+        run_case("ladybug-49", p, "pcg", "FP64-FP64", 50, huber=20.0, weights=True)
+        p = synthetic.make_named("trafalgar-257")
+        run_case("trafalgar-257", p, "pcg-schur", "FP64-FP64", 50, huber=20.0, weights=True)
+    if "robust2" in which:  # the reference's own run-to-run spread on the robust cases (float atomics)
+        for name, kw in [("ladybug-49", dict(huber=20.0, weights=True)), ("trafalgar-257", dict(huber=20.0, weights=True))]:
+            p = synthetic.make_named(name)
+            rec = run_case(name, p, "pcg-schur", "FP64-FP64", 50, **kw)
+            base = os.path.join(OUT, f"{name}__pcg-schur__FP64-FP64__huber20__weights")
+            os.replace(base + ".json", base + ".run2.json")
     if "dubrovnik" in which:
         p = synthetic.make_named("dubrovnik-356")
         second_run("dubrovnik-356", p)

@@ -49,6 +49,7 @@ struct Base {
   virtual void set_threads(int) = 0;
   virtual void get_params(double *, double *) = 0;
   virtual void set_params(const double *, const double *) = 0;
+  virtual void set_robust(int, double, const double *) = 0;
   virtual double residuals(double *) = 0;
   virtual void jacobians(double *, double *) = 0;
   virtual double linearize(double *, double *) = 0;
@@ -191,6 +192,11 @@ template <typename T> struct Impl : Base {
   std::vector<int64_t> pptr; // CSR by point over the (point,camera)-sorted observations
   std::vector<T> obs, cams, pts, cams_bak, pts_bak;
   std::vector<T> r, Jc, Jp; // J scaled after linearize (S == T)
+  // per-factor precision matrix P (row-major 2x2, identity by default: factor.hpp:397-405) and loss
+  // (loss.hpp:15-51: 0 = DefaultLoss, 1 = HuberLoss(delta)); dLv = loss'(r^T P r) of the last error evaluation
+  std::vector<T> Pm, dLv;
+  int loss_kind = 0;
+  T loss_delta = T(0);
   std::vector<T> scales, b;
   // Hessian blocks in the scaled space (undamped): B [nc][81], E [m][27], C [np][9], col-major blocks
   std::vector<T> Bk, Ek, Ck, Bd, Cd, Cinv;
@@ -212,6 +218,8 @@ template <typename T> struct Impl : Base {
     for (int64_t i = 0; i < m; i++) pptr[pi[i] + 1]++;
     for (int64_t i = 0; i < np; i++) pptr[i + 1] += pptr[i];
     r.resize(2 * m); Jc.resize(18 * m); Jp.resize(6 * m);
+    Pm.assign(4 * m, T(0)); dLv.assign(m, T(1));
+    for (int64_t f = 0; f < m; f++) Pm[4 * f] = Pm[4 * f + 3] = T(1);
     scales.resize(dimH); b.resize(dimH);
 #ifdef _OPENMP
     threads = omp_get_max_threads();
@@ -235,14 +243,42 @@ template <typename T> struct Impl : Base {
     for (int64_t i = 0; i < 3 * np; i++) pts[i] = (T)p[i];
   }
 
-  // ops/error.hpp:250-323 then ops/chi2.hpp:9-44 with P = I, DefaultLoss.
+  void set_robust(int kind, double delta, const double *P) override {
+    loss_kind = kind;
+    loss_delta = (T)delta;
+    for (int64_t f = 0; f < m; f++)
+      for (int i = 0; i < 4; i++) Pm[4 * f + i] = P ? (T)P[4 * f + i] : (i == 0 || i == 3 ? T(1) : T(0));
+  }
+  // a^T P b for 2-vectors, in the operation order of ops/hessian.hpp:58-72 / ops/product.hpp:270-281
+  static inline T pw(const T *a, const T *b, const T *P) {
+    T v = 0;
+    for (int i = 0; i < 2; i++) {
+      T pj = 0;
+      for (int j = 0; j < 2; j++) pj += P[i * 2 + j] * b[j];
+      v += a[i] * pj;
+    }
+    return v;
+  }
+  // loss.hpp:20-50
+  T loss_value(T x) const {
+    if (loss_kind == 0 || x <= loss_delta * loss_delta) return x;
+    return 2 * std::sqrt(x) * loss_delta - loss_delta * loss_delta;
+  }
+  T loss_derivative(T x) const {
+    if (loss_kind == 0 || x <= loss_delta * loss_delta) return T(1);
+    return loss_delta / std::sqrt(x);
+  }
+
+  // ops/error.hpp:250-323 then ops/chi2.hpp:9-44: chi2_f = loss(r^T P r), dL_f = loss'(r^T P r).
   T compute_error_chi2() {
     double total = 0; // thrust::reduce over T chi2_vec; accumulate wide here, cast below
     T tot_T = 0;
 #pragma omp parallel for num_threads(threads) schedule(static) reduction(+ : total)
     for (int64_t f = 0; f < m; f++) {
       residual(&cams[9 * ci[f]], &pts[3 * pi[f]], &obs[2 * f], &r[2 * f]);
-      total += (double)(r[2 * f] * r[2 * f] + r[2 * f + 1] * r[2 * f + 1]);
+      const T raw = pw(&r[2 * f], &r[2 * f], &Pm[4 * f]);
+      dLv[f] = loss_derivative(raw);
+      total += (double)loss_value(raw);
     }
     tot_T = (T)total;
     return tot_T;
@@ -261,6 +297,14 @@ template <typename T> struct Impl : Base {
     raw_jacobians();
     for (int64_t i = 0; i < 18 * m; i++) oc[i] = Jc[i];
     for (int64_t i = 0; i < 6 * m; i++) op[i] = Jp[i];
+  }
+
+  // x2 = dL P r (ops/linearize.hpp:277-291)
+  void weighted_residual(int64_t f, T *x2) const {
+    for (int i = 0; i < 2; i++) {
+      x2[i] = 0;
+      for (int j = 0; j < 2; j++) x2[i] += dLv[f] * Pm[4 * f + 2 * i + j] * r[2 * f + j];
+    }
   }
 
   // graph.hpp:236-290
@@ -284,7 +328,7 @@ template <typename T> struct Impl : Base {
       for (int64_t f = 0; f < m; f++) {
         const T *J = &Jc[18 * f];
         T *dd = d + 9 * ci[f];
-        for (int k = 0; k < 9; k++) dd[k] += J[2 * k] * J[2 * k] + J[2 * k + 1] * J[2 * k + 1];
+        for (int k = 0; k < 9; k++) dd[k] += pw(&J[2 * k], &J[2 * k], &Pm[4 * f]) * dLv[f];
       }
     }
     for (int t = 0; t < threads; t++)
@@ -294,7 +338,7 @@ template <typename T> struct Impl : Base {
       T acc[3] = {0, 0, 0};
       for (int64_t f = pptr[p]; f < pptr[p + 1]; f++) {
         const T *J = &Jp[6 * f];
-        for (int k = 0; k < 3; k++) acc[k] += J[2 * k] * J[2 * k] + J[2 * k + 1] * J[2 * k + 1];
+        for (int k = 0; k < 3; k++) acc[k] += pw(&J[2 * k], &J[2 * k], &Pm[4 * f]) * dLv[f];
       }
       for (int k = 0; k < 3; k++) diag[dimc + 3 * p + k] = acc[k];
     }
@@ -325,7 +369,9 @@ template <typename T> struct Impl : Base {
       for (int64_t f = 0; f < m; f++) {
         const T *J = &Jc[18 * f];
         T *dd = d + 9 * ci[f];
-        for (int k = 0; k < 9; k++) dd[k] -= J[2 * k] * r[2 * f] + J[2 * k + 1] * r[2 * f + 1];
+        T x2[2];
+        weighted_residual(f, x2);
+        for (int k = 0; k < 9; k++) dd[k] -= J[2 * k] * x2[0] + J[2 * k + 1] * x2[1];
       }
     }
     for (int t = 0; t < threads; t++)
@@ -335,7 +381,9 @@ template <typename T> struct Impl : Base {
       T acc[3] = {0, 0, 0};
       for (int64_t f = pptr[p]; f < pptr[p + 1]; f++) {
         const T *J = &Jp[6 * f];
-        for (int k = 0; k < 3; k++) acc[k] -= J[2 * k] * r[2 * f] + J[2 * k + 1] * r[2 * f + 1];
+        T x2[2];
+        weighted_residual(f, x2);
+        for (int k = 0; k < 3; k++) acc[k] -= J[2 * k] * x2[0] + J[2 * k + 1] * x2[1];
       }
       for (int k = 0; k < 3; k++) b[dimc + 3 * p + k] = acc[k];
     }
@@ -383,7 +431,7 @@ template <typename T> struct Impl : Base {
         const T *J = &Jc[18 * f];
         T *Bb = Bt + 81 * ci[f];
         for (int j = 0; j < 9; j++)
-          for (int i = 0; i < 9; i++) Bb[i + 9 * j] += J[2 * i] * J[2 * j] + J[2 * i + 1] * J[2 * j + 1];
+          for (int i = 0; i < 9; i++) Bb[i + 9 * j] += pw(&J[2 * i], &J[2 * j], &Pm[4 * f]) * dLv[f];
       }
     }
     for (int t = 0; t < threads; t++)
@@ -395,9 +443,9 @@ template <typename T> struct Impl : Base {
         const T *J = &Jc[18 * f], *Q = &Jp[6 * f];
         T *Eb = &Ek[27 * f];
         for (int j = 0; j < 3; j++)
-          for (int i = 0; i < 9; i++) Eb[i + 9 * j] = J[2 * i] * Q[2 * j] + J[2 * i + 1] * Q[2 * j + 1];
+          for (int i = 0; i < 9; i++) Eb[i + 9 * j] = pw(&J[2 * i], &Q[2 * j], &Pm[4 * f]) * dLv[f];
         for (int j = 0; j < 3; j++)
-          for (int i = 0; i < 3; i++) Cb[i + 3 * j] += Q[2 * i] * Q[2 * j] + Q[2 * i + 1] * Q[2 * j + 1];
+          for (int i = 0; i < 3; i++) Cb[i + 3 * j] += pw(&Q[2 * i], &Q[2 * j], &Pm[4 * f]) * dLv[f];
       }
     }
     // hessian.hpp:102-134 backup_diagonal
@@ -740,7 +788,7 @@ template <typename T> struct Impl : Base {
         for (int64_t f = 0; f < m; f++) {
           const T *J = &Jc[18 * f];
           T *dd = d + 9 * ci[f];
-          for (int k = 0; k < 9; k++) dd[k] += J[2 * k] * v1[2 * f] + J[2 * k + 1] * v1[2 * f + 1];
+          for (int k = 0; k < 9; k++) dd[k] += pw(&J[2 * k], &v1[2 * f], &Pm[4 * f]) * dLv[f]; // product.hpp:270-282
         }
       }
       for (int64_t i = 0; i < dimc; i++) { T a = 0; for (int t = 0; t < threads; t++) a += tl[t][i]; v2[i] = a; }
@@ -749,7 +797,7 @@ template <typename T> struct Impl : Base {
         T acc[3] = {0, 0, 0};
         for (int64_t f = pptr[p]; f < pptr[p + 1]; f++) {
           const T *Q = &Jp[6 * f];
-          for (int k = 0; k < 3; k++) acc[k] += Q[2 * k] * v1[2 * f] + Q[2 * k + 1] * v1[2 * f + 1];
+          for (int k = 0; k < 3; k++) acc[k] += pw(&Q[2 * k], &v1[2 * f], &Pm[4 * f]) * dLv[f];
         }
         for (int k = 0; k < 3; k++) v2[dimc + 3 * p + k] = acc[k];
       }
@@ -893,6 +941,7 @@ void orc_destroy(orc_problem *h) { if (h) { delete h->impl; delete h; } }
 void orc_set_threads(orc_problem *h, int t) { h->impl->set_threads(t); }
 void orc_get_params(orc_problem *h, double *c, double *p) { h->impl->get_params(c, p); }
 void orc_set_params(orc_problem *h, const double *c, const double *p) { h->impl->set_params(c, p); }
+void orc_set_robust(orc_problem *h, int loss_kind, double delta, const double *P) { h->impl->set_robust(loss_kind, delta, P); }
 double orc_residuals(orc_problem *h, double *r) { return h->impl->residuals(r); }
 void orc_jacobians(orc_problem *h, double *a, double *b) { h->impl->jacobians(a, b); }
 double orc_linearize(orc_problem *h, double *s, double *b) { return h->impl->linearize(s, b); }

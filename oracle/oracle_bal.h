@@ -40,6 +40,9 @@ void orc_set_threads(orc_problem *, int threads);
 /* Current parameters (as double, whatever T is). */
 void orc_get_params(orc_problem *, double *cams, double *pts);
 void orc_set_params(orc_problem *, const double *cams, const double *pts);
+/* Loss and per-factor precision matrices (factor.hpp:373-412, loss.hpp:15-51): loss_kind 0 = DefaultLoss,
+ * 1 = HuberLoss(delta); P: [m][4] row-major 2x2 per factor, NULL = identity. */
+void orc_set_robust(orc_problem *, int loss_kind, double delta, const double *P);
 
 /* ops/error.hpp:250-323 + examples/reprojection_error.cuh:61-99.  r: [m][2] (as double). Returns chi2. */
 double orc_residuals(orc_problem *, double *r);

@@ -105,12 +105,12 @@ __device__ static void bal_residual(const D *cam, const D *X, const Obs2<T> &obs
   error[1] = cam[6] * rd * py - static_cast<D>(obs.v[1]);
 }
 
-template <typename T, typename S> struct ReprojectionErrorTraits {
+template <typename T, typename S, typename LossT = DefaultLoss<T, 2>> struct ReprojectionErrorTraits {
   static constexpr size_t dimension = 2;
   using VertexDescriptors = std::tuple<CameraDescriptor<T, S>, PointDescriptor<T, S>>;
   using Observation = Obs2<T>;
   using Data = Empty;
-  using Loss = DefaultLoss<T, dimension>;
+  using Loss = LossT;
   using Differentiation = DifferentiationMode::Manual;
 
   template <typename D>
@@ -139,8 +139,8 @@ template <typename T, typename S> struct ReprojectionErrorTraits {
   }
 };
 
-template <typename T, typename S>
-using ReprojectionError = FactorDescriptor<T, S, ReprojectionErrorTraits<T, S>>;
+template <typename T, typename S, typename LossT = DefaultLoss<T, 2>>
+using ReprojectionError = FactorDescriptor<T, S, ReprojectionErrorTraits<T, S, LossT>>;
 
 } // namespace graphite
 
@@ -149,6 +149,8 @@ struct Args {
   double lambda = 1e-4, pcg_tol = 1.0, rej = 5.0;
   size_t iterations = 50, pcg_iter = 10;
   bool identity = false;
+  double huber = 0.0;    // > 0: HuberLoss(delta) on every factor (loss.hpp:27-51)
+  bool weights = false;  // per-factor precision matrices, the rational pattern of graphite_b200/synthetic.py:precision_matrices
 };
 
 struct Problem {
@@ -183,7 +185,8 @@ template <typename V> static void dump_vec(const std::string &path, const V &v) 
   fclose(f);
 }
 
-template <typename FP, typename SP> int run(const Args &a, const Problem &prob) {
+template <typename FP, typename SP, typename LossT = graphite::DefaultLoss<FP, 2>>
+int run(const Args &a, const Problem &prob, const LossT &loss = LossT()) {
   using namespace graphite;
   cudaSetDevice(0);
   Graph<FP, SP> graph;
@@ -197,13 +200,21 @@ template <typename FP, typename SP> int run(const Args &a, const Problem &prob) 
   auto camera_desc = CameraDescriptor<FP, SP>();
   camera_desc.reserve(prob.nc);
   graph.add_descriptor(&camera_desc);
-  auto r_desc = ReprojectionError<FP, SP>(&camera_desc, &point_desc);
+  auto r_desc = ReprojectionError<FP, SP, LossT>(&camera_desc, &point_desc);
   r_desc.reserve(prob.m);
   graph.add_descriptor(&r_desc);
 
   for (int64_t i = 0; i < prob.m; i++) {
     Obs2<FP> o{{(FP)prob.obs[2 * i], (FP)prob.obs[2 * i + 1]}};
-    r_desc.add_factor({(size_t)prob.cam_idx[i], (size_t)prob.pt_idx[i] + (size_t)prob.nc}, o);
+    if (a.weights) {
+      // exactly representable pattern (integer arithmetic + one correctly rounded division per entry), SPD
+      const SP pa = (SP)(1.0 + (double)((i * 7) % 11) / 22.0), pb = (SP)(0.8 + (double)((i * 5) % 13) / 26.0);
+      const SP pc = (SP)(((double)((i * 3) % 7) - 3.0) / 20.0);
+      const SP pm[4] = {pa, pc, pc, pb};
+      r_desc.add_factor({(size_t)prob.cam_idx[i], (size_t)prob.pt_idx[i] + (size_t)prob.nc}, o, pm, Empty{}, loss);
+    } else {
+      r_desc.add_factor({(size_t)prob.cam_idx[i], (size_t)prob.pt_idx[i] + (size_t)prob.nc}, o, nullptr, Empty{}, loss);
+    }
   }
   for (int64_t i = 0; i < prob.nc; i++) {
     for (int j = 0; j < 9; j++) cameras[i].v[j] = (FP)prob.cams[9 * i + j];
@@ -306,6 +317,8 @@ int main(int argc, char **argv) {
     else if (s == "--pcg_tolerance") a.pcg_tol = atof(next().c_str());
     else if (s == "--rejection_ratio") a.rej = atof(next().c_str());
     else if (s == "--identity_damping") a.identity = true;
+    else if (s == "--huber") a.huber = atof(next().c_str());
+    else if (s == "--weights") a.weights = true;
     else if (s == "--dump") a.dump = next();
     else a.file = s;
   }
@@ -313,6 +326,10 @@ int main(int argc, char **argv) {
   if (!load_problem(a.file, p)) { fprintf(stderr, "cannot read %s\n", a.file.c_str()); return 1; }
   printf("PROBLEM %ld %ld %ld solver=%s precision=%s\n", (long)p.nc, (long)p.np, (long)p.m,
          a.solver.c_str(), a.precision.c_str());
+  if (a.huber > 0.0) { // robust runs: FP64 only (one more instantiation of the whole reference stack)
+    if (a.precision != "FP64-FP64") { fprintf(stderr, "--huber is built for FP64-FP64 only\n"); return 2; }
+    return run<double, double, graphite::HuberLoss<double, 2>>(a, p, graphite::HuberLoss<double, 2>(a.huber));
+  }
   if (a.precision == "FP64-FP64") return run<double, double>(a, p);
   if (a.precision == "FP32-FP32") return run<float, float>(a, p);
   if (a.precision == "FP64-FP32") return run<double, float>(a, p);
