@@ -23,9 +23,9 @@ SYMBOLS = [
     "gb_problem_create", "gb_problem_destroy", "gb_problem_info", "gb_set_observations", "gb_set_vertices",
     "gb_get_vertices", "gb_set_loss", "gb_set_precision", "gb_hessian_structure", "gb_linearize", "gb_compute_cost", "gb_get_gradient", "gb_get_scales",
     "gb_get_residuals", "gb_get_jacobians", "gb_hessian_values", "gb_set_damping", "gb_solve", "gb_get_schur_rhs",
-    "gb_get_schur_diagonal", "gb_schur_multiply", "gb_try_step", "gb_revert_step", "gb_lm", "gb_kernel_launches",
+    "gb_get_schur_diagonal", "gb_schur_multiply", "gb_schur_structure", "gb_schur_values", "gb_try_step", "gb_revert_step", "gb_lm", "gb_kernel_launches",
     "gb_time_stage", "gb_structure_create", "gb_structure_destroy", "gb_structure_info", "gb_structure_array",
-    "gb_structure_hessian",
+    "gb_structure_hessian", "gb_structure_schur",
 ]
 
 
@@ -103,6 +103,8 @@ def load_library():
     L.gb_set_damping.argtypes = [vp, C.c_double, C.c_int]
     L.gb_solve.argtypes = [vp, C.POINTER(PcgOptions), vp, C.POINTER(SolveInfo)]
     L.gb_schur_multiply.argtypes = [vp, vp, vp]
+    L.gb_schur_structure.argtypes = [vp, vp, vp, C.POINTER(C.c_int64)]
+    L.gb_schur_values.argtypes = [vp, vp]
     L.gb_try_step.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.gb_revert_step.argtypes = [vp]
     L.gb_lm.argtypes = [vp, C.POINTER(LMOptions), C.POINTER(LMResult), vp]
@@ -114,6 +116,7 @@ def load_library():
     L.gb_structure_info.argtypes = [vp, C.POINTER(C.c_int64)]
     L.gb_structure_array.argtypes = [vp, C.c_int, vp, C.POINTER(C.c_int64)]
     L.gb_structure_hessian.argtypes = [vp, vp, vp, vp]
+    L.gb_structure_schur.argtypes = [vp, vp, vp, C.POINTER(C.c_int64)]
     _lib = L
     return L
 
@@ -302,6 +305,22 @@ class Problem:
         self.ctx.check(self.L.gb_schur_multiply(self.h, _ptr(xx), _ptr(y)))
         return y
 
+    def schur_structure(self):
+        """Upper block-CSC of S: (colptr [n_cams+1], rowidx [nnz])."""
+        n = C.c_int64()
+        self.ctx.check(self.L.gb_schur_structure(self.h, None, None, C.byref(n)))
+        cp = np.empty(self.n_cams + 1, dtype=np.int64)
+        ri = np.empty(n.value, dtype=np.int64)
+        self.ctx.check(self.L.gb_schur_structure(self.h, _ptr(cp), _ptr(ri), C.byref(n)))
+        return cp, ri
+
+    def schur_values(self):
+        """Explicit S at the current damping: [nnz][9][9] blocks (row, column) in structure order."""
+        cp, ri = self.schur_structure()
+        v = np.empty(len(ri) * 81, dtype=self.T)
+        self.ctx.check(self.L.gb_schur_values(self.h, _ptr(v)))
+        return v.reshape(len(ri), 9, 9).transpose(0, 2, 1)
+
     def try_step(self):
         a, b = C.c_double(), C.c_double()
         self.ctx.check(self.L.gb_try_step(self.h, C.byref(a), C.byref(b)))
@@ -372,6 +391,11 @@ def host_structure(cam_idx, pt_idx, n_cams: int, n_pts: int, tile_size: int = 0,
         cp = np.empty(nblk + 1, dtype=np.int64); ri = np.empty(nnz, dtype=np.int64); off = np.empty(nnz, dtype=np.int64)
         L.gb_structure_hessian(h, _ptr(cp), _ptr(ri), _ptr(off))
         out["hessian"] = (cp, ri, off)
+        n = C.c_int64()
+        L.gb_structure_schur(h, None, None, C.byref(n))
+        scp = np.empty(int(n_cams) + 1, dtype=np.int64); sri = np.empty(n.value, dtype=np.int64)
+        L.gb_structure_schur(h, _ptr(scp), _ptr(sri), C.byref(n))
+        out["schur"] = (scp, sri)
         return out
     finally:
         L.gb_structure_destroy(h)

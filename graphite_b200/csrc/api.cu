@@ -107,6 +107,8 @@ struct ProblemBase {
   virtual int get_schur_rhs(void *) = 0;
   virtual int get_schur_diagonal(void *) = 0;
   virtual int schur_multiply(const void *, void *) = 0;
+  virtual int schur_structure(int64_t *, int64_t *, int64_t *) = 0;
+  virtual int schur_values(void *) = 0;
   virtual int try_step(double *, double *) = 0;
   virtual int revert_step() = 0;
   virtual int lm(const gb_lm_options *, gb_lm_result *, double *) = 0;
@@ -952,6 +954,41 @@ template <typename T, typename S> struct Problem : ProblemBase {
     solved = false; // xs was overwritten
     return GB_OK;
   }
+  // ---- explicit Schur complement: structure (host, cached) and values (export path) -------------------------------
+  std::vector<int64_t> s_colptr;
+  std::vector<int32_t> s_rowidx;
+  int schur_structure(int64_t *colptr, int64_t *rowidx, int64_t *nnz) override {
+    if (s_colptr.empty()) hs.schur_structure(s_colptr, s_rowidx);
+    if (nnz) *nnz = (int64_t)s_rowidx.size();
+    if (colptr) std::copy(s_colptr.begin(), s_colptr.end(), colptr);
+    if (rowidx) for (size_t i = 0; i < s_rowidx.size(); i++) rowidx[i] = s_rowidx[i];
+    return GB_OK;
+  }
+  int schur_values(void *out) override {
+    GB_TRY(require(linearized, "gb_schur_values before gb_linearize"));
+    GB_TRY(require(ctx->nranks == 1, "gb_schur_values is single-rank only"));
+    if (!prepared) GB_TRY(enqueue_prepare());
+    int64_t nnz = 0;
+    GB_TRY(schur_structure(nullptr, nullptr, &nnz));
+    cudaStream_t st = ctx->stream;
+    int64_t *d_cp = nullptr;
+    int32_t *d_ri = nullptr;
+    T *vals = nullptr;
+    GB_CUDA(ctx, cudaMalloc((void **)&d_cp, s_colptr.size() * sizeof(int64_t)));
+    GB_CUDA(ctx, cudaMalloc((void **)&d_ri, s_rowidx.size() * sizeof(int32_t)));
+    GB_CUDA(ctx, cudaMalloc((void **)&vals, (size_t)nnz * 81 * sizeof(T)));
+    GB_CUDA(ctx, cudaMemcpyAsync(d_cp, s_colptr.data(), s_colptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    GB_CUDA(ctx, cudaMemcpyAsync(d_ri, s_rowidx.data(), s_rowidx.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    GB_CUDA(ctx, cudaMemsetAsync(vals, 0, (size_t)nnz * 81 * sizeof(T), st));
+    k_schur_explicit<T, S><<<(ts.Np + 7) / 8, 256, 0, st>>>(ts, J, W, scale, d_cp, d_ri, vals);
+    GB_LAUNCH(ctx);
+    k_schur_explicit_diag<T><<<(ts.Nc * 81 + 255) / 256, 256, 0, st>>>(ts.Nc, Sdiag, d_cp, vals);
+    GB_LAUNCH(ctx);
+    int rc = launch_check();
+    if (rc == GB_OK) rc = d2h(out, vals, (size_t)nnz * 81 * sizeof(T));
+    cudaFree(d_cp); cudaFree(d_ri); cudaFree(vals);
+    return rc;
+  }
   int try_step(double *new_chi2, double *rho_den) override {
     GB_TRY(require(solved || solved_full, "gb_try_step before gb_solve"));
     if (solved_full) GB_TRY(enqueue_step_full(true));
@@ -1310,6 +1347,16 @@ int gb_structure_array(const gb_structure *s, int which, void *out, int64_t *cou
   }
   return GB_OK;
 }
+int gb_structure_schur(const gb_structure *s, int64_t *cp, int64_t *ri, int64_t *nnz) {
+  if (!s) return GB_ERR_INVALID;
+  std::vector<int64_t> colptr;
+  std::vector<int32_t> rowidx;
+  s->hs.schur_structure(colptr, rowidx);
+  if (nnz) *nnz = (int64_t)rowidx.size();
+  if (cp) std::copy(colptr.begin(), colptr.end(), cp);
+  if (ri) for (size_t i = 0; i < rowidx.size(); i++) ri[i] = rowidx[i];
+  return GB_OK;
+}
 int gb_structure_hessian(const gb_structure *s, int64_t *cp, int64_t *ri, int64_t *off) {
   if (!s || !cp || !ri || !off) return GB_ERR_INVALID;
   s->hs.hessian_structure(cp, ri, off);
@@ -1349,6 +1396,8 @@ int gb_solve(gb_problem *p, const gb_pcg_options *o, void *d, gb_solve_info *i) 
 int gb_get_schur_rhs(gb_problem *p, void *b) { GB_P(p); return p->impl->get_schur_rhs(b); }
 int gb_get_schur_diagonal(gb_problem *p, void *b) { GB_P(p); return p->impl->get_schur_diagonal(b); }
 int gb_schur_multiply(gb_problem *p, const void *x, void *y) { GB_P(p); return p->impl->schur_multiply(x, y); }
+int gb_schur_structure(gb_problem *p, int64_t *cp, int64_t *ri, int64_t *nnz) { GB_P(p); return p->impl->schur_structure(cp, ri, nnz); }
+int gb_schur_values(gb_problem *p, void *v) { GB_P(p); if (!v) return GB_ERR_INVALID; return p->impl->schur_values(v); }
 int gb_try_step(gb_problem *p, double *c, double *r) { GB_P(p); return p->impl->try_step(c, r); }
 int gb_revert_step(gb_problem *p) { GB_P(p); return p->impl->revert_step(); }
 int gb_lm(gb_problem *p, const gb_lm_options *o, gb_lm_result *r, double *t) { GB_P(p); return p->impl->lm(o, r, t); }

@@ -339,6 +339,27 @@ struct HostStructure {
   int32_t ncta() const { return (int32_t)cta_st.size() - 1; }
   int32_t nchunks() const { return (int32_t)ch_ptr.size() - 1; }
 
+  // Upper block-CSC of the Schur complement S = B - E C^-1 E^T in the reference's order
+  // (SchurComplement::build_structure, schur.hpp:194-225, 397-585; csc_utils.hpp:16-50): block (i, j), i <= j, exists
+  // iff i == j or cameras i and j observe a common point; columns ascending, rows ascending inside a column.
+  void schur_structure(std::vector<int64_t> &colptr, std::vector<int32_t> &rowidx) const {
+    std::vector<std::vector<int32_t>> rows((size_t)Nc);
+    for (int32_t c = 0; c < Nc; c++) rows[c].push_back(c);
+    for (int32_t p = 0; p < Np; p++)
+      for (int32_t a = pptr[p]; a < pptr[p + 1]; a++)
+        for (int32_t b = a + 1; b < pptr[p + 1]; b++) rows[cam_idx[b]].push_back(cam_idx[a]); // cam_idx[a] < cam_idx[b]
+    colptr.assign((size_t)Nc + 1, 0);
+    rowidx.clear();
+    for (int32_t c = 0; c < Nc; c++) {
+      auto &v = rows[c];
+      std::sort(v.begin(), v.end());
+      v.erase(std::unique(v.begin(), v.end()), v.end());
+      rowidx.insert(rowidx.end(), v.begin(), v.end());
+      colptr[c + 1] = (int64_t)rowidx.size();
+      std::vector<int32_t>().swap(v);
+    }
+  }
+
   // Upper block-CSC of the Hessian in the reference's order (hessian.hpp:59-84, 270-278; csc_utils.hpp:16-50).
   void hessian_structure(int64_t *colptr, int64_t *rowidx, int64_t *offsets) const {
     int64_t k = 0, off = 0;

@@ -91,6 +91,7 @@ int gb_structure_destroy(gb_structure *s);
 int gb_structure_info(const gb_structure *s, int64_t info[12]);
 int gb_structure_array(const gb_structure *s, int which, void *out, int64_t *count);
 int gb_structure_hessian(const gb_structure *s, int64_t *colptr, int64_t *rowidx, int64_t *offsets);
+int gb_structure_schur(const gb_structure *s, int64_t *colptr, int64_t *rowidx, int64_t *nnz_blocks); /* see gb_schur_structure */
 
 /* Sizes: [0]=n_tiles [1]=n_partial_rows (super-tile x camera) [2]=max_track_length [3]=hessian_dim
  * [4]=n_hessian_blocks [5]=n_hessian_values [6]=device bytes allocated [7]=n_obs [8]=n_super_tiles
@@ -167,6 +168,16 @@ int gb_solve(gb_problem *p, const gb_pcg_options *opt, void *delta_host, gb_solv
 int gb_get_schur_rhs(gb_problem *p, void *bS_host);
 int gb_get_schur_diagonal(gb_problem *p, void *blocks_host);
 int gb_schur_multiply(gb_problem *p, const void *x_host, void *y_host);
+
+/* Replaces: SchurComplement::build_structure (schur.hpp:194-225, 397-585) — the upper-triangular block-CSC of
+ * S = B - E C^-1 E^T: block (i, j), i <= j, exists iff i == j or cameras i and j observe a common point; columns and the
+ * rows inside a column ascending (csc_utils.hpp:16-50).  colptr [n_cams+1], rowidx [nnz_blocks]; either may be NULL
+ * (query nnz_blocks first).  Host-side, cached after the first call. */
+int gb_schur_structure(gb_problem *p, int64_t *colptr, int64_t *rowidx, int64_t *nnz_blocks);
+/* Replaces: SchurComplement::update_values + get_values with an EXPLICIT S (schur.hpp:227-235, ops/schur.hpp:154-188)
+ * at the current damping: values [nnz_blocks][81], column-major 9x9 blocks in the order of gb_schur_structure (element
+ * type T).  Export for consumers of the reduced system (direct solvers, parity); the PCG itself stays matrix-free. */
+int gb_schur_values(gb_problem *p, void *values_host);
 
 /* Replaces: backup_parameters + apply_update + compute_error + chi2 + compute_rho
  * (levenberg_marquardt.hpp:174-185): applies the last solve's step, returns the new chi2 and the rho

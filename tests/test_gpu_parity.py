@@ -110,6 +110,41 @@ def test_reference_golden_first_linearisation(ctx):
     P.close()
 
 
+@pytest.mark.parametrize("case", ["schur-fixture", "ladybug-49"])
+def test_explicit_schur_matches_reference_and_oracle(ctx, case):
+    """gb_schur_structure / gb_schur_values: block pattern bit-exact, values against the reference's scalar CSC dump
+    (schur.update_csc_values) and the oracle's explicit S."""
+    prob = synthetic.schur_fixture() if case == "schur-fixture" else synthetic.make_named(case)
+    z = golden_npz(f"{case}__pcg-schur__FP64-FP64.npz")
+    g = golden_json(f"{case}__pcg-schur__FP64-FP64.json")
+    P = binding.problem_from_bal(ctx, prob, "f64-f64")
+    P.linearize()
+    P.set_damping(g["lambda"])
+    cp, ri = P.schur_structure()
+    assert np.array_equal(cp, z["S_colptr"]) and np.array_equal(ri, z["S_rowidx"])
+    vals = P.schur_values()
+    n = 9 * prob.n_cams
+    ours = np.zeros((n, n))
+    for j in range(prob.n_cams):
+        for k in range(cp[j], cp[j + 1]):
+            i = ri[k]
+            ours[9 * i:9 * i + 9, 9 * j:9 * j + 9] = vals[k]
+    ptr, idx, val = z["Scsc_ptr"], z["Scsc_idx"], z["Scsc_val"]
+    ref = np.zeros((n, n))
+    for c in range(n):
+        ref[idx[ptr[c]:ptr[c + 1]], c] = val[ptr[c]:ptr[c + 1]]
+    assert rel(np.triu(ours), ref) <= 1e-11
+    O = Oracle(prob)
+    O.linearize()
+    S, _ = O.schur(g["lambda"])
+    assert rel(np.triu(ours), np.triu(S)) <= 1e-11
+    # consistent with the matrix-free operator the solver uses
+    x = np.random.default_rng(3).normal(size=n)
+    full = np.triu(ours) + np.triu(ours, 1).T
+    assert rel(P.schur_multiply(x), full @ x) <= 1e-11
+    P.close()
+
+
 # ------------------------------------------------------------------------------------------------------
 # LM trajectories against the reference's own runs
 # ------------------------------------------------------------------------------------------------------
@@ -319,12 +354,17 @@ def test_robust_trajectory_matches_reference(ctx, name, solver, huber, weights):
     n = min(n, len(traj))
     assert n >= 15
     r = np.abs(traj[:n, 1] - t[:n, 2]) / t[:n, 2]
-    tol = np.full(n, 1e-9)
-    try:  # the reference's own run-to-run spread on this case (measured: 1.1e-9 at iteration 6 on Ladybug, 1.8e-9 on Trafalgar)
+    # These runs sit at lambda ~ 1e-5 .. 1e-11 with a 10-iteration PCG: rounding differences are amplified ~1e4 times per
+    # LM iteration (scripts/debug_robust3.py: perturbing the parameters by 1e-13 moves the next cost by 3e-10).  The
+    # reference's own run-to-run spread (float atomics, *.run2.json) reaches 1.1e-9 on Ladybug and 1.8e-9 on Trafalgar;
+    # the CPU oracle, which follows the reference's operation order, sits at up to 25x that spread (3.5e-8, Trafalgar
+    # iteration 15).  Bound: 5e-9 or 30x the accumulated reference spread.
+    tol = np.full(n, 5e-9)
+    try:
         t2 = np.array(golden_json(robust_tag(name, solver, huber, weights) + ".run2.json")["table"])
-        tol = np.maximum(tol, 10 * np.maximum.accumulate(np.abs(t[:n, 2] - t2[:n, 2]) / t[:n, 2]))
+        tol = np.maximum(tol, 30 * np.maximum.accumulate(np.abs(t[:n, 2] - t2[:n, 2]) / t[:n, 2]))
     except FileNotFoundError:
-        tol = np.full(n, 5e-9)  # no second reference run recorded for this variant: same problem, same spread class
+        pass
     assert np.all(r <= tol), (r, tol)
     assert np.array_equal(traj[:n, 0] == traj[:n, 1], t[:n, 1] == t[:n, 2])
     assert abs(traj[-1, 1] - g["final_chi2"]) <= 1e-4 * g["final_chi2"]

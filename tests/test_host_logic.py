@@ -57,6 +57,21 @@ def test_structure_matches_reference_golden(built):
     assert np.array_equal(cp, z["H_colptr"]) and np.array_equal(ri, z["H_rowidx"]) and np.array_equal(off, z["H_offsets"])
 
 
+@pytest.mark.parametrize("case", ["schur-fixture", "ladybug-49"])
+def test_schur_structure_matches_reference_golden(built, case):
+    """SchurComplement::build_structure: d_col_pointers / d_row_indices of the reference, bit-exact."""
+    prob = synthetic.schur_fixture() if case == "schur-fixture" else synthetic.make_named(case)
+    z = golden_npz(f"{case}__pcg-schur__FP64-FP64.npz")
+    hs = binding.host_structure(prob.cam_idx, prob.pt_idx, prob.n_cams, prob.n_pts)
+    cp, ri = hs["schur"]
+    assert np.array_equal(cp, z["S_colptr"]) and np.array_equal(ri, z["S_rowidx"])
+    # a sparser pattern: cameras that share no point have no block
+    ci = np.array([0, 1, 1, 2, 2, 3], dtype=np.int32)
+    pi = np.array([0, 0, 1, 1, 2, 2], dtype=np.int32)
+    cp, ri = binding.host_structure(ci, pi, 4, 3)["schur"]
+    assert cp.tolist() == [0, 1, 3, 5, 7] and ri.tolist() == [0, 0, 1, 1, 2, 2, 3]
+
+
 @pytest.mark.parametrize("tile,cap,st_obs", [(0, 0, 0), (64, 0, 0), (32, 40, 500), (0, 30, 2000)])
 def test_tiles_ranks_segments_and_super_tiles(built, tile, cap, st_obs):
     prob = synthetic.make_named("ladybug-49")
