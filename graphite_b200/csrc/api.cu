@@ -281,7 +281,8 @@ template <typename T, typename S> struct Problem : ProblemBase {
                                       SchurSmem<T, S>::TOTAL(NSTAGE)));
     GB_CUDA(ctx, cudaFuncSetAttribute(k_schur_product<T, S, NSTAGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       SchurSmem<T, S>::TOTAL(NSTAGE)));
-    GB_TRY(dalloc(diagB, dimc)); GB_TRY(dalloc(gc, dimc));
+    GB_TRY(dalloc(diagB, 2 * dimc)); // diag(B) | g_c contiguous: one exchange for both on the multi-GPU path
+    gc = diagB + dimc;
     GB_TRY(dalloc(scale, dimH)); GB_TRY(dalloc(b, dimH)); GB_TRY(dalloc(delta, dimH));
     GB_TRY(dalloc(W, (size_t)WST<T>::value * Np + 8)); GB_TRY(dalloc(h, (size_t)HST * Np + 8));
     GB_TRY(dalloc(Sdiag, Nc * 81)); GB_TRY(dalloc(Minv, Nc * 81));
@@ -398,15 +399,28 @@ template <typename T, typename S> struct Problem : ProblemBase {
     if (rc != 0) return ctx->fail(GB_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
     return GB_OK;
   }
-  template <typename X> int exchange(X *buf, size_t count) {
-    if (ctx->nranks <= 1) return GB_OK;
-    if (!p2p_on || count * sizeof(X) > pp.slot_bytes) return allreduce(buf, count, sizeof(X) == 8);
+  // sum over ranks, in place.  Peer-memory path: exchange_push stores the buffer into every rank's receive slot,
+  // exchange_sum waits for the peers and adds the slots in rank order; independent local kernels may be enqueued between
+  // the two so that they run while the peers' data is in flight.  NCCL fallback: the all-reduce happens in exchange_sum.
+  template <typename X> bool exchange_p2p(size_t count) const { return p2p_on && count * sizeof(X) <= pp.slot_bytes; }
+  template <typename X> int exchange_push(X *buf, size_t count) {
+    if (ctx->nranks <= 1 || !exchange_p2p<X>(count)) return GB_OK;
     const int grid = (int)std::min<size_t>((count + 255) / 256, 4 * 148);
     k_p2p_push<X><<<grid, 256, 0, ctx->stream>>>(pp, buf, (long long)count);
     GB_LAUNCH(ctx);
+    return GB_OK;
+  }
+  template <typename X> int exchange_sum(X *buf, size_t count) {
+    if (ctx->nranks <= 1) return GB_OK;
+    if (!exchange_p2p<X>(count)) return allreduce(buf, count, sizeof(X) == 8);
+    const int grid = (int)std::min<size_t>((count + 255) / 256, 4 * 148);
     k_p2p_sum<X><<<grid, 256, 0, ctx->stream>>>(pp, buf, (long long)count);
     GB_LAUNCH(ctx);
     return GB_OK;
+  }
+  template <typename X> int exchange(X *buf, size_t count) {
+    GB_TRY(exchange_push<X>(buf, count));
+    return exchange_sum<X>(buf, count);
   }
   int allreduce_T(T *buf, size_t count) { return exchange<T>(buf, count); }
 
@@ -478,7 +492,9 @@ template <typename T, typename S> struct Problem : ProblemBase {
     return GB_OK;
   }
 
-  int enqueue_linearize() {
+  // need_cost = false: the caller does not read chi2 of this linearisation (the accepted-step path of the LM loop
+  // already has it from the trial step), so its cross-rank sum is skipped
+  int enqueue_linearize(bool need_cost = true) {
     cudaStream_t st = ctx->stream;
     k_cam_precompute<T><<<(ts.Nc + 127) / 128, 128, 0, st>>>(ts.Nc, cams, camx);
     GB_LAUNCH(ctx);
@@ -489,17 +505,18 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_LAUNCH(ctx);
     k_sum_partials<<<1, 1024, 0, st>>>(cost_part, ts.ntiles, scalars, 0);
     GB_LAUNCH(ctx);
-    if (multi) {
-      GB_TRY(allreduce_T(diagB, dimc));
-      GB_TRY(allreduce_T(gc, dimc));
-      GB_TRY(exchange<double>(scalars, 1));
-      k_cam_finish_lin<T><<<(int)((dimc + 255) / 256), 256, 0, st>>>((int)dimc, scale_on ? 1 : 0, diagB, gc, scale, b);
-      GB_LAUNCH(ctx);
-    }
-    // point scales and b_p (mu-independent part of k_point_prepare); W/h are refreshed by prepare
+    if (multi) GB_TRY(exchange_push<T>(diagB, 2 * (size_t)dimc));
+    // point scales and b_p (mu-independent part of k_point_prepare); W/h are refreshed by prepare.  Purely local: on
+    // the multi-GPU path it runs while the peers' diag(B) | g_c are in flight
     k_point_prepare<T><<<(ts.Np + 255) / 256, 256, 0, st>>>(ts.Np, scale_on ? 1 : 0, mu, use_identity, Cg, scale + dimc,
                                                            b + dimc, W, h, 1);
     GB_LAUNCH(ctx);
+    if (multi) {
+      GB_TRY(exchange_sum<T>(diagB, 2 * (size_t)dimc));
+      if (need_cost) GB_TRY(exchange<double>(scalars, 1));
+      k_cam_finish_lin<T><<<(int)((dimc + 255) / 256), 256, 0, st>>>((int)dimc, scale_on ? 1 : 0, diagB, gc, scale, b);
+      GB_LAUNCH(ctx);
+    }
     GB_TRY(launch_check());
     linearized = true;
     prepared = solved = stepped = false;
@@ -657,13 +674,14 @@ template <typename T, typename S> struct Problem : ProblemBase {
     k_prepare_cams<T, S><<<ts.nchunks, PC_THREADS, 0, st>>>(ts, J, W, h, part54);
     GB_LAUNCH(ctx);
     const bool multi = ctx->nranks > 1;
+    const int xchg = (multi && exchange_p2p<T>((size_t)ts.Nc * 54)) ? 1 : 0; // push / pull fused into the two launches
     k_cam_reduce_prepare<T><<<ts.Nc, 288, 0, st>>>(ts, part54, 0, sums54, multi ? 0 : 1, mu, use_identity, diagB, gc,
-                                                   scale, Sdiag, Minv, bS, dterm);
+                                                   scale, Sdiag, Minv, bS, dterm, pp, xchg);
     GB_LAUNCH(ctx);
     if (multi) {
-      GB_TRY(allreduce_T(sums54, (size_t)ts.Nc * 54));
+      if (!xchg) GB_TRY(allreduce_T(sums54, (size_t)ts.Nc * 54));
       k_cam_reduce_prepare<T><<<ts.Nc, 288, 0, st>>>(ts, part54, 1, sums54, 1, mu, use_identity, diagB, gc, scale, Sdiag,
-                                                     Minv, bS, dterm);
+                                                     Minv, bS, dterm, pp, xchg);
       GB_LAUNCH(ctx);
     }
     GB_TRY(launch_check());
@@ -1089,7 +1107,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
         nu = T(2);
         mu = mu_l;
         GB_CUDA(ctx, cudaEventRecord(ev[0], st));
-        GB_TRY(enqueue_linearize());
+        GB_TRY(enqueue_linearize(false));
         GB_CUDA(ctx, cudaEventRecord(ev[1], st));
         GB_CUDA(ctx, cudaStreamSynchronize(st));
         cudaEventElapsedTime(&ms, ev[0], ev[1]);

@@ -855,16 +855,31 @@ __global__ void __launch_bounds__(288)
 k_cam_reduce_prepare(DevStruct ds, const T *__restrict__ part, int from_sums, T *__restrict__ sums /*[Nc][54]*/,
                      int finish, T mu, int use_identity, const T *__restrict__ diagB, const T *__restrict__ gc,
                      const T *__restrict__ scale_c, T *__restrict__ Sdiag /*[Nc][81]*/, T *__restrict__ Minv,
-                     T *__restrict__ bS, T *__restrict__ dterm) {
+                     T *__restrict__ bS, T *__restrict__ dterm, P2P pp, int xchg) {
   __shared__ T sh[32 * 9];
   __shared__ T out[54];
   __shared__ T Maug[9 * 18], fcol[9];
   const int c = blockIdx.x, t = threadIdx.x;
   if (!from_sums) {
     cam_gather<T>(ds, c, part, 54, 6, sh, out, ds.cam_ch_ptr); // rows of k_prepare_cams: one per camera chunk
+    if (xchg) {
+      // multi-GPU over peer memory: this rank's 54 sums go straight into every rank's receive slot (p2p.cuh); the
+      // second launch (from_sums) waits for the peers and adds the slots in rank order
+      const unsigned long long epoch = p2p_next_epoch(pp);
+      if (t < 54)
+        for (int q = 0; q < pp.nranks; q++) p2p_slot<T>(pp, q, pp.rank, epoch)[(int64_t)c * 54 + t] = out[t];
+      p2p_signal(pp, epoch, gridDim.x);
+      return;
+    }
     if (t < 54) sums[(int64_t)c * 54 + t] = out[t];
   } else {
-    if (t < 54) out[t] = sums[(int64_t)c * 54 + t];
+    if (xchg) {
+      const unsigned long long epoch = p2p_current_epoch(pp);
+      p2p_wait(pp, epoch);
+      if (t < 54) out[t] = p2p_sum<T>(pp, epoch, (long long)c * 54 + t);
+    } else if (t < 54) {
+      out[t] = sums[(int64_t)c * 54 + t];
+    }
     __syncthreads();
   }
   if (!finish) return;
@@ -1592,7 +1607,7 @@ k_pcg_iterate(DevStruct ds, PcgState<T> *st /*in: st[0], out: st[2]*/, T tol, T 
       *pp.seq = epoch;
       __threadfence_system();
       for (int q = 0; q < pp.nranks; q++)
-        if (q != pp.rank) st_release_sys(pp.flags[q] + pp.rank, epoch);
+        if (q != pp.rank) st_relaxed_sys(pp.flags[q] + pp.rank, epoch);
     }
     p2p_wait(pp, epoch);
     for (int c = c_begin + warp; c < c_end; c += PIT_WARPS) {

@@ -35,6 +35,11 @@ struct P2P {
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// relaxed system-scope store: after ONE __threadfence_system() the flag words of all peers are written back to back
+// (fence + relaxed store is a release pattern); st.release on every store would serialise one NVLink round trip per peer
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -72,7 +77,7 @@ __device__ __forceinline__ void p2p_signal(const P2P &pp, unsigned long long epo
       *pp.seq = epoch;  // every CTA has read seq before arriving
       __threadfence_system();
       for (int r = 0; r < pp.nranks; r++)
-        if (r != pp.rank) st_release_sys(pp.flags[r] + pp.rank, epoch);
+        if (r != pp.rank) st_relaxed_sys(pp.flags[r] + pp.rank, epoch);
     }
   }
 }
