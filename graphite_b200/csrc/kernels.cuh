@@ -751,9 +751,12 @@ k_prepare_tiles(DevStruct ds, const typename V2<S>::type *__restrict__ J, const 
 // its observations, gathers the 24 Jacobian values from the tile-major store by slot (adjacent slots of one camera
 // share sectors) plus W and h of the point, and keeps all 54 sums in registers - no staging, no segment tables; one
 // shuffle tree per CTA at the end.  Output: one 54-value row per chunk, rows of a camera contiguous (cam_ch_ptr).
+#ifndef PC_MIN_BLOCKS
+#define PC_MIN_BLOCKS 3 // 166 registers, no spills: 314 us against 344 us at 2 (202 registers) and 436 us at 4 (spills)
+#endif
 constexpr int PC_THREADS = 128;
 template <typename T, typename S>
-__global__ void __launch_bounds__(PC_THREADS, 2)
+__global__ void __launch_bounds__(PC_THREADS, PC_MIN_BLOCKS)
 k_prepare_cams(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *__restrict__ W,
                const T *__restrict__ h, T *__restrict__ part /*[nchunks][54]*/) {
   using S2 = typename V2<S>::type;
@@ -763,8 +766,14 @@ k_prepare_cams(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T
   T acc[54];
 #pragma unroll
   for (int v = 0; v < 54; v++) acc[v] = T(0);
-  for (int i = b + (int)threadIdx.x; i < e; i += PC_THREADS) {
-    const int slot = ds.cm_slot[i], p = ds.cm_pt[i];
+  // the indices of the next observation are fetched one iteration ahead: the 17 gathers of an observation then issue
+  // without waiting for a dependent index load
+  int i = b + (int)threadIdx.x;
+  int slot_n = 0, p_n = 0;
+  if (i < e) { slot_n = ds.cm_slot[i]; p_n = ds.cm_pt[i]; }
+  for (; i < e; i += PC_THREADS) {
+    const int slot = slot_n, p = p_n;
+    if (i + PC_THREADS < e) { slot_n = ds.cm_slot[i + PC_THREADS]; p_n = ds.cm_pt[i + PC_THREADS]; }
     const S2 *base = J + ((int64_t)(slot >> 8) * NPLANES) * TILE + (slot & (TILE - 1));
     T jc[18], jp[6];
 #pragma unroll

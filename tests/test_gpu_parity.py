@@ -355,7 +355,7 @@ def test_robust_trajectory_matches_reference(ctx, name, solver, huber, weights):
     assert n >= 15
     r = np.abs(traj[:n, 1] - t[:n, 2]) / t[:n, 2]
     # These runs sit at lambda ~ 1e-5 .. 1e-11 with a 10-iteration PCG: rounding differences are amplified ~1e4 times per
-    # LM iteration (scripts/debug_robust3.py: perturbing the parameters by 1e-13 moves the next cost by 3e-10).  The
+    # LM iteration (scripts/robust_sensitivity.py: perturbing the parameters by 1e-13 moves the next cost by 3e-10).  The
     # reference's own run-to-run spread (float atomics, *.run2.json) reaches 1.1e-9 on Ladybug and 1.8e-9 on Trafalgar;
     # the CPU oracle, which follows the reference's operation order, sits at up to 25x that spread (3.5e-8, Trafalgar
     # iteration 15).  Bound: 5e-9 or 30x the accumulated reference spread.
