@@ -281,6 +281,10 @@ template <typename T, typename S> struct Problem : ProblemBase {
                                       SchurSmem<T, S>::TOTAL(NSTAGE)));
     GB_CUDA(ctx, cudaFuncSetAttribute(k_schur_product<T, S, NSTAGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       SchurSmem<T, S>::TOTAL(NSTAGE)));
+    GB_CUDA(ctx, cudaFuncSetAttribute(k_schur_product2<T, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      SchurSmem2<T, S>::TOTAL));
+    GB_CUDA(ctx, cudaFuncSetAttribute(k_schur_product2<T, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      SchurSmem2<T, S>::TOTAL));
     GB_TRY(dalloc(diagB, 2 * dimc)); // diag(B) | g_c contiguous: one exchange for both on the multi-GPU path
     gc = diagB + dimc;
     GB_TRY(dalloc(scale, dimH)); GB_TRY(dalloc(b, dimH)); GB_TRY(dalloc(delta, dimH));
@@ -602,9 +606,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
       // v2 = J~^T J~ p + mu clamp(diag) p   (pcg.hpp:141-168)
       k_full_build_u<T><<<full_blocks, 256, 0, st>>>(ts.Nc, ts.Np, f_p, scale, xs, f_upw);
       GB_LAUNCH(ctx);
-      k_schur_product<T, S, NSTAGE, true><<<ts.ncta, 2 * TILE, SchurSmem<T, S>::TOTAL(NSTAGE), st>>>(ts, J, f_upw, xs, part9,
-                                                                                                     nullptr, f_outp);
-      GB_LAUNCH(ctx);
+      launch_product<true>(f_upw, nullptr, f_outp);
       k_cam_reduce_spmv<T><<<ts.Nc, 288, 0, st>>>(ts, part9, scale, Ap_raw, 0, dterm, nullptr, Ap, dot_part, nullptr, pp, 0);
       GB_LAUNCH(ctx);
       k_full_finish_v2<T><<<full_blocks, 256, 0, st>>>(ts.Nc, ts.Np, mu, use_identity, Ap_raw, f_outp, f_p, scale, diagB, Cg,
@@ -661,6 +663,16 @@ template <typename T, typename S> struct Problem : ProblemBase {
     return GB_OK;
   }
 
+  // the Schur product kernel (PRODUCT_PIPE selects the pipeline, kernels.cuh)
+  template <bool FULL> void launch_product(const T *Wp, const int *flag, T *outp) {
+#if PRODUCT_PIPE == 2
+    k_schur_product2<T, S, FULL><<<ts.ncta, 2 * TILE, SchurSmem2<T, S>::TOTAL, ctx->stream>>>(ts, J, Wp, xs, part9, flag, outp);
+#else
+    k_schur_product<T, S, NSTAGE, FULL><<<ts.ncta, 2 * TILE, SchurSmem<T, S>::TOTAL(NSTAGE), ctx->stream>>>(ts, J, Wp, xs, part9,
+                                                                                                          flag, outp);
+#endif
+    GB_LAUNCH(ctx);
+  }
   int enqueue_prepare_tiles_only() {
     k_prepare_cams<T, S><<<ts.nchunks, PC_THREADS, 0, ctx->stream>>>(ts, J, W, h, part54);
     GB_LAUNCH(ctx);
@@ -704,9 +716,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     }
     const bool multi = ctx->nranks > 1;
     const int finish = (!multi && pvec) ? 1 : 0;
-    k_schur_product<T, S, NSTAGE, false><<<ts.ncta, 2 * TILE, SchurSmem<T, S>::TOTAL(NSTAGE), st>>>(ts, J, W, xs, part9, flag,
-                                                                                                    nullptr);
-    GB_LAUNCH(ctx);
+    launch_product<false>(W, flag, nullptr);
     if (prof) GB_CUDA(ctx, cudaEventRecord(prof_ev[3 * prof_slot + 1], st));
     if (product_only) return GB_OK; // the fused iteration kernel sums the partial rows itself
     // The per-camera sum of the partial rows stays a separate, massively parallel kernel: fused into the tail of
@@ -1171,9 +1181,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
       case 3: GB_TRY(enqueue_step(false)); break;
       case 4: GB_TRY(enqueue_cost()); break;
       case 5: // the product kernel alone
-        k_schur_product<T, S, NSTAGE, false><<<ts.ncta, 2 * TILE, SchurSmem<T, S>::TOTAL(NSTAGE), st>>>(ts, J, W, xs, part9,
-                                                                                                        nullptr, nullptr);
-        GB_LAUNCH(ctx);
+        launch_product<false>(W, nullptr, nullptr);
         break;
       case 6: // the per-camera reduction of its partial rows alone (single-GPU form)
         k_cam_reduce_spmv<T><<<ts.Nc, 288, 0, st>>>(ts, part9, scale, Ap_raw, 1, dterm, pv, Ap, dot_part, nullptr, pp, 0);

@@ -37,6 +37,9 @@ namespace gb {
 constexpr int CAM_STRIDE = 10; // padded camera row
 constexpr int NPLANES = 12;
 // dynamic shared memory of the super-tile kernels, in elements of T
+#ifndef PRODUCT_PIPE
+#define PRODUCT_PIPE 2
+#endif
 #ifndef J_EVICT_FIRST
 #define J_EVICT_FIRST 1
 #endif
@@ -1120,6 +1123,196 @@ k_schur_product(DevStruct ds, const typename V2<S>::type *__restrict__ J, const 
     }
     __syncthreads();
     // rows of this super-tile: worker 0 (even ring indices) + worker 1 (odd), fixed order
+    for (int i = threadIdx.x; i < nslots * 9; i += 2 * TILE) {
+      const int s = i / 9, k = i - 9 * s;
+      part[(int64_t)ds.row_out[row0 + s] * 9 + k] = acc_all[i] + acc_all[SLOT_CAP * 9 + i];
+    }
+    __syncthreads(); // xl / acc are rewritten by the next super-tile
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4, second pipeline (PRODUCT_PIPE == 2).  ncu of the 3-stage ring above: a stage is refilled only when its tile is
+// completely processed, and the two workers consume concurrently, so the tile a worker needs next has been issued only
+// when the OTHER worker finished its previous one (5 polls per wait on average).  But the 48 KB Jacobian block of a tile
+// is dead as soon as its values are in registers, a fraction of a microsecond after the wait.  Here
+//   - the J ring has 2 slots, one per worker; right after the worker's first barrier (all threads hold their J values)
+//     the slot is refilled with the worker's NEXT tile (i + 2), which then has the whole tile time to land;
+//   - the small per-tile data that stays live during the tile (record 2.4 KB, W rows 6 KB) sits in its own 4-deep ring;
+//   - the staging areas get their own space (the point staging aliases the camera staging, they are never live together).
+// Tile i uses mbarrier i % 4; tiles i and i + 4 belong to the same worker, so a parity wait can never run a phase ahead.
+// ---------------------------------------------------------------------------------------------
+template <typename T, typename S> struct SchurSmem2 {
+  static constexpr int J_BYTES = NPLANES * TILE * (int)sizeof(typename V2<S>::type);
+  static constexpr int W_BYTES = TILE_PTS * WST<T>::value * (int)sizeof(T);
+  static constexpr int META_BYTES = REC_BYTES + W_BYTES;
+  static constexpr int NMETA = 4;
+  static constexpr int SV_BYTES = TILE * 9 * (int)sizeof(T);      // camera staging (point staging [TILE*3] aliases it)
+  static constexpr int SW_BYTES = TILE_PTS * 3 * (int)sizeof(T);  // point sums
+  static constexpr int STG_BYTES = SV_BYTES + SW_BYTES;           // per worker
+  static constexpr int META_OFF = 2 * J_BYTES;
+  static constexpr int STG_OFF = META_OFF + NMETA * META_BYTES;
+  static constexpr int XL_OFF = STG_OFF + 2 * STG_BYTES;
+  static constexpr int ACC_OFF = XL_OFF + SLOT_CAP * 9 * (int)sizeof(T);
+  static constexpr int BAR_OFF = ACC_OFF + 2 * SLOT_CAP * 9 * (int)sizeof(T);
+  static constexpr int TOTAL = BAR_OFF + 64;
+  static_assert(META_BYTES % 16 == 0 && STG_BYTES % 16 == 0, "TMA destinations must stay 16-byte aligned");
+};
+
+template <typename T, typename S, bool FULL>
+__global__ void __launch_bounds__(2 * TILE, 1)
+k_schur_product2(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *__restrict__ W,
+                 const T *__restrict__ xs, T *__restrict__ part /*[nrows][9]*/, const int *__restrict__ done_flag,
+                 T *__restrict__ out_p /*FULL: [Np][3]*/) {
+  using SM = SchurSmem2<T, S>;
+  using S2 = typename V2<S>::type;
+  extern __shared__ __align__(128) unsigned char smem[];
+  if (done_flag && *done_flag) return; // PCG already stopped: nothing to do (uniform across the grid)
+  const int worker = threadIdx.x >> 8, t = threadIdx.x & (TILE - 1);
+  T *xl = reinterpret_cast<T *>(smem + SM::XL_OFF);
+  T *acc_all = reinterpret_cast<T *>(smem + SM::ACC_OFF);
+  T *acc = acc_all + worker * SLOT_CAP * 9;
+  T *sv = reinterpret_cast<T *>(smem + SM::STG_OFF + worker * SM::STG_BYTES);
+  T *sv3 = sv; // point-order staging: dead before the camera staging is written
+  T *sw = reinterpret_cast<T *>(smem + SM::STG_OFF + worker * SM::STG_BYTES + SM::SV_BYTES);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM::BAR_OFF);
+  const int st_begin = ds.cta_st[blockIdx.x], st_end = ds.cta_st[blockIdx.x + 1];
+  const int tile0 = ds.st_tile[st_begin], ntl = ds.st_tile[st_end] - tile0;
+#if J_EVICT_FIRST
+  const uint64_t pol = l2_policy_evict_first();
+#endif
+
+  // ring index i: J slot i & 1 (= its worker), meta slot and mbarrier i & 3
+  auto issue = [&](int tile, int i, int p0, int np) {
+    unsigned char *jdst = smem + (i & 1) * SM::J_BYTES;
+    unsigned char *mdst = smem + SM::META_OFF + (i & 3) * SM::META_BYTES;
+    uint64_t *bar = &bars[i & 3];
+    const uint32_t wbytes = (uint32_t)(np * WST<T>::value * (int)sizeof(T));
+    mbar_expect_tx(bar, (uint32_t)(SM::J_BYTES + REC_BYTES) + wbytes);
+#if J_EVICT_FIRST
+    bulk_g2s_hint(jdst, J + (int64_t)tile * NPLANES * TILE, SM::J_BYTES, bar, pol);
+    bulk_g2s_hint(mdst, ds.trec + (int64_t)tile * REC_BYTES, REC_BYTES, bar, pol);
+#else
+    bulk_g2s(jdst, J + (int64_t)tile * NPLANES * TILE, SM::J_BYTES, bar);
+    bulk_g2s(mdst, ds.trec + (int64_t)tile * REC_BYTES, REC_BYTES, bar);
+#endif
+    bulk_g2s(mdst + REC_BYTES, W + (int64_t)p0 * WST<T>::value, wbytes, bar);
+  };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SM::NMETA; s++) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+    fence_proxy_async();
+    for (int i = 0; i < 2 && i < ntl; i++) {
+      const TileMeta tm = ds.tmeta[tile0 + i];
+      issue(tile0 + i, i, tm.p0, tm.np);
+    }
+  }
+
+  for (int st = st_begin; st < st_end; st++) {
+    const int row0 = ds.st_row[st], nslots = ds.st_row[st + 1] - row0;
+    for (int i = threadIdx.x; i < nslots * 9; i += 2 * TILE) {
+      const int s = i / 9, k = i - 9 * s;
+      xl[i] = xs[(int64_t)ds.row_cam[row0 + s] * CAM_STRIDE + k];
+    }
+    for (int i = t; i < nslots * 9; i += TILE) acc[i] = T(0);
+    __syncthreads(); // also: the mbarriers are initialised before any thread waits on them
+    const int ib = ds.st_tile[st] - tile0, ie = ds.st_tile[st + 1] - tile0; // ring indices of this super-tile
+    for (int i = ib + ((ib ^ worker) & 1); i < ie; i += 2) {                 // worker w takes ring indices of parity w
+      mbar_wait(&bars[i & 3], (uint32_t)((i >> 2) & 1));
+      const S2 *Js = reinterpret_cast<const S2 *>(smem + (i & 1) * SM::J_BYTES);
+      const unsigned char *rec = smem + SM::META_OFF + (i & 3) * SM::META_BYTES;
+      const T *Ws = reinterpret_cast<const T *>(rec + REC_BYTES);
+      const TileMeta tm = *reinterpret_cast<const TileMeta *>(rec + REC_META);
+      const int next_p0 = reinterpret_cast<const int32_t *>(rec + REC_NEXT)[2];  // tile i + 2
+      const int next_np = reinterpret_cast<const int32_t *>(rec + REC_NEXT)[3];
+      const uint32_t om = reinterpret_cast<const uint32_t *>(rec + REC_OMETA)[t];
+      const int cslot = (int)(om >> 16), rank = (int)((om >> 8) & 0xffu), ptl = (int)(om & 0xffu);
+      T jc[18], jp[6], y0 = T(0), y1 = T(0);
+#pragma unroll
+      for (int j = 0; j < 9; j++) {
+        const S2 v = Js[j * TILE + t];
+        jc[2 * j] = (T)v.x;
+        jc[2 * j + 1] = (T)v.y;
+      }
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const S2 v = Js[(9 + j) * TILE + t];
+        jp[2 * j] = (T)v.x;
+        jp[2 * j + 1] = (T)v.y;
+      }
+      {
+        const T *x = xl + cslot * 9;
+#pragma unroll
+        for (int j = 0; j < 9; j++) {
+          const T xv = x[j];
+          y0 += jc[2 * j] * xv;
+          y1 += jc[2 * j + 1] * xv;
+        }
+      }
+      if (FULL) {
+        const T *u = Ws + ptl * WST<T>::value;
+        y0 += jp[0] * u[0] + jp[2] * u[1] + jp[4] * u[2];
+        y1 += jp[1] * u[0] + jp[3] * u[1] + jp[5] * u[2];
+      }
+      sv3[rank * 3 + 0] = jp[0] * y0 + jp[1] * y1; // staged at the position in point order
+      sv3[rank * 3 + 1] = jp[2] * y0 + jp[3] * y1;
+      sv3[rank * 3 + 2] = jp[4] * y0 + jp[5] * y1;
+      worker_sync(worker); // every thread of the worker has its J values in registers: the worker's J slot is free
+      if (t == 0 && i + 2 < ntl) {
+        fence_proxy_async();
+        issue(tile0 + i + 2, i + 2, next_p0, next_np);
+      }
+      {
+        const uint16_t *pt = reinterpret_cast<const uint16_t *>(rec + REC_PT);
+        for (int item = t; item < tm.np * 3; item += TILE) {
+          const int q = item / 3, k = item - 3 * q;
+          const int b = pt[q], e = pt[q + 1];
+          T a = T(0);
+          for (int row = b; row < e; row++) a += sv3[row * 3 + k];
+          if (FULL) out_p[(int64_t)(tm.p0 + q) * 3 + k] = a;
+          else sw[item] = a;
+        }
+      }
+      worker_sync(worker);
+      {
+        T d0 = y0, d1 = y1;
+        if (!FULL) {
+          const T t0 = sw[ptl * 3], t1 = sw[ptl * 3 + 1], t2 = sw[ptl * 3 + 2];
+          const T *w = Ws + ptl * WST<T>::value;
+          const T w0 = w[0] * t0 + w[1] * t1 + w[2] * t2;
+          const T w1 = w[1] * t0 + w[3] * t1 + w[4] * t2;
+          const T w2 = w[2] * t0 + w[4] * t1 + w[5] * t2;
+          d0 = y0 - (jp[0] * w0 + jp[2] * w1 + jp[4] * w2);
+          d1 = y1 - (jp[1] * w0 + jp[3] * w1 + jp[5] * w2);
+        }
+        // stage v = Jc^T d at the slot's own row: slots are in camera order, so camera segments are contiguous rows
+#pragma unroll
+        for (int k = 0; k < 9; k++) sv[t * 9 + k] = jc[2 * k] * d0 + jc[2 * k + 1] * d1;
+      }
+      worker_sync(worker);
+      {
+        const uint32_t *sg = reinterpret_cast<const uint32_t *>(rec + REC_SEG);
+        for (int item = t; item < tm.nseg * 3; item += TILE) {
+          const int q = item / 3, g = item - 3 * q;
+          const uint32_t e0 = sg[q], e1 = sg[q + 1];
+          const int b = (int)(e0 >> 16), e = (int)(e1 >> 16), cs = (int)(e0 & 0xffffu);
+          T a0 = T(0), a1 = T(0), a2 = T(0);
+          for (int row = b; row < e; row++) {
+            const T *r = sv + row * 9 + 3 * g;
+            a0 += r[0];
+            a1 += r[1];
+            a2 += r[2];
+          }
+          T *ar = acc + cs * 9 + 3 * g;
+          ar[0] += a0;
+          ar[1] += a1;
+          ar[2] += a2;
+        }
+      }
+      worker_sync(worker); // staging and the meta slot are free for the worker's next tile
+    }
+    __syncthreads();
     for (int i = threadIdx.x; i < nslots * 9; i += 2 * TILE) {
       const int s = i / 9, k = i - 9 * s;
       part[(int64_t)ds.row_out[row0 + s] * 9 + k] = acc_all[i] + acc_all[SLOT_CAP * 9 + i];
