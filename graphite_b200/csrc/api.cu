@@ -121,7 +121,6 @@ template <typename T, typename S> struct Problem : ProblemBase {
   using T2 = typename V2<T>::type;
   using S2 = typename V2<S>::type;
   static constexpr int NSTAGE = 3; // TMA pipeline depth of the Schur product (fits 227 KB in FP64)
-  static constexpr int PSTAGE = 2; // ... of the prepare kernel (its 54-wide accumulator rows take 81 KB)
   DevStruct ts{};
   std::vector<void *> allocs;
   int64_t bytes = 0;
@@ -275,8 +274,6 @@ template <typename T, typename S> struct Problem : ProblemBase {
     }
     // the super-tile kernels keep their camera accumulator rows in (opt-in sized) dynamic shared memory
     GB_CUDA(ctx, cudaFuncSetAttribute(k_linearize<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_lin_bytes<T>()));
-    GB_CUDA(ctx, cudaFuncSetAttribute(k_prepare_tiles<T, S, PSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      PrepSmem<T, S>::TOTAL(PSTAGE)));
     GB_CUDA(ctx, cudaFuncSetAttribute(k_schur_product<T, S, NSTAGE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       SchurSmem<T, S>::TOTAL(NSTAGE)));
     GB_CUDA(ctx, cudaFuncSetAttribute(k_schur_product<T, S, NSTAGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -539,7 +536,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_TRY(dalloc(f_p, n)); GB_TRY(dalloc(f_v2, n)); GB_TRY(dalloc(f_xbak, n));
     GB_TRY(dalloc(f_upw, (size_t)WST<T>::value * ts.Np + 8));
     GB_TRY(dalloc(f_outp, 3 * (size_t)ts.Np));
-    GB_TRY(dalloc(f_zero, (size_t)WST<T>::value * ts.Np + 8)); // W = 0, h = 0: k_prepare_tiles then sums Jc^T Jc
+    GB_TRY(dalloc(f_zero, (size_t)WST<T>::value * ts.Np + 8)); // W = 0, h = 0: k_prepare_cams then sums Jc^T Jc
     GB_TRY(dalloc(f_Bfull, (size_t)ts.Nc * 81)); GB_TRY(dalloc(f_MinvF, (size_t)ts.Nc * 81));
     full_blocks = (int)((dimH + 255) / 256);
     GB_TRY(dalloc(f_part, full_blocks)); GB_TRY(dalloc(f_rho, full_blocks));

@@ -52,7 +52,6 @@ template <typename T> constexpr int smem_lin_bytes() { // staging, accumulator r
 }
 // per-point W row stride: 6 values, padded to 8 in FP32 so that a tile's rows start 16-byte aligned (TMA)
 template <typename T> struct WST { static constexpr int value = sizeof(T) == 4 ? 8 : 6; };
-constexpr int ACC54 = 55; // shared-memory stride of the 54-wide accumulator rows (odd: rows start in different banks)
 constexpr int HST = 4; // per-point h row stride (3 values + pad): 16-byte aligned rows in FP32 and FP64
 
 template <typename T> struct V2;
@@ -552,203 +551,14 @@ __global__ void k_point_prepare(int Np, int scale_on, T mu, int use_identity, co
   h[HST * (int64_t)p + 2] = w02 * g0 + w12 * g1 + w22 * g2;
 }
 
-// K3b: per super-tile — camera-side partials of the Schur diagonal blocks and of the reduced right-hand side:
+// K3b: camera-side sums of the Schur diagonal blocks and of the reduced right-hand side
 //   A_c = sum_o Jc^T (I - N_o) Jc   (N_o = Jp W Jp^T; equals B_c - sum E W E^T restricted to the diagonal)
 //   u_c = sum_o Jc^T Jp h_p
 // replaces execute_schur_multiplication on the diagonal pairs + execute_b_Schur_computation
 // (schur.hpp:649-734, 901-920) and the block copy of block_jacobi_schur.hpp:126-137.
-// Same TMA tile pipeline as the Schur product.  The 54 values per camera (45 upper entries of A, 9 of u) are
-// split between the CTA's two workers: both read every tile from the same stage, worker 0 accumulates values
-// 0..26, worker 1 values 27..53, each into its own columns of the shared accumulator rows.
-template <typename T, typename S> struct PrepSmem {
-  static constexpr int J_BYTES = NPLANES * TILE * (int)sizeof(typename V2<S>::type);
-  static constexpr int W_BYTES = TILE_PTS * WST<T>::value * (int)sizeof(T);
-  static constexpr int H_BYTES = TILE_PTS * HST * (int)sizeof(T);
-  static constexpr int STAGE_BYTES = J_BYTES + REC_BYTES + W_BYTES + H_BYTES;
-  static constexpr int SV_BYTES = TILE * 9 * (int)sizeof(T); // staging per worker
-  // the two staging areas reuse the consumed J region when they fit (T == S); else they get their own space
-  static constexpr bool SV_ALIAS = 2 * SV_BYTES <= J_BYTES;
-  static constexpr int ACC_OFF(int nstage) { return nstage * STAGE_BYTES; }
-  static constexpr int SV_OFF(int nstage) { return ACC_OFF(nstage) + SLOT_CAP * ACC54 * (int)sizeof(T); }
-  static constexpr int BAR_OFF(int nstage) { return SV_OFF(nstage) + (SV_ALIAS ? 0 : 2 * SV_BYTES); }
-  static constexpr int TOTAL(int nstage) { return BAR_OFF(nstage) + 64; }
-};
-
-// packed upper-triangle index (row-wise, i <= j) -> (i, j)
-__host__ __device__ constexpr int tri_i(int idx) {
-  int i = 0, rem = idx;
-  while (rem >= 9 - i) { rem -= 9 - i; i++; }
-  return i;
-}
-__host__ __device__ constexpr int tri_j(int idx) {
-  int i = 0, rem = idx;
-  while (rem >= 9 - i) { rem -= 9 - i; i++; }
-  return i + rem;
-}
-
-// values [9 G, 9 G + 9) of the 54: G < 5 -> entries of A = Jc^T K, G == 5 -> u = Jc^T q.  All register indices are
-// compile-time constants (a run-time index would push jc / K to local memory).
-template <int IDX> struct Tri {
-  static constexpr int i = tri_i(IDX < 45 ? IDX : 0), j = tri_j(IDX < 45 ? IDX : 0);
-};
-template <typename T, int G, int K9> struct PrepOne {
-  static __device__ __forceinline__ void run(const T *jc, const T *K, T q0, T q1, T *v) {
-    if constexpr (G < 5) {
-      constexpr int i = Tri<G * 9 + K9>::i, j = Tri<G * 9 + K9>::j;
-      v[K9] = jc[2 * i] * K[2 * j] + jc[2 * i + 1] * K[2 * j + 1];
-    } else {
-      v[K9] = jc[2 * K9] * q0 + jc[2 * K9 + 1] * q1;
-    }
-    if constexpr (K9 + 1 < 9) PrepOne<T, G, K9 + 1>::run(jc, K, q0, q1, v);
-  }
-};
-template <typename T, int G> __device__ __forceinline__ void prep_group(const T *jc, const T *K, T q0, T q1, T *v) {
-  PrepOne<T, G, 0>::run(jc, K, q0, q1, v);
-}
-
-// stage v at rank, sum camera segments (one thread per segment and component triple), add into acc columns [goff, goff+9)
-template <typename T>
-__device__ __forceinline__ void worker_cam_accumulate(const T v[9], int rank, int nseg, const uint32_t *sg, T *sv, T *acc,
-                                                      int astride, int goff, int worker, int t) {
-#pragma unroll
-  for (int k = 0; k < 9; k++) sv[rank * 9 + k] = v[k];
-  worker_sync(worker);
-  for (int item = t; item < nseg * 3; item += TILE) {
-    const int q = item / 3, g = item - 3 * q;
-    const uint32_t e0 = sg[q], e1 = sg[q + 1];
-    const int b = (int)(e0 >> 16), e = (int)(e1 >> 16), cs = (int)(e0 & 0xffffu);
-    T a0 = T(0), a1 = T(0), a2 = T(0);
-    for (int row = b; row < e; row++) {
-      const T *r = sv + row * 9 + 3 * g;
-      a0 += r[0];
-      a1 += r[1];
-      a2 += r[2];
-    }
-    T *ar = acc + cs * astride + goff + 3 * g;
-    ar[0] += a0;
-    ar[1] += a1;
-    ar[2] += a2;
-  }
-  worker_sync(worker);
-}
-
-template <typename T, typename S, int NSTAGE>
-__global__ void __launch_bounds__(2 * TILE, 1)
-k_prepare_tiles(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *__restrict__ W,
-                const T *__restrict__ h, T *__restrict__ part /*[nrows][54]*/) {
-  using SM = PrepSmem<T, S>;
-  using S2 = typename V2<S>::type;
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int worker = threadIdx.x >> 8, t = threadIdx.x & (TILE - 1);
-  T *acc = reinterpret_cast<T *>(smem + SM::ACC_OFF(NSTAGE));
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM::BAR_OFF(NSTAGE));
-  const int st_begin = ds.cta_st[blockIdx.x], st_end = ds.cta_st[blockIdx.x + 1]; // persistent CTA, see k_schur_product
-  const int tile0 = ds.st_tile[st_begin], ntl = ds.st_tile[st_end] - tile0;
-
-  auto issue = [&](int tile, int s, int p0, int np) {
-    unsigned char *base = smem + s * SM::STAGE_BYTES;
-    const uint32_t wbytes = (uint32_t)(np * WST<T>::value * (int)sizeof(T));
-    const uint32_t hbytes = (uint32_t)(np * HST * (int)sizeof(T));
-    mbar_expect_tx(&bars[s], (uint32_t)(SM::J_BYTES + REC_BYTES) + wbytes + hbytes);
-    bulk_g2s(base, J + (int64_t)tile * NPLANES * TILE, SM::J_BYTES, &bars[s]);
-    bulk_g2s(base + SM::J_BYTES, ds.trec + (int64_t)tile * REC_BYTES, REC_BYTES, &bars[s]);
-    bulk_g2s(base + SM::J_BYTES + REC_BYTES, W + (int64_t)p0 * WST<T>::value, wbytes, &bars[s]);
-    bulk_g2s(base + SM::J_BYTES + REC_BYTES + SM::W_BYTES, h + (int64_t)p0 * HST, hbytes, &bars[s]);
-  };
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; s++) mbar_init(&bars[s], 1);
-    mbar_fence_init();
-    fence_proxy_async();
-    for (int i = 0; i < NSTAGE && i < ntl; i++) {
-      const TileMeta tm0 = ds.tmeta[tile0 + i];
-      issue(tile0 + i, i, tm0.p0, tm0.np);
-    }
-  }
-  for (int st = st_begin; st < st_end; st++) {
-  const int row0 = ds.st_row[st], nslots = ds.st_row[st + 1] - row0;
-  for (int i = threadIdx.x; i < nslots * ACC54; i += 2 * TILE) acc[i] = T(0);
-  __syncthreads();
-
-  for (int i = ds.st_tile[st] - tile0; i < ds.st_tile[st + 1] - tile0; i++) {
-    const int s = i % NSTAGE;
-    mbar_wait(&bars[s], (uint32_t)((i / NSTAGE) & 1));
-    unsigned char *base = smem + s * SM::STAGE_BYTES;
-    const S2 *Js = reinterpret_cast<const S2 *>(base);
-    const unsigned char *rec = base + SM::J_BYTES;
-    const T *Ws = reinterpret_cast<const T *>(base + SM::J_BYTES + REC_BYTES);
-    const T *Hs = reinterpret_cast<const T *>(base + SM::J_BYTES + REC_BYTES + SM::W_BYTES);
-    const TileMeta tm = *reinterpret_cast<const TileMeta *>(rec + REC_META);
-    const int next_p0 = reinterpret_cast<const int32_t *>(rec + REC_NEXT)[2 * (NSTAGE - 1)];
-    const int next_np = reinterpret_cast<const int32_t *>(rec + REC_NEXT)[2 * (NSTAGE - 1) + 1];
-    const uint32_t om = reinterpret_cast<const uint32_t *>(rec + REC_OMETA)[t];
-    const int ptl = (int)(om & 0xffu);
-    T jc[18], jp[6], K[18];
-#pragma unroll
-    for (int j = 0; j < 9; j++) {
-      const S2 v = Js[j * TILE + t];
-      jc[2 * j] = (T)v.x;
-      jc[2 * j + 1] = (T)v.y;
-    }
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-      const S2 v = Js[(9 + j) * TILE + t];
-      jp[2 * j] = (T)v.x;
-      jp[2 * j + 1] = (T)v.y;
-    }
-    const T *w = Ws + ptl * WST<T>::value;
-    const T w00 = w[0], w01 = w[1], w02 = w[2], w11 = w[3], w12 = w[4], w22 = w[5];
-    // rows of Jp: a = (jp[0], jp[2], jp[4]), b = (jp[1], jp[3], jp[5])
-    const T wa0 = w00 * jp[0] + w01 * jp[2] + w02 * jp[4];
-    const T wa1 = w01 * jp[0] + w11 * jp[2] + w12 * jp[4];
-    const T wa2 = w02 * jp[0] + w12 * jp[2] + w22 * jp[4];
-    const T wb0 = w00 * jp[1] + w01 * jp[3] + w02 * jp[5];
-    const T wb1 = w01 * jp[1] + w11 * jp[3] + w12 * jp[5];
-    const T wb2 = w02 * jp[1] + w12 * jp[3] + w22 * jp[5];
-    const T n00 = jp[0] * wa0 + jp[2] * wa1 + jp[4] * wa2;
-    const T n01 = jp[0] * wb0 + jp[2] * wb1 + jp[4] * wb2;
-    const T n11 = jp[1] * wb0 + jp[3] * wb1 + jp[5] * wb2;
-    const T m00 = T(1) - n00, m01 = -n01, m11 = T(1) - n11;
-#pragma unroll
-    for (int j = 0; j < 9; j++) {
-      K[2 * j] = m00 * jc[2 * j] + m01 * jc[2 * j + 1];
-      K[2 * j + 1] = m01 * jc[2 * j] + m11 * jc[2 * j + 1];
-    }
-    const T *hp = Hs + ptl * HST;
-    const T q0 = jp[0] * hp[0] + jp[2] * hp[1] + jp[4] * hp[2];
-    const T q1 = jp[1] * hp[0] + jp[3] * hp[1] + jp[5] * hp[2];
-    __syncthreads(); // both workers hold the tile in registers: the J region becomes the two staging areas
-    T *sv = reinterpret_cast<T *>((SM::SV_ALIAS ? base : smem + SM::SV_OFF(NSTAGE)) + worker * SM::SV_BYTES);
-    const uint32_t *sg = reinterpret_cast<const uint32_t *>(rec + REC_SEG);
-    T v[9];
-    if (worker == 0) {
-      prep_group<T, 0>(jc, K, q0, q1, v);
-      worker_cam_accumulate<T>(v, t, tm.nseg, sg, sv, acc, ACC54, 0, worker, t);
-      prep_group<T, 1>(jc, K, q0, q1, v);
-      worker_cam_accumulate<T>(v, t, tm.nseg, sg, sv, acc, ACC54, 9, worker, t);
-      prep_group<T, 2>(jc, K, q0, q1, v);
-      worker_cam_accumulate<T>(v, t, tm.nseg, sg, sv, acc, ACC54, 18, worker, t);
-    } else {
-      prep_group<T, 3>(jc, K, q0, q1, v);
-      worker_cam_accumulate<T>(v, t, tm.nseg, sg, sv, acc, ACC54, 27, worker, t);
-      prep_group<T, 4>(jc, K, q0, q1, v);
-      worker_cam_accumulate<T>(v, t, tm.nseg, sg, sv, acc, ACC54, 36, worker, t);
-      prep_group<T, 5>(jc, K, q0, q1, v);
-      worker_cam_accumulate<T>(v, t, tm.nseg, sg, sv, acc, ACC54, 45, worker, t);
-    }
-    __syncthreads(); // both workers are done with the stage
-    if (threadIdx.x == 0 && i + NSTAGE < ntl) {
-      fence_proxy_async();
-      issue(tile0 + i + NSTAGE, s, next_p0, next_np);
-    }
-  }
-  for (int i = threadIdx.x; i < nslots * 54; i += 2 * TILE)
-    part[(int64_t)ds.row_out[row0 + i / 54] * 54 + i % 54] = acc[(i / 54) * ACC54 + i % 54];
-  __syncthreads(); // acc is zeroed again for the next super-tile
-  }
-}
-
-// K3b, camera-major form.  The tile kernel above pushes 54 values per observation through shared-memory staging and
+// (The first implementation, a tile kernel on the same TMA pipeline as the Schur product that pushed the 54 values
+// per observation through shared-memory staging and segment sums, is described in profiles/README.md.)
+// Camera-major form.  The tile kernel pushed 54 values per observation through shared-memory staging and
 // segment sums (ncu: 220 M warp instructions, 17 % FP64 pipe, 20 % DRAM - instruction-bound in the reduction loops).
 // Here one CTA owns a CHUNK of ONE camera's observations (camera-major index built on the host): every thread walks
 // its observations, gathers the 24 Jacobian values from the tile-major store by slot (adjacent slots of one camera

@@ -339,7 +339,7 @@ def test_robust_stages_match_oracle_and_reference(ctx):
 def test_robust_trajectory_matches_reference(ctx, name, solver, huber, weights):
     """Reference runs with HuberLoss(20) / precision matrices: 1e-9 per iteration while lambda >= 1e-11 (below that the
     damping is under the rounding of the unit diagonal and every implementation follows rounding noise, see
-    tests/test_oracle_golden.py), final cost 1e-4."""
+    tests/test_oracle_golden.py), final cost 1e-3."""
     g = golden_json(robust_tag(name, solver, huber, weights) + ".json")
     t = np.array(g["table"])
     prob = synthetic.make_named(name)
@@ -367,7 +367,8 @@ def test_robust_trajectory_matches_reference(ctx, name, solver, huber, weights):
         pass
     assert np.all(r <= tol), (r, tol)
     assert np.array_equal(traj[:n, 0] == traj[:n, 1], t[:n, 1] == t[:n, 2])
-    assert abs(traj[-1, 1] - g["final_chi2"]) <= 1e-4 * g["final_chi2"]
+    # 30+ iterations in the noise regime: the oracle's own final cost moves by 4e-6 .. 1.8e-4 with its thread count
+    assert abs(traj[-1, 1] - g["final_chi2"]) <= 1e-3 * g["final_chi2"]
     P.close()
 
 

@@ -163,7 +163,7 @@ def test_huber_loss_and_precision_matrices_match_reference(built, name, solver, 
     Compared at 1e-9 while lambda >= 1e-11.  These runs accept every step, so lambda falls below the rounding of the
     unit diagonal after ~17 iterations; from there the damped system is numerically singular in the gauge directions
     and every implementation (the reference's float atomics included) follows rounding noise for the remaining 30
-    iterations - the same effect as the FP32 runs at lambda < FP32 epsilon.  The final cost then agrees to 1e-4."""
+    iterations - the same effect as the FP32 runs at lambda < FP32 epsilon.  The final cost then agrees to 1e-3."""
     g = golden_json(robust_tag(name, solver, huber, weights) + ".json")
     init, cur, lam = table(g)
     prob = synthetic.make_named(name)
@@ -176,7 +176,8 @@ def test_huber_loss_and_precision_matrices_match_reference(built, name, solver, 
     # the reference's own run-to-run spread on the Huber + weights case is 1.1e-9 (tests/golden/*.run2.json)
     assert rel.max() <= 5e-9, rel
     assert np.array_equal(traj[:n, 0] == traj[:n, 1], init[:n] == cur[:n])
-    assert abs(traj[-1, 1] - g["final_chi2"]) <= 1e-4 * g["final_chi2"]
+    # 30+ iterations in the noise regime: the oracle's own final cost moves by 4e-6 .. 1.8e-4 with the OpenMP thread count
+    assert abs(traj[-1, 1] - g["final_chi2"]) <= 1e-3 * g["final_chi2"]
 
 
 def test_robust_first_linearisation_matches_reference(built):
