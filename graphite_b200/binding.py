@@ -20,7 +20,7 @@ _NP = {"f32": np.float32, "f64": np.float64}
 # every symbol include/graphite_b200.h declares
 SYMBOLS = [
     "gb_version", "gb_context_create", "gb_context_destroy", "gb_last_error", "gb_comm_unique_id", "gb_comm_init",
-    "gb_problem_create", "gb_problem_destroy", "gb_problem_info", "gb_set_observations", "gb_set_vertices",
+    "gb_problem_create", "gb_problem_destroy", "gb_problem_info", "gb_set_observations", "gb_stage_observations_async", "gb_commit_observations", "gb_set_vertices",
     "gb_get_vertices", "gb_set_loss", "gb_set_precision", "gb_hessian_structure", "gb_linearize", "gb_compute_cost", "gb_get_gradient", "gb_get_scales",
     "gb_get_residuals", "gb_get_jacobians", "gb_hessian_values", "gb_set_damping", "gb_solve", "gb_get_schur_rhs",
     "gb_get_schur_diagonal", "gb_schur_multiply", "gb_schur_structure", "gb_schur_values", "gb_try_step", "gb_revert_step", "gb_lm", "gb_kernel_launches",
@@ -48,7 +48,8 @@ class SolveInfo(C.Structure):
 class LMOptions(C.Structure):
     _fields_ = [("initial_damping", C.c_double), ("iterations", C.c_int64), ("use_identity", C.c_int32),
                 ("verbose", C.c_int32), ("pcg", PcgOptions), ("stop_flag", C.POINTER(C.c_int32)),
-                ("resume", C.c_int32), ("profile_product", C.c_int32), ("initial_nu", C.c_double)]
+                ("resume", C.c_int32), ("profile_product", C.c_int32), ("initial_nu", C.c_double),
+                ("defer_final_linearize", C.c_int32), ("reserved2", C.c_int32)]
 
 
 class LMResult(C.Structure):
@@ -90,6 +91,8 @@ def load_library():
     L.gb_problem_info.argtypes = [vp, C.POINTER(C.c_int64)]
     L.gb_set_observations.argtypes = [vp, vp]
     L.gb_set_vertices.argtypes = [vp, vp, vp]
+    L.gb_stage_observations_async.argtypes = [vp, vp, C.c_int]
+    L.gb_commit_observations.argtypes = [vp, C.c_int]
     L.gb_get_vertices.argtypes = [vp, vp, vp]
     L.gb_set_loss.argtypes = [vp, C.c_int, C.c_double]
     L.gb_set_precision.argtypes = [vp, vp]
@@ -229,6 +232,13 @@ class Problem:
     def set_observations_raw(self, obs_ptr: int):
         self.ctx.check(self.L.gb_set_observations(self.h, C.c_void_p(obs_ptr)))
 
+    def stage_observations_async(self, obs_ptr: int, slot: int):
+        """Start the H2D copy of a pinned host buffer ([n_obs][2] of T) into staging slot 0/1; returns at once."""
+        self.ctx.check(self.L.gb_stage_observations_async(self.h, C.c_void_p(obs_ptr), slot))
+
+    def commit_observations(self, slot: int):
+        self.ctx.check(self.L.gb_commit_observations(self.h, slot))
+
     def get_vertices(self):
         c = np.empty((self.n_cams, 9), dtype=self.T)
         p = np.empty((self.n_pts, 3), dtype=self.T)
@@ -330,10 +340,11 @@ class Problem:
         self.ctx.check(self.L.gb_revert_step(self.h))
 
     def lm(self, iterations=50, initial_damping=1e-4, pcg_iterations=10, pcg_tolerance=1.0, rejection_ratio=5.0,
-           use_identity=False, verbose=False, resume=False, initial_nu=2.0, profile_product=False, solver="pcg-schur"):
+           use_identity=False, verbose=False, resume=False, initial_nu=2.0, profile_product=False, solver="pcg-schur",
+           defer_final_linearize=False):
         o = LMOptions(initial_damping, iterations, int(use_identity), int(verbose),
                       PcgOptions(pcg_iterations, pcg_tolerance, rejection_ratio, SOLVERS[solver], 0), None, int(resume),
-                      int(profile_product), float(initial_nu))
+                      int(profile_product), float(initial_nu), int(defer_final_linearize), 0)
         res = LMResult()
         traj = np.zeros((max(iterations, 1), 4))
         self.ctx.check(self.L.gb_lm(self.h, C.byref(o), C.byref(res), _ptr(traj)))

@@ -55,6 +55,7 @@ constexpr int NCCL_INT8 = 0, NCCL_INT32 = 2, NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8,
 struct gb_context {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr; // uploads that overlap the compute stream (gb_stage_observations_async)
   std::string err;
   int64_t launches = 0;
   ncclComm_t comm = nullptr;
@@ -91,6 +92,8 @@ struct ProblemBase {
   virtual ~ProblemBase() {}
   virtual int init() = 0;
   virtual int set_observations(const void *) = 0;
+  virtual int stage_observations_async(const void *, int) = 0;
+  virtual int commit_observations(int) = 0;
   virtual int set_vertices(const void *, const void *) = 0;
   virtual int set_loss(int, double) = 0;
   virtual int set_precision(const void *) = 0;
@@ -128,6 +131,9 @@ template <typename T, typename S> struct Problem : ProblemBase {
   T *cams = nullptr, *pts = nullptr, *cams_bak = nullptr, *pts_bak = nullptr;
   T *camx = nullptr; // [Nc][CAMX] per-camera precomputed model terms (k_cam_precompute)
   T2 *obs = nullptr, *res = nullptr, *obs_stage = nullptr; // obs/res per storage slot; stage in caller order
+  T2 *obs_stage2[2] = {nullptr, nullptr};                   // double-buffered staging of the asynchronous upload
+  cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+  bool staged[2] = {false, false};
   const int64_t *d_perm = nullptr;                          // sorted position -> caller index (null = identity)
   S2 *J = nullptr; // tile-major [ntiles][12][256]
   T *Cg = nullptr, *part18 = nullptr, *part54 = nullptr, *part9 = nullptr, *sums54 = nullptr;
@@ -196,6 +202,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     if (h_p2p_err) cudaFreeHost(h_p2p_err);
     for (auto &e : ev) if (e) cudaEventDestroy(e);
     for (auto &e : prof_ev) cudaEventDestroy(e);
+    for (auto &e : ev_stage) if (e) cudaEventDestroy(e);
   }
   int64_t device_bytes() const override { return bytes; }
   int exchange_mode() const override { return ctx->nranks <= 1 ? 0 : (p2p_on ? 2 : 1); }
@@ -384,6 +391,12 @@ template <typename T, typename S> struct Problem : ProblemBase {
     return GB_OK;
   }
 
+  // device -> pinned host without the copy engine (k_store_host)
+  int store_host(void *host_dst, const void *src, size_t bytes) {
+    k_store_host<<<1, 32, 0, ctx->stream>>>((uint32_t *)host_dst, (const uint32_t *)src, (int)(bytes / 4));
+    GB_LAUNCH(ctx);
+    return GB_OK;
+  }
   int ensure_state_cap(int64_t max_iter) {
     const int need = (int)(2 * max_iter + 3);
     if (need > pcg_state_cap) {
@@ -436,11 +449,42 @@ template <typename T, typename S> struct Problem : ProblemBase {
     linearized = prepared = solved = stepped = false;
     return GB_OK;
   }
+  // Double-buffered observation upload on the context's copy stream: the H2D copy of the NEXT batch overlaps whatever
+  // the compute stream is doing (the LM iteration on the current batch).  stage -> returns at once; commit -> the compute
+  // stream waits for that slot's copy and scatters it into the tile-padded storage.  The host buffer must be pinned
+  // and stay valid until the commit.
+  int stage_observations_async(const void *o, int slot) override {
+    if (slot < 0 || slot > 1) return ctx->fail(GB_ERR_INVALID, "staging slot must be 0 or 1");
+    if (!obs_stage2[slot]) {
+      GB_TRY(dalloc(obs_stage2[slot], hs.M));
+      GB_CUDA(ctx, cudaEventCreateWithFlags(&ev_stage[slot], cudaEventDisableTiming));
+      GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // dalloc's memset is on the compute stream
+    }
+    GB_CUDA(ctx, cudaMemcpyAsync(obs_stage2[slot], o, 2 * hs.M * sizeof(T), cudaMemcpyHostToDevice, ctx->copy_stream));
+    GB_CUDA(ctx, cudaEventRecord(ev_stage[slot], ctx->copy_stream));
+    staged[slot] = true;
+    return GB_OK;
+  }
+  int commit_observations(int slot) override {
+    if (slot < 0 || slot > 1 || !staged[slot]) return ctx->fail(GB_ERR_INVALID, "gb_commit_observations: nothing staged in that slot");
+    GB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_stage[slot], 0));
+    k_scatter_slots<T2><<<(unsigned)((hs.M + 255) / 256), 256, 0, ctx->stream>>>(hs.M, ts.slot_of_obs, d_perm, obs_stage2[slot], obs);
+    GB_LAUNCH(ctx);
+    staged[slot] = false;
+    have_obs = true;
+    linearized = prepared = solved = solved_full = stepped = false;
+    return launch_check();
+  }
   int set_vertices(const void *c, const void *p) override {
     // 9 -> 10 padded rows: a strided 2-D copy, no host staging
     GB_CUDA(ctx, cudaMemcpy2DAsync(cams, CAM_STRIDE * sizeof(T), c, 9 * sizeof(T), 9 * sizeof(T), hs.Nc,
                                    cudaMemcpyHostToDevice, ctx->stream));
     GB_CUDA(ctx, cudaMemcpyAsync(pts, p, 3 * (size_t)hs.Np * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    // Leave the stream on the compute engine: the first kernel after a copy waits on a semaphore the driver appends to
+    // the copy engine's queue at that moment - behind any large upload another stream has queued there meanwhile
+    // (measured: every step waited the full 1.5 ms of the overlapped observation upload, scripts/e2e_probe.py).
+    k_cam_precompute<T><<<(ts.Nc + 127) / 128, 128, 0, ctx->stream>>>(ts.Nc, cams, camx);
+    GB_LAUNCH(ctx);
     GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     have_vertices = true;
     linearized = prepared = solved = stepped = false;
@@ -555,7 +599,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     cudaStream_t st = ctx->stream;
     k_vec_sum<T><<<1, 1024, 0, st>>>(f_part, full_blocks, f_scal);
     GB_LAUNCH(ctx);
-    GB_CUDA(ctx, cudaMemcpyAsync(h_scalars + 4, f_scal, sizeof(T), cudaMemcpyDeviceToHost, st));
+    GB_TRY(store_host(h_scalars + 4, f_scal, sizeof(T)));
     GB_CUDA(ctx, cudaStreamSynchronize(st));
     *out = *reinterpret_cast<const T *>(h_scalars + 4);
     return GB_OK;
@@ -739,10 +783,9 @@ template <typename T, typename S> struct Problem : ProblemBase {
     cudaStream_t st = ctx->stream;
     GB_TRY(ensure_state_cap(o->max_iterations));
     const int gridc = (ts.Nc + PCG_CAMS - 1) / PCG_CAMS;
-    GB_CUDA(ctx, cudaMemsetAsync(done_flag, 0, sizeof(int), st));
     k_pcg_init<T><<<gridc, 288, 0, st>>>(ts.Nc, bS, Minv, scale, x, r, z, pv, xs, rz_part);
     GB_LAUNCH(ctx);
-    k_pcg_init_state<T><<<1, 1024, 0, st>>>(ts.Nc, rz_part, pcg_state);
+    k_pcg_init_state<T><<<1, 1024, 0, st>>>(ts.Nc, rz_part, pcg_state, done_flag);
     GB_LAUNCH(ctx);
     const T tol = (T)o->tolerance, ratio = (T)o->rejection_ratio;
     const int max_iter = (int)o->max_iterations, nc = ts.Nc;
@@ -781,7 +824,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
       }
       if (profiling && 3 * k + 2 < (int64_t)prof_ev.size()) GB_CUDA(ctx, cudaEventRecord(prof_ev[3 * k + 2], st));
     }
-    GB_CUDA(ctx, cudaMemcpyAsync(h_state, pcg_state + 2 * o->max_iterations, sizeof(PcgState<T>), cudaMemcpyDeviceToHost, st));
+    GB_TRY(store_host(h_state, pcg_state + 2 * o->max_iterations, sizeof(PcgState<T>)));
     GB_TRY(launch_check());
     last_pcg = *o;
     solved = true;
@@ -822,7 +865,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
 
   int fetch_scalars() {
     if (ctx->nranks > 1) GB_TRY(exchange<double>(scalars, 2)); // cost and the point part of rho; the camera part is replicated
-    GB_CUDA(ctx, cudaMemcpyAsync(h_scalars, scalars, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GB_TRY(store_host(h_scalars, scalars, 3 * sizeof(double)));
     GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return p2p_check();
   }
@@ -836,7 +879,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
   int linearize(double *chi2) override {
     GB_TRY(require(have_obs && have_vertices, "gb_linearize needs observations and vertices"));
     GB_TRY(enqueue_linearize());
-    GB_CUDA(ctx, cudaMemcpyAsync(h_scalars, scalars, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GB_TRY(store_host(h_scalars, scalars, sizeof(double)));
     GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     last_chi2 = (double)(T)h_scalars[0];
     if (chi2) *chi2 = last_chi2;
@@ -846,7 +889,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_TRY(require(have_obs && have_vertices, "gb_compute_cost needs observations and vertices"));
     GB_TRY(enqueue_cost());
     if (ctx->nranks > 1) GB_TRY(exchange<double>(scalars, 1));
-    GB_CUDA(ctx, cudaMemcpyAsync(h_scalars, scalars, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GB_TRY(store_host(h_scalars, scalars, sizeof(double)));
     GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     GB_TRY(p2p_check());
     if (chi2) *chi2 = (double)(T)h_scalars[0];
@@ -1027,8 +1070,10 @@ template <typename T, typename S> struct Problem : ProblemBase {
   }
   int enqueue_revert() {
     cudaStream_t st = ctx->stream;
-    GB_CUDA(ctx, cudaMemcpyAsync(cams, cams_bak, (size_t)ts.Nc * CAM_STRIDE * sizeof(T), cudaMemcpyDeviceToDevice, st));
-    GB_CUDA(ctx, cudaMemcpyAsync(pts, pts_bak, 3 * (size_t)ts.Np * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    k_copy<T><<<32, 256, 0, st>>>((int64_t)ts.Nc * CAM_STRIDE, cams_bak, cams);
+    GB_LAUNCH(ctx);
+    k_copy<T><<<4 * 148, 256, 0, st>>>(3 * (int64_t)ts.Np, pts_bak, pts);
+    GB_LAUNCH(ctx);
     return GB_OK;
   }
   int revert_step() override {
@@ -1061,7 +1106,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
       GB_CUDA(ctx, cudaEventRecord(ev[0], st));
       GB_TRY(enqueue_linearize());
       GB_CUDA(ctx, cudaEventRecord(ev[1], st));
-      GB_CUDA(ctx, cudaMemcpyAsync(h_scalars, scalars, sizeof(double), cudaMemcpyDeviceToHost, st));
+      GB_TRY(store_host(h_scalars, scalars, sizeof(double)));
       GB_CUDA(ctx, cudaStreamSynchronize(st));
       cudaEventElapsedTime(&ms, ev[0], ev[1]);
       acc[0] += ms;
@@ -1113,12 +1158,17 @@ template <typename T, typename S> struct Problem : ProblemBase {
         mu_l *= (T)alpha;
         nu = T(2);
         mu = mu_l;
-        GB_CUDA(ctx, cudaEventRecord(ev[0], st));
-        GB_TRY(enqueue_linearize(false));
-        GB_CUDA(ctx, cudaEventRecord(ev[1], st));
-        GB_CUDA(ctx, cudaStreamSynchronize(st));
-        cudaEventElapsedTime(&ms, ev[0], ev[1]);
-        acc[0] += ms;
+        if (o->defer_final_linearize && it + 1 >= o->iterations) {
+          // last iteration of this call: whoever needs the linearisation at the new point next computes it
+          linearized = prepared = solved = solved_full = false;
+        } else {
+          GB_CUDA(ctx, cudaEventRecord(ev[0], st));
+          GB_TRY(enqueue_linearize(false));
+          GB_CUDA(ctx, cudaEventRecord(ev[1], st));
+          GB_CUDA(ctx, cudaStreamSynchronize(st));
+          cudaEventElapsedTime(&ms, ev[0], ev[1]);
+          acc[0] += ms;
+        }
         R.accepted++;
       } else {
         GB_TRY(enqueue_revert());
@@ -1224,7 +1274,8 @@ int gb_context_create(int device, gb_context **out) {
   if (prop.major != 10) return GB_ERR_UNSUPPORTED; // kernels are built for sm_100a only
   gb_context *c = new gb_context();
   c->device = device;
-  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete c;
     return GB_ERR_CUDA;
   }
@@ -1237,6 +1288,7 @@ int gb_context_destroy(gb_context *ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
   return GB_OK;
 }
@@ -1398,6 +1450,8 @@ int gb_problem_info(const gb_problem *p, int64_t info[12]) {
   cudaSetDevice((p)->impl->ctx->device)
 
 int gb_set_observations(gb_problem *p, const void *o) { GB_P(p); if (!o) return GB_ERR_INVALID; return p->impl->set_observations(o); }
+int gb_stage_observations_async(gb_problem *p, const void *o, int slot) { GB_P(p); if (!o) return GB_ERR_INVALID; return p->impl->stage_observations_async(o, slot); }
+int gb_commit_observations(gb_problem *p, int slot) { GB_P(p); return p->impl->commit_observations(slot); }
 int gb_set_vertices(gb_problem *p, const void *c, const void *q) { GB_P(p); if (!c || !q) return GB_ERR_INVALID; return p->impl->set_vertices(c, q); }
 int gb_get_vertices(gb_problem *p, void *c, void *q) { GB_P(p); return p->impl->get_vertices(c, q); }
 int gb_set_loss(gb_problem *p, int kind, double delta) { GB_P(p); return p->impl->set_loss(kind, delta); }

@@ -104,6 +104,13 @@ int gb_problem_info(const gb_problem *p, int64_t info[12]);
  * (examples/bal.cu:118-125), pts [n_pts][3], obs [n_obs][2]. */
 int gb_set_observations(gb_problem *p, const void *obs_host);
 int gb_set_vertices(gb_problem *p, const void *cams_host, const void *pts_host);
+/* Streaming form of gb_set_observations for callers that feed a new observation batch per solve (sliding-window /
+ * incremental use, docs/markdown/main.md "FastLoop"): gb_stage_observations_async starts the host-to-device copy of a
+ * PINNED host buffer into staging slot 0 or 1 on a second stream and returns at once, so the copy overlaps the LM
+ * iterations running on the previous batch; gb_commit_observations makes the compute stream wait for that slot and
+ * installs it (later calls use the new observations).  The host buffer must stay valid until the commit. */
+int gb_stage_observations_async(gb_problem *p, const void *obs_pinned_host, int slot);
+int gb_commit_observations(gb_problem *p, int slot);
 /* Replaces the loss_func and precision_matrix arguments of add_factor (factor.hpp:373-412; loss.hpp:15-51):
  *   chi2_f = loss(r^T P r), H += loss' J^T P J, b -= loss' J^T P r (ops/chi2.hpp:9-44, ops/hessian.hpp:58-76).
  * One loss for all factors: GB_LOSS_DEFAULT (identity) or GB_LOSS_HUBER(delta).  precision_host: [n_obs][4] row-major
@@ -198,6 +205,12 @@ typedef struct {
   int32_t resume;
   int32_t profile_product;  /* != 0: CUDA-event time every launch of the matrix-free Schur product kernel */
   double initial_nu;
+  /* != 0: when the LAST iteration of this call accepts its step, the re-linearisation at the new point
+   * (levenberg_marquardt.hpp:192-195) is left to whoever needs it next (the next gb_lm / gb_linearize, or an export) instead
+   * of being done before returning.  For callers that run one iteration per call and upload fresh vertices in between,
+   * where that linearisation would be computed twice. */
+  int32_t defer_final_linearize;
+  int32_t reserved2;
 } gb_lm_options;
 
 typedef struct {

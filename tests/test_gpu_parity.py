@@ -425,6 +425,38 @@ def test_runs_are_bit_reproducible(ctx):
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
 
 
+def test_staged_observation_upload_and_deferred_linearisation(ctx):
+    """gb_stage_observations_async / gb_commit_observations give the same state as gb_set_observations, and a call that
+    defers its final re-linearisation continues bit-identically."""
+    import torch
+    prob = synthetic.make_named("ladybug-49")
+    P = binding.problem_from_bal(ctx, prob, "f64-f64")
+    chi2 = P.linearize()
+    shifted = torch.from_numpy(np.ascontiguousarray(prob.obs + 0.25)).pin_memory()
+    same = torch.from_numpy(np.ascontiguousarray(prob.obs)).pin_memory()
+    P.stage_observations_async(shifted.data_ptr(), 0)
+    P.stage_observations_async(same.data_ptr(), 1)
+    assert P.compute_cost() == chi2, "staged observations take effect only at the commit"
+    P.commit_observations(0)
+    c_shift = P.linearize()
+    P2 = binding.problem_from_bal(ctx, synthetic.BALProblem(prob.cam_idx, prob.pt_idx, prob.obs + 0.25, prob.cams, prob.pts, "s"), "f64-f64")
+    assert c_shift == P2.linearize() and c_shift != chi2
+    P.commit_observations(1)
+    assert P.linearize() == chi2
+    with pytest.raises(binding.GraphiteB200Error, match="nothing staged"):
+        P.commit_observations(1)
+    # one call of 6 iterations == 6 calls of one iteration with the final linearisation deferred to the next call
+    t6, _ = P.lm(iterations=6)
+    P.set_vertices(prob.cams, prob.pts)
+    mu, nu, rows = 1e-4, 2.0, []
+    for k in range(6):
+        t1, r1 = P.lm(iterations=1, initial_damping=mu, initial_nu=nu, resume=k > 0, defer_final_linearize=True)
+        mu, nu = r1["final_damping"], r1["final_nu"]
+        rows.append(t1[0])
+    assert np.array_equal(np.array(rows), t6)
+    P.close(); P2.close()
+
+
 def test_revert_restores_the_state_exactly(ctx):
     prob = synthetic.make_named("ladybug-49")
     P = binding.problem_from_bal(ctx, prob, "f64-f64")
