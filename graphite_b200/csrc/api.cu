@@ -162,7 +162,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
   int ncamblocks = 0;
   gb_pcg_options last_pcg{10, 1.0, 5.0, 0, 0};
   int64_t dimc = 0, dimH = 0;
-  cudaEvent_t ev[8];
+  cudaEvent_t ev[10]; // [8], [9]: around the re-linearisation of an accepted step (read at the next synchronisation)
   double last_chi2 = 0.0;
   bool profiling = false;
   std::vector<cudaEvent_t> prof_ev; // pairs around k_schur_tiles<MODE 0>, one pair per PCG iteration
@@ -834,7 +834,8 @@ template <typename T, typename S> struct Problem : ProblemBase {
   }
 
   // back-substitution (+ optional application of the step) ; fills delta and the rho partials
-  int enqueue_step(bool apply) {
+  // sums = false: the caller runs enqueue_cost(true) next, which sums the rho partials together with the cost
+  int enqueue_step(bool apply, bool sums = true) {
     cudaStream_t st = ctx->stream;
     // camera part: delta_c = x, xs = D x, rho, (apply) cams += D x
     k_cam_step<T><<<ncamblocks, 256, 0, st>>>((int)dimc, x, scale, b, mu, xs, cams, cams_bak, delta, rho_part + ts.ntiles,
@@ -843,21 +844,28 @@ template <typename T, typename S> struct Problem : ProblemBase {
     k_backsubst_tiles<T, S><<<ts.ntiles, TILE, 0, st>>>(ts, J, W, xs, h, scale + dimc, b + dimc, mu, pts, pts_bak,
                                                         delta + dimc, rho_part, apply ? 1 : 0);
     GB_LAUNCH(ctx);
-    k_sum_partials<<<1, 1024, 0, st>>>(rho_part, ts.ntiles, scalars, 1);
-    GB_LAUNCH(ctx);
-    k_sum_partials<<<1, 1024, 0, st>>>(rho_part + ts.ntiles, ncamblocks, scalars, 2);
-    GB_LAUNCH(ctx);
+    if (sums) {
+      k_sum_partials<<<1, 1024, 0, st>>>(rho_part, ts.ntiles, scalars, 1);
+      GB_LAUNCH(ctx);
+      k_sum_partials<<<1, 1024, 0, st>>>(rho_part + ts.ntiles, ncamblocks, scalars, 2);
+      GB_LAUNCH(ctx);
+    }
     GB_TRY(launch_check());
     return GB_OK;
   }
 
-  int enqueue_cost() {
+  int enqueue_cost(bool with_rho = false) {
     cudaStream_t st = ctx->stream;
     k_cam_precompute<T><<<(ts.Nc + 127) / 128, 128, 0, st>>>(ts.Nc, cams, camx);
     GB_LAUNCH(ctx);
     k_cost_tiles<T><<<ts.ntiles, TILE, 0, st>>>(ts, camx, pts, obs, cost_part, rb);
     GB_LAUNCH(ctx);
-    k_sum_partials<<<1, 1024, 0, st>>>(cost_part, ts.ntiles, scalars, 0);
+    if (with_rho && !solved_full) { // cost and both rho sums of the Schur path in one launch
+      k_sum_partials3<<<3, 1024, 0, st>>>(SumJob{cost_part, ts.ntiles, 0}, SumJob{rho_part, ts.ntiles, 1},
+                                          SumJob{rho_part + ts.ntiles, ncamblocks, 2}, scalars);
+    } else {
+      k_sum_partials<<<1, 1024, 0, st>>>(cost_part, ts.ntiles, scalars, 0);
+    }
     GB_LAUNCH(ctx);
     GB_TRY(launch_check());
     return GB_OK;
@@ -1060,8 +1068,8 @@ template <typename T, typename S> struct Problem : ProblemBase {
   int try_step(double *new_chi2, double *rho_den) override {
     GB_TRY(require(solved || solved_full, "gb_try_step before gb_solve"));
     if (solved_full) GB_TRY(enqueue_step_full(true));
-    else GB_TRY(enqueue_step(true));
-    GB_TRY(enqueue_cost());
+    else GB_TRY(enqueue_step(true, false));
+    GB_TRY(enqueue_cost(!solved_full));
     GB_TRY(fetch_scalars());
     stepped = true;
     if (new_chi2) *new_chi2 = (double)(T)h_scalars[0];
@@ -1116,6 +1124,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     }
     R.initial_chi2 = (double)chi2;
     bool run = true;
+    bool lin_pending = false; // an accepted step's re-linearisation is in flight; its time is read after the next sync
     int64_t it = 0;
     for (; it < o->iterations && run; it++) {
       mu = mu_l;
@@ -1126,11 +1135,12 @@ template <typename T, typename S> struct Problem : ProblemBase {
       else GB_TRY(enqueue_pcg(&o->pcg));
       GB_CUDA(ctx, cudaEventRecord(ev[2], st));
       if (full) GB_TRY(enqueue_step_full(true));
-      else GB_TRY(enqueue_step(true));
+      else GB_TRY(enqueue_step(true, false));
       GB_CUDA(ctx, cudaEventRecord(ev[3], st));
-      GB_TRY(enqueue_cost());
+      GB_TRY(enqueue_cost(!full));
       GB_CUDA(ctx, cudaEventRecord(ev[4], st));
       GB_TRY(fetch_scalars());
+      if (lin_pending) { cudaEventElapsedTime(&ms, ev[8], ev[9]); acc[0] += ms; lin_pending = false; }
       cudaEventElapsedTime(&ms, ev[0], ev[1]); acc[1] += ms;
       cudaEventElapsedTime(&ms, ev[1], ev[2]); acc[2] += ms;
       cudaEventElapsedTime(&ms, ev[2], ev[3]); acc[3] += ms;
@@ -1162,12 +1172,11 @@ template <typename T, typename S> struct Problem : ProblemBase {
           // last iteration of this call: whoever needs the linearisation at the new point next computes it
           linearized = prepared = solved = solved_full = false;
         } else {
-          GB_CUDA(ctx, cudaEventRecord(ev[0], st));
+          // no host synchronisation here: the next iteration is enqueued while this linearisation runs
+          GB_CUDA(ctx, cudaEventRecord(ev[8], st));
           GB_TRY(enqueue_linearize(false));
-          GB_CUDA(ctx, cudaEventRecord(ev[1], st));
-          GB_CUDA(ctx, cudaStreamSynchronize(st));
-          cudaEventElapsedTime(&ms, ev[0], ev[1]);
-          acc[0] += ms;
+          GB_CUDA(ctx, cudaEventRecord(ev[9], st));
+          lin_pending = true;
         }
         R.accepted++;
       } else {
@@ -1191,6 +1200,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     }
     GB_CUDA(ctx, cudaEventRecord(ev[7], st));
     GB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (lin_pending) { cudaEventElapsedTime(&ms, ev[8], ev[9]); acc[0] += ms; lin_pending = false; }
     cudaEventElapsedTime(&ms, ev[6], ev[7]);
     stepped = false;
     profiling = false;

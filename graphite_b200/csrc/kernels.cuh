@@ -495,6 +495,18 @@ template <typename V> __global__ void k_copy(int64_t n, const V *__restrict__ sr
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
+// Up to three deterministic partial sums in one launch (block b sums array b): cost, rho of the points, rho of the
+// cameras at the end of an LM trial step.  Same per-array order as k_sum_partials.
+struct SumJob { const double *part; int n; int out_idx; };
+__global__ void __launch_bounds__(1024) k_sum_partials3(SumJob j0, SumJob j1, SumJob j2, double *__restrict__ out) {
+  __shared__ double shd[32];
+  const SumJob j = blockIdx.x == 0 ? j0 : (blockIdx.x == 1 ? j1 : j2);
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < j.n; i += blockDim.x) acc += j.part[i];
+  const double tot = block_sum<double>(acc, shd);
+  if (threadIdx.x == 0) out[j.out_idx] = tot;
+}
+
 // Deterministic sum of partials (single CTA).
 __global__ void k_sum_partials(const double *__restrict__ part, int n, double *__restrict__ out, int out_idx) {
   __shared__ double shd[32];
