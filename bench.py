@@ -287,7 +287,7 @@ def main():
     n_prod = max(int(res["product_launches"]), 1)
     prod_ms = 1e3 * res["product_seconds"] / n_prod
     achieved = prod_bytes / (prod_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_schur_product (matrix-free Schur product, TMA-staged, one launch per PCG iteration)",
+    roofline = {"bound": "hbm", "kernel": "k_schur_product2 (matrix-free Schur product, TMA: 2 J slots + 4-deep record ring, one launch per PCG iteration)",
                 "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "bytes_per_launch": prod_bytes, "launches_timed": int(res["product_launches"]), "ms_per_launch": prod_ms,
