@@ -141,6 +141,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
   bool coop_update = false; // the fused PCG update needs all its CTAs co-resident
   bool fused_iter = false;  // reduction + exchange + update of one PCG iteration in one cooperative launch (k_pcg_iterate)
   int iter_grid = 0;
+  bool iter_pre = true;
   T *cta_part = nullptr;
   T *diagB = nullptr, *gc = nullptr, *scale = nullptr /*[9Nc+3Np]*/, *b = nullptr /*[9Nc+3Np]*/;
   T *W = nullptr, *h = nullptr;
@@ -272,9 +273,13 @@ template <typename T, typename S> struct Problem : ProblemBase {
       GB_CUDA(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
       GB_CUDA(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
       coop_update = coop && (int64_t)per_sm * sms >= (Nc + PCG_CAMS - 1) / PCG_CAMS;
-      int per_sm2 = 0;
-      GB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_pcg_iterate<T>, PIT_THREADS, 0));
-      iter_grid = (int)std::min<int64_t>(std::min<int64_t>(2 * sms, (int64_t)per_sm2 * sms), (Nc + PIT_WARPS - 1) / PIT_WARPS);
+      // one camera per warp with the prefetching variant when the grid allows it, else the lean variant on a larger grid
+      int per_sm2 = 0, per_sm4 = 0;
+      GB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_pcg_iterate<T, true>, PIT_THREADS, 0));
+      GB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm4, k_pcg_iterate<T, false>, PIT_THREADS, 0));
+      const int64_t want = (Nc + PIT_WARPS - 1) / PIT_WARPS;
+      iter_pre = want <= (int64_t)std::min(2, per_sm2) * sms;
+      iter_grid = (int)std::min<int64_t>(want, (int64_t)(iter_pre ? std::min(2, per_sm2) : std::min(4, per_sm4)) * sms);
       const char *env = getenv("GB_FUSED_ITER");
       fused_iter = coop && iter_grid >= 1 && !(env && env[0] == '0');
       GB_TRY(dalloc(cta_part, 2 * (size_t)std::max(iter_grid, 1)));
@@ -800,7 +805,8 @@ template <typename T, typename S> struct Problem : ProblemBase {
                         (void *)&c_scale, (void *)&c_dterm, (void *)&c_Minv, (void *)&x, (void *)&xbak, (void *)&r,
                         (void *)&z, (void *)&pv, (void *)&xs, (void *)&Ap, (void *)&cta_part, (void *)&done_flag,
                         (void *)&pp, (void *)&multi};
-        GB_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)k_pcg_iterate<T>, dim3(iter_grid), dim3(PIT_THREADS), args, 0, st));
+        const void *fn = iter_pre ? (const void *)k_pcg_iterate<T, true> : (const void *)k_pcg_iterate<T, false>;
+        GB_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(iter_grid), dim3(PIT_THREADS), args, 0, st));
         GB_LAUNCH(ctx);
       } else if (coop_update) {
         // both halves of the vector update in one cooperative launch (grid-wide sync instead of a kernel boundary)

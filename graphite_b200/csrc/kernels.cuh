@@ -1543,8 +1543,11 @@ template <typename T> __device__ __forceinline__ T grid_total(const T *cta_part,
   return block_sum<T>(acc, sh);
 }
 
-template <typename T>
-__global__ void __launch_bounds__(PIT_THREADS)
+// PRE = true (every warp owns at most one camera, Nc <= grid * 8): everything phase 2 needs is prefetched into registers
+// during the row gather (96 registers, 2 CTAs per SM).  PRE = false (more cameras): no prefetch, 64 registers, 4 CTAs per
+// SM, i.e. twice the warps to walk the cameras (Final-13682: 100 us -> see profiles/README.md).
+template <typename T, bool PRE>
+__global__ void __launch_bounds__(PIT_THREADS, PRE ? 2 : 4)
 k_pcg_iterate(DevStruct ds, PcgState<T> *st /*in: st[0], out: st[2]*/, T tol, T ratio, int max_iter,
               const T *__restrict__ part /*[nrows][9]*/, const T *__restrict__ scale_c, const T *__restrict__ dterm,
               const T *__restrict__ Minv, T *x, T *xbak, T *r, T *z, T *p, T *xs, T *Ap, T *cta_part /*[2][grid]*/,
@@ -1579,9 +1582,9 @@ k_pcg_iterate(DevStruct ds, PcgState<T> *st /*in: st[0], out: st[2]*/, T tol, T 
   const unsigned long long epoch = multi ? p2p_next_epoch(pp) : 0ull;
   // the warp's first camera (its only one when Nc <= grid * warps): everything phase 2 needs is fetched now, so that the
   // loads overlap the row gather instead of following the grid barrier
-  const int c_first = c_begin + warp;
+  const int c_first = PRE ? c_begin + warp : -1;
   T m_pre[9], x_pre = T(0), r_pre = T(0), p_pre = T(0), sc_pre = T(0), dt_pre = T(0);
-  if (own && c_first < c_end) {
+  if (PRE && own && c_first < c_end) {
     const T *m = Minv + (int64_t)c_first * 81;
 #pragma unroll
     for (int j = 0; j < 9; j++) m_pre[j] = m[k + 9 * j];
