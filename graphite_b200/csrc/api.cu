@@ -156,6 +156,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
   double *h_scalars = nullptr;
   PcgState<T> *h_state = nullptr;
   // flags
+  bool camx_valid = false; // camx holds the precomputed camera-model terms of the current cameras
   bool have_obs = false, have_vertices = false, linearized = false, prepared = false, solved = false, stepped = false;
   bool scale_on = true;
   T mu = T(1e-4);
@@ -490,6 +491,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     // (measured: every step waited the full 1.5 ms of the overlapped observation upload, scripts/e2e_probe.py).
     k_cam_precompute<T><<<(ts.Nc + 127) / 128, 128, 0, ctx->stream>>>(ts.Nc, cams, camx);
     GB_LAUNCH(ctx);
+    camx_valid = true;
     GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     have_vertices = true;
     linearized = prepared = solved = stepped = false;
@@ -542,12 +544,18 @@ template <typename T, typename S> struct Problem : ProblemBase {
     return GB_OK;
   }
 
+  int ensure_camx() {
+    if (camx_valid) return GB_OK;
+    k_cam_precompute<T><<<(ts.Nc + 127) / 128, 128, 0, ctx->stream>>>(ts.Nc, cams, camx);
+    GB_LAUNCH(ctx);
+    camx_valid = true;
+    return GB_OK;
+  }
   // need_cost = false: the caller does not read chi2 of this linearisation (the accepted-step path of the LM loop
   // already has it from the trial step), so its cross-rank sum is skipped
   int enqueue_linearize(bool need_cost = true) {
     cudaStream_t st = ctx->stream;
-    k_cam_precompute<T><<<(ts.Nc + 127) / 128, 128, 0, st>>>(ts.Nc, cams, camx);
-    GB_LAUNCH(ctx);
+    GB_TRY(ensure_camx());
     k_linearize<T, S><<<ts.nst, TILE, smem_lin_bytes<T>(), st>>>(ts, camx, pts, obs, J, res, Cg, part18, cost_part, rb);
     GB_LAUNCH(ctx);
     const bool multi = ctx->nranks > 1;
@@ -696,6 +704,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     k_cam_step<T><<<ncamblocks, 256, 0, st>>>((int)dimc, f_x, scale, b, mu, xs, cams, cams_bak, delta, rho_part + ts.ntiles,
                                               apply ? 1 : 0);
     GB_LAUNCH(ctx);
+    if (apply) camx_valid = false;
     const int64_t n3 = 3 * (int64_t)ts.Np;
     const int nb = (int)((n3 + 255) / 256);
     k_full_point_step<T><<<nb, 256, 0, st>>>(n3, f_x + dimc, scale + dimc, b + dimc, mu, pts, pts_bak, delta + dimc, f_rho,
@@ -847,6 +856,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     k_cam_step<T><<<ncamblocks, 256, 0, st>>>((int)dimc, x, scale, b, mu, xs, cams, cams_bak, delta, rho_part + ts.ntiles,
                                               apply ? 1 : 0);
     GB_LAUNCH(ctx);
+    if (apply) camx_valid = false;
     k_backsubst_tiles<T, S><<<ts.ntiles, TILE, 0, st>>>(ts, J, W, xs, h, scale + dimc, b + dimc, mu, pts, pts_bak,
                                                         delta + dimc, rho_part, apply ? 1 : 0);
     GB_LAUNCH(ctx);
@@ -862,8 +872,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
 
   int enqueue_cost(bool with_rho = false) {
     cudaStream_t st = ctx->stream;
-    k_cam_precompute<T><<<(ts.Nc + 127) / 128, 128, 0, st>>>(ts.Nc, cams, camx);
-    GB_LAUNCH(ctx);
+    GB_TRY(ensure_camx());
     k_cost_tiles<T><<<ts.ntiles, TILE, 0, st>>>(ts, camx, pts, obs, cost_part, rb);
     GB_LAUNCH(ctx);
     if (with_rho && !solved_full) { // cost and both rho sums of the Schur path in one launch
@@ -1086,6 +1095,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     cudaStream_t st = ctx->stream;
     k_copy<T><<<32, 256, 0, st>>>((int64_t)ts.Nc * CAM_STRIDE, cams_bak, cams);
     GB_LAUNCH(ctx);
+    camx_valid = false;
     k_copy<T><<<4 * 148, 256, 0, st>>>(3 * (int64_t)ts.Np, pts_bak, pts);
     GB_LAUNCH(ctx);
     return GB_OK;

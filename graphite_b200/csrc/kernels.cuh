@@ -337,25 +337,38 @@ k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
   const int row0 = ds.st_row[st], nslots = ds.st_row[st + 1] - row0;
   for (int i = t; i < nslots * 18; i += TILE) acc[i] = T(0);
   __syncthreads();
-  for (int tile = ds.st_tile[st]; tile < ds.st_tile[st + 1]; tile++) {
+  // the per-slot inputs of the NEXT tile (meta word, camera, observation) are fetched one tile ahead, so that a tile
+  // starts with the camera / point gathers instead of a chain of dependent loads
+  const int tile_end = ds.st_tile[st + 1];
+  int64_t slot_n = (int64_t)ds.st_tile[st] * TILE + t;
+  uint32_t om_n = ds.ometa[slot_n];
+  int c_n = ds.tile_cam[slot_n];
+  typename V2<T>::type ov_n = obs[slot_n];
+  for (int tile = ds.st_tile[st]; tile < tile_end; tile++) {
     // the record is consumed after the first barrier below; its load overlaps the arithmetic
     if (t < REC_BYTES / 16)
       reinterpret_cast<uint4 *>(rec)[t] = __ldg(reinterpret_cast<const uint4 *>(ds.trec + (int64_t)tile * REC_BYTES) + t);
     const TileMeta tm = ds.tmeta[tile];
     const int64_t slot = (int64_t)tile * TILE + t;
-    const uint32_t om = ds.ometa[slot];
+    const uint32_t om = om_n;
+    const int c = c_n;
+    const typename V2<T>::type ov = ov_n;
+    if (tile + 1 < tile_end) {
+      om_n = ds.ometa[slot + TILE];
+      c_n = ds.tile_cam[slot + TILE];
+      ov_n = obs[slot + TILE];
+    }
     const int rank = (int)((om >> 8) & 0xffu), ptl = (int)(om & 0xffu);
     const bool active = t < tm.n;
     BalObs<T> B;
     double cost = 0.0;
     if (active) {
-      const int c = ds.tile_cam[slot], p = tm.p0 + ptl;
+      const int p = tm.p0 + ptl;
       T cx[CAMX], X[3], ob[2];
       load_camx<T>(cams, c, cx); // `cams` is the per-camera precomputed table (k_cam_precompute)
       X[0] = pts[3 * (int64_t)p];
       X[1] = pts[3 * (int64_t)p + 1];
       X[2] = pts[3 * (int64_t)p + 2];
-      const typename V2<T>::type ov = obs[slot];
       ob[0] = ov.x;
       ob[1] = ov.y;
       bal_residual_jacobian_pre<T>(cx, X, ob, B);
@@ -542,9 +555,10 @@ __global__ void k_point_prepare(int Np, int scale_on, T mu, int use_identity, co
     s1 = (T)(1.0 / (DBL_EPSILON + sqrt((double)c11)));
     s2 = (T)(1.0 / (DBL_EPSILON + sqrt((double)c22)));
   }
-  if (write_lin) {
+  if (write_lin) { // linearize: only the mu-independent part; W and h are computed by the call in prepare
     scale_p[3 * (int64_t)p] = s0; scale_p[3 * (int64_t)p + 1] = s1; scale_p[3 * (int64_t)p + 2] = s2;
     b_p[3 * (int64_t)p] = s0 * g0; b_p[3 * (int64_t)p + 1] = s1 * g1; b_p[3 * (int64_t)p + 2] = s2 * g2;
+    return;
   }
   // scaled, damped C
   const T a00 = damp_value<T>(s0 * s0 * c00, mu, use_identity);
