@@ -873,7 +873,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
   int enqueue_cost(bool with_rho = false) {
     cudaStream_t st = ctx->stream;
     GB_TRY(ensure_camx());
-    k_cost_tiles<T><<<ts.ntiles, TILE, 0, st>>>(ts, camx, pts, obs, cost_part, rb);
+    k_cost_tiles<T><<<(ts.ntiles + COST_TILES - 1) / COST_TILES, TILE, 0, st>>>(ts, camx, pts, obs, cost_part, rb);
     GB_LAUNCH(ctx);
     if (with_rho && !solved_full) { // cost and both rho sums of the Schur path in one launch
       k_sum_partials3<<<3, 1024, 0, st>>>(SumJob{cost_part, ts.ntiles, 0}, SumJob{rho_part, ts.ntiles, 1},

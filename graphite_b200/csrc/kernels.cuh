@@ -46,6 +46,7 @@ constexpr int NPLANES = 12;
 #ifndef LIN_MIN_BLOCKS
 #define LIN_MIN_BLOCKS 2
 #endif
+constexpr int COST_TILES = 4; // tiles per CTA of k_cost_tiles
 constexpr int LIN_STR = 19; // staging row stride of k_linearize (18 values; odd stride: conflict-free 64-bit rows)
 template <typename T> constexpr int smem_lin_bytes() { // staging, accumulator rows, tile record
   return (TILE * LIN_STR + SLOT_CAP * 18) * (int)sizeof(T) + 16 + REC_BYTES;
@@ -1782,27 +1783,44 @@ template <typename T>
 __global__ void __launch_bounds__(TILE)
 k_cost_tiles(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
              const typename V2<T>::type *__restrict__ obs, double *__restrict__ cost_part /*[ntiles]*/, Robust rb) {
+  // COST_TILES consecutive tiles per CTA; the slot inputs of the next tile are fetched while the current one is
+  // evaluated (one tile per CTA spent most of its time in the chain index -> camera / point gather -> arithmetic).
+  // The per-tile partial and its reduction tree are unchanged: chi2 stays bit-identical to the linearize kernel's.
   __shared__ double shd[32];
-  const int tile = blockIdx.x, t = threadIdx.x;
-  const TileMeta tm = ds.tmeta[tile];
-  double cost = 0.0;
-  if (t < tm.n) {
+  const int t = threadIdx.x;
+  const int tile_begin = blockIdx.x * COST_TILES, tile_end = min(ds.ntiles, tile_begin + COST_TILES);
+  int64_t slot_n = (int64_t)tile_begin * TILE + t;
+  uint32_t om_n = ds.ometa[slot_n];
+  int c_n = ds.tile_cam[slot_n];
+  typename V2<T>::type ov_n = obs[slot_n];
+  for (int tile = tile_begin; tile < tile_end; tile++) {
+    const TileMeta tm = ds.tmeta[tile];
     const int64_t slot = (int64_t)tile * TILE + t;
-    const int c = ds.tile_cam[slot], p = tm.p0 + (int)(ds.ometa[slot] & 0xffu);
-    T cx[CAMX], X[3], ob[2], r[2];
-    load_camx<T>(cams, c, cx); // `cams` is the per-camera precomputed table (k_cam_precompute)
-    X[0] = pts[3 * (int64_t)p];
-    X[1] = pts[3 * (int64_t)p + 1];
-    X[2] = pts[3 * (int64_t)p + 2];
-    const typename V2<T>::type ov = obs[slot];
-    ob[0] = ov.x;
-    ob[1] = ov.y;
-    bal_residual_pre<T>(cx, X, ob, r);
-    if (rb.Pu != nullptr || rb.loss_kind != 0) cost = (double)whiten_factor<T, T>(rb, slot, r, (T *)nullptr, (T *)nullptr);
-    else cost = (double)(r[0] * r[0] + r[1] * r[1]);
+    const uint32_t om = om_n;
+    const int c = c_n;
+    const typename V2<T>::type ov = ov_n;
+    if (tile + 1 < tile_end) {
+      om_n = ds.ometa[slot + TILE];
+      c_n = ds.tile_cam[slot + TILE];
+      ov_n = obs[slot + TILE];
+    }
+    double cost = 0.0;
+    if (t < tm.n) {
+      const int p = tm.p0 + (int)(om & 0xffu);
+      T cx[CAMX], X[3], ob[2], r[2];
+      load_camx<T>(cams, c, cx); // `cams` is the per-camera precomputed table (k_cam_precompute)
+      X[0] = pts[3 * (int64_t)p];
+      X[1] = pts[3 * (int64_t)p + 1];
+      X[2] = pts[3 * (int64_t)p + 2];
+      ob[0] = ov.x;
+      ob[1] = ov.y;
+      bal_residual_pre<T>(cx, X, ob, r);
+      if (rb.Pu != nullptr || rb.loss_kind != 0) cost = (double)whiten_factor<T, T>(rb, slot, r, (T *)nullptr, (T *)nullptr);
+      else cost = (double)(r[0] * r[0] + r[1] * r[1]);
+    }
+    const double tot = block_sum<double>(cost, shd);
+    if (t == 0) cost_part[tile] = tot;
   }
-  const double tot = block_sum<double>(cost, shd);
-  if (t == 0) cost_part[tile] = tot;
 }
 
 // ---------------------------------------------------------------------------------------------
