@@ -21,7 +21,7 @@ _NP = {"f32": np.float32, "f64": np.float64}
 SYMBOLS = [
     "gb_version", "gb_context_create", "gb_context_destroy", "gb_last_error", "gb_comm_unique_id", "gb_comm_init",
     "gb_problem_create", "gb_problem_destroy", "gb_problem_info", "gb_set_observations", "gb_stage_observations_async", "gb_commit_observations", "gb_set_vertices",
-    "gb_get_vertices", "gb_set_loss", "gb_set_precision", "gb_hessian_structure", "gb_linearize", "gb_compute_cost", "gb_get_gradient", "gb_get_scales",
+    "gb_get_vertices", "gb_set_factor", "gb_set_loss", "gb_set_precision", "gb_hessian_structure", "gb_linearize", "gb_compute_cost", "gb_get_gradient", "gb_get_scales",
     "gb_get_residuals", "gb_get_jacobians", "gb_hessian_values", "gb_set_damping", "gb_solve", "gb_get_schur_rhs",
     "gb_get_schur_diagonal", "gb_schur_multiply", "gb_schur_structure", "gb_schur_values", "gb_try_step", "gb_revert_step", "gb_lm", "gb_kernel_launches",
     "gb_time_stage", "gb_structure_create", "gb_structure_destroy", "gb_structure_info", "gb_structure_array",
@@ -94,6 +94,7 @@ def load_library():
     L.gb_stage_observations_async.argtypes = [vp, vp, C.c_int]
     L.gb_commit_observations.argtypes = [vp, C.c_int]
     L.gb_get_vertices.argtypes = [vp, vp, vp]
+    L.gb_set_factor.argtypes = [vp, vp, vp]
     L.gb_set_loss.argtypes = [vp, C.c_int, C.c_double]
     L.gb_set_precision.argtypes = [vp, vp]
     L.gb_hessian_structure.argtypes = [vp, vp, vp, vp]
@@ -212,6 +213,11 @@ class Problem:
         p = np.ascontiguousarray(pts, dtype=self.T)
         assert c.shape == (self.n_cams, 9) and p.shape == (self.n_pts, 3)
         self.ctx.check(self.L.gb_set_vertices(self.h, _ptr(c), _ptr(p)))
+
+    def set_factor(self, fn_ptr, user_ptr=None):
+        """User-defined factor: fn_ptr = address of a `gb_factor_fn` (int), or None for the built-in BAL factor."""
+        self.ctx.check(self.L.gb_set_factor(self.h, C.c_void_p(fn_ptr) if fn_ptr else None,
+                                            C.c_void_p(user_ptr) if user_ptr else None))
 
     def set_loss(self, loss: str = "default", delta: float = 0.0):
         self.ctx.check(self.L.gb_set_loss(self.h, {"default": 0, "huber": 1}[loss], float(delta)))

@@ -95,6 +95,7 @@ struct ProblemBase {
   virtual int stage_observations_async(const void *, int) = 0;
   virtual int commit_observations(int) = 0;
   virtual int set_vertices(const void *, const void *) = 0;
+  virtual int set_factor(gb_factor_fn, void *) = 0;
   virtual int set_loss(int, double) = 0;
   virtual int set_precision(const void *) = 0;
   virtual int get_vertices(void *, void *) = 0;
@@ -168,6 +169,13 @@ template <typename T, typename S> struct Problem : ProblemBase {
   double last_chi2 = 0.0;
   bool profiling = false;
   std::vector<cudaEvent_t> prof_ev; // pairs around k_schur_tiles<MODE 0>, one pair per PCG iteration
+  // user-defined factor: evaluated by the caller's kernel into caller-order buffers (gb_set_factor)
+  gb_factor_fn ext_fn = nullptr;
+  void *ext_user = nullptr;
+  T *ext_r = nullptr, *ext_Jc = nullptr, *ext_Jp = nullptr;
+  int32_t *d_slot_src = nullptr, *d_ci_caller = nullptr, *d_pi_caller = nullptr;
+  const T2 *obs_caller = nullptr; // the observations in the caller's order as last uploaded
+  ExtFactor ex{nullptr, nullptr, nullptr, nullptr};
   // loss and per-factor precision matrices (whitening in k_linearize / k_cost_tiles)
   T *Pu = nullptr;
   Robust rb{nullptr, 0, 0.0};
@@ -286,7 +294,8 @@ template <typename T, typename S> struct Problem : ProblemBase {
       GB_TRY(dalloc(cta_part, 2 * (size_t)std::max(iter_grid, 1)));
     }
     // the super-tile kernels keep their camera accumulator rows in (opt-in sized) dynamic shared memory
-    GB_CUDA(ctx, cudaFuncSetAttribute(k_linearize<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_lin_bytes<T>()));
+    GB_CUDA(ctx, cudaFuncSetAttribute(k_linearize<T, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_lin_bytes<T>()));
+    GB_CUDA(ctx, cudaFuncSetAttribute(k_linearize<T, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_lin_bytes<T>()));
     GB_CUDA(ctx, cudaFuncSetAttribute(k_schur_product<T, S, NSTAGE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       SchurSmem<T, S>::TOTAL(NSTAGE)));
     GB_CUDA(ctx, cudaFuncSetAttribute(k_schur_product<T, S, NSTAGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -450,6 +459,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_CUDA(ctx, cudaMemcpyAsync(obs_stage, o, 2 * hs.M * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
     k_scatter_slots<T2><<<(unsigned)((hs.M + 255) / 256), 256, 0, ctx->stream>>>(hs.M, ts.slot_of_obs, d_perm, obs_stage, obs);
     GB_LAUNCH(ctx);
+    obs_caller = obs_stage;
     GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     have_obs = true;
     linearized = prepared = solved = stepped = false;
@@ -476,6 +486,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_stage[slot], 0));
     k_scatter_slots<T2><<<(unsigned)((hs.M + 255) / 256), 256, 0, ctx->stream>>>(hs.M, ts.slot_of_obs, d_perm, obs_stage2[slot], obs);
     GB_LAUNCH(ctx);
+    obs_caller = obs_stage2[slot]; // stays untouched until this slot is staged again
     staged[slot] = false;
     have_obs = true;
     linearized = prepared = solved = solved_full = stepped = false;
@@ -496,6 +507,41 @@ template <typename T, typename S> struct Problem : ProblemBase {
     have_vertices = true;
     linearized = prepared = solved = stepped = false;
     return GB_OK;
+  }
+  int set_factor(gb_factor_fn fn, void *user) override {
+    linearized = prepared = solved = solved_full = stepped = false;
+    ext_fn = fn;
+    ext_user = user;
+    if (!fn || ext_r) return GB_OK;
+    GB_TRY(dalloc(ext_r, 2 * (size_t)hs.M)); GB_TRY(dalloc(ext_Jc, 18 * (size_t)hs.M)); GB_TRY(dalloc(ext_Jp, 6 * (size_t)hs.M));
+    std::vector<int32_t> src((size_t)hs.Mstore, -1), ci((size_t)hs.M), pi((size_t)hs.M);
+    for (int64_t spos = 0; spos < hs.M; spos++) {
+      const int64_t u = hs.identity_perm ? spos : hs.perm[spos];
+      src[hs.slot_of_obs[spos]] = (int32_t)u;
+      ci[u] = hs.cam_idx[spos];
+      pi[u] = hs.pt_idx[spos];
+    }
+    const int32_t *a = nullptr, *b = nullptr, *c = nullptr;
+    GB_TRY(upload(a, src)); GB_TRY(upload(b, ci)); GB_TRY(upload(c, pi));
+    d_slot_src = const_cast<int32_t *>(a); d_ci_caller = const_cast<int32_t *>(b); d_pi_caller = const_cast<int32_t *>(c);
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ex = ExtFactor{ext_r, ext_Jc, ext_Jp, d_slot_src};
+    return GB_OK;
+  }
+  // run the caller's factor kernel at the current vertices (with_jacobians = false: residuals only)
+  int evaluate_external(bool with_jacobians) {
+    if (!obs_caller) return ctx->fail(GB_ERR_INVALID, "user-defined factor: no observations uploaded");
+    gb_factor_eval e{};
+    e.num_observations = hs.M;
+    e.cameras = cams; e.points = pts; e.observations = obs_caller;
+    e.camera_index = d_ci_caller; e.point_index = d_pi_caller;
+    e.residuals = ext_r;
+    e.Jc = with_jacobians ? ext_Jc : nullptr;
+    e.Jp = with_jacobians ? ext_Jp : nullptr;
+    e.stream = (void *)ctx->stream;
+    const int rc = ext_fn(&e, ext_user);
+    if (rc != 0) return ctx->fail(GB_ERR_INVALID, "user-defined factor callback returned %d", rc);
+    return launch_check();
   }
   // Replaces the loss argument of add_factor (factor.hpp:373-412, loss.hpp): one loss for all factors.
   int set_loss(int kind, double delta) override {
@@ -556,7 +602,12 @@ template <typename T, typename S> struct Problem : ProblemBase {
   int enqueue_linearize(bool need_cost = true) {
     cudaStream_t st = ctx->stream;
     GB_TRY(ensure_camx());
-    k_linearize<T, S><<<ts.nst, TILE, smem_lin_bytes<T>(), st>>>(ts, camx, pts, obs, J, res, Cg, part18, cost_part, rb);
+    if (ext_fn) {
+      GB_TRY(evaluate_external(true));
+      k_linearize<T, S, true><<<ts.nst, TILE, smem_lin_bytes<T>(), st>>>(ts, camx, pts, obs, J, res, Cg, part18, cost_part, rb, ex);
+    } else {
+      k_linearize<T, S, false><<<ts.nst, TILE, smem_lin_bytes<T>(), st>>>(ts, camx, pts, obs, J, res, Cg, part18, cost_part, rb, ex);
+    }
     GB_LAUNCH(ctx);
     const bool multi = ctx->nranks > 1;
     k_cam_reduce_lin<T><<<ts.Nc, 288, 0, st>>>(ts, part18, diagB, gc, multi ? 0 : 1, scale_on ? 1 : 0, scale, b);
@@ -873,7 +924,12 @@ template <typename T, typename S> struct Problem : ProblemBase {
   int enqueue_cost(bool with_rho = false) {
     cudaStream_t st = ctx->stream;
     GB_TRY(ensure_camx());
-    k_cost_tiles<T><<<(ts.ntiles + COST_TILES - 1) / COST_TILES, TILE, 0, st>>>(ts, camx, pts, obs, cost_part, rb);
+    if (ext_fn) {
+      GB_TRY(evaluate_external(false));
+      k_cost_tiles<T, true><<<(ts.ntiles + COST_TILES - 1) / COST_TILES, TILE, 0, st>>>(ts, camx, pts, obs, cost_part, rb, ex);
+    } else {
+      k_cost_tiles<T, false><<<(ts.ntiles + COST_TILES - 1) / COST_TILES, TILE, 0, st>>>(ts, camx, pts, obs, cost_part, rb, ex);
+    }
     GB_LAUNCH(ctx);
     if (with_rho && !solved_full) { // cost and both rho sums of the Schur path in one launch
       k_sum_partials3<<<3, 1024, 0, st>>>(SumJob{cost_part, ts.ntiles, 0}, SumJob{rho_part, ts.ntiles, 1},
@@ -1480,6 +1536,7 @@ int gb_stage_observations_async(gb_problem *p, const void *o, int slot) { GB_P(p
 int gb_commit_observations(gb_problem *p, int slot) { GB_P(p); return p->impl->commit_observations(slot); }
 int gb_set_vertices(gb_problem *p, const void *c, const void *q) { GB_P(p); if (!c || !q) return GB_ERR_INVALID; return p->impl->set_vertices(c, q); }
 int gb_get_vertices(gb_problem *p, void *c, void *q) { GB_P(p); return p->impl->get_vertices(c, q); }
+int gb_set_factor(gb_problem *p, gb_factor_fn fn, void *user) { GB_P(p); return p->impl->set_factor(fn, user); }
 int gb_set_loss(gb_problem *p, int kind, double delta) { GB_P(p); return p->impl->set_loss(kind, delta); }
 int gb_set_precision(gb_problem *p, const void *P) { GB_P(p); return p->impl->set_precision(P); }
 int gb_hessian_structure(const gb_problem *p, int64_t *cp, int64_t *ri, int64_t *off) {

@@ -276,6 +276,13 @@ struct Robust {
   int loss_kind;   // 0 DefaultLoss, 1 HuberLoss
   double delta;
 };
+// User-defined factor (FactorTraits::error / ::jacobian, docs/markdown/main.md:284-289; dispatch ops/error.hpp:33-96,
+// ops/linearize.hpp:8-138): residuals and column-major 2x9 / 2x3 Jacobians evaluated by the CALLER's kernel into
+// caller-order buffers of T; the tile kernels read them through slot_src (storage slot -> caller's factor index).
+struct ExtFactor {
+  const void *r, *Jc, *Jp;    // [n_obs][2], [n_obs][18], [n_obs][6] of T
+  const int32_t *slot_src;    // [Mstore], -1 in padding slots
+};
 // returns chi2_f; whitens r (2), Jc (18), Jp (6) in place
 template <typename T, typename S>
 __device__ __forceinline__ T whiten_factor(const Robust &rb, int64_t slot, T *r, T *Jc, T *Jp) {
@@ -318,12 +325,12 @@ __device__ __forceinline__ T whiten_factor(const Robust &rb, int64_t slot, T *r,
 //     compute_hessian_scalar_diagonal_kernel / compute_b_kernel (ops/error.hpp:252, ops/linearize.hpp:10,238,
 //     ops/chi2.hpp:32, ops/hessian.hpp:418)
 // ---------------------------------------------------------------------------------------------
-template <typename T, typename S>
+template <typename T, typename S, bool EXT>
 __global__ void __launch_bounds__(TILE, LIN_MIN_BLOCKS)
 k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
             const typename V2<T>::type *__restrict__ obs, typename V2<S>::type *__restrict__ J,
             typename V2<T>::type *__restrict__ res, T *__restrict__ Cg, T *__restrict__ part /*[nrows][18]*/,
-            double *__restrict__ cost_part /*[ntiles]*/, Robust rb) {
+            double *__restrict__ cost_part /*[ntiles]*/, Robust rb, ExtFactor ex) {
   const bool robust = rb.Pu != nullptr || rb.loss_kind != 0;
   // ncu of the first version (tables read from global memory inside the reduction loops, two 9-wide camera passes):
   // 41 % of the stall samples were long-scoreboard waits in those loops, 61 % of all samples sat in the loops.
@@ -364,15 +371,28 @@ k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
     BalObs<T> B;
     double cost = 0.0;
     if (active) {
-      const int p = tm.p0 + ptl;
-      T cx[CAMX], X[3], ob[2];
-      load_camx<T>(cams, c, cx); // `cams` is the per-camera precomputed table (k_cam_precompute)
-      X[0] = pts[3 * (int64_t)p];
-      X[1] = pts[3 * (int64_t)p + 1];
-      X[2] = pts[3 * (int64_t)p + 2];
-      ob[0] = ov.x;
-      ob[1] = ov.y;
-      bal_residual_jacobian_pre<T>(cx, X, ob, B);
+      if (EXT) {
+        // the caller's kernel has evaluated this factor: fetch its residual and Jacobians
+        const int64_t u = ex.slot_src[slot];
+        const T *er = reinterpret_cast<const T *>(ex.r) + 2 * u;
+        const T *ec = reinterpret_cast<const T *>(ex.Jc) + 18 * u;
+        const T *ep = reinterpret_cast<const T *>(ex.Jp) + 6 * u;
+        B.r[0] = er[0]; B.r[1] = er[1];
+#pragma unroll
+        for (int j = 0; j < 18; j++) B.Jc[j] = ec[j];
+#pragma unroll
+        for (int j = 0; j < 6; j++) B.Jp[j] = ep[j];
+      } else {
+        const int p = tm.p0 + ptl;
+        T cx[CAMX], X[3], ob[2];
+        load_camx<T>(cams, c, cx); // `cams` is the per-camera precomputed table (k_cam_precompute)
+        X[0] = pts[3 * (int64_t)p];
+        X[1] = pts[3 * (int64_t)p + 1];
+        X[2] = pts[3 * (int64_t)p + 2];
+        ob[0] = ov.x;
+        ob[1] = ov.y;
+        bal_residual_jacobian_pre<T>(cx, X, ob, B);
+      }
       res[slot] = V2<T>::make(B.r[0], B.r[1]); // the residual itself (export); the assembly below uses the whitened one
       if (robust) cost = (double)whiten_factor<T, S>(rb, slot, B.r, B.Jc, B.Jp);
       else cost = (double)(B.r[0] * B.r[0] + B.r[1] * B.r[1]);
@@ -1779,10 +1799,11 @@ __global__ void k_cam_step(int n, const T *__restrict__ x, const T *__restrict__
 }
 
 // K5 cost: residual only (graph.hpp:221-234 compute_error + chi2); one CTA per tile
-template <typename T>
+template <typename T, bool EXT>
 __global__ void __launch_bounds__(TILE)
 k_cost_tiles(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
-             const typename V2<T>::type *__restrict__ obs, double *__restrict__ cost_part /*[ntiles]*/, Robust rb) {
+             const typename V2<T>::type *__restrict__ obs, double *__restrict__ cost_part /*[ntiles]*/, Robust rb,
+             ExtFactor ex) {
   // COST_TILES consecutive tiles per CTA; the slot inputs of the next tile are fetched while the current one is
   // evaluated (one tile per CTA spent most of its time in the chain index -> camera / point gather -> arithmetic).
   // The per-tile partial and its reduction tree are unchanged: chi2 stays bit-identical to the linearize kernel's.
@@ -1806,15 +1827,21 @@ k_cost_tiles(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts
     }
     double cost = 0.0;
     if (t < tm.n) {
-      const int p = tm.p0 + (int)(om & 0xffu);
-      T cx[CAMX], X[3], ob[2], r[2];
-      load_camx<T>(cams, c, cx); // `cams` is the per-camera precomputed table (k_cam_precompute)
-      X[0] = pts[3 * (int64_t)p];
-      X[1] = pts[3 * (int64_t)p + 1];
-      X[2] = pts[3 * (int64_t)p + 2];
-      ob[0] = ov.x;
-      ob[1] = ov.y;
-      bal_residual_pre<T>(cx, X, ob, r);
+      T r[2];
+      if (EXT) {
+        const T *er = reinterpret_cast<const T *>(ex.r) + 2 * (int64_t)ex.slot_src[slot];
+        r[0] = er[0]; r[1] = er[1];
+      } else {
+        const int p = tm.p0 + (int)(om & 0xffu);
+        T cx[CAMX], X[3], ob[2];
+        load_camx<T>(cams, c, cx); // `cams` is the per-camera precomputed table (k_cam_precompute)
+        X[0] = pts[3 * (int64_t)p];
+        X[1] = pts[3 * (int64_t)p + 1];
+        X[2] = pts[3 * (int64_t)p + 2];
+        ob[0] = ov.x;
+        ob[1] = ov.y;
+        bal_residual_pre<T>(cx, X, ob, r);
+      }
       if (rb.Pu != nullptr || rb.loss_kind != 0) cost = (double)whiten_factor<T, T>(rb, slot, r, (T *)nullptr, (T *)nullptr);
       else cost = (double)(r[0] * r[0] + r[1] * r[1]);
     }

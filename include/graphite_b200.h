@@ -120,6 +120,27 @@ int gb_commit_observations(gb_problem *p, int slot);
 typedef enum { GB_LOSS_DEFAULT = 0, GB_LOSS_HUBER = 1 } gb_loss;
 int gb_set_loss(gb_problem *p, int loss, double delta);
 int gb_set_precision(gb_problem *p, const void *precision_host);
+/* User-defined factor: replaces FactorTraits::error / ::jacobian (docs/markdown/main.md:284-289; dispatch in
+ * ops/error.hpp:33-96 and ops/linearize.hpp:8-138) for any binary factor of the BAL block shape (vertex 0: 9 parameters,
+ * vertex 1: 3 parameters, residual 2) - other camera models, other parameterisations.  The library calls `fn` whenever it
+ * needs the factors evaluated at the current vertices; `fn` launches the caller's own kernel on `stream` and returns 0.
+ * All pointers are DEVICE memory of element type T.  Jc / Jp are NULL when only residuals are needed (trial-step cost).
+ * Loss and precision matrices (gb_set_loss / gb_set_precision) are applied by the library on top, as in the reference
+ * (ops/chi2.hpp, ops/hessian.hpp).  fn = NULL restores the built-in BAL reprojection factor. */
+typedef struct {
+  int64_t num_observations;
+  const void *cameras;         /* [n_cams] rows of 10 values: 9 parameters + 1 pad */
+  const void *points;          /* [n_points][3] */
+  const void *observations;    /* [n_obs][2], caller's factor order */
+  const int32_t *camera_index; /* [n_obs], caller's factor order */
+  const int32_t *point_index;  /* [n_obs] */
+  void *residuals;             /* out [n_obs][2] */
+  void *Jc;                    /* out [n_obs][18], column-major 2x9 (ops/linearize.hpp:36-38), or NULL */
+  void *Jp;                    /* out [n_obs][6],  column-major 2x3, or NULL */
+  void *stream;                /* cudaStream_t the evaluation must be enqueued on */
+} gb_factor_eval;
+typedef int (*gb_factor_fn)(const gb_factor_eval *eval, void *user);
+int gb_set_factor(gb_problem *p, gb_factor_fn fn, void *user);
 /* Replaces the in-place update through user pointers (docs/markdown/memory.md:4-13): writes back. */
 int gb_get_vertices(gb_problem *p, void *cams_host, void *pts_host);
 

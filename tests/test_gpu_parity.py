@@ -5,6 +5,8 @@ Tolerances (BASELINE.json north_star): Hessian block structure bit-exact; FP64 p
 (looser only where the reference's own run-to-run spread, recorded in *.run2.json, is larger) and final cost 1e-6;
 FP32 / mixed 1e-4.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -455,6 +457,67 @@ def test_staged_observation_upload_and_deferred_linearisation(ctx):
         rows.append(t1[0])
     assert np.array_equal(np.array(rows), t6)
     P.close(); P2.close()
+
+
+@pytest.fixture(scope="module")
+def user_factor_lib():
+    """Compile the user's factor kernel (tests/user_factor/bal_user_factor.cu) the way a Graphite user would: nvcc, public header."""
+    import ctypes, subprocess
+    from conftest import ROOT
+    src = os.path.join(ROOT, "tests", "user_factor", "bal_user_factor.cu")
+    out = os.path.join(ROOT, "tests", "user_factor", "libuser_factor.so")
+    if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+        subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a",
+                               "--expt-relaxed-constexpr", "-shared", "-Xcompiler", "-fPIC", "-o", out, src])
+    return ctypes.CDLL(out)
+
+
+def test_user_defined_factor_drops_in(ctx, user_factor_lib):
+    """gb_set_factor: the same BAL factor evaluated by a USER kernel reproduces the built-in path bit for bit (stages,
+    LM trajectory, Huber + precision on top); a different factor (2x the residual) really is what gets optimised."""
+    import ctypes
+    fn = ctypes.cast(user_factor_lib.user_bal_factor_f64, ctypes.c_void_p).value
+    prob = synthetic.make_named("ladybug-49")
+    P0 = binding.problem_from_bal(ctx, prob, "f64-f64")
+    P1 = binding.problem_from_bal(ctx, prob, "f64-f64")
+    P1.set_factor(fn)
+    assert P1.linearize() == P0.linearize()
+    assert np.array_equal(P1.gradient(), P0.gradient()) and np.array_equal(P1.scales(), P0.scales())
+    assert np.array_equal(P1.hessian_values(), P0.hessian_values())
+    t0, _ = P0.lm(iterations=12)
+    t1, _ = P1.lm(iterations=12)
+    assert np.array_equal(t0, t1)
+    assert np.array_equal(P0.get_vertices()[0], P1.get_vertices()[0])
+    # loss and precision matrices are applied by the library on top of the user's factor
+    Pm = synthetic.precision_matrices(prob.n_obs)
+    for P in (P0, P1):
+        P.set_vertices(prob.cams, prob.pts)
+        P.set_loss("huber", 20.0)
+        P.set_precision(Pm)
+    assert np.array_equal(P0.lm(iterations=8)[0], P1.lm(iterations=8)[0])
+    # a different user factor: residual scaled by 2 -> cost x 4, gradient x 4 before scaling
+    scale = ctypes.c_double(2.0)
+    P2 = binding.problem_from_bal(ctx, prob, "f64-f64")
+    P2.set_factor(fn, ctypes.addressof(scale))
+    P3 = binding.problem_from_bal(ctx, prob, "f64-f64")
+    c2, c3 = P2.linearize(), P3.linearize()
+    assert abs(c2 - 4.0 * c3) <= 1e-14 * c2
+    assert P2.compute_cost() == c2
+    # unsorted input: the callback sees the caller's factor order
+    perm = np.random.default_rng(11).permutation(prob.n_obs)
+    shuffled = synthetic.BALProblem(prob.cam_idx[perm], prob.pt_idx[perm], prob.obs[perm], prob.cams, prob.pts, "shuffled")
+    P4 = binding.problem_from_bal(ctx, shuffled, "f64-f64")
+    P4.set_factor(fn)
+    assert np.array_equal(P4.lm(iterations=6)[0], t0[:6])
+    # a failing callback is reported, not ignored; NULL restores the built-in factor
+    P4.set_factor(ctypes.cast(user_factor_lib.user_failing_factor, ctypes.c_void_p).value)
+    with pytest.raises(binding.GraphiteB200Error, match="callback returned 7"):
+        P4.linearize()
+    P4.set_factor(None)
+    P4.set_vertices(prob.cams, prob.pts)
+    assert np.array_equal(P4.lm(iterations=6)[0], t0[:6])
+    for P in (P0, P1, P2, P3, P4):
+        P.close()
 
 
 def test_revert_restores_the_state_exactly(ctx):
