@@ -483,7 +483,7 @@ def test_user_defined_factor_drops_in(ctx, user_factor_lib):
     P1.set_factor(fn)
     assert P1.linearize() == P0.linearize()
     assert np.array_equal(P1.gradient(), P0.gradient()) and np.array_equal(P1.scales(), P0.scales())
-    assert np.array_equal(P1.hessian_values(), P0.hessian_values())
+    assert rel(P1.hessian_values(), P0.hessian_values()) <= 1e-14  # (the export sums the camera blocks with atomics)
     t0, _ = P0.lm(iterations=12)
     t1, _ = P1.lm(iterations=12)
     assert np.array_equal(t0, t1)
