@@ -22,6 +22,21 @@
 // All arithmetic on the Jacobians is done in the UNSCALED space; the Jacobi scaling of the reference
 // (graph.hpp:254-281) is applied as D_c / D_p on the camera- and point-sized quantities, which is the
 // same algebra: J~ = J D  =>  J~^T J~ = D J^T J D.
+//
+// Kernels of one LM iteration, in launch order (DESIGN.md section 3 has bytes, bounds and measured times):
+//   k_cam_precompute, k_linearize<EXT>   factor evaluation (built-in BAL model or the caller's kernel), whitening by
+//                                        loss / precision, J + residual store, C and g per point, diag(B) and g_c partials
+//   k_cam_reduce_lin, k_point_prepare    Jacobi scales, b; W = D (D C D + damping)^-1 D, h = W g
+//   k_prepare_cams, k_cam_reduce_prepare diagonal blocks of S and b_S by a camera-major gather; 9x9 inverses
+//   k_pcg_init(_state)                   PCG start
+//   k_schur_product2 + k_pcg_iterate     per PCG iteration: matrix-free (B - E W E^T) p on the TMA pipeline, then ONE
+//                                        cooperative launch for row sums, multi-GPU exchange (p2p.cuh), dots and updates
+//   k_cam_step, k_backsubst_tiles        step of the cameras, back-substitution and step of the points, rho partials
+//   k_cost_tiles, k_sum_partials3        cost at the trial point, cost + rho sums; k_store_host hands them to the host
+//   k_copy                               restore after a rejected step
+// Other entry points: k_schur_product2<FULL> + k_full_* (full-system PCG solver), k_schur_explicit (explicit S export),
+// k_hessian_export, k_scatter_slots, k_p2p_push / k_p2p_sum (generic exchange).  k_schur_product (first TMA ring),
+// k_cam_reduce_spmv, k_pcg_update* are the PRODUCT_PIPE=1 / GB_FUSED_ITER=0 / NCCL-fallback paths.
 #pragma once
 #include <cfloat>
 #include <cstdint>
