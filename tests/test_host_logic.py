@@ -215,3 +215,18 @@ def test_two_rank_sharding_over_gloo(built, tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
     assert res.returncode == 0, res.stderr[-2000:]
     assert "GLOO_OK" in res.stdout
+
+
+def test_bench_reference_arm_contract(built):
+    """`bench.py --impl reference` (the CPU arm: oracle port on the host cores) prints one JSON line with the contract's keys."""
+    import json
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "ladybug-49",
+                          "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, res.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "LM it/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["cams"] == 49 and "workload" in d["config"] and "model" not in d["config"]
