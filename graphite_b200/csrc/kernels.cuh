@@ -730,6 +730,7 @@ k_prepare_cams(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T
 // damping), so no pivoting is needed.  Every thread of the block must call it (barriers inside).
 template <typename T> __device__ __forceinline__ void invert9_block(T *M /*[9*18]*/, T *f /*[9]*/, int t) {
   const int i = t / 18, j = t - 18 * i; // element (i, j) for t < 162
+  __syncthreads(); // the callers fill M right before the call (racecheck: the first pivot read raced with that fill)
   for (int c = 0; c < 9; c++) {
     const T piv = M[c * 18 + c];
     __syncthreads();
