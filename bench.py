@@ -205,6 +205,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="venice-1778")
     ap.add_argument("--precision", default="f64-f64")
+    ap.add_argument("--solver", default="pcg-schur", choices=["pcg-schur", "pcg"],
+                    help="pcg-schur: PCGSchurSolver (headline); pcg: the reference's full-system PCGSolver (its mixed-precision path)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-steps", type=int, default=4)
     args = ap.parse_args()
@@ -266,13 +268,13 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    traj_w, res_w = P.lm(iterations=args.warmup)
+    traj_w, res_w = P.lm(iterations=args.warmup, solver=args.solver)
     barrier()
     sampler.mark(True)
     l0 = ctx.kernel_launches()
     t0 = time.perf_counter()
     traj, res = P.lm(iterations=args.steps, initial_damping=res_w["final_damping"], initial_nu=res_w["final_nu"],
-                     resume=True, profile_product=True)
+                     resume=True, profile_product=True, solver=args.solver)
     barrier()
     sampler.mark(False)
     wall = time.perf_counter() - t0
@@ -286,7 +288,7 @@ def main():
     prod_bytes, survey_k4 = algorithmic_bytes(nc, local.n_pts, info["n_obs"], info["n_partial_rows"], info["n_tiles"], sT, sS)
     n_prod = max(int(res["product_launches"]), 1)
     prod_ms = 1e3 * res["product_seconds"] / n_prod
-    achieved = prod_bytes / (prod_ms * 1e-3) / 1e9
+    achieved = prod_bytes / (prod_ms * 1e-3) / 1e9 if prod_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "k_schur_product2 (matrix-free Schur product, TMA: 2 J slots + 4-deep record ring, one launch per PCG iteration)",
                 "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None,
@@ -306,7 +308,7 @@ def main():
 
     # ---- e2e arm: every step copies its inputs from pinned host memory and reads the result back ----------
     P.set_vertices_raw(h_cams.data_ptr(), h_pts.data_ptr())
-    tw, rw = P.lm(iterations=args.warmup)
+    tw, rw = P.lm(iterations=args.warmup, solver=args.solver)
     # state after warm-up becomes the host-side state the steps start from
     P.get_vertices_raw(out_cams.data_ptr(), out_pts.data_ptr())
     mu, nu = rw["final_damping"], rw["final_nu"]
@@ -319,7 +321,7 @@ def main():
     for _ in range(args.steps):
         P.set_observations_raw(h_obs.data_ptr())                       # H2D
         P.set_vertices_raw(out_cams.data_ptr(), out_pts.data_ptr())    # H2D
-        tj, rj = P.lm(iterations=1, initial_damping=mu, initial_nu=nu)  # linearize + one LM iteration
+        tj, rj = P.lm(iterations=1, initial_damping=mu, initial_nu=nu, solver=args.solver)  # linearize + one LM iteration
         P.get_vertices_raw(out_cams.data_ptr(), out_pts.data_ptr())    # D2H (+ chi2 in rj)
         mu, nu = rj["final_damping"], rj["final_nu"]
         e2e_steps += 1
@@ -330,7 +332,7 @@ def main():
     # the same steps with the observation upload double-buffered on the library's copy stream: the batch of step k+1 is
     # copied (same bytes, inside the timed region) while step k computes; vertices stay in line (step k+1 needs step k's)
     P.set_vertices_raw(h_cams.data_ptr(), h_pts.data_ptr())
-    tw, rw = P.lm(iterations=args.warmup)
+    tw, rw = P.lm(iterations=args.warmup, solver=args.solver)
     P.get_vertices_raw(out_cams.data_ptr(), out_pts.data_ptr())
     mu, nu = rw["final_damping"], rw["final_nu"]
     P.stage_observations_async(h_obs.data_ptr(), 0)  # batch of step 0
@@ -342,7 +344,7 @@ def main():
         P.set_vertices_raw(out_cams.data_ptr(), out_pts.data_ptr())      # H2D (first: the step cannot start without them)
         P.stage_observations_async(h_obs.data_ptr(), (k + 1) % 2)        # H2D of the next step's batch, overlaps this step
         tj, rj = P.lm(iterations=1, initial_damping=mu, initial_nu=nu,   # linearize + one LM iteration; the linearisation
-                      defer_final_linearize=True)                       # at the accepted point is the next step's first act
+                      defer_final_linearize=True, solver=args.solver)   # at the accepted point is the next step's first act
         P.get_vertices_raw(out_cams.data_ptr(), out_pts.data_ptr())      # D2H (+ chi2 in rj)
         mu, nu = rj["final_damping"], rj["final_nu"]
     barrier()
@@ -382,12 +384,14 @@ def main():
                "sample": f"LM iterations 2..{args.cpu_baseline_steps + 1} of the same workload from the same initial state "
                          f"(oracle/oracle_bal.cpp, explicit Schur + PCG, OpenMP, {dtc:.1f} s)"}
 
+    if args.solver != "pcg-schur":  # the product kernel is not event-timed on the full-system solver's host-driven loop
+        roofline = None
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps_done, "warmup": args.warmup,
             "ms_per_step": 1e3 * seconds / max(steps_done, 1), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64" if tname == "f64" else "f32", "data": "synthetic",
-            "config": workload_config(prob, args.precision, world),
+            "config": dict(workload_config(prob, args.precision, world), solver=args.solver),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "pcg": {"iterations_per_step": [int(v) for v in traj[:, 3]], "total": int(res["pcg_iterations_total"]),
                     "ms_per_product_launch": prod_ms, "product_gbps": achieved,
