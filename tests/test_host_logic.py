@@ -230,3 +230,14 @@ def test_bench_reference_arm_contract(built):
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["cams"] == 49 and "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/graphite_b200.h must compile as C99 (-pedantic) and as C++17."""
+    src = tmp_path / "t.c"
+    src.write_text('#include "graphite_b200.h"\n'
+                   'int main(void) { gb_lm_options o = {0}; gb_pcg_options p = {10, 1.0, 5.0, GB_SOLVER_PCG_SCHUR, 0};\n'
+                   '  gb_factor_eval e = {0}; (void)o; (void)p; (void)e; return gb_version() == 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)])
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-fsyntax-only", "-x", "c++", "-I", inc, str(src)])
