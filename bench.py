@@ -395,7 +395,11 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "pcg": {"iterations_per_step": [int(v) for v in traj[:, 3]], "total": int(res["pcg_iterations_total"]),
                     "ms_per_product_launch": prod_ms, "product_gbps": achieved,
-                    "ms_per_iteration_rest": 1e3 * res["update_seconds"] / n_prod},
+                    "ms_per_iteration_rest": 1e3 * res["update_seconds"] / n_prod,
+                    # whole PCG iteration (product + reduction / exchange / update) against SURVEY 8(d)'s K4 bytes
+                    "ms_per_iteration": prod_ms + 1e3 * res["update_seconds"] / n_prod,
+                    "iteration_gbps": (survey_k4 / ((prod_ms + 1e3 * res["update_seconds"] / n_prod) * 1e-3) / 1e9) if prod_ms > 0 else None,
+                    "iteration_frac_of_hbm_peak": (survey_k4 / ((prod_ms + 1e3 * res["update_seconds"] / n_prod) * 1e-3) / 1e9 / peak) if prod_ms > 0 else None},
             "stages_ms_per_step": {k[8:]: 1e3 * v / max(steps_done, 1) for k, v in res.items()
                                    if k.startswith("seconds_") and k != "seconds_total"},
             "accepted": int(res["accepted"]), "rejected": int(res["rejected"]),

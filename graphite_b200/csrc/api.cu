@@ -86,6 +86,13 @@ struct gb_context {
 
 namespace gb {
 
+// scratch device memory of an export call: freed on every return path
+struct Scratch {
+  void *p = nullptr;
+  ~Scratch() { if (p) cudaFree(p); }
+  template <typename X> X *as() const { return (X *)p; }
+};
+
 struct ProblemBase {
   gb_context *ctx = nullptr;
   HostStructure hs;
@@ -1023,20 +1030,18 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_TRY(require(linearized, "gb_hessian_values before gb_linearize"));
     GB_TRY(require(ctx->nranks == 1, "gb_hessian_values is single-rank only"));
     const int64_t nv = 81 * (int64_t)hs.Nc + 27 * hs.M + 9 * (int64_t)hs.Np;
-    S *vals = nullptr;
-    double *Bacc = nullptr;
-    GB_CUDA(ctx, cudaMalloc((void **)&vals, nv * sizeof(S)));
-    GB_CUDA(ctx, cudaMalloc((void **)&Bacc, 81 * (size_t)hs.Nc * sizeof(double)));
+    Scratch s_vals, s_bacc;
+    GB_CUDA(ctx, cudaMalloc(&s_vals.p, nv * sizeof(S)));
+    GB_CUDA(ctx, cudaMalloc(&s_bacc.p, 81 * (size_t)hs.Nc * sizeof(double)));
+    S *vals = s_vals.as<S>();
+    double *Bacc = s_bacc.as<double>();
     GB_CUDA(ctx, cudaMemsetAsync(Bacc, 0, 81 * (size_t)hs.Nc * sizeof(double), ctx->stream));
     const int64_t n = std::max<int64_t>(hs.M, hs.Np);
     k_hessian_export<T, S><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ts, J, Cg, scale, scale + dimc, vals, Bacc);
     GB_LAUNCH(ctx);
     k_copy_B<S><<<(81 * hs.Nc + 255) / 256, 256, 0, ctx->stream>>>(81 * hs.Nc, Bacc, vals);
     GB_LAUNCH(ctx);
-    int rc = d2h(out, vals, nv * sizeof(S));
-    cudaFree(vals);
-    cudaFree(Bacc);
-    return rc;
+    return d2h(out, vals, nv * sizeof(S));
   }
   int set_damping(double m, int ident) override {
     mu = (T)m;
@@ -1118,12 +1123,13 @@ template <typename T, typename S> struct Problem : ProblemBase {
     int64_t nnz = 0;
     GB_TRY(schur_structure(nullptr, nullptr, &nnz));
     cudaStream_t st = ctx->stream;
-    int64_t *d_cp = nullptr;
-    int32_t *d_ri = nullptr;
-    T *vals = nullptr;
-    GB_CUDA(ctx, cudaMalloc((void **)&d_cp, s_colptr.size() * sizeof(int64_t)));
-    GB_CUDA(ctx, cudaMalloc((void **)&d_ri, s_rowidx.size() * sizeof(int32_t)));
-    GB_CUDA(ctx, cudaMalloc((void **)&vals, (size_t)nnz * 81 * sizeof(T)));
+    Scratch s_cp, s_ri, s_vals;
+    GB_CUDA(ctx, cudaMalloc(&s_cp.p, s_colptr.size() * sizeof(int64_t)));
+    GB_CUDA(ctx, cudaMalloc(&s_ri.p, s_rowidx.size() * sizeof(int32_t)));
+    GB_CUDA(ctx, cudaMalloc(&s_vals.p, (size_t)nnz * 81 * sizeof(T)));
+    int64_t *d_cp = s_cp.as<int64_t>();
+    int32_t *d_ri = s_ri.as<int32_t>();
+    T *vals = s_vals.as<T>();
     GB_CUDA(ctx, cudaMemcpyAsync(d_cp, s_colptr.data(), s_colptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     GB_CUDA(ctx, cudaMemcpyAsync(d_ri, s_rowidx.data(), s_rowidx.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     GB_CUDA(ctx, cudaMemsetAsync(vals, 0, (size_t)nnz * 81 * sizeof(T), st));
@@ -1131,10 +1137,8 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_LAUNCH(ctx);
     k_schur_explicit_diag<T><<<(ts.Nc * 81 + 255) / 256, 256, 0, st>>>(ts.Nc, Sdiag, d_cp, vals);
     GB_LAUNCH(ctx);
-    int rc = launch_check();
-    if (rc == GB_OK) rc = d2h(out, vals, (size_t)nnz * 81 * sizeof(T));
-    cudaFree(d_cp); cudaFree(d_ri); cudaFree(vals);
-    return rc;
+    GB_TRY(launch_check());
+    return d2h(out, vals, (size_t)nnz * 81 * sizeof(T));
   }
   int try_step(double *new_chi2, double *rho_den) override {
     GB_TRY(require(solved || solved_full, "gb_try_step before gb_solve"));
