@@ -154,6 +154,17 @@ def algorithmic_bytes(nc, npts, m, nrows, ntiles, sT, sS):
     return product, survey_k4
 
 
+def lm_iteration_bytes(nc, npts, m, sT, sS, k_pcg, accepted_fraction):
+    """algorithmic bytes of one LM iteration on the implicit-Schur path, with the PCG iterations
+    actually executed and the share of iterations that re-linearise (accepted steps)."""
+    V = 9 * nc * sT
+    k1k2 = m * (2 * sT + 8) + 9 * nc * sT + 3 * npts * sT + 2 * m * sT + 27 * m * sS + 81 * nc * sS + 9 * npts * sS + (9 * nc + 3 * npts) * sT
+    k3 = 2 * 9 * npts * sS + 27 * m * sS + (9 * nc + 3 * npts) * sT + V
+    k4 = 27 * m * sS + 4 * m + 9 * npts * sS + 81 * nc * sS + 10 * V
+    k5 = (27 * m * sS + 4 * m + 9 * npts * sS + 6 * npts * sT + V) + (12 * npts * sT + 4 * V + m * (2 * sT + 8))
+    return accepted_fraction * k1k2 + k3 + k_pcg * k4 + k5
+
+
 def run_reference(args):
     """CPU arm: the oracle port (the reference's Eigen CPU path cannot be built here: Eigen is absent)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -384,6 +395,16 @@ def main():
                "sample": f"LM iterations 2..{args.cpu_baseline_steps + 1} of the same workload from the same initial state "
                          f"(oracle/oracle_bal.cpp, explicit Schur + PCG, OpenMP, {dtc:.1f} s)"}
 
+    # whole LM iteration against the HBM roofline: SURVEY 8(d)'s algorithmic bytes (per rank) for the PCG iterations and
+    # re-linearisations this run actually executed, divided by the measured step time
+    k_avg = res["pcg_iterations_total"] / max(steps_done, 1)
+    acc_frac = res["accepted"] / max(steps_done, 1)
+    step_bytes = lm_iteration_bytes(nc, local.n_pts, info["n_obs"], sT, sS, k_avg, acc_frac)
+    step_gbps = step_bytes / (seconds / max(steps_done, 1)) / 1e9
+    lm_roofline = {"bytes_per_step": step_bytes, "pcg_iterations_per_step": k_avg, "accepted_fraction": acc_frac,
+                   "achieved": step_gbps, "peak": peak, "unit": "GB/s", "frac": step_gbps / peak,
+                   "note": "SURVEY 8(d) algorithmic bytes per LM iteration (implicit Schur), per rank, with the executed PCG "
+                           "iterations; at 10 PCG iterations and every step accepted the same formula gives 15.8 GB (Venice FP64)"}
     if args.solver != "pcg-schur":  # the product kernel is not event-timed on the full-system solver's host-driven loop
         roofline = None
     if rank == 0:
@@ -392,7 +413,8 @@ def main():
             "ms_per_step": 1e3 * seconds / max(steps_done, 1), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64" if tname == "f64" else "f32", "data": "synthetic",
             "config": dict(workload_config(prob, args.precision, world), solver=args.solver),
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "lm_roofline": lm_roofline,
+            "cpu_baseline": cpu,
             "pcg": {"iterations_per_step": [int(v) for v in traj[:, 3]], "total": int(res["pcg_iterations_total"]),
                     "ms_per_product_launch": prod_ms, "product_gbps": achieved,
                     "ms_per_iteration_rest": 1e3 * res["update_seconds"] / n_prod,
