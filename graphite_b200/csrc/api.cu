@@ -147,6 +147,8 @@ template <typename T, typename S> struct Problem : ProblemBase {
   T *Cg = nullptr, *part18 = nullptr, *part54 = nullptr, *part9 = nullptr, *sums54 = nullptr;
   T *dot_part = nullptr, *rz_part = nullptr;
   bool coop_update = false; // the fused PCG update needs all its CTAs co-resident
+  bool adaptive_pcg = true;  // enqueue the PCG iterations in two batches (see enqueue_pcg); GB_ADAPTIVE_PCG=0 disables
+  int64_t pcg_guess = 1 << 20; // iterations the previous solve executed
   bool fused_iter = false;  // reduction + exchange + update of one PCG iteration in one cooperative launch (k_pcg_iterate)
   int iter_grid = 0;
   bool iter_pre = true;
@@ -296,6 +298,8 @@ template <typename T, typename S> struct Problem : ProblemBase {
       const int64_t want = (Nc + PIT_WARPS - 1) / PIT_WARPS;
       iter_pre = want <= (int64_t)std::min(2, per_sm2) * sms;
       iter_grid = (int)std::min<int64_t>(want, (int64_t)(iter_pre ? std::min(2, per_sm2) : std::min(4, per_sm4)) * sms);
+      const char *env_a = getenv("GB_ADAPTIVE_PCG");
+      adaptive_pcg = !(env_a && env_a[0] == '0');
       const char *env = getenv("GB_FUSED_ITER");
       fused_iter = coop && iter_grid >= 1 && !(env && env[0] == '0');
       GB_TRY(dalloc(cta_part, 2 * (size_t)std::max(iter_grid, 1)));
@@ -861,7 +865,20 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_LAUNCH(ctx);
     const T tol = (T)o->tolerance, ratio = (T)o->rejection_ratio;
     const int max_iter = (int)o->max_iterations, nc = ts.Nc;
+    // An iteration enqueued after the PCG has stopped returns at once, but its two launches still cost ~25 us (the
+    // product grid is 1 CTA per SM with 217 KB of shared memory each: 162 such pairs per 50 LM iterations of the
+    // Venice run = 2.7 % of the time).  So only as many iterations as the previous solve needed, plus two, are enqueued
+    // at first; if that is fewer than max_iterations the state is read back (one host round trip) and the rest follows
+    // only when the PCG is still running.  All ranks see the same state and take the same branch.
+    const int64_t first_batch = adaptive_pcg ? std::min<int64_t>(o->max_iterations, pcg_guess + 2) : o->max_iterations;
+    int64_t last = first_batch;
     for (int64_t k = 0; k < o->max_iterations; k++) {
+      if (k == first_batch) {
+        GB_TRY(store_host(h_state, pcg_state + 2 * k, sizeof(PcgState<T>)));
+        GB_CUDA(ctx, cudaStreamSynchronize(st));
+        if (h_state->done) break;
+        last = o->max_iterations;
+      }
       const bool fused = fused_iter && (ctx->nranks == 1 || p2p_on); // without peer memory: separate kernels + NCCL
       GB_TRY(enqueue_schur_product(done_flag, pv, (int)k, fused));
       if (fused) {
@@ -897,7 +914,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
       }
       if (profiling && 3 * k + 2 < (int64_t)prof_ev.size()) GB_CUDA(ctx, cudaEventRecord(prof_ev[3 * k + 2], st));
     }
-    GB_TRY(store_host(h_state, pcg_state + 2 * o->max_iterations, sizeof(PcgState<T>)));
+    GB_TRY(store_host(h_state, pcg_state + 2 * last, sizeof(PcgState<T>)));
     GB_TRY(launch_check());
     last_pcg = *o;
     solved = true;
@@ -1070,6 +1087,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
       GB_TRY(d2h(delta_host, delta, dimH * sizeof(T)));
     }
     GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    pcg_guess = h_state->iter;
     if (info) {
       info->pcg_iterations = h_state->iter;
       info->rz_final = (double)h_state->rz;
@@ -1226,6 +1244,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
       const T denom = (T)(h_scalars[1] + h_scalars[2]) + (T)1.0e-3;
       const T rho = (chi2 - new_chi2) / denom;
       const int64_t k_exec = full ? full_info.pcg_iterations : h_state->iter;
+      if (!full) pcg_guess = k_exec;
       R.pcg_iterations_total += k_exec;
       if (profiling && !full) {
         // launches 0 .. k_exec-1 did the work (a launch after the stop flag returns at once), except that an
