@@ -49,7 +49,7 @@ class LMOptions(C.Structure):
     _fields_ = [("initial_damping", C.c_double), ("iterations", C.c_int64), ("use_identity", C.c_int32),
                 ("verbose", C.c_int32), ("pcg", PcgOptions), ("stop_flag", C.POINTER(C.c_int32)),
                 ("resume", C.c_int32), ("profile_product", C.c_int32), ("initial_nu", C.c_double),
-                ("defer_final_linearize", C.c_int32), ("reserved2", C.c_int32)]
+                ("defer_final_linearize", C.c_int32), ("early_stop", C.c_int32)]
 
 
 class LMResult(C.Structure):
@@ -347,10 +347,10 @@ class Problem:
 
     def lm(self, iterations=50, initial_damping=1e-4, pcg_iterations=10, pcg_tolerance=1.0, rejection_ratio=5.0,
            use_identity=False, verbose=False, resume=False, initial_nu=2.0, profile_product=False, solver="pcg-schur",
-           defer_final_linearize=False):
+           defer_final_linearize=False, early_stop=False):
         o = LMOptions(initial_damping, iterations, int(use_identity), int(verbose),
                       PcgOptions(pcg_iterations, pcg_tolerance, rejection_ratio, SOLVERS[solver], 0), None, int(resume),
-                      int(profile_product), float(initial_nu), int(defer_final_linearize), 0)
+                      int(profile_product), float(initial_nu), int(defer_final_linearize), int(early_stop))
         res = LMResult()
         traj = np.zeros((max(iterations, 1), 4))
         self.ctx.check(self.L.gb_lm(self.h, C.byref(o), C.byref(res), _ptr(traj)))

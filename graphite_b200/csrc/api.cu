@@ -1218,6 +1218,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     }
     R.initial_chi2 = (double)chi2;
     bool run = true;
+    int num_bad = 0;          // levenberg_marquardt2: consecutive accepted steps with < 0.1 % decrease
     bool lin_pending = false; // an accepted step's re-linearisation is in flight; its time is read after the next sync
     int64_t it = 0;
     for (; it < o->iterations && run; it++) {
@@ -1257,7 +1258,8 @@ template <typename T, typename S> struct Problem : ProblemBase {
           R.update_seconds += ms * 1e-3;
         }
       }
-      if (solve_ok && std::isfinite((double)new_chi2) && rho > T(0)) {
+      const bool accepted_now = solve_ok && std::isfinite((double)new_chi2) && rho > T(0);
+      if (accepted_now) {
         double alpha = 1.0 - std::pow(2.0 * (double)rho - 1.0, 3);
         alpha = std::max(std::min(alpha, 2.0 / 3.0), 1.0 / 3.0);
         mu_l *= (T)alpha;
@@ -1288,10 +1290,16 @@ template <typename T, typename S> struct Problem : ProblemBase {
       }
       if (o->verbose)
         printf("%6ld %22.12g %22.12g %16.8g  pcg %ld\n", (long)it, (double)chi2, (double)new_chi2, (double)mu_l, (long)k_exec);
+      const T initial_chi2 = chi2;
       chi2 = new_chi2;
       if (!std::isfinite((double)mu_l)) run = false;
       if (rho == T(0)) { it++; break; }
       if (o->stop_flag && *o->stop_flag) { it++; break; }
+      if (o->early_stop && accepted_now) { // levenberg_marquardt.hpp:403-413
+        if ((initial_chi2 - new_chi2) * T(1.0e3) < initial_chi2) num_bad++;
+        else num_bad = 0;
+        if (num_bad >= 3) { it++; break; }
+      }
     }
     GB_CUDA(ctx, cudaEventRecord(ev[7], st));
     GB_CUDA(ctx, cudaStreamSynchronize(st));

@@ -231,7 +231,9 @@ typedef struct {
    * of being done before returning.  For callers that run one iteration per call and upload fresh vertices in between,
    * where that linearisation would be computed twice. */
   int32_t defer_final_linearize;
-  int32_t reserved2;
+  /* != 0: optimizer::levenberg_marquardt2 (levenberg_marquardt.hpp:255-417), the ORB-SLAM-like early termination: an
+   * accepted step that lowers chi2 by less than 0.1 % counts as "bad", three bad accepted steps in a row end the loop. */
+  int32_t early_stop;
 } gb_lm_options;
 
 typedef struct {

@@ -520,6 +520,26 @@ def test_user_defined_factor_drops_in(ctx, user_factor_lib):
         P.close()
 
 
+def test_early_stop_rule_of_levenberg_marquardt2(ctx):
+    """gb_lm_options.early_stop = optimizer::levenberg_marquardt2 (levenberg_marquardt.hpp:255-417): the same iterations as
+    levenberg_marquardt, ended after three accepted steps in a row that each lower chi2 by less than 0.1 %."""
+    prob = synthetic.make_named("ladybug-49")
+    P = binding.problem_from_bal(ctx, prob, "f64-f64")
+    full, _ = P.lm(iterations=50)
+    bad, stop = 0, len(full)
+    for i, (c0, c1) in enumerate(full[:, :2]):
+        if c1 != c0:  # accepted (a rejected step reports the unchanged cost)
+            bad = bad + 1 if (c0 - c1) * 1e3 < c0 else 0
+            if bad >= 3:
+                stop = i + 1
+                break
+    assert stop < len(full), "the rule must fire inside 50 iterations on this problem"
+    P.set_vertices(prob.cams, prob.pts)
+    early, res = P.lm(iterations=50, early_stop=True)
+    assert len(early) == stop and np.array_equal(early, full[:stop])
+    P.close()
+
+
 def test_revert_restores_the_state_exactly(ctx):
     prob = synthetic.make_named("ladybug-49")
     P = binding.problem_from_bal(ctx, prob, "f64-f64")
