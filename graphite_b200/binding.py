@@ -58,7 +58,8 @@ class LMResult(C.Structure):
                 ("pcg_iterations_total", C.c_int64), ("seconds_total", C.c_double), ("seconds_linearize", C.c_double),
                 ("seconds_prepare", C.c_double), ("seconds_pcg", C.c_double), ("seconds_backsubst", C.c_double),
                 ("seconds_cost", C.c_double), ("final_nu", C.c_double), ("product_launches", C.c_int64),
-                ("product_seconds", C.c_double), ("update_seconds", C.c_double)]
+                ("product_seconds", C.c_double), ("update_seconds", C.c_double), ("termination", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 SOLVERS = {"pcg-schur": 0, "pcg": 1}  # names of examples/bal.cu --solver

@@ -141,6 +141,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
   T2 *obs = nullptr, *res = nullptr, *obs_stage = nullptr; // obs/res per storage slot; stage in caller order
   T2 *obs_stage2[2] = {nullptr, nullptr};                   // double-buffered staging of the asynchronous upload
   cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+  cudaEvent_t ev_slot_free = nullptr;
   bool staged[2] = {false, false};
   const int64_t *d_perm = nullptr;                          // sorted position -> caller index (null = identity)
   S2 *J = nullptr; // tile-major [ntiles][12][256]
@@ -222,6 +223,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     for (auto &e : ev) if (e) cudaEventDestroy(e);
     for (auto &e : prof_ev) cudaEventDestroy(e);
     for (auto &e : ev_stage) if (e) cudaEventDestroy(e);
+    if (ev_slot_free) cudaEventDestroy(ev_slot_free);
   }
   int64_t device_bytes() const override { return bytes; }
   int exchange_mode() const override { return ctx->nranks <= 1 ? 0 : (p2p_on ? 2 : 1); }
@@ -408,6 +410,14 @@ template <typename T, typename S> struct Problem : ProblemBase {
     }
     pp.half_bytes = half; pp.slot_bytes = slot;
     pp.counter = d_counter; pp.seq = d_seq; pp.error = h_p2p_err;
+    {
+      // ranks are only loosely in step on the host (structure builds, uploads): a consumer waits this long for a peer
+      // before the call fails with GB_ERR_NCCL (every multi-rank entry point checks the flag after its synchronise)
+      const char *envt = getenv("GB_P2P_TIMEOUT_S");
+      double sec = envt ? atof(envt) : 120.0;
+      if (!(sec > 0.0)) sec = 120.0;
+      pp.timeout_ns = (unsigned long long)(sec * 1e9);
+    }
     p2p_on = true;
     return GB_OK;
   }
@@ -473,7 +483,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     obs_caller = obs_stage;
     GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     have_obs = true;
-    linearized = prepared = solved = stepped = false;
+    linearized = prepared = solved = solved_full = full_lin_valid = stepped = false;
     return GB_OK;
   }
   // Double-buffered observation upload on the context's copy stream: the H2D copy of the NEXT batch overlaps whatever
@@ -485,8 +495,13 @@ template <typename T, typename S> struct Problem : ProblemBase {
     if (!obs_stage2[slot]) {
       GB_TRY(dalloc(obs_stage2[slot], hs.M));
       GB_CUDA(ctx, cudaEventCreateWithFlags(&ev_stage[slot], cudaEventDisableTiming));
+      if (!ev_slot_free) GB_CUDA(ctx, cudaEventCreateWithFlags(&ev_slot_free, cudaEventDisableTiming));
       GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // dalloc's memset is on the compute stream
     }
+    // the slot may still be read by work already enqueued on the compute stream (the scatter of its last commit, a
+    // user factor reading obs_caller): the copy starts only after that work, not after work enqueued later
+    GB_CUDA(ctx, cudaEventRecord(ev_slot_free, ctx->stream));
+    GB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ev_slot_free, 0));
     GB_CUDA(ctx, cudaMemcpyAsync(obs_stage2[slot], o, 2 * hs.M * sizeof(T), cudaMemcpyHostToDevice, ctx->copy_stream));
     GB_CUDA(ctx, cudaEventRecord(ev_stage[slot], ctx->copy_stream));
     staged[slot] = true;
@@ -516,7 +531,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     camx_valid = true;
     GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     have_vertices = true;
-    linearized = prepared = solved = stepped = false;
+    linearized = prepared = solved = solved_full = full_lin_valid = stepped = false;
     return GB_OK;
   }
   int set_factor(gb_factor_fn fn, void *user) override {
@@ -793,6 +808,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
   int enqueue_prepare_tiles_only() {
     k_prepare_cams<T, S><<<ts.nchunks, PC_THREADS, 0, ctx->stream>>>(ts, J, W, h, part54);
     GB_LAUNCH(ctx);
+    full_lin_valid = false; // part54 now holds the Schur sums, not the full-system solver's Jc^T Jc sums
     return GB_OK;
   }
   int enqueue_prepare() {
@@ -802,6 +818,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_LAUNCH(ctx);
     k_prepare_cams<T, S><<<ts.nchunks, PC_THREADS, 0, st>>>(ts, J, W, h, part54);
     GB_LAUNCH(ctx);
+    full_lin_valid = false; // part54 now holds the Schur sums, not the full-system solver's Jc^T Jc sums
     const bool multi = ctx->nranks > 1;
     const int xchg = (multi && exchange_p2p<T>((size_t)ts.Nc * 54)) ? 1 : 0; // push / pull fused into the two launches
     k_cam_reduce_prepare<T><<<ts.Nc, 288, 0, st>>>(ts, part54, 0, sums54, multi ? 0 : 1, mu, use_identity, diagB, gc,
@@ -984,6 +1001,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_TRY(enqueue_linearize());
     GB_TRY(store_host(h_scalars, scalars, sizeof(double)));
     GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    GB_TRY(p2p_check());
     last_chi2 = (double)(T)h_scalars[0];
     if (chi2) *chi2 = last_chi2;
     return GB_OK;
@@ -1001,7 +1019,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
   int d2h(void *dst, const void *src, size_t n) {
     GB_CUDA(ctx, cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, ctx->stream));
     GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return GB_OK;
+    return p2p_check();
   }
   int get_gradient(void *out) override {
     GB_TRY(require(linearized, "gb_get_gradient before gb_linearize"));
@@ -1087,6 +1105,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
       GB_TRY(d2h(delta_host, delta, dimH * sizeof(T)));
     }
     GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    GB_TRY(p2p_check());
     pcg_guess = h_state->iter;
     if (info) {
       info->pcg_iterations = h_state->iter;
@@ -1183,7 +1202,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_TRY(enqueue_revert());
     GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     stepped = false;
-    return GB_OK;
+    return p2p_check();
   }
 
   // optimizer::levenberg_marquardt (levenberg_marquardt.hpp:109-242)
@@ -1191,6 +1210,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_TRY(require(have_obs && have_vertices, "gb_lm needs observations and vertices"));
     GB_TRY(require(o && o->iterations >= 0, "bad LM options"));
     GB_TRY(require(o->pcg.solver == GB_SOLVER_PCG_SCHUR || o->pcg.solver == GB_SOLVER_PCG_FULL, "unknown solver"));
+    GB_TRY(require(o->pcg.max_iterations >= 0 && o->pcg.max_iterations < (1 << 20), "bad PCG options"));
     const bool full = o->pcg.solver == GB_SOLVER_PCG_FULL;
     if (full) GB_TRY(full_buffers());
     cudaStream_t st = ctx->stream;
@@ -1292,17 +1312,18 @@ template <typename T, typename S> struct Problem : ProblemBase {
         printf("%6ld %22.12g %22.12g %16.8g  pcg %ld\n", (long)it, (double)chi2, (double)new_chi2, (double)mu_l, (long)k_exec);
       const T initial_chi2 = chi2;
       chi2 = new_chi2;
-      if (!std::isfinite((double)mu_l)) run = false;
-      if (rho == T(0)) { it++; break; }
-      if (o->stop_flag && *o->stop_flag) { it++; break; }
+      if (!std::isfinite((double)mu_l)) { run = false; R.termination = GB_LM_DAMPING_NOT_FINITE; }
+      if (rho == T(0)) { it++; R.termination = GB_LM_RHO_ZERO; break; }
+      if (o->stop_flag && *o->stop_flag) { it++; R.termination = GB_LM_STOP_FLAG; break; }
       if (o->early_stop && accepted_now) { // levenberg_marquardt.hpp:403-413
         if ((initial_chi2 - new_chi2) * T(1.0e3) < initial_chi2) num_bad++;
         else num_bad = 0;
-        if (num_bad >= 3) { it++; break; }
+        if (num_bad >= 3) { it++; R.termination = GB_LM_EARLY_STOP; break; }
       }
     }
     GB_CUDA(ctx, cudaEventRecord(ev[7], st));
     GB_CUDA(ctx, cudaStreamSynchronize(st));
+    GB_TRY(p2p_check());
     if (lin_pending) { cudaEventElapsedTime(&ms, ev[8], ev[9]); acc[0] += ms; lin_pending = false; }
     cudaEventElapsedTime(&ms, ev[6], ev[7]);
     stepped = false;

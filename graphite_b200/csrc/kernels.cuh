@@ -52,12 +52,6 @@ namespace gb {
 constexpr int CAM_STRIDE = 10; // padded camera row
 constexpr int NPLANES = 12;
 // dynamic shared memory of the super-tile kernels, in elements of T
-#ifndef PRODUCT_PIPE
-#define PRODUCT_PIPE 2
-#endif
-#ifndef J_EVICT_FIRST
-#define J_EVICT_FIRST 1
-#endif
 #ifndef LIN_MIN_BLOCKS
 #define LIN_MIN_BLOCKS 2
 #endif
@@ -806,227 +800,26 @@ k_cam_reduce_prepare(DevStruct ds, const T *__restrict__ part, int from_sums, T 
 }
 
 // ---------------------------------------------------------------------------------------------
-// K4: matrix-free Schur product, one CTA per super-tile, tiles streamed through a TMA pipeline.
+// K4: matrix-free Schur product; tiles streamed through a TMA pipeline.
 //   xs = D_c x (10-padded rows).
 //   y_o = Jc x_c ; t_p = sum_o Jp^T y_o ; w_p = W_p t_p ; z_o = Jp w_p ; v_o = Jc^T (y_o - z_o)
 //   row[camera] += sum over the camera's segment of v_o      ( = (B - E W E^T) x restricted to the super-tile )
 // replaces execute_schur_vector_multiply (schur.hpp:347-393) on an explicit S.
 //
-// Shared memory: NSTAGE stages of {J tile (12 planes x 256 x vec2<S>), packed tile record, W of the tile's
-// points}, each filled by three bulk copies that complete on the stage's mbarrier; the camera vector rows and
-// the accumulator rows of the super-tile's cameras; small staging for the point sums.  The camera staging
-// (256 x 9) reuses the J region of the stage being consumed (its values are in registers by then).
-// While tile i is processed, tiles i+1 .. i+NSTAGE-1 are in flight, independent of the barriers below.
-// ---------------------------------------------------------------------------------------------
-template <typename T, typename S> struct SchurSmem {
-  static constexpr int J_BYTES = NPLANES * TILE * (int)sizeof(typename V2<S>::type);
-  static constexpr int W_BYTES = TILE_PTS * WST<T>::value * (int)sizeof(T);
-  static constexpr int STAGE_BYTES = J_BYTES + REC_BYTES + W_BYTES;
-  // inside the J region once its values are in registers: camera staging [TILE*9], then point sums [TILE_PTS*3]
-  static constexpr int SV_IN_STAGE = 0;
-  static constexpr int SW_IN_STAGE = TILE * 9 * (int)sizeof(T);
-  static constexpr int XL_OFF(int nstage) { return nstage * STAGE_BYTES; }
-  static constexpr int ACC_OFF(int nstage) { return XL_OFF(nstage) + SLOT_CAP * 9 * (int)sizeof(T); }      // 2 workers
-  static constexpr int SV3_OFF(int nstage) { return ACC_OFF(nstage) + 2 * SLOT_CAP * 9 * (int)sizeof(T); } // 2 workers
-  static constexpr int BAR_OFF(int nstage) { return SV3_OFF(nstage) + 2 * TILE * 3 * (int)sizeof(T); }
-  static constexpr int TOTAL(int nstage) { return BAR_OFF(nstage) + 64; }
-  static_assert(SW_IN_STAGE + TILE_PTS * 3 * (int)sizeof(T) <= J_BYTES, "staging must fit in the J region");
-};
-
-// The CTA has two WORKERS of 256 threads; worker w processes tiles w, w+2, ... of the super-tile with its own
-// accumulator rows (summed in fixed order at the end), so twice as many warps hide the shared-memory and FP64
-// latencies of the short per-tile phases while the TMA keeps the next tiles in flight.
+// A CTA has two WORKERS of 256 threads; worker w consumes the tiles of parity w of the CTA's tile sequence (ring index
+// i) with its own accumulator rows (added in a fixed order at the end of a super-tile).  Shared memory:
+//   - a J ring of 2 slots, one per worker.  The 48 KB Jacobian block of a tile is dead as soon as its values are in
+//     registers, so right after the worker's first barrier the slot is refilled with the worker's NEXT tile (i + 2),
+//     which then has the whole tile time to land;
+//   - the small per-tile data that stays live during the tile (record 2.4 KB, W rows 6 KB) in its own 4-deep ring;
+//   - staging areas per worker (the point staging aliases the camera staging, they are never live together).
+// Tile i uses mbarrier i % 4; tiles i and i + 4 belong to the same worker, so a parity wait can never run a phase ahead.
+// (History, profiles/README.md: a 3-stage ring refilled at the END of a tile polled its refill flag five times per
+// tile: 249 us -> 232 us with the early refill.)
 // FULL = true turns the same pipeline into the full-system product J^T J u of the matrix-free PCGSolver
 // (solver/pcg.hpp:141-163, kernels compute_Jv / compute_JtPv in ops/product.hpp): the W stage then carries the point part
 // of the direction (u_p, stride WST), y = Jc u_c + Jp u_p, the point sums sum_o Jp^T y go straight to out_p, and the
 // camera rows accumulate Jc^T y.
-template <typename T, typename S, int NSTAGE, bool FULL>
-__global__ void __launch_bounds__(2 * TILE, 1)
-k_schur_product(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *__restrict__ W,
-                const T *__restrict__ xs, T *__restrict__ part /*[nrows][9]*/, const int *__restrict__ done_flag,
-                T *__restrict__ out_p /*FULL: [Np][3]*/) {
-  using SM = SchurSmem<T, S>;
-  using S2 = typename V2<S>::type;
-  extern __shared__ __align__(128) unsigned char smem[];
-  if (done_flag && *done_flag) return; // PCG already stopped: nothing to do (uniform across the grid)
-  const int worker = threadIdx.x >> 8, t = threadIdx.x & (TILE - 1);
-  T *xl = reinterpret_cast<T *>(smem + SM::XL_OFF(NSTAGE));
-  T *acc_all = reinterpret_cast<T *>(smem + SM::ACC_OFF(NSTAGE));
-  T *acc = acc_all + worker * SLOT_CAP * 9;
-  T *sv3 = reinterpret_cast<T *>(smem + SM::SV3_OFF(NSTAGE)) + worker * TILE * 3;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM::BAR_OFF(NSTAGE));
-  // persistent CTA: a contiguous range of super-tiles = a contiguous range of tiles; the TMA ring runs across
-  // super-tile boundaries, only the camera rows (xl) and the accumulators are switched there
-  const int st_begin = ds.cta_st[blockIdx.x], st_end = ds.cta_st[blockIdx.x + 1];
-  const int tile0 = ds.st_tile[st_begin], ntl = ds.st_tile[st_end] - tile0;
-#if J_EVICT_FIRST
-  const uint64_t pol = l2_policy_evict_first();
-#endif
-
-  auto issue = [&](int tile, int s, int p0, int np) {
-    unsigned char *base = smem + s * SM::STAGE_BYTES;
-    const uint32_t wbytes = (uint32_t)(np * WST<T>::value * (int)sizeof(T));
-    mbar_expect_tx(&bars[s], (uint32_t)(SM::J_BYTES + REC_BYTES) + wbytes);
-#if J_EVICT_FIRST
-    bulk_g2s_hint(base, J + (int64_t)tile * NPLANES * TILE, SM::J_BYTES, &bars[s], pol);
-    bulk_g2s_hint(base + SM::J_BYTES, ds.trec + (int64_t)tile * REC_BYTES, REC_BYTES, &bars[s], pol);
-#else
-    bulk_g2s(base, J + (int64_t)tile * NPLANES * TILE, SM::J_BYTES, &bars[s]);
-    bulk_g2s(base + SM::J_BYTES, ds.trec + (int64_t)tile * REC_BYTES, REC_BYTES, &bars[s]);
-#endif
-    bulk_g2s(base + SM::J_BYTES + REC_BYTES, W + (int64_t)p0 * WST<T>::value, wbytes, &bars[s]);
-  };
-
-  // issued[s] = number of tiles issued into stage s so far.  Consecutive tiles of one stage are consumed by
-  // alternating workers, so a worker could reach its wait for tile i + NSTAGE before the other worker's tile i has
-  // even landed; a parity wait one phase ahead would then succeed spuriously.  Waiting first until the tile has been
-  // issued (which happens only after tile i was consumed) closes that window.
-  volatile int *issued = reinterpret_cast<volatile int *>(bars + NSTAGE);
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; s++) { mbar_init(&bars[s], 1); issued[s] = 0; }
-    mbar_fence_init();
-    fence_proxy_async();
-    for (int i = 0; i < NSTAGE && i < ntl; i++) {
-      const TileMeta tm = ds.tmeta[tile0 + i];
-      issue(tile0 + i, i, tm.p0, tm.np);
-      issued[i] = 1;
-    }
-  }
-
-  for (int st = st_begin; st < st_end; st++) {
-    const int row0 = ds.st_row[st], nslots = ds.st_row[st + 1] - row0;
-    for (int i = threadIdx.x; i < nslots * 9; i += 2 * TILE) {
-      const int s = i / 9, k = i - 9 * s;
-      xl[i] = xs[(int64_t)ds.row_cam[row0 + s] * CAM_STRIDE + k];
-    }
-    for (int i = t; i < nslots * 9; i += TILE) acc[i] = T(0);
-    __syncthreads();
-    const int ib = ds.st_tile[st] - tile0, ie = ds.st_tile[st + 1] - tile0; // ring indices of this super-tile
-    for (int i = ib + ((ib ^ worker) & 1); i < ie; i += 2) {                 // worker w takes ring indices of parity w
-      const int s = i % NSTAGE;
-      while (issued[s] < i / NSTAGE + 1) { } // see above; almost never spins
-      mbar_wait(&bars[s], (uint32_t)((i / NSTAGE) & 1));
-      unsigned char *base = smem + s * SM::STAGE_BYTES;
-      const S2 *Js = reinterpret_cast<const S2 *>(base);
-      const unsigned char *rec = base + SM::J_BYTES;
-      const T *Ws = reinterpret_cast<const T *>(base + SM::J_BYTES + REC_BYTES);
-      const TileMeta tm = *reinterpret_cast<const TileMeta *>(rec + REC_META);
-      const int next_p0 = reinterpret_cast<const int32_t *>(rec + REC_NEXT)[2 * (NSTAGE - 1)];
-      const int next_np = reinterpret_cast<const int32_t *>(rec + REC_NEXT)[2 * (NSTAGE - 1) + 1];
-      const uint32_t om = reinterpret_cast<const uint32_t *>(rec + REC_OMETA)[t];
-      const int cslot = (int)(om >> 16), rank = (int)((om >> 8) & 0xffu), ptl = (int)(om & 0xffu);
-      T jc[18], jp[6], y0 = T(0), y1 = T(0);
-#pragma unroll
-      for (int j = 0; j < 9; j++) {
-        const S2 v = Js[j * TILE + t];
-        jc[2 * j] = (T)v.x;
-        jc[2 * j + 1] = (T)v.y;
-      }
-#pragma unroll
-      for (int j = 0; j < 3; j++) {
-        const S2 v = Js[(9 + j) * TILE + t];
-        jp[2 * j] = (T)v.x;
-        jp[2 * j + 1] = (T)v.y;
-      }
-      {
-        const T *x = xl + cslot * 9;
-#pragma unroll
-        for (int j = 0; j < 9; j++) {
-          const T xv = x[j];
-          y0 += jc[2 * j] * xv;
-          y1 += jc[2 * j + 1] * xv;
-        }
-      }
-      if (FULL) {
-        const T *u = Ws + ptl * WST<T>::value;
-        y0 += jp[0] * u[0] + jp[2] * u[1] + jp[4] * u[2];
-        y1 += jp[1] * u[0] + jp[3] * u[1] + jp[5] * u[2];
-      }
-      sv3[rank * 3 + 0] = jp[0] * y0 + jp[1] * y1; // staged at the position in point order
-      sv3[rank * 3 + 1] = jp[2] * y0 + jp[3] * y1;
-      sv3[rank * 3 + 2] = jp[4] * y0 + jp[5] * y1;
-      worker_sync(worker); // also: every thread has its J values in registers, the stage's J region may be reused
-      T *sv = reinterpret_cast<T *>(base + SM::SV_IN_STAGE);
-      T *sw = reinterpret_cast<T *>(base + SM::SW_IN_STAGE);
-      {
-        const uint16_t *pt = reinterpret_cast<const uint16_t *>(rec + REC_PT);
-        for (int item = t; item < tm.np * 3; item += TILE) {
-          const int q = item / 3, k = item - 3 * q;
-          const int b = pt[q], e = pt[q + 1];
-          T a = T(0);
-          for (int row = b; row < e; row++) a += sv3[row * 3 + k];
-          if (FULL) out_p[(int64_t)(tm.p0 + q) * 3 + k] = a;
-          else sw[item] = a;
-        }
-      }
-      worker_sync(worker);
-      {
-        T d0 = y0, d1 = y1;
-        if (!FULL) {
-          const T t0 = sw[ptl * 3], t1 = sw[ptl * 3 + 1], t2 = sw[ptl * 3 + 2];
-          const T *w = Ws + ptl * WST<T>::value;
-          const T w0 = w[0] * t0 + w[1] * t1 + w[2] * t2;
-          const T w1 = w[1] * t0 + w[3] * t1 + w[4] * t2;
-          const T w2 = w[2] * t0 + w[4] * t1 + w[5] * t2;
-          d0 = y0 - (jp[0] * w0 + jp[2] * w1 + jp[4] * w2);
-          d1 = y1 - (jp[1] * w0 + jp[3] * w1 + jp[5] * w2);
-        }
-        // stage v = Jc^T d at the slot's own row: slots are in camera order, so camera segments are contiguous rows
-#pragma unroll
-        for (int k = 0; k < 9; k++) sv[t * 9 + k] = jc[2 * k] * d0 + jc[2 * k + 1] * d1;
-      }
-      worker_sync(worker);
-      {
-        // one thread per (segment, component triple): sum the segment's rows, add to the camera's accumulator row
-        const uint32_t *sg = reinterpret_cast<const uint32_t *>(rec + REC_SEG);
-        for (int item = t; item < tm.nseg * 3; item += TILE) {
-          const int q = item / 3, g = item - 3 * q;
-          const uint32_t e0 = sg[q], e1 = sg[q + 1];
-          const int b = (int)(e0 >> 16), e = (int)(e1 >> 16), cs = (int)(e0 & 0xffffu);
-          T a0 = T(0), a1 = T(0), a2 = T(0);
-          for (int row = b; row < e; row++) {
-            const T *r = sv + row * 9 + 3 * g;
-            a0 += r[0];
-            a1 += r[1];
-            a2 += r[2];
-          }
-          T *ar = acc + cs * 9 + 3 * g;
-          ar[0] += a0;
-          ar[1] += a1;
-          ar[2] += a2;
-        }
-      }
-      worker_sync(worker);
-      // the stage is free (all threads of the worker are past the barrier): refill it with tile i + NSTAGE, whose
-      // point range comes with the record just consumed (no dependent global load on the issue path)
-      if (t == 0 && i + NSTAGE < ntl) {
-        const int nxp0 = next_p0, nxnp = next_np;
-        fence_proxy_async();
-        issue(tile0 + i + NSTAGE, s, nxp0, nxnp);
-        __threadfence_block();
-        issued[s] = i / NSTAGE + 2;
-      }
-    }
-    __syncthreads();
-    // rows of this super-tile: worker 0 (even ring indices) + worker 1 (odd), fixed order
-    for (int i = threadIdx.x; i < nslots * 9; i += 2 * TILE) {
-      const int s = i / 9, k = i - 9 * s;
-      part[(int64_t)ds.row_out[row0 + s] * 9 + k] = acc_all[i] + acc_all[SLOT_CAP * 9 + i];
-    }
-    __syncthreads(); // xl / acc are rewritten by the next super-tile
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K4, second pipeline (PRODUCT_PIPE == 2).  ncu of the 3-stage ring above: a stage is refilled only when its tile is
-// completely processed, and the two workers consume concurrently, so the tile a worker needs next has been issued only
-// when the OTHER worker finished its previous one (5 polls per wait on average).  But the 48 KB Jacobian block of a tile
-// is dead as soon as its values are in registers, a fraction of a microsecond after the wait.  Here
-//   - the J ring has 2 slots, one per worker; right after the worker's first barrier (all threads hold their J values)
-//     the slot is refilled with the worker's NEXT tile (i + 2), which then has the whole tile time to land;
-//   - the small per-tile data that stays live during the tile (record 2.4 KB, W rows 6 KB) sits in its own 4-deep ring;
-//   - the staging areas get their own space (the point staging aliases the camera staging, they are never live together).
-// Tile i uses mbarrier i % 4; tiles i and i + 4 belong to the same worker, so a parity wait can never run a phase ahead.
 // ---------------------------------------------------------------------------------------------
 template <typename T, typename S> struct SchurSmem2 {
   static constexpr int J_BYTES = NPLANES * TILE * (int)sizeof(typename V2<S>::type);
@@ -1045,6 +838,125 @@ template <typename T, typename S> struct SchurSmem2 {
   static_assert(META_BYTES % 16 == 0 && STG_BYTES % 16 == 0, "TMA destinations must stay 16-byte aligned");
 };
 
+// One tile of the product, executed by the 256 threads of one worker after the tile's mbarrier wait.
+//   Js / rec / Ws: the tile's J slot, packed record and W rows in shared memory; xl: camera vector rows of the
+//   super-tile; acc: the worker's accumulator rows; sv / sw: the worker's staging.
+//   refill(next_p0, next_np) is called by the worker's thread 0 right after the first barrier (the J slot is free):
+//   it issues the bulk copies of the worker's next tile, whose point range comes with the record just consumed.
+template <typename T, typename S, bool FULL, typename Refill>
+__device__ __forceinline__ void product_tile(int worker, int t, const typename V2<S>::type *Js, const unsigned char *rec,
+                                             const T *Ws, const T *xl, T *acc, T *sv, T *sw, T *__restrict__ out_p,
+                                             Refill &&refill) {
+  using S2 = typename V2<S>::type;
+  T *sv3 = sv; // point-order staging: dead before the camera staging is written
+  const TileMeta tm = *reinterpret_cast<const TileMeta *>(rec + REC_META);
+  const int next_p0 = reinterpret_cast<const int32_t *>(rec + REC_NEXT)[2];  // tile + 2
+  const int next_np = reinterpret_cast<const int32_t *>(rec + REC_NEXT)[3];
+  const uint32_t om = reinterpret_cast<const uint32_t *>(rec + REC_OMETA)[t];
+  const int cslot = (int)(om >> 16), rank = (int)((om >> 8) & 0xffu), ptl = (int)(om & 0xffu);
+  T jc[18], jp[6], y0 = T(0), y1 = T(0);
+#pragma unroll
+  for (int j = 0; j < 9; j++) {
+    const S2 v = Js[j * TILE + t];
+    jc[2 * j] = (T)v.x;
+    jc[2 * j + 1] = (T)v.y;
+  }
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const S2 v = Js[(9 + j) * TILE + t];
+    jp[2 * j] = (T)v.x;
+    jp[2 * j + 1] = (T)v.y;
+  }
+  {
+    const T *x = xl + cslot * 9;
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+      const T xv = x[j];
+      y0 += jc[2 * j] * xv;
+      y1 += jc[2 * j + 1] * xv;
+    }
+  }
+  if (FULL) {
+    const T *u = Ws + ptl * WST<T>::value;
+    y0 += jp[0] * u[0] + jp[2] * u[1] + jp[4] * u[2];
+    y1 += jp[1] * u[0] + jp[3] * u[1] + jp[5] * u[2];
+  }
+  sv3[rank * 3 + 0] = jp[0] * y0 + jp[1] * y1; // staged at the position in point order
+  sv3[rank * 3 + 1] = jp[2] * y0 + jp[3] * y1;
+  sv3[rank * 3 + 2] = jp[4] * y0 + jp[5] * y1;
+  worker_sync(worker); // every thread of the worker has its J values in registers: the worker's J slot is free
+  if (t == 0) refill(next_p0, next_np);
+  {
+    const uint16_t *pt = reinterpret_cast<const uint16_t *>(rec + REC_PT);
+    for (int item = t; item < tm.np * 3; item += TILE) {
+      const int q = item / 3, k = item - 3 * q;
+      const int b = pt[q], e = pt[q + 1];
+      T a = T(0);
+      for (int row = b; row < e; row++) a += sv3[row * 3 + k];
+      if (FULL) out_p[(int64_t)(tm.p0 + q) * 3 + k] = a;
+      else sw[item] = a;
+    }
+  }
+  worker_sync(worker);
+  {
+    T d0 = y0, d1 = y1;
+    if (!FULL) {
+      const T t0 = sw[ptl * 3], t1 = sw[ptl * 3 + 1], t2 = sw[ptl * 3 + 2];
+      const T *w = Ws + ptl * WST<T>::value;
+      const T w0 = w[0] * t0 + w[1] * t1 + w[2] * t2;
+      const T w1 = w[1] * t0 + w[3] * t1 + w[4] * t2;
+      const T w2 = w[2] * t0 + w[4] * t1 + w[5] * t2;
+      d0 = y0 - (jp[0] * w0 + jp[2] * w1 + jp[4] * w2);
+      d1 = y1 - (jp[1] * w0 + jp[3] * w1 + jp[5] * w2);
+    }
+    // stage v = Jc^T d at the slot's own row: slots are in camera order, so camera segments are contiguous rows
+#pragma unroll
+    for (int k = 0; k < 9; k++) sv[t * 9 + k] = jc[2 * k] * d0 + jc[2 * k + 1] * d1;
+  }
+  worker_sync(worker);
+  {
+    // one thread per (segment, component triple): sum the segment's rows, add to the camera's accumulator row
+    const uint32_t *sg = reinterpret_cast<const uint32_t *>(rec + REC_SEG);
+    for (int item = t; item < tm.nseg * 3; item += TILE) {
+      const int q = item / 3, g = item - 3 * q;
+      const uint32_t e0 = sg[q], e1 = sg[q + 1];
+      const int b = (int)(e0 >> 16), e = (int)(e1 >> 16), cs = (int)(e0 & 0xffffu);
+      T a0 = T(0), a1 = T(0), a2 = T(0);
+      for (int row = b; row < e; row++) {
+        const T *r = sv + row * 9 + 3 * g;
+        a0 += r[0];
+        a1 += r[1];
+        a2 += r[2];
+      }
+      T *ar = acc + cs * 9 + 3 * g;
+      ar[0] += a0;
+      ar[1] += a1;
+      ar[2] += a2;
+    }
+  }
+  worker_sync(worker); // staging and the meta slot are free for the worker's next tile
+}
+
+// bulk copies of one tile into ring position i: J slot i & 1 (= its worker), meta slot and mbarrier i & 3.  The J and
+// record copies carry an L2 evict-first policy: the 1 GB stream is read once per pass, the ~70 MB of vectors every
+// pass re-reads then stay in the 126 MB L2 (-4.7 % on the kernel).
+template <typename T, typename S>
+__device__ __forceinline__ void product_issue(unsigned char *smem, uint64_t *bars, const DevStruct &ds,
+                                              const typename V2<S>::type *__restrict__ J, const T *__restrict__ W,
+                                              int tile, int i, int p0, int np, uint64_t pol) {
+  using SM = SchurSmem2<T, S>;
+  unsigned char *jdst = smem + (i & 1) * SM::J_BYTES;
+  unsigned char *mdst = smem + SM::META_OFF + (i & 3) * SM::META_BYTES;
+  uint64_t *bar = &bars[i & 3];
+  const uint32_t wbytes = (uint32_t)(np * WST<T>::value * (int)sizeof(T));
+  mbar_expect_tx(bar, (uint32_t)(SM::J_BYTES + REC_BYTES) + wbytes);
+  bulk_g2s_hint(jdst, J + (int64_t)tile * NPLANES * TILE, SM::J_BYTES, bar, pol);
+  bulk_g2s_hint(mdst, ds.trec + (int64_t)tile * REC_BYTES, REC_BYTES, bar, pol);
+  bulk_g2s(mdst + REC_BYTES, W + (int64_t)p0 * WST<T>::value, wbytes, bar);
+}
+
+// One launch = one product: one CTA per super-tile (exports, the full-system solver, the NCCL fallback path and the
+// stage timers; the Schur PCG itself runs k_pcg_solve, pcg_solve.cuh, which embeds the same pipeline).
 template <typename T, typename S, bool FULL>
 __global__ void __launch_bounds__(2 * TILE, 1)
 k_schur_product2(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *__restrict__ W,
@@ -1059,31 +971,11 @@ k_schur_product2(DevStruct ds, const typename V2<S>::type *__restrict__ J, const
   T *acc_all = reinterpret_cast<T *>(smem + SM::ACC_OFF);
   T *acc = acc_all + worker * SLOT_CAP * 9;
   T *sv = reinterpret_cast<T *>(smem + SM::STG_OFF + worker * SM::STG_BYTES);
-  T *sv3 = sv; // point-order staging: dead before the camera staging is written
   T *sw = reinterpret_cast<T *>(smem + SM::STG_OFF + worker * SM::STG_BYTES + SM::SV_BYTES);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM::BAR_OFF);
   const int st_begin = ds.cta_st[blockIdx.x], st_end = ds.cta_st[blockIdx.x + 1];
   const int tile0 = ds.st_tile[st_begin], ntl = ds.st_tile[st_end] - tile0;
-#if J_EVICT_FIRST
   const uint64_t pol = l2_policy_evict_first();
-#endif
-
-  // ring index i: J slot i & 1 (= its worker), meta slot and mbarrier i & 3
-  auto issue = [&](int tile, int i, int p0, int np) {
-    unsigned char *jdst = smem + (i & 1) * SM::J_BYTES;
-    unsigned char *mdst = smem + SM::META_OFF + (i & 3) * SM::META_BYTES;
-    uint64_t *bar = &bars[i & 3];
-    const uint32_t wbytes = (uint32_t)(np * WST<T>::value * (int)sizeof(T));
-    mbar_expect_tx(bar, (uint32_t)(SM::J_BYTES + REC_BYTES) + wbytes);
-#if J_EVICT_FIRST
-    bulk_g2s_hint(jdst, J + (int64_t)tile * NPLANES * TILE, SM::J_BYTES, bar, pol);
-    bulk_g2s_hint(mdst, ds.trec + (int64_t)tile * REC_BYTES, REC_BYTES, bar, pol);
-#else
-    bulk_g2s(jdst, J + (int64_t)tile * NPLANES * TILE, SM::J_BYTES, bar);
-    bulk_g2s(mdst, ds.trec + (int64_t)tile * REC_BYTES, REC_BYTES, bar);
-#endif
-    bulk_g2s(mdst + REC_BYTES, W + (int64_t)p0 * WST<T>::value, wbytes, bar);
-  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < SM::NMETA; s++) mbar_init(&bars[s], 1);
@@ -1091,7 +983,7 @@ k_schur_product2(DevStruct ds, const typename V2<S>::type *__restrict__ J, const
     fence_proxy_async();
     for (int i = 0; i < 2 && i < ntl; i++) {
       const TileMeta tm = ds.tmeta[tile0 + i];
-      issue(tile0 + i, i, tm.p0, tm.np);
+      product_issue<T, S>(smem, bars, ds, J, W, tile0 + i, i, tm.p0, tm.np, pol);
     }
   }
 
@@ -1109,94 +1001,12 @@ k_schur_product2(DevStruct ds, const typename V2<S>::type *__restrict__ J, const
       const S2 *Js = reinterpret_cast<const S2 *>(smem + (i & 1) * SM::J_BYTES);
       const unsigned char *rec = smem + SM::META_OFF + (i & 3) * SM::META_BYTES;
       const T *Ws = reinterpret_cast<const T *>(rec + REC_BYTES);
-      const TileMeta tm = *reinterpret_cast<const TileMeta *>(rec + REC_META);
-      const int next_p0 = reinterpret_cast<const int32_t *>(rec + REC_NEXT)[2];  // tile i + 2
-      const int next_np = reinterpret_cast<const int32_t *>(rec + REC_NEXT)[3];
-      const uint32_t om = reinterpret_cast<const uint32_t *>(rec + REC_OMETA)[t];
-      const int cslot = (int)(om >> 16), rank = (int)((om >> 8) & 0xffu), ptl = (int)(om & 0xffu);
-      T jc[18], jp[6], y0 = T(0), y1 = T(0);
-#pragma unroll
-      for (int j = 0; j < 9; j++) {
-        const S2 v = Js[j * TILE + t];
-        jc[2 * j] = (T)v.x;
-        jc[2 * j + 1] = (T)v.y;
-      }
-#pragma unroll
-      for (int j = 0; j < 3; j++) {
-        const S2 v = Js[(9 + j) * TILE + t];
-        jp[2 * j] = (T)v.x;
-        jp[2 * j + 1] = (T)v.y;
-      }
-      {
-        const T *x = xl + cslot * 9;
-#pragma unroll
-        for (int j = 0; j < 9; j++) {
-          const T xv = x[j];
-          y0 += jc[2 * j] * xv;
-          y1 += jc[2 * j + 1] * xv;
+      product_tile<T, S, FULL>(worker, t, Js, rec, Ws, xl, acc, sv, sw, out_p, [&](int next_p0, int next_np) {
+        if (i + 2 < ntl) {
+          fence_proxy_async();
+          product_issue<T, S>(smem, bars, ds, J, W, tile0 + i + 2, i + 2, next_p0, next_np, pol);
         }
-      }
-      if (FULL) {
-        const T *u = Ws + ptl * WST<T>::value;
-        y0 += jp[0] * u[0] + jp[2] * u[1] + jp[4] * u[2];
-        y1 += jp[1] * u[0] + jp[3] * u[1] + jp[5] * u[2];
-      }
-      sv3[rank * 3 + 0] = jp[0] * y0 + jp[1] * y1; // staged at the position in point order
-      sv3[rank * 3 + 1] = jp[2] * y0 + jp[3] * y1;
-      sv3[rank * 3 + 2] = jp[4] * y0 + jp[5] * y1;
-      worker_sync(worker); // every thread of the worker has its J values in registers: the worker's J slot is free
-      if (t == 0 && i + 2 < ntl) {
-        fence_proxy_async();
-        issue(tile0 + i + 2, i + 2, next_p0, next_np);
-      }
-      {
-        const uint16_t *pt = reinterpret_cast<const uint16_t *>(rec + REC_PT);
-        for (int item = t; item < tm.np * 3; item += TILE) {
-          const int q = item / 3, k = item - 3 * q;
-          const int b = pt[q], e = pt[q + 1];
-          T a = T(0);
-          for (int row = b; row < e; row++) a += sv3[row * 3 + k];
-          if (FULL) out_p[(int64_t)(tm.p0 + q) * 3 + k] = a;
-          else sw[item] = a;
-        }
-      }
-      worker_sync(worker);
-      {
-        T d0 = y0, d1 = y1;
-        if (!FULL) {
-          const T t0 = sw[ptl * 3], t1 = sw[ptl * 3 + 1], t2 = sw[ptl * 3 + 2];
-          const T *w = Ws + ptl * WST<T>::value;
-          const T w0 = w[0] * t0 + w[1] * t1 + w[2] * t2;
-          const T w1 = w[1] * t0 + w[3] * t1 + w[4] * t2;
-          const T w2 = w[2] * t0 + w[4] * t1 + w[5] * t2;
-          d0 = y0 - (jp[0] * w0 + jp[2] * w1 + jp[4] * w2);
-          d1 = y1 - (jp[1] * w0 + jp[3] * w1 + jp[5] * w2);
-        }
-        // stage v = Jc^T d at the slot's own row: slots are in camera order, so camera segments are contiguous rows
-#pragma unroll
-        for (int k = 0; k < 9; k++) sv[t * 9 + k] = jc[2 * k] * d0 + jc[2 * k + 1] * d1;
-      }
-      worker_sync(worker);
-      {
-        const uint32_t *sg = reinterpret_cast<const uint32_t *>(rec + REC_SEG);
-        for (int item = t; item < tm.nseg * 3; item += TILE) {
-          const int q = item / 3, g = item - 3 * q;
-          const uint32_t e0 = sg[q], e1 = sg[q + 1];
-          const int b = (int)(e0 >> 16), e = (int)(e1 >> 16), cs = (int)(e0 & 0xffffu);
-          T a0 = T(0), a1 = T(0), a2 = T(0);
-          for (int row = b; row < e; row++) {
-            const T *r = sv + row * 9 + 3 * g;
-            a0 += r[0];
-            a1 += r[1];
-            a2 += r[2];
-          }
-          T *ar = acc + cs * 9 + 3 * g;
-          ar[0] += a0;
-          ar[1] += a1;
-          ar[2] += a2;
-        }
-      }
-      worker_sync(worker); // staging and the meta slot are free for the worker's next tile
+      });
     }
     __syncthreads();
     for (int i = threadIdx.x; i < nslots * 9; i += 2 * TILE) {

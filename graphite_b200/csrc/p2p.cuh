@@ -29,7 +29,8 @@ struct P2P {
   unsigned long long half_bytes, slot_bytes; // receive area = [2 halves][nranks slots][slot_bytes]
   unsigned int *counter;                     // local: CTAs of the running producer that have finished pushing
   unsigned long long *seq;                   // local: epoch of the last exchange this rank has pushed
-  int *error;                                // local: set when a wait timed out (a peer died)
+  int *error;                                // local (pinned host): set when a wait timed out (a peer died)
+  unsigned long long timeout_ns;             // how long a consumer waits for a peer before it gives up (GB_P2P_TIMEOUT_S)
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
@@ -89,7 +90,7 @@ __device__ __forceinline__ void p2p_wait(const P2P &pp, unsigned long long epoch
     if (ld_acquire_sys(f) < epoch) {
       const unsigned long long t0 = global_timer_ns();
       while (ld_acquire_sys(f) < epoch) {
-        if (global_timer_ns() - t0 > 20000000000ull) { // 20 s: a peer is gone; fail loudly on the host instead of hanging
+        if (global_timer_ns() - t0 > pp.timeout_ns) { // a peer is gone: fail loudly on the host (p2p_check) instead of hanging
           *pp.error = 1;
           break;
         }

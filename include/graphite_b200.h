@@ -63,7 +63,8 @@ typedef struct {
   const int32_t *camera_index; /* host [num_observations] */
   const int32_t *point_index;  /* host [num_observations], local point index */
   int32_t tile_size;         /* max observations per tile, 0 = default (256, the storage tile) */
-  int32_t slot_cap;          /* max distinct cameras per super-tile, 0 = default (256) */
+  int32_t slot_cap;          /* max distinct cameras per super-tile, 0 = default = maximum (192); also the longest
+                              * supported track: a point with more observations is rejected (GB_ERR_UNSUPPORTED) */
   int64_t super_tile_observations; /* target observations per super-tile (one CTA), 0 = default M / (148*8) */
   int64_t flags;             /* GB_FLAG_* */
 } gb_problem_desc;
@@ -246,7 +247,13 @@ typedef struct {
   int64_t product_launches;  /* profile_product: executed launches of the Schur product kernel and their device time */
   double product_seconds;
   double update_seconds;     /* profile_product: device time of the rest of those PCG iterations (reduction, exchange, update) */
+  /* why the loop ended (levenberg_marquardt.hpp:224-241): GB_LM_DONE all iterations ran; GB_LM_DAMPING_NOT_FINITE the
+   * reference returns false here (gb_lm still returns GB_OK: the vertices hold the last accepted state); GB_LM_RHO_ZERO;
+   * GB_LM_STOP_FLAG; GB_LM_EARLY_STOP (levenberg_marquardt2, :403-413) */
+  int32_t termination;
+  int32_t reserved;
 } gb_lm_result;
+typedef enum { GB_LM_DONE = 0, GB_LM_DAMPING_NOT_FINITE = 1, GB_LM_RHO_ZERO = 2, GB_LM_STOP_FLAG = 3, GB_LM_EARLY_STOP = 4 } gb_lm_termination;
 
 /* Replaces: optimizer::levenberg_marquardt (levenberg_marquardt.hpp:109-242).  trajectory (optional,
  * host, [iterations][4]) receives initial chi2, current chi2, lambda, executed PCG iterations. */

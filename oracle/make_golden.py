@@ -154,6 +154,20 @@ def main(which):
         p = synthetic.make_named("venice-1778")
         second_run("venice-1778", p)
         run_case("venice-1778", p, "pcg-schur", "FP64-FP64", 50, timeout=6000)
+    if "mixed" in which:  # round 2: the precision matrix of examples/bal.cu:159-236 at the sizes round 1 left out
+        p = synthetic.make_named("venice-1778")
+        run_case("venice-1778", p, "pcg-schur", "FP32-FP32", 50, timeout=6000)
+        run_case("venice-1778", p, "pcg", "FP64-FP32", 50, timeout=6000)
+        run_case("venice-1778", p, "pcg", "FP64-BF16", 50, timeout=6000)
+        for name in ("ladybug-49", "trafalgar-257"):
+            p = synthetic.make_named(name)
+            run_case(name, p, "pcg", "FP64-BF16", 50)
+        p = synthetic.make_named("dubrovnik-356")
+        run_case("dubrovnik-356", p, "pcg-schur", "FP32-FP32", 50)
+    if "final" in which:  # BASELINE configs[4]: Final-13682 shape, FP32 / mixed
+        p = synthetic.make_named("final-13682")
+        run_case("final-13682", p, "pcg-schur", "FP32-FP32", 50, timeout=6000)
+        run_case("final-13682", p, "pcg", "FP64-FP32", 30, timeout=6000)
     # .gbal inputs are regenerated from the seed; do not ship them back
     for f in os.listdir(OUT):
         if f.endswith(".gbal"):

@@ -27,6 +27,7 @@
 #include <string>
 #include <vector>
 
+#include <cuda_bf16.h>
 #include <Eigen/Core>
 #include <graphite/common.hpp>
 
@@ -333,6 +334,7 @@ int main(int argc, char **argv) {
   if (a.precision == "FP64-FP64") return run<double, double>(a, p);
   if (a.precision == "FP32-FP32") return run<float, float>(a, p);
   if (a.precision == "FP64-FP32") return run<double, float>(a, p);
+  if (a.precision == "FP64-BF16") return run<double, __nv_bfloat16>(a, p); // examples/bal.cu:186-236, pcg only (types.hpp:10-19)
   fprintf(stderr, "unsupported precision\n");
   return 2;
 }
