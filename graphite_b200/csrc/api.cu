@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "pcg_solve.cuh"
 #include "structure.hpp"
 
 // ---- NCCL, bound at run time (the library must load on boxes where only torch's bundled NCCL exists) ----
@@ -131,7 +132,6 @@ struct ProblemBase {
 template <typename T, typename S> struct Problem : ProblemBase {
   using T2 = typename V2<T>::type;
   using S2 = typename V2<S>::type;
-  static constexpr int NSTAGE = 3; // TMA pipeline depth of the Schur product (fits 227 KB in FP64)
   DevStruct ts{};
   std::vector<void *> allocs;
   int64_t bytes = 0;
@@ -147,13 +147,14 @@ template <typename T, typename S> struct Problem : ProblemBase {
   S2 *J = nullptr; // tile-major [ntiles][12][256]
   T *Cg = nullptr, *part18 = nullptr, *part54 = nullptr, *part9 = nullptr, *sums54 = nullptr;
   T *dot_part = nullptr, *rz_part = nullptr;
-  bool coop_update = false; // the fused PCG update needs all its CTAs co-resident
-  bool adaptive_pcg = true;  // enqueue the PCG iterations in two batches (see enqueue_pcg); GB_ADAPTIVE_PCG=0 disables
+  // the PCG solve is ONE persistent cooperative kernel (k_pcg_solve, pcg_solve.cuh): one CTA per SM
+  int solve_grid = 0;
+  T *pbuf = nullptr, *st_dot = nullptr, *cta_red = nullptr;
+  unsigned int *work_counter = nullptr;
+  unsigned long long *d_timing = nullptr, *h_timing = nullptr; // per-iteration phase stamps of CTA 0 (profile_product)
+  int timing_cap = 0;
+  // NCCL fallback (no peer memory between the ranks): product + reduction + all-reduce + cooperative update per iteration
   int64_t pcg_guess = 1 << 20; // iterations the previous solve executed
-  bool fused_iter = false;  // reduction + exchange + update of one PCG iteration in one cooperative launch (k_pcg_iterate)
-  int iter_grid = 0;
-  bool iter_pre = true;
-  T *cta_part = nullptr;
   T *diagB = nullptr, *gc = nullptr, *scale = nullptr /*[9Nc+3Np]*/, *b = nullptr /*[9Nc+3Np]*/;
   T *W = nullptr, *h = nullptr;
   T *Sdiag = nullptr, *Minv = nullptr, *bS = nullptr, *dterm = nullptr;
@@ -178,7 +179,6 @@ template <typename T, typename S> struct Problem : ProblemBase {
   cudaEvent_t ev[10]; // [8], [9]: around the re-linearisation of an accepted step (read at the next synchronisation)
   double last_chi2 = 0.0;
   bool profiling = false;
-  std::vector<cudaEvent_t> prof_ev; // pairs around k_schur_tiles<MODE 0>, one pair per PCG iteration
   // user-defined factor: evaluated by the caller's kernel into caller-order buffers (gb_set_factor)
   gb_factor_fn ext_fn = nullptr;
   void *ext_user = nullptr;
@@ -221,7 +221,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     if (h_state) cudaFreeHost(h_state);
     if (h_p2p_err) cudaFreeHost(h_p2p_err);
     for (auto &e : ev) if (e) cudaEventDestroy(e);
-    for (auto &e : prof_ev) cudaEventDestroy(e);
+    if (h_timing) cudaFreeHost(h_timing);
     for (auto &e : ev_stage) if (e) cudaEventDestroy(e);
     if (ev_slot_free) cudaEventDestroy(ev_slot_free);
   }
@@ -288,35 +288,28 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_TRY(dalloc(part9, (size_t)ts.nrows * 9)); GB_TRY(dalloc(sums54, Nc * 54));
     GB_TRY(dalloc(dot_part, Nc)); GB_TRY(dalloc(rz_part, Nc));
     {
-      int per_sm = 0, sms = 0, coop = 0;
-      GB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_update<T>, 288, 0));
+      int per_sm = 0, per_sm_solve = 0, sms = 0, coop = 0;
       GB_CUDA(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
       GB_CUDA(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
-      coop_update = coop && (int64_t)per_sm * sms >= (Nc + PCG_CAMS - 1) / PCG_CAMS;
-      // one camera per warp with the prefetching variant when the grid allows it, else the lean variant on a larger grid
-      int per_sm2 = 0, per_sm4 = 0;
-      GB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_pcg_iterate<T, true>, PIT_THREADS, 0));
-      GB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm4, k_pcg_iterate<T, false>, PIT_THREADS, 0));
-      const int64_t want = (Nc + PIT_WARPS - 1) / PIT_WARPS;
-      iter_pre = want <= (int64_t)std::min(2, per_sm2) * sms;
-      iter_grid = (int)std::min<int64_t>(want, (int64_t)(iter_pre ? std::min(2, per_sm2) : std::min(4, per_sm4)) * sms);
-      const char *env_a = getenv("GB_ADAPTIVE_PCG");
-      adaptive_pcg = !(env_a && env_a[0] == '0');
-      const char *env = getenv("GB_FUSED_ITER");
-      fused_iter = coop && iter_grid >= 1 && !(env && env[0] == '0');
-      GB_TRY(dalloc(cta_part, 2 * (size_t)std::max(iter_grid, 1)));
+      // the super-tile kernels keep their camera accumulator rows in (opt-in sized) dynamic shared memory
+      GB_CUDA(ctx, cudaFuncSetAttribute(k_linearize<T, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_lin_bytes<T>()));
+      GB_CUDA(ctx, cudaFuncSetAttribute(k_linearize<T, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_lin_bytes<T>()));
+      GB_CUDA(ctx, cudaFuncSetAttribute(k_schur_product2<T, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        SchurSmem2<T, S>::TOTAL));
+      GB_CUDA(ctx, cudaFuncSetAttribute(k_schur_product2<T, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        SchurSmem2<T, S>::TOTAL));
+      GB_CUDA(ctx, cudaFuncSetAttribute(k_pcg_solve<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, SolveSmem<T, S>::TOTAL));
+      GB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_update<T>, 288, 0));
+      GB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_solve, k_pcg_solve<T, S>, SOLVE_THREADS,
+                                                                 SolveSmem<T, S>::TOTAL));
+      if (!coop || per_sm_solve < 1 || (int64_t)per_sm * sms < (Nc + PCG_CAMS - 1) / PCG_CAMS)
+        return ctx->fail(GB_ERR_UNSUPPORTED, "the device cannot co-schedule the PCG kernels (cooperative launch)");
+      solve_grid = sms; // the same on every rank: the per-CTA exchange pairs CTA b with CTA b of the peers
+      GB_TRY(dalloc(cta_red, 2 * (size_t)solve_grid));
+      GB_TRY(dalloc(pbuf, 2 * (size_t)dimc));
+      GB_TRY(dalloc(st_dot, (size_t)ts.nst));
+      GB_TRY(dalloc(work_counter, 1));
     }
-    // the super-tile kernels keep their camera accumulator rows in (opt-in sized) dynamic shared memory
-    GB_CUDA(ctx, cudaFuncSetAttribute(k_linearize<T, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_lin_bytes<T>()));
-    GB_CUDA(ctx, cudaFuncSetAttribute(k_linearize<T, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_lin_bytes<T>()));
-    GB_CUDA(ctx, cudaFuncSetAttribute(k_schur_product<T, S, NSTAGE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      SchurSmem<T, S>::TOTAL(NSTAGE)));
-    GB_CUDA(ctx, cudaFuncSetAttribute(k_schur_product<T, S, NSTAGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      SchurSmem<T, S>::TOTAL(NSTAGE)));
-    GB_CUDA(ctx, cudaFuncSetAttribute(k_schur_product2<T, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      SchurSmem2<T, S>::TOTAL));
-    GB_CUDA(ctx, cudaFuncSetAttribute(k_schur_product2<T, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      SchurSmem2<T, S>::TOTAL));
     GB_TRY(dalloc(diagB, 2 * dimc)); // diag(B) | g_c contiguous: one exchange for both on the multi-GPU path
     gc = diagB + dimc;
     GB_TRY(dalloc(scale, dimH)); GB_TRY(dalloc(b, dimH)); GB_TRY(dalloc(delta, dimH));
@@ -347,8 +340,10 @@ template <typename T, typename S> struct Problem : ProblemBase {
     const char *env = getenv("GB_P2P");
     int fail = (env && env[0] == '0') || n > P2P_MAX_RANKS || !g_nccl.AllGather ? 1 : 0;
     const size_t slot = (((size_t)54 * ts.Nc * sizeof(T) + 1024) + 255) / 256 * 256;
-    const size_t half = slot * n, flag_off = 2 * half, magic_off = flag_off + 256;
-    const size_t total = std::max<size_t>((magic_off + 256 + (1 << 21) - 1) >> 21 << 21, (size_t)4 << 20); // own VA range
+    // [2 halves][n slots] | flag words (256 B) | magic (256 B) | per-CTA flag words of k_pcg_solve [n][solve_grid]
+    const size_t half = slot * n, flag_off = 2 * half, magic_off = flag_off + 256, cta_flag_off = magic_off + 256;
+    const size_t area_end = cta_flag_off + (size_t)n * solve_grid * sizeof(unsigned long long);
+    const size_t total = std::max<size_t>((area_end + (1 << 21) - 1) >> 21 << 21, (size_t)4 << 20); // own VA range
     struct Pack { cudaIpcMemHandle_t h; unsigned long long magic; };
     std::vector<Pack> packs(n);
     unsigned char *hbuf = nullptr;
@@ -408,7 +403,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
       pp.recv[r] = (unsigned char *)p2p_peer[r];
       pp.flags[r] = (unsigned long long *)((unsigned char *)p2p_peer[r] + flag_off);
     }
-    pp.half_bytes = half; pp.slot_bytes = slot;
+    pp.half_bytes = half; pp.slot_bytes = slot; pp.cta_flag_off = cta_flag_off;
     pp.counter = d_counter; pp.seq = d_seq; pp.error = h_p2p_err;
     {
       // ranks are only loosely in step on the host (structure builds, uploads): a consumer waits this long for a peer
@@ -795,14 +790,9 @@ template <typename T, typename S> struct Problem : ProblemBase {
     return GB_OK;
   }
 
-  // the Schur product kernel (PRODUCT_PIPE selects the pipeline, kernels.cuh)
+  // one launch of the Schur product kernel (exports, full-system solver, NCCL fallback, stage timers)
   template <bool FULL> void launch_product(const T *Wp, const int *flag, T *outp) {
-#if PRODUCT_PIPE == 2
     k_schur_product2<T, S, FULL><<<ts.ncta, 2 * TILE, SchurSmem2<T, S>::TOTAL, ctx->stream>>>(ts, J, Wp, xs, part9, flag, outp);
-#else
-    k_schur_product<T, S, NSTAGE, FULL><<<ts.ncta, 2 * TILE, SchurSmem<T, S>::TOTAL(NSTAGE), ctx->stream>>>(ts, J, Wp, xs, part9,
-                                                                                                          flag, outp);
-#endif
     GB_LAUNCH(ctx);
   }
   int enqueue_prepare_tiles_only() {
@@ -836,102 +826,91 @@ template <typename T, typename S> struct Problem : ProblemBase {
   }
 
   // Ap_raw = D (B - E W E^T) D v for the vector v whose scaled copy D v is in xs; with `pvec` also
-  // Ap = Ap_raw + dterm pvec and the per-camera partials of pvec.Ap
-  int enqueue_schur_product(const int *flag, const T *pvec, int prof_slot = -1, bool product_only = false) {
+  // Ap = Ap_raw + dterm pvec and the per-camera partials of pvec.Ap.  One product launch + the per-camera sum of its
+  // partial rows: the form the exports (gb_schur_multiply), the stage timers and the NCCL fallback use.
+  int enqueue_schur_product(const int *flag, const T *pvec) {
     cudaStream_t st = ctx->stream;
-    const bool prof = profiling && prof_slot >= 0;
-    if (prof) {
-      while ((int)prof_ev.size() < 3 * prof_slot + 3) {
-        cudaEvent_t e;
-        GB_CUDA(ctx, cudaEventCreate(&e));
-        prof_ev.push_back(e);
-      }
-      GB_CUDA(ctx, cudaEventRecord(prof_ev[3 * prof_slot], st));
-    }
     const bool multi = ctx->nranks > 1;
     const int finish = (!multi && pvec) ? 1 : 0;
     launch_product<false>(W, flag, nullptr);
-    if (prof) GB_CUDA(ctx, cudaEventRecord(prof_ev[3 * prof_slot + 1], st));
-    if (product_only) return GB_OK; // the fused iteration kernel sums the partial rows itself
-    // The per-camera sum of the partial rows stays a separate, massively parallel kernel: fused into the tail of
-    // the product kernel (last-arriver-reduces with per-camera counters) it cost 25 us per CTA of exposed latency,
-    // because that kernel runs one CTA per SM (measured 463 us vs 249 + 11 us).
-    // multi-GPU with the cooperative update: the reduction pushes its nine values per camera into every rank's receive
-    // slot and k_pcg_update pulls + sums them (one-shot all-gather over peer memory, p2p.cuh); otherwise NCCL / the
-    // generic exchange kernels all-reduce Ap_raw
-    const int push = (multi && p2p_on && pvec && coop_update) ? 1 : 0;
-    k_cam_reduce_spmv<T><<<ts.Nc, 288, 0, st>>>(ts, part9, scale, Ap_raw, finish, dterm, pvec, Ap, dot_part, flag, pp, push);
+    k_cam_reduce_spmv<T><<<ts.Nc, 288, 0, st>>>(ts, part9, scale, Ap_raw, finish, dterm, pvec, Ap, dot_part, flag, pp, 0);
     GB_LAUNCH(ctx);
-    if (multi && !push) {
-      GB_TRY(allreduce_T(Ap_raw, dimc));
-      if (pvec && !coop_update) { // with the cooperative update, Ap and the dot partials are formed inside it
-        k_dot_partials<T><<<(ts.Nc + 127) / 128, 128, 0, st>>>(ts.Nc, Ap_raw, dterm, pvec, Ap, dot_part, flag);
-        GB_LAUNCH(ctx);
-      }
+    if (multi) GB_TRY(allreduce_T(Ap_raw, dimc)); // Ap and the dot partials are then formed inside k_pcg_update
+    return GB_OK;
+  }
+
+  int ensure_timing(int64_t max_iter) {
+    const int need = (int)((max_iter + 1) * SOLVE_STAMPS);
+    if (need > timing_cap) {
+      GB_TRY(dalloc(d_timing, need));
+      if (h_timing) cudaFreeHost(h_timing);
+      GB_CUDA(ctx, cudaMallocHost((void **)&h_timing, need * sizeof(unsigned long long)));
+      timing_cap = need;
     }
     return GB_OK;
   }
 
+  // PCGSchurSolver::solve (pcg_schur.hpp:79-168) after the Schur / preconditioner values: ONE cooperative launch
+  // (k_pcg_solve).  Without peer memory between the ranks (GB_P2P=0, IPC unavailable) the iterations are separate
+  // launches with an NCCL all-reduce of S p in between.
   int enqueue_pcg(const gb_pcg_options *o) {
     cudaStream_t st = ctx->stream;
-    GB_TRY(ensure_state_cap(o->max_iterations));
-    const int gridc = (ts.Nc + PCG_CAMS - 1) / PCG_CAMS;
-    k_pcg_init<T><<<gridc, 288, 0, st>>>(ts.Nc, bS, Minv, scale, x, r, z, pv, xs, rz_part);
-    GB_LAUNCH(ctx);
-    k_pcg_init_state<T><<<1, 1024, 0, st>>>(ts.Nc, rz_part, pcg_state, done_flag);
-    GB_LAUNCH(ctx);
     const T tol = (T)o->tolerance, ratio = (T)o->rejection_ratio;
-    const int max_iter = (int)o->max_iterations, nc = ts.Nc;
-    // An iteration enqueued after the PCG has stopped returns at once, but its two launches still cost ~25 us (the
-    // product grid is 1 CTA per SM with 217 KB of shared memory each: 162 such pairs per 50 LM iterations of the
-    // Venice run = 2.7 % of the time).  So only as many iterations as the previous solve needed, plus two, are enqueued
-    // at first; if that is fewer than max_iterations the state is read back (one host round trip) and the rest follows
-    // only when the PCG is still running.  All ranks see the same state and take the same branch.
-    const int64_t first_batch = adaptive_pcg ? std::min<int64_t>(o->max_iterations, pcg_guess + 2) : o->max_iterations;
-    int64_t last = first_batch;
-    for (int64_t k = 0; k < o->max_iterations; k++) {
-      if (k == first_batch) {
-        GB_TRY(store_host(h_state, pcg_state + 2 * k, sizeof(PcgState<T>)));
-        GB_CUDA(ctx, cudaStreamSynchronize(st));
-        if (h_state->done) break;
-        last = o->max_iterations;
-      }
-      const bool fused = fused_iter && (ctx->nranks == 1 || p2p_on); // without peer memory: separate kernels + NCCL
-      GB_TRY(enqueue_schur_product(done_flag, pv, (int)k, fused));
-      if (fused) {
+    const int max_iter = (int)o->max_iterations;
+    if (ctx->nranks == 1 || p2p_on) {
+      if (profiling) GB_TRY(ensure_timing(o->max_iterations));
+      const S2 *c_J = J;
+      const T *c_W = W, *c_scale = scale, *c_dterm = dterm, *c_Minv = Minv, *c_bS = bS;
+      PcgState<T> *stp = pcg_state;
+      int multi = ctx->nranks > 1 ? 1 : 0;
+      unsigned long long *cflags = multi ? (unsigned long long *)((unsigned char *)p2p_area + pp.cta_flag_off) : nullptr;
+      unsigned long long *tim = profiling ? d_timing : nullptr;
+      T tol_ = tol, ratio_ = ratio;
+      int mi = max_iter;
+      void *args[] = {(void *)&ts, (void *)&c_J, (void *)&c_W, (void *)&c_scale, (void *)&c_dterm, (void *)&c_Minv,
+                      (void *)&c_bS, (void *)&x, (void *)&xbak, (void *)&r, (void *)&z, (void *)&pbuf, (void *)&part9,
+                      (void *)&st_dot, (void *)&cta_red, (void *)&stp, (void *)&work_counter, (void *)&tol_, (void *)&ratio_,
+                      (void *)&mi, (void *)&pp, (void *)&multi, (void *)&cflags, (void *)&tim};
+      GB_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)k_pcg_solve<T, S>, dim3(solve_grid), dim3(SOLVE_THREADS), args,
+                                               SolveSmem<T, S>::TOTAL, st));
+      GB_LAUNCH(ctx);
+      GB_TRY(store_host(h_state, pcg_state, sizeof(PcgState<T>)));
+      if (profiling) GB_TRY(store_host(h_timing, d_timing, (size_t)(max_iter + 1) * SOLVE_STAMPS * sizeof(unsigned long long)));
+    } else {
+      GB_TRY(ensure_state_cap(o->max_iterations));
+      const int gridc = (ts.Nc + PCG_CAMS - 1) / PCG_CAMS;
+      k_pcg_init<T><<<gridc, 288, 0, st>>>(ts.Nc, bS, Minv, scale, x, r, z, pv, xs, rz_part);
+      GB_LAUNCH(ctx);
+      k_pcg_init_state<T><<<1, 1024, 0, st>>>(ts.Nc, rz_part, pcg_state, done_flag);
+      GB_LAUNCH(ctx);
+      const int nc = ts.Nc;
+      // An iteration enqueued after the PCG has stopped returns at once but still costs its launches, so only as many
+      // iterations as the previous solve needed, plus two, are enqueued at first; if that is fewer than max_iterations
+      // the state is read back and the rest follows only when the PCG is still running (identical on all ranks).
+      const int64_t first_batch = std::min<int64_t>(o->max_iterations, pcg_guess + 2);
+      int64_t last = first_batch;
+      for (int64_t k = 0; k < o->max_iterations; k++) {
+        if (k == first_batch) {
+          GB_TRY(store_host(h_state, pcg_state + 2 * k, sizeof(PcgState<T>)));
+          GB_CUDA(ctx, cudaStreamSynchronize(st));
+          if (h_state->done) break;
+          last = o->max_iterations;
+        }
+        GB_TRY(enqueue_schur_product(done_flag, pv));
         PcgState<T> *stp = pcg_state + 2 * k;
-        const T *c_part = part9, *c_scale = scale, *c_dterm = dterm, *c_Minv = Minv;
-        int multi = ctx->nranks > 1 ? 1 : 0;
-        void *args[] = {(void *)&ts, (void *)&stp, (void *)&tol, (void *)&ratio, (void *)&max_iter, (void *)&c_part,
-                        (void *)&c_scale, (void *)&c_dterm, (void *)&c_Minv, (void *)&x, (void *)&xbak, (void *)&r,
-                        (void *)&z, (void *)&pv, (void *)&xs, (void *)&Ap, (void *)&cta_part, (void *)&done_flag,
-                        (void *)&pp, (void *)&multi};
-        const void *fn = iter_pre ? (const void *)k_pcg_iterate<T, true> : (const void *)k_pcg_iterate<T, false>;
-        GB_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(iter_grid), dim3(PIT_THREADS), args, 0, st));
-        GB_LAUNCH(ctx);
-      } else if (coop_update) {
-        // both halves of the vector update in one cooperative launch (grid-wide sync instead of a kernel boundary)
-        PcgState<T> *stp = pcg_state + 2 * k;
-        const T *c_Minv = Minv, *c_scale = scale, *c_dterm = dterm;
-        const T *c_raw = ctx->nranks > 1 ? Ap_raw : nullptr;
-        int pull = (ctx->nranks > 1 && p2p_on) ? 1 : 0;
-        void *args[] = {(void *)&nc, (void *)&stp, (void *)&tol, (void *)&ratio, (void *)&max_iter, (void *)&dot_part,
+        const T *c_Minv = Minv, *c_scale = scale, *c_dterm = dterm, *c_raw = Ap_raw;
+        int pull = 0;
+        T tol_ = tol, ratio_ = ratio;
+        int mi = max_iter;
+        void *args[] = {(void *)&nc, (void *)&stp, (void *)&tol_, (void *)&ratio_, (void *)&mi, (void *)&dot_part,
                         (void *)&Ap, (void *)&c_Minv, (void *)&c_scale, (void *)&x, (void *)&xbak, (void *)&r,
                         (void *)&z, (void *)&pv, (void *)&xs, (void *)&rz_part, (void *)&done_flag, (void *)&c_raw,
                         (void *)&c_dterm, (void *)&pp, (void *)&pull};
         GB_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)k_pcg_update<T>, dim3(gridc), dim3(288), args, 0, st));
         GB_LAUNCH(ctx);
-      } else {
-        k_pcg_update1<T><<<gridc, 288, 0, st>>>(ts.Nc, pcg_state + 2 * k, pcg_state + 2 * k + 1, dot_part, Ap, Minv, x, xbak,
-                                                r, z, pv, rz_part, done_flag);
-        GB_LAUNCH(ctx);
-        k_pcg_update2<T><<<gridc, 288, 0, st>>>(ts.Nc, pcg_state + 2 * k + 1, pcg_state + 2 * k + 2, tol, ratio, max_iter,
-                                                scale, rz_part, x, xbak, z, pv, xs, done_flag);
-        GB_LAUNCH(ctx);
       }
-      if (profiling && 3 * k + 2 < (int64_t)prof_ev.size()) GB_CUDA(ctx, cudaEventRecord(prof_ev[3 * k + 2], st));
+      GB_TRY(store_host(h_state, pcg_state + 2 * last, sizeof(PcgState<T>)));
     }
-    GB_TRY(store_host(h_state, pcg_state + 2 * last, sizeof(PcgState<T>)));
     GB_TRY(launch_check());
     last_pcg = *o;
     solved = true;
@@ -1267,15 +1246,15 @@ template <typename T, typename S> struct Problem : ProblemBase {
       const int64_t k_exec = full ? full_info.pcg_iterations : h_state->iter;
       if (!full) pcg_guess = k_exec;
       R.pcg_iterations_total += k_exec;
-      if (profiling && !full) {
-        // launches 0 .. k_exec-1 did the work (a launch after the stop flag returns at once), except that an
-        // iteration stopped by rz == 0 or a bad denominator never used its product
-        for (int64_t k = 0; k < k_exec && 3 * k + 2 < (int64_t)prof_ev.size(); k++) {
-          cudaEventElapsedTime(&ms, prof_ev[3 * k], prof_ev[3 * k + 1]);
-          R.product_seconds += ms * 1e-3;
+      if (profiling && !full && h_timing && (ctx->nranks == 1 || p2p_on)) {
+        // phase stamps of CTA 0 (globaltimer, ns): product phase = P start .. after barrier A (every CTA has finished
+        // its super-tiles), rest of the iteration = after barrier A .. after barrier B
+        for (int64_t k = 0; k < k_exec; k++) {
+          const unsigned long long *tk = h_timing + k * SOLVE_STAMPS;
+          if (tk[5] <= tk[0]) continue; // an iteration that stopped before barrier B (bad denominator)
+          R.product_seconds += 1e-9 * (double)(tk[2] - tk[0]);
+          R.update_seconds += 1e-9 * (double)(tk[5] - tk[2]);
           R.product_launches++;
-          cudaEventElapsedTime(&ms, prof_ev[3 * k + 1], prof_ev[3 * k + 2]);
-          R.update_seconds += ms * 1e-3;
         }
       }
       const bool accepted_now = solve_ok && std::isfinite((double)new_chi2) && rho > T(0);

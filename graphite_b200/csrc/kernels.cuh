@@ -28,15 +28,15 @@
 //                                        loss / precision, J + residual store, C and g per point, diag(B) and g_c partials
 //   k_cam_reduce_lin, k_point_prepare    Jacobi scales, b; W = D (D C D + damping)^-1 D, h = W g
 //   k_prepare_cams, k_cam_reduce_prepare diagonal blocks of S and b_S by a camera-major gather; 9x9 inverses
-//   k_pcg_init(_state)                   PCG start
-//   k_schur_product2 + k_pcg_iterate     per PCG iteration: matrix-free (B - E W E^T) p on the TMA pipeline, then ONE
-//                                        cooperative launch for row sums, multi-GPU exchange (p2p.cuh), dots and updates
+//   k_pcg_solve (pcg_solve.cuh)          the whole PCG solve in ONE persistent cooperative launch: per iteration the
+//                                        matrix-free (B - E W E^T) p on the TMA pipeline (product_tile below), row sums,
+//                                        multi-GPU exchange (p2p.cuh), dots and updates, two grid barriers
 //   k_cam_step, k_backsubst_tiles        step of the cameras, back-substitution and step of the points, rho partials
 //   k_cost_tiles, k_sum_partials3        cost at the trial point, cost + rho sums; k_store_host hands them to the host
 //   k_copy                               restore after a rejected step
-// Other entry points: k_schur_product2<FULL> + k_full_* (full-system PCG solver), k_schur_explicit (explicit S export),
-// k_hessian_export, k_scatter_slots, k_p2p_push / k_p2p_sum (generic exchange).  k_schur_product (first TMA ring),
-// k_cam_reduce_spmv, k_pcg_update* are the PRODUCT_PIPE=1 / GB_FUSED_ITER=0 / NCCL-fallback paths.
+// Other entry points: k_schur_product2 (one product per launch: exports, <FULL> for the full-system PCG solver, NCCL
+// fallback) + k_cam_reduce_spmv, k_pcg_init*, k_pcg_update (NCCL fallback), k_full_* (full-system PCG solver),
+// k_schur_explicit (explicit S export), k_hessian_export, k_scatter_slots, k_p2p_push / k_p2p_sum (generic exchange).
 #pragma once
 #include <cfloat>
 #include <cstdint>
@@ -1307,18 +1307,6 @@ __device__ __forceinline__ void pcg_half2(int Nc, const PcgState<T> *sin, PcgSta
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(288)
-k_pcg_update1(int Nc, const PcgState<T> *sin, PcgState<T> *sout, const T *dot_part, const T *Ap, const T *Minv, T *x,
-              T *xbak, T *r, T *z, const T *p, T *rz_part, int *done_flag) {
-  pcg_half1<T>(Nc, sin, sout, dot_part, Ap, Minv, x, xbak, r, z, p, rz_part, done_flag);
-}
-template <typename T>
-__global__ void __launch_bounds__(288)
-k_pcg_update2(int Nc, const PcgState<T> *sin, PcgState<T> *sout, T tol, T ratio, int max_iter, const T *scale_c,
-              const T *rz_part, T *x, const T *xbak, const T *z, T *p, T *xs, int *done_flag) {
-  pcg_half2<T>(Nc, sin, sout, tol, ratio, max_iter, scale_c, rz_part, x, xbak, z, p, xs, done_flag);
-}
 // Both halves in one cooperative launch (all CTAs co-resident): the grid-wide sync replaces a kernel boundary.
 // st[0] -> st[1] -> st[2] are consecutive entries of the ping-pong state array.
 template <typename T>
@@ -1368,16 +1356,8 @@ k_pcg_update(int Nc, PcgState<T> *st, T tol, T ratio, int max_iter, T *dot_part,
 }
 
 // ---------------------------------------------------------------------------------------------
-// One PCG iteration after the product kernel, in ONE cooperative launch: per-camera sum of the partial rows
-// (k_cam_reduce_spmv), the multi-GPU exchange of S p (p2p.cuh), both dot products and all vector updates
-// (pcg_half1 / pcg_half2), separated by grid-wide barriers instead of kernel boundaries.  ncu on Venice: the three
-// separate kernels took 12 + 17 us per iteration plus launch gaps next to a 250 us product.
-// A CTA owns a contiguous block of cameras, a warp works on one camera at a time: lanes (sub, k) = (lane / 9, lane % 9)
-// for lane < 27 sum rows sub, sub+3, ... of component k; lanes 0..8 then own the camera's nine vector entries.
-// Every sum has a fixed order: bit-reproducible, and identical on all ranks (the exchange adds the ranks in rank order).
+// helpers of the persistent PCG kernel (pcg_solve.cuh)
 // ---------------------------------------------------------------------------------------------
-constexpr int PIT_THREADS = 256, PIT_WARPS = PIT_THREADS / 32;
-
 // lanes 0..8 hold v (others 0): fixed-tree sum, valid in lane 0
 template <typename T> __device__ __forceinline__ T sum9(T v) {
   v += __shfl_down_sync(0xffffffffu, v, 8);
@@ -1386,216 +1366,11 @@ template <typename T> __device__ __forceinline__ T sum9(T v) {
   v += __shfl_down_sync(0xffffffffu, v, 1);
   return v;
 }
-// per-warp values (lane 0) -> CTA total -> cta_part[blockIdx.x]; then, after the grid barrier, the grid total
-template <typename T> __device__ __forceinline__ void cta_publish(T wv, T *wpart, T *cta_part) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) wpart[warp] = wv;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    T tot = T(0);
-#pragma unroll
-    for (int w = 0; w < PIT_WARPS; w++) tot += wpart[w];
-    *(volatile T *)(cta_part + blockIdx.x) = tot;
-  }
-}
-template <typename T> __device__ __forceinline__ T grid_total(const T *cta_part, int n, T *sh) {
+// fixed-order sum of n values written by other CTAs of the running grid (L2 loads); valid in every thread
+template <typename T> __device__ __forceinline__ T grid_total(const T *vals, int n, T *sh) {
   T acc = T(0);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += __ldcg(cta_part + i);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += __ldcg(vals + i);
   return block_sum<T>(acc, sh);
-}
-
-// PRE = true (every warp owns at most one camera, Nc <= grid * 8): everything phase 2 needs is prefetched into registers
-// during the row gather (96 registers, 2 CTAs per SM).  PRE = false (more cameras): no prefetch, 64 registers, 4 CTAs per
-// SM, i.e. twice the warps to walk the cameras (Final-13682: 100 us -> see profiles/README.md).
-template <typename T, bool PRE>
-__global__ void __launch_bounds__(PIT_THREADS, PRE ? 2 : 4)
-k_pcg_iterate(DevStruct ds, PcgState<T> *st /*in: st[0], out: st[2]*/, T tol, T ratio, int max_iter,
-              const T *__restrict__ part /*[nrows][9]*/, const T *__restrict__ scale_c, const T *__restrict__ dterm,
-              const T *__restrict__ Minv, T *x, T *xbak, T *r, T *z, T *p, T *xs, T *Ap, T *cta_part /*[2][grid]*/,
-              int *done_flag, P2P pp, int multi) {
-  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
-  __shared__ T sh[32];
-  __shared__ T wpart[PIT_WARPS];
-#ifdef PIT_TIMING
-  unsigned long long tm_[8];
-  tm_[0] = global_timer_ns();
-#define PIT_STAMP(i) tm_[i] = global_timer_ns()
-#else
-#define PIT_STAMP(i)
-#endif
-  PcgState<T> s = *st;
-  const bool leader = blockIdx.x == 0 && threadIdx.x == 0;
-  // stopped earlier, or rz == 0 (pcg_schur.hpp:109-111): uniform across the grid and across ranks
-  if (s.done) {
-    if (leader) st[2] = s;
-    return;
-  }
-  if (s.rz == T(0)) {
-    if (leader) { s.done = 1; s.reason = 3; st[2] = s; *done_flag = 1; }
-    return;
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int G = gridDim.x, Nc = ds.Nc;
-  const int cpc = (Nc + G - 1) / G;
-  const int c_begin = blockIdx.x * cpc, c_end = min(Nc, c_begin + cpc);
-  const int k = lane % 9, sub = lane / 9;
-  const bool own = lane < 9;
-  const unsigned long long epoch = multi ? p2p_next_epoch(pp) : 0ull;
-  // the warp's first camera (its only one when Nc <= grid * warps): everything phase 2 needs is fetched now, so that the
-  // loads overlap the row gather instead of following the grid barrier
-  const int c_first = PRE ? c_begin + warp : -1;
-  T m_pre[9], x_pre = T(0), r_pre = T(0), p_pre = T(0), sc_pre = T(0), dt_pre = T(0);
-  if (PRE && own && c_first < c_end) {
-    const T *m = Minv + (int64_t)c_first * 81;
-#pragma unroll
-    for (int j = 0; j < 9; j++) m_pre[j] = m[k + 9 * j];
-    const int i = c_first * 9 + k;
-    x_pre = x[i]; r_pre = r[i]; p_pre = p[i]; sc_pre = scale_c[i]; dt_pre = dterm[i];
-  }
-
-  // Ap = raw + dterm p and the p.Ap contribution of one camera (lanes 0..8)
-  auto finish = [&](int c, T raw) -> T {
-    T prod = T(0);
-    if (own) {
-      const int i = c * 9 + k;
-      const T pk = c == c_first ? p_pre : p[i];
-      const T ap = raw + (c == c_first ? dt_pre : dterm[i]) * pk;
-      Ap[i] = ap;
-      prod = pk * ap;
-    }
-    return sum9<T>(prod);
-  };
-
-  // ---- phase 1: raw = D_c * (sum of the camera's partial rows) ----
-  T dot_w = T(0);
-  for (int c = c_begin + warp; c < c_end; c += PIT_WARPS) {
-    const int b = ds.cam_row_ptr[c], n = ds.cam_row_ptr[c + 1] - b;
-    T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0), a4 = T(0), a5 = T(0), a6 = T(0), a7 = T(0);
-    if (sub < 3) {
-      const T *base = part + (int64_t)b * 9 + k;
-      int row = sub;
-      for (; row + 21 < n; row += 24) { // eight independent loads in flight per lane
-        a0 += base[row * 9];
-        a1 += base[(row + 3) * 9];
-        a2 += base[(row + 6) * 9];
-        a3 += base[(row + 9) * 9];
-        a4 += base[(row + 12) * 9];
-        a5 += base[(row + 15) * 9];
-        a6 += base[(row + 18) * 9];
-        a7 += base[(row + 21) * 9];
-      }
-      for (; row + 3 < n; row += 6) {
-        a0 += base[row * 9];
-        a1 += base[(row + 3) * 9];
-      }
-      for (; row < n; row += 3) a0 += base[row * 9];
-    }
-    const T v = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
-    const T v1 = __shfl_sync(0xffffffffu, v, k + 9), v2 = __shfl_sync(0xffffffffu, v, k + 18);
-    T raw = T(0);
-    if (own) raw = (c == c_first ? sc_pre : scale_c[c * 9 + k]) * ((v + v1) + v2);
-    if (multi) {
-      if (own)
-        for (int q = 0; q < pp.nranks; q++) p2p_slot<T>(pp, q, pp.rank, epoch)[c * 9 + k] = raw;
-    } else {
-      dot_w += finish(c, raw);
-    }
-  }
-  if (multi) {
-    // every CTA has pushed -> publish the epoch to the peers -> wait for theirs -> sum the slots in rank order
-    __threadfence_system();
-    grid.sync();
-    if (leader) {
-      *pp.seq = epoch;
-      __threadfence_system();
-      for (int q = 0; q < pp.nranks; q++)
-        if (q != pp.rank) st_relaxed_sys(pp.flags[q] + pp.rank, epoch);
-    }
-    p2p_wait(pp, epoch);
-    for (int c = c_begin + warp; c < c_end; c += PIT_WARPS) {
-      T raw = T(0);
-      if (own) raw = p2p_sum<T>(pp, epoch, c * 9 + k);
-      dot_w += finish(c, raw);
-    }
-  }
-  PIT_STAMP(1);
-  cta_publish<T>(dot_w, wpart, cta_part);
-  __threadfence();
-  grid.sync();
-  PIT_STAMP(2);
-  const T denom = grid_total<T>(cta_part, G, sh);
-  PIT_STAMP(3);
-  if (denom == T(0) || isnan(denom)) { // pcg_schur.hpp:120-122
-    if (leader) { s.done = 1; s.reason = 4; s.denom = denom; st[2] = s; *done_flag = 1; }
-    return;
-  }
-  const T alpha = s.rz / denom;
-
-  // ---- phase 2: x += alpha p ; r -= alpha Ap ; z = Minv r ; r.z ----
-  T rz_w = T(0);
-  for (int c = c_begin + warp; c < c_end; c += PIT_WARPS) {
-    T rn = T(0);
-    const int i = c * 9 + k;
-    const bool first = c == c_first;
-    if (own) {
-      const T pi = first ? p_pre : p[i], xo = first ? x_pre : x[i];
-      xbak[i] = xo;
-      x[i] = alpha * pi + xo;                         // ops::axpy_async(x, alpha, p, x)
-      rn = -alpha * Ap[i] + (first ? r_pre : r[i]);   // ops::axpy_async(r, -alpha, Ap, r)
-      r[i] = rn;
-    }
-    const T *m = Minv + (int64_t)c * 81;
-    T acc = T(0);
-#pragma unroll
-    for (int j = 0; j < 9; j++) {
-      const T rj = __shfl_sync(0xffffffffu, rn, j);
-      if (own) acc += (first ? m_pre[j] : m[k + 9 * j]) * rj;
-    }
-    if (own) z[i] = acc;
-    rz_w += sum9<T>(own ? rn * acc : T(0));
-  }
-  PIT_STAMP(4);
-  __syncthreads(); // wpart is reused
-  cta_publish<T>(rz_w, wpart, cta_part + G);
-  __threadfence();
-  grid.sync();
-  PIT_STAMP(5);
-  const T rzn = grid_total<T>(cta_part + G, G, sh);
-  PIT_STAMP(6);
-
-  // ---- phase 3: rejection / convergence tests, beta, p, xs = D p (pcg_schur.hpp:144-163) ----
-  s.iter += 1;
-  s.alpha = alpha;
-  s.denom = denom;
-  if (fabs(rzn) > ratio * s.rz0 || isnan(rzn)) {
-    for (int c = c_begin + warp; c < c_end; c += PIT_WARPS)
-      if (own) x[c * 9 + k] = xbak[c * 9 + k];
-    if (leader) { s.done = 1; s.reason = 2; s.rz = rzn; st[2] = s; *done_flag = 1; }
-    return;
-  }
-  s.rz0 = fmin(s.rz0, fabs(rzn));
-  const T beta = rzn / s.rz;
-  s.beta = beta;
-  s.rz = rzn;
-  for (int c = c_begin + warp; c < c_end; c += PIT_WARPS)
-    if (own) {
-      const int i = c * 9 + k;
-      const T pn = beta * p[i] + z[i]; // ops::axpy_async(p, beta, p, z)
-      p[i] = pn;
-      xs[c * CAM_STRIDE + k] = scale_c[i] * pn;
-    }
-  if (fabs(rzn) < tol) { s.done = 1; s.reason = 1; }
-  else if (s.iter >= max_iter) { s.done = 1; s.reason = 0; }
-  if (leader) {
-    st[2] = s;
-    if (s.done) *done_flag = 1;
-  }
-#ifdef PIT_TIMING
-  PIT_STAMP(7);
-  if (leader && s.iter == 3)
-    printf("pit ns: gather %llu sync1 %llu total1 %llu phase2 %llu sync2 %llu total2 %llu phase3 %llu | whole %llu\n", tm_[1] - tm_[0],
-           tm_[2] - tm_[1], tm_[3] - tm_[2], tm_[4] - tm_[3], tm_[5] - tm_[4], tm_[6] - tm_[5], tm_[7] - tm_[6], tm_[7] - tm_[0]);
-#endif
 }
 
 // xs = D_c x (for the back-substitution) ; also camera update + rho partial (ops/update.hpp:9-31,

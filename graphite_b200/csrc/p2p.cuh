@@ -30,6 +30,7 @@ struct P2P {
   unsigned int *counter;                     // local: CTAs of the running producer that have finished pushing
   unsigned long long *seq;                   // local: epoch of the last exchange this rank has pushed
   int *error;                                // local (pinned host): set when a wait timed out (a peer died)
+  unsigned long long cta_flag_off;           // receive area + this = per-CTA flag words [nranks][grid] of k_pcg_solve
   unsigned long long timeout_ns;             // how long a consumer waits for a peer before it gives up (GB_P2P_TIMEOUT_S)
 };
 
