@@ -516,7 +516,9 @@ def main():
                     "iteration_frac_of_hbm_peak": survey_k4 * k_total / pcg_seconds / 1e9 / peak,
                     # in-kernel stamps: product phase and the rest of an iteration (row sums, exchange, updates, barrier B)
                     "ms_product_phase": prod_ms, "product_phase_gbps": prod_gbps,
-                    "ms_per_iteration_rest": 1e3 * res["update_seconds"] / n_prod},
+                    "ms_per_iteration_rest": 1e3 * res["update_seconds"] / n_prod,
+                    "us_per_iteration_by_phase": dict(zip(["product_cta0", "barrier_A", "sums_exchange", "rows_update", "barrier_B"],
+                                                          [1e6 * v / n_prod for v in res["pcg_phase_seconds"][:5]]))},
             "stages_ms_per_step": {k[8:]: 1e3 * v / max(steps_done, 1) for k, v in res.items()
                                    if k.startswith("seconds_") and k != "seconds_total"},
             "accepted": int(res["accepted"]), "rejected": int(res["rejected"]),

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgraphite_b200.so")
+LIB_PATH = os.environ.get("GRAPHITE_B200_LIB") or os.path.join(_HERE, "libgraphite_b200.so")  # env: A/B builds of the same ABI
 
 GB_F32, GB_F64 = 0, 1
 _DT = {"f32": GB_F32, "f64": GB_F64}
@@ -25,7 +25,8 @@ SYMBOLS = [
     "gb_get_residuals", "gb_get_jacobians", "gb_hessian_values", "gb_set_damping", "gb_solve", "gb_get_schur_rhs",
     "gb_get_schur_diagonal", "gb_schur_multiply", "gb_schur_structure", "gb_schur_values", "gb_try_step", "gb_revert_step", "gb_lm", "gb_kernel_launches",
     "gb_time_stage", "gb_structure_create", "gb_structure_destroy", "gb_structure_info", "gb_structure_array",
-    "gb_structure_hessian", "gb_structure_schur",
+    "gb_structure_hessian", "gb_structure_schur", "gb_context_create_on_stream", "gb_set_observations_device",
+    "gb_set_vertices_device", "gb_get_vertices_device", "gb_import_linearization", "gb_solve_device",
 ]
 
 
@@ -59,7 +60,7 @@ class LMResult(C.Structure):
                 ("seconds_prepare", C.c_double), ("seconds_pcg", C.c_double), ("seconds_backsubst", C.c_double),
                 ("seconds_cost", C.c_double), ("final_nu", C.c_double), ("product_launches", C.c_int64),
                 ("product_seconds", C.c_double), ("update_seconds", C.c_double), ("termination", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("reserved", C.c_int32), ("pcg_phase_seconds", C.c_double * 6)]
 
 
 SOLVERS = {"pcg-schur": 0, "pcg": 1}  # names of examples/bal.cu --solver
@@ -356,6 +357,7 @@ class Problem:
         traj = np.zeros((max(iterations, 1), 4))
         self.ctx.check(self.L.gb_lm(self.h, C.byref(o), C.byref(res), _ptr(traj)))
         out = {k: getattr(res, k) for k, _ in LMResult._fields_}
+        out["pcg_phase_seconds"] = [float(v) for v in res.pcg_phase_seconds]
         return traj[: res.iterations], out
 
     def time_stage(self, stage: int, repetitions: int) -> float:

@@ -57,6 +57,7 @@ struct gb_context {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr; // uploads that overlap the compute stream (gb_stage_observations_async)
+  bool owns_stream = true;            // false: the caller's stream (gb_context_create_on_stream)
   std::string err;
   int64_t launches = 0;
   ncclComm_t comm = nullptr;
@@ -103,6 +104,11 @@ struct ProblemBase {
   virtual int stage_observations_async(const void *, int) = 0;
   virtual int commit_observations(int) = 0;
   virtual int set_vertices(const void *, const void *) = 0;
+  virtual int set_observations_device(const void *) = 0;
+  virtual int set_vertices_device(const void *, const void *) = 0;
+  virtual int get_vertices_device(void *, void *) = 0;
+  virtual int import_linearization(const void *, const void *, const void *) = 0;
+  virtual int solve_device(const gb_pcg_options *, void *, gb_solve_info *) = 0;
   virtual int set_factor(gb_factor_fn, void *) = 0;
   virtual int set_loss(int, double) = 0;
   virtual int set_precision(const void *) = 0;
@@ -529,12 +535,9 @@ template <typename T, typename S> struct Problem : ProblemBase {
     linearized = prepared = solved = solved_full = full_lin_valid = stepped = false;
     return GB_OK;
   }
-  int set_factor(gb_factor_fn fn, void *user) override {
-    linearized = prepared = solved = solved_full = stepped = false;
-    ext_fn = fn;
-    ext_user = user;
-    if (!fn || ext_r) return GB_OK;
-    GB_TRY(dalloc(ext_r, 2 * (size_t)hs.M)); GB_TRY(dalloc(ext_Jc, 18 * (size_t)hs.M)); GB_TRY(dalloc(ext_Jp, 6 * (size_t)hs.M));
+  // storage slot -> caller's factor index, camera / point index per caller factor: what a caller-order buffer needs
+  int ensure_caller_maps() {
+    if (d_slot_src) return GB_OK;
     std::vector<int32_t> src((size_t)hs.Mstore, -1), ci((size_t)hs.M), pi((size_t)hs.M);
     for (int64_t spos = 0; spos < hs.M; spos++) {
       const int64_t u = hs.identity_perm ? spos : hs.perm[spos];
@@ -546,6 +549,55 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_TRY(upload(a, src)); GB_TRY(upload(b, ci)); GB_TRY(upload(c, pi));
     d_slot_src = const_cast<int32_t *>(a); d_ci_caller = const_cast<int32_t *>(b); d_pi_caller = const_cast<int32_t *>(c);
     GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GB_OK;
+  }
+  int set_observations_device(const void *o) override {
+    k_scatter_slots<T2><<<(unsigned)((hs.M + 255) / 256), 256, 0, ctx->stream>>>(hs.M, ts.slot_of_obs, d_perm, (const T2 *)o, obs);
+    GB_LAUNCH(ctx);
+    obs_caller = (const T2 *)o; // the caller keeps the buffer alive while a user-defined factor may read it
+    have_obs = true;
+    linearized = prepared = solved = solved_full = full_lin_valid = stepped = false;
+    return launch_check();
+  }
+  int set_vertices_device(const void *c, const void *p) override {
+    GB_CUDA(ctx, cudaMemcpy2DAsync(cams, CAM_STRIDE * sizeof(T), c, 9 * sizeof(T), 9 * sizeof(T), hs.Nc,
+                                   cudaMemcpyDeviceToDevice, ctx->stream));
+    GB_CUDA(ctx, cudaMemcpyAsync(pts, p, 3 * (size_t)hs.Np * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+    camx_valid = false;
+    have_vertices = true;
+    linearized = prepared = solved = solved_full = full_lin_valid = stepped = false;
+    return GB_OK;
+  }
+  int get_vertices_device(void *c, void *p) override {
+    if (!have_vertices) return ctx->fail(GB_ERR_INVALID, "gb_get_vertices_device before the vertices were set");
+    if (c)
+      GB_CUDA(ctx, cudaMemcpy2DAsync(c, 9 * sizeof(T), cams, CAM_STRIDE * sizeof(T), 9 * sizeof(T), hs.Nc,
+                                     cudaMemcpyDeviceToDevice, ctx->stream));
+    if (p) GB_CUDA(ctx, cudaMemcpyAsync(p, pts, 3 * (size_t)hs.Np * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+    return GB_OK;
+  }
+  // Solver::update_values for a caller that linearises itself: the reference's residuals and SCALED Jacobians, in its
+  // factor order, take the place of the built-in factor evaluation; everything downstream (assembly, Schur operator,
+  // PCG) is the production path with scales = 1.
+  int import_linearization(const void *rdev, const void *jc, const void *jp) override {
+    if constexpr (!std::is_same<T, S>::value) {
+      return ctx->fail(GB_ERR_UNSUPPORTED, "gb_import_linearization needs T == S");
+    } else {
+      GB_TRY(require(ctx->nranks == 1, "gb_import_linearization is single-rank"));
+      GB_TRY(ensure_caller_maps());
+      scale_on = false;
+      have_obs = have_vertices = true; // the caller owns both; nothing here evaluates factors
+      GB_TRY(enqueue_linearize(true, ExtFactor{rdev, jc, jp, d_slot_src}));
+      return GB_OK;
+    }
+  }
+  int set_factor(gb_factor_fn fn, void *user) override {
+    linearized = prepared = solved = solved_full = stepped = false;
+    ext_fn = fn;
+    ext_user = user;
+    if (!fn || ext_r) return GB_OK;
+    GB_TRY(dalloc(ext_r, 2 * (size_t)hs.M)); GB_TRY(dalloc(ext_Jc, 18 * (size_t)hs.M)); GB_TRY(dalloc(ext_Jp, 6 * (size_t)hs.M));
+    GB_TRY(ensure_caller_maps());
     ex = ExtFactor{ext_r, ext_Jc, ext_Jp, d_slot_src};
     return GB_OK;
   }
@@ -620,13 +672,17 @@ template <typename T, typename S> struct Problem : ProblemBase {
   }
   // need_cost = false: the caller does not read chi2 of this linearisation (the accepted-step path of the LM loop
   // already has it from the trial step), so its cross-rank sum is skipped
-  int enqueue_linearize(bool need_cost = true) {
+  // imported.r != nullptr: the caller's own linearisation (gb_import_linearization) instead of a factor evaluation
+  int enqueue_linearize(bool need_cost = true, ExtFactor imported = ExtFactor{nullptr, nullptr, nullptr, nullptr}) {
     cudaStream_t st = ctx->stream;
-    GB_TRY(ensure_camx());
-    if (ext_fn) {
+    if (imported.r) {
+      k_linearize<T, S, true><<<ts.nst, TILE, smem_lin_bytes<T>(), st>>>(ts, camx, pts, obs, J, res, Cg, part18, cost_part, rb, imported);
+    } else if (ext_fn) {
+      GB_TRY(ensure_camx());
       GB_TRY(evaluate_external(true));
       k_linearize<T, S, true><<<ts.nst, TILE, smem_lin_bytes<T>(), st>>>(ts, camx, pts, obs, J, res, Cg, part18, cost_part, rb, ex);
     } else {
+      GB_TRY(ensure_camx());
       k_linearize<T, S, false><<<ts.nst, TILE, smem_lin_bytes<T>(), st>>>(ts, camx, pts, obs, J, res, Cg, part18, cost_part, rb, ex);
     }
     GB_LAUNCH(ctx);
@@ -977,6 +1033,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
   // ---- public operations ---------------------------------------------------------------------------------
   int linearize(double *chi2) override {
     GB_TRY(require(have_obs && have_vertices, "gb_linearize needs observations and vertices"));
+    scale_on = true; // (an imported linearisation, gb_import_linearization, runs with scales = 1)
     GB_TRY(enqueue_linearize());
     GB_TRY(store_host(h_scalars, scalars, sizeof(double)));
     GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1094,6 +1151,28 @@ template <typename T, typename S> struct Problem : ProblemBase {
     }
     return GB_OK;
   }
+  int solve_device(const gb_pcg_options *o, void *delta_dev, gb_solve_info *info) override {
+    GB_TRY(require(linearized, "gb_solve_device before a linearisation"));
+    GB_TRY(require(o && o->max_iterations >= 0 && o->max_iterations < (1 << 20), "bad PCG options"));
+    GB_TRY(require(o->solver == GB_SOLVER_PCG_SCHUR, "gb_solve_device: the Schur PCG solver only"));
+    GB_TRY(enqueue_prepare());
+    GB_TRY(enqueue_pcg(o));
+    GB_TRY(enqueue_step(false));
+    if (delta_dev) {
+      k_copy<T><<<4 * 148, 256, 0, ctx->stream>>>((int64_t)dimH, delta, (T *)delta_dev);
+      GB_LAUNCH(ctx);
+    }
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    GB_TRY(p2p_check());
+    pcg_guess = h_state->iter;
+    if (info) {
+      info->pcg_iterations = h_state->iter;
+      info->rz_final = (double)h_state->rz;
+      info->stop_reason = h_state->reason;
+      info->reserved = 0;
+    }
+    return GB_OK;
+  }
   int get_schur_rhs(void *out) override {
     GB_TRY(require(linearized, "gb_get_schur_rhs before gb_linearize"));
     if (!prepared) GB_TRY(enqueue_prepare());
@@ -1194,6 +1273,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     if (full) GB_TRY(full_buffers());
     cudaStream_t st = ctx->stream;
     gb_lm_result R{};
+    if (!scale_on) { scale_on = true; linearized = false; } // leave the imported-linearisation mode
     const bool resume = o->resume != 0 && linearized;
     T mu_l = (T)o->initial_damping, nu = o->initial_nu > 0 ? (T)o->initial_nu : T(2);
     use_identity = o->use_identity;
@@ -1255,6 +1335,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
           R.product_seconds += 1e-9 * (double)(tk[2] - tk[0]);
           R.update_seconds += 1e-9 * (double)(tk[5] - tk[2]);
           R.product_launches++;
+          for (int ph = 0; ph < 5; ph++) R.pcg_phase_seconds[ph] += 1e-9 * (double)(tk[ph + 1] - tk[ph]);
         }
       }
       const bool accepted_now = solve_ok && std::isfinite((double)new_chi2) && rho > T(0);
@@ -1396,11 +1477,20 @@ int gb_context_create(int device, gb_context **out) {
   return GB_OK;
 }
 
+int gb_context_create_on_stream(int device, void *cuda_stream, gb_context **out) {
+  const int rc = gb_context_create(device, out);
+  if (rc != GB_OK) return rc;
+  cudaStreamDestroy((*out)->stream);
+  (*out)->stream = (cudaStream_t)cuda_stream;
+  (*out)->owns_stream = false;
+  return GB_OK;
+}
+
 int gb_context_destroy(gb_context *ctx) {
   if (!ctx) return GB_OK;
   cudaSetDevice(ctx->device);
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
-  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->stream && ctx->owns_stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
   return GB_OK;
@@ -1567,6 +1657,15 @@ int gb_stage_observations_async(gb_problem *p, const void *o, int slot) { GB_P(p
 int gb_commit_observations(gb_problem *p, int slot) { GB_P(p); return p->impl->commit_observations(slot); }
 int gb_set_vertices(gb_problem *p, const void *c, const void *q) { GB_P(p); if (!c || !q) return GB_ERR_INVALID; return p->impl->set_vertices(c, q); }
 int gb_get_vertices(gb_problem *p, void *c, void *q) { GB_P(p); return p->impl->get_vertices(c, q); }
+int gb_set_observations_device(gb_problem *p, const void *o) { GB_P(p); if (!o) return GB_ERR_INVALID; return p->impl->set_observations_device(o); }
+int gb_set_vertices_device(gb_problem *p, const void *c, const void *q) { GB_P(p); if (!c || !q) return GB_ERR_INVALID; return p->impl->set_vertices_device(c, q); }
+int gb_get_vertices_device(gb_problem *p, void *c, void *q) { GB_P(p); return p->impl->get_vertices_device(c, q); }
+int gb_import_linearization(gb_problem *p, const void *r, const void *jc, const void *jp) {
+  GB_P(p);
+  if (!r || !jc || !jp) return GB_ERR_INVALID;
+  return p->impl->import_linearization(r, jc, jp);
+}
+int gb_solve_device(gb_problem *p, const gb_pcg_options *o, void *d, gb_solve_info *i) { GB_P(p); return p->impl->solve_device(o, d, i); }
 int gb_set_factor(gb_problem *p, gb_factor_fn fn, void *user) { GB_P(p); return p->impl->set_factor(fn, user); }
 int gb_set_loss(gb_problem *p, int kind, double delta) { GB_P(p); return p->impl->set_loss(kind, delta); }
 int gb_set_precision(gb_problem *p, const void *P) { GB_P(p); return p->impl->set_precision(P); }

@@ -44,6 +44,9 @@ typedef struct gb_problem gb_problem;
 
 /* Replaces: cudaSetDevice + StreamPool (examples/bal.cu:53,251; include/graphite/stream.hpp). */
 int gb_context_create(int device, gb_context **out);
+/* The same on a stream the caller owns (cudaStream_t passed as void*; the reference hands its StreamPool to every Solver
+ * call, solver/solver.hpp:16-24): all work of the context's problems is enqueued on it.  The stream must outlive the context. */
+int gb_context_create_on_stream(int device, void *cuda_stream, gb_context **out);
 int gb_context_destroy(gb_context *ctx);
 const char *gb_last_error(const gb_context *ctx);
 int gb_version(void);
@@ -112,6 +115,12 @@ int gb_set_vertices(gb_problem *p, const void *cams_host, const void *pts_host);
  * installs it (later calls use the new observations).  The host buffer must stay valid until the commit. */
 int gb_stage_observations_async(gb_problem *p, const void *obs_pinned_host, int slot);
 int gb_commit_observations(gb_problem *p, int slot);
+/* Device-pointer forms for callers whose data already lives on the GPU (the reference keeps vertices behind device-visible
+ * pointers and observations in managed memory, docs/markdown/memory.md:4-27): same layouts, element type T, copied on the
+ * context stream; the call returns after the copy has been enqueued and ordered before later calls. */
+int gb_set_observations_device(gb_problem *p, const void *obs_dev);
+int gb_set_vertices_device(gb_problem *p, const void *cams_dev /*[n_cams][9]*/, const void *pts_dev /*[n_pts][3]*/);
+int gb_get_vertices_device(gb_problem *p, void *cams_dev, void *pts_dev);
 /* Replaces the loss_func and precision_matrix arguments of add_factor (factor.hpp:373-412; loss.hpp:15-51):
  *   chi2_f = loss(r^T P r), H += loss' J^T P J, b -= loss' J^T P r (ops/chi2.hpp:9-44, ops/hessian.hpp:58-76).
  * One loss for all factors: GB_LOSS_DEFAULT (identity) or GB_LOSS_HUBER(delta).  precision_host: [n_obs][4] row-major
@@ -154,6 +163,15 @@ int gb_hessian_structure(const gb_problem *p, int64_t *colptr, int64_t *rowidx, 
 int gb_linearize(gb_problem *p, double *chi2);
 /* Replaces: Graph::compute_error + chi2 (graph.hpp:221-234). */
 int gb_compute_cost(gb_problem *p, double *chi2);
+/* Replaces: Solver::update_values (solver/solver.hpp:20; PCGSchurSolver::update_values, pcg_schur.hpp:67-69) for a caller
+ * that linearises ITSELF - the reference's Graph::linearize (graph.hpp:236-290) run by its own levenberg_marquardt with this
+ * library plugged in as the Solver.  Imports, from DEVICE memory in the caller's factor order, the residuals [n_obs][2]
+ * (FactorDescriptor::residuals) and the Jacobi-SCALED column-major Jacobians J~ = J D, [n_obs][18] and [n_obs][6]
+ * (FactorDescriptor::jacobians[0|1].data after scale_jacobians_async, ops/linearize.hpp:140-180).  Requires T == S (as the
+ * reference's PCGSchurSolver does).  The imported system is solved as it is: scales = 1, so gb_solve's step is in the
+ * caller's scaled space (the Solver::solve contract).  Loss / precision matrices set with gb_set_loss / gb_set_precision
+ * are applied on top, as in ops/hessian.hpp:58-76.  A later gb_linearize / gb_lm returns to the built-in linearisation. */
+int gb_import_linearization(gb_problem *p, const void *residuals_dev, const void *Jc_dev, const void *Jp_dev);
 /* Parity exports (host, element type T): b and scales [hessian_dim] (graph.hpp:57,67); residuals [n_obs][2]
  * in the caller's factor order; Jacobians unscaled, column-major 2x9 / 2x3 per factor (as double). */
 int gb_get_gradient(gb_problem *p, void *b_host);
@@ -192,6 +210,10 @@ int gb_set_damping(gb_problem *p, double mu, int use_identity);
  * (block_jacobi_schur.hpp:114-151) + PCG + compute_landmark_update (schur.hpp:279-302).
  * delta_host (optional) receives the scaled-space step (element type T). */
 int gb_solve(gb_problem *p, const gb_pcg_options *opt, void *delta_host, gb_solve_info *info);
+/* The same with the step written to DEVICE memory (bool Solver::solve(Graph*, T *delta_x, StreamPool&), solver/solver.hpp:24:
+ * delta_x is a device vector of hessian_dim values in the scaled space); synchronises the context stream before returning,
+ * as PCGSchurSolver::solve does (pcg_schur.hpp:165). */
+int gb_solve_device(gb_problem *p, const gb_pcg_options *opt, void *delta_dev, gb_solve_info *info);
 /* Parity exports of the reduced system at the current damping (element type T): b_S [9 n_cams]
  * (schur.hpp:237), diagonal blocks of S [n_cams][81] column-major, and y = S x for a host vector. */
 int gb_get_schur_rhs(gb_problem *p, void *bS_host);
@@ -252,6 +274,11 @@ typedef struct {
    * GB_LM_STOP_FLAG; GB_LM_EARLY_STOP (levenberg_marquardt2, :403-413) */
   int32_t termination;
   int32_t reserved;
+  /* profile_product: where the PCG iterations spent their time, from globaltimer stamps of CTA 0 inside k_pcg_solve,
+   * summed over the executed iterations: [0] product phase up to CTA 0's arrival at the grid barrier that ends it,
+   * [1] that barrier (waiting for the slowest CTA), [2] scalar sums + multi-GPU exchange (push, flags, waiting for the
+   * peers), [3] row sums and vector updates, [4] the second grid barrier, [5] reserved */
+  double pcg_phase_seconds[6];
 } gb_lm_result;
 typedef enum { GB_LM_DONE = 0, GB_LM_DAMPING_NOT_FINITE = 1, GB_LM_RHO_ZERO = 2, GB_LM_STOP_FLAG = 3, GB_LM_EARLY_STOP = 4 } gb_lm_termination;
 
