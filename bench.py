@@ -285,6 +285,10 @@ def main():
     ap.add_argument("--precision", default="f64-f64")
     ap.add_argument("--solver", default="pcg-schur", choices=["pcg-schur", "pcg"],
                     help="pcg-schur: PCGSchurSolver (headline); pcg: the reference's full-system PCGSolver (its mixed-precision path)")
+    ap.add_argument("--super-tile-obs", type=int, default=0,
+                    help="tuning: target observations per super-tile (gb_problem_desc.super_tile_observations), 0 = library default")
+    ap.add_argument("--device-only", action="store_true",
+                    help="tuning sweeps: only the device-resident arm (no e2e, CPU or reference legs); not a reportable line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true",
                     help="skip the leg that runs the unmodified reference's GPU path (oracle/_ref/ref_bal) on the same box")
@@ -320,7 +324,8 @@ def main():
     T = np.float64 if tname == "f64" else np.float32
     sT, sS = (8 if tname == "f64" else 4), (8 if sname == "f64" else 4)
     t_struct = time.perf_counter()
-    P = binding.Problem(ctx, local.cam_idx, local.pt_idx, local.n_cams, local.n_pts, args.precision, partition=world > 1)
+    P = binding.Problem(ctx, local.cam_idx, local.pt_idx, local.n_cams, local.n_pts, args.precision, partition=world > 1,
+                        super_tile_observations=args.super_tile_obs)
     structure_seconds = time.perf_counter() - t_struct  # one-time: sort, tiles, segments, camera CSR, uploads
     info = P.info()
 
@@ -409,6 +414,21 @@ def main():
         except Exception:
             pass
 
+    if args.device_only:
+        if rank == 0:
+            emit({"tuning_only": True, "value": value, "ms_per_step": 1e3 * seconds / max(steps_done, 1), "n_gpus": world,
+                  "super_tile_obs": args.super_tile_obs, "structure": info, "parity": parity,
+                  "stages_ms_per_step": {k[8:]: 1e3 * v / max(steps_done, 1) for k, v in res.items()
+                                         if k.startswith("seconds_") and k != "seconds_total"},
+                  "pcg_us_by_phase": [1e6 * v / n_prod for v in res["pcg_phase_seconds"]], "ms_product_phase": prod_ms,
+                  "pcg_ms_per_iteration": 1e3 * pcg_seconds / k_total})
+        if rank == 0:
+            sampler.stop()
+        P.close()
+        ctx.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return
     # ---- e2e arm: every step copies its inputs from pinned host memory and reads the result back ----------
     P.set_vertices_raw(h_cams.data_ptr(), h_pts.data_ptr())
     tw, rw = P.lm(iterations=args.warmup, solver=args.solver)
@@ -517,8 +537,8 @@ def main():
                     # in-kernel stamps: product phase and the rest of an iteration (row sums, exchange, updates, barrier B)
                     "ms_product_phase": prod_ms, "product_phase_gbps": prod_gbps,
                     "ms_per_iteration_rest": 1e3 * res["update_seconds"] / n_prod,
-                    "us_per_iteration_by_phase": dict(zip(["product_cta0", "barrier_A", "sums_exchange", "rows_update", "barrier_B"],
-                                                          [1e6 * v / n_prod for v in res["pcg_phase_seconds"][:5]]))},
+                    "us_per_iteration_by_phase": dict(zip(["product_cta0", "barrier_A", "sums_exchange", "rows_update", "barrier_B", "of_sums_exchange_until_pushed"],
+                                                          [1e6 * v / n_prod for v in res["pcg_phase_seconds"][:6]]))},
             "stages_ms_per_step": {k[8:]: 1e3 * v / max(steps_done, 1) for k, v in res.items()
                                    if k.startswith("seconds_") and k != "seconds_total"},
             "accepted": int(res["accepted"]), "rejected": int(res["rejected"]),

@@ -274,6 +274,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_TRY(upload(ts.cam_row_ptr, hs.cam_row_ptr));
     GB_TRY(upload(ts.row_out, hs.row_out));
     GB_TRY(upload(ts.cta_st, hs.cta_st));
+    GB_TRY(upload(ts.strec, hs.strec));
     ts.ncta = hs.ncta(); ts.pad2 = 0;
     GB_TRY(upload(ts.cm_slot, hs.cm_slot));
     GB_TRY(upload(ts.cm_pt, hs.cm_pt));
@@ -346,9 +347,11 @@ template <typename T, typename S> struct Problem : ProblemBase {
     const char *env = getenv("GB_P2P");
     int fail = (env && env[0] == '0') || n > P2P_MAX_RANKS || !g_nccl.AllGather ? 1 : 0;
     const size_t slot = (((size_t)54 * ts.Nc * sizeof(T) + 1024) + 255) / 256 * 256;
-    // [2 halves][n slots] | flag words (256 B) | magic (256 B) | per-CTA flag words of k_pcg_solve [n][solve_grid]
-    const size_t half = slot * n, flag_off = 2 * half, magic_off = flag_off + 256, cta_flag_off = magic_off + 256;
-    const size_t area_end = cta_flag_off + (size_t)n * solve_grid * sizeof(unsigned long long);
+    // [2 halves][n slots] | flag words (256 B) | magic (256 B) | LL area of k_pcg_solve [2 halves][n slots]: every 32-bit
+    // half of a value in an 8-byte word with its epoch (9 Nc values + the dot scalar per slot)
+    const size_t half = slot * n, flag_off = 2 * half, magic_off = flag_off + 256, ll_off = magic_off + 256;
+    const size_t ll_slot = (((size_t)9 * ts.Nc + 8) * (sizeof(T) / 4) * 8 + 255) / 256 * 256, ll_half = ll_slot * n;
+    const size_t area_end = ll_off + 2 * ll_half;
     const size_t total = std::max<size_t>((area_end + (1 << 21) - 1) >> 21 << 21, (size_t)4 << 20); // own VA range
     struct Pack { cudaIpcMemHandle_t h; unsigned long long magic; };
     std::vector<Pack> packs(n);
@@ -409,7 +412,8 @@ template <typename T, typename S> struct Problem : ProblemBase {
       pp.recv[r] = (unsigned char *)p2p_peer[r];
       pp.flags[r] = (unsigned long long *)((unsigned char *)p2p_peer[r] + flag_off);
     }
-    pp.half_bytes = half; pp.slot_bytes = slot; pp.cta_flag_off = cta_flag_off;
+    pp.half_bytes = half; pp.slot_bytes = slot;
+    pp.ll_off = ll_off; pp.ll_half_bytes = ll_half; pp.ll_slot_bytes = ll_slot;
     pp.counter = d_counter; pp.seq = d_seq; pp.error = h_p2p_err;
     {
       // ranks are only loosely in step on the host (structure builds, uploads): a consumer waits this long for a peer
@@ -919,14 +923,13 @@ template <typename T, typename S> struct Problem : ProblemBase {
       const T *c_W = W, *c_scale = scale, *c_dterm = dterm, *c_Minv = Minv, *c_bS = bS;
       PcgState<T> *stp = pcg_state;
       int multi = ctx->nranks > 1 ? 1 : 0;
-      unsigned long long *cflags = multi ? (unsigned long long *)((unsigned char *)p2p_area + pp.cta_flag_off) : nullptr;
       unsigned long long *tim = profiling ? d_timing : nullptr;
       T tol_ = tol, ratio_ = ratio;
       int mi = max_iter;
       void *args[] = {(void *)&ts, (void *)&c_J, (void *)&c_W, (void *)&c_scale, (void *)&c_dterm, (void *)&c_Minv,
                       (void *)&c_bS, (void *)&x, (void *)&xbak, (void *)&r, (void *)&z, (void *)&pbuf, (void *)&part9,
                       (void *)&st_dot, (void *)&cta_red, (void *)&stp, (void *)&work_counter, (void *)&tol_, (void *)&ratio_,
-                      (void *)&mi, (void *)&pp, (void *)&multi, (void *)&cflags, (void *)&tim};
+                      (void *)&mi, (void *)&pp, (void *)&multi, (void *)&tim};
       GB_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)k_pcg_solve<T, S>, dim3(solve_grid), dim3(SOLVE_THREADS), args,
                                                SolveSmem<T, S>::TOTAL, st));
       GB_LAUNCH(ctx);
@@ -1336,6 +1339,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
           R.update_seconds += 1e-9 * (double)(tk[5] - tk[2]);
           R.product_launches++;
           for (int ph = 0; ph < 5; ph++) R.pcg_phase_seconds[ph] += 1e-9 * (double)(tk[ph + 1] - tk[ph]);
+          if (tk[6] > tk[2]) R.pcg_phase_seconds[5] += 1e-9 * (double)(tk[6] - tk[2]); // multi-GPU: own sums pushed
         }
       }
       const bool accepted_now = solve_ok && std::isfinite((double)new_chi2) && rho > T(0);

@@ -88,6 +88,7 @@ struct DevStruct {
   const int32_t *row_cam;    // [nrows] camera of each partial row
   const int32_t *cam_row_ptr;  // [Nc+1] camera -> its contiguous rows in the partial buffers (ascending super-tile)
   const int32_t *row_out;      // [nrows] super-tile row (st_row + slot) -> position in the partial buffers
+  const unsigned char *strec;  // [nst][STREC_BYTES] packed per-super-tile record (k_pcg_solve)
   const int32_t *cta_st;       // [ncta+1] super-tile ranges of the persistent CTAs
   int32_t ncta, pad2;
   const int32_t *cm_slot, *cm_pt;  // [M] camera-major observation -> storage slot / point

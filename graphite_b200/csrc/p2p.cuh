@@ -30,7 +30,7 @@ struct P2P {
   unsigned int *counter;                     // local: CTAs of the running producer that have finished pushing
   unsigned long long *seq;                   // local: epoch of the last exchange this rank has pushed
   int *error;                                // local (pinned host): set when a wait timed out (a peer died)
-  unsigned long long cta_flag_off;           // receive area + this = per-CTA flag words [nranks][grid] of k_pcg_solve
+  unsigned long long ll_off, ll_half_bytes, ll_slot_bytes; // receive area + ll_off = the LL area [2 halves][nranks][slot]
   unsigned long long timeout_ns;             // how long a consumer waits for a peer before it gives up (GB_P2P_TIMEOUT_S)
 };
 
@@ -106,6 +106,55 @@ template <typename T> __device__ __forceinline__ T p2p_sum(const P2P &pp, unsign
   T acc = __ldcg(p2p_slot<T>(pp, pp.rank, 0, epoch) + i);
   for (int r = 1; r < pp.nranks; r++) acc += __ldcg(p2p_slot<T>(pp, pp.rank, r, epoch) + i);
   return acc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// LL ("low latency") exchange of the PCG solve kernel.  The flag protocol above costs two serialised NVLink latencies
+// (stores, system fence, flag store; measured 16 us per PCG iteration with the waits at 2-4 GPUs).  Here every 32-bit half
+// of a value travels in ONE 8-byte word together with the 32-bit epoch of the exchange: an 8-byte store is indivisible, so
+// a reader that sees the epoch has the data - no fence, no flag, one one-way latency.  The LL area is separate from the
+// flag-protocol area (a plain value must never be mistaken for a stamped word) and starts zeroed (epoch 0 is never used).
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T> struct LLW { static constexpr int words = sizeof(T) / 4; }; // 8-byte words per value
+__device__ __forceinline__ unsigned long long *ll_slot(const P2P &pp, int dst, int src, unsigned long long epoch) {
+  return reinterpret_cast<unsigned long long *>(pp.recv[dst] + pp.ll_off + (epoch & 1ull) * pp.ll_half_bytes +
+                                                (unsigned long long)src * pp.ll_slot_bytes);
+}
+__device__ __forceinline__ void ll_store_word(unsigned long long *p, unsigned int data, unsigned int epoch32) {
+  const unsigned long long w = ((unsigned long long)epoch32 << 32) | (unsigned long long)data;
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ unsigned int ll_load_word(const P2P &pp, const unsigned long long *p, unsigned int epoch32) {
+  unsigned long long w;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+  if ((unsigned int)(w >> 32) != epoch32) {
+    const unsigned long long t0 = global_timer_ns();
+    unsigned int polls = 0;
+    do {
+      asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+      if ((++polls & 1023u) == 0u && global_timer_ns() - t0 > pp.timeout_ns) { // a peer is gone: fail loudly on the host
+        *pp.error = 1;
+        break;
+      }
+    } while ((unsigned int)(w >> 32) != epoch32);
+  }
+  return (unsigned int)w;
+}
+__device__ __forceinline__ void ll_store(unsigned long long *base, long long i, double v, unsigned int epoch32) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  ll_store_word(base + 2 * i, (unsigned int)b, epoch32);
+  ll_store_word(base + 2 * i + 1, (unsigned int)(b >> 32), epoch32);
+}
+__device__ __forceinline__ void ll_store(unsigned long long *base, long long i, float v, unsigned int epoch32) {
+  ll_store_word(base + i, __float_as_uint(v), epoch32);
+}
+template <typename T> __device__ __forceinline__ T ll_load(const P2P &pp, const unsigned long long *base, long long i, unsigned int epoch32);
+template <> __device__ __forceinline__ double ll_load<double>(const P2P &pp, const unsigned long long *base, long long i, unsigned int epoch32) {
+  const unsigned long long lo = ll_load_word(pp, base + 2 * i, epoch32), hi = ll_load_word(pp, base + 2 * i + 1, epoch32);
+  return __longlong_as_double((long long)((hi << 32) | lo));
+}
+template <> __device__ __forceinline__ float ll_load<float>(const P2P &pp, const unsigned long long *base, long long i, unsigned int epoch32) {
+  return __uint_as_float(ll_load_word(pp, base + i, epoch32));
 }
 
 // Generic pair for buffers that have no fused producer / consumer: push src to every rank, then sum in place.

@@ -15,11 +15,12 @@
 //              beta (no xs round trip).  Each super-tile also leaves  sum_rows (D p)_row . row  - its share of p.(S p) -
 //              so the first dot product needs no pass over the reduced vectors.
 //     barrier A
-//              denom = sum of the super-tile dots (fixed order) + sum p dterm p ; alpha.   [multi-GPU: one scalar per
-//              rank crosses NVLink here, overlapped with the row gather below]
-//     phase U  owners: Ap_c = D_c sum(partial rows of c) [multi-GPU: pushed into every rank's receive slot with one
-//              flag per CTA - CTA b only waits for CTA b of its peers - and added in rank order], x += alpha p,
-//              r -= alpha Ap, z = M^-1 r, partial of r.z
+//              owners: Ap_c = D_c sum(partial rows of c)  [multi-GPU: stored straight into every rank's LL slot - data and
+//              epoch in one 8-byte word, no fence, no flag (p2p.cuh); CTA b of a peer owns the same cameras and polls
+//              exactly those words; the sums are added in rank order]
+//              denom = sum of the super-tile dots (fixed order) + sum p dterm p ; alpha   [multi-GPU: plus one scalar
+//              per rank, sent the same way while the vector is in flight]
+//     phase U  x += alpha p, r -= alpha Ap, z = M^-1 r, partial of r.z
 //     barrier B
 //              rz_new, rejection / convergence tests, beta           (pcg_schur.hpp:144-163)
 //   All CTAs (and all ranks) carry the PCG scalars redundantly from bit-identical sums, so control flow is uniform
@@ -30,14 +31,17 @@
 namespace gb {
 
 constexpr int SOLVE_THREADS = 2 * TILE, SOLVE_WARPS = SOLVE_THREADS / 32;
-constexpr int SOLVE_STAMPS = 8; // per iteration: P start, before A, after A, exchange done, before B, after B
+constexpr int SOLVE_STAMPS = 8; // per iteration: P start, before A, after A, exchange done, before B, after B, [6] pushed
 
 template <typename T, typename S> struct SolveSmem {
   using SM = SchurSmem2<T, S>;
   static constexpr int RED_OFF = SM::TOTAL;                       // T[32] reduction scratch
   static constexpr int WP_OFF = RED_OFF + 32 * (int)sizeof(double); // T[SOLVE_WARPS]
   static constexpr int CTL_OFF = WP_OFF + SOLVE_WARPS * (int)sizeof(double); // int[8]
-  static constexpr int TOTAL = CTL_OFF + 64;
+  static constexpr int NREC = 3;                                  // ring of per-super-tile records (current, next, next-next)
+  static constexpr int REC_OFF = CTL_OFF + 64;
+  static constexpr int TOTAL = REC_OFF + NREC * STREC_BYTES;
+  static_assert(REC_OFF % 16 == 0 && STREC_BYTES % 16 == 0, "TMA destinations must stay 16-byte aligned");
 };
 
 // p = beta p + z (ops::axpy_async(p, beta, p, z)): ONE definition, so that the owner of a camera and every CTA that
@@ -58,32 +62,13 @@ template <typename T> __device__ __forceinline__ void solve_publish(T wv, T *wpa
   }
 }
 
-// wait until every peer has published `epoch` in flag word f[q * stride]; a peer that never arrives sets the error flag
-__device__ __forceinline__ void solve_wait_peers(const P2P &pp, const unsigned long long *f, int stride,
-                                                 unsigned long long epoch) {
-  if (threadIdx.x < pp.nranks && (int)threadIdx.x != pp.rank) {
-    const unsigned long long *w = f + (size_t)threadIdx.x * stride;
-    if (ld_acquire_sys(w) < epoch) {
-      const unsigned long long t0 = global_timer_ns();
-      while (ld_acquire_sys(w) < epoch) {
-        if (global_timer_ns() - t0 > pp.timeout_ns) {
-          *pp.error = 1;
-          break;
-        }
-      }
-    }
-  }
-  __syncthreads();
-}
-
 template <typename T, typename S>
 __global__ void __launch_bounds__(SOLVE_THREADS, 1)
 k_pcg_solve(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *__restrict__ W,
             const T *__restrict__ scale_c, const T *__restrict__ dterm, const T *__restrict__ Minv,
             const T *__restrict__ bS, T *x, T *xbak, T *r, T *z, T *pbuf /*[2][9 Nc]*/, T *part /*[nrows][9]*/,
             T *st_dot /*[nst]*/, T *cta_red /*[2][grid]*/, PcgState<T> *st_out, unsigned int *work, T tol, T ratio,
-            int max_iter, P2P pp, int multi, unsigned long long *cta_flags /*own: [nranks][grid]*/,
-            unsigned long long *timing /*[max_iter + 1][SOLVE_STAMPS] or null*/) {
+            int max_iter, P2P pp, int multi, unsigned long long *timing /*[max_iter + 1][SOLVE_STAMPS] or null*/) {
   namespace cg = cooperative_groups;
   using SM = SchurSmem2<T, S>;
   using SS = SolveSmem<T, S>;
@@ -115,12 +100,38 @@ k_pcg_solve(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *_
   const unsigned long long epoch0 = multi ? p2p_current_epoch(pp) : 0ull;
   const unsigned int grabs_per_iter = (unsigned int)(nst + G); // every CTA ends an iteration with one failing grab
 
+  unsigned char *recbuf = smem + SS::REC_OFF;
+  uint64_t *rbar = bars + SM::NMETA; // one mbarrier per record buffer
   if (threadIdx.x == 0) {
-    for (int s = 0; s < SM::NMETA; s++) mbar_init(&bars[s], 1);
+    for (int s = 0; s < SM::NMETA + SS::NREC; s++) mbar_init(&bars[s], 1);
     mbar_fence_init();
     fence_proxy_async();
   }
   if (leader) *work = 0u;
+  // Work items (super-tiles) come from an atomic counter that is never reset during the solve: every CTA ends an
+  // iteration with exactly ONE failing grab, so iteration k hands out the values k * (nst + G) ... .  Item number n of this
+  // CTA (over the whole solve) has its record in buffer n % 3, on that buffer's mbarrier with phase parity (n / 3) & 1.
+  int n_cur = 0; // sequence number of the current item (identical in all threads)
+  // thread 0: grab the first two items of iteration kk and start fetching their records; ctl[0] = cur, ctl[1] = next
+  auto grab_first = [&](int kk) {
+    const unsigned int base = (unsigned int)kk * grabs_per_iter;
+    const int cur = (int)(atomicAdd(work, 1u) - base);
+    const int nxt = cur < nst ? (int)(atomicAdd(work, 1u) - base) : cur;
+    fence_proxy_async();
+    if (cur < nst) {
+      mbar_expect_tx(&rbar[n_cur % SS::NREC], STREC_BYTES);
+      bulk_g2s(recbuf + (n_cur % SS::NREC) * STREC_BYTES, ds.strec + (int64_t)cur * STREC_BYTES, STREC_BYTES, &rbar[n_cur % SS::NREC]);
+    }
+    if (nxt < nst) {
+      mbar_expect_tx(&rbar[(n_cur + 1) % SS::NREC], STREC_BYTES);
+      bulk_g2s(recbuf + ((n_cur + 1) % SS::NREC) * STREC_BYTES, ds.strec + (int64_t)nxt * STREC_BYTES, STREC_BYTES,
+               &rbar[(n_cur + 1) % SS::NREC]);
+    }
+    ctl[0] = cur;
+    ctl[1] = nxt;
+  };
+  auto rec_wait = [&](int n) { mbar_wait(&rbar[n % SS::NREC], (uint32_t)((n / SS::NREC) & 1)); };
+  auto rec_ptr = [&](int n) { return reinterpret_cast<const int32_t *>(recbuf + (n % SS::NREC) * STREC_BYTES); };
 
   // ---- start: x = 0, r = b_S, z = M^-1 r, p_old = 0, rz = r.z   (pcg_schur.hpp:90-106) ----------------------------
   {
@@ -153,6 +164,8 @@ k_pcg_solve(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *_
   s.rz0 = (T)INFINITY; s.alpha = T(0); s.beta = T(0); s.denom = T(0);
   s.iter = 0; s.done = 0; s.reason = 0; s.pad = 0;
   T beta = T(0);
+  if (threadIdx.x == 0) grab_first(0); // (later iterations: grabbed before barrier B, while other CTAs still update)
+  bool pregrabbed = true;              // items are grabbed and their records in flight, not yet consumed
   int ring = 0;        // ring index of the next tile of this CTA's tile sequence
   int my_issued = -1;  // (thread 0 of each worker) highest ring index of the worker's parity whose copies are issued
   int k = 0;
@@ -178,27 +191,38 @@ k_pcg_solve(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *_
       solve_publish<T>(pdp_w, wpart, cta_red);
     }
     // ---- the product over the super-tiles the work counter hands out -----------------------------------------------
+    // A super-tile boundary costs two CTA barriers and one pass: the rows and the dot of the finished super-tile are
+    // written in the same pass that builds the camera vector rows of the next one, whose record (camera list, row
+    // positions, tile range) was fetched by TMA a super-tile ahead.  (First version: separate epilogue and prologue with
+    // dependent global loads st_row -> row_cam -> p, z and five barriers: 3.6 us per boundary, measured by sweeping the
+    // super-tile size, gpurun_out/r2h_sweep4.log.)
     {
       const unsigned int base = (unsigned int)k * grabs_per_iter;
-      if (threadIdx.x == 0) ctl[0] = (int)(atomicAdd(work, 1u) - base);
-      __syncthreads();
-      int cur = ctl[0];
+      // xl row i of camera cam[i / 9]: (D p)_c with the owner's arithmetic; p_old and z were written by other CTAs
+      // during this kernel: L2 loads
+      auto build_xl = [&](const int32_t *cam, int i) {
+        const int sl = i / 9, kk = i - 9 * sl;
+        const int j = cam[sl] * 9 + kk;
+        xl[i] = scale_c[j] * pcg_direction<T>(beta, __ldcg(p_old + j), __ldcg(z + j));
+      };
+      __syncthreads(); // ctl[0], ctl[1] of grab_first
+      pregrabbed = false;
+      int cur = ctl[0], nxt = ctl[1];
       int ib = ring;
-      while (cur < nst) {
-        if (threadIdx.x == 0) ctl[1] = (int)(atomicAdd(work, 1u) - base); // the next item, known a super-tile ahead
-        const int tile_base = ds.st_tile[cur], ie = ib + (ds.st_tile[cur + 1] - tile_base);
-        const int row0 = ds.st_row[cur], nslots = ds.st_row[cur + 1] - row0;
-        for (int i = threadIdx.x; i < nslots * 9; i += SOLVE_THREADS) {
-          const int sl = i / 9, kk = i - 9 * sl;
-          const int j = ds.row_cam[row0 + sl] * 9 + kk;
-          // (D p)_c with the owner's arithmetic; p_old and z were written by other CTAs during this kernel: L2 loads
-          xl[i] = scale_c[j] * pcg_direction<T>(beta, __ldcg(p_old + j), __ldcg(z + j));
+      if (cur < nst) {
+        rec_wait(n_cur);
+        const int32_t *R = rec_ptr(n_cur);
+        const int n9 = R[3] * 9;
+        for (int i = threadIdx.x; i < n9; i += SOLVE_THREADS) {
+          build_xl(R + STREC_CAM / 4, i);
+          acc_all[i] = T(0);
+          acc_all[SLOT_CAP * 9 + i] = T(0);
         }
-        for (int i = t; i < nslots * 9; i += TILE) acc[i] = T(0);
         __syncthreads();
-        const int nxt = ctl[1];
-        int nb_tile = 0, nb_nt = 0;
-        if (nxt < nst) { nb_tile = ds.st_tile[nxt]; nb_nt = ds.st_tile[nxt + 1] - nb_tile; }
+      }
+      while (cur < nst) {
+        const int32_t *R = rec_ptr(n_cur);
+        const int tile_base = R[0], ie = ib + R[1], n9 = R[3] * 9;
         for (int i = ib + ((ib ^ worker) & 1); i < ie; i += 2) { // worker w takes ring indices of parity w
           if (t == 0 && i > my_issued) { // not prefetched (first tiles of an iteration, one-tile super-tiles)
             const int tile = tile_base + (i - ib);
@@ -218,29 +242,72 @@ k_pcg_solve(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *_
               fence_proxy_async();
               product_issue<T, S>(smem, bars, ds, J, W, tile_base + (j - ib), j, next_p0, next_np, pol);
               my_issued = j;
-            } else if (j - ie < nb_nt) { // first tiles of the NEXT super-tile: the ring runs across the boundary
-              const int tile = nb_tile + (j - ie);
-              const int p0 = ds.tmeta[tile].p0, np = ds.tmeta[tile].np;
-              fence_proxy_async();
-              product_issue<T, S>(smem, bars, ds, J, W, tile, j, p0, np, pol);
-              my_issued = j;
+            } else if (nxt < nst) { // first tiles of the NEXT super-tile: the ring runs across the boundary
+              rec_wait(n_cur + 1);
+              const int32_t *RN = rec_ptr(n_cur + 1);
+              if (j - ie < RN[1]) {
+                const int tile = RN[0] + (j - ie);
+                const int p0 = ds.tmeta[tile].p0, np = ds.tmeta[tile].np;
+                fence_proxy_async();
+                product_issue<T, S>(smem, bars, ds, J, W, tile, j, p0, np, pol);
+                my_issued = j;
+              }
             }
           });
         }
-        __syncthreads();
-        // rows of this super-tile (worker 0 + worker 1, fixed order) and its share of p . (S p)
-        T d = T(0);
-        for (int i = threadIdx.x; i < nslots * 9; i += SOLVE_THREADS) {
-          const int sl = i / 9, kk = i - 9 * sl;
-          const T v = acc_all[i] + acc_all[SLOT_CAP * 9 + i];
-          part[(int64_t)ds.row_out[row0 + sl] * 9 + kk] = v;
-          d += xl[i] * v;
+        __syncthreads(); // both workers' accumulator rows are complete
+        // the item after next, grabbed a super-tile ahead (its record lands while the next super-tile is processed)
+        if (threadIdx.x == 0) {
+          int nn = nxt;
+          if (nxt < nst) {
+            nn = (int)(atomicAdd(work, 1u) - base);
+            if (nn < nst) {
+              fence_proxy_async();
+              mbar_expect_tx(&rbar[(n_cur + 2) % SS::NREC], STREC_BYTES);
+              bulk_g2s(recbuf + ((n_cur + 2) % SS::NREC) * STREC_BYTES, ds.strec + (int64_t)nn * STREC_BYTES, STREC_BYTES,
+                       &rbar[(n_cur + 2) % SS::NREC]);
+            }
+          }
+          ctl[2] = nn;
         }
-        d = block_sum<T>(d, red);
-        if (threadIdx.x == 0) st_dot[cur] = d;
-        __syncthreads(); // xl / acc / ctl are rewritten by the next super-tile
+        // one pass: rows of this super-tile (worker 0 + worker 1, fixed order), its share of p . (S p), and the camera
+        // vector rows + cleared accumulators of the next super-tile
+        const int32_t *RN = nullptr;
+        int m9 = 0;
+        if (nxt < nst) {
+          rec_wait(n_cur + 1);
+          RN = rec_ptr(n_cur + 1);
+          m9 = RN[3] * 9;
+        }
+        T d = T(0);
+        const int32_t *out = R + STREC_OUT / 4;
+        for (int i = threadIdx.x; i < max(n9, m9); i += SOLVE_THREADS) {
+          if (i < n9) {
+            const int sl = i / 9, kk = i - 9 * sl;
+            const T v = acc_all[i] + acc_all[SLOT_CAP * 9 + i];
+            part[(int64_t)out[sl] * 9 + kk] = v;
+            d += xl[i] * v;
+          }
+          if (i < m9) {
+            build_xl(RN + STREC_CAM / 4, i);
+            acc_all[i] = T(0);
+            acc_all[SLOT_CAP * 9 + i] = T(0);
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) d += __shfl_down_sync(0xffffffffu, d, o);
+        if (lane == 0) wpart[warp] = d;
+        __syncthreads(); // next super-tile's rows are ready; the warp partials of the dot and ctl[2] are visible
+        if (threadIdx.x == 0) {
+          T tot = T(0);
+#pragma unroll
+          for (int w = 0; w < SOLVE_WARPS; w++) tot += wpart[w];
+          st_dot[cur] = tot;
+        }
         ib = ie;
         cur = nxt;
+        nxt = ctl[2];
+        n_cur++;
       }
       ring = ib;
     }
@@ -249,19 +316,7 @@ k_pcg_solve(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *_
     grid.sync(); // ---- barrier A: partial rows, super-tile dots and p are visible -------------------------------------
     if (timing && leader) timing[k * SOLVE_STAMPS + 2] = global_timer_ns();
     const unsigned long long epoch = epoch0 + (unsigned long long)k + 1ull;
-    T dot = grid_total<T>(st_dot, nst, red);
-    const T pdp = grid_total<T>(cta_red, G, red);
-    if (multi && blockIdx.x == 0) {
-      // this rank's share of p.(S p) goes to every peer (one scalar after the vector area of the slot), then the flag
-      if (threadIdx.x < pp.nranks && (int)threadIdx.x != pp.rank)
-        *reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(p2p_slot<T>(pp, threadIdx.x, pp.rank, epoch)) +
-                               (size_t)54 * Nc * sizeof(T)) = dot;
-      __threadfence_system();
-      __syncthreads();
-      if (threadIdx.x < pp.nranks && (int)threadIdx.x != pp.rank) st_relaxed_sys(pp.flags[threadIdx.x] + pp.rank, epoch);
-    }
-
-    // ---- phase U: Ap_raw = D_c * (sum of the camera's partial rows) --------------------------------------------------
+    const unsigned int e32 = (unsigned int)epoch;
     auto gather_raw = [&](int c) -> T { // valid in lanes 0..8
       const int b = ds.cam_row_ptr[c], n = ds.cam_row_ptr[c + 1] - b;
       T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0), a4 = T(0), a5 = T(0), a6 = T(0), a7 = T(0);
@@ -289,27 +344,25 @@ k_pcg_solve(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *_
       return own ? scale_c[c * 9 + k9] * ((v + v1) + v2) : T(0);
     };
     if (multi) {
-      // this rank's sums go straight into every rank's receive slot; one flag per CTA: CTA b of a peer owns the same
-      // cameras and waits for nothing else
+      // this rank's sums go straight into every rank's LL slot (p2p.cuh): data and epoch in one 8-byte word, no fence, no
+      // flag; CTA b of every peer owns the same cameras and polls exactly these words
       for (int c = c_begin + warp; c < c_end; c += SOLVE_WARPS) {
         const T raw = gather_raw(c);
         if (own)
-          for (int q = 0; q < pp.nranks; q++) p2p_slot<T>(pp, q, pp.rank, epoch)[c * 9 + k9] = raw;
+          for (int q = 0; q < pp.nranks; q++) ll_store(ll_slot(pp, q, pp.rank, epoch), (long long)c * 9 + k9, raw, e32);
       }
-      __threadfence_system();
-      __syncthreads();
-      if (threadIdx.x < pp.nranks && (int)threadIdx.x != pp.rank)
-        st_relaxed_sys(reinterpret_cast<unsigned long long *>(pp.recv[threadIdx.x] + pp.cta_flag_off) +
-                           (size_t)pp.rank * G + blockIdx.x, epoch);
-      solve_wait_peers(pp, pp.flags[pp.rank], 1, epoch);
+    }
+    T dot = grid_total<T>(st_dot, nst, red);
+    const T pdp = grid_total<T>(cta_red, G, red);
+    if (multi) {
+      // p.(S p) needs one scalar per rank: CTA 0 sends this rank's (the word after the vector), everybody reads all of them
+      if (blockIdx.x == 0 && threadIdx.x < pp.nranks)
+        ll_store(ll_slot(pp, threadIdx.x, pp.rank, epoch), (long long)9 * Nc, dot, e32);
+      if (timing && leader) timing[k * SOLVE_STAMPS + 6] = global_timer_ns();
       T tot = T(0);
-      for (int q = 0; q < pp.nranks; q++) // rank order; this rank's own share straight from the register
-        tot += q == pp.rank ? dot
-                            : __ldcg(reinterpret_cast<const T *>(reinterpret_cast<const unsigned char *>(
-                                                                     p2p_slot<T>(pp, pp.rank, q, epoch)) +
-                                                                 (size_t)54 * Nc * sizeof(T)));
+      for (int q = 0; q < pp.nranks; q++) // rank order: bit-identical on every rank
+        tot += q == pp.rank ? dot : ll_load<T>(pp, ll_slot(pp, pp.rank, q, epoch), (long long)9 * Nc, e32);
       dot = tot;
-      solve_wait_peers(pp, cta_flags + blockIdx.x, G, epoch);
     }
     if (timing && leader) timing[k * SOLVE_STAMPS + 3] = global_timer_ns();
     const T denom = dot + pdp;
@@ -323,7 +376,9 @@ k_pcg_solve(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *_
       const T raw0 = multi ? T(0) : gather_raw(c);
       T rn = T(0);
       if (own) {
-        const T raw = multi ? p2p_sum<T>(pp, epoch, i) : raw0;
+        T raw = raw0;
+        if (multi) // the ranks' sums in rank order (this rank's own went through its own slot too)
+          for (int q = 0; q < pp.nranks; q++) raw += ll_load<T>(pp, ll_slot(pp, pp.rank, q, epoch), i, e32);
         const T pn = p_new[i];
         const T ap = raw + dterm[i] * pn;
         const T xo = x[i];
@@ -341,6 +396,12 @@ k_pcg_solve(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *_
       }
       if (own) z[i] = a;
       rz_w += sum9<T>(own ? rn * a : T(0));
+    }
+    // this CTA's share of the update is done: take the first work items of the next iteration now, so that their
+    // records are in shared memory when barrier B opens
+    if (k + 1 < max_iter) {
+      if (threadIdx.x == 0) grab_first(k + 1);
+      pregrabbed = true;
     }
     solve_publish<T>(rz_w, wpart, cta_red + G);
     if (timing && leader) timing[k * SOLVE_STAMPS + 4] = global_timer_ns();
@@ -365,6 +426,11 @@ k_pcg_solve(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *_
     if (fabs(rzn) < tol) { s.done = 1; s.reason = 1; k++; break; } // :160-162 (the p update before it is not needed)
   }
   if (!s.done) { s.done = 1; s.reason = 0; }
+  if (pregrabbed) { // records of items that will never be processed are still in flight: let them land before the CTA exits
+    __syncthreads();
+    if (ctl[0] < nst) rec_wait(n_cur);
+    if (ctl[1] < nst) rec_wait(n_cur + 1);
+  }
   if (leader) {
     *st_out = s;
     // exchanges consumed: one per iteration that reached barrier A (k counts them on every exit path)

@@ -42,6 +42,12 @@ constexpr int REC_META = REC_PT + (TILE_PTS + 8) * 2;    // 2336
 constexpr int REC_NEXT = REC_META + 32;                  // 2368: (p0, np) of tiles k+1 .. k+4 (TMA issue needs them)
 constexpr int REC_BYTES = REC_NEXT + 32;                 // 2400 = 150 * 16
 
+// Packed per-super-tile record (one TMA bulk copy, fetched a super-tile ahead by k_pcg_solve): first tile, tile count, first
+// partial row, camera rows | camera of every row [SLOT_CAP] | position of every row in the partial buffers [SLOT_CAP]
+constexpr int STREC_CAM = 16;
+constexpr int STREC_OUT = STREC_CAM + SLOT_CAP * 4;
+constexpr int STREC_BYTES = STREC_OUT + SLOT_CAP * 4;    // 1552 = 97 * 16
+
 struct TileMeta {
   int32_t p0;      // first point
   int32_t n;       // observations in the tile
@@ -73,6 +79,7 @@ struct HostStructure {
   std::vector<int32_t> st_tile, st_row, row_cam, cam_row_ptr, cam_row_list, slot_of_obs;
   std::vector<int32_t> row_out;                 // [nrows] super-tile row -> camera-major position in the partial buffers
   std::vector<int32_t> cta_st;                  // [ncta+1] super-tile ranges of the persistent CTAs (balanced by tiles)
+  std::vector<uint8_t> strec;                   // [nst][STREC_BYTES] packed per-super-tile records
   std::vector<int32_t> tile_cam;                // [Mstore] camera per storage slot (0 in padding)
   // camera-major view (k_prepare_cams): the observations of camera c in ascending (point) order are entries
   // [cm_ptr(c), cm_ptr(c+1)); they are cut into chunks of <= CAM_CHUNK, one CTA and one partial row each
@@ -295,6 +302,17 @@ struct HostStructure {
     // partial buffers are camera-major: the rows of one camera are contiguous, in ascending super-tile order
     row_out.resize(nrows);
     for (int32_t i = 0; i < nrows; i++) row_out[cam_row_list[i]] = i;
+    // ---- packed per-super-tile records -----------------------------------------------------------------------
+    strec.assign((size_t)nst * STREC_BYTES, 0);
+    for (int32_t s2 = 0; s2 < nst; s2++) {
+      int32_t *r = reinterpret_cast<int32_t *>(strec.data() + (size_t)s2 * STREC_BYTES);
+      r[0] = st_tile[s2]; r[1] = st_tile[s2 + 1] - st_tile[s2];
+      r[2] = st_row[s2];  r[3] = st_row[s2 + 1] - st_row[s2];
+      for (int32_t q = 0; q < r[3]; q++) {
+        r[STREC_CAM / 4 + q] = row_cam[st_row[s2] + q];
+        r[STREC_OUT / 4 + q] = row_out[st_row[s2] + q];
+      }
+    }
     // ---- camera-major view: counting sort by camera (stable: ascending point order inside a camera) ---------
     {
       std::vector<int32_t> cptr((size_t)nc + 1, 0);

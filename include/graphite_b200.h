@@ -277,7 +277,8 @@ typedef struct {
   /* profile_product: where the PCG iterations spent their time, from globaltimer stamps of CTA 0 inside k_pcg_solve,
    * summed over the executed iterations: [0] product phase up to CTA 0's arrival at the grid barrier that ends it,
    * [1] that barrier (waiting for the slowest CTA), [2] scalar sums + multi-GPU exchange (push, flags, waiting for the
-   * peers), [3] row sums and vector updates, [4] the second grid barrier, [5] reserved */
+   * peers), [3] row sums and vector updates, [4] the second grid barrier, [5] multi-GPU: the part of [2] until this rank's
+   * own sums are on their way (the rest of [2] is waiting for the peers) */
   double pcg_phase_seconds[6];
 } gb_lm_result;
 typedef enum { GB_LM_DONE = 0, GB_LM_DAMPING_NOT_FINITE = 1, GB_LM_RHO_ZERO = 2, GB_LM_STOP_FLAG = 3, GB_LM_EARLY_STOP = 4 } gb_lm_termination;
