@@ -264,8 +264,6 @@ template <typename T, typename S> struct Problem : ProblemBase {
     ts.Nc = hs.Nc; ts.Np = hs.Np; ts.ntiles = hs.ntiles(); ts.nst = hs.nst(); ts.nrows = hs.nrows(); ts.pad = 0;
     GB_TRY(upload(ts.tmeta, hs.tmeta));
     GB_TRY(upload(ts.ometa, hs.ometa));
-    GB_TRY(upload(ts.seg_tab, hs.seg_tab));
-    GB_TRY(upload(ts.pt_tab, hs.pt_tab));
     GB_TRY(upload(ts.trec, hs.trec));
     GB_TRY(upload(ts.tile_cam, hs.tile_cam));
     GB_TRY(upload(ts.st_tile, hs.st_tile));
@@ -1600,6 +1598,7 @@ int gb_structure_info(const gb_structure *s, int64_t info[12]) {
 }
 int gb_structure_array(const gb_structure *s, int which, void *out, int64_t *count) {
   if (!s || !count) return GB_ERR_INVALID;
+  if (which == 14 || which == 15) const_cast<gb_structure *>(s)->hs.materialize_tables();
   const gb::HostStructure &h = s->hs;
   const std::vector<int32_t> *v32[] = {&h.cam_idx, &h.pt_idx, &h.pptr, &h.tile_obs, &h.tile_pt, &h.st_tile,
                                        &h.st_row, &h.row_cam, &h.cam_row_ptr, &h.cam_row_list, &h.slot_of_obs};

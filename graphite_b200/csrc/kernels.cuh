@@ -79,8 +79,6 @@ struct DevStruct {
   int32_t Nc, Np, ntiles, nst, nrows, pad;
   const TileMeta *tmeta;     // [ntiles]
   const uint32_t *ometa;     // [Mstore]  cslot:16 | position in point order:8 | point-in-tile:8
-  const uint32_t *seg_tab;   // per tile at seg_off: nseg + 1 entries  begin:16 | cslot:16
-  const uint16_t *pt_tab;    // per tile at pt_off: np + 1 row offsets
   const unsigned char *trec; // [ntiles][REC_BYTES] packed per-tile record (ometa | seg_tab | pt_tab | meta)
   const int32_t *tile_cam;   // [Mstore] camera of each storage slot (one-CTA-per-tile kernels)
   const int32_t *st_tile;    // [nst+1]

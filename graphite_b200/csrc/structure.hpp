@@ -25,6 +25,7 @@
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace gb {
@@ -91,6 +92,31 @@ struct HostStructure {
   int32_t max_track = 0;
   int64_t nseg_total = 0;
 
+  // run fn(begin, end) over [0, n) split into contiguous ranges on the host's hardware threads (<= 16)
+  static int host_threads(int64_t n) {
+    return (int)std::min<int64_t>(std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u), std::max<int64_t>(n, 1));
+  }
+  template <typename F> static void parallel_indexed(int64_t n, int nth, F &&fn) { // fn(thread index, begin, end)
+    if (nth <= 1) { fn(0, (int64_t)0, n); return; }
+    std::vector<std::thread> th;
+    for (int i = 0; i < nth; i++) th.emplace_back([&, i]() { fn(i, n * i / nth, n * (i + 1) / nth); });
+    for (auto &t : th) t.join();
+  }
+  template <typename F> static void parallel_ranges(int64_t n, F &&fn) {
+    parallel_indexed(n, host_threads(n), [&](int, int64_t b, int64_t e) { fn((int32_t)b, (int32_t)e); });
+  }
+  // compact per-tile tables (host view for tests / exports; the kernels read the packed records)
+  void materialize_tables() {
+    if (!seg_tab.empty() || tmeta.empty()) return;
+    for (size_t k = 0; k < tmeta.size(); k++) {
+      const TileMeta &tm = tmeta[k];
+      const uint32_t *sg = reinterpret_cast<const uint32_t *>(trec.data() + k * REC_BYTES + REC_SEG);
+      const uint16_t *pt = reinterpret_cast<const uint16_t *>(trec.data() + k * REC_BYTES + REC_PT);
+      for (int32_t i = 0; i < (tm.nseg + 1 + 3) / 4 * 4; i++) seg_tab.push_back(sg[i]);
+      for (int32_t i = 0; i < (tm.np + 1 + 7) / 8 * 8; i++) pt_tab.push_back(pt[i]);
+    }
+  }
+
   // returns an empty string on success, else the reason
   std::string build(int64_t nc, int64_t np, int64_t m, const int32_t *ci, const int32_t *pi, int tile_size,
                     int slot_cap_opt = 0, int64_t st_obs_opt = 0, bool partition = false) {
@@ -101,16 +127,27 @@ struct HostStructure {
     if (slot_cap_opt <= 0) slot_cap_opt = SLOT_CAP;
     if (slot_cap_opt > SLOT_CAP) return "slot cap must be <= 192";
     M = m; Nc = (int32_t)nc; Np = (int32_t)np; tile_fill = tile_size; slot_cap = slot_cap_opt;
-    for (int64_t i = 0; i < m; i++)
-      if (ci[i] < 0 || ci[i] >= nc || pi[i] < 0 || pi[i] >= np) return "observation index out of range";
-    bool sorted = true;
-    for (int64_t i = 1; i < m && sorted; i++)
-      sorted = (pi[i] > pi[i - 1]) || (pi[i] == pi[i - 1] && ci[i] > ci[i - 1]);
     cam_idx.resize(m); pt_idx.resize(m);
+    bool sorted = true;
+    {
+      // range check, order check and copy in one pass on the host threads
+      const int nth = host_threads(m / 65536 + 1);
+      std::vector<int> bad((size_t)nth, 0), unsorted((size_t)nth, 0);
+      parallel_indexed(m, nth, [&](int t, int64_t ob, int64_t oe) {
+        for (int64_t i = ob; i < oe; i++) {
+          if (ci[i] < 0 || ci[i] >= nc || pi[i] < 0 || pi[i] >= np) bad[t] = 1;
+          if (i > 0 && !((pi[i] > pi[i - 1]) || (pi[i] == pi[i - 1] && ci[i] > ci[i - 1]))) unsorted[t] = 1;
+          cam_idx[i] = ci[i];
+          pt_idx[i] = pi[i];
+        }
+      });
+      for (int t = 0; t < nth; t++) {
+        if (bad[t]) return "observation index out of range";
+        if (unsorted[t]) sorted = false;
+      }
+    }
     if (sorted) {
       identity_perm = true;
-      std::copy(ci, ci + m, cam_idx.begin());
-      std::copy(pi, pi + m, pt_idx.begin());
     } else {
       identity_perm = false;
       perm.resize(m);
@@ -229,66 +266,74 @@ struct HostStructure {
     // ---- per-tile tables ----------------------------------------------------------------------------------
     tmeta.assign((size_t)nt, TileMeta{});
     ometa.assign((size_t)Mstore, 0u);
-    rank.assign((size_t)m, 0);
+    rank.resize((size_t)m);
     slot_of_obs.resize(m);
     tile_cam.assign((size_t)Mstore, 0);
-    seg_tab.clear(); pt_tab.clear();
-    nseg_total = 0;
-    std::vector<std::pair<int32_t, int32_t>> loc;
-    for (int32_t s = 0; s < nst; s++) {
-      for (int32_t r = st_row[s]; r < st_row[s + 1]; r++) local[row_cam[r]] = r - st_row[s];
-      for (int32_t k = st_tile[s]; k < st_tile[s + 1]; k++) {
-        const int32_t o0 = tile_obs[k], n = tile_obs[k + 1] - o0;
-        const int32_t p0 = tile_pt[k], npt = tile_pt[k + 1] - p0;
-        TileMeta &tm = tmeta[k];
-        tm.p0 = p0; tm.n = n; tm.np = npt; tm.o0 = o0; tm.pad = 0;
-        loc.resize(n);
-        for (int32_t u = 0; u < n; u++) loc[u] = {cam_idx[o0 + u], u};
-        std::sort(loc.begin(), loc.end());
-        tm.seg_off = (int32_t)seg_tab.size();
-        int32_t nseg = 0;
-        for (int32_t u = 0; u < n; u++) {
-          const int32_t pos = loc[u].second;
-          rank[o0 + pos] = (uint8_t)u;
-          const uint32_t cslot = (uint32_t)local[loc[u].first];
-          const uint32_t ptl = (uint32_t)(pt_idx[o0 + pos] - p0);
-          // the slot of an observation is its position u in the tile's (camera, observation) order: threads of one
-          // camera segment are adjacent (broadcast reads of the camera row, conflict-free staging); the meta keeps
-          // the position `pos` in (point, camera) order, where the point-side sums are staged
-          ometa[(size_t)k * TILE + u] = (cslot << 16) | ((uint32_t)pos << 8) | ptl;
-          slot_of_obs[o0 + pos] = k * TILE + u;
-          tile_cam[(size_t)k * TILE + u] = loc[u].first;
-          if (u == 0 || loc[u].first != loc[u - 1].first) {
-            seg_tab.push_back(((uint32_t)u << 16) | cslot);
-            nseg++;
+    seg_tab.clear(); pt_tab.clear(); // compact copies of the tables are materialised on demand (materialize_tables)
+    trec.assign((size_t)nt * REC_BYTES, 0);
+    // Per-tile tables, written straight into the packed records.  Super-tiles are independent: host threads take
+    // contiguous ranges of them.  Inside a tile the observations are put in (camera, observation) order by a counting
+    // sort on the camera's row slot in the super-tile (<= slot_cap values), which is the ascending camera order.
+    parallel_ranges(nst, [&](int32_t s_begin, int32_t s_end) {
+      std::vector<int32_t> local_t((size_t)nc, 0);
+      int32_t start[SLOT_CAP + 1];
+      int32_t cs[TILE], order[TILE];
+      for (int32_t s = s_begin; s < s_end; s++) {
+        const int32_t nslots = st_row[s + 1] - st_row[s];
+        for (int32_t r = st_row[s]; r < st_row[s + 1]; r++) local_t[row_cam[r]] = r - st_row[s];
+        for (int32_t k = st_tile[s]; k < st_tile[s + 1]; k++) {
+          const int32_t o0 = tile_obs[k], n = tile_obs[k + 1] - o0;
+          const int32_t p0 = tile_pt[k], npt = tile_pt[k + 1] - p0;
+          TileMeta &tm = tmeta[k];
+          tm.p0 = p0; tm.n = n; tm.np = npt; tm.o0 = o0; tm.pad = 0;
+          for (int32_t q = 0; q <= nslots; q++) start[q] = 0;
+          for (int32_t u = 0; u < n; u++) { cs[u] = local_t[cam_idx[o0 + u]]; start[cs[u] + 1]++; }
+          for (int32_t q = 0; q < nslots; q++) start[q + 1] += start[q];
+          for (int32_t u = 0; u < n; u++) order[start[cs[u]]++] = u; // stable: ties keep the (point, camera) order
+          uint8_t *rec = trec.data() + (size_t)k * REC_BYTES;
+          uint32_t *om = reinterpret_cast<uint32_t *>(rec + REC_OMETA);
+          uint32_t *sg = reinterpret_cast<uint32_t *>(rec + REC_SEG);
+          int32_t nseg = 0;
+          for (int32_t u = 0; u < n; u++) {
+            const int32_t pos = order[u];
+            rank[o0 + pos] = (uint8_t)u;
+            const uint32_t cslot = (uint32_t)cs[pos];
+            const uint32_t ptl = (uint32_t)(pt_idx[o0 + pos] - p0);
+            // the slot of an observation is its position u in the tile's (camera, observation) order: threads of one
+            // camera segment are adjacent (broadcast reads of the camera row, conflict-free staging); the meta keeps
+            // the position `pos` in (point, camera) order, where the point-side sums are staged
+            const uint32_t w = (cslot << 16) | ((uint32_t)pos << 8) | ptl;
+            ometa[(size_t)k * TILE + u] = w;
+            om[u] = w;
+            slot_of_obs[o0 + pos] = k * TILE + u;
+            tile_cam[(size_t)k * TILE + u] = cam_idx[o0 + pos];
+            if (u == 0 || cslot != (uint32_t)cs[order[u - 1]]) sg[nseg++] = ((uint32_t)u << 16) | cslot;
+          }
+          // padding slots: unique point-order positions n..TILE-1 (their rows are never read), camera slot 0, point 0
+          for (int32_t u = n; u < TILE; u++) { ometa[(size_t)k * TILE + u] = ((uint32_t)u << 8); om[u] = ((uint32_t)u << 8); }
+          tm.nseg = nseg;
+          for (int32_t i = nseg; i < TILE + 4; i++) sg[i] = ((uint32_t)n << 16); // sentinel: end of the last segment
+          uint16_t *pt = reinterpret_cast<uint16_t *>(rec + REC_PT);
+          for (int32_t i = 0; i < TILE_PTS + 8; i++) pt[i] = i <= npt ? (uint16_t)(pptr[p0 + i] - o0) : (uint16_t)n;
+          int32_t *nx = reinterpret_cast<int32_t *>(rec + REC_NEXT);
+          for (int32_t d = 1; d <= 4; d++) {
+            nx[2 * (d - 1)] = k + d < nt ? tile_pt[k + d] : 0;
+            nx[2 * (d - 1) + 1] = k + d < nt ? tile_pt[k + d + 1] - tile_pt[k + d] : 0;
           }
         }
-        // padding slots: unique point-order positions n..TILE-1 (their rows are never read), camera slot 0, point 0
-        for (int32_t u = n; u < TILE; u++) ometa[(size_t)k * TILE + u] = ((uint32_t)u << 8);
-        tm.nseg = nseg;
-        nseg_total += nseg;
-        seg_tab.push_back(((uint32_t)n << 16)); // sentinel: end of the last segment
-        while (seg_tab.size() % 4) seg_tab.push_back(((uint32_t)n << 16));
-        tm.pt_off = (int32_t)pt_tab.size();
-        for (int32_t q = 0; q <= npt; q++) pt_tab.push_back((uint16_t)(pptr[p0 + q] - o0));
-        while (pt_tab.size() % 8) pt_tab.push_back((uint16_t)n);
       }
-    }
-    // ---- packed per-tile records ----------------------------------------------------------------------------
-    trec.assign((size_t)nt * REC_BYTES, 0);
-    for (int32_t k = 0; k < nt; k++) {
-      uint8_t *rec = trec.data() + (size_t)k * REC_BYTES;
-      const TileMeta &tm = tmeta[k];
-      memcpy(rec + REC_OMETA, ometa.data() + (size_t)k * TILE, TILE * 4);
-      uint32_t *sg = reinterpret_cast<uint32_t *>(rec + REC_SEG);
-      for (int32_t i = 0; i < TILE + 4; i++) sg[i] = i <= tm.nseg ? seg_tab[tm.seg_off + i] : ((uint32_t)tm.n << 16);
-      uint16_t *pt = reinterpret_cast<uint16_t *>(rec + REC_PT);
-      for (int32_t i = 0; i < TILE_PTS + 8; i++) pt[i] = i <= tm.np ? pt_tab[tm.pt_off + i] : (uint16_t)tm.n;
-      memcpy(rec + REC_META, &tm, sizeof(TileMeta));
-      int32_t *nx = reinterpret_cast<int32_t *>(rec + REC_NEXT);
-      for (int32_t d = 1; d <= 4; d++) {
-        nx[2 * (d - 1)] = k + d < nt ? tmeta[k + d].p0 : 0;
-        nx[2 * (d - 1) + 1] = k + d < nt ? tmeta[k + d].np : 0;
+    });
+    // offsets of the compact tables (multiples of 4 / 8 entries per tile) and the tile meta inside the records
+    nseg_total = 0;
+    {
+      int32_t seg_off = 0, pt_off = 0;
+      for (int32_t k = 0; k < nt; k++) {
+        TileMeta &tm = tmeta[k];
+        tm.seg_off = seg_off; tm.pt_off = pt_off;
+        seg_off += (tm.nseg + 1 + 3) / 4 * 4;
+        pt_off += (tm.np + 1 + 7) / 8 * 8;
+        nseg_total += tm.nseg;
+        memcpy(trec.data() + (size_t)k * REC_BYTES + REC_META, &tm, sizeof(TileMeta));
       }
     }
     // ---- camera -> partial rows, ascending super-tile order ------------------------------------------------
@@ -303,9 +348,17 @@ struct HostStructure {
     row_out.resize(nrows);
     for (int32_t i = 0; i < nrows; i++) row_out[cam_row_list[i]] = i;
     // ---- packed per-super-tile records -----------------------------------------------------------------------
+    // Work-queue order of k_pcg_solve = record order: longest super-tiles first, so that the items the atomic counter hands
+    // out last are the short ones and the CTAs finish the product phase close together (longest-processing-time rule).
     strec.assign((size_t)nst * STREC_BYTES, 0);
-    for (int32_t s2 = 0; s2 < nst; s2++) {
-      int32_t *r = reinterpret_cast<int32_t *>(strec.data() + (size_t)s2 * STREC_BYTES);
+    std::vector<int32_t> order((size_t)nst);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+      return st_tile[a + 1] - st_tile[a] > st_tile[b + 1] - st_tile[b];
+    });
+    for (int32_t j = 0; j < nst; j++) {
+      const int32_t s2 = order[j];
+      int32_t *r = reinterpret_cast<int32_t *>(strec.data() + (size_t)j * STREC_BYTES);
       r[0] = st_tile[s2]; r[1] = st_tile[s2 + 1] - st_tile[s2];
       r[2] = st_row[s2];  r[3] = st_row[s2 + 1] - st_row[s2];
       for (int32_t q = 0; q < r[3]; q++) {
@@ -315,16 +368,31 @@ struct HostStructure {
     }
     // ---- camera-major view: counting sort by camera (stable: ascending point order inside a camera) ---------
     {
+      // stable counting sort by camera on the host threads: per-thread histograms over contiguous observation ranges
+      const int nth = host_threads(m / 65536 + 1);
+      std::vector<std::vector<int32_t>> hist((size_t)nth, std::vector<int32_t>((size_t)nc, 0));
+      parallel_indexed(m, nth, [&](int i, int64_t ob, int64_t oe) {
+        int32_t *h = hist[i].data();
+        for (int64_t o = ob; o < oe; o++) h[cam_idx[o]]++;
+      });
       std::vector<int32_t> cptr((size_t)nc + 1, 0);
-      for (int64_t o = 0; o < m; o++) cptr[cam_idx[o] + 1]++;
-      for (int64_t c = 0; c < nc; c++) cptr[c + 1] += cptr[c];
-      cm_slot.resize(m); cm_pt.resize(m);
-      std::vector<int32_t> fillc(cptr.begin(), cptr.end() - 1);
-      for (int64_t o = 0; o < m; o++) {
-        const int32_t pos = fillc[cam_idx[o]]++;
-        cm_slot[pos] = slot_of_obs[o];
-        cm_pt[pos] = pt_idx[o];
+      {
+        int32_t run = 0;
+        for (int64_t c = 0; c < nc; c++) {
+          cptr[c] = run;
+          for (int i = 0; i < nth; i++) { const int32_t v = hist[i][c]; hist[i][c] = run; run += v; }
+        }
+        cptr[nc] = run;
       }
+      cm_slot.resize(m); cm_pt.resize(m);
+      parallel_indexed(m, nth, [&](int i, int64_t ob, int64_t oe) {
+        int32_t *h = hist[i].data();
+        for (int64_t o = ob; o < oe; o++) {
+          const int32_t pos = h[cam_idx[o]]++;
+          cm_slot[pos] = slot_of_obs[o];
+          cm_pt[pos] = pt_idx[o];
+        }
+      });
       ch_ptr.assign(1, 0);
       cam_ch_ptr.assign((size_t)nc + 1, 0);
       for (int64_t c = 0; c < nc; c++) {
