@@ -360,11 +360,18 @@ k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
   uint32_t om_n = ds.ometa[slot_n];
   int c_n = ds.tile_cam[slot_n];
   typename V2<T>::type ov_n = obs[slot_n];
-  for (int tile = ds.st_tile[st]; tile < tile_end; tile++) {
-    // the record is consumed after the first barrier below; its load overlaps the arithmetic
-    if (t < REC_BYTES / 16)
-      reinterpret_cast<uint4 *>(rec)[t] = __ldg(reinterpret_cast<const uint4 *>(ds.trec + (int64_t)tile * REC_BYTES) + t);
-    const TileMeta tm = ds.tmeta[tile];
+  // ... and so are the tile's packed record (one 16-byte piece per thread, stored to shared memory at the top of its tile)
+  // and its meta words.  (ncu source page of the version that loaded them at the top of the tile: the shared-memory
+  // store of the record waited for its own global load - 6 % of all stall samples - and the first use of the tile meta
+  // another 4 %, profiles/r2_ncu_stages_summary.txt.)
+  const int tile_first = ds.st_tile[st];
+  uint4 rec_n = make_uint4(0u, 0u, 0u, 0u);
+  if (t < REC_BYTES / 16) rec_n = __ldg(reinterpret_cast<const uint4 *>(ds.trec + (int64_t)tile_first * REC_BYTES) + t);
+  TileMeta tm_n = ds.tmeta[tile_first];
+  for (int tile = tile_first; tile < tile_end; tile++) {
+    // the record is consumed after the first barrier below
+    if (t < REC_BYTES / 16) reinterpret_cast<uint4 *>(rec)[t] = rec_n;
+    const TileMeta tm = tm_n;
     const int64_t slot = (int64_t)tile * TILE + t;
     const uint32_t om = om_n;
     const int c = c_n;
@@ -373,6 +380,8 @@ k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
       om_n = ds.ometa[slot + TILE];
       c_n = ds.tile_cam[slot + TILE];
       ov_n = obs[slot + TILE];
+      if (t < REC_BYTES / 16) rec_n = __ldg(reinterpret_cast<const uint4 *>(ds.trec + (int64_t)(tile + 1) * REC_BYTES) + t);
+      tm_n = ds.tmeta[tile + 1];
     }
     const int rank = (int)((om >> 8) & 0xffu), ptl = (int)(om & 0xffu);
     const bool active = t < tm.n;
@@ -426,7 +435,20 @@ k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
       row[7] = -(B.Jp[2] * B.r[0] + B.Jp[3] * B.r[1]);
       row[8] = -(B.Jp[4] * B.r[0] + B.Jp[5] * B.r[1]);
     }
+    // per-tile cost partial with the reduction tree of block_sum (k_cost_tiles): chi2 of linearize == chi2 of cost, bit
+    // for bit.  Its warp partials ride on the barriers the staging needs anyway.
+    {
+      double cw = cost;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cw += __shfl_down_sync(0xffffffffu, cw, o);
+      if ((t & 31) == 0) shd[t >> 5] = cw;
+    }
     __syncthreads();
+    if (t == 0) {
+      double tot = 0.0;
+      for (int i = 0; i < TILE / 32; i++) tot += shd[i];
+      cost_part[tile] = tot;
+    }
     {
       // one thread per (point, component triple)
       const uint16_t *pt = reinterpret_cast<const uint16_t *>(rec + REC_PT);
@@ -476,12 +498,8 @@ k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
         ar[2] += a2;
       }
     }
-    // per-tile cost partial with the same reduction tree as k_cost_tiles: chi2 of linearize == chi2 of cost, bit for bit
-    // (its two barriers also separate this tile's staging reads from the next tile's record and staging writes)
-    const double tot = block_sum<double>(cost, shd);
-    if (t == 0) cost_part[tile] = tot;
+    __syncthreads(); // this tile's staging reads are done: the next tile may write its record and staging
   }
-  __syncthreads();
   for (int i = t; i < nslots * 18; i += TILE) part[(int64_t)ds.row_out[row0 + i / 18] * 18 + i % 18] = acc[i];
 }
 
@@ -1370,6 +1388,25 @@ template <typename T> __device__ __forceinline__ T grid_total(const T *vals, int
   T acc = T(0);
   for (int i = threadIdx.x; i < n; i += blockDim.x) acc += __ldcg(vals + i);
   return block_sum<T>(acc, sh);
+}
+
+// two such sums with one pair of CTA barriers (sh: 64 values)
+template <typename T>
+__device__ __forceinline__ void grid_total2(const T *a, int na, const T *b, int nb, T *sh /*[64]*/, T &ta, T &tb) {
+  T va = T(0), vb = T(0);
+  for (int i = threadIdx.x; i < na; i += blockDim.x) va += __ldcg(a + i);
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) vb += __ldcg(b + i);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    va += __shfl_down_sync(0xffffffffu, va, o);
+    vb += __shfl_down_sync(0xffffffffu, vb, o);
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) { sh[w] = va; sh[32 + w] = vb; }
+  __syncthreads();
+  ta = T(0); tb = T(0);
+  for (int i = 0; i < nw; i++) { ta += sh[i]; tb += sh[32 + i]; }
 }
 
 // xs = D_c x (for the back-substitution) ; also camera update + rho partial (ops/update.hpp:9-31,

@@ -35,8 +35,8 @@ constexpr int SOLVE_STAMPS = 8; // per iteration: P start, before A, after A, ex
 
 template <typename T, typename S> struct SolveSmem {
   using SM = SchurSmem2<T, S>;
-  static constexpr int RED_OFF = SM::TOTAL;                       // T[32] reduction scratch
-  static constexpr int WP_OFF = RED_OFF + 32 * (int)sizeof(double); // T[SOLVE_WARPS]
+  static constexpr int RED_OFF = SM::TOTAL;                       // T[64] reduction scratch
+  static constexpr int WP_OFF = RED_OFF + 64 * (int)sizeof(double); // T[SOLVE_WARPS]
   static constexpr int CTL_OFF = WP_OFF + SOLVE_WARPS * (int)sizeof(double); // int[8]
   static constexpr int NREC = 3;                                  // ring of per-super-tile records (current, next, next-next)
   static constexpr int REC_OFF = CTL_OFF + 64;
@@ -352,17 +352,14 @@ k_pcg_solve(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *_
           for (int q = 0; q < pp.nranks; q++) ll_store(ll_slot(pp, q, pp.rank, epoch), (long long)c * 9 + k9, raw, e32);
       }
     }
-    T dot = grid_total<T>(st_dot, nst, red);
-    const T pdp = grid_total<T>(cta_red, G, red);
+    T dot, pdp;
+    grid_total2<T>(st_dot, nst, cta_red, G, red, dot, pdp);
     if (multi) {
       // p.(S p) needs one scalar per rank: CTA 0 sends this rank's (the word after the vector), everybody reads all of them
-      if (blockIdx.x == 0 && threadIdx.x < pp.nranks)
+      if (blockIdx.x == 0 && threadIdx.x < pp.nranks) // (to this rank's own slot too: ll_sum reads all nranks slots)
         ll_store(ll_slot(pp, threadIdx.x, pp.rank, epoch), (long long)9 * Nc, dot, e32);
       if (timing && leader) timing[k * SOLVE_STAMPS + 6] = global_timer_ns();
-      T tot = T(0);
-      for (int q = 0; q < pp.nranks; q++) // rank order: bit-identical on every rank
-        tot += q == pp.rank ? dot : ll_load<T>(pp, ll_slot(pp, pp.rank, q, epoch), (long long)9 * Nc, e32);
-      dot = tot;
+      dot = ll_sum<T>(pp, epoch, (long long)9 * Nc, e32); // rank order: bit-identical on every rank
     }
     if (timing && leader) timing[k * SOLVE_STAMPS + 3] = global_timer_ns();
     const T denom = dot + pdp;
@@ -376,9 +373,8 @@ k_pcg_solve(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *_
       const T raw0 = multi ? T(0) : gather_raw(c);
       T rn = T(0);
       if (own) {
-        T raw = raw0;
-        if (multi) // the ranks' sums in rank order (this rank's own went through its own slot too)
-          for (int q = 0; q < pp.nranks; q++) raw += ll_load<T>(pp, ll_slot(pp, pp.rank, q, epoch), i, e32);
+        // multi-GPU: the ranks' sums in rank order (this rank's own went through its own slot too)
+        const T raw = multi ? ll_sum<T>(pp, epoch, i, e32) : raw0;
         const T pn = p_new[i];
         const T ap = raw + dterm[i] * pn;
         const T xo = x[i];

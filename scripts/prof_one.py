@@ -10,5 +10,6 @@ prec = sys.argv[2] if len(sys.argv) > 2 else "f64-f64"
 prob = synthetic.make_named(case)
 ctx = binding.Context(0)
 P = binding.problem_from_bal(ctx, prob, prec)
-traj, res = P.lm(iterations=3)
+iters = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+traj, res = P.lm(iterations=iters)
 print(traj)

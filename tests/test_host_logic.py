@@ -260,3 +260,36 @@ def test_roofline_byte_model_matches_the_survey_figures():
     product, k4 = mod.algorithmic_bytes(1778, 993923, 5001946, 221455, 19788, 8, 8)
     assert abs(k4 / 1e9 - 1.17) < 0.01                         # "1.17 GB implicit" per PCG iteration
     assert product < k4                                        # the stored-factor layout moves fewer bytes than the E blocks
+
+
+def test_bal_text_round_trip(tmp_path):
+    """BAL text format as parsed by examples/bal.cu:63-147: `<n_cams> <n_pts> <n_obs>`, one `cam pt x y` line per
+    observation, then 9 values per camera and 3 per point.  Written with 17 significant digits: the round trip is exact."""
+    prob = synthetic.make_bal(12, 300, 1100, seed=3, name="tiny")
+    path = str(tmp_path / "tiny.txt")
+    synthetic.write_bal_text(prob, path)
+    head = open(path).readline().split()
+    assert [int(v) for v in head] == [12, 300, 1100]
+    back = synthetic.read_bal_text(path)
+    assert np.array_equal(back.cam_idx, prob.cam_idx) and np.array_equal(back.pt_idx, prob.pt_idx)
+    assert np.array_equal(back.obs, prob.obs) and np.array_equal(back.cams, prob.cams) and np.array_equal(back.pts, prob.pts)
+    # the parsed problem builds the same structure (ids as in bal.cu: camera id = index, point id = n_cams + index)
+    a = binding.host_structure(prob.cam_idx, prob.pt_idx, prob.n_cams, prob.n_pts)
+    b = binding.host_structure(back.cam_idx, back.pt_idx, back.n_cams, back.n_pts)
+    for x, y in zip(a["hessian"], b["hessian"]):
+        assert np.array_equal(x, y)
+
+
+def test_long_tracks_are_rejected_loudly():
+    """A point observed by more cameras than a super-tile has accumulator rows (192) cannot be tiled: the structure build
+    says so instead of producing wrong sums (include/graphite_b200.h, gb_problem_desc.slot_cap)."""
+    nc, npts = 200, 3
+    cam = np.concatenate([np.arange(193), [0, 1], [2, 3]]).astype(np.int32)
+    pt = np.concatenate([np.zeros(193), [1, 1], [2, 2]]).astype(np.int32)
+    with pytest.raises(binding.GraphiteB200Error, match="more observations than"):
+        binding.host_structure(cam, pt, nc, npts)
+    # 192 is fine (the remaining cameras are observed by the other points, so no vertex is unused)
+    cam2 = np.concatenate([np.arange(192), np.arange(192, 200), [0, 1]]).astype(np.int32)
+    pt2 = np.concatenate([np.zeros(192), np.ones(8), [2, 2]]).astype(np.int32)
+    s = binding.host_structure(cam2, pt2, nc, npts)
+    assert s["info"]["max_track"] == 192
