@@ -256,7 +256,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": dict(workload_config(prob, "f64-f64", args.gpus), solver=args.solver),
+        "config": dict(workload_config(prob, "f64-f64", args.gpus, args.schur_mode), solver=args.solver),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{args.steps} LM iterations after {args.warmup} warm-up iterations of the same workload "
                                    f"(explicit Schur + PCG, OpenMP); pcg iterations per step {ks}"},
@@ -266,12 +266,13 @@ def run_reference(args):
     emit(line)
 
 
-def workload_config(prob, precision, n_gpus):
+def workload_config(prob, precision, n_gpus, schur_mode="auto"):
     nc, npts, m = prob.shape()
     return {"workload": f"{prob.name}: {nc} cams / {npts} pts / {m} obs, seed 0, {precision.upper()}, points eliminated, "
                         f"lambda0 1e-4, PCG 10 it / tol 1.0 / rejection 5.0, diagonal damping, Jacobi scaling",
             "cams": nc, "points": npts, "observations": m, "precision": precision,
-            "schur": "implicit (matrix-free)", "parallelism": f"points partitioned over {n_gpus} GPU(s), cameras replicated",
+            "schur": {"auto": "library rule (implicit at this size)", "implicit": "implicit (matrix-free)",
+                      "explicit": "explicit (stored S)"}[schur_mode], "parallelism": f"points partitioned over {n_gpus} GPU(s), cameras replicated",
             "l2": "no flush needed: each pass streams the 0.96 GB Jacobian store (FP64) which is larger than the 126 MB L2"}
 
 
@@ -285,6 +286,8 @@ def main():
     ap.add_argument("--precision", default="f64-f64")
     ap.add_argument("--solver", default="pcg-schur", choices=["pcg-schur", "pcg"],
                     help="pcg-schur: PCGSchurSolver (headline); pcg: the reference's full-system PCGSolver (its mixed-precision path)")
+    ap.add_argument("--schur-mode", default="auto", choices=["auto", "implicit", "explicit"],
+                    help="form of the Schur complement (gb_pcg_options.schur_mode): matrix-free, stored, or the library's rule")
     ap.add_argument("--super-tile-obs", type=int, default=0,
                     help="tuning: target observations per super-tile (gb_problem_desc.super_tile_observations), 0 = library default")
     ap.add_argument("--device-only", action="store_true",
@@ -355,13 +358,13 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    traj_w, res_w = P.lm(iterations=args.warmup, solver=args.solver)
+    traj_w, res_w = P.lm(iterations=args.warmup, solver=args.solver, schur_mode=args.schur_mode)
     barrier()
     sampler.mark(True)
     l0 = ctx.kernel_launches()
     t0 = time.perf_counter()
     traj, res = P.lm(iterations=args.steps, initial_damping=res_w["final_damping"], initial_nu=res_w["final_nu"],
-                     resume=True, profile_product=True, solver=args.solver)
+                     resume=True, profile_product=True, solver=args.solver, schur_mode=args.schur_mode)
     barrier()
     sampler.mark(False)
     wall = time.perf_counter() - t0
@@ -417,7 +420,7 @@ def main():
     if args.device_only:
         if rank == 0:
             emit({"tuning_only": True, "value": value, "ms_per_step": 1e3 * seconds / max(steps_done, 1), "n_gpus": world,
-                  "super_tile_obs": args.super_tile_obs, "structure": info, "parity": parity,
+                  "super_tile_obs": args.super_tile_obs, "schur_mode": args.schur_mode, "workload": args.workload, "structure": info, "parity": parity,
                   "stages_ms_per_step": {k[8:]: 1e3 * v / max(steps_done, 1) for k, v in res.items()
                                          if k.startswith("seconds_") and k != "seconds_total"},
                   "pcg_us_by_phase": [1e6 * v / n_prod for v in res["pcg_phase_seconds"]], "ms_product_phase": prod_ms,
@@ -431,7 +434,7 @@ def main():
         return
     # ---- e2e arm: every step copies its inputs from pinned host memory and reads the result back ----------
     P.set_vertices_raw(h_cams.data_ptr(), h_pts.data_ptr())
-    tw, rw = P.lm(iterations=args.warmup, solver=args.solver)
+    tw, rw = P.lm(iterations=args.warmup, solver=args.solver, schur_mode=args.schur_mode)
     # state after warm-up becomes the host-side state the steps start from
     P.get_vertices_raw(out_cams.data_ptr(), out_pts.data_ptr())
     mu, nu = rw["final_damping"], rw["final_nu"]
@@ -444,7 +447,7 @@ def main():
     for _ in range(args.steps):
         P.set_observations_raw(h_obs.data_ptr())                       # H2D
         P.set_vertices_raw(out_cams.data_ptr(), out_pts.data_ptr())    # H2D
-        tj, rj = P.lm(iterations=1, initial_damping=mu, initial_nu=nu, solver=args.solver)  # linearize + one LM iteration
+        tj, rj = P.lm(iterations=1, initial_damping=mu, initial_nu=nu, solver=args.solver, schur_mode=args.schur_mode)  # linearize + one LM iteration
         P.get_vertices_raw(out_cams.data_ptr(), out_pts.data_ptr())    # D2H (+ chi2 in rj)
         mu, nu = rj["final_damping"], rj["final_nu"]
         e2e_steps += 1
@@ -455,7 +458,7 @@ def main():
     # the same steps with the observation upload double-buffered on the library's copy stream: the batch of step k+1 is
     # copied (same bytes, inside the timed region) while step k computes; vertices stay in line (step k+1 needs step k's)
     P.set_vertices_raw(h_cams.data_ptr(), h_pts.data_ptr())
-    tw, rw = P.lm(iterations=args.warmup, solver=args.solver)
+    tw, rw = P.lm(iterations=args.warmup, solver=args.solver, schur_mode=args.schur_mode)
     P.get_vertices_raw(out_cams.data_ptr(), out_pts.data_ptr())
     mu, nu = rw["final_damping"], rw["final_nu"]
     P.stage_observations_async(h_obs.data_ptr(), 0)  # batch of step 0
@@ -467,7 +470,7 @@ def main():
         P.set_vertices_raw(out_cams.data_ptr(), out_pts.data_ptr())      # H2D (first: the step cannot start without them)
         P.stage_observations_async(h_obs.data_ptr(), (k + 1) % 2)        # H2D of the next step's batch, overlaps this step
         tj, rj = P.lm(iterations=1, initial_damping=mu, initial_nu=nu,   # linearize + one LM iteration; the linearisation
-                      defer_final_linearize=True, solver=args.solver)   # at the accepted point is the next step's first act
+                      defer_final_linearize=True, solver=args.solver, schur_mode=args.schur_mode)   # at the accepted point is the next step's first act
         P.get_vertices_raw(out_cams.data_ptr(), out_pts.data_ptr())      # D2H (+ chi2 in rj)
         mu, nu = rj["final_damping"], rj["final_nu"]
     barrier()
@@ -525,7 +528,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps_done, "warmup": args.warmup,
             "ms_per_step": 1e3 * seconds / max(steps_done, 1), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64" if tname == "f64" else "f32", "data": "synthetic",
-            "config": dict(workload_config(prob, args.precision, world), solver=args.solver),
+            "config": dict(workload_config(prob, args.precision, world, args.schur_mode), solver=args.solver),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "lm_roofline": lm_roofline,
             "cpu_baseline": cpu, "reference_gpu": ref_gpu, "parity": parity,
             "structure_seconds": structure_seconds,

@@ -39,11 +39,11 @@ class ProblemDesc(C.Structure):
 
 class PcgOptions(C.Structure):
     _fields_ = [("max_iterations", C.c_int64), ("tolerance", C.c_double), ("rejection_ratio", C.c_double),
-                ("solver", C.c_int32), ("reserved", C.c_int32)]
+                ("solver", C.c_int32), ("schur_mode", C.c_int32)]
 
 
 class SolveInfo(C.Structure):
-    _fields_ = [("pcg_iterations", C.c_int64), ("rz_final", C.c_double), ("stop_reason", C.c_int32), ("reserved", C.c_int32)]
+    _fields_ = [("pcg_iterations", C.c_int64), ("rz_final", C.c_double), ("stop_reason", C.c_int32), ("schur_mode", C.c_int32)]
 
 
 class LMOptions(C.Structure):
@@ -64,6 +64,7 @@ class LMResult(C.Structure):
 
 
 SOLVERS = {"pcg-schur": 0, "pcg": 1}  # names of examples/bal.cu --solver
+SCHUR_MODES = {"auto": 0, "implicit": 1, "explicit": 2}
 
 _lib = None
 
@@ -304,12 +305,13 @@ class Problem:
     def set_damping(self, mu: float, use_identity: bool = False):
         self.ctx.check(self.L.gb_set_damping(self.h, float(mu), int(use_identity)))
 
-    def solve(self, max_iterations=10, tolerance=1.0, rejection_ratio=5.0, want_delta=True, solver="pcg-schur"):
-        o = PcgOptions(max_iterations, tolerance, rejection_ratio, SOLVERS[solver], 0)
+    def solve(self, max_iterations=10, tolerance=1.0, rejection_ratio=5.0, want_delta=True, solver="pcg-schur", schur_mode="auto"):
+        o = PcgOptions(max_iterations, tolerance, rejection_ratio, SOLVERS[solver], SCHUR_MODES[schur_mode])
         info = SolveInfo()
         d = np.empty(self.dimH, dtype=self.T) if want_delta else None
         self.ctx.check(self.L.gb_solve(self.h, C.byref(o), _ptr(d) if want_delta else None, C.byref(info)))
-        return d, {"pcg_iterations": int(info.pcg_iterations), "rz_final": info.rz_final, "stop_reason": int(info.stop_reason)}
+        return d, {"pcg_iterations": int(info.pcg_iterations), "rz_final": info.rz_final, "stop_reason": int(info.stop_reason),
+                   "schur_mode": int(info.schur_mode)}
 
     def schur_rhs(self):
         return self._get(self.L.gb_get_schur_rhs, self.dimc, self.T)
@@ -349,9 +351,9 @@ class Problem:
 
     def lm(self, iterations=50, initial_damping=1e-4, pcg_iterations=10, pcg_tolerance=1.0, rejection_ratio=5.0,
            use_identity=False, verbose=False, resume=False, initial_nu=2.0, profile_product=False, solver="pcg-schur",
-           defer_final_linearize=False, early_stop=False):
+           defer_final_linearize=False, early_stop=False, schur_mode="auto"):
         o = LMOptions(initial_damping, iterations, int(use_identity), int(verbose),
-                      PcgOptions(pcg_iterations, pcg_tolerance, rejection_ratio, SOLVERS[solver], 0), None, int(resume),
+                      PcgOptions(pcg_iterations, pcg_tolerance, rejection_ratio, SOLVERS[solver], SCHUR_MODES[schur_mode]), None, int(resume),
                       int(profile_product), float(initial_nu), int(defer_final_linearize), int(early_stop))
         res = LMResult()
         traj = np.zeros((max(iterations, 1), 4))

@@ -16,6 +16,7 @@
 
 #include "kernels.cuh"
 #include "pcg_solve.cuh"
+#include "explicit_schur.cuh"
 #include "structure.hpp"
 
 // ---- NCCL, bound at run time (the library must load on boxes where only torch's bundled NCCL exists) ----
@@ -159,6 +160,13 @@ template <typename T, typename S> struct Problem : ProblemBase {
   unsigned int *work_counter = nullptr;
   unsigned long long *d_timing = nullptr, *h_timing = nullptr; // per-iteration phase stamps of CTA 0 (profile_product)
   int timing_cap = 0;
+  // explicit Schur complement as a solve mode (explicit_schur.cuh): structure and buffers are built on first use
+  HostStructure::ExplicitSchur xs_host;
+  ExplicitDev xs_dev{};
+  bool xs_ready = false;
+  T *xs_vals = nullptr, *xs_p = nullptr, *xs_red = nullptr;
+  int xs_grid = 0;
+  int last_schur_mode = GB_SCHUR_IMPLICIT;
   // NCCL fallback (no peer memory between the ranks): product + reduction + all-reduce + cooperative update per iteration
   int64_t pcg_guess = 1 << 20; // iterations the previous solve executed
   T *diagB = nullptr, *gc = nullptr, *scale = nullptr /*[9Nc+3Np]*/, *b = nullptr /*[9Nc+3Np]*/;
@@ -897,6 +905,61 @@ template <typename T, typename S> struct Problem : ProblemBase {
     return GB_OK;
   }
 
+  int ensure_explicit() {
+    if (xs_ready) return GB_OK;
+    hs.explicit_schur(xs_host);
+    const HostStructure::ExplicitSchur &E = xs_host;
+    xs_dev.Nc = ts.Nc;
+    xs_dev.nblocks = (int32_t)E.rowidx.size();
+    GB_TRY(upload(xs_dev.tptr, E.tptr));
+    GB_TRY(upload(xs_dev.tup_a, E.tup_a)); GB_TRY(upload(xs_dev.tup_b, E.tup_b)); GB_TRY(upload(xs_dev.tup_p, E.tup_p));
+    GB_TRY(upload(xs_dev.blk_row, E.blk_row)); GB_TRY(upload(xs_dev.blk_col, E.blk_col));
+    GB_TRY(upload(xs_dev.diag_block, E.diag_block));
+    GB_TRY(upload(xs_dev.row_ptr, E.row_ptr)); GB_TRY(upload(xs_dev.row_ent, E.row_ent)); GB_TRY(upload(xs_dev.row_other, E.row_other));
+    GB_TRY(dalloc(xs_vals, (size_t)xs_dev.nblocks * 81));
+    GB_TRY(dalloc(xs_p, (size_t)dimc));
+    int per_sm = 0, sms = 0;
+    GB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_solve_explicit<T>, XS_THREADS, 0));
+    GB_CUDA(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    xs_grid = (int)std::min<int64_t>((int64_t)std::max(per_sm, 1) * sms, ts.Nc);
+    GB_TRY(dalloc(xs_red, 2 * (size_t)xs_grid));
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    xs_ready = true;
+    return GB_OK;
+  }
+  // S at the current linearisation and damping, blocks in the order of gb_schur_structure (needs enqueue_prepare: W, Sdiag)
+  int enqueue_schur_build() {
+    GB_TRY(ensure_explicit());
+    k_schur_build<T, S><<<(xs_dev.nblocks + 7) / 8, 256, 0, ctx->stream>>>(xs_dev, J, W, scale, Sdiag, xs_vals);
+    GB_LAUNCH(ctx);
+    return launch_check();
+  }
+  // Which form of the Schur complement a solve runs on.  GB_SCHUR_AUTO is the measured rule of DESIGN.md section 3
+  // (scripts/schur_crossover.py on one B200, FP64; gpurun_out/r2o_crossover.log): per solve
+  //     implicit  t = a_i + k (17.2 us + 43.9 us per million observations)
+  //     explicit  t = a_i + 0.05 ms + 0.55 ns per (point, camera pair) tuple + k (9.8 us + 0.435 us per thousand blocks of S)
+  // so the explicit form pays when the solve may run more than k* = build / saving-per-iteration PCG iterations: 11 / 24 /
+  // 53 / 84 iterations measured at the Ladybug / Trafalgar / Dubrovnik / Venice shapes.  With the reference's BAL protocol
+  // (10 iterations, examples/bal.cu:284-309) every BASELINE shape therefore runs matrix-free.  The number of blocks is
+  // bounded by min(Nc (Nc + 1) / 2, tuples + Nc) without building the structure.
+  double xs_kstar = -1.0;
+  int choose_schur_mode(const gb_pcg_options *o) {
+    if (o->schur_mode == GB_SCHUR_EXPLICIT || o->schur_mode == GB_SCHUR_IMPLICIT) return o->schur_mode;
+    if (xs_kstar < 0.0) {
+      double tuples = 0.0;
+      for (int32_t p = 0; p < hs.Np; p++) {
+        const double t = (double)(hs.pptr[p + 1] - hs.pptr[p]);
+        tuples += 0.5 * t * (t - 1.0);
+      }
+      const double nc = (double)hs.Nc, blocks = std::min(0.5 * nc * (nc + 1.0), tuples + nc);
+      const double scale_s = sizeof(S) == 8 ? 1.0 : 0.6; // FP32 Jacobians: the matrix-free pass is cheaper (measured 0.55-0.6)
+      const double build_us = 50.0 + 0.55e-3 * tuples;
+      const double saving_us = (17.2 + 43.9e-6 * (double)hs.M * scale_s) - (9.8 + 0.435e-3 * blocks);
+      xs_kstar = saving_us > 0.5 ? build_us / saving_us : 1e30;
+    }
+    return (double)o->max_iterations > xs_kstar ? GB_SCHUR_EXPLICIT : GB_SCHUR_IMPLICIT;
+  }
+
   int ensure_timing(int64_t max_iter) {
     const int need = (int)((max_iter + 1) * SOLVE_STAMPS);
     if (need > timing_cap) {
@@ -915,7 +978,22 @@ template <typename T, typename S> struct Problem : ProblemBase {
     cudaStream_t st = ctx->stream;
     const T tol = (T)o->tolerance, ratio = (T)o->rejection_ratio;
     const int max_iter = (int)o->max_iterations;
-    if (ctx->nranks == 1 || p2p_on) {
+    last_schur_mode = choose_schur_mode(o);
+    if (last_schur_mode == GB_SCHUR_EXPLICIT && (ctx->nranks == 1 || p2p_on)) {
+      GB_TRY(enqueue_schur_build());
+      const T *c_vals = xs_vals, *c_Minv = Minv, *c_bS = bS;
+      PcgState<T> *stp = pcg_state;
+      int multi = ctx->nranks > 1 ? 1 : 0;
+      T tol_ = tol, ratio_ = ratio;
+      int mi = max_iter;
+      void *args[] = {(void *)&xs_dev, (void *)&c_vals, (void *)&c_Minv, (void *)&c_bS, (void *)&x, (void *)&xbak, (void *)&r,
+                      (void *)&z, (void *)&xs_p, (void *)&Ap, (void *)&xs_red, (void *)&stp, (void *)&tol_, (void *)&ratio_,
+                      (void *)&mi, (void *)&pp, (void *)&multi};
+      GB_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)k_pcg_solve_explicit<T>, dim3(xs_grid), dim3(XS_THREADS), args, 0, st));
+      GB_LAUNCH(ctx);
+      GB_TRY(store_host(h_state, pcg_state, sizeof(PcgState<T>)));
+    } else if (ctx->nranks == 1 || p2p_on) {
+      last_schur_mode = GB_SCHUR_IMPLICIT;
       if (profiling) GB_TRY(ensure_timing(o->max_iterations));
       const S2 *c_J = J;
       const T *c_W = W, *c_scale = scale, *c_dterm = dterm, *c_Minv = Minv, *c_bS = bS;
@@ -934,6 +1012,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
       GB_TRY(store_host(h_state, pcg_state, sizeof(PcgState<T>)));
       if (profiling) GB_TRY(store_host(h_timing, d_timing, (size_t)(max_iter + 1) * SOLVE_STAMPS * sizeof(unsigned long long)));
     } else {
+      last_schur_mode = GB_SCHUR_IMPLICIT;
       GB_TRY(ensure_state_cap(o->max_iterations));
       const int gridc = (ts.Nc + PCG_CAMS - 1) / PCG_CAMS;
       k_pcg_init<T><<<gridc, 288, 0, st>>>(ts.Nc, bS, Minv, scale, x, r, z, pv, xs, rz_part);
@@ -1125,6 +1204,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_TRY(require(linearized, "gb_solve before gb_linearize"));
     GB_TRY(require(o && o->max_iterations >= 0 && o->max_iterations < (1 << 20), "bad PCG options"));
     GB_TRY(require(o->solver == GB_SOLVER_PCG_SCHUR || o->solver == GB_SOLVER_PCG_FULL, "unknown solver"));
+    GB_TRY(require(o->schur_mode >= GB_SCHUR_AUTO && o->schur_mode <= GB_SCHUR_EXPLICIT, "unknown schur_mode"));
     if (o->solver == GB_SOLVER_PCG_FULL) {
       GB_TRY(solve_full(o));
       if (delta_host) {
@@ -1148,7 +1228,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
       info->pcg_iterations = h_state->iter;
       info->rz_final = (double)h_state->rz;
       info->stop_reason = h_state->reason;
-      info->reserved = 0;
+      info->schur_mode = last_schur_mode;
     }
     return GB_OK;
   }
@@ -1170,7 +1250,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
       info->pcg_iterations = h_state->iter;
       info->rz_final = (double)h_state->rz;
       info->stop_reason = h_state->reason;
-      info->reserved = 0;
+      info->schur_mode = last_schur_mode;
     }
     return GB_OK;
   }
@@ -1202,7 +1282,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     solved = false; // xs was overwritten
     return GB_OK;
   }
-  // ---- explicit Schur complement: structure (host, cached) and values (export path) -------------------------------
+  // ---- explicit Schur complement: structure (host, cached) and values ------------------------------------------------
   std::vector<int64_t> s_colptr;
   std::vector<int32_t> s_rowidx;
   int schur_structure(int64_t *colptr, int64_t *rowidx, int64_t *nnz) override {
@@ -1216,25 +1296,8 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_TRY(require(linearized, "gb_schur_values before gb_linearize"));
     GB_TRY(require(ctx->nranks == 1, "gb_schur_values is single-rank only"));
     if (!prepared) GB_TRY(enqueue_prepare());
-    int64_t nnz = 0;
-    GB_TRY(schur_structure(nullptr, nullptr, &nnz));
-    cudaStream_t st = ctx->stream;
-    Scratch s_cp, s_ri, s_vals;
-    GB_CUDA(ctx, cudaMalloc(&s_cp.p, s_colptr.size() * sizeof(int64_t)));
-    GB_CUDA(ctx, cudaMalloc(&s_ri.p, s_rowidx.size() * sizeof(int32_t)));
-    GB_CUDA(ctx, cudaMalloc(&s_vals.p, (size_t)nnz * 81 * sizeof(T)));
-    int64_t *d_cp = s_cp.as<int64_t>();
-    int32_t *d_ri = s_ri.as<int32_t>();
-    T *vals = s_vals.as<T>();
-    GB_CUDA(ctx, cudaMemcpyAsync(d_cp, s_colptr.data(), s_colptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    GB_CUDA(ctx, cudaMemcpyAsync(d_ri, s_rowidx.data(), s_rowidx.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    GB_CUDA(ctx, cudaMemsetAsync(vals, 0, (size_t)nnz * 81 * sizeof(T), st));
-    k_schur_explicit<T, S><<<(ts.Np + 7) / 8, 256, 0, st>>>(ts, J, W, scale, d_cp, d_ri, vals);
-    GB_LAUNCH(ctx);
-    k_schur_explicit_diag<T><<<(ts.Nc * 81 + 255) / 256, 256, 0, st>>>(ts.Nc, Sdiag, d_cp, vals);
-    GB_LAUNCH(ctx);
-    GB_TRY(launch_check());
-    return d2h(out, vals, (size_t)nnz * 81 * sizeof(T));
+    GB_TRY(enqueue_schur_build());
+    return d2h(out, xs_vals, (size_t)xs_dev.nblocks * 81 * sizeof(T));
   }
   int try_step(double *new_chi2, double *rho_den) override {
     GB_TRY(require(solved || solved_full, "gb_try_step before gb_solve"));
@@ -1270,6 +1333,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_TRY(require(o && o->iterations >= 0, "bad LM options"));
     GB_TRY(require(o->pcg.solver == GB_SOLVER_PCG_SCHUR || o->pcg.solver == GB_SOLVER_PCG_FULL, "unknown solver"));
     GB_TRY(require(o->pcg.max_iterations >= 0 && o->pcg.max_iterations < (1 << 20), "bad PCG options"));
+    GB_TRY(require(o->pcg.schur_mode >= GB_SCHUR_AUTO && o->pcg.schur_mode <= GB_SCHUR_EXPLICIT, "unknown schur_mode"));
     const bool full = o->pcg.solver == GB_SOLVER_PCG_FULL;
     if (full) GB_TRY(full_buffers());
     cudaStream_t st = ctx->stream;

@@ -36,7 +36,7 @@
 //   k_copy                               restore after a rejected step
 // Other entry points: k_schur_product2 (one product per launch: exports, <FULL> for the full-system PCG solver, NCCL
 // fallback) + k_cam_reduce_spmv, k_pcg_init*, k_pcg_update (NCCL fallback), k_full_* (full-system PCG solver),
-// k_schur_explicit (explicit S export), k_hessian_export, k_scatter_slots, k_p2p_push / k_p2p_sum (generic exchange).
+// k_hessian_export, k_scatter_slots, k_p2p_push / k_p2p_sum (generic exchange).
 #pragma once
 #include <cfloat>
 #include <cstdint>
@@ -1632,70 +1632,6 @@ k_full_point_step(int64_t n3, const T *__restrict__ xp, const T *__restrict__ sc
   }
   const double tot = block_sum<double>(rho, shd);
   if (threadIdx.x == 0) rho_part[blockIdx.x] = tot;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Explicit Schur complement, off-diagonal blocks (export path; the solver itself is matrix-free):
-//   S_ij = - D_i (sum_p E_ip W_p E_jp^T) D_j   for cameras i < j that share points   (ops/schur.hpp:154-188)
-// One warp per point, lanes over (camera pair, block element); accumulation with atomics like the reference's.
-// The diagonal blocks come from the production path (k_cam_reduce_prepare: Sdiag).
-// ---------------------------------------------------------------------------------------------
-template <typename T, typename S>
-__global__ void __launch_bounds__(256)
-k_schur_explicit(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *__restrict__ W,
-                 const T *__restrict__ scale_c, const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
-                 T *__restrict__ values /*[nnz][81] column-major blocks*/) {
-  using S2 = typename V2<S>::type;
-  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (p >= ds.Np) return;
-  const int o0 = ds.pptr[p], t = ds.pptr[p + 1] - o0;
-  const int npairs = t * (t - 1) / 2;
-  const T *w = W + (int64_t)p * WST<T>::value;
-  const T w00 = w[0], w01 = w[1], w02 = w[2], w11 = w[3], w12 = w[4], w22 = w[5];
-  for (int item = lane; item < npairs * 81; item += 32) {
-    const int pr = item / 81, el = item - 81 * pr, r = el % 9, c = el / 9;
-    // pair index -> (a, b), a < b, row-wise enumeration
-    int a = 0, rem = pr;
-    while (rem >= t - 1 - a) { rem -= t - 1 - a; a++; }
-    const int b = a + 1 + rem;
-    const int ca = ds.cam_idx[o0 + a], cb = ds.cam_idx[o0 + b];
-    const int sa = ds.slot_of_obs[o0 + a], sb = ds.slot_of_obs[o0 + b];
-    const S2 *ja = J + ((int64_t)(sa >> 8) * NPLANES) * TILE + (sa & (TILE - 1));
-    const S2 *jb = J + ((int64_t)(sb >> 8) * NPLANES) * TILE + (sb & (TILE - 1));
-    T pa[6], pb[6];
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-      const S2 va = ja[(9 + j) * TILE], vb = jb[(9 + j) * TILE];
-      pa[2 * j] = (T)va.x; pa[2 * j + 1] = (T)va.y;
-      pb[2 * j] = (T)vb.x; pb[2 * j + 1] = (T)vb.y;
-    }
-    // q_v = W Jp_b^T e_v (v = 0, 1), N[u][v] = Jp_a[u] . q_v
-    const T q00 = w00 * pb[0] + w01 * pb[2] + w02 * pb[4], q01 = w01 * pb[0] + w11 * pb[2] + w12 * pb[4],
-            q02 = w02 * pb[0] + w12 * pb[2] + w22 * pb[4];
-    const T q10 = w00 * pb[1] + w01 * pb[3] + w02 * pb[5], q11 = w01 * pb[1] + w11 * pb[3] + w12 * pb[5],
-            q12 = w02 * pb[1] + w12 * pb[3] + w22 * pb[5];
-    const T n00 = pa[0] * q00 + pa[2] * q01 + pa[4] * q02, n01 = pa[0] * q10 + pa[2] * q11 + pa[4] * q12;
-    const T n10 = pa[1] * q00 + pa[3] * q01 + pa[5] * q02, n11 = pa[1] * q10 + pa[3] * q11 + pa[5] * q12;
-    const S2 var = ja[r * TILE], vbc = jb[c * TILE];
-    const T a0 = (T)var.x, a1 = (T)var.y, b0 = (T)vbc.x, b1 = (T)vbc.y;
-    const T val = a0 * (n00 * b0 + n01 * b1) + a1 * (n10 * b0 + n11 * b1);
-    // block (row ca, column cb): binary search of ca in column cb
-    int64_t lo = colptr[cb], hi = colptr[cb + 1] - 1;
-    while (lo < hi) {
-      const int64_t mid = (lo + hi) >> 1;
-      if (rowidx[mid] < ca) lo = mid + 1; else hi = mid;
-    }
-    atomicAdd(values + lo * 81 + r + 9 * c, -scale_c[ca * 9 + r] * scale_c[cb * 9 + c] * val);
-  }
-}
-// diagonal blocks of S (already damped) into their places
-template <typename T>
-__global__ void k_schur_explicit_diag(int Nc, const T *__restrict__ Sdiag, const int64_t *__restrict__ colptr,
-                                      T *__restrict__ values) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= Nc * 81) return;
-  const int c = i / 81, e = i - 81 * c;
-  values[(colptr[c + 1] - 1) * 81 + e] = Sdiag[i]; // the diagonal block is the last of its column (rows ascending)
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -448,6 +448,73 @@ struct HostStructure {
     }
   }
 
+  // Execution structure of the EXPLICIT Schur complement (SchurComplement::build_structure / setup_schur_multiplication,
+  // schur.hpp:397-585, where the reference emits one MulOp per (point, camera pair) and scatters with atomics).  Here the
+  // (point, pair) tuples are sorted ONCE by the block they contribute to, so that one warp owns a block and sums its
+  // tuples in a fixed order (no atomics), and the symmetric matrix gets a row view for the product S p:
+  //   tptr[b] .. tptr[b+1]   tuples (slot of the row camera's observation, slot of the column camera's, point) of
+  //                          off-diagonal block b (blocks in the order of schur_structure; diagonal blocks have none)
+  //   row_ptr[c] ..          entries of block row c of the full symmetric matrix: block index << 1 | transposed, and
+  //                          the camera whose part of p the block multiplies; the diagonal block is not listed
+  struct ExplicitSchur {
+    std::vector<int64_t> colptr;
+    std::vector<int32_t> rowidx;
+    std::vector<int32_t> diag_block;           // [Nc] index of block (c, c)
+    std::vector<int64_t> tptr;                 // [nblocks + 1]
+    std::vector<int32_t> tup_a, tup_b, tup_p;  // [ntuples]
+    std::vector<int32_t> blk_row, blk_col;     // [nblocks] cameras of the block
+    std::vector<int32_t> row_ptr, row_ent, row_other;
+    int64_t ntuples = 0;
+  };
+  void explicit_schur(ExplicitSchur &E) const {
+    schur_structure(E.colptr, E.rowidx);
+    const int64_t nb = (int64_t)E.rowidx.size();
+    E.diag_block.resize((size_t)Nc);
+    E.blk_row.resize((size_t)nb); E.blk_col.resize((size_t)nb);
+    for (int32_t c = 0; c < Nc; c++) {
+      E.diag_block[c] = (int32_t)(E.colptr[c + 1] - 1); // rows ascending: the diagonal block is the last of its column
+      for (int64_t k = E.colptr[c]; k < E.colptr[c + 1]; k++) { E.blk_row[k] = E.rowidx[k]; E.blk_col[k] = c; }
+    }
+    auto find_block = [&](int32_t row, int32_t col) -> int64_t { // row < col
+      const int32_t *lo = E.rowidx.data() + E.colptr[col], *hi = E.rowidx.data() + E.colptr[col + 1];
+      return (int64_t)(std::lower_bound(lo, hi, row) - E.rowidx.data());
+    };
+    // count, prefix, fill (points ascending, pairs in (a, b) order inside a point: a fixed summation order per block)
+    E.tptr.assign((size_t)nb + 1, 0);
+    for (int32_t p = 0; p < Np; p++)
+      for (int32_t a = pptr[p]; a < pptr[p + 1]; a++)
+        for (int32_t b = a + 1; b < pptr[p + 1]; b++) E.tptr[find_block(cam_idx[a], cam_idx[b]) + 1]++;
+    for (int64_t k = 0; k < nb; k++) E.tptr[k + 1] += E.tptr[k];
+    E.ntuples = E.tptr[nb];
+    E.tup_a.resize((size_t)E.ntuples); E.tup_b.resize((size_t)E.ntuples); E.tup_p.resize((size_t)E.ntuples);
+    std::vector<int64_t> fill(E.tptr.begin(), E.tptr.end() - 1);
+    for (int32_t p = 0; p < Np; p++)
+      for (int32_t a = pptr[p]; a < pptr[p + 1]; a++)
+        for (int32_t b = a + 1; b < pptr[p + 1]; b++) {
+          const int64_t pos = fill[find_block(cam_idx[a], cam_idx[b])]++;
+          E.tup_a[pos] = slot_of_obs[a]; E.tup_b[pos] = slot_of_obs[b]; E.tup_p[pos] = p;
+        }
+    // row view of the symmetric matrix without the diagonal: for camera c the blocks (r, c), r < c, transposed, then the
+    // blocks (c, j), j > c, as stored
+    E.row_ptr.assign((size_t)Nc + 1, 0);
+    for (int64_t k = 0; k < nb; k++)
+      if (E.blk_row[k] != E.blk_col[k]) { E.row_ptr[E.blk_row[k] + 1]++; E.row_ptr[E.blk_col[k] + 1]++; }
+    for (int32_t c = 0; c < Nc; c++) E.row_ptr[c + 1] += E.row_ptr[c];
+    E.row_ent.resize((size_t)E.row_ptr[Nc]); E.row_other.resize((size_t)E.row_ptr[Nc]);
+    std::vector<int32_t> rf(E.row_ptr.begin(), E.row_ptr.end() - 1);
+    for (int32_t c = 0; c < Nc; c++) // column c, rows r < c: entry of row c (transposed) -> ascending r
+      for (int64_t k = E.colptr[c]; k < E.colptr[c + 1] - 1; k++) {
+        const int32_t q = rf[c]++;
+        E.row_ent[q] = (int32_t)(k << 1) | 1; E.row_other[q] = E.rowidx[k];
+      }
+    for (int32_t c = 0; c < Nc; c++) // column c, rows r < c: entry of row r (as stored) -> ascending c
+      for (int64_t k = E.colptr[c]; k < E.colptr[c + 1] - 1; k++) {
+        const int32_t r = E.rowidx[k];
+        const int32_t q = rf[r]++;
+        E.row_ent[q] = (int32_t)(k << 1); E.row_other[q] = c;
+      }
+  }
+
   // Upper block-CSC of the Hessian in the reference's order (hessian.hpp:59-84, 270-278; csc_utils.hpp:16-50).
   void hessian_structure(int64_t *colptr, int64_t *rowidx, int64_t *offsets) const {
     int64_t k = 0, off = 0;

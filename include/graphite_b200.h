@@ -188,19 +188,27 @@ int gb_hessian_values(gb_problem *p, void *values_host);
  *                        matrix-free PCG on the full camera + point system, the reference's mixed-precision path */
 typedef enum { GB_SOLVER_PCG_SCHUR = 0, GB_SOLVER_PCG_FULL = 1 } gb_solver;
 
+/* Form of the Schur complement the PCG runs on (GB_SOLVER_PCG_SCHUR):
+ *   GB_SCHUR_IMPLICIT  matrix-free (B - E W E^T) p per iteration: one streaming pass over the Jacobians
+ *   GB_SCHUR_EXPLICIT  S built once per solve (the reference's form, schur.hpp:227-235, ops/schur.hpp:154-188), then a
+ *                      block-sparse S p per iteration (schur.hpp:347-393)
+ *   GB_SCHUR_AUTO      chosen per problem size and iteration count by the measured rule of DESIGN.md section 3
+ * All three give the same iterates up to rounding. */
+typedef enum { GB_SCHUR_AUTO = 0, GB_SCHUR_IMPLICIT = 1, GB_SCHUR_EXPLICIT = 2 } gb_schur_mode;
+
 typedef struct {
   int64_t max_iterations;  /* PCGSchurSolver / PCGSolver ctor (pcg_schur.hpp:42-45, pcg.hpp:40-45); bal default 10 */
   double tolerance;        /* 1.0 */
   double rejection_ratio;  /* 5.0 */
   int32_t solver;          /* gb_solver */
-  int32_t reserved;
+  int32_t schur_mode;      /* gb_schur_mode */
 } gb_pcg_options;
 
 typedef struct {
   int64_t pcg_iterations;  /* executed */
   double rz_final;
   int32_t stop_reason;     /* 0 max_iter, 1 converged, 2 rejected iterate, 3 rz==0, 4 bad denominator */
-  int32_t reserved;
+  int32_t schur_mode;      /* the form that ran: GB_SCHUR_IMPLICIT or GB_SCHUR_EXPLICIT */
 } gb_solve_info;
 
 /* Replaces: Solver::set_damping_factor (Hessian::apply_damping, hessian.hpp:136-176). */
@@ -227,7 +235,7 @@ int gb_schur_multiply(gb_problem *p, const void *x_host, void *y_host);
 int gb_schur_structure(gb_problem *p, int64_t *colptr, int64_t *rowidx, int64_t *nnz_blocks);
 /* Replaces: SchurComplement::update_values + get_values with an EXPLICIT S (schur.hpp:227-235, ops/schur.hpp:154-188)
  * at the current damping: values [nnz_blocks][81], column-major 9x9 blocks in the order of gb_schur_structure (element
- * type T).  Export for consumers of the reduced system (direct solvers, parity); the PCG itself stays matrix-free. */
+ * type T).  The same deterministic build the explicit solve mode runs on (one warp per block, tuples in a fixed order). */
 int gb_schur_values(gb_problem *p, void *values_host);
 
 /* Replaces: backup_parameters + apply_update + compute_error + chi2 + compute_rho

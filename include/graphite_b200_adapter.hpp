@@ -121,7 +121,7 @@ public:
     opt.tolerance = (double)tol;
     opt.rejection_ratio = (double)rejection_ratio;
     opt.solver = GB_SOLVER_PCG_SCHUR;
-    opt.reserved = 0;
+    opt.schur_mode = GB_SCHUR_AUTO;
     if (gb_context_create(device, &ctx) != GB_OK) ctx = nullptr;
   }
   ~B200SchurSolver() override {

@@ -15,6 +15,7 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 case = sys.argv[1] if len(sys.argv) > 1 else "trafalgar-257"
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+mode = sys.argv[3] if len(sys.argv) > 3 else "auto"  # schur_mode of the N-rank run (the single-GPU run is matrix-free)
 prob = synthetic.make_named(case)
 ctx = binding.Context(local)
 uid = [binding.Context.comm_unique_id() if rank == 0 else None]
@@ -22,7 +23,7 @@ dist.broadcast_object_list(uid, src=0)
 ctx.comm_init(world, rank, uid[0])
 part = partition_by_point(prob, world, rank)
 P = binding.problem_from_bal(ctx, part, "f64-f64", partition=True)
-traj, res = P.lm(iterations=iters)
+traj, res = P.lm(iterations=iters, schur_mode=mode)
 cams, pts = P.get_vertices()
 ok = True
 if rank == 0:

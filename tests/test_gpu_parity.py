@@ -179,6 +179,39 @@ def test_fp64_trajectory_matches_reference(ctx, case):
     P.close()
 
 
+@pytest.mark.parametrize("case", ["schur-fixture", "ladybug-49", "trafalgar-257", "dubrovnik-356"])
+def test_explicit_schur_mode_follows_the_same_trajectory(ctx, case):
+    """schur_mode = explicit (S built block by block without atomics, then a block-sparse S p per PCG iteration: the
+    reference's form, schur.hpp:227-235, 347-393) against the matrix-free mode and against the reference's own run:
+    per-iteration cost 1e-9, identical decisions and PCG iteration counts, final cost 1e-6."""
+    g = golden_json(f"{case}__pcg-schur__FP64-FP64.json")
+    t = np.array(g["table"])
+    prob = synthetic.schur_fixture() if case == "schur-fixture" else synthetic.make_named(case)
+    P = binding.problem_from_bal(ctx, prob, "f64-f64")
+    ti, _ = P.lm(iterations=len(t), schur_mode="implicit")
+    P.set_vertices(prob.cams, prob.pts)
+    te, _ = P.lm(iterations=len(t), schur_mode="explicit")
+    assert len(te) == len(ti) == len(t)
+    spread = ref_spread(case)
+    tol = np.full(len(t), 5e-9 if case == "schur-fixture" else 1e-9)
+    if spread is not None:
+        tol = np.maximum(tol, 10 * np.maximum.accumulate(spread))
+    assert np.all(np.abs(te[:, 1] - ti[:, 1]) / ti[:, 1] <= tol)
+    assert np.all(np.abs(te[:, 1] - t[:, 2]) / t[:, 2] <= tol)
+    assert np.array_equal(te[:, 0] == te[:, 1], t[:, 1] == t[:, 2]), "accept / reject decisions differ"
+    assert np.array_equal(te[:, 3], ti[:, 3]), "PCG iteration counts differ between the two forms"
+    assert abs(te[-1, 1] - g["final_chi2"]) <= 1e-6 * g["final_chi2"]
+    # one solve, both forms: the same step
+    P.set_vertices(prob.cams, prob.pts)
+    P.linearize()
+    P.set_damping(1e-3)
+    di, ii = P.solve(30, 1e-12, 5.0, schur_mode="implicit")
+    de, ie = P.solve(30, 1e-12, 5.0, schur_mode="explicit")
+    assert ie["schur_mode"] == 2 and ii["schur_mode"] == 1 and ie["pcg_iterations"] == ii["pcg_iterations"]
+    assert rel(de, di) <= 1e-9
+    P.close()
+
+
 def test_venice_final_cost_matches_reference(ctx):
     """BASELINE configs[3] at full size: final cost after 50 LM iterations to 1e-6."""
     g = golden_json("venice-1778__pcg-schur__FP64-FP64.json")
