@@ -26,7 +26,7 @@ SYMBOLS = [
     "gb_get_schur_diagonal", "gb_schur_multiply", "gb_schur_structure", "gb_schur_values", "gb_try_step", "gb_revert_step", "gb_lm", "gb_kernel_launches",
     "gb_time_stage", "gb_structure_create", "gb_structure_destroy", "gb_structure_info", "gb_structure_array",
     "gb_structure_hessian", "gb_structure_schur", "gb_context_create_on_stream", "gb_set_observations_device",
-    "gb_set_vertices_device", "gb_get_vertices_device", "gb_import_linearization", "gb_solve_device",
+    "gb_set_vertices_device", "gb_get_vertices_device", "gb_import_linearization", "gb_solve_device", "gb_schur_csc",
 ]
 
 
@@ -63,7 +63,7 @@ class LMResult(C.Structure):
                 ("reserved", C.c_int32), ("pcg_phase_seconds", C.c_double * 6)]
 
 
-SOLVERS = {"pcg-schur": 0, "pcg": 1}  # names of examples/bal.cu --solver
+SOLVERS = {"pcg-schur": 0, "pcg": 1, "direct-schur": 2}  # names of examples/bal.cu --solver (eigen-schur / cudss-schur: direct)
 SCHUR_MODES = {"auto": 0, "implicit": 1, "explicit": 2}
 
 _lib = None
@@ -112,6 +112,7 @@ def load_library():
     L.gb_schur_multiply.argtypes = [vp, vp, vp]
     L.gb_schur_structure.argtypes = [vp, vp, vp, C.POINTER(C.c_int64)]
     L.gb_schur_values.argtypes = [vp, vp]
+    L.gb_schur_csc.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_int64)]
     L.gb_try_step.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.gb_revert_step.argtypes = [vp]
     L.gb_lm.argtypes = [vp, C.POINTER(LMOptions), C.POINTER(LMResult), vp]
@@ -340,6 +341,16 @@ class Problem:
         v = np.empty(len(ri) * 81, dtype=self.T)
         self.ctx.check(self.L.gb_schur_values(self.h, _ptr(v)))
         return v.reshape(len(ri), 9, 9).transpose(0, 2, 1)
+
+    def schur_csc(self):
+        """S as the reference's scalar upper CSC (csc_utils.hpp:73-193): (pointers, indices, values)."""
+        n = C.c_int64()
+        self.ctx.check(self.L.gb_schur_csc(self.h, None, None, None, C.byref(n)))
+        ptr = np.empty(9 * self.n_cams + 1, dtype=np.int32)
+        idx = np.empty(n.value, dtype=np.int32)
+        val = np.empty(n.value, dtype=self.T)
+        self.ctx.check(self.L.gb_schur_csc(self.h, _ptr(ptr), _ptr(idx), _ptr(val), C.byref(n)))
+        return ptr, idx, val
 
     def try_step(self):
         a, b = C.c_double(), C.c_double()

@@ -17,6 +17,7 @@
 #include "kernels.cuh"
 #include "pcg_solve.cuh"
 #include "explicit_schur.cuh"
+#include "direct_schur.cuh"
 #include "structure.hpp"
 
 // ---- NCCL, bound at run time (the library must load on boxes where only torch's bundled NCCL exists) ----
@@ -128,6 +129,7 @@ struct ProblemBase {
   virtual int schur_multiply(const void *, void *) = 0;
   virtual int schur_structure(int64_t *, int64_t *, int64_t *) = 0;
   virtual int schur_values(void *) = 0;
+  virtual int schur_csc(int32_t *, int32_t *, void *, int64_t *) = 0;
   virtual int try_step(double *, double *) = 0;
   virtual int revert_step() = 0;
   virtual int lm(const gb_lm_options *, gb_lm_result *, double *) = 0;
@@ -167,6 +169,10 @@ template <typename T, typename S> struct Problem : ProblemBase {
   T *xs_vals = nullptr, *xs_p = nullptr, *xs_red = nullptr;
   int xs_grid = 0;
   int last_schur_mode = GB_SCHUR_IMPLICIT;
+  // direct solve of the reduced system (direct_schur.cuh)
+  T *dn_A = nullptr;
+  int *dn_fail = nullptr;
+  int dn_grid = 0;
   // NCCL fallback (no peer memory between the ranks): product + reduction + all-reduce + cooperative update per iteration
   int64_t pcg_guess = 1 << 20; // iterations the previous solve executed
   T *diagB = nullptr, *gc = nullptr, *scale = nullptr /*[9Nc+3Np]*/, *b = nullptr /*[9Nc+3Np]*/;
@@ -960,6 +966,45 @@ template <typename T, typename S> struct Problem : ProblemBase {
     return (double)o->max_iterations > xs_kstar ? GB_SCHUR_EXPLICIT : GB_SCHUR_IMPLICIT;
   }
 
+  // EigenSchurLDLTSolver::solve (eigen_schur.hpp:72-108) on the device: S (explicit blocks) -> dense -> Cholesky -> x_c
+  int enqueue_direct(const gb_pcg_options *o) {
+    cudaStream_t st = ctx->stream;
+    GB_TRY(require(ctx->nranks == 1, "the direct Schur solver is single-rank"));
+    const int n = (int)dimc;
+    if (dimc > 20000) return ctx->fail(GB_ERR_UNSUPPORTED, "direct Schur solve: 9 n_cams = %ld > 20000 (dense factorisation)", (long)dimc);
+    GB_TRY(enqueue_schur_build());
+    if (!dn_A) {
+      GB_TRY(dalloc(dn_A, (size_t)n * n));
+      GB_TRY(dalloc(dn_fail, 1));
+      int per_sm = 0, sms = 0;
+      GB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cholesky<T>, CH_THREADS, 0));
+      GB_CUDA(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+      dn_grid = std::max(1, std::min(per_sm, 2)) * sms;
+    }
+    GB_CUDA(ctx, cudaMemsetAsync(dn_A, 0, (size_t)n * n * sizeof(T), st));
+    GB_CUDA(ctx, cudaMemsetAsync(dn_fail, 0, sizeof(int), st));
+    k_dense_from_blocks<T><<<(xs_dev.nblocks + 7) / 8, 256, 0, st>>>(ts.Nc, xs_dev.nblocks, xs_dev.blk_row, xs_dev.blk_col, xs_vals, dn_A);
+    GB_LAUNCH(ctx);
+    {
+      int nn = n;
+      void *args[] = {(void *)&nn, (void *)&dn_A, (void *)&dn_fail};
+      GB_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)k_cholesky<T>, dim3(dn_grid), dim3(CH_THREADS), args, 0, st));
+      GB_LAUNCH(ctx);
+    }
+    k_cholesky_solve<T><<<1, 1024, 0, st>>>(n, dn_A, bS, x, dn_fail);
+    GB_LAUNCH(ctx);
+    k_direct_state<T><<<1, 1, 0, st>>>(pcg_state, dn_fail);
+    GB_LAUNCH(ctx);
+    GB_TRY(store_host(h_state, pcg_state, sizeof(PcgState<T>)));
+    GB_TRY(launch_check());
+    last_pcg = *o;
+    last_schur_mode = GB_SCHUR_EXPLICIT;
+    solved = true;
+    solved_full = false;
+    stepped = false;
+    return GB_OK;
+  }
+
   int ensure_timing(int64_t max_iter) {
     const int need = (int)((max_iter + 1) * SOLVE_STAMPS);
     if (need > timing_cap) {
@@ -1203,7 +1248,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
   int solve(const gb_pcg_options *o, void *delta_host, gb_solve_info *info) override {
     GB_TRY(require(linearized, "gb_solve before gb_linearize"));
     GB_TRY(require(o && o->max_iterations >= 0 && o->max_iterations < (1 << 20), "bad PCG options"));
-    GB_TRY(require(o->solver == GB_SOLVER_PCG_SCHUR || o->solver == GB_SOLVER_PCG_FULL, "unknown solver"));
+    GB_TRY(require(o->solver >= GB_SOLVER_PCG_SCHUR && o->solver <= GB_SOLVER_DIRECT_SCHUR, "unknown solver"));
     GB_TRY(require(o->schur_mode >= GB_SCHUR_AUTO && o->schur_mode <= GB_SCHUR_EXPLICIT, "unknown schur_mode"));
     if (o->solver == GB_SOLVER_PCG_FULL) {
       GB_TRY(solve_full(o));
@@ -1216,7 +1261,8 @@ template <typename T, typename S> struct Problem : ProblemBase {
       return GB_OK;
     }
     GB_TRY(enqueue_prepare());
-    GB_TRY(enqueue_pcg(o));
+    if (o->solver == GB_SOLVER_DIRECT_SCHUR) GB_TRY(enqueue_direct(o));
+    else GB_TRY(enqueue_pcg(o));
     if (delta_host) {
       GB_TRY(enqueue_step(false));
       GB_TRY(d2h(delta_host, delta, dimH * sizeof(T)));
@@ -1299,6 +1345,43 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_TRY(enqueue_schur_build());
     return d2h(out, xs_vals, (size_t)xs_dev.nblocks * 81 * sizeof(T));
   }
+  // scalar upper CSC of S in the reference's layout (csc_utils.hpp:73-193): host-side conversion of the block values
+  int schur_csc(int32_t *ptr, int32_t *idx, void *vals_out, int64_t *nnz_out) override {
+    int64_t nb = 0;
+    GB_TRY(schur_structure(nullptr, nullptr, &nb));
+    const int64_t n = 9 * (int64_t)hs.Nc;
+    // column 9 j + c holds, for every block (i, j) of block column j (rows ascending), rows 9 i + r with 9 i + r <= 9 j + c
+    int64_t nnz = 0;
+    for (int64_t j = 0; j < hs.Nc; j++) {
+      const int64_t off = s_colptr[j + 1] - s_colptr[j] - 1; // blocks above the diagonal one
+      nnz += 9 * (9 * off) + 45;
+    }
+    if (nnz_out) *nnz_out = nnz;
+    if (nnz >= (int64_t(1) << 31)) return ctx->fail(GB_ERR_UNSUPPORTED, "scalar CSC of S needs 64-bit indices");
+    std::vector<T> blocks;
+    if (vals_out) {
+      blocks.resize((size_t)nb * 81);
+      GB_TRY(schur_values(blocks.data()));
+    }
+    if (!ptr && !idx && !vals_out) return GB_OK;
+    T *vo = (T *)vals_out;
+    int64_t w = 0;
+    for (int64_t j = 0; j < hs.Nc; j++)
+      for (int c = 0; c < 9; c++) {
+        const int64_t col = 9 * j + c;
+        if (ptr) ptr[col] = (int32_t)w;
+        for (int64_t k = s_colptr[j]; k < s_colptr[j + 1]; k++) {
+          const int64_t i = s_rowidx[k];
+          for (int r = 0; r < 9 && 9 * i + r <= col; r++) {
+            if (idx) idx[w] = (int32_t)(9 * i + r);
+            if (vo) vo[w] = blocks[(size_t)k * 81 + r + 9 * c]; // column-major 9x9 block
+            w++;
+          }
+        }
+      }
+    if (ptr) ptr[n] = (int32_t)w;
+    return GB_OK;
+  }
   int try_step(double *new_chi2, double *rho_den) override {
     GB_TRY(require(solved || solved_full, "gb_try_step before gb_solve"));
     if (solved_full) GB_TRY(enqueue_step_full(true));
@@ -1331,10 +1414,10 @@ template <typename T, typename S> struct Problem : ProblemBase {
   int lm(const gb_lm_options *o, gb_lm_result *res_out, double *traj) override {
     GB_TRY(require(have_obs && have_vertices, "gb_lm needs observations and vertices"));
     GB_TRY(require(o && o->iterations >= 0, "bad LM options"));
-    GB_TRY(require(o->pcg.solver == GB_SOLVER_PCG_SCHUR || o->pcg.solver == GB_SOLVER_PCG_FULL, "unknown solver"));
+    GB_TRY(require(o->pcg.solver >= GB_SOLVER_PCG_SCHUR && o->pcg.solver <= GB_SOLVER_DIRECT_SCHUR, "unknown solver"));
     GB_TRY(require(o->pcg.max_iterations >= 0 && o->pcg.max_iterations < (1 << 20), "bad PCG options"));
     GB_TRY(require(o->pcg.schur_mode >= GB_SCHUR_AUTO && o->pcg.schur_mode <= GB_SCHUR_EXPLICIT, "unknown schur_mode"));
-    const bool full = o->pcg.solver == GB_SOLVER_PCG_FULL;
+    const bool full = o->pcg.solver == GB_SOLVER_PCG_FULL, direct = o->pcg.solver == GB_SOLVER_DIRECT_SCHUR;
     if (full) GB_TRY(full_buffers());
     cudaStream_t st = ctx->stream;
     gb_lm_result R{};
@@ -1371,6 +1454,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
       if (!full) GB_TRY(enqueue_prepare());
       GB_CUDA(ctx, cudaEventRecord(ev[1], st));
       if (full) GB_TRY(solve_full(&o->pcg));
+      else if (direct) GB_TRY(enqueue_direct(&o->pcg));
       else GB_TRY(enqueue_pcg(&o->pcg));
       GB_CUDA(ctx, cudaEventRecord(ev[2], st));
       if (full) GB_TRY(enqueue_step_full(true));
@@ -1385,8 +1469,11 @@ template <typename T, typename S> struct Problem : ProblemBase {
       cudaEventElapsedTime(&ms, ev[2], ev[3]); acc[3] += ms;
       cudaEventElapsedTime(&ms, ev[3], ev[4]); acc[4] += ms;
       T new_chi2 = (T)h_scalars[0];
-      const bool solve_ok = true; // PCGSchurSolver::solve always returns true (pcg_schur.hpp:167)
-      const T denom = (T)(h_scalars[1] + h_scalars[2]) + (T)1.0e-3;
+      // PCGSchurSolver::solve always returns true (pcg_schur.hpp:167); the direct solver reports a failed factorisation
+      // (eigen_schur.hpp:79-82), which the loop turns into a rejected step (levenberg_marquardt.hpp:181-187, :19-47)
+      const bool solve_ok = !(direct && h_state->reason == 6);
+      if (!solve_ok) new_chi2 = std::numeric_limits<T>::max();
+      const T denom = solve_ok ? (T)(h_scalars[1] + h_scalars[2]) + (T)1.0e-3 : T(1);
       const T rho = (chi2 - new_chi2) / denom;
       const int64_t k_exec = full ? full_info.pcg_iterations : h_state->iter;
       if (!full) pcg_guess = k_exec;
@@ -1755,6 +1842,7 @@ int gb_get_schur_diagonal(gb_problem *p, void *b) { GB_P(p); return p->impl->get
 int gb_schur_multiply(gb_problem *p, const void *x, void *y) { GB_P(p); return p->impl->schur_multiply(x, y); }
 int gb_schur_structure(gb_problem *p, int64_t *cp, int64_t *ri, int64_t *nnz) { GB_P(p); return p->impl->schur_structure(cp, ri, nnz); }
 int gb_schur_values(gb_problem *p, void *v) { GB_P(p); if (!v) return GB_ERR_INVALID; return p->impl->schur_values(v); }
+int gb_schur_csc(gb_problem *p, int32_t *ptr, int32_t *idx, void *v, int64_t *nnz) { GB_P(p); return p->impl->schur_csc(ptr, idx, v, nnz); }
 int gb_try_step(gb_problem *p, double *c, double *r) { GB_P(p); return p->impl->try_step(c, r); }
 int gb_revert_step(gb_problem *p) { GB_P(p); return p->impl->revert_step(); }
 int gb_lm(gb_problem *p, const gb_lm_options *o, gb_lm_result *r, double *t) { GB_P(p); return p->impl->lm(o, r, t); }

@@ -185,8 +185,13 @@ int gb_hessian_values(gb_problem *p, void *values_host);
 /* Linear solver behind Solver<T,S> (solver/solver.hpp:16-24):
  *   GB_SOLVER_PCG_SCHUR  PCGSchurSolver + BlockJacobiSchurPreconditioner (solver/pcg_schur.hpp) — points eliminated
  *   GB_SOLVER_PCG_FULL   PCGSolver + BlockJacobiPreconditioner (solver/pcg.hpp:61-232, preconditioner/block_jacobi.hpp):
- *                        matrix-free PCG on the full camera + point system, the reference's mixed-precision path */
-typedef enum { GB_SOLVER_PCG_SCHUR = 0, GB_SOLVER_PCG_FULL = 1 } gb_solver;
+ *                        matrix-free PCG on the full camera + point system, the reference's mixed-precision path
+ *   GB_SOLVER_DIRECT_SCHUR  EigenSchurLDLTSolver / cudssSchurSolver (solver/eigen_schur.hpp:52-108, solver/cudss_schur.hpp):
+ *                        the explicit S factorised - here a dense blocked Cholesky ON THE GPU (S is SPD after damping)
+ *                        instead of the reference's host-side SimplicialLDLT - then the same back-substitution; gives the
+ *                        exact LM step.  Single rank, 9 n_cams <= 20000.  A factorisation failure makes the solve report
+ *                        stop_reason 6 and the LM loop reject the step, as the reference does (eigen_schur.hpp:79-82). */
+typedef enum { GB_SOLVER_PCG_SCHUR = 0, GB_SOLVER_PCG_FULL = 1, GB_SOLVER_DIRECT_SCHUR = 2 } gb_solver;
 
 /* Form of the Schur complement the PCG runs on (GB_SOLVER_PCG_SCHUR):
  *   GB_SCHUR_IMPLICIT  matrix-free (B - E W E^T) p per iteration: one streaming pass over the Jacobians
@@ -207,7 +212,8 @@ typedef struct {
 typedef struct {
   int64_t pcg_iterations;  /* executed */
   double rz_final;
-  int32_t stop_reason;     /* 0 max_iter, 1 converged, 2 rejected iterate, 3 rz==0, 4 bad denominator */
+  int32_t stop_reason;     /* 0 max_iter, 1 converged, 2 rejected iterate, 3 rz==0, 4 bad denominator; direct solver: 5 solved,
+                            * 6 factorisation failed (solve_ok = false) */
   int32_t schur_mode;      /* the form that ran: GB_SCHUR_IMPLICIT or GB_SCHUR_EXPLICIT */
 } gb_solve_info;
 
@@ -237,6 +243,12 @@ int gb_schur_structure(gb_problem *p, int64_t *colptr, int64_t *rowidx, int64_t 
  * at the current damping: values [nnz_blocks][81], column-major 9x9 blocks in the order of gb_schur_structure (element
  * type T).  The same deterministic build the explicit solve mode runs on (one warp per block, tuples in a fixed order). */
 int gb_schur_values(gb_problem *p, void *values_host);
+/* Replaces: SchurComplement::build_csc_structure + update_csc_values -> csc::build_scalar_csc_structure /
+ * update_scalar_csc_values (csc_utils.hpp:73-193): S as a SCALAR upper-triangular CSC matrix of dimension 9 n_cams, the
+ * interchange format the reference's direct solvers consume (solver/eigen_schur.hpp:52-108, solver/cudss_schur.hpp): per
+ * scalar column the rows of every block of its block column, ascending, cut at the diagonal.  pointers [9 n_cams + 1],
+ * indices / values [nnz] (values of element type T); any of them may be NULL (query nnz first). */
+int gb_schur_csc(gb_problem *p, int32_t *pointers, int32_t *indices, void *values_host, int64_t *nnz);
 
 /* Replaces: backup_parameters + apply_update + compute_error + chi2 + compute_rho
  * (levenberg_marquardt.hpp:174-185): applies the last solve's step, returns the new chi2 and the rho
