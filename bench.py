@@ -137,7 +137,7 @@ class ClockSampler:
                 "source": self.mode, "sampled": where}
 
 
-GOLDEN_PRECISION = {"f64-f64": "FP64-FP64", "f32-f32": "FP32-FP32", "f64-f32": "FP64-FP32"}
+GOLDEN_PRECISION = {"f64-f64": "FP64-FP64", "f32-f32": "FP32-FP32", "f64-f32": "FP64-FP32", "f64-bf16": "FP64-BF16"}
 
 
 def golden_parity(workload, precision, solver, chi2_end, accepted_vector):
@@ -325,7 +325,7 @@ def main():
         ctx.comm_init(world, rank, uid[0])
     tname, sname = args.precision.split("-")
     T = np.float64 if tname == "f64" else np.float32
-    sT, sS = (8 if tname == "f64" else 4), (8 if sname == "f64" else 4)
+    sT, sS = (8 if tname == "f64" else 4), {"f64": 8, "f32": 4, "bf16": 2}[sname]
     t_struct = time.perf_counter()
     P = binding.Problem(ctx, local.cam_idx, local.pt_idx, local.n_cams, local.n_pts, args.precision, partition=world > 1,
                         super_tile_observations=args.super_tile_obs)

@@ -14,8 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GRAPHITE_B200_LIB") or os.path.join(_HERE, "libgraphite_b200.so")  # env: A/B builds of the same ABI
 
 GB_F32, GB_F64 = 0, 1
-_DT = {"f32": GB_F32, "f64": GB_F64}
-_NP = {"f32": np.float32, "f64": np.float64}
+_DT = {"f32": GB_F32, "f64": GB_F64, "bf16": 2}
+_NP = {"f32": np.float32, "f64": np.float64, "bf16": np.uint16}  # (bf16: storage precision only, never exported)
 
 # every symbol include/graphite_b200.h declares
 SYMBOLS = [

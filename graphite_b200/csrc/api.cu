@@ -191,6 +191,13 @@ template <typename T, typename S> struct Problem : ProblemBase {
   bool camx_valid = false; // camx holds the precomputed camera-model terms of the current cameras
   bool have_obs = false, have_vertices = false, linearized = false, prepared = false, solved = false, stepped = false;
   bool scale_on = true;
+  // Low-precision Jacobian storage (S = bf16): the stored Jacobians are the reference's scaled, twice-rounded J~
+  // (k_linearize<RESCALE>), the algebra downstream runs with D = I, and only the parameter update uses the true Jacobi
+  // scales, kept in scale_true.
+  static constexpr bool prescaled = IsLowPrecision<S>::value;
+  T *scale_true = nullptr;
+  int alg_scale() const { return (scale_on && !prescaled) ? 1 : 0; }
+  const T *apply_scale() const { return prescaled ? scale_true : scale; }
   T mu = T(1e-4);
   int use_identity = 0;
   int ncamblocks = 0;
@@ -205,7 +212,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
   T *ext_r = nullptr, *ext_Jc = nullptr, *ext_Jp = nullptr;
   int32_t *d_slot_src = nullptr, *d_ci_caller = nullptr, *d_pi_caller = nullptr;
   const T2 *obs_caller = nullptr; // the observations in the caller's order as last uploaded
-  ExtFactor ex{nullptr, nullptr, nullptr, nullptr};
+  ExtFactor ex{nullptr, nullptr, nullptr, nullptr, nullptr};
   // loss and per-factor precision matrices (whitening in k_linearize / k_cost_tiles)
   T *Pu = nullptr;
   Robust rb{nullptr, 0, 0.0};
@@ -313,6 +320,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
       // the super-tile kernels keep their camera accumulator rows in (opt-in sized) dynamic shared memory
       GB_CUDA(ctx, cudaFuncSetAttribute(k_linearize<T, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_lin_bytes<T>()));
       GB_CUDA(ctx, cudaFuncSetAttribute(k_linearize<T, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_lin_bytes<T>()));
+      GB_CUDA(ctx, cudaFuncSetAttribute(k_linearize<T, S, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_lin_bytes<T>()));
       GB_CUDA(ctx, cudaFuncSetAttribute(k_schur_product2<T, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         SchurSmem2<T, S>::TOTAL));
       GB_CUDA(ctx, cudaFuncSetAttribute(k_schur_product2<T, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -332,6 +340,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_TRY(dalloc(diagB, 2 * dimc)); // diag(B) | g_c contiguous: one exchange for both on the multi-GPU path
     gc = diagB + dimc;
     GB_TRY(dalloc(scale, dimH)); GB_TRY(dalloc(b, dimH)); GB_TRY(dalloc(delta, dimH));
+    if (prescaled) GB_TRY(dalloc(scale_true, dimH));
     GB_TRY(dalloc(W, (size_t)WST<T>::value * Np + 8)); GB_TRY(dalloc(h, (size_t)HST * Np + 8));
     GB_TRY(dalloc(Sdiag, Nc * 81)); GB_TRY(dalloc(Minv, Nc * 81));
     GB_TRY(dalloc(bS, dimc)); GB_TRY(dalloc(dterm, dimc));
@@ -603,7 +612,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
       GB_TRY(ensure_caller_maps());
       scale_on = false;
       have_obs = have_vertices = true; // the caller owns both; nothing here evaluates factors
-      GB_TRY(enqueue_linearize(true, ExtFactor{rdev, jc, jp, d_slot_src}));
+      GB_TRY(enqueue_linearize(true, ExtFactor{rdev, jc, jp, d_slot_src, nullptr}));
       return GB_OK;
     }
   }
@@ -614,7 +623,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     if (!fn || ext_r) return GB_OK;
     GB_TRY(dalloc(ext_r, 2 * (size_t)hs.M)); GB_TRY(dalloc(ext_Jc, 18 * (size_t)hs.M)); GB_TRY(dalloc(ext_Jp, 6 * (size_t)hs.M));
     GB_TRY(ensure_caller_maps());
-    ex = ExtFactor{ext_r, ext_Jc, ext_Jp, d_slot_src};
+    ex = ExtFactor{ext_r, ext_Jc, ext_Jp, d_slot_src, nullptr};
     return GB_OK;
   }
   // run the caller's factor kernel at the current vertices (with_jacobians = false: residuals only)
@@ -689,8 +698,13 @@ template <typename T, typename S> struct Problem : ProblemBase {
   // need_cost = false: the caller does not read chi2 of this linearisation (the accepted-step path of the LM loop
   // already has it from the trial step), so its cross-rank sum is skipped
   // imported.r != nullptr: the caller's own linearisation (gb_import_linearization) instead of a factor evaluation
-  int enqueue_linearize(bool need_cost = true, ExtFactor imported = ExtFactor{nullptr, nullptr, nullptr, nullptr}) {
+  int enqueue_linearize(bool need_cost = true, ExtFactor imported = ExtFactor{nullptr, nullptr, nullptr, nullptr, nullptr}) {
     cudaStream_t st = ctx->stream;
+    const bool multi = ctx->nranks > 1;
+    if (prescaled) {
+      GB_TRY(require(!multi && !imported.r && !ext_fn && !rb.Pu && rb.loss_kind == 0,
+                     "bf16 Jacobian storage: single rank, built-in factor, default loss and identity precision only"));
+    }
     if (imported.r) {
       k_linearize<T, S, true><<<ts.nst, TILE, smem_lin_bytes<T>(), st>>>(ts, camx, pts, obs, J, res, Cg, part18, cost_part, rb, imported);
     } else if (ext_fn) {
@@ -702,21 +716,34 @@ template <typename T, typename S> struct Problem : ProblemBase {
       k_linearize<T, S, false><<<ts.nst, TILE, smem_lin_bytes<T>(), st>>>(ts, camx, pts, obs, J, res, Cg, part18, cost_part, rb, ex);
     }
     GB_LAUNCH(ctx);
-    const bool multi = ctx->nranks > 1;
-    k_cam_reduce_lin<T><<<ts.Nc, 288, 0, st>>>(ts, part18, diagB, gc, multi ? 0 : 1, scale_on ? 1 : 0, scale, b);
+    // pre-scaled storage: this first pass only yields the rounded Jacobians and, from them, the true Jacobi scales
+    const int son = prescaled ? (scale_on ? 1 : 0) : alg_scale();
+    k_cam_reduce_lin<T><<<ts.Nc, 288, 0, st>>>(ts, part18, diagB, gc, multi ? 0 : 1, son, scale, b);
     GB_LAUNCH(ctx);
     k_sum_partials<<<1, 1024, 0, st>>>(cost_part, ts.ntiles, scalars, 0);
     GB_LAUNCH(ctx);
     if (multi) GB_TRY(exchange_push<T>(diagB, 2 * (size_t)dimc));
     // point scales and b_p (mu-independent part of k_point_prepare); W/h are refreshed by prepare.  Purely local: on
     // the multi-GPU path it runs while the peers' diag(B) | g_c are in flight
-    k_point_prepare<T><<<(ts.Np + 255) / 256, 256, 0, st>>>(ts.Np, scale_on ? 1 : 0, mu, use_identity, Cg, scale + dimc,
+    k_point_prepare<T><<<(ts.Np + 255) / 256, 256, 0, st>>>(ts.Np, son, mu, use_identity, Cg, scale + dimc,
                                                            b + dimc, W, h, 1);
     GB_LAUNCH(ctx);
     if (multi) {
       GB_TRY(exchange_sum<T>(diagB, 2 * (size_t)dimc));
       if (need_cost) GB_TRY(exchange<double>(scalars, 1));
-      k_cam_finish_lin<T><<<(int)((dimc + 255) / 256), 256, 0, st>>>((int)dimc, scale_on ? 1 : 0, diagB, gc, scale, b);
+      k_cam_finish_lin<T><<<(int)((dimc + 255) / 256), 256, 0, st>>>((int)dimc, son, diagB, gc, scale, b);
+      GB_LAUNCH(ctx);
+    }
+    if (prescaled) {
+      // second pass (ops/linearize.hpp:140-180): J~ = (S)((T)J * s) in place, then the assembly from J~ with unit scales
+      k_copy<T><<<4 * 148, 256, 0, st>>>((int64_t)dimH, scale, scale_true);
+      GB_LAUNCH(ctx);
+      ExtFactor rs{nullptr, nullptr, nullptr, nullptr, scale_true};
+      k_linearize<T, S, false, true><<<ts.nst, TILE, smem_lin_bytes<T>(), st>>>(ts, camx, pts, obs, J, res, Cg, part18, cost_part, rb, rs);
+      GB_LAUNCH(ctx);
+      k_cam_reduce_lin<T><<<ts.Nc, 288, 0, st>>>(ts, part18, diagB, gc, 1, 0, scale, b);
+      GB_LAUNCH(ctx);
+      k_point_prepare<T><<<(ts.Np + 255) / 256, 256, 0, st>>>(ts.Np, 0, mu, use_identity, Cg, scale + dimc, b + dimc, W, h, 1);
       GB_LAUNCH(ctx);
     }
     GB_TRY(launch_check());
@@ -785,7 +812,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
       full_lin_valid = true;
       prepared = false; // part54 no longer holds the Schur sums
     }
-    k_point_prepare<T><<<(ts.Np + 255) / 256, 256, 0, st>>>(ts.Np, scale_on ? 1 : 0, mu, use_identity, Cg, scale + dimc,
+    k_point_prepare<T><<<(ts.Np + 255) / 256, 256, 0, st>>>(ts.Np, alg_scale(), mu, use_identity, Cg, scale + dimc,
                                                            b + dimc, W, h, 0);
     GB_LAUNCH(ctx);
     k_full_cam_blocks<T><<<ts.Nc, 288, 0, st>>>(ts, part54, mu, use_identity, scale, f_Bfull, f_MinvF);
@@ -846,13 +873,13 @@ template <typename T, typename S> struct Problem : ProblemBase {
   int enqueue_step_full(bool apply) {
     cudaStream_t st = ctx->stream;
     k_cam_step<T><<<ncamblocks, 256, 0, st>>>((int)dimc, f_x, scale, b, mu, xs, cams, cams_bak, delta, rho_part + ts.ntiles,
-                                              apply ? 1 : 0);
+                                              apply ? 1 : 0, apply_scale());
     GB_LAUNCH(ctx);
     if (apply) camx_valid = false;
     const int64_t n3 = 3 * (int64_t)ts.Np;
     const int nb = (int)((n3 + 255) / 256);
     k_full_point_step<T><<<nb, 256, 0, st>>>(n3, f_x + dimc, scale + dimc, b + dimc, mu, pts, pts_bak, delta + dimc, f_rho,
-                                             apply ? 1 : 0);
+                                             apply ? 1 : 0, apply_scale() + dimc);
     GB_LAUNCH(ctx);
     k_sum_partials<<<1, 1024, 0, st>>>(f_rho, nb, scalars, 1);
     GB_LAUNCH(ctx);
@@ -875,7 +902,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
   }
   int enqueue_prepare() {
     cudaStream_t st = ctx->stream;
-    k_point_prepare<T><<<(ts.Np + 255) / 256, 256, 0, st>>>(ts.Np, scale_on ? 1 : 0, mu, use_identity, Cg, scale + dimc,
+    k_point_prepare<T><<<(ts.Np + 255) / 256, 256, 0, st>>>(ts.Np, alg_scale(), mu, use_identity, Cg, scale + dimc,
                                                            b + dimc, W, h, 0);
     GB_LAUNCH(ctx);
     k_prepare_cams<T, S><<<ts.nchunks, PC_THREADS, 0, st>>>(ts, J, W, h, part54);
@@ -1106,11 +1133,11 @@ template <typename T, typename S> struct Problem : ProblemBase {
     cudaStream_t st = ctx->stream;
     // camera part: delta_c = x, xs = D x, rho, (apply) cams += D x
     k_cam_step<T><<<ncamblocks, 256, 0, st>>>((int)dimc, x, scale, b, mu, xs, cams, cams_bak, delta, rho_part + ts.ntiles,
-                                              apply ? 1 : 0);
+                                              apply ? 1 : 0, apply_scale());
     GB_LAUNCH(ctx);
     if (apply) camx_valid = false;
     k_backsubst_tiles<T, S><<<ts.ntiles, TILE, 0, st>>>(ts, J, W, xs, h, scale + dimc, b + dimc, mu, pts, pts_bak,
-                                                        delta + dimc, rho_part, apply ? 1 : 0);
+                                                        delta + dimc, rho_part, apply ? 1 : 0, apply_scale() + dimc);
     GB_LAUNCH(ctx);
     if (sums) {
       k_sum_partials<<<1, 1024, 0, st>>>(rho_part, ts.ntiles, scalars, 1);
@@ -1188,7 +1215,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
   }
   int get_scales(void *out) override {
     GB_TRY(require(linearized, "gb_get_scales before gb_linearize"));
-    return d2h(out, scale, dimH * sizeof(T));
+    return d2h(out, apply_scale(), dimH * sizeof(T));
   }
   int get_residuals(void *out) override {
     GB_TRY(require(linearized, "gb_get_residuals before gb_linearize"));
@@ -1225,6 +1252,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
   int hessian_values(void *out) override {
     GB_TRY(require(linearized, "gb_hessian_values before gb_linearize"));
     GB_TRY(require(ctx->nranks == 1, "gb_hessian_values is single-rank only"));
+    if (prescaled) return ctx->fail(GB_ERR_UNSUPPORTED, "gb_hessian_values: not offered for bf16 storage");
     const int64_t nv = 81 * (int64_t)hs.Nc + 27 * hs.M + 9 * (int64_t)hs.Np;
     Scratch s_vals, s_bacc;
     GB_CUDA(ctx, cudaMalloc(&s_vals.p, nv * sizeof(S)));
@@ -1681,6 +1709,7 @@ int gb_problem_create(gb_context *ctx, const gb_problem_desc *d, gb_problem **ou
   if (d->precision_T == GB_F64 && d->precision_S == GB_F64) impl = new gb::Problem<double, double>();
   else if (d->precision_T == GB_F32 && d->precision_S == GB_F32) impl = new gb::Problem<float, float>();
   else if (d->precision_T == GB_F64 && d->precision_S == GB_F32) impl = new gb::Problem<double, float>();
+  else if (d->precision_T == GB_F64 && d->precision_S == GB_BF16) impl = new gb::Problem<double, __nv_bfloat16>();
   else return ctx->fail(GB_ERR_UNSUPPORTED, "precision (T=%d,S=%d) not supported", d->precision_T, d->precision_S);
   impl->ctx = ctx;
   const std::string why = impl->hs.build(d->num_cameras, d->num_points, d->num_observations, d->camera_index,

@@ -41,6 +41,7 @@
 #include <cfloat>
 #include <cstdint>
 #include <cooperative_groups.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include "bal_math.cuh"
@@ -73,6 +74,13 @@ template <> struct V2<float> {
   using type = float2;
   static __device__ __forceinline__ type make(float a, float b) { return make_float2(a, b); }
 };
+// bf16 Jacobian storage (the reference's low-precision S, types.hpp:10-19; examples/bal.cu:186-236): 4 bytes per pair
+template <> struct V2<__nv_bfloat16> {
+  using type = __nv_bfloat162;
+  static __device__ __forceinline__ type make(__nv_bfloat16 a, __nv_bfloat16 b) { return __halves2bfloat162(a, b); }
+};
+template <typename S> struct IsLowPrecision { static constexpr bool value = false; };
+template <> struct IsLowPrecision<__nv_bfloat16> { static constexpr bool value = true; };
 
 struct DevStruct {
   int64_t M, Mstore;
@@ -290,6 +298,7 @@ struct Robust {
 struct ExtFactor {
   const void *r, *Jc, *Jp;    // [n_obs][2], [n_obs][18], [n_obs][6] of T
   const int32_t *slot_src;    // [Mstore], -1 in padding slots
+  const void *rescale;        // k_linearize<RESCALE>: Jacobi scales [9 Nc + 3 Np] of T the stored Jacobians are multiplied by
 };
 // returns chi2_f; whitens r (2), Jc (18), Jp (6) in place
 template <typename T, typename S>
@@ -333,7 +342,12 @@ __device__ __forceinline__ T whiten_factor(const Robust &rb, int64_t slot, T *r,
 //     compute_hessian_scalar_diagonal_kernel / compute_b_kernel (ops/error.hpp:252, ops/linearize.hpp:10,238,
 //     ops/chi2.hpp:32, ops/hessian.hpp:418)
 // ---------------------------------------------------------------------------------------------
-template <typename T, typename S, bool EXT>
+// RESCALE = true is the second pass of a low-precision (bf16) linearisation: the reference casts the Jacobians to S when
+// they are evaluated (ops/linearize.hpp:43-64), computes the Jacobi scales from those rounded values and then scales
+// them IN PLACE, rounding to S a second time (scale_jacobians_kernel, ops/linearize.hpp:140-180:
+// J = (S)((T)J * scale)).  The pass reads the stored (rounded, unscaled) Jacobians and residuals back, applies exactly
+// that second rounding, stores J~ and assembles from J~; every later kernel then works in the scaled space with D = I.
+template <typename T, typename S, bool EXT, bool RESCALE = false>
 __global__ void __launch_bounds__(TILE, LIN_MIN_BLOCKS)
 k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
             const typename V2<T>::type *__restrict__ obs, typename V2<S>::type *__restrict__ J,
@@ -388,7 +402,24 @@ k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
     BalObs<T> B;
     double cost = 0.0;
     if (active) {
-      if (EXT) {
+      if (RESCALE) {
+        const int p = tm.p0 + ptl;
+        load_J<T, S>(J, tile, t, B.Jc, B.Jp);
+        const typename V2<T>::type rv = res[slot];
+        B.r[0] = rv.x; B.r[1] = rv.y;
+        const T *sc = reinterpret_cast<const T *>(ex.rescale) + (int64_t)c * 9;
+        const T *sp = reinterpret_cast<const T *>(ex.rescale) + 9 * (int64_t)ds.Nc + 3 * (int64_t)p;
+#pragma unroll
+        for (int j = 0; j < 9; j++) {
+          B.Jc[2 * j] = (T)(S)(B.Jc[2 * j] * sc[j]);
+          B.Jc[2 * j + 1] = (T)(S)(B.Jc[2 * j + 1] * sc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          B.Jp[2 * j] = (T)(S)(B.Jp[2 * j] * sp[j]);
+          B.Jp[2 * j + 1] = (T)(S)(B.Jp[2 * j + 1] * sp[j]);
+        }
+      } else if (EXT) {
         // the caller's kernel has evaluated this factor: fetch its residual and Jacobians
         const int64_t u = ex.slot_src[slot];
         const T *er = reinterpret_cast<const T *>(ex.r) + 2 * u;
@@ -1043,7 +1074,8 @@ __global__ void __launch_bounds__(TILE)
 k_backsubst_tiles(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *__restrict__ W,
                   const T *__restrict__ xs, const T *__restrict__ h, const T *__restrict__ scale_p,
                   const T *__restrict__ b_p, T mu, T *__restrict__ pts, T *__restrict__ pts_bak,
-                  T *__restrict__ delta_p, double *__restrict__ rho_part /*[ntiles]*/, int apply) {
+                  T *__restrict__ delta_p, double *__restrict__ rho_part /*[ntiles]*/, int apply,
+                  const T *__restrict__ scale_apply /*scales of the update x += delta~ * s (= scale_p unless J is pre-scaled)*/) {
   __shared__ T sv3[TILE * 3];
   __shared__ double shd[32];
   const int tile = blockIdx.x, t = threadIdx.x;
@@ -1091,7 +1123,7 @@ k_backsubst_tiles(DevStruct ds, const typename V2<S>::type *__restrict__ J, cons
       if (apply) {
         const T old = pts[i];
         pts_bak[i] = old;
-        pts[i] = old + xt * s;
+        pts[i] = old + xt * scale_apply[i];
       }
     }
   }
@@ -1414,7 +1446,8 @@ __device__ __forceinline__ void grid_total2(const T *a, int na, const T *b, int 
 template <typename T>
 __global__ void k_cam_step(int n, const T *__restrict__ x, const T *__restrict__ scale_c, const T *__restrict__ b_c,
                            T mu, T *__restrict__ xs, T *__restrict__ cams, T *__restrict__ cams_bak,
-                           T *__restrict__ delta_c, double *__restrict__ rho_part, int apply) {
+                           T *__restrict__ delta_c, double *__restrict__ rho_part, int apply,
+                           const T *__restrict__ scale_apply) {
   __shared__ double shd[32];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double rho = 0.0;
@@ -1428,7 +1461,7 @@ __global__ void k_cam_step(int n, const T *__restrict__ x, const T *__restrict__
     if (apply) {
       const T old = cams[c * CAM_STRIDE + k];
       cams_bak[c * CAM_STRIDE + k] = old;
-      cams[c * CAM_STRIDE + k] = old + d;
+      cams[c * CAM_STRIDE + k] = old + xt * scale_apply[i];
     }
   }
   const double tot = block_sum<double>(rho, shd);
@@ -1616,7 +1649,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k_full_point_step(int64_t n3, const T *__restrict__ xp, const T *__restrict__ scale_p, const T *__restrict__ b_p, T mu,
                   T *__restrict__ pts, T *__restrict__ pts_bak, T *__restrict__ delta_p, double *__restrict__ rho_part,
-                  int apply) {
+                  int apply, const T *__restrict__ scale_apply) {
   __shared__ double shd[32];
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double rho = 0.0;
@@ -1627,7 +1660,7 @@ k_full_point_step(int64_t n3, const T *__restrict__ xp, const T *__restrict__ sc
     if (apply) {
       const T old = pts[i];
       pts_bak[i] = old;
-      pts[i] = old + xt * scale_p[i];
+      pts[i] = old + xt * scale_apply[i];
     }
   }
   const double tot = block_sum<double>(rho, shd);

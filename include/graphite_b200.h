@@ -37,7 +37,10 @@ typedef enum {
   GB_ERR_NO_DEVICE = -5
 } gb_status;
 
-typedef enum { GB_F32 = 0, GB_F64 = 1 } gb_dtype;
+/* GB_BF16: linear-system precision S only (stored Jacobians), with T = GB_F64 - the reference's low-precision mode
+ * (types.hpp:10-19, examples/bal.cu:186-236, `--precision FP64-BF16`): Jacobians are rounded to bf16 when they are
+ * evaluated and again after Jacobi scaling (ops/linearize.hpp:43-64, 140-180), every product accumulates in T. */
+typedef enum { GB_F32 = 0, GB_F64 = 1, GB_BF16 = 2 } gb_dtype;
 
 typedef struct gb_context gb_context;
 typedef struct gb_problem gb_problem;
@@ -59,7 +62,7 @@ int gb_comm_init(gb_context *ctx, int nranks, int rank, const void *id128);
 
 typedef struct {
   int32_t precision_T;       /* gb_dtype */
-  int32_t precision_S;       /* gb_dtype; (F64,F64), (F32,F32), (F64,F32) */
+  int32_t precision_S;       /* gb_dtype; (F64,F64), (F32,F32), (F64,F32), (F64,BF16) */
   int64_t num_cameras;       /* all cameras (replicated on every rank) */
   int64_t num_points;        /* points owned by this rank */
   int64_t num_observations;  /* observations of those points */

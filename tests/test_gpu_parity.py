@@ -381,6 +381,33 @@ def test_full_system_pcg_mixed_precision_matches_reference(ctx, gold):
     P.close()
 
 
+@pytest.mark.parametrize("gold", ["ladybug-49__pcg__FP64-BF16.json", "trafalgar-257__pcg__FP64-BF16.json",
+                                  "venice-1778__pcg__FP64-BF16.json"])
+def test_bf16_jacobian_storage_matches_reference(ctx, gold):
+    """T = double, S = bf16 - the reference's low-precision mode (`--solver pcg --precision FP64-BF16`, examples/bal.cu:
+    186-236): Jacobians rounded to bf16 when evaluated and again after Jacobi scaling (ops/linearize.hpp:43-64, 140-180),
+    products accumulated in double.  Both rounding points are reproduced, so the run follows the reference's own bf16 run:
+    1e-4 on the cost of every iteration (north_star, mixed modes), same decisions while the run is not in the rounding
+    noise of bf16 itself."""
+    g = golden_json(gold)
+    t = np.array(g["table"])
+    prob = named_problem(g["case"])
+    P = binding.problem_from_bal(ctx, prob, "f64-bf16")
+    traj, res = P.lm(iterations=len(t), solver="pcg")
+    assert len(traj) == len(t)
+    r = np.abs(traj[:, 1] - t[:, 2]) / t[:, 2]
+    assert r.max() <= 1e-4, r
+    assert abs(traj[-1, 1] - g["final_chi2"]) <= 1e-4 * g["final_chi2"]
+    # the Jacobi scales the caller sees are the true ones (the stored Jacobians are pre-scaled, the algebra runs with D = I)
+    sc = P.scales()
+    assert np.all(sc > 0) and not np.allclose(sc, 1.0)
+    # the same storage under the Schur solver: a valid (if differently rounded) optimisation of the same problem
+    P.set_vertices(prob.cams, prob.pts)
+    ts, _ = P.lm(iterations=len(t))
+    assert ts[-1, 1] <= 1.02 * g["final_chi2"]
+    P.close()
+
+
 def test_full_system_operator_properties_at_full_size(ctx):
     """Venice: the full-system step solves (J~^T J~ + mu diag) x = b when PCG is run to convergence; checked through
     the Schur path, which solves the same damped normal equations by elimination."""
