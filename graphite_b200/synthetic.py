@@ -235,3 +235,97 @@ def read_bal_text(path: str) -> BALProblem:
     cams = rest[: 9 * nc].reshape(nc, 9)
     pts = rest[9 * nc: 9 * nc + 3 * npts].reshape(npts, 3)
     return BALProblem(o[:, 0].astype(np.int32), o[:, 1].astype(np.int32), np.ascontiguousarray(o[:, 2:]), cams, pts, path)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# pose-graph fixture for the generic factor-graph path (6-dof poses [w, t], between factors 6/6/6, unary priors 6/6)
+# ---------------------------------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class PoseGraph:
+    ids: np.ndarray  # int64 [N] global vertex ids (descending: the block order is NOT the insertion order)
+    poses: np.ndarray  # float64 [N, 6] initial estimate
+    fixed: np.ndarray  # uint8 [N]
+    bt_idx: np.ndarray  # int32 [Mb, 2] (i, j) local pose indices
+    bt_meas: np.ndarray  # float64 [Mb, 6]
+    bt_P: np.ndarray  # float64 [Mb, 6, 6] SPD precision matrices
+    bt_active: np.ndarray  # uint8 [Mb] FactorDescriptor::set_active values (the level from which a factor is active)
+    pr_idx: np.ndarray  # int32 [Mp]
+    pr_meas: np.ndarray  # float64 [Mp, 6]
+    huber: float = 0.5  # HuberLoss delta on the between factors
+
+
+def _aa_to_R(w):
+    return _rodrigues(np.asarray(w, dtype=np.float64)[None, :])[0]
+
+
+def _R_to_aa(R):
+    c = (np.trace(R) - 1.0) / 2.0
+    th = np.arccos(np.clip(c, -1.0, 1.0))
+    if th < 1e-12:
+        return np.zeros(3)
+    return th / (2.0 * np.sin(th)) * np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+
+
+def pose_graph(n: int = 40, seed: int = 0) -> PoseGraph:
+    """Poses on a noisy helix, odometry edges i -> i+1, loop closures i -> i+5 / i+11, priors on every 8th pose.
+    Pose 0 is fixed (gauge), pose 3 is fixed as well; the last two between factors are switched off (one from level 1 on, one
+    never), so the activity masks matter.  Rational-pattern SPD precision matrices (exact in FP32 as well)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    k = np.arange(n)
+    gt = np.zeros((n, 6))
+    gt[:, 3] = 4.0 * np.cos(0.35 * k)
+    gt[:, 4] = 4.0 * np.sin(0.35 * k)
+    gt[:, 5] = 0.1 * k
+    gt[:, 0:3] = np.stack([0.05 * np.sin(0.2 * k), 0.04 * np.cos(0.3 * k), 0.35 * k * 0.1 + 0.02], axis=1)
+    edges = [(i, i + 1) for i in range(n - 1)] + [(i, i + 5) for i in range(0, n - 5, 3)] + [(i, i + 11) for i in range(0, n - 11, 7)]
+    bt_idx = np.array(edges, dtype=np.int32)
+    meas = np.zeros((len(edges), 6))
+    for e, (i, j) in enumerate(edges):
+        Ri, Rj = _aa_to_R(gt[i, :3]), _aa_to_R(gt[j, :3])
+        meas[e, :3] = _R_to_aa(Ri.T @ Rj) + rng.normal(0.0, 0.01, 3)
+        meas[e, 3:] = Ri.T @ (gt[j, 3:] - gt[i, 3:]) + rng.normal(0.0, 0.02, 3)
+    # a few gross outliers so that the Huber branch is taken
+    for e in range(7, len(edges), 13):
+        meas[e, 3:] += np.array([0.9, -0.7, 0.8])
+    P = np.zeros((len(edges), 6, 6))
+    for e in range(len(edges)):
+        dg = np.array([4.0 + (e * 3) % 5, 4.5 + (e * 5) % 3, 5.0 + (e * 7) % 4, 1.0 + ((e * 2) % 7) / 4.0, 1.25 + ((e * 3) % 5) / 4.0, 1.5 + (e % 3) / 2.0])
+        P[e] = np.diag(dg)
+        off = ((e * 5) % 9 - 4) / 16.0
+        P[e, 0, 3] = P[e, 3, 0] = off
+        P[e, 1, 4] = P[e, 4, 1] = -off / 2.0
+    active = np.zeros(len(edges), dtype=np.uint8)
+    # the switched-off factors are the LAST ones: the reference's chi2 kernel walks the first active_count factors instead of
+    # the active index list (ops/chi2.hpp:32-44 as launched by ops/chi2.hpp:46-66), so its cost is only meaningful when
+    # the inactive factors form a suffix of the factor array
+    active[-2] = 1  # only active from optimisation level 1 on
+    active[-1] = 0x7F  # never active below level 127 (FactorDescriptor::set_active keeps only the low 7 bits, factor.hpp:419-430)
+    pr_idx = np.arange(0, n, 8, dtype=np.int32)
+    pr_meas = gt[pr_idx] + rng.normal(0.0, 0.01, (len(pr_idx), 6))
+    init = gt + np.concatenate([rng.normal(0.0, 0.03, (n, 3)), rng.normal(0.0, 0.15, (n, 3))], axis=1)
+    fixed = np.zeros(n, dtype=np.uint8)
+    fixed[0] = fixed[3] = 1
+    init[0] = gt[0]
+    return PoseGraph(ids=(1000 - 7 * k).astype(np.int64), poses=init, fixed=fixed, bt_idx=bt_idx, bt_meas=meas, bt_P=P,
+                     bt_active=active, pr_idx=pr_idx, pr_meas=pr_meas)
+
+
+def pose_graph_hard() -> PoseGraph:
+    """The same graph started far from the optimum (1.2 rad / 5 units of noise): several LM steps are
+    rejected, so backup / revert and the damping schedule are exercised."""
+    pg = pose_graph(seed=3)
+    rng = np.random.Generator(np.random.PCG64(11))
+    n = len(pg.ids) - 1
+    pg.poses[1:] += np.concatenate([rng.normal(0, 1.2, (n, 3)), rng.normal(0, 5.0, (n, 3))], axis=1)
+    return pg
+
+
+def write_pose_graph(pg: PoseGraph, path: str) -> None:
+    """GPG1 binary (read by the pose-graph driver of the unmodified reference that generates the golden runs): int64 n, mb, mp | f64 huber | i64 ids[n] | f64 poses[6n] | i64 fixed[n] |
+    i64 bt_idx[2mb] | f64 bt_meas[6mb] | f64 bt_P[36mb] | i64 bt_active[mb] | i64 pr_idx[mp] | f64 pr_meas[6mp]."""
+    with open(path, "wb") as fh:
+        fh.write(struct.pack("<qqq", len(pg.ids), len(pg.bt_idx), len(pg.pr_idx)))
+        fh.write(struct.pack("<d", pg.huber))
+        for a, dt in ((pg.ids, np.int64), (pg.poses, np.float64), (pg.fixed, np.int64), (pg.bt_idx, np.int64), (pg.bt_meas, np.float64),
+                      (pg.bt_P, np.float64), (pg.bt_active, np.int64), (pg.pr_idx, np.int64), (pg.pr_meas, np.float64)):
+            fh.write(np.ascontiguousarray(a, dtype=dt).tobytes())

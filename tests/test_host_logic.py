@@ -13,9 +13,10 @@ from graphite_b200 import binding, synthetic
 from graphite_b200.distributed import partition_by_point, point_ranges
 
 
-def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "graphite_b200.h")).read()
+def declared_symbols(header="graphite_b200.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"typedef[^;]*\(\*gb_[a-z0-9_]+\)[^;]*;", "", text)  # callback typedefs are not entry points
     return sorted(set(re.findall(r"\b(gb_[a-z0-9_]+)\s*\(", text)))
 
 
@@ -27,6 +28,13 @@ def test_library_exports_every_declared_symbol(built):
         assert hasattr(L, n), f"libgraphite_b200.so does not export {n}"
     assert sorted(binding.SYMBOLS) == names, "binding.SYMBOLS must list exactly the header's entry points"
     assert L.gb_version() == 100
+    # the generic factor-graph ABI (include/graphite_b200_graph.h)
+    from graphite_b200 import graph
+    gnames = declared_symbols("graphite_b200_graph.h")
+    assert len(gnames) >= 20
+    for n in gnames:
+        assert hasattr(L, n), f"libgraphite_b200.so does not export {n}"
+    assert sorted(graph.SYMBOLS) == gnames, "graph.SYMBOLS must list exactly the header's entry points"
 
 
 def test_no_gpu_means_loud_failure(built):
@@ -235,9 +243,10 @@ def test_bench_reference_arm_contract(built):
 def test_header_is_plain_c(tmp_path):
     """The drop-in boundary is a C ABI: include/graphite_b200.h must compile as C99 (-pedantic) and as C++17."""
     src = tmp_path / "t.c"
-    src.write_text('#include "graphite_b200.h"\n'
+    src.write_text('#include "graphite_b200.h"\n#include "graphite_b200_graph.h"\n'
                    'int main(void) { gb_lm_options o = {0}; gb_pcg_options p = {10, 1.0, 5.0, GB_SOLVER_PCG_SCHUR, 0};\n'
-                   '  gb_factor_eval e = {0}; (void)o; (void)p; (void)e; return gb_version() == 0; }\n')
+                   '  gb_factor_eval e = {0}; gb_graph_eval g = {0}; gb_vertex_set_desc v = {0}; gb_factor_set_desc f = {0};\n'
+                   '  (void)o; (void)p; (void)e; (void)g; (void)v; (void)f; return gb_version() == 0; }\n')
     inc = os.path.join(ROOT, "include")
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)])
     subprocess.check_call(["g++", "-std=c++17", "-Wall", "-fsyntax-only", "-x", "c++", "-I", inc, str(src)])
