@@ -26,7 +26,7 @@ SYMBOLS = [
     "gb_get_schur_diagonal", "gb_schur_multiply", "gb_schur_structure", "gb_schur_values", "gb_try_step", "gb_revert_step", "gb_lm", "gb_kernel_launches",
     "gb_time_stage", "gb_structure_create", "gb_structure_destroy", "gb_structure_info", "gb_structure_array",
     "gb_structure_hessian", "gb_structure_schur", "gb_context_create_on_stream", "gb_set_observations_device",
-    "gb_set_vertices_device", "gb_get_vertices_device", "gb_import_linearization", "gb_solve_device", "gb_schur_csc",
+    "gb_set_vertices_device", "gb_get_vertices_device", "gb_import_linearization", "gb_solve_device", "gb_schur_csc", "gb_set_fixed",
 ]
 
 
@@ -99,6 +99,7 @@ def load_library():
     L.gb_get_vertices.argtypes = [vp, vp, vp]
     L.gb_set_factor.argtypes = [vp, vp, vp]
     L.gb_set_loss.argtypes = [vp, C.c_int, C.c_double]
+    L.gb_set_fixed.argtypes = [vp, vp, vp]
     L.gb_set_precision.argtypes = [vp, vp]
     L.gb_hessian_structure.argtypes = [vp, vp, vp, vp]
     L.gb_linearize.argtypes = [vp, C.POINTER(C.c_double)]
@@ -222,6 +223,14 @@ class Problem:
         """User-defined factor: fn_ptr = address of a `gb_factor_fn` (int), or None for the built-in BAL factor."""
         self.ctx.check(self.L.gb_set_factor(self.h, C.c_void_p(fn_ptr) if fn_ptr else None,
                                             C.c_void_p(user_ptr) if user_ptr else None))
+
+    def set_fixed(self, cameras_fixed=None, points_fixed=None):
+        """VertexDescriptor::set_fixed for cameras / points (uint8 masks, None = none fixed)."""
+        fc = None if cameras_fixed is None else np.ascontiguousarray(cameras_fixed, dtype=np.uint8)
+        fp = None if points_fixed is None else np.ascontiguousarray(points_fixed, dtype=np.uint8)
+        assert fc is None or fc.size == self.n_cams
+        assert fp is None or fp.size == self.n_pts
+        self.ctx.check(self.L.gb_set_fixed(self.h, None if fc is None else _ptr(fc), None if fp is None else _ptr(fp)))
 
     def set_loss(self, loss: str = "default", delta: float = 0.0):
         self.ctx.check(self.L.gb_set_loss(self.h, {"default": 0, "huber": 1}[loss], float(delta)))

@@ -45,6 +45,7 @@ struct ProblemBase {
   virtual int solve_device(const gb_pcg_options *, void *, gb_solve_info *) = 0;
   virtual int set_factor(gb_factor_fn, void *) = 0;
   virtual int set_loss(int, double) = 0;
+  virtual int set_fixed(const uint8_t *, const uint8_t *) = 0;
   virtual int set_precision(const void *) = 0;
   virtual int get_vertices(void *, void *) = 0;
   virtual int linearize(double *) = 0;
@@ -128,6 +129,9 @@ template <typename T, typename S> struct Problem : ProblemBase {
   // scales, kept in scale_true.
   static constexpr bool prescaled = IsLowPrecision<S>::value;
   T *scale_true = nullptr;
+  // fixed vertices (gb_set_fixed): device masks, null when nothing is fixed
+  unsigned char *fixed_c = nullptr, *fixed_p = nullptr;
+  bool any_fixed = false;
   int alg_scale() const { return (scale_on && !prescaled) ? 1 : 0; }
   const T *apply_scale() const { return prescaled ? scale_true : scale; }
   T mu = T(1e-4);
@@ -573,6 +577,29 @@ template <typename T, typename S> struct Problem : ProblemBase {
     if (rc != 0) return ctx->fail(GB_ERR_INVALID, "user-defined factor callback returned %d", rc);
     return launch_check();
   }
+  // Replaces VertexDescriptor::set_fixed (vertex.hpp:254-266): fixed cameras / points keep their slot in every vector
+  // (scale 0, gradient 0, step 0) instead of being left out of the Hessian ordering; every other unknown gets the same
+  // numbers as in the reference's reduced system.
+  int set_fixed(const uint8_t *fc, const uint8_t *fp) override {
+    if (prescaled) return ctx->fail(GB_ERR_UNSUPPORTED, "fixed vertices with bf16 Jacobian storage: use the generic factor-graph path");
+    auto install = [&](const uint8_t *src, int64_t n, unsigned char *&dst) -> int {
+      bool any = false;
+      if (src) for (int64_t i = 0; i < n; i++) any = any || src[i] != 0;
+      if (!any) { dst = nullptr; return GB_OK; }
+      unsigned char *buf = nullptr;
+      GB_CUDA(ctx, cudaMalloc((void **)&buf, (size_t)n));
+      allocs.push_back(buf);
+      GB_CUDA(ctx, cudaMemcpyAsync(buf, src, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+      GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      dst = buf;
+      return GB_OK;
+    };
+    GB_TRY(install(fc, ts.Nc, fixed_c));
+    GB_TRY(install(fp, ts.Np, fixed_p));
+    any_fixed = fixed_c != nullptr || fixed_p != nullptr;
+    linearized = prepared = solved = solved_full = stepped = false;
+    return GB_OK;
+  }
   // Replaces the loss argument of add_factor (factor.hpp:373-412, loss.hpp): one loss for all factors.
   int set_loss(int kind, double delta) override {
     if (kind != 0 && kind != 1) return ctx->fail(GB_ERR_INVALID, "unknown loss %d", kind);
@@ -650,7 +677,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_LAUNCH(ctx);
     // pre-scaled storage: this first pass only yields the rounded Jacobians and, from them, the true Jacobi scales
     const int son = prescaled ? (scale_on ? 1 : 0) : alg_scale();
-    k_cam_reduce_lin<T><<<ts.Nc, 288, 0, st>>>(ts, part18, diagB, gc, multi ? 0 : 1, son, scale, b);
+    k_cam_reduce_lin<T><<<ts.Nc, 288, 0, st>>>(ts, part18, diagB, gc, multi ? 0 : 1, son, scale, b, fixed_c);
     GB_LAUNCH(ctx);
     k_sum_partials<<<1, 1024, 0, st>>>(cost_part, ts.ntiles, scalars, 0);
     GB_LAUNCH(ctx);
@@ -658,12 +685,12 @@ template <typename T, typename S> struct Problem : ProblemBase {
     // point scales and b_p (mu-independent part of k_point_prepare); W/h are refreshed by prepare.  Purely local: on
     // the multi-GPU path it runs while the peers' diag(B) | g_c are in flight
     k_point_prepare<T><<<(ts.Np + 255) / 256, 256, 0, st>>>(ts.Np, son, mu, use_identity, Cg, scale + dimc,
-                                                           b + dimc, W, h, 1);
+                                                           b + dimc, W, h, 1, fixed_p);
     GB_LAUNCH(ctx);
     if (multi) {
       GB_TRY(exchange_sum<T>(diagB, 2 * (size_t)dimc));
       if (need_cost) GB_TRY(exchange<double>(scalars, 1));
-      k_cam_finish_lin<T><<<(int)((dimc + 255) / 256), 256, 0, st>>>((int)dimc, son, diagB, gc, scale, b);
+      k_cam_finish_lin<T><<<(int)((dimc + 255) / 256), 256, 0, st>>>((int)dimc, son, diagB, gc, scale, b, fixed_c);
       GB_LAUNCH(ctx);
     }
     if (prescaled) {
@@ -745,7 +772,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
       prepared = false; // part54 no longer holds the Schur sums
     }
     k_point_prepare<T><<<(ts.Np + 255) / 256, 256, 0, st>>>(ts.Np, alg_scale(), mu, use_identity, Cg, scale + dimc,
-                                                           b + dimc, W, h, 0);
+                                                           b + dimc, W, h, 0, fixed_p);
     GB_LAUNCH(ctx);
     k_full_cam_blocks<T><<<ts.Nc, 288, 0, st>>>(ts, part54, mu, use_identity, scale, f_Bfull, f_MinvF);
     GB_LAUNCH(ctx);
@@ -835,7 +862,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
   int enqueue_prepare() {
     cudaStream_t st = ctx->stream;
     k_point_prepare<T><<<(ts.Np + 255) / 256, 256, 0, st>>>(ts.Np, alg_scale(), mu, use_identity, Cg, scale + dimc,
-                                                           b + dimc, W, h, 0);
+                                                           b + dimc, W, h, 0, fixed_p);
     GB_LAUNCH(ctx);
     k_prepare_cams<T, S><<<ts.nchunks, PC_THREADS, 0, st>>>(ts, J, W, h, part54);
     GB_LAUNCH(ctx);
@@ -1784,6 +1811,7 @@ int gb_solve_device(gb_problem *p, const gb_pcg_options *o, void *d, gb_solve_in
 int gb_set_factor(gb_problem *p, gb_factor_fn fn, void *user) { GB_P(p); return p->impl->set_factor(fn, user); }
 int gb_set_loss(gb_problem *p, int kind, double delta) { GB_P(p); return p->impl->set_loss(kind, delta); }
 int gb_set_precision(gb_problem *p, const void *P) { GB_P(p); return p->impl->set_precision(P); }
+int gb_set_fixed(gb_problem *p, const uint8_t *fc, const uint8_t *fp) { GB_P(p); return p->impl->set_fixed(fc, fp); }
 int gb_hessian_structure(const gb_problem *p, int64_t *cp, int64_t *ri, int64_t *off) {
   if (!p || !cp || !ri || !off) return GB_ERR_INVALID;
   p->impl->hs.hessian_structure(cp, ri, off);

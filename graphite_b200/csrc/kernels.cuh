@@ -58,8 +58,9 @@ constexpr int NPLANES = 12;
 #endif
 constexpr int COST_TILES = 4; // tiles per CTA of k_cost_tiles
 constexpr int LIN_STR = 19; // staging row stride of k_linearize (18 values; odd stride: conflict-free 64-bit rows)
-template <typename T> constexpr int smem_lin_bytes() { // staging, accumulator rows, tile record
-  return (TILE * LIN_STR + SLOT_CAP * 18) * (int)sizeof(T) + 16 + REC_BYTES;
+constexpr int LIN_PTS = 128 * 3; // staged point coordinates of a tile (<= 128 points)
+template <typename T> constexpr int smem_lin_bytes() { // staging, accumulator rows, tile record, camera table, tile points
+  return (TILE * LIN_STR + SLOT_CAP * 18) * (int)sizeof(T) + 16 + REC_BYTES + (SLOT_CAP * CAMX + LIN_PTS) * (int)sizeof(T);
 }
 // per-point W row stride: 6 values, padded to 8 in FP32 so that a tile's rows start 16-byte aligned (TMA)
 template <typename T> struct WST { static constexpr int value = sizeof(T) == 4 ? 8 : 6; };
@@ -362,10 +363,28 @@ k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
   T *sv = reinterpret_cast<T *>(smem_raw);            // [TILE*LIN_STR] staging (point side uses the first TILE*9)
   T *acc = sv + TILE * LIN_STR;                       // [SLOT_CAP*18]
   unsigned char *rec = smem_raw + (((TILE * LIN_STR + SLOT_CAP * 18) * (int)sizeof(T) + 15) & ~15); // [REC_BYTES]
+  // the super-tile's cameras (<= SLOT_CAP rows of the precomputed model terms) and the tile's points live in shared
+  // memory: every observation then reads its 24 camera terms and 3 coordinates with LDS instead of a dependent chain of
+  // global gathers (ncu of the gather version: long-scoreboard was the top stall, 4.7 cycles per issued instruction)
+  T *cxs = reinterpret_cast<T *>(rec + REC_BYTES);    // [SLOT_CAP*CAMX]
+  T *pxs = cxs + SLOT_CAP * CAMX;                     // [LIN_PTS]
   __shared__ double shd[32];
   const int st = blockIdx.x, t = threadIdx.x;
   const int row0 = ds.st_row[st], nslots = ds.st_row[st + 1] - row0;
   for (int i = t; i < nslots * 18; i += TILE) acc[i] = T(0);
+  if (!EXT && !RESCALE) {
+    constexpr int VEC = 16 / (int)sizeof(T), ROWV = CAMX / VEC; // 16-byte pieces per camera row
+    for (int i = t; i < nslots * ROWV; i += TILE) {
+      const int cs = i / ROWV, k = i - cs * ROWV;
+      reinterpret_cast<uint4 *>(cxs)[i] = __ldg(reinterpret_cast<const uint4 *>(cams + (int64_t)ds.row_cam[row0 + cs] * CAMX) + k);
+    }
+    // the first tile's point coordinates (a tile owns a contiguous range of <= 128 points); the following tiles' are
+    // fetched during the reduction phases of the tile before them
+    const TileMeta tm0 = ds.tmeta[ds.st_tile[st]];
+    const T *src = pts + 3 * (int64_t)tm0.p0;
+    if (t < tm0.np * 3) pxs[t] = src[t];
+    if (t + TILE < tm0.np * 3) pxs[t + TILE] = src[t + TILE];
+  }
   __syncthreads();
   // the per-slot inputs of the NEXT tile (meta word, camera, observation) are fetched one tile ahead, so that a tile
   // starts with the camera / point gathers instead of a chain of dependent loads
@@ -431,12 +450,11 @@ k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
 #pragma unroll
         for (int j = 0; j < 6; j++) B.Jp[j] = ep[j];
       } else {
-        const int p = tm.p0 + ptl;
-        T cx[CAMX], X[3], ob[2];
-        load_camx<T>(cams, c, cx); // `cams` is the per-camera precomputed table (k_cam_precompute)
-        X[0] = pts[3 * (int64_t)p];
-        X[1] = pts[3 * (int64_t)p + 1];
-        X[2] = pts[3 * (int64_t)p + 2];
+        T X[3], ob[2];
+        const T *cx = cxs + (int)(om >> 16) * CAMX; // `cams` is the per-camera precomputed table (k_cam_precompute)
+        X[0] = pxs[3 * ptl];
+        X[1] = pxs[3 * ptl + 1];
+        X[2] = pxs[3 * ptl + 2];
         ob[0] = ov.x;
         ob[1] = ov.y;
         bal_residual_jacobian_pre<T>(cx, X, ob, B);
@@ -475,6 +493,15 @@ k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
       if ((t & 31) == 0) shd[t >> 5] = cw;
     }
     __syncthreads();
+    // every thread has its point in registers: the staged coordinates are dead, fetch the next tile's (stored before the
+    // last barrier of this tile; the two reduction phases hide the latency)
+    T px_n0 = T(0), px_n1 = T(0);
+    if (!EXT && !RESCALE && tile + 1 < tile_end) {
+      const int n3 = tm_n.np * 3;
+      const T *src = pts + 3 * (int64_t)tm_n.p0;
+      if (t < n3) px_n0 = src[t];
+      if (t + TILE < n3) px_n1 = src[t + TILE];
+    }
     if (t == 0) {
       double tot = 0.0;
       for (int i = 0; i < TILE / 32; i++) tot += shd[i];
@@ -529,6 +556,10 @@ k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
         ar[2] += a2;
       }
     }
+    if (!EXT && !RESCALE && tile + 1 < tile_end) {
+      pxs[t] = px_n0;
+      if (t < LIN_PTS - TILE) pxs[t + TILE] = px_n1;
+    }
     __syncthreads(); // this tile's staging reads are done: the next tile may write its record and staging
   }
   for (int i = t; i < nslots * 18; i += TILE) part[(int64_t)ds.row_out[row0 + i / 18] * 18 + i % 18] = acc[i];
@@ -538,7 +569,8 @@ k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
 template <typename T>
 __global__ void __launch_bounds__(288)
 k_cam_reduce_lin(DevStruct ds, const T *__restrict__ part, T *__restrict__ diagB, T *__restrict__ gc,
-                 int do_finish, int scale_on, T *__restrict__ scale_c, T *__restrict__ b_c) {
+                 int do_finish, int scale_on, T *__restrict__ scale_c, T *__restrict__ b_c,
+                 const unsigned char *__restrict__ fixed_c = nullptr) {
   __shared__ T sh[32 * 9];
   __shared__ T out[18];
   const int c = blockIdx.x;
@@ -548,7 +580,9 @@ k_cam_reduce_lin(DevStruct ds, const T *__restrict__ part, T *__restrict__ diagB
     diagB[c * 9 + k] = out[k];
     gc[c * 9 + k] = out[9 + k];
     if (do_finish) {
-      const T s = scale_on ? (T)(1.0 / (DBL_EPSILON + sqrt((double)out[k]))) : T(1);
+      // a FIXED vertex (vertex.hpp:254-266) keeps its slot with scale 0: J~ = 0, b = 0, step 0 - the same numbers for
+      // every other variable as the reference gets by leaving its columns out of the system
+      const T s = (fixed_c && fixed_c[c]) ? T(0) : (scale_on ? (T)(1.0 / (DBL_EPSILON + sqrt((double)out[k]))) : T(1));
       scale_c[c * 9 + k] = s;
       b_c[c * 9 + k] = s * out[9 + k];
     }
@@ -557,10 +591,10 @@ k_cam_reduce_lin(DevStruct ds, const T *__restrict__ part, T *__restrict__ diagB
 // After a multi-GPU allreduce of diagB / gc.
 template <typename T>
 __global__ void k_cam_finish_lin(int n, int scale_on, const T *__restrict__ diagB, const T *__restrict__ gc,
-                                 T *__restrict__ scale_c, T *__restrict__ b_c) {
+                                 T *__restrict__ scale_c, T *__restrict__ b_c, const unsigned char *__restrict__ fixed_c = nullptr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const T s = scale_on ? (T)(1.0 / (DBL_EPSILON + sqrt((double)diagB[i]))) : T(1);
+  const T s = (fixed_c && fixed_c[i / 9]) ? T(0) : (scale_on ? (T)(1.0 / (DBL_EPSILON + sqrt((double)diagB[i]))) : T(1));
   scale_c[i] = s;
   b_c[i] = s * gc[i];
 }
@@ -621,9 +655,18 @@ template <typename T> __device__ __forceinline__ T damp_value(T d, T mu, int use
 template <typename T>
 __global__ void k_point_prepare(int Np, int scale_on, T mu, int use_identity, const T *__restrict__ Cg,
                                 T *__restrict__ scale_p, T *__restrict__ b_p, T *__restrict__ W, T *__restrict__ h,
-                                int write_lin) {
+                                int write_lin, const unsigned char *__restrict__ fixed_p = nullptr) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= Np) return;
+  if (fixed_p && fixed_p[p]) { // fixed point: scale 0, b = 0, W = 0, h = 0 (it adds nothing to S, b_S and gets no step)
+    if (write_lin) {
+      for (int k = 0; k < 3; k++) { scale_p[3 * (int64_t)p + k] = T(0); b_p[3 * (int64_t)p + k] = T(0); }
+    } else {
+      for (int k = 0; k < 6; k++) W[(int64_t)p * WST<T>::value + k] = T(0);
+      for (int k = 0; k < 3; k++) h[HST * (int64_t)p + k] = T(0);
+    }
+    return;
+  }
   const T *cg = Cg + (int64_t)p * 9;
   const T c00 = cg[0], c01 = cg[1], c02 = cg[2], c11 = cg[3], c12 = cg[4], c22 = cg[5];
   const T g0 = cg[6], g1 = cg[7], g2 = cg[8];
@@ -828,13 +871,15 @@ k_cam_reduce_prepare(DevStruct ds, const T *__restrict__ part, int from_sums, T 
     const int a = i < j ? i : j, b = i < j ? j : i;
     const int idx = a * 9 - (a * (a - 1)) / 2 + (b - a); // packed upper index of (a,b), row-wise
     const T si = scale_c[c * 9 + i], sj = scale_c[c * 9 + j];
+    const bool fx = scale_c[c * 9] == T(0); // fixed camera: identity block, zero right-hand side (its unknowns stay 0)
     T val = si * sj * out[idx];
     if (i == j) {
       const T bt = si * si * diagB[c * 9 + i];
-      const T dt = damp_value<T>(bt, mu, use_identity) - bt;
+      const T dt = fx ? T(0) : damp_value<T>(bt, mu, use_identity) - bt;
       val += dt;
       dterm[c * 9 + i] = dt;
       bS[c * 9 + i] = si * (gc[c * 9 + i] - out[45 + i]);
+      if (fx) val = T(1);
     }
     Maug[i * 18 + j] = val;
     Maug[i * 18 + 9 + j] = (i == j) ? T(1) : T(0);
@@ -1117,7 +1162,7 @@ k_backsubst_tiles(DevStruct ds, const typename V2<S>::type *__restrict__ J, cons
     for (int k = 0; k < 3; k++) {
       const int64_t i = 3 * (int64_t)p + k;
       const T s = scale_p[i];
-      const T xt = (h[HST * (int64_t)p + k] - wv[k]) / s; // scaled-space step of the point
+      const T xt = s != T(0) ? (h[HST * (int64_t)p + k] - wv[k]) / s : T(0); // scaled-space step of the point (0: fixed)
       delta_p[i] = xt;
       rho += (double)(xt * (mu * xt + b_p[i]));
       if (apply) {
@@ -1541,7 +1586,7 @@ k_full_cam_blocks(DevStruct ds, const T *__restrict__ part /*[nrows][54]*/, T mu
     const int idx = a * 9 - (a * (a - 1)) / 2 + (b - a);
     T val = scale_c[c * 9 + i] * scale_c[c * 9 + j] * out[idx];
     Bfull[(int64_t)c * 81 + i + 9 * j] = val;
-    if (i == j) val = damp_value<T>(val, mu, use_identity);
+    if (i == j) val = scale_c[c * 9] == T(0) ? T(1) : damp_value<T>(val, mu, use_identity); // fixed camera: identity
     Maug[i * 18 + j] = val;
     Maug[i * 18 + 9 + j] = (i == j) ? T(1) : T(0);
   }
@@ -1638,6 +1683,7 @@ __global__ void k_full_precond(int Nc, int Np, const T *__restrict__ MinvF, cons
     const int k = (int)((i - dimc) % 3);
     const T *w = W + q * WST<T>::value;
     const T *sc = scale + dimc + 3 * q, *yy = y + dimc + 3 * q;
+    if (sc[0] == T(0)) { z[i] = T(0); return; } // fixed point
     const T a0 = yy[0] / sc[0], a1 = yy[1] / sc[1], a2 = yy[2] / sc[2];
     const T r = k == 0 ? w[0] * a0 + w[1] * a1 + w[2] * a2
               : (k == 1 ? w[1] * a0 + w[3] * a1 + w[4] * a2 : w[2] * a0 + w[4] * a1 + w[5] * a2);

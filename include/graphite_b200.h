@@ -133,6 +133,13 @@ int gb_get_vertices_device(gb_problem *p, void *cams_dev, void *pts_dev);
 typedef enum { GB_LOSS_DEFAULT = 0, GB_LOSS_HUBER = 1 } gb_loss;
 int gb_set_loss(gb_problem *p, int loss, double delta);
 int gb_set_precision(gb_problem *p, const void *precision_host);
+/* Replaces: VertexDescriptor::set_fixed (vertex.hpp:254-266) for cameras and points: cameras_fixed [n_cams] / points_fixed
+ * [n_points] (host, != 0 = fixed; NULL = none).  A fixed vertex is never updated and adds no unknowns: the other unknowns get
+ * exactly the system the reference builds without its columns (graph.hpp:112-147, ops/linearize.hpp:24-27), factors on fixed
+ * vertices still count in chi2.  LAYOUT: fixed vertices KEEP their slot in the vectors of this header (gradient, scales, step,
+ * Hessian / Schur exports: zero rows and columns, unit diagonal blocks in S) instead of being renumbered away - use the generic
+ * path (graphite_b200_graph.h) for the reference's reduced block order.  Not offered with GB_BF16 storage. */
+int gb_set_fixed(gb_problem *p, const uint8_t *cameras_fixed, const uint8_t *points_fixed);
 /* User-defined factor: replaces FactorTraits::error / ::jacobian (docs/markdown/main.md:284-289; dispatch in
  * ops/error.hpp:33-96 and ops/linearize.hpp:8-138) for any binary factor of the BAL block shape (vertex 0: 9 parameters,
  * vertex 1: 3 parameters, residual 2) - other camera models, other parameterisations.  The library calls `fn` whenever it

@@ -43,7 +43,7 @@ def parse_table(text: str):
     return rows
 
 
-def run_case(name, prob, solver, precision, iterations, dump=False, lam=1e-4, timeout=3000, huber=0.0, weights=False):
+def run_case(name, prob, solver, precision, iterations, dump=False, lam=1e-4, timeout=3000, huber=0.0, weights=False, fix_cameras=0, fix_points=0):
     os.makedirs(OUT, exist_ok=True)
     gbal = os.path.join(OUT, f"{name}.gbal")
     if not os.path.exists(gbal):
@@ -56,6 +56,9 @@ def run_case(name, prob, solver, precision, iterations, dump=False, lam=1e-4, ti
     if weights:    # per-factor precision matrices, synthetic.precision_matrices
         tag += "__weights"
         cmd += ["--weights"]
+    if fix_cameras or fix_points:  # VertexDescriptor::set_fixed on the first cameras / every K-th point
+        tag += f"__fixed{fix_cameras}c{fix_points}p"
+        cmd += ["--fix_cameras", str(fix_cameras), "--fix_points", str(fix_points)]
     prefix = os.path.join(OUT, tag)
     if dump:
         cmd += ["--dump", prefix]
@@ -68,7 +71,7 @@ def run_case(name, prob, solver, precision, iterations, dump=False, lam=1e-4, ti
     dchi = [l for l in res.stdout.splitlines() if l.startswith("DUMP chi2")]
     rec = {
         "case": name, "shape": list(prob.shape()), "seed": 0, "solver": solver, "precision": precision,
-        "lambda": lam, "huber": huber, "weights": weights, "pcg_iterations": 10, "pcg_tolerance": 1.0, "rejection_ratio": 5.0,
+        "lambda": lam, "huber": huber, "weights": weights, "fix_cameras": fix_cameras, "fix_points": fix_points, "pcg_iterations": 10, "pcg_tolerance": 1.0, "rejection_ratio": 5.0,
         "iterations": iterations, "returncode": res.returncode,
         "table_columns": ["iteration", "initial_chi2", "current_chi2", "lambda", "iter_seconds", "total_seconds"],
         "table": rows,
@@ -146,6 +149,13 @@ def main(which):
             rec = run_case(name, p, "pcg-schur", "FP64-FP64", 50, **kw)
             base = os.path.join(OUT, f"{name}__pcg-schur__FP64-FP64__huber20__weights")
             os.replace(base + ".json", base + ".run2.json")
+    if "fixed" in which:  # fixed vertices (gauge cameras, some fixed points): pcg-schur and pcg, final vertices dumped
+        p = synthetic.make_named("ladybug-49")
+        run_case("ladybug-49", p, "pcg-schur", "FP64-FP64", 30, dump=True, fix_cameras=2, fix_points=50)
+        run_case("ladybug-49", p, "pcg", "FP64-FP64", 30, fix_cameras=2, fix_points=50)
+        run_case("ladybug-49", p, "pcg-schur", "FP32-FP32", 30, fix_cameras=2, fix_points=50)
+        p = synthetic.make_named("trafalgar-257")
+        run_case("trafalgar-257", p, "pcg-schur", "FP64-FP64", 30, fix_cameras=1, fix_points=0)
     if "dubrovnik" in which:
         p = synthetic.make_named("dubrovnik-356")
         second_run("dubrovnik-356", p)

@@ -43,6 +43,8 @@ struct Args {
   bool identity = false;
   double huber = 0.0;    // > 0: HuberLoss(delta) on every factor (loss.hpp:27-51)
   bool weights = false;  // per-factor precision matrices, the rational pattern of graphite_b200/synthetic.py:precision_matrices
+  int64_t fix_cameras = 0; // VertexDescriptor::set_fixed on the first N cameras (vertex.hpp:254-266)
+  int64_t fix_points = 0;  // ... and on every K-th point (0: none)
 };
 
 template <typename V> static void dump_vec(const std::string &path, const V &v) {
@@ -93,6 +95,9 @@ int run(const Args &a, const Problem &prob, const LossT &loss = LossT()) {
     point_desc.add_vertex(i + prob.nc, &points[i]);
   }
   point_desc.set_eliminate(true);
+  for (int64_t i = 0; i < a.fix_cameras && i < prob.nc; i++) camera_desc.set_fixed(i, true);
+  if (a.fix_points > 0)
+    for (int64_t i = 0; i < prob.np; i += a.fix_points) point_desc.set_fixed(i + prob.nc, true);
 
   StreamPool streams(8);
 
@@ -187,6 +192,8 @@ int main(int argc, char **argv) {
     else if (s == "--identity_damping") a.identity = true;
     else if (s == "--huber") a.huber = atof(next().c_str());
     else if (s == "--weights") a.weights = true;
+    else if (s == "--fix_cameras") a.fix_cameras = atol(next().c_str());
+    else if (s == "--fix_points") a.fix_points = atol(next().c_str());
     else if (s == "--dump") a.dump = next();
     else a.file = s;
   }

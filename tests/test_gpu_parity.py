@@ -785,3 +785,81 @@ def test_multi_gpu_equals_single_gpu(ctx):
            "--master-port", "29621", os.path.join(ROOT, "scripts", "multi_gpu_check.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0 and "MULTI_GPU_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+# ------------------------------------------------------------------------------------------------------
+# fixed vertices (VertexDescriptor::set_fixed, vertex.hpp:254-266) on the BAL / Schur path
+# ------------------------------------------------------------------------------------------------------
+def _fixed_masks(prob, n_cams_fixed, every_kth_point):
+    fc = np.zeros(prob.n_cams, np.uint8)
+    fc[:n_cams_fixed] = 1
+    fp = np.zeros(prob.n_pts, np.uint8)
+    if every_kth_point:
+        fp[::every_kth_point] = 1
+    return fc, fp
+
+
+@pytest.mark.parametrize("case,solver,precision,tag,nc,kp,tol", [
+    ("ladybug-49", "pcg-schur", "f64-f64", "FP64-FP64", 2, 50, 1e-9),
+    ("ladybug-49", "pcg", "f64-f64", "FP64-FP64", 2, 50, 1e-9),
+    ("ladybug-49", "pcg-schur", "f32-f32", "FP32-FP32", 2, 50, 1e-4),
+    ("trafalgar-257", "pcg-schur", "f64-f64", "FP64-FP64", 1, 0, 1e-9),
+])
+def test_fixed_vertices_match_reference(ctx, case, solver, precision, tag, nc, kp, tol):
+    """Gauge cameras and some points fixed: the LM trajectory of the reference run with set_fixed on the same vertices
+    (oracle/ref_driver.cu --fix_cameras / --fix_points), fixed vertices untouched bit for bit."""
+    name = f"{case}__{solver}__{tag}__fixed{nc}c{kp}p"
+    try:
+        g = golden_json(name + ".json")
+    except FileNotFoundError:
+        pytest.skip(f"golden {name} not generated yet (oracle/make_golden.py fixed)")
+    prob = named_problem(case)
+    fc, fp = _fixed_masks(prob, nc, kp)
+    P = binding.problem_from_bal(ctx, prob, precision)
+    P.set_fixed(fc, fp)
+    ref = np.array(g["table"])
+    traj, res = P.lm(iterations=len(ref), solver=solver)
+    assert np.array_equal(traj[:, 0] == traj[:, 1], ref[:, 1] == ref[:, 2])
+    assert np.abs(traj[:, 1] - ref[:, 2]).max() / ref[0, 1] < tol
+    assert abs(traj[-1, 1] - g["final_chi2"]) / g["final_chi2"] < max(tol, 1e-6)
+    cams, pts = P.get_vertices()
+    T = np.float32 if precision.startswith("f32") else np.float64
+    assert np.array_equal(cams[fc == 1], prob.cams[fc == 1].astype(T)) and np.array_equal(pts[fp == 1], prob.pts[fp == 1].astype(T))
+    assert not np.array_equal(cams[fc == 0], prob.cams[fc == 0].astype(T))
+    if precision == "f64-f64" and solver == "pcg-schur" and case == "ladybug-49":
+        z = golden_npz(name + ".npz")
+        assert rel(cams.reshape(-1), z["final_cams"]) < 1e-6 and rel(pts.reshape(-1), z["final_pts"]) < 1e-6
+    P.close()
+
+
+def test_fixed_vertices_first_linearisation_and_modes(ctx):
+    """Fixed vertices keep their slot with zero gradient / scale / step; the remaining entries are those of the reference's
+    reduced system (b, scales of its first-linearisation dump); explicit and direct Schur modes agree with the implicit one."""
+    name = "ladybug-49__pcg-schur__FP64-FP64__fixed2c50p"
+    try:
+        z = golden_npz(name + ".npz")
+    except FileNotFoundError:
+        pytest.skip("golden not generated yet")
+    prob = named_problem("ladybug-49")
+    fc, fp = _fixed_masks(prob, 2, 50)
+    P = binding.problem_from_bal(ctx, prob, "f64-f64")
+    P.set_fixed(fc, fp)
+    P.linearize()
+    keep = np.concatenate([np.repeat(fc == 0, 9), np.repeat(fp == 0, 3)])
+    b, s = P.gradient(), P.scales()
+    assert not b[~keep].any() and not s[~keep].any()
+    assert rel(b[keep], z["b"]) < 1e-12 and rel(s[keep], z["scales"]) < 1e-12
+    P.set_damping(1e-4)
+    steps = {}
+    for mode in ("implicit", "explicit"):
+        steps[mode], info = P.solve(max_iterations=10, schur_mode=mode)
+        assert not steps[mode][~keep].any()
+    assert rel(steps["explicit"], steps["implicit"]) < 1e-9
+    xd, _ = P.solve(solver="direct-schur")
+    xi, _ = P.solve(max_iterations=200, tolerance=1e-26, rejection_ratio=1e30, schur_mode="implicit")
+    assert not xd[~keep].any() and rel(xd, xi) < 1e-6
+    # clearing the masks restores the unconstrained problem
+    P.set_fixed(None, None)
+    P.linearize()
+    assert P.scales().all()
+    P.close()
