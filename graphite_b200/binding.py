@@ -26,7 +26,7 @@ SYMBOLS = [
     "gb_get_schur_diagonal", "gb_schur_multiply", "gb_schur_structure", "gb_schur_values", "gb_try_step", "gb_revert_step", "gb_lm", "gb_kernel_launches",
     "gb_time_stage", "gb_structure_create", "gb_structure_destroy", "gb_structure_info", "gb_structure_array",
     "gb_structure_hessian", "gb_structure_schur", "gb_context_create_on_stream", "gb_set_observations_device",
-    "gb_set_vertices_device", "gb_get_vertices_device", "gb_import_linearization", "gb_solve_device", "gb_schur_csc", "gb_set_fixed",
+    "gb_set_vertices_device", "gb_get_vertices_device", "gb_import_linearization", "gb_solve_device", "gb_schur_csc", "gb_set_fixed", "gb_problem_structure_array",
 ]
 
 
@@ -124,6 +124,7 @@ def load_library():
     L.gb_structure_destroy.argtypes = [vp]
     L.gb_structure_info.argtypes = [vp, C.POINTER(C.c_int64)]
     L.gb_structure_array.argtypes = [vp, C.c_int, vp, C.POINTER(C.c_int64)]
+    L.gb_problem_structure_array.argtypes = [vp, C.c_int, vp, C.POINTER(C.c_int64)]
     L.gb_structure_hessian.argtypes = [vp, vp, vp, vp]
     L.gb_structure_schur.argtypes = [vp, vp, vp, C.POINTER(C.c_int64)]
     _lib = L
@@ -174,7 +175,7 @@ class Problem:
     """One BAL problem on one GPU (one rank's point partition)."""
 
     def __init__(self, ctx: Context, cam_idx, pt_idx, n_cams: int, n_pts: int, precision: str = "f64-f64", tile_size: int = 0,
-                 slot_cap: int = 0, super_tile_observations: int = 0, partition: bool = False):
+                 slot_cap: int = 0, super_tile_observations: int = 0, partition: bool = False, host_tables: bool = False):
         self.ctx, self.L = ctx, ctx.L
         t, s = precision.split("-")
         self.T, self.S = _NP[t], _NP[s]
@@ -186,7 +187,7 @@ class Problem:
         pi = np.ascontiguousarray(pt_idx, dtype=np.int32)
         d = ProblemDesc(_DT[t], _DT[s], self.n_cams, self.n_pts, self.n_obs, ci.ctypes.data_as(C.POINTER(C.c_int32)),
                         pi.ctypes.data_as(C.POINTER(C.c_int32)), tile_size, slot_cap, super_tile_observations,
-                        1 if partition else 0)
+                        (1 if partition else 0) | (2 if host_tables else 0))
         h = C.c_void_p()
         ctx.check(self.L.gb_problem_create(ctx.h, C.byref(d), C.byref(h)))
         self.h = h
@@ -201,6 +202,14 @@ class Problem:
             self.close()
         except Exception:
             pass
+
+    def structure_array(self, which: int):
+        """A structure table as it is on the device (10 slot_of_obs, 13 ometa, 17 tile records, 18 tile_cam, 19 cm_slot, 20 cm_pt)."""
+        n = C.c_int64()
+        self.ctx.check(self.L.gb_problem_structure_array(self.h, which, None, C.byref(n)))
+        out = np.empty(n.value, dtype=np.uint8 if which == 17 else (np.uint32 if which == 13 else np.int32))
+        self.ctx.check(self.L.gb_problem_structure_array(self.h, which, _ptr(out), C.byref(n)))
+        return out
 
     def info(self):
         a = (C.c_int64 * 12)()
@@ -389,9 +398,9 @@ class Problem:
 
 
 def problem_from_bal(ctx: Context, prob, precision="f64-f64", tile_size=0, slot_cap=0, super_tile_observations=0,
-                     partition=False) -> Problem:
+                     partition=False, host_tables=False) -> Problem:
     p = Problem(ctx, prob.cam_idx, prob.pt_idx, prob.n_cams, prob.n_pts, precision, tile_size, slot_cap,
-                super_tile_observations, partition)
+                super_tile_observations, partition, host_tables)
     p.set_observations(prob.obs)
     p.set_vertices(prob.cams, prob.pts)
     return p

@@ -19,6 +19,7 @@
 #include "explicit_schur.cuh"
 #include "direct_schur.cuh"
 #include "structure.hpp"
+#include "structure_device.cuh"
 
 namespace gb {
 
@@ -67,6 +68,7 @@ struct ProblemBase {
   virtual int revert_step() = 0;
   virtual int lm(const gb_lm_options *, gb_lm_result *, double *) = 0;
   virtual int time_stage(int, int, double *) = 0;
+  virtual int structure_array(int, void *, int64_t *) = 0;
   virtual int64_t device_bytes() const = 0;
   virtual int exchange_mode() const = 0; // 0 single rank, 1 NCCL all-reduce, 2 peer-memory exchange (p2p.cuh)
 };
@@ -209,6 +211,26 @@ template <typename T, typename S> struct Problem : ProblemBase {
     return GB_OK;
   }
 
+  // device copies of the structure tables (gb_problem_structure_array): the GPU-built arrays against the host view
+  int structure_array(int which, void *out, int64_t *count) override {
+    const void *src = nullptr;
+    size_t bytes = 0;
+    switch (which) {
+      case 10: src = ts.slot_of_obs; bytes = (size_t)ts.M * 4; *count = ts.M; break;
+      case 13: src = ts.ometa; bytes = (size_t)ts.Mstore * 4; *count = ts.Mstore; break;
+      case 17: src = ts.trec; bytes = (size_t)ts.ntiles * REC_BYTES; *count = (int64_t)bytes; break;
+      case 18: src = ts.tile_cam; bytes = (size_t)ts.Mstore * 4; *count = ts.Mstore; break;
+      case 19: src = ts.cm_slot; bytes = (size_t)ts.M * 4; *count = ts.M; break;
+      case 20: src = ts.cm_pt; bytes = (size_t)ts.M * 4; *count = ts.M; break;
+      default: return ctx->fail(GB_ERR_INVALID, "gb_problem_structure_array: unknown array %d", which);
+    }
+    if (out) {
+      GB_CUDA(ctx, cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+      GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return GB_OK;
+  }
+
   int init() override {
     GB_CUDA(ctx, cudaSetDevice(ctx->device));
     for (auto &e : ev) e = nullptr;
@@ -220,9 +242,6 @@ template <typename T, typename S> struct Problem : ProblemBase {
     ts.Mstore = hs.Mstore;
     ts.Nc = hs.Nc; ts.Np = hs.Np; ts.ntiles = hs.ntiles(); ts.nst = hs.nst(); ts.nrows = hs.nrows(); ts.pad = 0;
     GB_TRY(upload(ts.tmeta, hs.tmeta));
-    GB_TRY(upload(ts.ometa, hs.ometa));
-    GB_TRY(upload(ts.trec, hs.trec));
-    GB_TRY(upload(ts.tile_cam, hs.tile_cam));
     GB_TRY(upload(ts.st_tile, hs.st_tile));
     GB_TRY(upload(ts.st_row, hs.st_row));
     GB_TRY(upload(ts.row_cam, hs.row_cam));
@@ -231,15 +250,48 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_TRY(upload(ts.cta_st, hs.cta_st));
     GB_TRY(upload(ts.strec, hs.strec));
     ts.ncta = hs.ncta(); ts.pad2 = 0;
-    GB_TRY(upload(ts.cm_slot, hs.cm_slot));
-    GB_TRY(upload(ts.cm_pt, hs.cm_pt));
     GB_TRY(upload(ts.ch_ptr, hs.ch_ptr));
     GB_TRY(upload(ts.cam_ch_ptr, hs.cam_ch_ptr));
     ts.nchunks = hs.nchunks(); ts.pad3 = 0;
-    GB_TRY(upload(ts.slot_of_obs, hs.slot_of_obs));
     GB_TRY(upload(ts.cam_idx, hs.cam_idx));
     GB_TRY(upload(ts.pt_idx, hs.pt_idx));
     GB_TRY(upload(ts.pptr, hs.pptr));
+    if (hs.tables_on_device) {
+      // the observation-sized tables are built here, on the device (structure_device.cuh); the host made the cuts only
+      const int32_t *d_tile_obs = nullptr, *d_tile_pt = nullptr, *d_tile_st = nullptr;
+      GB_TRY(upload(d_tile_obs, hs.tile_obs));
+      GB_TRY(upload(d_tile_pt, hs.tile_pt));
+      GB_TRY(upload(d_tile_st, hs.tile_st));
+      uint32_t *d_ometa = nullptr;
+      unsigned char *d_trec = nullptr;
+      int32_t *d_tile_cam = nullptr, *d_slot = nullptr, *d_cm_slot = nullptr, *d_cm_pt = nullptr;
+      GB_TRY(dalloc(d_ometa, hs.Mstore)); GB_TRY(dalloc(d_trec, (size_t)ts.ntiles * REC_BYTES));
+      GB_TRY(dalloc(d_tile_cam, hs.Mstore)); GB_TRY(dalloc(d_slot, M));
+      GB_TRY(dalloc(d_cm_slot, M)); GB_TRY(dalloc(d_cm_pt, M));
+      k_build_tile_tables<<<ts.ntiles, TILE, 0, ctx->stream>>>(ts.ntiles, ts.cam_idx, ts.pt_idx, ts.pptr, d_tile_obs, d_tile_pt, d_tile_st,
+                                                                ts.st_row, ts.row_cam, ts.tmeta, d_ometa, d_trec, d_tile_cam, d_slot);
+      GB_LAUNCH(ctx);
+      {
+        Scratch k1, k2, k3;
+        GB_CUDA(ctx, cudaMalloc(&k1.p, (size_t)M * 4)); GB_CUDA(ctx, cudaMalloc(&k2.p, (size_t)M * 4)); GB_CUDA(ctx, cudaMalloc(&k3.p, (size_t)M * 4));
+        GB_CUDA(ctx, camera_major_order(M, hs.Nc, ts.cam_idx, k1.as<int32_t>(), k2.as<int32_t>(), k3.as<int32_t>(), ctx->stream));
+        k_camera_major<<<(unsigned)((M + 255) / 256), 256, 0, ctx->stream>>>(M, k3.as<int32_t>(), d_slot, ts.pt_idx, d_cm_slot, d_cm_pt);
+        GB_LAUNCH(ctx);
+        GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      }
+      ts.ometa = d_ometa; ts.trec = d_trec; ts.tile_cam = d_tile_cam; ts.slot_of_obs = d_slot; ts.cm_slot = d_cm_slot; ts.cm_pt = d_cm_pt;
+      // host-side exports permute through slot_of_obs: keep a copy (20 MB at Venice)
+      hs.slot_of_obs.resize((size_t)M);
+      GB_CUDA(ctx, cudaMemcpyAsync(hs.slot_of_obs.data(), d_slot, (size_t)M * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    } else {
+      GB_TRY(upload(ts.ometa, hs.ometa));
+      GB_TRY(upload(ts.trec, hs.trec));
+      GB_TRY(upload(ts.tile_cam, hs.tile_cam));
+      GB_TRY(upload(ts.cm_slot, hs.cm_slot));
+      GB_TRY(upload(ts.cm_pt, hs.cm_pt));
+      GB_TRY(upload(ts.slot_of_obs, hs.slot_of_obs));
+    }
     GB_TRY(dalloc(cams, Nc * CAM_STRIDE)); GB_TRY(dalloc(cams_bak, Nc * CAM_STRIDE)); GB_TRY(dalloc(camx, Nc * CAMX));
     GB_TRY(dalloc(pts, 3 * Np)); GB_TRY(dalloc(pts_bak, 3 * Np));
     GB_TRY(dalloc(obs, hs.Mstore)); GB_TRY(dalloc(res, hs.Mstore)); GB_TRY(dalloc(obs_stage, M));
@@ -1673,7 +1725,7 @@ int gb_problem_create(gb_context *ctx, const gb_problem_desc *d, gb_problem **ou
   impl->ctx = ctx;
   const std::string why = impl->hs.build(d->num_cameras, d->num_points, d->num_observations, d->camera_index,
                                          d->point_index, d->tile_size, d->slot_cap, d->super_tile_observations,
-                                      (d->flags & GB_FLAG_PARTITION) != 0);
+                                         (d->flags & GB_FLAG_PARTITION) != 0, (d->flags & GB_FLAG_HOST_TABLES) == 0);
   if (!why.empty()) {
     delete impl;
     return ctx->fail(GB_ERR_UNSUPPORTED, "structure: %s", why.c_str());
@@ -1762,6 +1814,13 @@ int gb_structure_array(const gb_structure *s, int which, void *out, int64_t *cou
   } else if (which == 16) {
     *count = (int64_t)h.tmeta.size() * 8;
     if (out) memcpy(out, h.tmeta.data(), h.tmeta.size() * sizeof(gb::TileMeta));
+  } else if (which == 17) {
+    *count = (int64_t)h.trec.size();
+    if (out) memcpy(out, h.trec.data(), h.trec.size());
+  } else if (which >= 18 && which <= 20) {
+    const std::vector<int32_t> &v = which == 18 ? h.tile_cam : (which == 19 ? h.cm_slot : h.cm_pt);
+    *count = (int64_t)v.size();
+    if (out) memcpy(out, v.data(), v.size() * sizeof(int32_t));
   } else {
     return GB_ERR_INVALID;
   }
@@ -1811,6 +1870,11 @@ int gb_solve_device(gb_problem *p, const gb_pcg_options *o, void *d, gb_solve_in
 int gb_set_factor(gb_problem *p, gb_factor_fn fn, void *user) { GB_P(p); return p->impl->set_factor(fn, user); }
 int gb_set_loss(gb_problem *p, int kind, double delta) { GB_P(p); return p->impl->set_loss(kind, delta); }
 int gb_set_precision(gb_problem *p, const void *P) { GB_P(p); return p->impl->set_precision(P); }
+int gb_problem_structure_array(gb_problem *p, int which, void *out, int64_t *count) {
+  GB_P(p);
+  if (!count) return GB_ERR_INVALID;
+  return p->impl->structure_array(which, out, count);
+}
 int gb_set_fixed(gb_problem *p, const uint8_t *fc, const uint8_t *fp) { GB_P(p); return p->impl->set_fixed(fc, fp); }
 int gb_hessian_structure(const gb_problem *p, int64_t *cp, int64_t *ri, int64_t *off) {
   if (!p || !cp || !ri || !off) return GB_ERR_INVALID;

@@ -59,8 +59,9 @@ constexpr int NPLANES = 12;
 constexpr int COST_TILES = 4; // tiles per CTA of k_cost_tiles
 constexpr int LIN_STR = 19; // staging row stride of k_linearize (18 values; odd stride: conflict-free 64-bit rows)
 constexpr int LIN_PTS = 128 * 3; // staged point coordinates of a tile (<= 128 points)
+constexpr int LIN_CXS = CAMX + 1; // row stride of the staged camera table: odd, so that the rows of different cameras hit different banks
 template <typename T> constexpr int smem_lin_bytes() { // staging, accumulator rows, tile record, camera table, tile points
-  return (TILE * LIN_STR + SLOT_CAP * 18) * (int)sizeof(T) + 16 + REC_BYTES + (SLOT_CAP * CAMX + LIN_PTS) * (int)sizeof(T);
+  return (TILE * LIN_STR + SLOT_CAP * 18) * (int)sizeof(T) + 16 + REC_BYTES + (SLOT_CAP * LIN_CXS + LIN_PTS) * (int)sizeof(T);
 }
 // per-point W row stride: 6 values, padded to 8 in FP32 so that a tile's rows start 16-byte aligned (TMA)
 template <typename T> struct WST { static constexpr int value = sizeof(T) == 4 ? 8 : 6; };
@@ -366,17 +367,16 @@ k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
   // the super-tile's cameras (<= SLOT_CAP rows of the precomputed model terms) and the tile's points live in shared
   // memory: every observation then reads its 24 camera terms and 3 coordinates with LDS instead of a dependent chain of
   // global gathers (ncu of the gather version: long-scoreboard was the top stall, 4.7 cycles per issued instruction)
-  T *cxs = reinterpret_cast<T *>(rec + REC_BYTES);    // [SLOT_CAP*CAMX]
-  T *pxs = cxs + SLOT_CAP * CAMX;                     // [LIN_PTS]
+  T *cxs = reinterpret_cast<T *>(rec + REC_BYTES);    // [SLOT_CAP*LIN_CXS]
+  T *pxs = cxs + SLOT_CAP * LIN_CXS;                  // [LIN_PTS]
   __shared__ double shd[32];
   const int st = blockIdx.x, t = threadIdx.x;
   const int row0 = ds.st_row[st], nslots = ds.st_row[st + 1] - row0;
   for (int i = t; i < nslots * 18; i += TILE) acc[i] = T(0);
   if (!EXT && !RESCALE) {
-    constexpr int VEC = 16 / (int)sizeof(T), ROWV = CAMX / VEC; // 16-byte pieces per camera row
-    for (int i = t; i < nslots * ROWV; i += TILE) {
-      const int cs = i / ROWV, k = i - cs * ROWV;
-      reinterpret_cast<uint4 *>(cxs)[i] = __ldg(reinterpret_cast<const uint4 *>(cams + (int64_t)ds.row_cam[row0 + cs] * CAMX) + k);
+    for (int i = t; i < nslots * CAMX; i += TILE) {
+      const int cs = i / CAMX, k = i - cs * CAMX;
+      cxs[cs * LIN_CXS + k] = __ldg(cams + (int64_t)ds.row_cam[row0 + cs] * CAMX + k);
     }
     // the first tile's point coordinates (a tile owns a contiguous range of <= 128 points); the following tiles' are
     // fetched during the reduction phases of the tile before them
@@ -451,7 +451,7 @@ k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
         for (int j = 0; j < 6; j++) B.Jp[j] = ep[j];
       } else {
         T X[3], ob[2];
-        const T *cx = cxs + (int)(om >> 16) * CAMX; // `cams` is the per-camera precomputed table (k_cam_precompute)
+        const T *cx = cxs + (int)(om >> 16) * LIN_CXS; // `cams` is the per-camera precomputed table (k_cam_precompute)
         X[0] = pxs[3 * ptl];
         X[1] = pxs[3 * ptl + 1];
         X[2] = pxs[3 * ptl + 2];

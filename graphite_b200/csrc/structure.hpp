@@ -21,6 +21,8 @@
 //   per tile    segment table (begin:16 | cslot:16) and point offset table.
 #pragma once
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -90,6 +92,9 @@ struct HostStructure {
   std::vector<int32_t> cam_ch_ptr;              // [Nc+1] camera -> its contiguous chunk rows
   // per sorted observation (tests / host view): rank in tile order and camera segment count
   std::vector<uint8_t> rank;
+  std::vector<int32_t> tile_ncam;               // [ntiles] distinct cameras (= camera segments) of each tile
+  std::vector<int32_t> tile_st;                 // [ntiles] super-tile of each tile
+  bool tables_on_device = false;
   int32_t max_track = 0;
   int64_t nseg_total = 0;
 
@@ -119,8 +124,19 @@ struct HostStructure {
   }
 
   // returns an empty string on success, else the reason
+  // device_tables = true: the observation-sized tables (ometa, trec contents, tile_cam, slot_of_obs, cm_slot, cm_pt) are
+  // left to the kernels of structure_device.cuh; the host only makes the cuts (tiles, super-tiles, rows, chunks)
   std::string build(int64_t nc, int64_t np, int64_t m, const int32_t *ci, const int32_t *pi, int tile_size,
-                    int slot_cap_opt = 0, int64_t st_obs_opt = 0, bool partition = false) {
+                    int slot_cap_opt = 0, int64_t st_obs_opt = 0, bool partition = false, bool device_tables = false) {
+    // GB_STRUCT_TIMING=1: phase times of the build on stderr (profiles/README.md, "structure build")
+    const bool timing = getenv("GB_STRUCT_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+      if (!timing) return;
+      const auto now = std::chrono::steady_clock::now();
+      fprintf(stderr, "[structure] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+      t_last = now;
+    };
     if (nc <= 0 || np <= 0 || m <= 0) return "empty problem";
     if (m >= (int64_t(1) << 30) || nc + np >= (int64_t(1) << 31)) return "problem too large for 32-bit indices";
     if (tile_size <= 0) tile_size = TILE;
@@ -161,6 +177,7 @@ struct HostStructure {
         if (pt_idx[i] == pt_idx[i - 1] && cam_idx[i] == cam_idx[i - 1])
           return "duplicate (camera, point) observations are not supported";
     }
+    lap("copy / order check / sort");
     pptr.assign((size_t)np + 1, 0);
     for (int64_t i = 0; i < m; i++) pptr[pt_idx[i] + 1]++;
     max_track = 0;
@@ -177,8 +194,9 @@ struct HostStructure {
       for (int64_t c = 0; c < nc; c++)
         if (!seen[c]) return "a camera has no observation (unused vertices are not supported)";
     }
+    lap("point CSR / unused checks");
     // ---- tiles of whole points ----------------------------------------------------------------------
-    tile_obs.clear(); tile_pt.clear();
+    tile_obs.clear(); tile_pt.clear(); tile_ncam.clear();
     tile_obs.push_back(0); tile_pt.push_back(0);
     int32_t cur = 0, ncam_tile = 0;
     std::vector<int32_t> tstamp((size_t)nc, -1);
@@ -190,6 +208,7 @@ struct HostStructure {
       for (int32_t o = pptr[p]; o < pptr[p + 1]; o++) add += tstamp[cam_idx[o]] != tid;
       if (cur + t > tile_fill || p - tile_pt.back() >= TILE_PTS || ncam_tile + add > slot_cap) {
         tile_obs.push_back(pptr[p]); tile_pt.push_back(p);
+        tile_ncam.push_back(ncam_tile);
         cur = 0; ncam_tile = 0;
       }
       const int32_t tid2 = (int32_t)tile_pt.size() - 1;
@@ -198,14 +217,16 @@ struct HostStructure {
       cur += t;
     }
     tile_obs.push_back((int32_t)m); tile_pt.push_back(Np);
+    tile_ncam.push_back(ncam_tile);
     const int32_t nt = (int32_t)tile_obs.size() - 1;
     Mstore = (int64_t)nt * TILE;
     if (Mstore >= (int64_t(1) << 31)) return "problem too large for 32-bit slot indices";
+    lap("tiles");
     // ---- super-tiles: consecutive tiles, bounded observation count and distinct cameras ----------------
-    std::vector<int32_t> stamp((size_t)nc, -1), local((size_t)nc, 0);
-    int32_t stamp_base = 0;
     auto partition_tiles = [&](int64_t st_obs, std::vector<int32_t> &o_tile, std::vector<int32_t> &o_row,
-                               std::vector<int32_t> &o_cam) -> bool {
+                               std::vector<int32_t> &o_cam) -> bool { // re-entrant: the candidate lengths run concurrently
+      std::vector<int32_t> stamp((size_t)nc, -1);
+      const int32_t stamp_base = 0;
       o_tile.clear(); o_row.clear(); o_cam.clear();
       int32_t k = 0;
       while (k < nt) {
@@ -232,7 +253,6 @@ struct HostStructure {
         std::sort(cams_here.begin(), cams_here.end());
         o_cam.insert(o_cam.end(), cams_here.begin(), cams_here.end());
       }
-      stamp_base += (int32_t)o_tile.size() + 1;
       o_tile.push_back(nt);
       o_row.push_back((int32_t)o_cam.size());
       return true;
@@ -252,25 +272,53 @@ struct HostStructure {
         if (!partition_tiles(1, st_tile, st_row, row_cam)) return "a tile touches more cameras than the slot cap";
       } else {
         const int w0 = std::min(8, std::max(2, (int)((nt + 6 * sm_count) / (12 * sm_count))));
+        // the (up to three) candidate lengths are independent greedy scans: one host thread each
+        struct Trial { int w; int64_t target; std::vector<int32_t> t_tile, t_row, t_cam; bool ok = true; };
+        std::vector<Trial> trials;
         for (int w = std::max(2, w0 - 1); w <= w0 + 1; w++) {
-          const int64_t target = std::max<int64_t>(TILE, (m + (int64_t)sm_count * w - 1) / ((int64_t)sm_count * w));
-          if (!partition_tiles(target, t_tile, t_row, t_cam)) return "a tile touches more cameras than the slot cap";
-          const int64_t n = (int64_t)t_tile.size() - 1;
+          Trial tr;
+          tr.w = w;
+          tr.target = std::max<int64_t>(TILE, (m + (int64_t)sm_count * w - 1) / ((int64_t)sm_count * w));
+          trials.push_back(std::move(tr));
+          if (trials.back().target == TILE) break;
+        }
+        {
+          std::vector<std::thread> th;
+          for (auto &tr : trials) {
+            Trial *tp = &tr;
+            th.emplace_back([&, tp]() { tp->ok = partition_tiles(tp->target, tp->t_tile, tp->t_row, tp->t_cam); });
+          }
+          for (auto &t : th) t.join();
+        }
+        for (auto &tr : trials) {
+          if (!tr.ok) return "a tile touches more cameras than the slot cap";
+          const int64_t n = (int64_t)tr.t_tile.size() - 1;
           double eff = (double)n / (double)(((n + sm_count - 1) / sm_count) * sm_count);
-          if (w == w0) eff += 0.02; // prefer the target length unless a neighbour fills its last wave clearly better
-          if (eff > best + 1e-9) { best = eff; st_tile = t_tile; st_row = t_row; row_cam = t_cam; }
-          if (target == TILE) break;
+          if (tr.w == w0) eff += 0.02; // prefer the target length unless a neighbour fills its last wave clearly better
+          if (eff > best + 1e-9) { best = eff; st_tile = tr.t_tile; st_row = tr.t_row; row_cam = tr.t_cam; }
         }
       }
     }
     const int32_t nst = (int32_t)st_tile.size() - 1;
+    lap("super-tiles");
     // ---- per-tile tables ----------------------------------------------------------------------------------
+    tables_on_device = device_tables;
     tmeta.assign((size_t)nt, TileMeta{});
+    tile_st.assign((size_t)nt, 0);
+    for (int32_t s = 0; s < nst; s++)
+      for (int32_t k = st_tile[s]; k < st_tile[s + 1]; k++) tile_st[k] = s;
+    for (int32_t k = 0; k < nt; k++) {
+      TileMeta &tm = tmeta[k];
+      tm.p0 = tile_pt[k]; tm.n = tile_obs[k + 1] - tile_obs[k]; tm.np = tile_pt[k + 1] - tile_pt[k];
+      tm.nseg = tile_ncam[k]; tm.o0 = tile_obs[k]; tm.pad = 0;
+    }
+    seg_tab.clear(); pt_tab.clear(); // compact copies of the tables are materialised on demand (materialize_tables)
+    ometa.clear(); rank.clear(); slot_of_obs.clear(); tile_cam.clear(); trec.clear();
+    if (!device_tables) {
     ometa.assign((size_t)Mstore, 0u);
     rank.resize((size_t)m);
     slot_of_obs.resize(m);
     tile_cam.assign((size_t)Mstore, 0);
-    seg_tab.clear(); pt_tab.clear(); // compact copies of the tables are materialised on demand (materialize_tables)
     trec.assign((size_t)nt * REC_BYTES, 0);
     // Per-tile tables, written straight into the packed records.  Super-tiles are independent: host threads take
     // contiguous ranges of them.  Inside a tile the observations are put in (camera, observation) order by a counting
@@ -324,6 +372,8 @@ struct HostStructure {
         }
       }
     });
+    } // !device_tables
+    lap("per-tile tables");
     // offsets of the compact tables (multiples of 4 / 8 entries per tile) and the tile meta inside the records
     nseg_total = 0;
     {
@@ -334,7 +384,7 @@ struct HostStructure {
         seg_off += (tm.nseg + 1 + 3) / 4 * 4;
         pt_off += (tm.np + 1 + 7) / 8 * 8;
         nseg_total += tm.nseg;
-        memcpy(trec.data() + (size_t)k * REC_BYTES + REC_META, &tm, sizeof(TileMeta));
+        if (!device_tables) memcpy(trec.data() + (size_t)k * REC_BYTES + REC_META, &tm, sizeof(TileMeta));
       }
     }
     // ---- camera -> partial rows, ascending super-tile order ------------------------------------------------
@@ -368,6 +418,7 @@ struct HostStructure {
         r[STREC_OUT / 4 + q] = row_out[st_row[s2] + q];
       }
     }
+    lap("rows / super-tile records");
     // ---- camera-major view: counting sort by camera (stable: ascending point order inside a camera) ---------
     {
       // stable counting sort by camera on the host threads: per-thread histograms over contiguous observation ranges
@@ -386,15 +437,18 @@ struct HostStructure {
         }
         cptr[nc] = run;
       }
-      cm_slot.resize(m); cm_pt.resize(m);
-      parallel_indexed(m, nth, [&](int i, int64_t ob, int64_t oe) {
-        int32_t *h = hist[i].data();
-        for (int64_t o = ob; o < oe; o++) {
-          const int32_t pos = h[cam_idx[o]]++;
-          cm_slot[pos] = slot_of_obs[o];
-          cm_pt[pos] = pt_idx[o];
-        }
-      });
+      cm_slot.clear(); cm_pt.clear();
+      if (!device_tables) {
+        cm_slot.resize(m); cm_pt.resize(m);
+        parallel_indexed(m, nth, [&](int i, int64_t ob, int64_t oe) {
+          int32_t *h = hist[i].data();
+          for (int64_t o = ob; o < oe; o++) {
+            const int32_t pos = h[cam_idx[o]]++;
+            cm_slot[pos] = slot_of_obs[o];
+            cm_pt[pos] = pt_idx[o];
+          }
+        });
+      }
       ch_ptr.assign(1, 0);
       cam_ch_ptr.assign((size_t)nc + 1, 0);
       for (int64_t c = 0; c < nc; c++) {
@@ -405,6 +459,7 @@ struct HostStructure {
         cam_ch_ptr[c + 1] = cam_ch_ptr[c] + nch;
       }
     }
+    lap("camera-major view");
     // persistent CTAs: contiguous super-tile ranges with near-equal tile counts
     {
       const int32_t ncta = std::min<int32_t>(nst, persistent_ctas);

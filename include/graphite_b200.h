@@ -77,6 +77,10 @@ typedef struct {
 /* This rank holds a point partition: cameras without a local observation are legal (their sums come from the
  * other ranks through the all-reduce).  Without the flag such a camera is an unused vertex and is rejected. */
 #define GB_FLAG_PARTITION 1
+/* Build the observation-sized structure tables on the host threads instead of the GPU (the default: per-tile records, slot
+ * order, camera-major view by the kernels of csrc/structure_device.cuh; only the greedy cuts stay on the host).  Both give
+ * bit-identical arrays; the flag exists for the A/B test and for timing. */
+#define GB_FLAG_HOST_TABLES 2
 
 /* Replaces: Graph::initialize_optimization + build_structure (graph.hpp:92-219),
  * FactorDescriptor::initialize_device_ids (factor.hpp:455-467), Hessian::build_structure
@@ -97,6 +101,9 @@ int gb_structure_create(const gb_problem_desc *desc, gb_structure **out, char *e
 int gb_structure_destroy(gb_structure *s);
 int gb_structure_info(const gb_structure *s, int64_t info[12]);
 int gb_structure_array(const gb_structure *s, int which, void *out, int64_t *count);
+/* the same arrays as they are ON THE DEVICE of a problem (built by the GPU unless GB_FLAG_HOST_TABLES): which = 10
+ * slot_of_obs, 13 ometa, 17 packed tile records (bytes), 18 tile_cam, 19 cm_slot, 20 cm_pt (17-20 also answer above) */
+int gb_problem_structure_array(gb_problem *p, int which, void *out, int64_t *count);
 int gb_structure_hessian(const gb_structure *s, int64_t *colptr, int64_t *rowidx, int64_t *offsets);
 int gb_structure_schur(const gb_structure *s, int64_t *colptr, int64_t *rowidx, int64_t *nnz_blocks); /* see gb_schur_structure */
 
