@@ -315,7 +315,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
                                         SchurSmem2<T, S>::TOTAL));
       GB_CUDA(ctx, cudaFuncSetAttribute(k_pcg_solve<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, SolveSmem<T, S>::TOTAL));
       GB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_update<T>, 288, 0));
-      GB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_solve, k_pcg_solve<T, S>, SOLVE_THREADS,
+      GB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_solve, k_pcg_solve<T, S>, SolveSmem<T, S>::THREADS,
                                                                  SolveSmem<T, S>::TOTAL));
       if (!coop || per_sm_solve < 1 || (int64_t)per_sm * sms < (Nc + PCG_CAMS - 1) / PCG_CAMS)
         return ctx->fail(GB_ERR_UNSUPPORTED, "the device cannot co-schedule the PCG kernels (cooperative launch)");
@@ -1089,7 +1089,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
                       (void *)&c_bS, (void *)&x, (void *)&xbak, (void *)&r, (void *)&z, (void *)&pbuf, (void *)&part9,
                       (void *)&st_dot, (void *)&cta_red, (void *)&stp, (void *)&work_counter, (void *)&tol_, (void *)&ratio_,
                       (void *)&mi, (void *)&pp, (void *)&multi, (void *)&tim};
-      GB_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)k_pcg_solve<T, S>, dim3(solve_grid), dim3(SOLVE_THREADS), args,
+      GB_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)k_pcg_solve<T, S>, dim3(solve_grid), dim3(SolveSmem<T, S>::THREADS), args,
                                                SolveSmem<T, S>::TOTAL, st));
       GB_LAUNCH(ctx);
       GB_TRY(store_host(h_state, pcg_state, sizeof(PcgState<T>)));

@@ -914,20 +914,22 @@ k_cam_reduce_prepare(DevStruct ds, const T *__restrict__ part, int from_sums, T 
 // of the direction (u_p, stride WST), y = Jc u_c + Jp u_p, the point sums sum_o Jp^T y go straight to out_p, and the
 // camera rows accumulate Jc^T y.
 // ---------------------------------------------------------------------------------------------
-template <typename T, typename S> struct SchurSmem2 {
+// NW = workers per CTA (256 threads each).  Two in general; three for (float, float), where the halved Jacobian slots and
+// staging leave room and the kernel is bound by per-tile latency, not bytes.
+template <typename T, typename S, int NW = 2> struct SchurSmem2 {
   static constexpr int J_BYTES = NPLANES * TILE * (int)sizeof(typename V2<S>::type);
   static constexpr int W_BYTES = TILE_PTS * WST<T>::value * (int)sizeof(T);
   static constexpr int META_BYTES = REC_BYTES + W_BYTES;
-  static constexpr int NMETA = 4;
+  static constexpr int NMETA = 2 * NW; // tiles i and i + NMETA belong to the same worker: a parity wait cannot run a phase ahead
   static constexpr int SV_BYTES = TILE * 9 * (int)sizeof(T);      // camera staging (point staging [TILE*3] aliases it)
   static constexpr int SW_BYTES = TILE_PTS * 3 * (int)sizeof(T);  // point sums
   static constexpr int STG_BYTES = SV_BYTES + SW_BYTES;           // per worker
-  static constexpr int META_OFF = 2 * J_BYTES;
+  static constexpr int META_OFF = NW * J_BYTES;
   static constexpr int STG_OFF = META_OFF + NMETA * META_BYTES;
-  static constexpr int XL_OFF = STG_OFF + 2 * STG_BYTES;
+  static constexpr int XL_OFF = STG_OFF + NW * STG_BYTES;
   static constexpr int ACC_OFF = XL_OFF + SLOT_CAP * 9 * (int)sizeof(T);
-  static constexpr int BAR_OFF = ACC_OFF + 2 * SLOT_CAP * 9 * (int)sizeof(T);
-  static constexpr int TOTAL = BAR_OFF + 64;
+  static constexpr int BAR_OFF = ACC_OFF + NW * SLOT_CAP * 9 * (int)sizeof(T);
+  static constexpr int TOTAL = BAR_OFF + 128; // mbarriers: NMETA tile slots + the record buffers of k_pcg_solve
   static_assert(META_BYTES % 16 == 0 && STG_BYTES % 16 == 0, "TMA destinations must stay 16-byte aligned");
 };
 
@@ -936,15 +938,15 @@ template <typename T, typename S> struct SchurSmem2 {
 //   super-tile; acc: the worker's accumulator rows; sv / sw: the worker's staging.
 //   refill(next_p0, next_np) is called by the worker's thread 0 right after the first barrier (the J slot is free):
 //   it issues the bulk copies of the worker's next tile, whose point range comes with the record just consumed.
-template <typename T, typename S, bool FULL, typename Refill>
+template <typename T, typename S, bool FULL, int NW = 2, typename Refill>
 __device__ __forceinline__ void product_tile(int worker, int t, const typename V2<S>::type *Js, const unsigned char *rec,
                                              const T *Ws, const T *xl, T *acc, T *sv, T *sw, T *__restrict__ out_p,
                                              Refill &&refill) {
   using S2 = typename V2<S>::type;
   T *sv3 = sv; // point-order staging: dead before the camera staging is written
   const TileMeta tm = *reinterpret_cast<const TileMeta *>(rec + REC_META);
-  const int next_p0 = reinterpret_cast<const int32_t *>(rec + REC_NEXT)[2];  // tile + 2
-  const int next_np = reinterpret_cast<const int32_t *>(rec + REC_NEXT)[3];
+  const int next_p0 = reinterpret_cast<const int32_t *>(rec + REC_NEXT)[2 * (NW - 1)];  // tile + NW: the worker's next tile
+  const int next_np = reinterpret_cast<const int32_t *>(rec + REC_NEXT)[2 * (NW - 1) + 1];
   const uint32_t om = reinterpret_cast<const uint32_t *>(rec + REC_OMETA)[t];
   const int cslot = (int)(om >> 16), rank = (int)((om >> 8) & 0xffu), ptl = (int)(om & 0xffu);
   T jc[18], jp[6], y0 = T(0), y1 = T(0);
@@ -1033,14 +1035,14 @@ __device__ __forceinline__ void product_tile(int worker, int t, const typename V
 // bulk copies of one tile into ring position i: J slot i & 1 (= its worker), meta slot and mbarrier i & 3.  The J and
 // record copies carry an L2 evict-first policy: the 1 GB stream is read once per pass, the ~70 MB of vectors every
 // pass re-reads then stay in the 126 MB L2 (-4.7 % on the kernel).
-template <typename T, typename S>
+template <typename T, typename S, int NW = 2>
 __device__ __forceinline__ void product_issue(unsigned char *smem, uint64_t *bars, const DevStruct &ds,
                                               const typename V2<S>::type *__restrict__ J, const T *__restrict__ W,
                                               int tile, int i, int p0, int np, uint64_t pol) {
-  using SM = SchurSmem2<T, S>;
-  unsigned char *jdst = smem + (i & 1) * SM::J_BYTES;
-  unsigned char *mdst = smem + SM::META_OFF + (i & 3) * SM::META_BYTES;
-  uint64_t *bar = &bars[i & 3];
+  using SM = SchurSmem2<T, S, NW>;
+  unsigned char *jdst = smem + (i % NW) * SM::J_BYTES;
+  unsigned char *mdst = smem + SM::META_OFF + (i % SM::NMETA) * SM::META_BYTES;
+  uint64_t *bar = &bars[i % SM::NMETA];
   const uint32_t wbytes = (uint32_t)(np * WST<T>::value * (int)sizeof(T));
   mbar_expect_tx(bar, (uint32_t)(SM::J_BYTES + REC_BYTES) + wbytes);
   bulk_g2s_hint(jdst, J + (int64_t)tile * NPLANES * TILE, SM::J_BYTES, bar, pol);

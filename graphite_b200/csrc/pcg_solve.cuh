@@ -30,14 +30,18 @@
 
 namespace gb {
 
-constexpr int SOLVE_THREADS = 2 * TILE, SOLVE_WARPS = SOLVE_THREADS / 32;
+// workers per CTA of the solve kernel: three for (float, float) - 80 registers without spills, 178 KB of shared memory -
+// two otherwise (FP64 staging and Jacobian slots fill the 227 KB with two)
+template <typename T, typename S> struct SolveWorkers { static constexpr int value = (sizeof(T) == 4 && sizeof(S) == 4) ? 3 : 2; };
 constexpr int SOLVE_STAMPS = 8; // per iteration: P start, before A, after A, exchange done, before B, after B, [6] pushed
 
 template <typename T, typename S> struct SolveSmem {
-  using SM = SchurSmem2<T, S>;
+  static constexpr int NW = SolveWorkers<T, S>::value;
+  static constexpr int THREADS = NW * TILE, WARPS = THREADS / 32;
+  using SM = SchurSmem2<T, S, NW>;
   static constexpr int RED_OFF = SM::TOTAL;                       // T[64] reduction scratch
-  static constexpr int WP_OFF = RED_OFF + 64 * (int)sizeof(double); // T[SOLVE_WARPS]
-  static constexpr int CTL_OFF = WP_OFF + SOLVE_WARPS * (int)sizeof(double); // int[8]
+  static constexpr int WP_OFF = RED_OFF + 64 * (int)sizeof(double); // T[WARPS]
+  static constexpr int CTL_OFF = WP_OFF + 32 * (int)sizeof(double); // int[8]
   static constexpr int NREC = 3;                                  // ring of per-super-tile records (current, next, next-next)
   static constexpr int REC_OFF = CTL_OFF + 64;
   static constexpr int TOTAL = REC_OFF + NREC * STREC_BYTES;
@@ -49,7 +53,7 @@ template <typename T, typename S> struct SolveSmem {
 template <typename T> __device__ __forceinline__ T pcg_direction(T beta, T p_old, T z) { return fma(beta, p_old, z); }
 
 // per-warp values (lane 0) -> CTA total -> dst[blockIdx.x]
-template <typename T> __device__ __forceinline__ void solve_publish(T wv, T *wpart, T *dst) {
+template <typename T, int SOLVE_WARPS> __device__ __forceinline__ void solve_publish(T wv, T *wpart, T *dst) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __syncthreads(); // wpart may still be read from the previous use
   if (lane == 0) wpart[warp] = wv;
@@ -63,15 +67,16 @@ template <typename T> __device__ __forceinline__ void solve_publish(T wv, T *wpa
 }
 
 template <typename T, typename S>
-__global__ void __launch_bounds__(SOLVE_THREADS, 1)
+__global__ void __launch_bounds__((SolveSmem<T, S>::THREADS), 1)
 k_pcg_solve(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *__restrict__ W,
             const T *__restrict__ scale_c, const T *__restrict__ dterm, const T *__restrict__ Minv,
             const T *__restrict__ bS, T *x, T *xbak, T *r, T *z, T *pbuf /*[2][9 Nc]*/, T *part /*[nrows][9]*/,
             T *st_dot /*[nst]*/, T *cta_red /*[2][grid]*/, PcgState<T> *st_out, unsigned int *work, T tol, T ratio,
             int max_iter, P2P pp, int multi, unsigned long long *timing /*[max_iter + 1][SOLVE_STAMPS] or null*/) {
   namespace cg = cooperative_groups;
-  using SM = SchurSmem2<T, S>;
   using SS = SolveSmem<T, S>;
+  using SM = typename SS::SM;
+  constexpr int NW = SS::NW, SOLVE_THREADS = SS::THREADS, SOLVE_WARPS = SS::WARPS, NMETA = SM::NMETA;
   using S2 = typename V2<S>::type;
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(128) unsigned char smem[];
@@ -155,7 +160,7 @@ k_pcg_solve(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *_
       if (own) z[i] = a;
       rz_w += sum9<T>(own ? rn * a : T(0));
     }
-    solve_publish<T>(rz_w, wpart, cta_red + G);
+    solve_publish<T, SOLVE_WARPS>(rz_w, wpart, cta_red + G);
   }
   __threadfence();
   grid.sync();
@@ -188,7 +193,7 @@ k_pcg_solve(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *_
         }
         pdp_w += sum9<T>(v);
       }
-      solve_publish<T>(pdp_w, wpart, cta_red);
+      solve_publish<T, SOLVE_WARPS>(pdp_w, wpart, cta_red);
     }
     // ---- the product over the super-tiles the work counter hands out -----------------------------------------------
     // A super-tile boundary costs two CTA barriers and one pass: the rows and the dot of the finished super-tile are
@@ -215,32 +220,32 @@ k_pcg_solve(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *_
         const int n9 = R[3] * 9;
         for (int i = threadIdx.x; i < n9; i += SOLVE_THREADS) {
           build_xl(R + STREC_CAM / 4, i);
-          acc_all[i] = T(0);
-          acc_all[SLOT_CAP * 9 + i] = T(0);
+#pragma unroll
+          for (int w = 0; w < NW; w++) acc_all[w * SLOT_CAP * 9 + i] = T(0);
         }
         __syncthreads();
       }
       while (cur < nst) {
         const int32_t *R = rec_ptr(n_cur);
         const int tile_base = R[0], ie = ib + R[1], n9 = R[3] * 9;
-        for (int i = ib + ((ib ^ worker) & 1); i < ie; i += 2) { // worker w takes ring indices of parity w
+        for (int i = ib + (worker - ib % NW + NW) % NW; i < ie; i += NW) { // worker w takes the ring indices i with i % NW == w
           if (t == 0 && i > my_issued) { // not prefetched (first tiles of an iteration, one-tile super-tiles)
             const int tile = tile_base + (i - ib);
             const int p0 = ds.tmeta[tile].p0, np = ds.tmeta[tile].np;
             fence_proxy_async();
-            product_issue<T, S>(smem, bars, ds, J, W, tile, i, p0, np, pol);
+            product_issue<T, S, NW>(smem, bars, ds, J, W, tile, i, p0, np, pol);
             my_issued = i;
           }
-          mbar_wait(&bars[i & 3], (uint32_t)((i >> 2) & 1));
-          const S2 *Js = reinterpret_cast<const S2 *>(smem + (i & 1) * SM::J_BYTES);
-          const unsigned char *rec = smem + SM::META_OFF + (i & 3) * SM::META_BYTES;
+          mbar_wait(&bars[i % NMETA], (uint32_t)((i / NMETA) & 1));
+          const S2 *Js = reinterpret_cast<const S2 *>(smem + (i % NW) * SM::J_BYTES);
+          const unsigned char *rec = smem + SM::META_OFF + (i % NMETA) * SM::META_BYTES;
           const T *Ws = reinterpret_cast<const T *>(rec + REC_BYTES);
-          product_tile<T, S, false>(worker, t, Js, rec, Ws, xl, acc, sv, sw, (T *)nullptr, [&](int next_p0, int next_np) {
-            const int j = i + 2;
+          product_tile<T, S, false, NW>(worker, t, Js, rec, Ws, xl, acc, sv, sw, (T *)nullptr, [&](int next_p0, int next_np) {
+            const int j = i + NW;
             if (j <= my_issued) return;
             if (j < ie) {
               fence_proxy_async();
-              product_issue<T, S>(smem, bars, ds, J, W, tile_base + (j - ib), j, next_p0, next_np, pol);
+              product_issue<T, S, NW>(smem, bars, ds, J, W, tile_base + (j - ib), j, next_p0, next_np, pol);
               my_issued = j;
             } else if (nxt < nst) { // first tiles of the NEXT super-tile: the ring runs across the boundary
               rec_wait(n_cur + 1);
@@ -249,7 +254,7 @@ k_pcg_solve(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *_
                 const int tile = RN[0] + (j - ie);
                 const int p0 = ds.tmeta[tile].p0, np = ds.tmeta[tile].np;
                 fence_proxy_async();
-                product_issue<T, S>(smem, bars, ds, J, W, tile, j, p0, np, pol);
+                product_issue<T, S, NW>(smem, bars, ds, J, W, tile, j, p0, np, pol);
                 my_issued = j;
               }
             }
@@ -284,14 +289,16 @@ k_pcg_solve(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *_
         for (int i = threadIdx.x; i < max(n9, m9); i += SOLVE_THREADS) {
           if (i < n9) {
             const int sl = i / 9, kk = i - 9 * sl;
-            const T v = acc_all[i] + acc_all[SLOT_CAP * 9 + i];
+            T v = acc_all[i] + acc_all[SLOT_CAP * 9 + i]; // the workers' rows in worker order
+#pragma unroll
+            for (int w = 2; w < NW; w++) v += acc_all[w * SLOT_CAP * 9 + i];
             part[(int64_t)out[sl] * 9 + kk] = v;
             d += xl[i] * v;
           }
           if (i < m9) {
             build_xl(RN + STREC_CAM / 4, i);
-            acc_all[i] = T(0);
-            acc_all[SLOT_CAP * 9 + i] = T(0);
+#pragma unroll
+            for (int w = 0; w < NW; w++) acc_all[w * SLOT_CAP * 9 + i] = T(0);
           }
         }
 #pragma unroll
@@ -399,7 +406,7 @@ k_pcg_solve(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *_
       if (threadIdx.x == 0) grab_first(k + 1);
       pregrabbed = true;
     }
-    solve_publish<T>(rz_w, wpart, cta_red + G);
+    solve_publish<T, SOLVE_WARPS>(rz_w, wpart, cta_red + G);
     if (timing && leader) timing[k * SOLVE_STAMPS + 4] = global_timer_ns();
     __threadfence();
     grid.sync(); // ---- barrier B: z and the r.z partials are visible --------------------------------------------------
