@@ -562,6 +562,10 @@ struct GraphBase {
   virtual int set_damping(double, int) = 0;
   virtual int solve(const gb_pcg_options *, void *, gb_solve_info *) = 0;
   virtual int lm(const gb_lm_options *, gb_lm_result *, double *) = 0;
+  virtual int bind_linearization(int, const void *const *, const void *, const void *) = 0;
+  virtual int bind_gradient(const void *) = 0;
+  virtual int update_values() = 0;
+  virtual int solve_device(const gb_pcg_options *, void *, gb_solve_info *) = 0;
 };
 
 template <typename T, typename S> struct Graph : GraphBase {
@@ -597,6 +601,9 @@ template <typename T, typename S> struct Graph : GraphBase {
     S *J[GB_MAX_ARITY] = {nullptr, nullptr, nullptr, nullptr};
     T *Jt[GB_MAX_ARITY] = {nullptr, nullptr, nullptr, nullptr}; // the caller's T output when S != T
     long long roff = 0;
+    // a caller-owned linearisation bound in place of the library's buffers (gb_graph_bind_linearization); null = own
+    const S *bound_J[GB_MAX_ARITY] = {nullptr, nullptr, nullptr, nullptr};
+    const S *bound_dL = nullptr, *bound_P = nullptr;
   };
   std::vector<VSetH> V;
   std::vector<FSetH> F;
@@ -617,6 +624,8 @@ template <typename T, typename S> struct Graph : GraphBase {
   T *b = nullptr, *scales = nullptr, *cdiag = nullptr, *x = nullptr, *xb = nullptr, *r = nullptr, *z = nullptr, *p = nullptr,
     *v1 = nullptr, *v2 = nullptr, *partial = nullptr, *scal = nullptr, *tmpH = nullptr;
   PcgState *state_d = nullptr;
+  const T *b_bound = nullptr; // caller-owned gradient (gb_graph_bind_gradient)
+  bool bound = false;         // the linearisation is the caller's: gb_graph_linearize / gb_graph_lm are not available
   double *h_pin = nullptr; // pinned: [0] chi2 [1] rho denominator; PcgState after it
   double mu = 0;
   int use_identity = 0;
@@ -805,7 +814,7 @@ template <typename T, typename S> struct Graph : GraphBase {
     for (int s = 0; s < f.d.arity; s++) {
       d.d[s] = V[f.d.vertex_set[s]].d.dimension;
       d.vset[s] = f.d.vertex_set[s];
-      d.J[s] = f.J[s];
+      d.J[s] = f.bound_J[s] ? const_cast<S *>(f.bound_J[s]) : f.J[s];
     }
     d.count = f.d.count;
     d.nactive = (long long)f.active_idx.size();
@@ -814,8 +823,8 @@ template <typename T, typename S> struct Graph : GraphBase {
     d.active_idx = f.active_idx_d;
     d.r = f.r;
     d.chi2 = f.chi2;
-    d.dL = f.dL;
-    d.P = f.P;
+    d.dL = f.bound_dL ? const_cast<S *>(f.bound_dL) : f.dL;
+    d.P = f.bound_P ? const_cast<S *>(f.bound_P) : f.P;
     return d;
   }
   DVSet<T> make_dvset(const VSetH &v) const {
@@ -1160,6 +1169,7 @@ template <typename T, typename S> struct Graph : GraphBase {
     return GB_OK;
   }
   int linearize(double *chi2) override {
+    GB_TRY(require(!bound, "a caller-owned linearisation is bound: unbind it (gb_graph_bind_linearization with NULL) first"));
     GB_TRY(check_ready());
     GB_TRY(enqueue_linearize());
     GB_TRY(read_scalars(1));
@@ -1273,7 +1283,7 @@ template <typename T, typename S> struct Graph : GraphBase {
     A.dimH = dimH; A.rows = rows; A.nf = (int)F.size(); A.nv = (int)V.size();
     A.max_iter = (int)o->max_iterations; A.use_identity = use_identity;
     A.mu = (T)mu; A.tol = (T)o->tolerance; A.ratio = (T)o->rejection_ratio;
-    A.b = b; A.cdiag = cdiag; A.x = x; A.xb = xb; A.r = r; A.z = z; A.p = p; A.v1 = v1; A.v2 = v2;
+    A.b = b_bound ? b_bound : b; A.cdiag = cdiag; A.x = x; A.xb = xb; A.r = r; A.z = z; A.p = p; A.v1 = v1; A.v2 = v2;
     A.partial = partial; A.colmap = colmap_d; A.state = state_d;
     const long long work = std::max<long long>(dimH, nactive_total * GB_MAX_RESIDUAL / 2);
     int blocks = (int)std::min<long long>((work + 255) / 256, (long long)nsm * coop_blocks_per_sm);
@@ -1337,7 +1347,73 @@ template <typename T, typename S> struct Graph : GraphBase {
     return GB_OK;
   }
 
+  // ---- Solver<T,S> plug-in mode: the CALLER linearises (Graphite's own Graph::linearize through the user's traits); its
+  //      device buffers are used in place: stored (scaled) Jacobians, loss derivatives, precision matrices, gradient ----
+  int bind_linearization(int fsi, const void *const *jac, const void *dl, const void *prec) override {
+    GB_TRY(require(initialized, "graph is not initialised (gb_graph_initialize)"));
+    GB_TRY(require(fsi >= 0 && fsi < (int)F.size(), "unknown factor set"));
+    FSetH &f = F[fsi];
+    if (!jac) { // unbind
+      for (int s = 0; s < GB_MAX_ARITY; s++) f.bound_J[s] = nullptr;
+      f.bound_dL = f.bound_P = nullptr;
+    } else {
+      GB_TRY(require(dl != nullptr, "loss derivatives missing"));
+      for (int s = 0; s < f.d.arity; s++) {
+        GB_TRY(require(jac[s] != nullptr, "Jacobian pointer missing"));
+        f.bound_J[s] = (const S *)jac[s];
+      }
+      f.bound_dL = (const S *)dl;
+      f.bound_P = (const S *)prec; // null: the set's own precision matrices
+    }
+    bound = false;
+    for (auto &g : F) bound = bound || g.bound_dL != nullptr;
+    linearized = damped = solved = false;
+    return upload_tables();
+  }
+  int bind_gradient(const void *bd) override {
+    b_bound = (const T *)bd;
+    solved = false;
+    return GB_OK;
+  }
+  // Solver::update_values: block diagonals of the preconditioner and the clamped scalar diagonal from the bound Jacobians
+  int update_values() override {
+    GB_TRY(require(initialized && bound, "gb_graph_update_values needs a bound linearisation"));
+    for (auto &f : F) GB_TRY(require(f.bound_dL != nullptr || f.active_idx.empty(), "every active factor set needs a bound linearisation"));
+    GB_TRY(require(b_bound != nullptr, "gradient missing (gb_graph_bind_gradient)"));
+    cudaStream_t st = ctx->stream;
+    for (size_t i = 0; i < V.size(); i++) {
+      const long long n = V[i].d.count * V[i].d.dimension * V[i].d.dimension;
+      if (n == 0) continue;
+      k_g_blockdiag<T, S, IP><<<grid_for(n), 256, 0, st>>>(fs_d, vs_d, (int)i);
+      GB_TRY(launched());
+    }
+    k_g_columns<T, S, 0><<<grid_for(dimH), 256, 0, st>>>(fs_d, vs_d, colmap_d, dimH, nullptr, tmpH, 0);
+    GB_TRY(launched());
+    k_g_clamp<T><<<grid_for(dimH), 256, 0, st>>>(dimH, tmpH, cdiag, (T)1.0e-6, (T)1.0e32);
+    GB_TRY(launched());
+    linearized = true;
+    damped = solved = false;
+    return GB_OK;
+  }
+  int solve_device(const gb_pcg_options *o, void *delta_dev, gb_solve_info *info) override {
+    GB_TRY(require(initialized && linearized && delta_dev, "gb_graph_solve_device needs a linearised graph"));
+    GB_TRY(check_pcg(o));
+    GB_TRY(enqueue_damping());
+    GB_TRY(enqueue_pcg(o));
+    GB_CUDA(ctx, cudaMemcpyAsync(delta_dev, x, (size_t)dimH * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+    PcgState stt{};
+    GB_TRY(d2h(&stt, state_d, sizeof(PcgState)));
+    if (info) {
+      info->pcg_iterations = stt.iterations;
+      info->rz_final = stt.rz_final;
+      info->stop_reason = stt.stop_reason;
+      info->schur_mode = 0;
+    }
+    return GB_OK;
+  }
+
   int lm(const gb_lm_options *o, gb_lm_result *res_out, double *traj) override {
+    GB_TRY(require(!bound, "a caller-owned linearisation is bound: the caller drives the LM loop"));
     GB_TRY(check_ready());
     GB_TRY(require(o && o->iterations >= 0, "bad LM options"));
     GB_TRY(check_pcg(&o->pcg));
@@ -1481,5 +1557,12 @@ int gb_graph_jtpv(gb_graph *g, const void *v, void *y) { GG(g); return g->impl->
 int gb_graph_set_damping(gb_graph *g, double mu, int ident) { GG(g); return g->impl->set_damping(mu, ident); }
 int gb_graph_solve(gb_graph *g, const gb_pcg_options *o, void *d, gb_solve_info *i) { GG(g); return g->impl->solve(o, d, i); }
 int gb_graph_lm(gb_graph *g, const gb_lm_options *o, gb_lm_result *r, double *t) { GG(g); return g->impl->lm(o, r, t); }
+int gb_graph_bind_linearization(gb_graph *g, int fs, const void *const *jac, const void *dl, const void *prec) {
+  GG(g);
+  return g->impl->bind_linearization(fs, jac, dl, prec);
+}
+int gb_graph_bind_gradient(gb_graph *g, const void *b) { GG(g); return g->impl->bind_gradient(b); }
+int gb_graph_update_values(gb_graph *g) { GG(g); return g->impl->update_values(); }
+int gb_graph_solve_device(gb_graph *g, const gb_pcg_options *o, void *d, gb_solve_info *i) { GG(g); return g->impl->solve_device(o, d, i); }
 
 } // extern "C"

@@ -21,6 +21,7 @@ SYMBOLS = [
     "gb_graph_set_precision", "gb_graph_set_loss", "gb_graph_set_scaling", "gb_graph_initialize", "gb_graph_vertex_columns",
     "gb_graph_hessian_structure", "gb_graph_linearize", "gb_graph_cost", "gb_graph_get", "gb_graph_hessian_values",
     "gb_graph_jv", "gb_graph_jtpv", "gb_graph_set_damping", "gb_graph_solve", "gb_graph_lm",
+    "gb_graph_bind_linearization", "gb_graph_bind_gradient", "gb_graph_update_values", "gb_graph_solve_device",
 ]
 
 

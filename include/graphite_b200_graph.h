@@ -146,6 +146,22 @@ int gb_graph_solve(gb_graph *g, const gb_pcg_options *opt, void *delta_host, gb_
  * trajectory layout as gb_lm (the Schur-only fields are ignored). */
 int gb_graph_lm(gb_graph *g, const gb_lm_options *opt, gb_lm_result *result, double *trajectory);
 
+/* ---- Solver<T,S> plug-in mode (solver/solver.hpp:12-25): Graphite keeps linearising through the user's traits
+ * (Graph::linearize, graph.hpp:236-290); the library solves on Graphite's OWN device buffers, used in place.
+ *   gb_graph_bind_linearization  per factor set: jacobians_dev[slot] = FactorDescriptor::jacobians[slot].data (E x d
+ *       column-major per factor, element type S, Jacobi-scaled by scale_jacobians_async), loss_derivative_dev =
+ *       chi2_derivative [count] (S), precision_dev = precision_matrices [count][E*E] (S; NULL = the set's own).
+ *       jacobians_dev = NULL unbinds.  Factor callbacks are never called while a linearisation is bound.
+ *   gb_graph_bind_gradient       b = Graph::get_b() [hessian_dim] (T), the right-hand side of the solve
+ *   gb_graph_update_values       Solver::update_values: the block-Jacobi blocks from the bound Jacobians
+ *   gb_graph_solve_device        bool Solver::solve(Graph*, T *delta_x, StreamPool&): the scaled-space step into DEVICE
+ *                                memory; synchronises the context stream before returning */
+int gb_graph_bind_linearization(gb_graph *g, int factor_set, const void *const *jacobians_dev, const void *loss_derivative_dev,
+                                const void *precision_dev);
+int gb_graph_bind_gradient(gb_graph *g, const void *b_dev);
+int gb_graph_update_values(gb_graph *g);
+int gb_graph_solve_device(gb_graph *g, const gb_pcg_options *opt, void *delta_dev, gb_solve_info *info);
+
 #ifdef __cplusplus
 }
 #endif
