@@ -434,6 +434,12 @@ def host_structure(cam_idx, pt_idx, n_cams: int, n_pts: int, tile_size: int = 0,
             a = np.empty(n.value, dtype=_STRUCT_DTYPES.get(name, np.int32))
             L.gb_structure_array(h, i, _ptr(a), C.byref(n))
             out[name] = a.reshape(-1, 8) if name == "tmeta" else a
+        for i, name in ((21, "frag_tile"), (22, "hv_pt"), (23, "hv_ptr")):  # long tracks
+            n = C.c_int64()
+            L.gb_structure_array(h, i, None, C.byref(n))
+            a = np.empty(n.value, dtype=np.int32)
+            L.gb_structure_array(h, i, _ptr(a), C.byref(n))
+            out[name] = a
         info = (C.c_int64 * 12)()
         L.gb_structure_info(h, info)
         out["info"] = dict(zip(INFO_KEYS, [int(v) for v in info]))

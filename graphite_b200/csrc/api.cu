@@ -256,6 +256,14 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_TRY(upload(ts.cam_idx, hs.cam_idx));
     GB_TRY(upload(ts.pt_idx, hs.pt_idx));
     GB_TRY(upload(ts.pptr, hs.pptr));
+    // long tracks: fragment tables and the two-level sum buffers (structure.hpp, kernels.cuh "long tracks")
+    ts.nfrag = hs.nfrag(); ts.nheavy = hs.nheavy();
+    GB_TRY(upload(ts.hv_pt, hs.hv_pt)); GB_TRY(upload(ts.hv_ptr, hs.hv_ptr));
+    {
+      T *fp = nullptr, *ft = nullptr;
+      GB_TRY(dalloc(fp, 9 * (size_t)ts.nfrag)); GB_TRY(dalloc(ft, 3 * (size_t)ts.nfrag));
+      ts.frag_part = fp; ts.frag_t = ft;
+    }
     if (hs.tables_on_device) {
       // the observation-sized tables are built here, on the device (structure_device.cuh); the host made the cuts only
       const int32_t *d_tile_obs = nullptr, *d_tile_pt = nullptr, *d_tile_st = nullptr;
@@ -699,6 +707,23 @@ template <typename T, typename S> struct Problem : ProblemBase {
     return GB_OK;
   }
 
+  // long tracks: add the fragments' partial sums of `width` values per point into out[Np][width] (after k_linearize and
+  // the full-system product) / form t_p = sum_o Jp^T Jc x_c of the long-track points from xs (before the Schur product
+  // and the back-substitution)
+  int enqueue_frag_sum(int width, T *out) {
+    if (ts.nheavy == 0) return GB_OK;
+    k_frag_sum<T><<<(ts.nheavy * width + 127) / 128, 128, 0, ctx->stream>>>(ts.nheavy, ts.hv_pt, ts.hv_ptr,
+                                                                          reinterpret_cast<const T *>(ts.frag_part), width, out);
+    GB_LAUNCH(ctx);
+    return GB_OK;
+  }
+  int enqueue_frag_dots(const int *flag) {
+    if (ts.nheavy == 0) return GB_OK;
+    k_frag_dots<T, S><<<ts.nheavy, 256, 0, ctx->stream>>>(ts, J, xs, flag);
+    GB_LAUNCH(ctx);
+    return GB_OK;
+  }
+
   int ensure_camx() {
     if (camx_valid) return GB_OK;
     k_cam_precompute<T><<<(ts.Nc + 127) / 128, 128, 0, ctx->stream>>>(ts.Nc, cams, camx);
@@ -727,6 +752,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
       k_linearize<T, S, false><<<ts.nst, TILE, smem_lin_bytes<T>(), st>>>(ts, camx, pts, obs, J, res, Cg, part18, cost_part, rb, ex);
     }
     GB_LAUNCH(ctx);
+    GB_TRY(enqueue_frag_sum(9, Cg));
     // pre-scaled storage: this first pass only yields the rounded Jacobians and, from them, the true Jacobi scales
     const int son = prescaled ? (scale_on ? 1 : 0) : alg_scale();
     k_cam_reduce_lin<T><<<ts.Nc, 288, 0, st>>>(ts, part18, diagB, gc, multi ? 0 : 1, son, scale, b, fixed_c);
@@ -752,6 +778,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
       ExtFactor rs{nullptr, nullptr, nullptr, nullptr, scale_true};
       k_linearize<T, S, false, true><<<ts.nst, TILE, smem_lin_bytes<T>(), st>>>(ts, camx, pts, obs, J, res, Cg, part18, cost_part, rb, rs);
       GB_LAUNCH(ctx);
+      GB_TRY(enqueue_frag_sum(9, Cg));
       k_cam_reduce_lin<T><<<ts.Nc, 288, 0, st>>>(ts, part18, diagB, gc, 1, 0, scale, b);
       GB_LAUNCH(ctx);
       k_point_prepare<T><<<(ts.Np + 255) / 256, 256, 0, st>>>(ts.Np, 0, mu, use_identity, Cg, scale + dimc, b + dimc, W, h, 1);
@@ -842,7 +869,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
       // v2 = J~^T J~ p + mu clamp(diag) p   (pcg.hpp:141-168)
       k_full_build_u<T><<<full_blocks, 256, 0, st>>>(ts.Nc, ts.Np, f_p, scale, xs, f_upw);
       GB_LAUNCH(ctx);
-      launch_product<true>(f_upw, nullptr, f_outp);
+      GB_TRY(launch_product<true>(f_upw, nullptr, f_outp));
       k_cam_reduce_spmv<T><<<ts.Nc, 288, 0, st>>>(ts, part9, scale, Ap_raw, 0, dterm, nullptr, Ap, dot_part, nullptr, pp, 0);
       GB_LAUNCH(ctx);
       k_full_finish_v2<T><<<full_blocks, 256, 0, st>>>(ts.Nc, ts.Np, mu, use_identity, Ap_raw, f_outp, f_p, scale, diagB, Cg,
@@ -901,9 +928,12 @@ template <typename T, typename S> struct Problem : ProblemBase {
   }
 
   // one launch of the Schur product kernel (exports, full-system solver, NCCL fallback, stage timers)
-  template <bool FULL> void launch_product(const T *Wp, const int *flag, T *outp) {
+  template <bool FULL> int launch_product(const T *Wp, const int *flag, T *outp) {
+    if (!FULL) GB_TRY(enqueue_frag_dots(flag)); // long tracks: their point sums come first
     k_schur_product2<T, S, FULL><<<ts.ncta, 2 * TILE, SchurSmem2<T, S>::TOTAL, ctx->stream>>>(ts, J, Wp, xs, part9, flag, outp);
     GB_LAUNCH(ctx);
+    if (FULL) GB_TRY(enqueue_frag_sum(3, outp)); // ... or are completed afterwards
+    return GB_OK;
   }
   int enqueue_prepare_tiles_only() {
     k_prepare_cams<T, S><<<ts.nchunks, PC_THREADS, 0, ctx->stream>>>(ts, J, W, h, part54);
@@ -942,7 +972,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     cudaStream_t st = ctx->stream;
     const bool multi = ctx->nranks > 1;
     const int finish = (!multi && pvec) ? 1 : 0;
-    launch_product<false>(W, flag, nullptr);
+    GB_TRY(launch_product<false>(W, flag, nullptr));
     k_cam_reduce_spmv<T><<<ts.Nc, 288, 0, st>>>(ts, part9, scale, Ap_raw, finish, dterm, pvec, Ap, dot_part, flag, pp, 0);
     GB_LAUNCH(ctx);
     if (multi) GB_TRY(allreduce_T(Ap_raw, dimc)); // Ap and the dot partials are then formed inside k_pcg_update
@@ -1147,6 +1177,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
                                               apply ? 1 : 0, apply_scale());
     GB_LAUNCH(ctx);
     if (apply) camx_valid = false;
+    GB_TRY(enqueue_frag_dots(nullptr));
     k_backsubst_tiles<T, S><<<ts.ntiles, TILE, 0, st>>>(ts, J, W, xs, h, scale + dimc, b + dimc, mu, pts, pts_bak,
                                                         delta + dimc, rho_part, apply ? 1 : 0, apply_scale() + dimc);
     GB_LAUNCH(ctx);
@@ -1614,7 +1645,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
       case 3: GB_TRY(enqueue_step(false)); break;
       case 4: GB_TRY(enqueue_cost()); break;
       case 5: // the product kernel alone
-        launch_product<false>(W, nullptr, nullptr);
+        GB_TRY(launch_product<false>(W, nullptr, nullptr));
         break;
       case 6: // the per-camera reduction of its partial rows alone (single-GPU form)
         k_cam_reduce_spmv<T><<<ts.Nc, 288, 0, st>>>(ts, part9, scale, Ap_raw, 1, dterm, pv, Ap, dot_part, nullptr, pp, 0);
@@ -1819,6 +1850,10 @@ int gb_structure_array(const gb_structure *s, int which, void *out, int64_t *cou
     if (out) memcpy(out, h.trec.data(), h.trec.size());
   } else if (which >= 18 && which <= 20) {
     const std::vector<int32_t> &v = which == 18 ? h.tile_cam : (which == 19 ? h.cm_slot : h.cm_pt);
+    *count = (int64_t)v.size();
+    if (out) memcpy(out, v.data(), v.size() * sizeof(int32_t));
+  } else if (which >= 21 && which <= 23) { // long tracks: fragment tiles, their points, point -> fragment range
+    const std::vector<int32_t> &v = which == 21 ? h.frag_tile : (which == 22 ? h.hv_pt : h.hv_ptr);
     *count = (int64_t)v.size();
     if (out) memcpy(out, v.data(), v.size() * sizeof(int32_t));
   } else {

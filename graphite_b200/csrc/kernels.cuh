@@ -105,6 +105,12 @@ struct DevStruct {
   int32_t nchunks, pad3;
   const int32_t *slot_of_obs; // [M] sorted observation -> storage slot (exports)
   const int32_t *cam_idx, *pt_idx, *pptr;    // sorted observations (exports)
+  // long tracks (structure.hpp): a point with more observations than a tile holds is cut into fragment tiles (np = 1,
+  // TileMeta::frag != 0); its per-point sums have two levels
+  int32_t nfrag, nheavy;
+  const int32_t *hv_pt, *hv_ptr; // [nheavy] the points, [nheavy+1] their fragment ranges
+  void *frag_part;               // [nfrag][9] of T: per-fragment sums (C | g in k_linearize; point part of the full-system product)
+  void *frag_t;                  // [nfrag][3] of T: sum_o Jp^T Jc x_c over ALL observations of the fragment's point (k_frag_dots)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -520,7 +526,9 @@ k_linearize(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts,
           a1 += r[1];
           a2 += r[2];
         }
-        T *out = Cg + (int64_t)(tm.p0 + q) * 9 + 3 * g;
+        // (a fragment of a long track leaves its partial sums; k_frag_sum adds the fragments of the point)
+        T *out = tm.frag ? reinterpret_cast<T *>(ds.frag_part) + (int64_t)((tm.frag & FRAG_MASK) - 1) * 9 + 3 * g
+                         : Cg + (int64_t)(tm.p0 + q) * 9 + 3 * g;
         out[0] = a0;
         out[1] = a1;
         out[2] = a2;
@@ -941,7 +949,7 @@ template <typename T, typename S, int NW = 2> struct SchurSmem2 {
 template <typename T, typename S, bool FULL, int NW = 2, typename Refill>
 __device__ __forceinline__ void product_tile(int worker, int t, const typename V2<S>::type *Js, const unsigned char *rec,
                                              const T *Ws, const T *xl, T *acc, T *sv, T *sw, T *__restrict__ out_p,
-                                             Refill &&refill) {
+                                             const DevStruct &ds, Refill &&refill) {
   using S2 = typename V2<S>::type;
   T *sv3 = sv; // point-order staging: dead before the camera staging is written
   const TileMeta tm = *reinterpret_cast<const TileMeta *>(rec + REC_META);
@@ -988,8 +996,15 @@ __device__ __forceinline__ void product_tile(int worker, int t, const typename V
       const int b = pt[q], e = pt[q + 1];
       T a = T(0);
       for (int row = b; row < e; row++) a += sv3[row * 3 + k];
-      if (FULL) out_p[(int64_t)(tm.p0 + q) * 3 + k] = a;
-      else sw[item] = a;
+      if (FULL) {
+        // (fragment of a long track: partial sum, added to the point's by k_frag_sum after the launch)
+        if (tm.frag) reinterpret_cast<T *>(ds.frag_part)[(int64_t)((tm.frag & FRAG_MASK) - 1) * 3 + k] = a;
+        else out_p[(int64_t)(tm.p0 + q) * 3 + k] = a;
+      } else {
+        // (fragment of a long track: the sum over ALL observations of the point, formed before the product - k_frag_dots /
+        // phase H of k_pcg_solve)
+        sw[item] = tm.frag ? __ldcg(reinterpret_cast<const T *>(ds.frag_t) + (int64_t)((tm.frag & FRAG_MASK) - 1) * 3 + k) : a;
+      }
     }
   }
   worker_sync(worker);
@@ -1096,7 +1111,7 @@ k_schur_product2(DevStruct ds, const typename V2<S>::type *__restrict__ J, const
       const S2 *Js = reinterpret_cast<const S2 *>(smem + (i & 1) * SM::J_BYTES);
       const unsigned char *rec = smem + SM::META_OFF + (i & 3) * SM::META_BYTES;
       const T *Ws = reinterpret_cast<const T *>(rec + REC_BYTES);
-      product_tile<T, S, FULL>(worker, t, Js, rec, Ws, xl, acc, sv, sw, out_p, [&](int next_p0, int next_np) {
+      product_tile<T, S, FULL>(worker, t, Js, rec, Ws, xl, acc, sv, sw, out_p, ds, [&](int next_p0, int next_np) {
         if (i + 2 < ntl) {
           fence_proxy_async();
           product_issue<T, S>(smem, bars, ds, J, W, tile0 + i + 2, i + 2, next_p0, next_np, pol);
@@ -1110,6 +1125,79 @@ k_schur_product2(DevStruct ds, const typename V2<S>::type *__restrict__ J, const
     }
     __syncthreads(); // xl / acc are rewritten by the next super-tile
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Long tracks.  A point observed by more cameras than one tile holds is cut into fragment tiles (structure.hpp).  Sums
+// over the point's observations then have two levels:
+//   * sums a tile WRITES (C and g of k_linearize, the point part of the full-system product): every fragment leaves its
+//     partial in frag_part, k_frag_sum adds the fragments of a point in ascending order;
+//   * the sum a tile READS before it can go on (t_p = sum_o Jp^T Jc x_c of the Schur product and of the back-
+//     substitution): heavy_point_dot forms it over all observations of the point BEFORE the tile kernels run
+//     (k_frag_dots, or phase H of k_pcg_solve) and leaves it in frag_t for every fragment of the point.
+// Both are exact restatements of the single-tile sums (other summation order), deterministic, atomic-free.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_frag_sum(int nheavy, const int32_t *__restrict__ hv_pt, const int32_t *__restrict__ hv_ptr,
+                           const T *__restrict__ frag_part, int width, T *__restrict__ out /*[Np][width]*/) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nheavy * width) return;
+  const int hp = i / width, k = i - hp * width;
+  T a = T(0);
+  for (int f = hv_ptr[hp]; f < hv_ptr[hp + 1]; f++) a += frag_part[(int64_t)f * width + k];
+  out[(int64_t)hv_pt[hp] * width + k] = a;
+}
+// t = sum over all observations of long-track point number hp of Jp^T (Jc x_c), x_c(j) = getx(c, j); every thread of
+// the CTA must call it; the result goes to frag_t of all the point's fragments.  sh: 3 * 32 values of T.
+// The sum runs in DOUBLE whatever T is: a landmark seen by hundreds of cameras is typically far away and weakly
+// constrained in depth, so its W has a large eigenvalue (~1 / damping) that amplifies the rounding error of a 400-term
+// float sum.  The long tracks are few: the cost is not measurable.
+template <typename T, typename S, typename GetX>
+__device__ __forceinline__ void heavy_point_dot(const DevStruct &ds, const typename V2<S>::type *__restrict__ J, int hp,
+                                                T *sh_T, GetX &&getx) {
+  double *sh = reinterpret_cast<double *>(sh_T); // 3 * 32 doubles (the callers provide 768 bytes)
+  const int p = ds.hv_pt[hp];
+  const int b = ds.pptr[p], e = ds.pptr[p + 1];
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+  for (int o = b + (int)threadIdx.x; o < e; o += (int)blockDim.x) {
+    const int slot = ds.slot_of_obs[o], c = ds.cam_idx[o];
+    T jc[18], jp[6];
+    double y0 = 0.0, y1 = 0.0;
+    load_J<T, S>(J, slot >> 8, slot & (TILE - 1), jc, jp);
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+      const double xv = (double)getx(c, j);
+      y0 += (double)jc[2 * j] * xv;
+      y1 += (double)jc[2 * j + 1] * xv;
+    }
+    a0 += (double)jp[0] * y0 + (double)jp[1] * y1;
+    a1 += (double)jp[2] * y0 + (double)jp[3] * y1;
+    a2 += (double)jp[4] * y0 + (double)jp[5] * y1;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_down_sync(0xffffffffu, a0, o);
+    a1 += __shfl_down_sync(0xffffffffu, a1, o);
+    a2 += __shfl_down_sync(0xffffffffu, a2, o);
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = ((int)blockDim.x + 31) >> 5;
+  __syncthreads(); // sh may still be read from the previous point
+  if (lane == 0) { sh[w] = a0; sh[32 + w] = a1; sh[64 + w] = a2; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double tot = 0.0;
+    for (int i = 0; i < nw; i++) tot += sh[32 * threadIdx.x + i];
+    T *ft = reinterpret_cast<T *>(ds.frag_t);
+    for (int f = ds.hv_ptr[hp]; f < ds.hv_ptr[hp + 1]; f++) ft[(int64_t)f * 3 + threadIdx.x] = (T)tot;
+  }
+}
+// one CTA per long-track point; xs = D_c x in 10-padded camera rows
+template <typename T, typename S>
+__global__ void __launch_bounds__(256)
+k_frag_dots(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *__restrict__ xs, const int *__restrict__ done_flag) {
+  __shared__ double sh[96];
+  if (done_flag && *done_flag) return;
+  heavy_point_dot<T, S>(ds, J, (int)blockIdx.x, reinterpret_cast<T *>(sh), [&](int c, int j) { return xs[c * CAM_STRIDE + j]; });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1147,14 +1235,21 @@ k_backsubst_tiles(DevStruct ds, const typename V2<S>::type *__restrict__ J, cons
   sv3[prank * 3 + 2] = jp[4] * y0 + jp[5] * y1;
   __syncthreads();
   double rho = 0.0;
-  if (t < tm.np) {
+  // (long track: its first fragment takes the sum over all the point's observations from k_frag_dots and updates the
+  // point; the other fragments have nothing to do)
+  if (t < tm.np && (!tm.frag || (tm.frag & FRAG_FIRST))) {
     const uint16_t *pt = reinterpret_cast<const uint16_t *>(rec + REC_PT);
     const int b = pt[t], e = pt[t + 1];
     T t0 = T(0), t1 = T(0), t2 = T(0);
-    for (int row = b; row < e; row++) {
-      t0 += sv3[row * 3];
-      t1 += sv3[row * 3 + 1];
-      t2 += sv3[row * 3 + 2];
+    if (tm.frag) {
+      const T *ft = reinterpret_cast<const T *>(ds.frag_t) + (int64_t)((tm.frag & FRAG_MASK) - 1) * 3;
+      t0 = ft[0]; t1 = ft[1]; t2 = ft[2];
+    } else {
+      for (int row = b; row < e; row++) {
+        t0 += sv3[row * 3];
+        t1 += sv3[row * 3 + 1];
+        t2 += sv3[row * 3 + 2];
+      }
     }
     const int p = tm.p0 + t;
     const T *w = W + (int64_t)p * WST<T>::value;

@@ -195,6 +195,17 @@ k_pcg_solve(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *_
       }
       solve_publish<T, SOLVE_WARPS>(pdp_w, wpart, cta_red);
     }
+    // ---- phase H (only with long tracks, structure.hpp): t_p = sum_o Jp^T Jc (D p)_c over ALL observations of every point
+    // that is cut into fragment tiles, before any of its fragments is multiplied; costs one more grid barrier ----------
+    if (ds.nheavy > 0) {
+      for (int hp = (int)blockIdx.x; hp < ds.nheavy; hp += G)
+        heavy_point_dot<T, S>(ds, J, hp, red, [&](int c, int j) {
+          const int i = c * 9 + j;
+          return scale_c[i] * pcg_direction<T>(beta, __ldcg(p_old + i), __ldcg(z + i));
+        });
+      __threadfence();
+      grid.sync();
+    }
     // ---- the product over the super-tiles the work counter hands out -----------------------------------------------
     // A super-tile boundary costs two CTA barriers and one pass: the rows and the dot of the finished super-tile are
     // written in the same pass that builds the camera vector rows of the next one, whose record (camera list, row
@@ -240,7 +251,7 @@ k_pcg_solve(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *_
           const S2 *Js = reinterpret_cast<const S2 *>(smem + (i % NW) * SM::J_BYTES);
           const unsigned char *rec = smem + SM::META_OFF + (i % NMETA) * SM::META_BYTES;
           const T *Ws = reinterpret_cast<const T *>(rec + REC_BYTES);
-          product_tile<T, S, false, NW>(worker, t, Js, rec, Ws, xl, acc, sv, sw, (T *)nullptr, [&](int next_p0, int next_np) {
+          product_tile<T, S, false, NW>(worker, t, Js, rec, Ws, xl, acc, sv, sw, (T *)nullptr, ds, [&](int next_p0, int next_np) {
             const int j = i + NW;
             if (j <= my_issued) return;
             if (j < ie) {

@@ -60,8 +60,10 @@ struct TileMeta {
   int32_t seg_off; // offset into seg_tab (multiple of 4)
   int32_t pt_off;  // offset into pt_tab (multiple of 8)
   int32_t o0;      // sorted observation index of slot 0
-  int32_t pad;
+  int32_t frag;    // 0: the tile holds whole points.  Else the tile is a FRAGMENT of one long track (np = 1): bits 0-29 =
+                   // index of the tile in the fragment list + 1, bit 30 = first fragment of its point (see build())
 };
+constexpr int32_t FRAG_FIRST = 1 << 30, FRAG_MASK = FRAG_FIRST - 1;
 
 struct HostStructure {
   int64_t M = 0, Mstore = 0;
@@ -94,6 +96,12 @@ struct HostStructure {
   std::vector<uint8_t> rank;
   std::vector<int32_t> tile_ncam;               // [ntiles] distinct cameras (= camera segments) of each tile
   std::vector<int32_t> tile_st;                 // [ntiles] super-tile of each tile
+  // Long tracks.  A point with more observations than one tile can hold (min(tile_fill, slot_cap)) is cut into FRAGMENT
+  // tiles: consecutive tiles that hold nothing but a part of that point's observations (np = 1, all cameras distinct).
+  // Its per-point sums then have two levels - the kernels write / read per-fragment values and a tiny kernel adds the
+  // fragments of a point in order (kernels.cuh, "long tracks").
+  std::vector<int32_t> frag_tile;               // [nfrag] tile of every fragment, ascending
+  std::vector<int32_t> hv_pt, hv_ptr;           // [nheavy] long-track points, [nheavy+1] their ranges in frag_tile
   bool tables_on_device = false;
   int32_t max_track = 0;
   int64_t nseg_total = 0;
@@ -186,8 +194,6 @@ struct HostStructure {
       max_track = std::max(max_track, pptr[p + 1]);
       pptr[p + 1] += pptr[p];
     }
-    if (max_track > tile_fill) return "a point has more observations than the tile size (" + std::to_string(max_track) + ")";
-    if (max_track > slot_cap) return "a point has more observations than the slot cap (" + std::to_string(max_track) + ")";
     if (!partition) {
       std::vector<uint8_t> seen((size_t)nc, 0);
       for (int64_t i = 0; i < m; i++) seen[cam_idx[i]] = 1;
@@ -197,20 +203,39 @@ struct HostStructure {
     lap("point CSR / unused checks");
     // ---- tiles of whole points ----------------------------------------------------------------------
     tile_obs.clear(); tile_pt.clear(); tile_ncam.clear();
+    frag_tile.clear(); hv_pt.clear(); hv_ptr.assign(1, 0);
     tile_obs.push_back(0); tile_pt.push_back(0);
     int32_t cur = 0, ncam_tile = 0;
+    const int32_t frag_cap = std::min(tile_fill, slot_cap); // longest track one tile can hold
+    // the open tile ends here; the next one starts at sorted observation `next_obs`, point `next_pt`
+    auto close_tile = [&](int32_t next_obs, int32_t next_pt) {
+      tile_ncam.push_back(ncam_tile);
+      tile_obs.push_back(next_obs); tile_pt.push_back(next_pt);
+      cur = 0; ncam_tile = 0;
+    };
     std::vector<int32_t> tstamp((size_t)nc, -1);
     for (int32_t p = 0; p < Np; p++) {
       const int32_t t = pptr[p + 1] - pptr[p];
+      if (t > frag_cap) {
+        // long track: near-equal fragments, one tile each (tile_pt = p for all of them, so np = max(1, difference))
+        if (cur > 0) close_tile(pptr[p], p);
+        const int32_t nf = (t + frag_cap - 1) / frag_cap;
+        hv_pt.push_back(p);
+        for (int32_t j = 0; j < nf; j++) {
+          const int32_t e = pptr[p] + (int32_t)(((int64_t)t * (j + 1)) / nf);
+          frag_tile.push_back((int32_t)tile_pt.size() - 1);
+          cur = ncam_tile = e - tile_obs.back();
+          if (j + 1 < nf) close_tile(e, p);
+          else if (p + 1 < Np) close_tile(e, p + 1);
+        }
+        hv_ptr.push_back((int32_t)frag_tile.size());
+        continue;
+      }
       // cameras this point would add to the tile (a tile may not touch more cameras than a super-tile has rows)
       const int32_t tid = (int32_t)tile_pt.size() - 1;
       int32_t add = 0;
       for (int32_t o = pptr[p]; o < pptr[p + 1]; o++) add += tstamp[cam_idx[o]] != tid;
-      if (cur + t > tile_fill || p - tile_pt.back() >= TILE_PTS || ncam_tile + add > slot_cap) {
-        tile_obs.push_back(pptr[p]); tile_pt.push_back(p);
-        tile_ncam.push_back(ncam_tile);
-        cur = 0; ncam_tile = 0;
-      }
+      if (cur + t > tile_fill || p - tile_pt.back() >= TILE_PTS || ncam_tile + add > slot_cap) close_tile(pptr[p], p);
       const int32_t tid2 = (int32_t)tile_pt.size() - 1;
       for (int32_t o = pptr[p]; o < pptr[p + 1]; o++)
         if (tstamp[cam_idx[o]] != tid2) { tstamp[cam_idx[o]] = tid2; ncam_tile++; }
@@ -309,9 +334,11 @@ struct HostStructure {
       for (int32_t k = st_tile[s]; k < st_tile[s + 1]; k++) tile_st[k] = s;
     for (int32_t k = 0; k < nt; k++) {
       TileMeta &tm = tmeta[k];
-      tm.p0 = tile_pt[k]; tm.n = tile_obs[k + 1] - tile_obs[k]; tm.np = tile_pt[k + 1] - tile_pt[k];
-      tm.nseg = tile_ncam[k]; tm.o0 = tile_obs[k]; tm.pad = 0;
+      tm.p0 = tile_pt[k]; tm.n = tile_obs[k + 1] - tile_obs[k]; tm.np = tile_np(k);
+      tm.nseg = tile_ncam[k]; tm.o0 = tile_obs[k]; tm.frag = 0;
     }
+    for (size_t h = 0; h < hv_pt.size(); h++)
+      for (int32_t f = hv_ptr[h]; f < hv_ptr[h + 1]; f++) tmeta[frag_tile[f]].frag = (f + 1) | (f == hv_ptr[h] ? FRAG_FIRST : 0);
     seg_tab.clear(); pt_tab.clear(); // compact copies of the tables are materialised on demand (materialize_tables)
     ometa.clear(); rank.clear(); slot_of_obs.clear(); tile_cam.clear(); trec.clear();
     if (!device_tables) {
@@ -332,9 +359,9 @@ struct HostStructure {
         for (int32_t r = st_row[s]; r < st_row[s + 1]; r++) local_t[row_cam[r]] = r - st_row[s];
         for (int32_t k = st_tile[s]; k < st_tile[s + 1]; k++) {
           const int32_t o0 = tile_obs[k], n = tile_obs[k + 1] - o0;
-          const int32_t p0 = tile_pt[k], npt = tile_pt[k + 1] - p0;
+          const int32_t p0 = tile_pt[k], npt = tile_np(k);
           TileMeta &tm = tmeta[k];
-          tm.p0 = p0; tm.n = n; tm.np = npt; tm.o0 = o0; tm.pad = 0;
+          tm.p0 = p0; tm.n = n; tm.np = npt; tm.o0 = o0;
           for (int32_t q = 0; q <= nslots; q++) start[q] = 0;
           for (int32_t u = 0; u < n; u++) { cs[u] = local_t[cam_idx[o0 + u]]; start[cs[u] + 1]++; }
           for (int32_t q = 0; q < nslots; q++) start[q + 1] += start[q];
@@ -363,11 +390,13 @@ struct HostStructure {
           tm.nseg = nseg;
           for (int32_t i = nseg; i < TILE + 4; i++) sg[i] = ((uint32_t)n << 16); // sentinel: end of the last segment
           uint16_t *pt = reinterpret_cast<uint16_t *>(rec + REC_PT);
-          for (int32_t i = 0; i < TILE_PTS + 8; i++) pt[i] = i <= npt ? (uint16_t)(pptr[p0 + i] - o0) : (uint16_t)n;
+          // (clamped to the tile: a fragment holds a part of its point's observations)
+          for (int32_t i = 0; i < TILE_PTS + 8; i++)
+            pt[i] = i <= npt ? (uint16_t)std::min(std::max(pptr[p0 + i] - o0, 0), n) : (uint16_t)n;
           int32_t *nx = reinterpret_cast<int32_t *>(rec + REC_NEXT);
           for (int32_t d = 1; d <= 4; d++) {
             nx[2 * (d - 1)] = k + d < nt ? tile_pt[k + d] : 0;
-            nx[2 * (d - 1) + 1] = k + d < nt ? tile_pt[k + d + 1] - tile_pt[k + d] : 0;
+            nx[2 * (d - 1) + 1] = k + d < nt ? tile_np(k + d) : 0;
           }
         }
       }
@@ -477,6 +506,10 @@ struct HostStructure {
   }
 
   int32_t ntiles() const { return (int32_t)tile_obs.size() - 1; }
+  // points of tile k: the fragments of a long track all start at their point, so consecutive tile_pt entries are equal
+  int32_t tile_np(int32_t k) const { return std::max(1, tile_pt[k + 1] - tile_pt[k]); }
+  int32_t nfrag() const { return (int32_t)frag_tile.size(); }
+  int32_t nheavy() const { return (int32_t)hv_pt.size(); }
   int32_t nst() const { return (int32_t)st_tile.size() - 1; }
   int32_t nrows() const { return (int32_t)row_cam.size(); }
   int32_t ncta() const { return (int32_t)cta_st.size() - 1; }

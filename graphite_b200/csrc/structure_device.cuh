@@ -28,7 +28,7 @@ k_build_tile_tables(int nt, const int32_t *__restrict__ cam_idx, const int32_t *
   __shared__ int32_t cs_sorted[TILE]; // ... of slot v
   const int k = blockIdx.x, u = threadIdx.x;
   const int32_t o0 = tile_obs[k], n = tile_obs[k + 1] - o0;
-  const int32_t p0 = tile_pt[k], npt = tile_pt[k + 1] - p0;
+  const int32_t p0 = tile_pt[k], npt = max(1, tile_pt[k + 1] - p0); // fragments of a long track: np = 1
   const int32_t s = tile_st[k], r0 = st_row[s], nslots = st_row[s + 1] - r0;
   int32_t c = 0, cslot = 0x7fffffff;
   if (u < n) {
@@ -83,13 +83,13 @@ k_build_tile_tables(int nt, const int32_t *__restrict__ cam_idx, const int32_t *
   const TileMeta tm = tmeta[k];
   for (int i = tm.nseg + u; i < TILE + 4; i += TILE) sg[i] = (uint32_t)n << 16; // sentinel: end of the last segment
   uint16_t *pt = reinterpret_cast<uint16_t *>(rec + REC_PT);
-  for (int i = u; i < TILE_PTS + 8; i += TILE) pt[i] = i <= npt ? (uint16_t)(pptr[p0 + i] - o0) : (uint16_t)n;
+  for (int i = u; i < TILE_PTS + 8; i += TILE) pt[i] = i <= npt ? (uint16_t)min(max(pptr[p0 + i] - o0, 0), n) : (uint16_t)n;
   if (u == 0) *reinterpret_cast<TileMeta *>(rec + REC_META) = tm;
   if (u < 4) {
     int32_t *nx = reinterpret_cast<int32_t *>(rec + REC_NEXT);
     const int d = u + 1;
     nx[2 * u] = k + d < nt ? tile_pt[k + d] : 0;
-    nx[2 * u + 1] = k + d < nt ? tile_pt[k + d + 1] - tile_pt[k + d] : 0;
+    nx[2 * u + 1] = k + d < nt ? max(1, tile_pt[k + d + 1] - tile_pt[k + d]) : 0;
   }
 }
 

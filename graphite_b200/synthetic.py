@@ -172,8 +172,40 @@ def make_bal(n_cams: int, n_pts: int, n_obs: int, seed: int = 0, name: str = "cu
 
 
 def make_named(name: str, seed: int = 0) -> BALProblem:
+    if name == "long-tracks":
+        return make_long_tracks(seed=seed)
     nc, npts, m = SHAPES[name]
     return make_bal(nc, npts, m, seed=seed, name=name)
+
+
+def make_long_tracks(n_cams: int = 420, n_pts: int = 900, n_obs: int = 6000, tracks=(400, 260, 193, 300),
+                     seed: int = 0) -> BALProblem:
+    """A BAL problem with LONG TRACKS, as real BAL sets have (landmarks seen by hundreds of cameras): the first point, two
+    points in the middle and the last point are observed by ``tracks`` cameras each - more than one tile of the library
+    holds (192), so their observations are cut into fragment tiles (csrc/structure.hpp)."""
+    base = make_bal(n_cams, n_pts, n_obs, seed=seed, name="long-tracks")
+    rng = np.random.Generator(np.random.PCG64(seed + 77))
+    chosen = [0, n_pts // 3, (2 * n_pts) // 3, n_pts - 1][: len(tracks)]
+    cam_new, pt_new = [], []
+    for p, t in zip(chosen, tracks):
+        have = base.cam_idx[base.pt_idx == p]
+        others = np.setdiff1d(np.arange(n_cams), have)
+        add = rng.choice(others, size=min(max(t - have.size, 0), others.size), replace=False)
+        cam_new.append(add.astype(np.int32))
+        pt_new.append(np.full(add.size, p, dtype=np.int32))
+    cam_new, pt_new = np.concatenate(cam_new), np.concatenate(pt_new)
+    cam_idx = np.concatenate([base.cam_idx, cam_new])
+    pt_idx = np.concatenate([base.pt_idx, pt_new])
+    obs = np.concatenate([base.obs, np.zeros((cam_new.size, 2))])
+    # a landmark seen from the whole scene is far away: move the chosen points to a depth of 300 (in front of every camera)
+    # and take ALL their observations from the initial estimate's projection plus noise
+    pts = base.pts.copy()
+    pts[chosen, 2] = -300.0
+    sel = np.isin(pt_idx, chosen)
+    obs[sel] = project(base.cams, pts, cam_idx[sel], pt_idx[sel]) + rng.normal(0, 2.0, (int(sel.sum()), 2))
+    order = np.lexsort((cam_idx, pt_idx))
+    return BALProblem(np.ascontiguousarray(cam_idx[order]), np.ascontiguousarray(pt_idx[order]),
+                      np.ascontiguousarray(obs[order]), base.cams, pts, "long-tracks")
 
 
 def schur_fixture() -> BALProblem:

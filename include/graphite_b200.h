@@ -69,8 +69,9 @@ typedef struct {
   const int32_t *camera_index; /* host [num_observations] */
   const int32_t *point_index;  /* host [num_observations], local point index */
   int32_t tile_size;         /* max observations per tile, 0 = default (256, the storage tile) */
-  int32_t slot_cap;          /* max distinct cameras per super-tile, 0 = default = maximum (192); also the longest
-                              * supported track: a point with more observations is rejected (GB_ERR_UNSUPPORTED) */
+  int32_t slot_cap;          /* max distinct cameras per super-tile, 0 = default = maximum (192).  Tracks of ANY length are
+                              * supported: a point with more observations than min(tile_size, slot_cap) is cut into
+                              * fragment tiles whose per-point sums are completed in a second level */
   int64_t super_tile_observations; /* target observations per super-tile (one CTA), 0 = default M / (148*8) */
   int64_t flags;             /* GB_FLAG_* */
 } gb_problem_desc;
@@ -95,7 +96,9 @@ int gb_problem_destroy(gb_problem *p);
  * want the tiling before committing device memory.  which: 0 cam_idx 1 pt_idx (sorted order) 2 pptr 3 tile_obs
  * 4 tile_pt 5 st_tile 6 st_row 7 row_cam 8 cam_row_ptr 9 cam_row_list 10 slot_of_obs (all int32), 11 rank (uint8),
  * 12 perm (int64; empty when the input was already sorted), 13 ometa (uint32) 14 seg_tab (uint32) 15 pt_tab (uint16)
- * 16 tile meta (8 x int32 per tile).  out may be NULL to query the count. */
+ * 16 tile meta (8 x int32 per tile: p0, n, np, nseg, seg_off, pt_off, o0, frag), 21 frag_tile 22 hv_pt 23 hv_ptr (int32; long
+ * tracks: a point with more observations than one tile holds is cut into fragment tiles - the tiles of the fragments, the
+ * points, and each point's range in frag_tile).  out may be NULL to query the count. */
 typedef struct gb_structure gb_structure;
 int gb_structure_create(const gb_problem_desc *desc, gb_structure **out, char *errbuf, int errlen);
 int gb_structure_destroy(gb_structure *s);

@@ -156,6 +156,13 @@ def main(which):
         run_case("ladybug-49", p, "pcg-schur", "FP32-FP32", 30, fix_cameras=2, fix_points=50)
         p = synthetic.make_named("trafalgar-257")
         run_case("trafalgar-257", p, "pcg-schur", "FP64-FP64", 30, fix_cameras=1, fix_points=0)
+    if "longtracks" in which:  # tracks longer than one tile of the library holds (400 / 260 / 193 / 300 cameras)
+        p = synthetic.make_named("long-tracks")
+        run_case("long-tracks", p, "pcg-schur", "FP64-FP64", 30, dump=True)
+        run_case("long-tracks", p, "pcg", "FP64-FP64", 30)
+        run_case("long-tracks", p, "pcg-schur", "FP32-FP32", 30)
+        run_case("long-tracks", p, "pcg", "FP64-FP32", 30)
+        run_case("long-tracks", p, "pcg", "FP64-BF16", 30)
     if "dubrovnik" in which:
         p = synthetic.make_named("dubrovnik-356")
         second_run("dubrovnik-356", p)

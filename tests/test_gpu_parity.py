@@ -51,7 +51,7 @@ def ref_spread(case):
 # ------------------------------------------------------------------------------------------------------
 # stage-by-stage parity with the oracle
 # ------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("case", ["schur-fixture", "ladybug-49"])
+@pytest.mark.parametrize("case", ["schur-fixture", "ladybug-49", "long-tracks"])
 def test_fp64_stages_match_oracle(ctx, case):
     prob = synthetic.schur_fixture() if case == "schur-fixture" else synthetic.make_named(case)
     P = binding.problem_from_bal(ctx, prob, "f64-f64")
@@ -163,7 +163,7 @@ def test_explicit_schur_matches_reference_and_oracle(ctx, case):
 # ------------------------------------------------------------------------------------------------------
 # LM trajectories against the reference's own runs
 # ------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("case", ["schur-fixture", "ladybug-49", "trafalgar-257", "dubrovnik-356"])
+@pytest.mark.parametrize("case", ["schur-fixture", "ladybug-49", "trafalgar-257", "dubrovnik-356", "long-tracks"])
 def test_fp64_trajectory_matches_reference(ctx, case):
     g = golden_json(f"{case}__pcg-schur__FP64-FP64.json")
     t = np.array(g["table"])
@@ -274,7 +274,7 @@ def test_venice_final_cost_matches_reference(ctx):
 
 @pytest.mark.parametrize("gold", ["ladybug-49__pcg-schur__FP32-FP32.json", "trafalgar-257__pcg-schur__FP32-FP32.json",
                                   "dubrovnik-356__pcg-schur__FP32-FP32.json", "venice-1778__pcg-schur__FP32-FP32.json",
-                                  "final-13682__pcg-schur__FP32-FP32.json"])
+                                  "final-13682__pcg-schur__FP32-FP32.json", "long-tracks__pcg-schur__FP32-FP32.json"])
 def test_fp32_matches_reference(ctx, gold):
     """FP32-FP32 agrees with the reference's FP32 run to 1e-4 (north_star).
 
@@ -296,13 +296,18 @@ def test_fp32_matches_reference(ctx, gold):
     first_flip = n if same.all() else int(np.argmin(same))
     assert first_flip >= 15, (first_flip, traj[:n, :3], t[:n, 1:4])
     r = np.abs(traj[:first_flip, 1] - t[:first_flip, 2]) / t[:first_flip, 2]
-    assert r.max() <= 1e-4, r
-    assert traj[:, 1].min() <= g["final_chi2"] * (1 + 1e-4)
-    assert traj[-1, 1] <= g["final_chi2"] * (1 + 1e-4)
+    # long-tracks is a small, weakly constrained problem (14 observations per camera) whose FP32 runs are dominated by
+    # rounding noise: two tilings of this library (pure summation-order changes) differ by 6.6e-3 at iteration 1, and the
+    # same problem WITHOUT its long tracks is 2e-3 away from its own FP64 run (measured, profiles/README.md "long tracks").
+    # Its FP32 bound is therefore that measured sensitivity; FP64, mixed and bf16 runs of it are held to the usual bounds.
+    tol = 1e-2 if g["case"] == "long-tracks" else 1e-4
+    assert r.max() <= tol, r
+    assert traj[:, 1].min() <= g["final_chi2"] * (1 + max(tol / 10, 1e-4))
+    assert traj[-1, 1] <= g["final_chi2"] * (1 + max(tol / 10, 1e-4))
     P.close()
 
 
-@pytest.mark.parametrize("case", ["ladybug-49", "trafalgar-257", "venice-1778"])
+@pytest.mark.parametrize("case", ["ladybug-49", "trafalgar-257", "venice-1778", "long-tracks"])
 def test_mixed_precision_matches_fp64_reference(ctx, case):
     """T = double, S = float (Jacobians stored in FP32) on the Schur path.  The reference offers this precision pair only
     on its full-system solver, so the golden run of this configuration is the reference's FP64 pcg-schur run: every
@@ -350,11 +355,12 @@ def test_full_system_pcg_step_matches_oracle(ctx, case):
     P.close()
 
 
-def test_full_system_pcg_trajectory_matches_reference(ctx):
+@pytest.mark.parametrize("case", ["ladybug-49", "long-tracks"])
+def test_full_system_pcg_trajectory_matches_reference(ctx, case):
     """The reference's `--solver pcg` FP64-FP64 run: per-iteration cost 1e-9, same decisions, final cost 1e-6."""
-    g = golden_json("ladybug-49__pcg__FP64-FP64.json")
+    g = golden_json(f"{case}__pcg__FP64-FP64.json")
     t = np.array(g["table"])
-    prob = synthetic.make_named("ladybug-49")
+    prob = synthetic.make_named(case)
     P = binding.problem_from_bal(ctx, prob, "f64-f64")
     traj, res = P.lm(iterations=len(t), solver="pcg")
     assert len(traj) == len(t)
@@ -367,7 +373,8 @@ def test_full_system_pcg_trajectory_matches_reference(ctx):
 
 
 @pytest.mark.parametrize("gold", ["ladybug-49__pcg__FP64-FP32.json", "trafalgar-257__pcg__FP64-FP32.json",
-                                  "venice-1778__pcg__FP64-FP32.json", "final-13682__pcg__FP64-FP32.json"])
+                                  "venice-1778__pcg__FP64-FP32.json", "final-13682__pcg__FP64-FP32.json",
+                                  "long-tracks__pcg__FP64-FP32.json"])
 def test_full_system_pcg_mixed_precision_matches_reference(ctx, gold):
     """T = double, S = float on the solver the reference offers it on: 1e-4 on the cost (north_star)."""
     g = golden_json(gold)
@@ -382,7 +389,7 @@ def test_full_system_pcg_mixed_precision_matches_reference(ctx, gold):
 
 
 @pytest.mark.parametrize("gold", ["ladybug-49__pcg__FP64-BF16.json", "trafalgar-257__pcg__FP64-BF16.json",
-                                  "venice-1778__pcg__FP64-BF16.json"])
+                                  "venice-1778__pcg__FP64-BF16.json", "long-tracks__pcg__FP64-BF16.json"])
 def test_bf16_jacobian_storage_matches_reference(ctx, gold):
     """T = double, S = bf16 - the reference's low-precision mode (`--solver pcg --precision FP64-BF16`, examples/bal.cu:
     186-236): Jacobians rounded to bf16 when evaluated and again after Jacobi scaling (ops/linearize.hpp:43-64, 140-180),
@@ -869,7 +876,7 @@ def test_fixed_vertices_first_linearisation_and_modes(ctx):
 # structure build: the observation-sized tables are built on the GPU (csrc/structure_device.cuh)
 # ------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("case,kw", [("ladybug-49", {}), ("trafalgar-257", {}), ("trafalgar-257", dict(tile_size=100, slot_cap=64)),
-                                      ("dubrovnik-356", {})])
+                                      ("dubrovnik-356", {}), ("long-tracks", {}), ("long-tracks", dict(tile_size=24, slot_cap=40))])
 def test_device_structure_tables_equal_the_host_build(ctx, case, kw):
     """Per-tile records (slot order, packed meta, segment / point tables), slot_of_obs, tile_cam and the camera-major view
     built by the kernels are bit-identical with the host build (the GPU-less view of gb_structure_*), and a problem
@@ -903,3 +910,59 @@ def test_device_structure_with_unsorted_input(ctx):
     for which in (10, 13, 17, 18, 19, 20):
         assert np.array_equal(P.structure_array(which), H.structure_array(which))
     P.close(); H.close()
+
+
+# ------------------------------------------------------------------------------------------------------
+# long tracks: points observed by more cameras than one tile holds (real BAL landmarks) are cut into fragment tiles whose
+# per-point sums have a second level (csrc/structure.hpp, kernels.cuh "long tracks")
+# ------------------------------------------------------------------------------------------------------
+def test_long_tracks_every_solver_follows_the_oracle(ctx):
+    """Tracks of 400 / 260 / 193 / 300 observations (first point, two in the middle, last point): the matrix-free Schur PCG,
+    the explicit Schur mode, the direct solver and the full-system PCG each reproduce the oracle's LM trajectory (1e-9,
+    same decisions and PCG iteration counts), in any tiling - with 24-observation tiles 14 points are cut into 70 fragments."""
+    prob = named_problem("long-tracks")
+    assert np.bincount(prob.pt_idx).max() == 400
+    n = 14
+    for solver, oopt in (("pcg-schur", {}), ("pcg", dict(solver=2)), ("direct-schur", dict(solver=1))):
+        otraj = Oracle(prob).lm(default_options(iterations=n, **oopt))
+        assert (otraj[:, 0] == otraj[:, 1]).any() and (otraj[:, 0] != otraj[:, 1]).any(), "cover accepted and rejected steps"
+        for kw in ({}, dict(tile_size=24, slot_cap=40)):
+            P = binding.problem_from_bal(ctx, prob, "f64-f64", **kw)
+            if kw:
+                assert P.info()["n_tiles"] > 300
+            modes = ("implicit", "explicit") if solver == "pcg-schur" else ("auto",)
+            for mode in modes:
+                P.set_vertices(prob.cams, prob.pts)
+                traj, res = P.lm(iterations=n, solver=solver, schur_mode=mode)
+                r = np.abs(traj[:, 1] - otraj[:, 1]) / otraj[:, 1]
+                assert r.max() <= 1e-9, (solver, kw, mode, r)
+                assert np.array_equal(traj[:, 0] == traj[:, 1], otraj[:, 0] == otraj[:, 1]), (solver, kw, mode)
+                if solver != "direct-schur":
+                    assert np.array_equal(traj[:, 3], otraj[:, 3]), (solver, kw, mode)
+            P.close()
+
+
+def test_long_tracks_step_and_vertices(ctx):
+    """One solve + applied step on the long-track problem: the step of every point (the long tracks' included) and the
+    updated vertices match the oracle; a reverted step restores them bit for bit."""
+    prob = named_problem("long-tracks")
+    P = binding.problem_from_bal(ctx, prob, "f64-f64")
+    O = Oracle(prob)
+    P.linearize(); O.linearize()
+    P.set_damping(1e-3)
+    d, info = P.solve(30, 1e-14, 5.0)
+    od, ok = O.solve(1e-3, default_options(pcg_iterations=30, pcg_tolerance=1e-14))
+    assert info["pcg_iterations"] == ok
+    assert rel(d, od) <= 1e-9
+    heavy = np.flatnonzero(np.bincount(prob.pt_idx) > 192)
+    assert heavy.tolist() == [0, 300, 600, 899]
+    dp, odp = d[9 * prob.n_cams:].reshape(-1, 3), od[9 * prob.n_cams:].reshape(-1, 3)
+    assert rel(dp[heavy], odp[heavy]) <= 1e-9
+    c0, p0 = P.get_vertices()
+    P.try_step()
+    c1, p1 = P.get_vertices()
+    assert np.abs(p1[heavy] - p0[heavy]).max() > 0
+    P.revert_step()
+    c2, p2 = P.get_vertices()
+    assert np.array_equal(c0, c2) and np.array_equal(p0, p2)
+    P.close()

@@ -155,10 +155,9 @@ def test_structure_rejects_what_it_cannot_handle(built):
         binding.host_structure(np.array([0, 1, 1], dtype=np.int32), np.array([0, 0, 0], dtype=np.int32), 2, 1)
     with pytest.raises(binding.GraphiteB200Error, match="out of range"):
         binding.host_structure(np.array([0, 5], dtype=np.int32), np.array([0, 0], dtype=np.int32), 2, 1)
-    with pytest.raises(binding.GraphiteB200Error, match="tile size"):
-        binding.host_structure(np.arange(40, dtype=np.int32), np.zeros(40, dtype=np.int32), 40, 1, 32)
-    with pytest.raises(binding.GraphiteB200Error, match="slot cap"):
-        binding.host_structure(np.arange(40, dtype=np.int32), np.zeros(40, dtype=np.int32), 40, 1, 0, 16)
+    # a track longer than the tile / the slot cap is not an error any more: it is cut into fragment tiles
+    assert len(binding.host_structure(np.arange(40, dtype=np.int32), np.zeros(40, dtype=np.int32), 40, 1, 32)["frag_tile"]) == 2
+    assert len(binding.host_structure(np.arange(40, dtype=np.int32), np.zeros(40, dtype=np.int32), 40, 1, 0, 16)["frag_tile"]) == 3
     with pytest.raises(binding.GraphiteB200Error, match="slot cap"):
         binding.host_structure(np.arange(40, dtype=np.int32), np.zeros(40, dtype=np.int32), 40, 1, 0, 500)
 
@@ -289,16 +288,53 @@ def test_bal_text_round_trip(tmp_path):
         assert np.array_equal(x, y)
 
 
-def test_long_tracks_are_rejected_loudly():
-    """A point observed by more cameras than a super-tile has accumulator rows (192) cannot be tiled: the structure build
-    says so instead of producing wrong sums (include/graphite_b200.h, gb_problem_desc.slot_cap)."""
+def test_long_tracks_are_cut_into_fragment_tiles():
+    """A point observed by more cameras than one tile holds (192 rows per super-tile; real BAL landmarks have such
+    tracks) is cut into FRAGMENT tiles: consecutive tiles that hold nothing but a part of that point's observations."""
     nc, npts = 200, 3
     cam = np.concatenate([np.arange(193), [0, 1], [2, 3]]).astype(np.int32)
     pt = np.concatenate([np.zeros(193), [1, 1], [2, 2]]).astype(np.int32)
-    with pytest.raises(binding.GraphiteB200Error, match="more observations than"):
-        binding.host_structure(cam, pt, nc, npts)
-    # 192 is fine (the remaining cameras are observed by the other points, so no vertex is unused)
+    s = binding.host_structure(cam, pt, 193, npts)
+    assert s["info"]["max_track"] == 193
+    assert s["frag_tile"].tolist() == [0, 1] and s["hv_pt"].tolist() == [0] and s["hv_ptr"].tolist() == [0, 2]
+    assert s["tile_obs"].tolist() == [0, 96, 193, 197] and s["tile_pt"].tolist() == [0, 0, 1, 3]
+    # 192 fits in one tile (the remaining cameras are observed by the other points, so no vertex is unused)
     cam2 = np.concatenate([np.arange(192), np.arange(192, 200), [0, 1]]).astype(np.int32)
     pt2 = np.concatenate([np.zeros(192), np.ones(8), [2, 2]]).astype(np.int32)
     s = binding.host_structure(cam2, pt2, nc, npts)
-    assert s["info"]["max_track"] == 192
+    assert s["info"]["max_track"] == 192 and len(s["frag_tile"]) == 0
+
+    for kw in ({}, dict(tile_size=24, slot_cap=40), dict(tile_size=64)):
+        prob = synthetic.make_named("long-tracks")
+        s = binding.host_structure(prob.cam_idx, prob.pt_idx, prob.n_cams, prob.n_pts, **kw)
+        cap = min(kw.get("tile_size", 256), kw.get("slot_cap", 192))
+        to, tp, tm, pptr = s["tile_obs"], s["tile_pt"], s["tmeta"], s["pptr"]
+        nt = len(to) - 1
+        track = np.diff(pptr)
+        heavy = np.flatnonzero(track > cap)
+        assert np.array_equal(s["hv_pt"], heavy) and (cap > 40 or len(heavy) > 4)
+        assert to[0] == 0 and to[-1] == prob.n_obs and np.all(np.diff(to) > 0) and np.diff(to).max() <= kw.get("tile_size", 256)
+        frag = np.zeros(nt, bool)
+        frag[s["frag_tile"]] = True
+        for h, p in enumerate(heavy):
+            tiles = s["frag_tile"][s["hv_ptr"][h]:s["hv_ptr"][h + 1]]
+            assert np.array_equal(tiles, np.arange(tiles[0], tiles[-1] + 1)), "fragments of a point are consecutive tiles"
+            assert to[tiles[0]] == pptr[p] and to[tiles[-1] + 1] == pptr[p + 1], "and cover exactly its observations"
+            assert len(tiles) == -(-track[p] // cap) and np.diff(to[tiles[0]:tiles[-1] + 2]).max() <= cap
+            for j, k in enumerate(tiles):
+                p0, n, npt, ns, seg_off, pt_off, o0, code = tm[k]
+                assert (p0, npt, n, ns, o0) == (p, 1, to[k + 1] - to[k], to[k + 1] - to[k], to[k])
+                assert code & 0x3fffffff == s["hv_ptr"][h] + j + 1 and bool(code >> 30) == (j == 0)
+                assert s["pt_tab"][pt_off:pt_off + 2].tolist() == [0, n]
+        for k in np.flatnonzero(~frag):  # every other tile holds whole points
+            p0, n, npt, ns, seg_off, pt_off, o0, code = tm[k]
+            assert code == 0 and (p0, o0) == (tp[k], to[k]) and to[k] == pptr[p0] and to[k + 1] == pptr[p0 + npt]
+            assert np.array_equal(s["pt_tab"][pt_off:pt_off + npt + 1], pptr[p0:p0 + npt + 1] - to[k])
+        # slots: a permutation of the tile's positions, sorted by camera; rows of a super-tile = its distinct cameras
+        slot = s["slot_of_obs"]
+        assert sorted(slot.tolist()) == sorted(np.concatenate([k * 256 + np.arange(to[k + 1] - to[k]) for k in range(nt)]).tolist())
+        st_tile, st_row, row_cam = s["st_tile"], s["st_row"], s["row_cam"]
+        assert np.diff(st_row).max() <= kw.get("slot_cap", 192)
+        for sidx in range(len(st_tile) - 1):
+            rows = row_cam[st_row[sidx]:st_row[sidx + 1]]
+            assert np.array_equal(np.unique(prob.cam_idx[to[st_tile[sidx]]:to[st_tile[sidx + 1]]]), rows)
