@@ -521,8 +521,21 @@ def main():
                    "achieved": step_gbps, "peak": peak, "unit": "GB/s", "frac": step_gbps / peak,
                    "note": "SURVEY 8(d) algorithmic bytes per LM iteration (implicit Schur), per rank, with the executed PCG "
                            "iterations; at 10 PCG iterations and every step accepted the same formula gives 15.8 GB (Venice FP64)"}
-    if args.solver != "pcg-schur":  # the product kernel is not event-timed on the full-system solver's host-driven loop
-        roofline = None
+    if args.solver != "pcg-schur":
+        # Full-system PCG (PCGSolver, solver/pcg.hpp): the loop is device-resident (no host reads inside a solve), so the CUDA
+        # events around the solve time its iterations.  Algorithmic bytes of ONE iteration in this layout: the J^T J product
+        # (Jacobians + meta + tile tables, the direction's point part in and the point sums out, camera rows) plus the
+        # vector kernels over the 9 Nc + 3 Np unknowns (direction 5 passes, v2 / p.v2 6, x / r update 7, preconditioner 4).
+        dimH = 9 * nc + 3 * local.n_pts
+        full_bytes = (info["n_obs"] * (24 * sS + 4) + info["n_tiles"] * (2400 - 1024) + local.n_pts * 9 * sT
+                      + 2 * info["n_partial_rows"] * 9 * sT + 22 * dimH * sT)
+        ach = full_bytes * k_total / pcg_seconds / 1e9
+        roofline = {"bound": "hbm", "kernel": "full-system PCG iteration (k_schur_product2<FULL> on the TMA pipeline + the vector "
+                                               "kernels of the device-resident loop), CUDA events around each solve",
+                    "achieved": ach, "peak": peak, "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
+                    "unit": "GB/s", "frac": ach / peak, "traffic": None, "bytes_per_pcg_iteration": full_bytes,
+                    "pcg_iterations_timed": k_total, "ms_per_pcg_iteration": 1e3 * pcg_seconds / k_total,
+                    "share_of_step": pcg_seconds / max(res["seconds_total"], 1e-12)}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps_done, "warmup": args.warmup,

@@ -161,9 +161,10 @@ template <typename T, typename S> struct Problem : ProblemBase {
   void *p2p_area = nullptr;                  // own receive area + flag words (one cudaMalloc, exported by cudaIpc)
   void *p2p_peer[P2P_MAX_RANKS] = {nullptr}; // peers' areas as mapped here
   // full-system PCG (solver/pcg.hpp): work vectors of the whole Hessian dimension, allocated on first use
-  T *f_x = nullptr, *f_r = nullptr, *f_y = nullptr, *f_z = nullptr, *f_p = nullptr, *f_v2 = nullptr, *f_xbak = nullptr;
+  T *f_x = nullptr, *f_r = nullptr, *f_z = nullptr, *f_p = nullptr, *f_v2 = nullptr, *f_xbak = nullptr;
   T *f_upw = nullptr, *f_outp = nullptr, *f_zero = nullptr, *f_Bfull = nullptr, *f_MinvF = nullptr, *f_part = nullptr;
-  T *f_scal = nullptr;
+  FullState<T> *f_state = nullptr, *h_fstate = nullptr; // PCG scalars of the full-system solver (device) and their pinned host copy
+  bool full_info_pending = false;
   double *f_rho = nullptr;
   bool full_alloc = false, full_lin_valid = false, solved_full = false;
   int full_blocks = 0;
@@ -185,6 +186,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     if (h_scalars) cudaFreeHost(h_scalars);
     if (h_state) cudaFreeHost(h_state);
     if (h_p2p_err) cudaFreeHost(h_p2p_err);
+    if (h_fstate) cudaFreeHost(h_fstate);
     for (auto &e : ev) if (e) cudaEventDestroy(e);
     if (h_timing) cudaFreeHost(h_timing);
     for (auto &e : ev_stage) if (e) cudaEventDestroy(e);
@@ -798,7 +800,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     if (full_alloc) return GB_OK;
     GB_TRY(require(ctx->nranks == 1, "the full-system PCG solver is single-rank"));
     const size_t n = (size_t)dimH;
-    GB_TRY(dalloc(f_x, n)); GB_TRY(dalloc(f_r, n)); GB_TRY(dalloc(f_y, n)); GB_TRY(dalloc(f_z, n));
+    GB_TRY(dalloc(f_x, n)); GB_TRY(dalloc(f_r, n)); GB_TRY(dalloc(f_z, n));
     GB_TRY(dalloc(f_p, n)); GB_TRY(dalloc(f_v2, n)); GB_TRY(dalloc(f_xbak, n));
     GB_TRY(dalloc(f_upw, (size_t)WST<T>::value * ts.Np + 8));
     GB_TRY(dalloc(f_outp, 3 * (size_t)ts.Np));
@@ -806,38 +808,47 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_TRY(dalloc(f_Bfull, (size_t)ts.Nc * 81)); GB_TRY(dalloc(f_MinvF, (size_t)ts.Nc * 81));
     full_blocks = (int)((dimH + 255) / 256);
     GB_TRY(dalloc(f_part, full_blocks)); GB_TRY(dalloc(f_rho, full_blocks));
-    GB_TRY(dalloc(f_scal, 4));
+    GB_TRY(dalloc(f_state, 1));
+    GB_CUDA(ctx, cudaMallocHost((void **)&h_fstate, sizeof(FullState<T>)));
     full_alloc = true;
     return GB_OK;
   }
-  // host value of sum_i a_i b_i (two-stage, fixed order)
-  int full_dot(const T *a, const T *bb, T *out) {
+  // One batch of PCG iterations [k0, k1) enqueued without reading anything back: every kernel returns at once when the
+  // device state says the solve has stopped.
+  int enqueue_full_iterations(int64_t k0, int64_t k1, T tol, T ratio, int max_iter) {
     cudaStream_t st = ctx->stream;
-    k_vec_dot<T><<<full_blocks, 256, 0, st>>>(dimH, a, bb, f_part);
-    GB_LAUNCH(ctx);
-    return full_read_sum(out);
-  }
-  int full_read_sum(T *out) {
-    cudaStream_t st = ctx->stream;
-    k_vec_sum<T><<<1, 1024, 0, st>>>(f_part, full_blocks, f_scal);
-    GB_LAUNCH(ctx);
-    GB_TRY(store_host(h_scalars + 4, f_scal, sizeof(T)));
-    GB_CUDA(ctx, cudaStreamSynchronize(st));
-    *out = *reinterpret_cast<const T *>(h_scalars + 4);
+    const int *flag = &f_state->done;
+    for (int64_t k = k0; k < k1; k++) {
+      // p = beta p + z (p = z at the start), u = D p ; v2 = J~^T J~ p + mu clamp(diag) p   (pcg.hpp:141-168)
+      k_full_direction<T><<<full_blocks, 256, 0, st>>>(ts.Nc, ts.Np, k == 0 ? 1 : 0, f_state, f_p, f_z, scale, xs, f_upw);
+      GB_LAUNCH(ctx);
+      GB_TRY(launch_product<true>(f_upw, flag, f_outp));
+      k_cam_reduce_spmv<T><<<ts.Nc, 288, 0, st>>>(ts, part9, scale, Ap_raw, 0, dterm, nullptr, Ap, dot_part, flag, pp, 0);
+      GB_LAUNCH(ctx);
+      k_full_finish_v2<T><<<full_blocks, 256, 0, st>>>(ts.Nc, ts.Np, mu, use_identity, Ap_raw, f_outp, f_p, scale, diagB, Cg,
+                                                       f_v2, f_part, flag);
+      GB_LAUNCH(ctx);
+      k_full_scalar<T><<<1, 1024, 0, st>>>(2, f_part, full_blocks, f_state, tol, ratio, max_iter); // alpha = rz / p.v2
+      GB_LAUNCH(ctx);
+      k_full_update_xr<T><<<full_blocks, 256, 0, st>>>(dimH, f_state, f_p, f_v2, f_x, f_xbak, f_r, f_part);
+      GB_LAUNCH(ctx);
+      k_full_scalar<T><<<1, 1024, 0, st>>>(3, f_part, full_blocks, f_state, tol, ratio, max_iter); // 1 / |r|
+      GB_LAUNCH(ctx);
+      k_full_precond<T><<<full_blocks, 256, 0, st>>>(ts.Nc, ts.Np, f_state, f_MinvF, W, scale, f_r, f_z, f_part, 1);
+      GB_LAUNCH(ctx);
+      k_full_scalar<T><<<1, 1024, 0, st>>>(4, f_part, full_blocks, f_state, tol, ratio, max_iter); // r.z, tests, beta
+      GB_LAUNCH(ctx);
+    }
     return GB_OK;
   }
-  // y = r / |r| ; z = M^-1 y   (pcg.hpp:108-121, 184-192)
-  int full_precondition() {
-    cudaStream_t st = ctx->stream;
-    T rr;
-    GB_TRY(full_dot(f_r, f_r, &rr));
-    const T rnorm = std::sqrt(rr);
-    const T sc = (T)(1.0 / rnorm);
-    k_vec_scale<T><<<full_blocks, 256, 0, st>>>(dimH, f_y, sc, f_r);
-    GB_LAUNCH(ctx);
-    k_full_precond<T><<<full_blocks, 256, 0, st>>>(ts.Nc, ts.Np, f_MinvF, W, scale, f_y, f_z);
-    GB_LAUNCH(ctx);
-    return GB_OK;
+  // the state of the finished solve as the host sees it (after a synchronise of the stream)
+  void full_finish_info() {
+    if (!full_info_pending) return;
+    full_info = gb_solve_info{};
+    full_info.pcg_iterations = h_fstate->iter;
+    full_info.rz_final = (double)h_fstate->rzn;
+    full_info.stop_reason = h_fstate->reason;
+    full_info_pending = false;
   }
   int solve_full(const gb_pcg_options *o) {
     cudaStream_t st = ctx->stream;
@@ -855,51 +866,36 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_LAUNCH(ctx);
     k_full_cam_blocks<T><<<ts.Nc, 288, 0, st>>>(ts, part54, mu, use_identity, scale, f_Bfull, f_MinvF);
     GB_LAUNCH(ctx);
-    GB_CUDA(ctx, cudaMemsetAsync(f_x, 0, nbytes, st));
-    GB_CUDA(ctx, cudaMemcpyAsync(f_r, b, nbytes, cudaMemcpyDeviceToDevice, st));
-    GB_TRY(full_precondition());
-    GB_CUDA(ctx, cudaMemcpyAsync(f_p, f_z, nbytes, cudaMemcpyDeviceToDevice, st));
-    T rz;
-    GB_TRY(full_dot(f_r, f_z, &rz));
-    T rz0 = std::numeric_limits<T>::infinity();
     const T tol = (T)o->tolerance, ratio = (T)o->rejection_ratio;
-    full_info = gb_solve_info{};
-    for (int64_t k = 0; k < o->max_iterations; k++) {
-      if (rz == T(0)) { full_info.stop_reason = 3; break; }
-      // v2 = J~^T J~ p + mu clamp(diag) p   (pcg.hpp:141-168)
-      k_full_build_u<T><<<full_blocks, 256, 0, st>>>(ts.Nc, ts.Np, f_p, scale, xs, f_upw);
-      GB_LAUNCH(ctx);
-      GB_TRY(launch_product<true>(f_upw, nullptr, f_outp));
-      k_cam_reduce_spmv<T><<<ts.Nc, 288, 0, st>>>(ts, part9, scale, Ap_raw, 0, dterm, nullptr, Ap, dot_part, nullptr, pp, 0);
-      GB_LAUNCH(ctx);
-      k_full_finish_v2<T><<<full_blocks, 256, 0, st>>>(ts.Nc, ts.Np, mu, use_identity, Ap_raw, f_outp, f_p, scale, diagB, Cg,
-                                                       f_v2, f_part);
-      GB_LAUNCH(ctx);
-      T pv2;
-      GB_TRY(full_read_sum(&pv2));
-      const T alpha = rz / pv2;
-      GB_CUDA(ctx, cudaMemcpyAsync(f_xbak, f_x, nbytes, cudaMemcpyDeviceToDevice, st));
-      k_vec_axpy<T><<<full_blocks, 256, 0, st>>>(dimH, f_x, alpha, f_p, f_x);
-      GB_LAUNCH(ctx);
-      k_vec_axpy<T><<<full_blocks, 256, 0, st>>>(dimH, f_r, -alpha, f_v2, f_r);
-      GB_LAUNCH(ctx);
-      GB_TRY(full_precondition());
-      T rzn;
-      GB_TRY(full_dot(f_r, f_z, &rzn));
-      full_info.pcg_iterations = k + 1;
-      full_info.rz_final = (double)rzn;
-      if (std::abs(rzn) > ratio * rz0 || std::isnan(rzn)) {
-        GB_CUDA(ctx, cudaMemcpyAsync(f_x, f_xbak, nbytes, cudaMemcpyDeviceToDevice, st));
-        full_info.stop_reason = 2;
-        break;
+    const int max_iter = (int)o->max_iterations;
+    // x = 0 ; r = b ; y = r / |r| ; z = M^-1 y ; rz = r.z   (pcg.hpp:93-121)
+    GB_CUDA(ctx, cudaMemsetAsync(f_x, 0, nbytes, st));
+    k_copy<T><<<4 * 148, 256, 0, st>>>((int64_t)dimH, b, f_r);
+    GB_LAUNCH(ctx);
+    k_vec_dot<T><<<full_blocks, 256, 0, st>>>(dimH, f_r, f_r, f_part);
+    GB_LAUNCH(ctx);
+    k_full_scalar<T><<<1, 1024, 0, st>>>(0, f_part, full_blocks, f_state, tol, ratio, max_iter);
+    GB_LAUNCH(ctx);
+    k_full_precond<T><<<full_blocks, 256, 0, st>>>(ts.Nc, ts.Np, f_state, f_MinvF, W, scale, f_r, f_z, f_part, 0);
+    GB_LAUNCH(ctx);
+    k_full_scalar<T><<<1, 1024, 0, st>>>(1, f_part, full_blocks, f_state, tol, ratio, max_iter);
+    GB_LAUNCH(ctx);
+    // Iterations in batches: the whole solve when it is short (the BAL protocol's 10 iterations: no read-back at all), else
+    // 32 at a time with one look at the state in between, so that a converged solve does not pay for thousands of launches
+    // that return at once.
+    constexpr int64_t BATCH = 32;
+    for (int64_t k0 = 0; k0 < max_iter; k0 += BATCH) {
+      if (k0 > 0) {
+        GB_TRY(store_host(h_fstate, f_state, sizeof(FullState<T>)));
+        GB_CUDA(ctx, cudaStreamSynchronize(st));
+        if (h_fstate->done) break;
       }
-      rz0 = std::min(rz0, std::abs(rzn));
-      const T beta = rzn / rz;
-      rz = rzn;
-      k_vec_axpy<T><<<full_blocks, 256, 0, st>>>(dimH, f_p, beta, f_p, f_z);
-      GB_LAUNCH(ctx);
-      if (std::abs(rzn) < tol) { full_info.stop_reason = 1; break; }
+      GB_TRY(enqueue_full_iterations(k0, std::min<int64_t>(max_iter, k0 + BATCH), tol, ratio, max_iter));
     }
+    k_full_restore<T><<<4 * 148, 256, 0, st>>>((int64_t)dimH, f_state, f_xbak, f_x);
+    GB_LAUNCH(ctx);
+    GB_TRY(store_host(h_fstate, f_state, sizeof(FullState<T>)));
+    full_info_pending = true; // read by full_finish_info() after the caller's synchronise
     GB_TRY(launch_check());
     last_pcg = *o;
     solved_full = true;
@@ -1327,6 +1323,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
         GB_TRY(d2h(delta_host, delta, dimH * sizeof(T)));
       }
       GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      full_finish_info();
       if (info) *info = full_info;
       return GB_OK;
     }
@@ -1545,6 +1542,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
       if (!solve_ok) new_chi2 = std::numeric_limits<T>::max();
       const T denom = solve_ok ? (T)(h_scalars[1] + h_scalars[2]) + (T)1.0e-3 : T(1);
       const T rho = (chi2 - new_chi2) / denom;
+      if (full) full_finish_info(); // (the stream was synchronised by fetch_scalars)
       const int64_t k_exec = full ? full_info.pcg_iterations : h_state->iter;
       if (!full) pcg_guess = k_exec;
       R.pcg_iterations_total += k_exec;

@@ -1664,9 +1664,17 @@ k_cost_tiles(DevStruct ds, const T *__restrict__ cams, const T *__restrict__ pts
 
 // ---------------------------------------------------------------------------------------------
 // Full-system matrix-free PCG (solver/pcg.hpp:61-232 + preconditioner/block_jacobi.hpp): small vector kernels.
-// The loop is driven from the host like the reference's (blocking scalar reads); the reductions are two-stage with
-// a fixed order.  Vector layout: [9 Nc camera scalars | 3 Np point scalars], scaled space.
+// The loop is DEVICE-RESIDENT: the PCG scalars (r.z, alpha, beta, 1/|r|, stop reason) live in a FullState on the device,
+// written by one-CTA k_full_scalar launches from two-stage fixed-order reductions; every kernel of an iteration returns at
+// once when the state says the solve has stopped, so the host enqueues whole batches of iterations without reading anything
+// back (the reference: three blocking scalar reads per iteration, pcg.hpp:108-192).  Vector layout: [9 Nc camera scalars |
+// 3 Np point scalars], scaled space.
 // ---------------------------------------------------------------------------------------------
+// PCG state of the full-system solver on the device
+template <typename T> struct FullState {
+  T rz, rz0, alpha, beta, sc /*1 / |r|*/, rzn;
+  int iter, done, reason, pad;
+};
 // per-camera: full scaled block B~ (from the 45 packed sums), damped diagonal, inverse (block-parallel Gauss-Jordan)
 template <typename T>
 __global__ void __launch_bounds__(288)
@@ -1693,17 +1701,6 @@ k_full_cam_blocks(DevStruct ds, const T *__restrict__ part /*[nrows][54]*/, T mu
     MinvF[(int64_t)c * 81 + i + 9 * j] = Maug[i * 18 + 9 + j];
   }
 }
-// u = D p: cameras into the 10-padded rows read by the product kernel, points into the W-strided stage buffer
-template <typename T>
-__global__ void k_full_build_u(int Nc, int Np, const T *__restrict__ p, const T *__restrict__ scale, T *__restrict__ xs,
-                               T *__restrict__ upw) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t dimc = 9 * (int64_t)Nc, n = dimc + 3 * (int64_t)Np;
-  if (i >= n) return;
-  const T v = scale[i] * p[i];
-  if (i < dimc) xs[(i / 9) * CAM_STRIDE + i % 9] = v;
-  else upw[((i - dimc) / 3) * WST<T>::value + (i - dimc) % 3] = v;
-}
 // clamped scalar diagonal of J~^T J~ (pcg.hpp:93-104): cameras from diag(B), points from diag(C)
 template <typename T>
 __device__ __forceinline__ T full_diag(int64_t i, int64_t dimc, const T *diagB, const T *Cg, const T *scale) {
@@ -1722,8 +1719,9 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k_full_finish_v2(int Nc, int Np, T mu, int use_identity, const T *__restrict__ Ap_raw, const T *__restrict__ out_p,
                  const T *__restrict__ p, const T *__restrict__ scale, const T *__restrict__ diagB, const T *__restrict__ Cg,
-                 T *__restrict__ v2, T *__restrict__ partial) {
+                 T *__restrict__ v2, T *__restrict__ partial, const int *__restrict__ done_flag) {
   __shared__ T sh[32];
+  if (done_flag && *done_flag) return;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t dimc = 9 * (int64_t)Nc, n = dimc + 3 * (int64_t)Np;
   T prod = T(0);
@@ -1745,48 +1743,127 @@ k_vec_dot(int64_t n, const T *__restrict__ a, const T *__restrict__ b, T *__rest
   const T tot = block_sum<T>(i < n ? a[i] * b[i] : T(0), sh);
   if (threadIdx.x == 0) partial[blockIdx.x] = tot;
 }
+// y = r / |r| ; z = M^-1 y: 9x9 blocks for the cameras (MinvF), 3x3 for the points (D^-1 W D^-1, W from k_point_prepare);
+// per-block partial of r.z   (pcg.hpp:108-121, 184-192; y is formed on the fly with the rounding of the stored vector)
 template <typename T>
-__global__ void __launch_bounds__(1024) k_vec_sum(const T *__restrict__ partial, int n, T *__restrict__ out) {
+__global__ void __launch_bounds__(256)
+k_full_precond(int Nc, int Np, const FullState<T> *__restrict__ st, const T *__restrict__ MinvF, const T *__restrict__ W,
+               const T *__restrict__ scale, const T *__restrict__ r, T *__restrict__ z, T *__restrict__ partial, int check_done) {
   __shared__ T sh[32];
-  const T tot = sum_all<T>(partial, n, sh);
-  if (threadIdx.x == 0) *out = tot;
-}
-// z = a x + y (ops/vector.hpp:6-14) ; out = s x (:69-78)
-template <typename T> __global__ void k_vec_axpy(int64_t n, T *z, T a, const T *x, const T *y) {
+  if (check_done && st->done) return;
+  const T sc = st->sc;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) z[i] = a * x[i] + y[i];
+  const int64_t dimc = 9 * (int64_t)Nc, n = dimc + 3 * (int64_t)Np;
+  T prod = T(0);
+  if (i < n) {
+    T zi;
+    if (i < dimc) {
+      const int64_t c = i / 9;
+      const int k = (int)(i % 9);
+      const T *m = MinvF + c * 81;
+      T acc = T(0);
+#pragma unroll
+      for (int j = 0; j < 9; j++) acc += m[k + 9 * j] * (sc * r[c * 9 + j]);
+      zi = acc;
+    } else {
+      const int64_t q = (i - dimc) / 3;
+      const int k = (int)((i - dimc) % 3);
+      const T *w = W + q * WST<T>::value;
+      const T *sp = scale + dimc + 3 * q, *rr = r + dimc + 3 * q;
+      if (sp[0] == T(0)) {
+        zi = T(0); // fixed point
+      } else {
+        const T a0 = (sc * rr[0]) / sp[0], a1 = (sc * rr[1]) / sp[1], a2 = (sc * rr[2]) / sp[2];
+        const T v = k == 0 ? w[0] * a0 + w[1] * a1 + w[2] * a2
+                  : (k == 1 ? w[1] * a0 + w[3] * a1 + w[4] * a2 : w[2] * a0 + w[4] * a1 + w[5] * a2);
+        zi = v / sp[k];
+      }
+    }
+    z[i] = zi;
+    prod = r[i] * zi;
+  }
+  const T tot = block_sum<T>(prod, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
 }
-template <typename T> __global__ void k_vec_scale(int64_t n, T *out, T s, const T *x) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = s * x[i];
-}
-// z = M^-1 y: 9x9 blocks for the cameras (MinvF), 3x3 for the points (D^-1 W D^-1, W from k_point_prepare)
+// One CTA: tot = fixed-order sum of the per-block partials, then the scalar step `stage` of the loop (pcg.hpp:93-232):
+//   0  1/|r| from r.r at the start       1  rz = r.z at the start, state reset, rz == 0 / max_iter == 0 stops
+//   2  alpha = rz / p.v2                  3  1/|r| from r.r
+//   4  rz_new: iteration count, rejection (reason 2), beta, convergence (1), iteration limit (0), rz == 0 (3)
 template <typename T>
-__global__ void k_full_precond(int Nc, int Np, const T *__restrict__ MinvF, const T *__restrict__ W,
-                               const T *__restrict__ scale, const T *__restrict__ y, T *__restrict__ z) {
+__global__ void __launch_bounds__(1024)
+k_full_scalar(int stage, const T *__restrict__ partial, int n, FullState<T> *st, T tol, T ratio, int max_iter) {
+  __shared__ T sh[32];
+  if (stage >= 2 && st->done) return;
+  const T tot = sum_all<T>(partial, n, sh);
+  if (threadIdx.x != 0) return;
+  FullState<T> s = *st;
+  if (stage == 0 || stage == 3) {
+    s.sc = (T)(1.0 / sqrt(tot)); // y = r / |r| (pcg.hpp:108-121): the division runs in double as on the host
+  } else if (stage == 1) {
+    s.rz = tot; s.rz0 = (T)INFINITY; s.alpha = T(0); s.beta = T(0); s.rzn = T(0);
+    s.iter = 0; s.done = 0; s.reason = 0; s.pad = 0;
+    if (max_iter <= 0) s.done = 1;
+    else if (tot == T(0)) { s.done = 1; s.reason = 3; }
+  } else if (stage == 2) {
+    s.alpha = s.rz / tot;
+  } else {
+    s.iter += 1;
+    s.rzn = tot;
+    if (fabs(tot) > ratio * s.rz0 || isnan(tot)) { // rejected iterate: x is restored by k_full_restore
+      s.done = 1; s.reason = 2;
+    } else {
+      s.rz0 = fmin(s.rz0, fabs(tot));
+      s.beta = tot / s.rz;
+      s.rz = tot;
+      if (fabs(tot) < tol) { s.done = 1; s.reason = 1; }
+      else if (s.iter >= max_iter) { s.done = 1; s.reason = 0; }
+      else if (tot == T(0)) { s.done = 1; s.reason = 3; }
+    }
+  }
+  *st = s;
+}
+// p = first ? z : beta p + z (ops::axpy), then u = D p: cameras into the 10-padded rows read by the product kernel,
+// points into the W-strided stage buffer
+template <typename T>
+__global__ void k_full_direction(int Nc, int Np, int first, const FullState<T> *__restrict__ st, T *__restrict__ p,
+                                 const T *__restrict__ z, const T *__restrict__ scale, T *__restrict__ xs, T *__restrict__ upw) {
+  if (st->done) return;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t dimc = 9 * (int64_t)Nc, n = dimc + 3 * (int64_t)Np;
   if (i >= n) return;
-  if (i < dimc) {
-    const int64_t c = i / 9;
-    const int k = (int)(i % 9);
-    const T *m = MinvF + c * 81;
-    T acc = T(0);
-#pragma unroll
-    for (int j = 0; j < 9; j++) acc += m[k + 9 * j] * y[c * 9 + j];
-    z[i] = acc;
-  } else {
-    const int64_t q = (i - dimc) / 3;
-    const int k = (int)((i - dimc) % 3);
-    const T *w = W + q * WST<T>::value;
-    const T *sc = scale + dimc + 3 * q, *yy = y + dimc + 3 * q;
-    if (sc[0] == T(0)) { z[i] = T(0); return; } // fixed point
-    const T a0 = yy[0] / sc[0], a1 = yy[1] / sc[1], a2 = yy[2] / sc[2];
-    const T r = k == 0 ? w[0] * a0 + w[1] * a1 + w[2] * a2
-              : (k == 1 ? w[1] * a0 + w[3] * a1 + w[4] * a2 : w[2] * a0 + w[4] * a1 + w[5] * a2);
-    z[i] = r / sc[k];
-  }
+  const T pn = first ? z[i] : st->beta * p[i] + z[i];
+  p[i] = pn;
+  const T v = scale[i] * pn;
+  if (i < dimc) xs[(i / 9) * CAM_STRIDE + i % 9] = v;
+  else upw[((i - dimc) / 3) * WST<T>::value + (i - dimc) % 3] = v;
 }
+// xbak = x ; x += alpha p ; r -= alpha v2 ; per-block partial of r.r
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_full_update_xr(int64_t n, const FullState<T> *__restrict__ st, const T *__restrict__ p, const T *__restrict__ v2,
+                 T *__restrict__ x, T *__restrict__ xbak, T *__restrict__ r, T *__restrict__ partial) {
+  __shared__ T sh[32];
+  if (st->done) return;
+  const T alpha = st->alpha;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  T rn = T(0);
+  if (i < n) {
+    const T xo = x[i];
+    xbak[i] = xo;
+    x[i] = alpha * p[i] + xo;
+    rn = -alpha * v2[i] + r[i];
+    r[i] = rn;
+  }
+  const T tot = block_sum<T>(rn * rn, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+// rejected iterate (pcg.hpp:194-199): x = xbak
+template <typename T>
+__global__ void k_full_restore(int64_t n, const FullState<T> *__restrict__ st, const T *__restrict__ xbak, T *__restrict__ x) {
+  if (st->reason != 2) return;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] = xbak[i];
+}
+
 // point part of the step for the full-system solver: delta_p = x_p, rho partial, backup + update (ops/update.hpp:9-31)
 template <typename T>
 __global__ void __launch_bounds__(256)
