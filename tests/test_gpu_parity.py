@@ -970,3 +970,56 @@ def test_long_tracks_step_and_vertices(ctx):
     c2, p2 = P.get_vertices()
     assert np.array_equal(c0, c2) and np.array_equal(p0, p2)
     P.close()
+
+
+def test_long_tracks_with_loss_weights_fixed_vertices_and_unsorted_input(ctx):
+    """The long-track problem given in a shuffled factor order, with Huber loss, per-factor precision matrices and fixed
+    vertices (one of the long-track points among them): first linearisation, reduced system and one solve against the
+    oracle; the LM trajectories with the robust cost agree while the run is above the rounding-noise regime."""
+    prob = named_problem("long-tracks")
+    rng = np.random.default_rng(11)
+    perm = rng.permutation(prob.n_obs)
+    shuffled = synthetic.BALProblem(prob.cam_idx[perm], prob.pt_idx[perm], prob.obs[perm], prob.cams, prob.pts, "shuffled")
+    Pm = synthetic.precision_matrices(prob.n_obs)
+    P = binding.problem_from_bal(ctx, shuffled, "f64-f64")
+    P.set_loss("huber", 20.0)
+    P.set_precision(Pm[perm])
+    O = Oracle(prob)
+    O.set_robust("huber", 20.0, Pm)
+    chi2 = P.linearize()
+    ochi2, osc, ob = O.linearize()
+    assert abs(chi2 - ochi2) <= 1e-13 * ochi2
+    assert rel(P.scales(), osc) <= 1e-12 and rel(P.gradient(), ob) <= 1e-12
+    r, _ = Oracle(prob).residuals()
+    assert rel(P.residuals(), r[perm]) <= 1e-13, "residuals come back in the caller's factor order"
+    assert rel(P.hessian_values(), O.hessian_values()) <= 1e-12
+    for mu in (1e-4, 1e-1):
+        P.set_damping(mu)
+        S, obS = O.schur(mu)
+        assert rel(P.schur_rhs(), obS) <= 1e-11
+        Sfull = np.triu(S) + np.triu(S, 1).T
+        x = rng.normal(size=9 * prob.n_cams)
+        assert rel(P.schur_multiply(x), Sfull @ x) <= 1e-11
+        d, info = P.solve(20, 1e-14, 5.0)
+        od, ok = O.solve(mu, default_options(pcg_iterations=20, pcg_tolerance=1e-14))
+        assert info["pcg_iterations"] == ok and rel(d, od) <= 1e-9
+    traj, _ = P.lm(iterations=6)
+    otraj = O.lm(default_options(iterations=6))
+    assert np.abs(traj[:, 1] - otraj[:, 1]).max() <= 1e-8 * otraj[0, 0]
+    assert np.array_equal(traj[:, 0] == traj[:, 1], otraj[:, 0] == otraj[:, 1])
+    # fixed vertices: two cameras and every 50th point, which includes long-track point 0 and point 300
+    P.set_loss("default"); P.set_precision(None)
+    fc, fp = np.zeros(prob.n_cams, np.uint8), np.zeros(prob.n_pts, np.uint8)
+    fc[:2] = 1
+    fp[::50] = 1
+    P.set_fixed(fc, fp)
+    P.set_vertices(prob.cams, prob.pts)
+    tf, _ = P.lm(iterations=8)
+    cams, pts = P.get_vertices()
+    assert np.array_equal(cams[:2], prob.cams[:2]) and np.array_equal(pts[::50], prob.pts[::50]), "fixed vertices do not move"
+    assert tf[-1, 1] < tf[0, 0], "and the rest of the problem is still optimised"
+    for mode in ("explicit",):
+        P.set_vertices(prob.cams, prob.pts)
+        te, _ = P.lm(iterations=8, schur_mode=mode)
+        assert np.abs(te[:, 1] - tf[:, 1]).max() <= 1e-9 * tf[0, 0] and np.array_equal(te[:, 3], tf[:, 3])
+    P.close()
