@@ -721,7 +721,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
   }
   int enqueue_frag_dots(const int *flag) {
     if (ts.nheavy == 0) return GB_OK;
-    k_frag_dots<T, S><<<ts.nheavy, 256, 0, ctx->stream>>>(ts, J, xs, flag);
+    k_frag_dots<T, S><<<(ts.nheavy + FRAG_DOT_WARPS - 1) / FRAG_DOT_WARPS, FRAG_DOT_WARPS * 32, 0, ctx->stream>>>(ts, J, xs, flag);
     GB_LAUNCH(ctx);
     return GB_OK;
   }

@@ -1133,8 +1133,8 @@ k_schur_product2(DevStruct ds, const typename V2<S>::type *__restrict__ J, const
 //   * sums a tile WRITES (C and g of k_linearize, the point part of the full-system product): every fragment leaves its
 //     partial in frag_part, k_frag_sum adds the fragments of a point in ascending order;
 //   * the sum a tile READS before it can go on (t_p = sum_o Jp^T Jc x_c of the Schur product and of the back-
-//     substitution): heavy_point_dot forms it over all observations of the point BEFORE the tile kernels run
-//     (k_frag_dots, or phase H of k_pcg_solve) and leaves it in frag_t for every fragment of the point.
+//     substitution): heavy_point_dot (one warp per point) forms it over all observations of the point BEFORE the tile
+//     kernels run (k_frag_dots, or phase H of k_pcg_solve) and leaves it in frag_t for every fragment of the point.
 // Both are exact restatements of the single-tile sums (other summation order), deterministic, atomic-free.
 // ---------------------------------------------------------------------------------------------
 template <typename T>
@@ -1147,19 +1147,21 @@ __global__ void k_frag_sum(int nheavy, const int32_t *__restrict__ hv_pt, const 
   for (int f = hv_ptr[hp]; f < hv_ptr[hp + 1]; f++) a += frag_part[(int64_t)f * width + k];
   out[(int64_t)hv_pt[hp] * width + k] = a;
 }
-// t = sum over all observations of long-track point number hp of Jp^T (Jc x_c), x_c(j) = getx(c, j); every thread of
-// the CTA must call it; the result goes to frag_t of all the point's fragments.  sh: 3 * 32 values of T.
+// t = sum over all observations of long-track point number hp of Jp^T (Jc x_c), x_c(j) = getx(c, j), by ONE WARP (all 32
+// lanes must call it; no shared memory, no barrier): lanes stride over the point's observations - which are contiguous
+// slots of its fragment tiles, so the twelve plane loads are coalesced - then a fixed shuffle tree; the result goes to
+// frag_t of all the point's fragments.  One warp per point keeps many points in flight per SM (a real BAL set can have
+// thousands of long tracks); a 2000-observation track costs its warp ~60 dependent rounds, which only that warp waits for.
 // The sum runs in DOUBLE whatever T is: a landmark seen by hundreds of cameras is typically far away and weakly
 // constrained in depth, so its W has a large eigenvalue (~1 / damping) that amplifies the rounding error of a 400-term
-// float sum.  The long tracks are few: the cost is not measurable.
+// float sum.
 template <typename T, typename S, typename GetX>
-__device__ __forceinline__ void heavy_point_dot(const DevStruct &ds, const typename V2<S>::type *__restrict__ J, int hp,
-                                                T *sh_T, GetX &&getx) {
-  double *sh = reinterpret_cast<double *>(sh_T); // 3 * 32 doubles (the callers provide 768 bytes)
+__device__ __forceinline__ void heavy_point_dot(const DevStruct &ds, const typename V2<S>::type *__restrict__ J, int hp, GetX &&getx) {
+  const int lane = threadIdx.x & 31;
   const int p = ds.hv_pt[hp];
   const int b = ds.pptr[p], e = ds.pptr[p + 1];
   double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-  for (int o = b + (int)threadIdx.x; o < e; o += (int)blockDim.x) {
+  for (int o = b + lane; o < e; o += 32) {
     const int slot = ds.slot_of_obs[o], c = ds.cam_idx[o];
     T jc[18], jp[6];
     double y0 = 0.0, y1 = 0.0;
@@ -1180,24 +1182,23 @@ __device__ __forceinline__ void heavy_point_dot(const DevStruct &ds, const typen
     a1 += __shfl_down_sync(0xffffffffu, a1, o);
     a2 += __shfl_down_sync(0xffffffffu, a2, o);
   }
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = ((int)blockDim.x + 31) >> 5;
-  __syncthreads(); // sh may still be read from the previous point
-  if (lane == 0) { sh[w] = a0; sh[32 + w] = a1; sh[64 + w] = a2; }
-  __syncthreads();
-  if (threadIdx.x < 3) {
-    double tot = 0.0;
-    for (int i = 0; i < nw; i++) tot += sh[32 * threadIdx.x + i];
+  if (lane == 0) {
     T *ft = reinterpret_cast<T *>(ds.frag_t);
-    for (int f = ds.hv_ptr[hp]; f < ds.hv_ptr[hp + 1]; f++) ft[(int64_t)f * 3 + threadIdx.x] = (T)tot;
+    for (int f = ds.hv_ptr[hp]; f < ds.hv_ptr[hp + 1]; f++) {
+      ft[(int64_t)f * 3] = (T)a0;
+      ft[(int64_t)f * 3 + 1] = (T)a1;
+      ft[(int64_t)f * 3 + 2] = (T)a2;
+    }
   }
 }
-// one CTA per long-track point; xs = D_c x in 10-padded camera rows
+// one warp per long-track point; xs = D_c x in 10-padded camera rows
+constexpr int FRAG_DOT_WARPS = 8;
 template <typename T, typename S>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(FRAG_DOT_WARPS * 32)
 k_frag_dots(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *__restrict__ xs, const int *__restrict__ done_flag) {
-  __shared__ double sh[96];
   if (done_flag && *done_flag) return;
-  heavy_point_dot<T, S>(ds, J, (int)blockIdx.x, reinterpret_cast<T *>(sh), [&](int c, int j) { return xs[c * CAM_STRIDE + j]; });
+  const int hp = (int)blockIdx.x * FRAG_DOT_WARPS + ((int)threadIdx.x >> 5);
+  if (hp < ds.nheavy) heavy_point_dot<T, S>(ds, J, hp, [&](int c, int j) { return xs[c * CAM_STRIDE + j]; });
 }
 
 // ---------------------------------------------------------------------------------------------

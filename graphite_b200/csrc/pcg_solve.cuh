@@ -196,10 +196,10 @@ k_pcg_solve(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *_
       solve_publish<T, SOLVE_WARPS>(pdp_w, wpart, cta_red);
     }
     // ---- phase H (only with long tracks, structure.hpp): t_p = sum_o Jp^T Jc (D p)_c over ALL observations of every point
-    // that is cut into fragment tiles, before any of its fragments is multiplied; costs one more grid barrier ----------
+    // that is cut into fragment tiles (one warp per point), before any of its fragments is multiplied; one more grid barrier --
     if (ds.nheavy > 0) {
-      for (int hp = (int)blockIdx.x; hp < ds.nheavy; hp += G)
-        heavy_point_dot<T, S>(ds, J, hp, red, [&](int c, int j) {
+      for (int hp = warp * G + (int)blockIdx.x; hp < ds.nheavy; hp += G * SOLVE_WARPS) // one warp per point, spread over the SMs
+        heavy_point_dot<T, S>(ds, J, hp, [&](int c, int j) {
           const int i = c * 9 + j;
           return scale_c[i] * pcg_direction<T>(beta, __ldcg(p_old + i), __ldcg(z + i));
         });

@@ -185,7 +185,11 @@ def make_long_tracks(n_cams: int = 420, n_pts: int = 900, n_obs: int = 6000, tra
     holds (192), so their observations are cut into fragment tiles (csrc/structure.hpp)."""
     base = make_bal(n_cams, n_pts, n_obs, seed=seed, name="long-tracks")
     rng = np.random.Generator(np.random.PCG64(seed + 77))
-    chosen = [0, n_pts // 3, (2 * n_pts) // 3, n_pts - 1][: len(tracks)]
+    if len(tracks) <= 4:
+        chosen = [0, n_pts // 3, (2 * n_pts) // 3, n_pts - 1][: len(tracks)]
+    else:  # many long tracks: evenly spread over the point range, first and last point included
+        chosen = np.unique(np.linspace(0, n_pts - 1, len(tracks)).astype(np.int64)).tolist()
+        tracks = tracks[: len(chosen)]
     cam_new, pt_new = [], []
     for p, t in zip(chosen, tracks):
         have = base.cam_idx[base.pt_idx == p]

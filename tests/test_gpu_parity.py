@@ -1023,3 +1023,23 @@ def test_long_tracks_with_loss_weights_fixed_vertices_and_unsorted_input(ctx):
         te, _ = P.lm(iterations=8, schur_mode=mode)
         assert np.abs(te[:, 1] - tf[:, 1]).max() <= 1e-9 * tf[0, 0] and np.array_equal(te[:, 3], tf[:, 3])
     P.close()
+
+
+def test_many_long_tracks(ctx):
+    """300 long tracks of 200-420 observations next to 2700 ordinary points (four fifths of the observations sit in fragment
+    tiles): one warp per long-track point forms the point sums (phase H of k_pcg_solve, k_frag_dots); LM trajectory against
+    the oracle, both Schur forms and the full-system solver."""
+    tracks = tuple(200 + (i * 37) % 221 for i in range(300))
+    prob = synthetic.make_long_tracks(n_cams=420, n_pts=3000, n_obs=20000, tracks=tracks, seed=3)
+    assert (np.bincount(prob.pt_idx) > 192).sum() == 300
+    P = binding.problem_from_bal(ctx, prob, "f64-f64")
+    n = 8
+    for solver, oopt, modes in (("pcg-schur", {}, ("implicit", "explicit")), ("pcg", dict(solver=2), ("auto",))):
+        otraj = Oracle(prob).lm(default_options(iterations=n, **oopt))
+        for mode in modes:
+            P.set_vertices(prob.cams, prob.pts)
+            traj, _ = P.lm(iterations=n, solver=solver, schur_mode=mode)
+            r = np.abs(traj[:, 1] - otraj[:, 1]) / otraj[:, 1]
+            assert r.max() <= 1e-9, (solver, mode, r)
+            assert np.array_equal(traj[:, 0] == traj[:, 1], otraj[:, 0] == otraj[:, 1]) and np.array_equal(traj[:, 3], otraj[:, 3])
+    P.close()
