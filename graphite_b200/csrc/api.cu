@@ -131,6 +131,12 @@ template <typename T, typename S> struct Problem : ProblemBase {
   // scales, kept in scale_true.
   static constexpr bool prescaled = IsLowPrecision<S>::value;
   T *scale_true = nullptr;
+  // point sums of the PCG iterations kept by k_pcg_solve for the Jacobian-free back-substitution (k_backsubst_points)
+  static constexpr int TK_MAX = 16; // solves with more iterations stream the Jacobians in the back-substitution instead
+  T *tk_buf = nullptr, *tk_alpha = nullptr;
+  int tk_alloc = 0;   // iterations tk_buf has room for
+  int tk_iters = 0;   // > 0: the last solve left its point sums for this many iterations (0: use k_backsubst_tiles)
+  int rho_pt_n = 0;   // entries of rho_part the last back-substitution wrote
   // fixed vertices (gb_set_fixed): device masks, null when nothing is fixed
   unsigned char *fixed_c = nullptr, *fixed_p = nullptr;
   bool any_fixed = false;
@@ -259,6 +265,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     GB_TRY(upload(ts.pt_idx, hs.pt_idx));
     GB_TRY(upload(ts.pptr, hs.pptr));
     // long tracks: fragment tables and the two-level sum buffers (structure.hpp, kernels.cuh "long tracks")
+    ts.tk = nullptr; ts.tk_alpha = nullptr; ts.tk_cap = 0; ts.pad4 = 0;
     ts.nfrag = hs.nfrag(); ts.nheavy = hs.nheavy();
     GB_TRY(upload(ts.hv_pt, hs.hv_pt)); GB_TRY(upload(ts.hv_ptr, hs.hv_ptr));
     {
@@ -1034,6 +1041,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
   int enqueue_direct(const gb_pcg_options *o) {
     cudaStream_t st = ctx->stream;
     GB_TRY(require(ctx->nranks == 1, "the direct Schur solver is single-rank"));
+    tk_iters = 0;
     const int n = (int)dimc;
     if (dimc > 20000) return ctx->fail(GB_ERR_UNSUPPORTED, "direct Schur solve: 9 n_cams = %ld > 20000 (dense factorisation)", (long)dimc);
     GB_TRY(enqueue_schur_build());
@@ -1080,6 +1088,14 @@ template <typename T, typename S> struct Problem : ProblemBase {
     return GB_OK;
   }
 
+  int ensure_tk(int iters) {
+    if (!tk_alpha) GB_TRY(dalloc(tk_alpha, TK_MAX));
+    if (iters > tk_alloc) {
+      GB_TRY(dalloc(tk_buf, (size_t)iters * 3 * ts.Np)); // (a smaller earlier buffer stays in `allocs` until the problem goes)
+      tk_alloc = iters;
+    }
+    return GB_OK;
+  }
   // PCGSchurSolver::solve (pcg_schur.hpp:79-168) after the Schur / preconditioner values: ONE cooperative launch
   // (k_pcg_solve).  Without peer memory between the ranks (GB_P2P=0, IPC unavailable) the iterations are separate
   // launches with an NCCL all-reduce of S p in between.
@@ -1087,6 +1103,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     cudaStream_t st = ctx->stream;
     const T tol = (T)o->tolerance, ratio = (T)o->rejection_ratio;
     const int max_iter = (int)o->max_iterations;
+    tk_iters = 0;
     last_schur_mode = choose_schur_mode(o);
     if (last_schur_mode == GB_SCHUR_EXPLICIT && (ctx->nranks == 1 || p2p_on)) {
       GB_TRY(enqueue_schur_build());
@@ -1104,6 +1121,13 @@ template <typename T, typename S> struct Problem : ProblemBase {
     } else if (ctx->nranks == 1 || p2p_on) {
       last_schur_mode = GB_SCHUR_IMPLICIT;
       if (profiling) GB_TRY(ensure_timing(o->max_iterations));
+      // short solves (the BAL protocol: 10 iterations) keep their per-iteration point sums: the back-substitution then
+      // reads 3 values per point and iteration instead of streaming the Jacobians once more
+      ts.tk_cap = 0;
+      if (max_iter >= 1 && max_iter <= TK_MAX) {
+        GB_TRY(ensure_tk(max_iter));
+        ts.tk = tk_buf; ts.tk_alpha = tk_alpha; ts.tk_cap = max_iter;
+      }
       const S2 *c_J = J;
       const T *c_W = W, *c_scale = scale, *c_dterm = dterm, *c_Minv = Minv, *c_bS = bS;
       PcgState<T> *stp = pcg_state;
@@ -1120,6 +1144,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
       GB_LAUNCH(ctx);
       GB_TRY(store_host(h_state, pcg_state, sizeof(PcgState<T>)));
       if (profiling) GB_TRY(store_host(h_timing, d_timing, (size_t)(max_iter + 1) * SOLVE_STAMPS * sizeof(unsigned long long)));
+      tk_iters = ts.tk_cap;
     } else {
       last_schur_mode = GB_SCHUR_IMPLICIT;
       GB_TRY(ensure_state_cap(o->max_iterations));
@@ -1173,12 +1198,21 @@ template <typename T, typename S> struct Problem : ProblemBase {
                                               apply ? 1 : 0, apply_scale());
     GB_LAUNCH(ctx);
     if (apply) camx_valid = false;
-    GB_TRY(enqueue_frag_dots(nullptr));
-    k_backsubst_tiles<T, S><<<ts.ntiles, TILE, 0, st>>>(ts, J, W, xs, h, scale + dimc, b + dimc, mu, pts, pts_bak,
-                                                        delta + dimc, rho_part, apply ? 1 : 0, apply_scale() + dimc);
+    if (tk_iters > 0) {
+      // the solve kernel kept t_p(p_k) and alpha_k of its iterations: no pass over the Jacobians
+      const int nb = (ts.Np + 255) / 256;
+      k_backsubst_points<T><<<nb, 256, 0, st>>>(ts, tk_iters, W, h, scale + dimc, b + dimc, mu, pts, pts_bak, delta + dimc, rho_part,
+                                               apply ? 1 : 0, apply_scale() + dimc);
+      rho_pt_n = nb;
+    } else {
+      GB_TRY(enqueue_frag_dots(nullptr));
+      k_backsubst_tiles<T, S><<<ts.ntiles, TILE, 0, st>>>(ts, J, W, xs, h, scale + dimc, b + dimc, mu, pts, pts_bak,
+                                                          delta + dimc, rho_part, apply ? 1 : 0, apply_scale() + dimc);
+      rho_pt_n = ts.ntiles;
+    }
     GB_LAUNCH(ctx);
     if (sums) {
-      k_sum_partials<<<1, 1024, 0, st>>>(rho_part, ts.ntiles, scalars, 1);
+      k_sum_partials<<<1, 1024, 0, st>>>(rho_part, rho_pt_n, scalars, 1);
       GB_LAUNCH(ctx);
       k_sum_partials<<<1, 1024, 0, st>>>(rho_part + ts.ntiles, ncamblocks, scalars, 2);
       GB_LAUNCH(ctx);
@@ -1198,7 +1232,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     }
     GB_LAUNCH(ctx);
     if (with_rho && !solved_full) { // cost and both rho sums of the Schur path in one launch
-      k_sum_partials3<<<3, 1024, 0, st>>>(SumJob{cost_part, ts.ntiles, 0}, SumJob{rho_part, ts.ntiles, 1},
+      k_sum_partials3<<<3, 1024, 0, st>>>(SumJob{cost_part, ts.ntiles, 0}, SumJob{rho_part, rho_pt_n, 1},
                                           SumJob{rho_part + ts.ntiles, ncamblocks, 2}, scalars);
     } else {
       k_sum_partials<<<1, 1024, 0, st>>>(cost_part, ts.ntiles, scalars, 0);
@@ -1628,6 +1662,7 @@ template <typename T, typename S> struct Problem : ProblemBase {
     if (!linearized) GB_TRY(enqueue_linearize());
     if (stage >= 2 && !prepared) GB_TRY(enqueue_prepare());
     if (stage == 2 || stage == 3 || stage == 5 || stage == 6) {
+      tk_iters = 0; // x comes from the initialisation below, not from a solve: the Jacobian-streaming back-substitution
       // a defined vector in xs / x: one PCG initialisation
       const int gridc = (ts.Nc + PCG_CAMS - 1) / PCG_CAMS;
       k_pcg_init<T><<<gridc, 288, 0, st>>>(ts.Nc, bS, Minv, scale, x, r, z, pv, xs, rz_part);

@@ -111,6 +111,10 @@ struct DevStruct {
   const int32_t *hv_pt, *hv_ptr; // [nheavy] the points, [nheavy+1] their fragment ranges
   void *frag_part;               // [nfrag][9] of T: per-fragment sums (C | g in k_linearize; point part of the full-system product)
   void *frag_t;                  // [nfrag][3] of T: sum_o Jp^T Jc x_c over ALL observations of the fragment's point (k_frag_dots)
+  // per-iteration point sums of k_pcg_solve kept for the back-substitution (k_backsubst_points): tk[k][Np][3] of T holds
+  // t_p(p_k) = sum_o Jp^T Jc (D p_k)_c of PCG iteration k, tk_alpha[k] its step length (0: not applied); tk_cap = 0: off
+  void *tk, *tk_alpha;
+  int32_t tk_cap, pad4;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -949,7 +953,8 @@ template <typename T, typename S, int NW = 2> struct SchurSmem2 {
 template <typename T, typename S, bool FULL, int NW = 2, typename Refill>
 __device__ __forceinline__ void product_tile(int worker, int t, const typename V2<S>::type *Js, const unsigned char *rec,
                                              const T *Ws, const T *xl, T *acc, T *sv, T *sw, T *__restrict__ out_p,
-                                             const DevStruct &ds, Refill &&refill) {
+                                             const DevStruct &ds, T *tk_cur /*[Np][3]: this PCG iteration's point sums are kept, or null*/,
+                                             Refill &&refill) {
   using S2 = typename V2<S>::type;
   T *sv3 = sv; // point-order staging: dead before the camera staging is written
   const TileMeta tm = *reinterpret_cast<const TileMeta *>(rec + REC_META);
@@ -1003,7 +1008,11 @@ __device__ __forceinline__ void product_tile(int worker, int t, const typename V
       } else {
         // (fragment of a long track: the sum over ALL observations of the point, formed before the product - k_frag_dots /
         // phase H of k_pcg_solve)
-        sw[item] = tm.frag ? __ldcg(reinterpret_cast<const T *>(ds.frag_t) + (int64_t)((tm.frag & FRAG_MASK) - 1) * 3 + k) : a;
+        const T tv = tm.frag ? __ldcg(reinterpret_cast<const T *>(ds.frag_t) + (int64_t)((tm.frag & FRAG_MASK) - 1) * 3 + k) : a;
+        sw[item] = tv;
+        // keep t_p(p_k) for the back-substitution: x = sum_k alpha_k p_k, so t_p(x) = sum_k alpha_k t_p(p_k) and the
+        // back-substitution need not stream the Jacobians again (k_backsubst_points)
+        if (tk_cur != nullptr && (!tm.frag || (tm.frag & FRAG_FIRST))) tk_cur[(int64_t)tm.p0 * 3 + item] = tv;
       }
     }
   }
@@ -1111,7 +1120,7 @@ k_schur_product2(DevStruct ds, const typename V2<S>::type *__restrict__ J, const
       const S2 *Js = reinterpret_cast<const S2 *>(smem + (i & 1) * SM::J_BYTES);
       const unsigned char *rec = smem + SM::META_OFF + (i & 3) * SM::META_BYTES;
       const T *Ws = reinterpret_cast<const T *>(rec + REC_BYTES);
-      product_tile<T, S, FULL>(worker, t, Js, rec, Ws, xl, acc, sv, sw, out_p, ds, [&](int next_p0, int next_np) {
+      product_tile<T, S, FULL>(worker, t, Js, rec, Ws, xl, acc, sv, sw, out_p, ds, (T *)nullptr, [&](int next_p0, int next_np) {
         if (i + 2 < ntl) {
           fence_proxy_async();
           product_issue<T, S>(smem, bars, ds, J, W, tile0 + i + 2, i + 2, next_p0, next_np, pol);
@@ -1272,6 +1281,53 @@ k_backsubst_tiles(DevStruct ds, const typename V2<S>::type *__restrict__ J, cons
   }
   const double tot = block_sum<double>(rho, shd);
   if (t == 0) rho_part[tile] = tot;
+}
+
+// K5a': the same back-substitution WITHOUT the Jacobians.  The PCG solve kernel left t_p(p_k) of every iteration k it
+// executed (DevStruct::tk) and the step lengths alpha_k (0 for an iterate that was rejected or never applied); the solution
+// is x = sum_k alpha_k p_k, so t_p(x) = sum_k alpha_k t_p(p_k): one thread per point reads k_max x 3 values instead of the
+// kernel above streaming 24 Jacobian values per observation (Venice FP64: 1.16 GB -> 0.33 GB per step, 236 -> ~70 us).
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_backsubst_points(DevStruct ds, int kmax, const T *__restrict__ W, const T *__restrict__ h, const T *__restrict__ scale_p,
+                   const T *__restrict__ b_p, T mu, T *__restrict__ pts, T *__restrict__ pts_bak, T *__restrict__ delta_p,
+                   double *__restrict__ rho_part /*[gridDim.x]*/, int apply, const T *__restrict__ scale_apply) {
+  __shared__ double shd[32];
+  __shared__ T al[32];
+  if (threadIdx.x < 32) al[threadIdx.x] = (int)threadIdx.x < kmax ? reinterpret_cast<const T *>(ds.tk_alpha)[threadIdx.x] : T(0);
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  double rho = 0.0;
+  if (p < ds.Np) {
+    T t0 = T(0), t1 = T(0), t2 = T(0);
+    const T *tk = reinterpret_cast<const T *>(ds.tk) + 3 * (int64_t)p;
+    for (int k = 0; k < kmax; k++) {
+      const T a = al[k];
+      if (a == T(0)) continue; // (uniform across the block)
+      const T *tp = tk + (int64_t)k * ds.Np * 3;
+      t0 += a * tp[0];
+      t1 += a * tp[1];
+      t2 += a * tp[2];
+    }
+    const T *w = W + (int64_t)p * WST<T>::value;
+    const T wv[3] = {w[0] * t0 + w[1] * t1 + w[2] * t2, w[1] * t0 + w[3] * t1 + w[4] * t2,
+                     w[2] * t0 + w[4] * t1 + w[5] * t2};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const int64_t i = 3 * (int64_t)p + k;
+      const T s = scale_p[i];
+      const T xt = s != T(0) ? (h[HST * (int64_t)p + k] - wv[k]) / s : T(0); // scaled-space step of the point (0: fixed)
+      delta_p[i] = xt;
+      rho += (double)(xt * (mu * xt + b_p[i]));
+      if (apply) {
+        const T old = pts[i];
+        pts_bak[i] = old;
+        pts[i] = old + xt * scale_apply[i];
+      }
+    }
+  }
+  const double tot = block_sum<double>(rho, shd);
+  if (threadIdx.x == 0) rho_part[blockIdx.x] = tot;
 }
 
 // ---------------------------------------------------------------------------------------------

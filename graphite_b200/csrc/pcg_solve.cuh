@@ -112,7 +112,10 @@ k_pcg_solve(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *_
     mbar_fence_init();
     fence_proxy_async();
   }
-  if (leader) *work = 0u;
+  if (leader) {
+    *work = 0u;
+    for (int i = 0; i < ds.tk_cap; i++) reinterpret_cast<T *>(ds.tk_alpha)[i] = T(0); // step lengths of the iterates applied to x
+  }
   // Work items (super-tiles) come from an atomic counter that is never reset during the solve: every CTA ends an
   // iteration with exactly ONE failing grab, so iteration k hands out the values k * (nst + G) ... .  Item number n of this
   // CTA (over the whole solve) has its record in buffer n % 3, on that buffer's mbarrier with phase parity (n / 3) & 1.
@@ -180,6 +183,8 @@ k_pcg_solve(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *_
     if (timing && leader) timing[k * SOLVE_STAMPS + 0] = global_timer_ns();
     const T *p_old = pbuf + (size_t)(k & 1) * dimc;
     T *p_new = pbuf + (size_t)((k + 1) & 1) * dimc;
+    const int keep_k = k < ds.tk_cap ? k : -1; // this iteration's point sums are kept for k_backsubst_points
+    T *tk_cur = keep_k >= 0 ? reinterpret_cast<T *>(ds.tk) + (size_t)k * 3 * (size_t)ds.Np : nullptr;
     // ---- phase P: p = beta p + z for the owned cameras (ops::axpy_async(p, beta, p, z)), sum p dterm p --------------
     {
       T pdp_w = T(0);
@@ -251,7 +256,7 @@ k_pcg_solve(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *_
           const S2 *Js = reinterpret_cast<const S2 *>(smem + (i % NW) * SM::J_BYTES);
           const unsigned char *rec = smem + SM::META_OFF + (i % NMETA) * SM::META_BYTES;
           const T *Ws = reinterpret_cast<const T *>(rec + REC_BYTES);
-          product_tile<T, S, false, NW>(worker, t, Js, rec, Ws, xl, acc, sv, sw, (T *)nullptr, ds, [&](int next_p0, int next_np) {
+          product_tile<T, S, false, NW>(worker, t, Js, rec, Ws, xl, acc, sv, sw, (T *)nullptr, ds, tk_cur, [&](int next_p0, int next_np) {
             const int j = i + NW;
             if (j <= my_issued) return;
             if (j < ie) {
@@ -383,6 +388,7 @@ k_pcg_solve(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *_
     const T denom = dot + pdp;
     if (denom == T(0) || isnan(denom)) { s.done = 1; s.reason = 4; s.denom = denom; break; } // pcg_schur.hpp:120-122
     const T alpha = s.rz / denom;
+    if (leader && keep_k >= 0) reinterpret_cast<T *>(ds.tk_alpha)[k] = alpha;
 
     // x += alpha p ; r -= alpha Ap ; z = M^-1 r ; r.z
     T rz_w = T(0);
@@ -429,6 +435,7 @@ k_pcg_solve(DevStruct ds, const typename V2<S>::type *__restrict__ J, const T *_
     if (fabs(rzn) > ratio * s.rz0 || isnan(rzn)) { // pcg_schur.hpp:144-148: restore x, stop
       for (int c = c_begin + warp; c < c_end; c += SOLVE_WARPS)
         if (own) x[c * 9 + k9] = xbak[c * 9 + k9];
+      if (leader && keep_k >= 0) reinterpret_cast<T *>(ds.tk_alpha)[k] = T(0); // the rejected iterate is not part of x
       s.done = 1; s.reason = 2; s.rz = rzn;
       k++;
       break;
