@@ -1,6 +1,7 @@
 """compute-sanitizer target: a few LM iterations of small problems through every kernel of the library - the BAL path (FP64
 two workers, FP32 three workers, both solvers, explicit and direct Schur, Huber + precision matrices, fixed vertices, device
-structure build) and the generic factor-graph path (pose graph with the user kernels of tests/user_factor)."""
+structure build, long tracks cut into fragment tiles, the Jacobian-free and the Jacobian-streaming back-substitution) and
+the generic factor-graph path (pose graph with the user kernels of tests/user_factor)."""
 import ctypes
 import os
 import subprocess
@@ -35,6 +36,22 @@ P32 = binding.problem_from_bal(ctx, prob, "f32-f32")
 t7, _ = P32.lm(iterations=3)
 P32.close()
 print("bal ok", t[-1, 1], t2[-1, 1], t3[-1, 1], v.shape, t4[-1, 1], t5[-1, 1], t6[-1, 1], t7[-1, 1])
+
+# long tracks: fragment tiles, phase H of k_pcg_solve, k_frag_sum / k_frag_dots; a 20-iteration solve takes the
+# Jacobian-streaming back-substitution, the 10-iteration ones the kept point sums
+lt = synthetic.make_named("long-tracks")
+for kw in ({}, dict(tile_size=24, slot_cap=40)):
+    PL = binding.problem_from_bal(ctx, lt, "f64-f64", **kw)
+    l1, _ = PL.lm(iterations=2)
+    l2, _ = PL.lm(iterations=1, pcg_iterations=20)
+    l3, _ = PL.lm(iterations=1, solver="pcg")
+    l4, _ = PL.lm(iterations=1, schur_mode="explicit")
+    PL.close()
+    print("long tracks ok", kw, l1[-1, 1], l2[-1, 1], l3[-1, 1], l4[-1, 1])
+PL = binding.problem_from_bal(ctx, lt, "f32-f32")
+l5, _ = PL.lm(iterations=2)
+PL.close()
+print("long tracks f32 ok", l5[-1, 1])
 
 # generic path
 src = os.path.join(ROOT, "tests", "user_factor", "graph_factors.cu")
