@@ -386,6 +386,8 @@ def main():
     # after the grid barrier that ends it) is listed next to it.
     peak, peak_kind = load_peaks()
     prod_bytes, survey_k4 = algorithmic_bytes(nc, local.n_pts, info["n_obs"], info["n_partial_rows"], info["n_tiles"], sT, sS)
+    if args.solver == "pcg-schur":  # (the protocol's 10 PCG iterations: within the 16 the library keeps point sums for)
+        prod_bytes += 3 * local.n_pts * sT  # the point sums t_p(p_k) every iteration leaves for the Jacobian-free back-substitution
     k_total = max(int(res["pcg_iterations_total"]), 1)
     pcg_seconds = max(res["seconds_pcg"], 1e-12)
     launches_timed = max(steps_done, 1)
@@ -517,8 +519,19 @@ def main():
     acc_frac = res["accepted"] / max(steps_done, 1)
     step_bytes = lm_iteration_bytes(nc, local.n_pts, info["n_obs"], sT, sS, k_avg, acc_frac)
     step_gbps = step_bytes / (seconds / max(steps_done, 1)) / 1e9
+    # the same with the bytes THIS layout has to move (J stored as 24 values per observation instead of
+    # the 27 of the E blocks, Jacobian-free back-substitution from the kept point sums): the stricter of the two fractions
+    m_, np_, R_, nt_ = info["n_obs"], local.n_pts, info["n_partial_rows"], info["n_tiles"]
+    nch_ = info.get("n_camera_chunks", 0)
+    lay_lin = m_ * (2 * sT + 4) + 3 * np_ * sT + m_ * (24 * sS + 2 * sT) + 9 * np_ * sT + 18 * R_ * sT
+    lay_prep = np_ * 24 * sT + m_ * (24 * sS + 8) + 9 * m_ * sT + 54 * nch_ * sT
+    lay_back = (3 * k_avg + 20) * np_ * sT if k_avg <= 16 else m_ * (24 * sS + 8) + 20 * np_ * sT
+    lay_cost = m_ * (2 * sT + 8)
+    layout_bytes = acc_frac * lay_lin + lay_prep + k_avg * prod_bytes + lay_back + lay_cost
+    layout_gbps = layout_bytes / (seconds / max(steps_done, 1)) / 1e9
     lm_roofline = {"bytes_per_step": step_bytes, "pcg_iterations_per_step": k_avg, "accepted_fraction": acc_frac,
                    "achieved": step_gbps, "peak": peak, "unit": "GB/s", "frac": step_gbps / peak,
+                   "layout_bytes_per_step": layout_bytes, "layout_achieved": layout_gbps, "layout_frac": layout_gbps / peak,
                    "note": "SURVEY 8(d) algorithmic bytes per LM iteration (implicit Schur), per rank, with the executed PCG "
                            "iterations; at 10 PCG iterations and every step accepted the same formula gives 15.8 GB (Venice FP64)"}
     if args.solver != "pcg-schur":
