@@ -31,12 +31,15 @@
 //   k_pcg_solve (pcg_solve.cuh)          the whole PCG solve in ONE persistent cooperative launch: per iteration the
 //                                        matrix-free (B - E W E^T) p on the TMA pipeline (product_tile below), row sums,
 //                                        multi-GPU exchange (p2p.cuh), dots and updates, two grid barriers
-//   k_cam_step, k_backsubst_tiles        step of the cameras, back-substitution and step of the points, rho partials
+//   k_cam_step, k_backsubst_points       step of the cameras; back-substitution and step of the points from the point sums the
+//                                        solve kernel kept (no pass over J); k_backsubst_tiles streams J instead (long solves,
+//                                        explicit / direct Schur); rho partials
 //   k_cost_tiles, k_sum_partials3        cost at the trial point, cost + rho sums; k_store_host hands them to the host
 //   k_copy                               restore after a rejected step
 // Other entry points: k_schur_product2 (one product per launch: exports, <FULL> for the full-system PCG solver, NCCL
-// fallback) + k_cam_reduce_spmv, k_pcg_init*, k_pcg_update (NCCL fallback), k_full_* (full-system PCG solver),
-// k_hessian_export, k_scatter_slots, k_p2p_push / k_p2p_sum (generic exchange).
+// fallback) + k_cam_reduce_spmv, k_pcg_init*, k_pcg_update (NCCL fallback), k_full_* (full-system PCG solver: a
+// device-resident loop, scalars and stop rules in a FullState), k_frag_sum / k_frag_dots (second level of the per-point sums
+// of long tracks), k_hessian_export, k_scatter_slots, k_p2p_push / k_p2p_sum (generic exchange).
 #pragma once
 #include <cfloat>
 #include <cstdint>

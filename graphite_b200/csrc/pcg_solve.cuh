@@ -23,6 +23,9 @@
 //     phase U  x += alpha p, r -= alpha Ap, z = M^-1 r, partial of r.z
 //     barrier B
 //              rz_new, rejection / convergence tests, beta           (pcg_schur.hpp:144-163)
+//   With long tracks (points cut into fragment tiles, structure.hpp) a phase H precedes the product: one warp per such point
+//   forms t_p over all its observations, then one more grid barrier.  Solves of <= 16 iterations also keep every point sum
+//   t_p(p_k) and step length alpha_k: the back-substitution then needs no pass over the Jacobians (k_backsubst_points).
 //   All CTAs (and all ranks) carry the PCG scalars redundantly from bit-identical sums, so control flow is uniform
 //   with no broadcast.  Every sum has a fixed order: runs are bit-reproducible whatever the work counter hands out.
 #pragma once
