@@ -1022,6 +1022,11 @@ template <typename T, typename S> struct Problem : ProblemBase {
   double xs_kstar = -1.0;
   int choose_schur_mode(const gb_pcg_options *o) {
     if (o->schur_mode == GB_SCHUR_EXPLICIT || o->schur_mode == GB_SCHUR_IMPLICIT) return o->schur_mode;
+    // Several ranks: every rank must run the SAME form (the two solve kernels exchange differently), and the rule below
+    // looks at this rank's share only - on small shares ranks disagreed (8 ranks on a 7 k-observation problem: some chose
+    // the stored S, the others waited for their exchange for ever).  The stored S does not shrink with the number of ranks
+    // (points shard, camera pairs do not), so auto means matrix-free there; explicit stays available on request.
+    if (ctx->nranks > 1) return GB_SCHUR_IMPLICIT;
     if (xs_kstar < 0.0) {
       double tuples = 0.0;
       for (int32_t p = 0; p < hs.Np; p++) {

@@ -217,7 +217,9 @@ typedef enum { GB_SOLVER_PCG_SCHUR = 0, GB_SOLVER_PCG_FULL = 1, GB_SOLVER_DIRECT
  *   GB_SCHUR_IMPLICIT  matrix-free (B - E W E^T) p per iteration: one streaming pass over the Jacobians
  *   GB_SCHUR_EXPLICIT  S built once per solve (the reference's form, schur.hpp:227-235, ops/schur.hpp:154-188), then a
  *                      block-sparse S p per iteration (schur.hpp:347-393)
- *   GB_SCHUR_AUTO      chosen per problem size and iteration count by the measured rule of DESIGN.md section 3
+ *   GB_SCHUR_AUTO      chosen per problem size and iteration count by the measured rule of DESIGN.md section 3; with
+ *                      several ranks always matrix-free (all ranks must run the same form, and S does not shrink with
+ *                      the number of ranks)
  * All three give the same iterates up to rounding. */
 typedef enum { GB_SCHUR_AUTO = 0, GB_SCHUR_IMPLICIT = 1, GB_SCHUR_EXPLICIT = 2 } gb_schur_mode;
 
