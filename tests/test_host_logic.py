@@ -176,6 +176,20 @@ def test_point_partition_covers_everything(built):
             assert p.n_cams == prob.n_cams and p.pt_idx.min() == 0 and p.pt_idx.max() == p.n_pts - 1
 
 
+def test_point_partition_keeps_long_tracks_whole(built):
+    """Ranks own contiguous point ranges: a long track (cut into fragment tiles inside its rank) is never split over ranks."""
+    prob = synthetic.make_named("long-tracks")
+    track = np.bincount(prob.pt_idx)
+    for n in (2, 4, 8):
+        parts = [partition_by_point(prob, n, r) for r in range(n)]
+        assert sum(p.n_obs for p in parts) == prob.n_obs and sum(p.n_pts for p in parts) == prob.n_pts
+        local_tracks = np.concatenate([np.bincount(p.pt_idx) for p in parts])
+        assert np.array_equal(local_tracks, track)
+        for p in parts:  # a rank's share builds (cameras without a local observation are legal in a partition)
+            ci, pi = p.cam_idx, p.pt_idx
+            assert pi.min() == 0 and pi.max() == p.n_pts - 1 and np.all(np.diff(pi.astype(np.int64) * p.n_cams + ci) > 0)
+
+
 WORKER = r'''
 import os, sys
 sys.path.insert(0, sys.argv[1])

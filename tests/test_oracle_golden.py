@@ -105,6 +105,45 @@ def test_fp64_trajectory_matches_reference(built, case, rtol_iter, rtol_final):
     assert abs(traj[-1, 1] - g["final_chi2"]) <= rtol_final * g["final_chi2"]
 
 
+def test_long_tracks_fixture_pins_the_oracle(built):
+    """The long-track problem (tracks of 400 / 260 / 193 / 300 observations: a point seen by more cameras than one tile of the
+    library holds) as the unmodified reference ran it on a B200: first linearisation (structure bit-exact, b, scales, H, b_S,
+    S) and the trajectories of both solvers against the oracle."""
+    prob = synthetic.make_named("long-tracks")
+    z = golden_npz("long-tracks__pcg-schur__FP64-FP64.npz")
+    g = golden_json("long-tracks__pcg-schur__FP64-FP64.json")
+    assert g["shape"] == list(prob.shape()) and np.bincount(prob.pt_idx).max() == 400
+    key = prob.pt_idx.astype(np.int64) * prob.n_cams + prob.cam_idx
+    assert np.all(np.diff(key) > 0), "sorted by (point, camera), no duplicates"
+    o = Oracle(prob)
+    chi2, sc, b = o.linearize()
+    assert abs(chi2 - g["initial_chi2_17g"]) <= 1e-13 * chi2
+    np.testing.assert_allclose(sc, z["scales"], rtol=1e-12)
+    np.testing.assert_allclose(b, z["b"], rtol=0, atol=1e-12 * np.abs(z["b"]).max())
+    cp, ri, off = o.hessian_structure()
+    assert np.array_equal(cp, z["H_colptr"]) and np.array_equal(ri, z["H_rowidx"]) and np.array_equal(off, z["H_offsets"])
+    hv = o.hessian_values()
+    nc = prob.n_cams
+    np.testing.assert_allclose(hv[: 81 * nc], z["H_cam_blocks"], rtol=0, atol=1e-12 * np.abs(z["H_cam_blocks"]).max())
+    assert abs(hv.sum() - z["H_values_sum"][0]) <= 1e-12 * z["H_values_sum"][1]
+    S, bS = o.schur(g["lambda"])
+    np.testing.assert_allclose(bS, z["bS"], rtol=0, atol=1e-11 * np.abs(z["bS"]).max())
+    ptr, idx, val = z["Scsc_ptr"], z["Scsc_idx"], z["Scsc_val"]
+    n = 9 * nc
+    Sd = np.zeros((n, n))
+    for c in range(n):
+        Sd[idx[ptr[c]:ptr[c + 1]], c] = val[ptr[c]:ptr[c + 1]]
+    np.testing.assert_allclose(np.triu(S), Sd, rtol=0, atol=1e-11 * np.abs(Sd).max())
+    for solver, so in (("pcg-schur", 0), ("pcg", 2)):
+        gs = golden_json(f"long-tracks__{solver}__FP64-FP64.json")
+        init, cur, lam = table(gs)
+        traj = Oracle(prob).lm(default_options(iterations=len(cur), solver=so))
+        rel = np.abs(traj[:, 1] - cur) / cur
+        assert rel.max() <= 1e-9, (solver, rel)
+        assert np.array_equal(traj[:, 0] == traj[:, 1], init == cur)
+        assert abs(traj[-1, 1] - gs["final_chi2"]) <= 1e-6 * gs["final_chi2"]
+
+
 def test_reference_run_to_run_spread_is_below_tolerance():
     a = golden_json("ladybug-49__pcg-schur__FP64-FP64.json")
     b = golden_json("ladybug-49__pcg-schur__FP64-FP64.run2.json")
