@@ -144,6 +144,25 @@ def test_long_tracks_fixture_pins_the_oracle(built):
         assert abs(traj[-1, 1] - gs["final_chi2"]) <= 1e-6 * gs["final_chi2"]
 
 
+def test_long_tracks_fixture_fp32_sensitivity(built):
+    """FP32 on the long-track fixture is dominated by rounding noise (a small, weakly constrained problem: 14 observations
+    per camera, landmarks at depth 300): this independent FP32 implementation is 1.3e-3 away from the reference's FP32 run at
+    iteration 1 and 1e-4 later, and its own runs with 1 and 16 threads (summation order only) differ by 5e-4 of the initial
+    cost.  The fixture's FP32 bound - here and for the CUDA path (tests/test_gpu_parity.py) - is therefore 1e-2 per iteration
+    and 1e-3 on the final cost; its FP64, mixed and bf16 runs are held to the usual bounds."""
+    prob = synthetic.make_named("long-tracks")
+    g = golden_json("long-tracks__pcg-schur__FP32-FP32.json")
+    init, cur, lam = table(g)
+    traj = Oracle(prob, "f32", threads=4).lm(default_options(iterations=len(cur), threads=4))  # fixed summation order
+    n = min(len(traj), len(cur))
+    same = (traj[:n, 1] < traj[:n, 0]) == (cur[:n] < init[:n])
+    first_flip = n if same.all() else int(np.argmin(same))
+    assert first_flip >= 10, first_flip
+    rel = np.abs(traj[:first_flip, 1] - cur[:first_flip]) / cur[:first_flip]
+    assert rel.max() <= 1e-2, rel
+    assert traj[-1, 1] <= g["final_chi2"] * (1 + 1e-3)
+
+
 def test_reference_run_to_run_spread_is_below_tolerance():
     a = golden_json("ladybug-49__pcg-schur__FP64-FP64.json")
     b = golden_json("ladybug-49__pcg-schur__FP64-FP64.run2.json")
