@@ -318,8 +318,9 @@ def test_long_tracks_are_cut_into_fragment_tiles():
     s = binding.host_structure(cam2, pt2, nc, npts)
     assert s["info"]["max_track"] == 192 and len(s["frag_tile"]) == 0
 
-    for kw in ({}, dict(tile_size=24, slot_cap=40), dict(tile_size=64)):
-        prob = synthetic.make_named("long-tracks")
+    many = synthetic.make_long_tracks(n_cams=420, n_pts=3000, n_obs=20000, tracks=tuple(200 + (i * 37) % 221 for i in range(300)), seed=3)
+    for kw, prob in (({}, synthetic.make_named("long-tracks")), (dict(tile_size=24, slot_cap=40), synthetic.make_named("long-tracks")),
+                     (dict(tile_size=64), synthetic.make_named("long-tracks")), ({}, many)):
         s = binding.host_structure(prob.cam_idx, prob.pt_idx, prob.n_cams, prob.n_pts, **kw)
         cap = min(kw.get("tile_size", 256), kw.get("slot_cap", 192))
         to, tp, tm, pptr = s["tile_obs"], s["tile_pt"], s["tmeta"], s["pptr"]
