@@ -353,3 +353,89 @@ def test_long_tracks_are_cut_into_fragment_tiles():
         for sidx in range(len(st_tile) - 1):
             rows = row_cam[st_row[sidx]:st_row[sidx + 1]]
             assert np.array_equal(np.unique(prob.cam_idx[to[st_tile[sidx]]:to[st_tile[sidx + 1]]]), rows)
+
+def _check_structure(cam, pt, nc, npts, s, tile_size, slot_cap):
+    """Invariants the kernels rely on (csrc/structure.hpp): tiles and fragments partition the sorted observations, slots are a
+    camera-sorted permutation of the tile, segment / point tables describe them, super-tile rows are its distinct cameras."""
+    fill, capv = tile_size or 256, slot_cap or 192
+    cap = min(fill, capv)
+    to, tp, tm, pptr = s["tile_obs"], s["tile_pt"], s["tmeta"], s["pptr"]
+    m, nt = len(cam), len(to) - 1
+    assert np.array_equal(s["cam_idx"], cam) and np.array_equal(s["pt_idx"], pt)
+    assert to[0] == 0 and to[-1] == m and np.all(np.diff(to) > 0) and np.diff(to).max() <= fill
+    track = np.diff(pptr)
+    heavy = np.flatnonzero(track > cap)
+    assert np.array_equal(s["hv_pt"], heavy) and s["info"]["max_track"] == track.max()
+    frag = np.zeros(nt, bool)
+    frag[s["frag_tile"]] = True
+    assert len(s["hv_ptr"]) == len(heavy) + 1 and s["hv_ptr"][-1] == len(s["frag_tile"])
+    for h, p in enumerate(heavy):
+        tiles = s["frag_tile"][s["hv_ptr"][h]:s["hv_ptr"][h + 1]]
+        assert np.array_equal(tiles, np.arange(tiles[0], tiles[-1] + 1))
+        assert to[tiles[0]] == pptr[p] and to[tiles[-1] + 1] == pptr[p + 1] and len(tiles) == -(-track[p] // cap)
+        for j, k in enumerate(tiles):
+            assert tm[k][0] == p and tm[k][2] == 1 and tm[k][7] & 0x3fffffff == s["hv_ptr"][h] + j + 1 and bool(tm[k][7] >> 30) == (j == 0)
+    slot = s["slot_of_obs"]
+    assert sorted(slot.tolist()) == sorted(np.concatenate([k * 256 + np.arange(to[k + 1] - to[k]) for k in range(nt)]).tolist())
+    st_tile, st_row, row_cam = s["st_tile"], s["st_row"], s["row_cam"]
+    assert st_tile[0] == 0 and st_tile[-1] == nt and np.all(np.diff(st_tile) > 0) and np.diff(st_row).max() <= capv
+    covered = 0
+    for sidx in range(len(st_tile) - 1):
+        rows = row_cam[st_row[sidx]:st_row[sidx + 1]]
+        assert np.array_equal(np.unique(cam[to[st_tile[sidx]]:to[st_tile[sidx + 1]]]), rows)
+        for k in range(st_tile[sidx], st_tile[sidx + 1]):
+            p0, n, npt, ns, seg_off, pt_off, o0k, code = tm[k]
+            assert (n, o0k) == (to[k + 1] - to[k], to[k]) and 1 <= npt <= 128 and (code != 0) == frag[k]
+            covered += n
+            om = s["ometa"][k * 256:(k + 1) * 256]
+            cslot, prank, ptl = om >> 16, (om >> 8) & 0xff, om & 0xff
+            assert sorted(prank.tolist()) == list(range(256))
+            obs_of_slot = to[k] + prank[:n].astype(int)
+            assert np.array_equal(slot[obs_of_slot], k * 256 + np.arange(n))
+            cams_sorted = cam[obs_of_slot]
+            assert np.all(np.diff(cams_sorted) >= 0) and np.array_equal(rows[cslot[:n]], cams_sorted)
+            assert np.array_equal(ptl[:n] + p0, pt[obs_of_slot])
+            seg = s["seg_tab"][seg_off:seg_off + ns + 1]
+            heads = np.flatnonzero(np.diff(cams_sorted, prepend=-1) != 0)
+            assert ns == len(heads) and np.array_equal(seg[:ns] >> 16, heads) and seg[ns] >> 16 == n
+            assert np.array_equal(rows[seg[:ns] & 0xffff], cams_sorted[heads])
+            ptab = s["pt_tab"][pt_off:pt_off + npt + 1]
+            assert np.array_equal(ptab, np.clip(pptr[p0:p0 + npt + 1] - to[k], 0, n))
+            if not frag[k]:
+                assert to[k] == pptr[p0] and to[k + 1] == pptr[p0 + npt], "an ordinary tile holds whole points"
+    assert covered == m
+    # camera -> partial rows: every row once, ascending super-tile order inside a camera
+    ptr, lst = s["cam_row_ptr"], s["cam_row_list"]
+    assert ptr[0] == 0 and ptr[-1] == len(row_cam) and sorted(lst.tolist()) == list(range(len(row_cam)))
+    for c in range(nc):
+        mine = lst[ptr[c]:ptr[c + 1]]
+        assert np.all(row_cam[mine] == c) and np.all(np.diff(mine) > 0)
+
+
+def test_structure_invariants_on_random_problems(built):
+    """Random small problems with random track lengths (many of them longer than the tile / slot cap in force) in random
+    tilings: the cut logic (tiles of whole points, fragments of long tracks, super-tiles) keeps every invariant."""
+    rng = np.random.default_rng(2026)
+    n_heavy_cases = 0
+    for trial in range(60):
+        nc = int(rng.integers(3, 70))
+        npts = int(rng.integers(2, 150))
+        tile_size = int(rng.choice([0, 8, 13, 32, 100]))
+        slot_cap = int(rng.choice([0, 4, 7, 16, 50]))
+        cams, pts = [], []
+        for p in range(npts):
+            kind = rng.random()
+            t = nc if kind < 0.08 else int(rng.integers(1, max(2, min(nc, 6)) + 1)) if kind < 0.8 else int(rng.integers(1, nc + 1))
+            cams.append(np.sort(rng.choice(nc, size=t, replace=False)))
+            pts.append(np.full(t, p))
+        cam, pt = np.concatenate(cams).astype(np.int32), np.concatenate(pts).astype(np.int32)
+        missing = np.setdiff1d(np.arange(nc), cam)  # every camera must be observed: give the missing ones to the last point
+        if missing.size:
+            keep = pt != npts - 1
+            last = np.union1d(cam[~keep], missing)
+            cam = np.concatenate([cam[keep], last]).astype(np.int32)
+            pt = np.concatenate([pt[keep], np.full(last.size, npts - 1)]).astype(np.int32)
+        s = binding.host_structure(cam, pt, nc, npts, tile_size, slot_cap)
+        _check_structure(cam, pt, nc, npts, s, tile_size, slot_cap)
+        n_heavy_cases += len(s["hv_pt"]) > 0
+    assert n_heavy_cases >= 20
