@@ -109,6 +109,25 @@ def run_case(name, prob, solver, precision, iterations, dump=False, lam=1e-4, ti
     return rec
 
 
+def reduce_schur(path, n_cams):
+    """Keep a fixture small when S is nearly dense (long tracks connect almost every camera pair: 7 M scalars = 55 MB):
+    replace the scalar upper CSC of S by what the tests compare - y = S x for the seeded vector the tests use, the diagonal
+    blocks, and checksums (sum, sum of magnitudes, count) of the upper triangle.  `python oracle/make_golden.py --reduce F.npz N`."""
+    z = dict(np.load(path))
+    ptr, idx, val = z.pop("Scsc_ptr"), z.pop("Scsc_idx"), z.pop("Scsc_val")
+    n = 9 * n_cams
+    Sd = np.zeros((n, n))
+    for c in range(n):
+        Sd[idx[ptr[c]:ptr[c + 1]], c] = val[ptr[c]:ptr[c + 1]]
+    Sfull = Sd + np.triu(Sd, 1).T
+    x = np.random.default_rng(2).normal(size=n)
+    z["S_times_x"] = Sfull @ x
+    z["S_diag_blocks"] = np.stack([Sfull[9 * c:9 * c + 9, 9 * c:9 * c + 9] for c in range(n_cams)])
+    z["S_sum"] = np.array([val.sum(dtype=np.float64), np.abs(val).sum(dtype=np.float64), float(val.size)])
+    z["Scsc_ptr"] = ptr
+    np.savez_compressed(path, **z)
+
+
 def second_run(name, prob):
     """An extra FP64 run kept as *.run2.json: the reference's own run-to-run spread (float atomics)."""
     run_case(name, prob, "pcg-schur", "FP64-FP64", 50, timeout=6000)
@@ -159,6 +178,7 @@ def main(which):
     if "longtracks" in which:  # tracks longer than one tile of the library holds (400 / 260 / 193 / 300 cameras)
         p = synthetic.make_named("long-tracks")
         run_case("long-tracks", p, "pcg-schur", "FP64-FP64", 30, dump=True)
+        reduce_schur(os.path.join(OUT, "long-tracks__pcg-schur__FP64-FP64.npz"), p.n_cams)
         run_case("long-tracks", p, "pcg", "FP64-FP64", 30)
         run_case("long-tracks", p, "pcg-schur", "FP32-FP32", 30)
         run_case("long-tracks", p, "pcg", "FP64-FP32", 30)
@@ -192,4 +212,7 @@ def main(which):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1:] or ["fixture", "ladybug", "trafalgar"])
+    if len(sys.argv) == 4 and sys.argv[1] == "--reduce":
+        reduce_schur(sys.argv[2], int(sys.argv[3]))
+    else:
+        main(sys.argv[1:] or ["fixture", "ladybug", "trafalgar"])
